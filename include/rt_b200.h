@@ -1,0 +1,202 @@
+/* rt_b200.h — C ABI of librt_b200.so, the B200 (sm_100a) drop-in for the per-pixel ray hot
+ * path of Dark565/raytracer.js.
+ *
+ * What it replaces (paths relative to the reference tree):
+ *   Raytracer.trace_frame()            src/raytracer.ts:308-330   -> rt_render*
+ *   new Raytracer(config, otree, ...)  src/raytracer.ts:291-298   -> rt_create + rt_scene_upload
+ *   RaytracerConfig                    src/raytracer.ts:33-43     -> rt_params
+ *   Camera pose + CameraConfig         src/view/camera.ts:27-75   -> rt_camera
+ *   ExposureBuffer.pixels / set_color  src/view/exposure_buffer.ts:27,68-91 -> the rgb in/out buffer
+ *   EntityOtree (Octree<EntitySet,OctreeDim>) + Entity/Material/Texture/Substance objects
+ *                                      src/octree.ts:25-126, src/octree_entity.ts:32-49,
+ *                                      src/entities/..., src/material.ts:67-103, src/texture/...,
+ *                                      src/substance.ts:1-11      -> rt_scene_desc (flat SoA)
+ *
+ * The host keeps building the octree exactly as today (add_entity_to_octree,
+ * src/octree_entity.ts:174-188); a flattener walks it (DFS pre-order, children 0..7) and fills
+ * rt_scene_desc.  The binding a maintainer adds on the reference side (N-API addon + the
+ * GpuRaytracer TypeScript class) is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every array is caller-owned and COPIED during the
+ * call; every function returns an rt_status (0 = ok) and never aborts the process; the message of
+ * the last failure is rt_last_error(ctx) (ctx may be NULL for rt_create failures).  A ctx is not
+ * thread-safe; distinct ctxs are independent.  There is no CPU fallback: without a CUDA device
+ * rt_create fails with RT_ERR_CUDA.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+typedef struct rt_ctx rt_ctx;
+
+typedef enum rt_status {
+	RT_OK = 0,
+	RT_ERR_INVALID = 1,     /* bad argument / inconsistent scene description */
+	RT_ERR_CUDA = 2,        /* CUDA runtime failure (message has the CUDA error string) */
+	RT_ERR_NO_SCENE = 3,    /* rt_render before rt_scene_upload */
+	RT_ERR_UNSUPPORTED = 4, /* a feature the reference would accept but this path does not */
+	RT_ERR_BOUNDS = 5,      /* "x or y out of bounds": non-square frame with RT_CAM_REFERENCE_EXTENTS
+	                           (ExposureBuffer.check_bounds, src/view/exposure_buffer.ts:181-186) */
+	RT_ERR_TEXTURE = 6      /* 'Texture coordinates out of bounds' (src/texture/texture_image.ts:49-50) */
+} rt_status;
+
+/* Entity kinds: SphereEntity (src/entities/entity_sphere.ts), BoxEntity (src/entities/entity_box.ts) */
+#define RT_ENTITY_SPHERE 0u
+#define RT_ENTITY_BOX 1u
+/* ResponseType, src/material.ts:22-26 */
+#define RT_RESPONSE_REFLECTION 0u
+#define RT_RESPONSE_TRANSMISSION 1u
+#define RT_RESPONSE_BOTH 2u
+/* Texture kinds: SolidTexture (src/texture/texture_solid.ts), ImageTexture (src/texture/texture_image.ts) */
+#define RT_TEXTURE_SOLID 0u
+#define RT_TEXTURE_IMAGE 1u
+
+/* The flattened scene.  Node 0 is the octree root handed to `new Raytracer(...)`, which must also be
+ * the absolute root (tree.parent == undefined); nodes are numbered in DFS pre-order.  All reals are
+ * the reference's float64 values, unchanged. */
+typedef struct rt_scene_desc {
+	uint32_t struct_size; /* sizeof(rt_scene_desc), for ABI checking */
+
+	/* octree nodes: Octree.id = OctreeDim{pos,size} (src/octree_space.ts:30-33) */
+	uint32_t n_nodes;
+	const double* node_pos;        /* [n_nodes*3] */
+	const double* node_size;       /* [n_nodes]   */
+	const int32_t* node_child;     /* [n_nodes*8] child node index or -1 (Octree.get(n)) */
+	const int32_t* node_parent;    /* [n_nodes]   -1 for the root */
+	const int32_t* node_octant;    /* [n_nodes]   index_within_parent() (src/octree_space.ts:113-125), -1 root */
+	const uint32_t* node_list_off; /* [n_nodes+1] CSR offsets into list_entity */
+	uint32_t n_list;               /* node_list_off[n_nodes] */
+	const uint32_t* list_entity;   /* [n_list] entity ids; each node's run is EntitySet.set in insertion order */
+
+	/* entities; the id of an entity is its index here */
+	uint32_t n_entities;
+	const uint8_t* ent_type;       /* [n_entities] RT_ENTITY_* */
+	const double* ent_pos;         /* [n_entities*3] get_pos() */
+	const double* ent_extent;      /* [n_entities] get_diameter() | get_size() */
+	const int32_t* ent_material;   /* [n_entities] */
+	const int32_t* ent_texture;    /* [n_entities] */
+	const int32_t* ent_substance;  /* [n_entities] index or -1 for `undefined` (src/raytracer.ts:243-248) */
+
+	/* StaticMaterial fields, src/material.ts:73-81 */
+	uint32_t n_materials;
+	const uint8_t* mat_response;   /* RT_RESPONSE_* */
+	const uint8_t* mat_light;      /* light_source */
+	const uint8_t* mat_mirror;     /* mirror */
+	const double* mat_roughness;   /* roughness_index */
+
+	/* textures */
+	uint32_t n_textures;
+	const uint8_t* tex_kind;       /* RT_TEXTURE_* */
+	const double* tex_color;       /* [n_textures*4] SolidTexture.color | ImageTexture.fallback_color (rgba) */
+	const int32_t* tex_width;      /* image only */
+	const int32_t* tex_height;     /* image only */
+	const uint8_t* tex_loaded;     /* image only: 0 -> get_color answers the fallback colour */
+	const uint64_t* tex_texel_off; /* image only: first texel of this image in `texels` (in texels) */
+	uint64_t n_texels;
+	const uint8_t* texels;         /* [n_texels*3] RGB8 as decoded by load_image (value/255.0 on use) */
+
+	/* Substance.refractive_index, src/substance.ts:1-11 */
+	uint32_t n_substances;
+	const double* sub_refractive_index;
+} rt_scene_desc;
+
+/* rt_camera.flags */
+#define RT_CAM_REFERENCE_EXTENTS 1u /* keep the reference's swapped scan extents (src/view/camera.ts:242-249):
+                                       identical on square frames, RT_ERR_BOUNDS on non-square ones.
+                                       Without it x runs over [0,width) and y over [0,height). */
+
+/* Camera pose (private fields norm_fr/norm_lf/norm_up/pos/conf of src/view/camera.ts:51-59).  The
+ * per-pixel direction is the generator's: fr rotated (y - (height>>1)) steps of fov_v/height towards up,
+ * then (x - (width>>1)) steps of fov_h/width towards lf (src/view/camera.ts:207-250), un-normalised. */
+typedef struct rt_camera {
+	double pos[3];
+	double fr[3], lf[3], up[3];
+	double fov_h, fov_v;
+	uint32_t width, height; /* CameraConfig.screen_w / screen_h == ExposureBuffer width / height */
+	uint32_t flags;
+	uint32_t _pad;
+} rt_camera;
+
+#define RT_PRECISION_F32 0u /* float search + float64 confirmation/shading of the found hit (default) */
+
+/* RaytracerConfig (src/raytracer.ts:33-43) + exposure state + the harness RNG policy */
+typedef struct rt_params {
+	int32_t refmax;
+	int32_t sky_texture;        /* SkySphere(texture) (src/sky/sky_sphere.ts); index into textures */
+	int32_t default_substance;  /* index into substances */
+	int32_t _pad0;
+	double distance_attenuation_factor;
+	/* n_frames consecutive trace_frame() calls, the first one at ExposureBuffer.frame_count ==
+	 * frame_first (0 right after reset_exposure()), with next_frame() between them
+	 * (src/view/exposure_buffer.ts:53-66; src/main.ts:210).  This is how the reference does spp > 1. */
+	uint32_t n_frames;
+	uint32_t frame_first;
+	/* Rough materials draw from one shared sequential FpLcg in pixel-scan order in the reference
+	 * (SURVEY.md F6), which no parallel renderer can reproduce.  This path reseeds per pixel through
+	 * the public PRNG.seed(): seed = rng_seed + (y*width + x) + frame_count*width*height. */
+	double rng_seed;
+	uint32_t precision;         /* RT_PRECISION_* */
+	uint32_t flags;
+} rt_params;
+
+/* Work counters of the last render (what the per-ray-bytes roofline is built from). */
+typedef struct rt_counters {
+	uint64_t paths;     /* pixels x frames */
+	uint64_t segments;  /* traversals started (primary + continued bounces) */
+	uint64_t nodes;     /* octree nodes returned by the walker order */
+	uint64_t tests;     /* entity hit tests executed */
+	uint64_t shades;    /* alter_ray calls */
+	uint64_t confirms;  /* float64 confirmations of float candidates */
+	uint64_t texture_errors;
+	uint64_t acute_warnings; /* the console.warn path of src/raytracer.ts:200-203 */
+} rt_counters;
+
+/* rt_render flags */
+#define RT_RENDER_COUNTERS 1u  /* collect rt_counters (slower kernel variant) */
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* device < 0: current CUDA device. */
+rt_status rt_create(int32_t device, rt_ctx** out);
+void rt_destroy(rt_ctx* ctx);
+const char* rt_last_error(const rt_ctx* ctx);
+uint32_t rt_abi_version(void);
+/* Use an existing CUDA stream (cudaStream_t as void*) for all work of this ctx; NULL = the ctx's own. */
+rt_status rt_set_stream(rt_ctx* ctx, void* cuda_stream);
+
+/* ---- scene ---------------------------------------------------------------------------------- */
+/* Validates and copies the scene to the device (replaces any previous scene of the ctx). */
+rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* scene);
+
+/* ---- render: the trace_frame() drop-in ------------------------------------------------------- */
+/* Host buffers.  rgb: float32 [height][width][3], the ExposureBuffer pixel store, read when
+ * frame_first > 0 and always written.  first_ids (optional): int32 [height][width], the entity of
+ * the first collision of each pixel's path in the last frame, -1 = none.  Synchronous. */
+rt_status rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* params, uint32_t render_flags,
+                    float* rgb, int32_t* first_ids, rt_counters* counters);
+
+/* Device buffers (same layouts), enqueued on the ctx stream, asynchronous.  For callers that keep
+ * the ExposureBuffer resident on the GPU (tone mapping on device, multi-GPU tile exchange). */
+rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* params, uint32_t render_flags,
+                           float* rgb_dev, int32_t* first_ids_dev);
+/* Counters of the last rt_render_device with RT_RENDER_COUNTERS (synchronises the stream). */
+rt_status rt_get_counters(rt_ctx* ctx, rt_counters* counters);
+rt_status rt_synchronize(rt_ctx* ctx);
+
+/* ---- device timing on the ctx stream (CUDA events) ------------------------------------------- */
+rt_status rt_timer_start(rt_ctx* ctx);
+rt_status rt_timer_stop(rt_ctx* ctx, float* elapsed_ms); /* synchronises */
+/* Number of kernels this library launched on the ctx since rt_create. */
+uint64_t rt_launch_count(const rt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

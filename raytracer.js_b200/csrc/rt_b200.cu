@@ -1,0 +1,331 @@
+// rt_b200.cu — librt_b200.so: the C ABI of include/rt_b200.h and the sm_100a kernels behind it.
+// No PyTorch, no CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include "rt_host.h"
+#include "rt_trace.cuh"
+
+// ================================================================== kernels
+#define RT_TILE_W 16
+#define RT_TILE_H 16
+#define RT_BLOCK (RT_TILE_W * RT_TILE_H)
+
+// One CTA per 16x16 screen tile, one thread per pixel; each warp owns an 8x4 pixel patch so that its
+// 32 rays walk nearly the same octree cells and scan the same entity lists (uniform LDG.128 addresses).
+// Tiles are interleaved over ranks for multi-GPU sharding: tile t belongs to rank t % tile_world.
+template <bool COUNT>
+__global__ void __launch_bounds__(RT_BLOCK) rt_render_kernel(const __grid_constant__ RtDevScene S,
+                                                             const __grid_constant__ RtFrame F, int tiles_x,
+                                                             int n_tiles) {
+	const int tile = F.tile_rank + blockIdx.x * F.tile_world;
+	if (tile >= n_tiles) return;
+	const int tx = tile % tiles_x, ty = tile / tiles_x;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int x = tx * RT_TILE_W + (warp & 1) * 8 + (lane & 7);
+	const int y = ty * RT_TILE_H + (warp >> 1) * 4 + (lane >> 3);
+	RtCounts cnt = {0, 0, 0, 0, 0};
+	uint32_t err = 0;
+	const bool inside = x < F.width && y < F.height;
+	if (inside) render_pixel<COUNT>(S, F, x, y, cnt, err);
+	if (COUNT) {
+		unsigned long long v[6] = {inside ? (unsigned long long)F.n_frames : 0ull, cnt.segments, cnt.nodes,
+		                           cnt.tests, cnt.shades, cnt.confirms};
+#pragma unroll
+		for (int k = 0; k < 6; k++) {
+			unsigned long long s = v[k];
+			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+			if (lane == 0 && s) atomicAdd(F.counters + k, s);
+		}
+	}
+	if (err) atomicOr(F.error_flags, err);
+}
+
+// ================================================================== host side
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	cudaError_t alloc(size_t count) {
+		if (count <= n && p) return cudaSuccess;
+		release();
+		cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+		if (e == cudaSuccess) n = count;
+		else p = nullptr;
+		return e;
+	}
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr;
+		n = 0;
+	}
+};
+
+}  // namespace
+
+struct rt_ctx {
+	int device = 0;
+	cudaStream_t own_stream = nullptr, stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::string err;
+	uint64_t launches = 0;
+	bool has_scene = false;
+
+	RtHostScene host;  // packed host copy (also serves the once-per-frame start state)
+	DevBuf<RtF4> node_geom;
+	DevBuf<RtI4> node_link;
+	DevBuf<int> node_child;
+	DevBuf<RtF4> slot_geom;
+	DevBuf<RtD4> slot_geom64;
+	DevBuf<RtI4> slot_attr;
+	DevBuf<RtMaterial> materials;
+	DevBuf<RtTexture> textures;
+	DevBuf<double> substances;
+	DevBuf<uint8_t> texels;
+	RtDevScene dev{};
+
+	// per-frame
+	DevBuf<RtD2> col_cs;
+	DevBuf<RtD4> row_fr;
+	DevBuf<float> rgb;
+	DevBuf<int> ids;
+	DevBuf<unsigned long long> counters;
+	DevBuf<uint32_t> errflags;
+	std::vector<RtD2> h_col_cs;
+	std::vector<RtD4> h_row_fr;
+};
+
+namespace {
+
+rt_status fail(rt_ctx* ctx, rt_status st, const std::string& msg) {
+	if (ctx) ctx->err = msg;
+	else g_create_error = msg;
+	return st;
+}
+
+#define RT_CUDA(ctx, call)                                                                               \
+	do {                                                                                                 \
+		cudaError_t e_ = (call);                                                                         \
+		if (e_ != cudaSuccess)                                                                           \
+			return fail(ctx, RT_ERR_CUDA, rt_format("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+	} while (0)
+
+template <class T>
+rt_status upload(rt_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& host) {
+	RT_CUDA(ctx, buf.alloc(host.size()));
+	if (!host.empty())
+		RT_CUDA(ctx, cudaMemcpyAsync(buf.p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	return RT_OK;
+}
+
+rt_status check_args(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm) {
+	if (!ctx) return RT_ERR_INVALID;
+	std::string err;
+	const rt_status st = rt_check_render_args(ctx->has_scene, (uint32_t)ctx->host.textures.size(),
+	                                          (uint32_t)ctx->host.substances.size(), cam, prm, err);
+	return st ? fail(ctx, st, err) : RT_OK;
+}
+
+// Builds the RtFrame (camera tables, start state) and launches the kernel on the ctx stream.
+rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb_dev,
+                        int* ids_dev, int tile_rank, int tile_world) {
+	rt_build_camera_tables(*cam, ctx->h_col_cs, ctx->h_row_fr);
+	if (rt_status st = upload(ctx, ctx->col_cs, ctx->h_col_cs)) return st;
+	if (rt_status st = upload(ctx, ctx->row_fr, ctx->h_row_fr)) return st;
+	RtFrame F{};
+	std::string err;
+	if (rt_status st = rt_fill_frame(ctx->host, cam, prm, F, err)) return fail(ctx, st, err);
+	F.col_cs = ctx->col_cs.p;
+	F.row_fr = ctx->row_fr.p;
+	F.rgb = rgb_dev;
+	F.first_ids = ids_dev;
+	F.tile_rank = tile_rank;
+	F.tile_world = tile_world;
+	RT_CUDA(ctx, ctx->errflags.alloc(1));
+	RT_CUDA(ctx, cudaMemsetAsync(ctx->errflags.p, 0, sizeof(uint32_t), ctx->stream));
+	F.error_flags = ctx->errflags.p;
+	const bool count = (flags & RT_RENDER_COUNTERS) != 0;
+	RT_CUDA(ctx, ctx->counters.alloc(8));
+	RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+	F.counters = ctx->counters.p;
+	const int tiles_x = (F.width + RT_TILE_W - 1) / RT_TILE_W, tiles_y = (F.height + RT_TILE_H - 1) / RT_TILE_H;
+	const int n_tiles = tiles_x * tiles_y;
+	const int my_tiles = (n_tiles - tile_rank + tile_world - 1) / tile_world;
+	if (my_tiles > 0) {
+		if (count)
+			rt_render_kernel<true><<<my_tiles, RT_BLOCK, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles);
+		else
+			rt_render_kernel<false><<<my_tiles, RT_BLOCK, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles);
+		ctx->launches++;
+		RT_CUDA(ctx, cudaGetLastError());
+	}
+	return RT_OK;
+}
+
+rt_status read_counters(rt_ctx* ctx, rt_counters* out) {
+	unsigned long long h[8] = {0};
+	uint32_t ef = 0;
+	if (ctx->counters.p)
+		RT_CUDA(ctx, cudaMemcpyAsync(h, ctx->counters.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->errflags.p)
+		RT_CUDA(ctx, cudaMemcpyAsync(&ef, ctx->errflags.p, sizeof ef, cudaMemcpyDeviceToHost, ctx->stream));
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	out->paths = h[0]; out->segments = h[1]; out->nodes = h[2]; out->tests = h[3]; out->shades = h[4];
+	out->confirms = h[5];
+	out->texture_errors = (ef & RT_ERRFLAG_TEXTURE) ? 1 : 0;
+	out->acute_warnings = (ef & RT_ERRFLAG_ACUTE) ? 1 : 0;
+	return RT_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+uint32_t rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+
+const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+rt_status rt_create(int32_t device, rt_ctx** out) {
+	if (!out) return fail(nullptr, RT_ERR_INVALID, "rt_create: out is NULL");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(nullptr, RT_ERR_CUDA,
+		            rt_format("rt_create: no CUDA device (%s); this library has no CPU path",
+		                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
+	if (device < 0) {
+		if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+	}
+	if (device >= count) return fail(nullptr, RT_ERR_INVALID, rt_format("rt_create: device %d of %d", device, count));
+	e = cudaSetDevice(device);
+	if (e != cudaSuccess) return fail(nullptr, RT_ERR_CUDA, rt_format("cudaSetDevice(%d): %s", device, cudaGetErrorString(e)));
+	rt_ctx* ctx = new rt_ctx();
+	ctx->device = device;
+	if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+		rt_status st = fail(nullptr, RT_ERR_CUDA, rt_format("rt_create: %s", cudaGetErrorString(e)));
+		delete ctx;
+		return st;
+	}
+	ctx->stream = ctx->own_stream;
+	*out = ctx;
+	return RT_OK;
+}
+
+void rt_destroy(rt_ctx* ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release();
+	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
+	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
+	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
+	ctx->counters.release(); ctx->errflags.release();
+	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+	delete ctx;
+}
+
+rt_status rt_set_stream(rt_ctx* ctx, void* cuda_stream) {
+	if (!ctx) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+	return RT_OK;
+}
+
+rt_status rt_synchronize(rt_ctx* ctx) {
+	if (!ctx) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return RT_OK;
+}
+
+rt_status rt_timer_start(rt_ctx* ctx) {
+	if (!ctx) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	return RT_OK;
+}
+
+rt_status rt_timer_stop(rt_ctx* ctx, float* elapsed_ms) {
+	if (!ctx || !elapsed_ms) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	RT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+	RT_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+	return RT_OK;
+}
+
+uint64_t rt_launch_count(const rt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
+	if (!ctx) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	std::string err;
+	RtHostScene hs;
+	if (rt_status st = rt_pack_scene(sc, hs, err)) return fail(ctx, st, err);
+	ctx->has_scene = false;
+	ctx->host = std::move(hs);
+	const RtHostScene& H = ctx->host;
+	rt_status st;
+	if ((st = upload(ctx, ctx->node_geom, H.node_geom)) || (st = upload(ctx, ctx->node_link, H.node_link)) ||
+	    (st = upload(ctx, ctx->node_child, H.node_child)) || (st = upload(ctx, ctx->slot_geom, H.slot_geom)) ||
+	    (st = upload(ctx, ctx->slot_geom64, H.slot_geom64)) || (st = upload(ctx, ctx->slot_attr, H.slot_attr)) ||
+	    (st = upload(ctx, ctx->materials, H.materials)) || (st = upload(ctx, ctx->textures, H.textures)) ||
+	    (st = upload(ctx, ctx->substances, H.substances)) || (st = upload(ctx, ctx->texels, H.texels)))
+		return st;
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	RtDevScene& D = ctx->dev;
+	D.node_geom = ctx->node_geom.p; D.node_link = ctx->node_link.p; D.node_child = ctx->node_child.p;
+	D.slot_geom = ctx->slot_geom.p; D.slot_geom64 = ctx->slot_geom64.p; D.slot_attr = ctx->slot_attr.p;
+	D.materials = ctx->materials.p; D.textures = ctx->textures.p; D.substances = ctx->substances.p;
+	D.texels = ctx->texels.p;
+	for (int k = 0; k < 3; k++) D.root_pos[k] = H.root_pos[k];
+	D.root_size = H.root_size;
+	D.n_nodes = (int)H.node_geom.size();
+	D.n_slots = (int)H.slot_geom.size();
+	D.err_l = H.err_l;
+	ctx->has_scene = true;
+	return RT_OK;
+}
+
+rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb_dev,
+                           int32_t* ids_dev) {
+	if (rt_status st = check_args(ctx, cam, prm)) return st;
+	if (!rgb_dev) return fail(ctx, RT_ERR_INVALID, "rt_render_device: rgb_dev is NULL");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	return launch_render(ctx, cam, prm, flags, rgb_dev, ids_dev, 0, 1);
+}
+
+rt_status rt_get_counters(rt_ctx* ctx, rt_counters* out) {
+	if (!ctx || !out) return RT_ERR_INVALID;
+	return read_counters(ctx, out);
+}
+
+rt_status rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb,
+                    int32_t* first_ids, rt_counters* counters) {
+	if (rt_status st = check_args(ctx, cam, prm)) return st;
+	if (!rgb) return fail(ctx, RT_ERR_INVALID, "rt_render: rgb is NULL");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t npx = (size_t)cam->width * cam->height;
+	RT_CUDA(ctx, ctx->rgb.alloc(npx * 3));
+	if (first_ids) RT_CUDA(ctx, ctx->ids.alloc(npx));
+	if (prm->frame_first > 0)
+		RT_CUDA(ctx, cudaMemcpyAsync(ctx->rgb.p, rgb, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	if (counters) flags |= RT_RENDER_COUNTERS;
+	if (rt_status st = launch_render(ctx, cam, prm, flags, ctx->rgb.p, first_ids ? ctx->ids.p : nullptr, 0, 1)) return st;
+	RT_CUDA(ctx, cudaMemcpyAsync(rgb, ctx->rgb.p, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	if (first_ids)
+		RT_CUDA(ctx, cudaMemcpyAsync(first_ids, ctx->ids.p, npx * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	rt_counters tmp;
+	if (rt_status st = read_counters(ctx, &tmp)) return st;  // also synchronises and fetches the error flags
+	if (counters) *counters = tmp;
+	if (tmp.texture_errors) return fail(ctx, RT_ERR_TEXTURE, "Texture coordinates out of bounds");
+	return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// rt_common.h — device-visible scene/frame structures of librt_b200 (HBM layout).
+//
+// Layout idea: everything the per-ray loop touches is addressed by *slot*, not by entity id.
+// A slot is a position in the concatenation of all node entity lists (each run in EntitySet
+// insertion order, src/octree_entity.ts:32-49).  Every entity lives in exactly one node
+// (src/octree_entity.ts:174-188), so slots are a permutation of the entities and a node's list is
+// one contiguous run of 16-byte records: a warp scanning a list issues consecutive LDG.128s.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RT_HD __host__ __device__ __forceinline__
+#define RT_D __device__ __forceinline__
+#else
+#define RT_HD inline
+#define RT_D inline
+#endif
+
+struct alignas(16) RtF4 { float x, y, z, w; };
+struct alignas(16) RtI4 { int x, y, z, w; };
+struct alignas(16) RtD2 { double x, y; };
+struct alignas(32) RtD4 { double x, y, z, w; };
+struct RtD3 { double x, y, z; };
+struct RtF3 { float x, y, z; };
+
+// material flags
+#define RT_MAT_RESPONSE_MASK 3u
+#define RT_MAT_LIGHT 4u
+#define RT_MAT_MIRROR 8u
+
+struct alignas(16) RtMaterial {
+	uint32_t flags;
+	uint32_t _pad;
+	double roughness;
+};
+
+struct alignas(16) RtTexture {
+	double r, g, b;      // SolidTexture colour or ImageTexture fallback
+	uint32_t image;      // 1: loaded image -> texel lookup, 0: constant colour
+	int32_t width, height;
+	uint32_t _pad;
+	uint64_t texel_off;  // first texel in the pool
+};
+
+// slot_attr.y packs material | type<<24
+#define RT_ATTR_MAT_MASK 0x00ffffff
+#define RT_ATTR_TYPE_SHIFT 24
+
+struct RtDevScene {
+	// octree, 64 B per node across three arrays
+	const RtF4* node_geom;   // pos.xyz, size  (float copy of OctreeDim)
+	const RtI4* node_link;   // parent, index_within_parent, list_off, list_cnt
+	const int* node_child;   // [n*8], -1 none
+	// entity lists, slot order
+	const RtF4* slot_geom;   // centre.xyz, w = radius (>0, sphere) | -half_size (<0, box)
+	const RtD4* slot_geom64; // centre.xyz, w = diameter | size  (the reference's float64 values)
+	const RtI4* slot_attr;   // entity id, material|type<<24, texture, substance (-1 undefined)
+	// tables
+	const RtMaterial* materials;
+	const RtTexture* textures;
+	const double* substances;
+	const uint8_t* texels;   // RGB8
+	double root_pos[3];
+	double root_size;
+	int n_nodes, n_slots;
+	float err_l;             // bound on the float error of a point-to-line distance in this scene
+	float _pad;
+};
+
+struct RtFrame {
+	// camera
+	double pos[3];
+	double lf[3];
+	const RtD2* col_cs;  // [width]  (cos,sin) of the accumulated horizontal scan rotation
+	const RtD4* row_fr;  // [height] fr rotated towards up by the accumulated vertical scan rotation
+	int width, height;
+	// start state shared by all primary rays (src/raytracer.ts:309-313)
+	int start_node, start_octant;  // start_node < 0: camera outside the root cube
+	int start_substance;
+	// RaytracerConfig
+	int refmax, sky_texture, default_substance;
+	double attenuation;
+	// exposure + rng
+	uint32_t n_frames, frame_first;
+	double rng_seed;
+	// outputs
+	float* rgb;
+	int* first_ids;
+	unsigned long long* counters;  // 8 x u64 or null
+	uint32_t* error_flags;
+	// pixel subset for tile-sharded rendering: tiles t with t % tile_world == tile_rank
+	int tile_rank, tile_world;
+};
+
+#define RT_ERRFLAG_TEXTURE 1u
+#define RT_ERRFLAG_ACUTE 2u

@@ -1,0 +1,325 @@
+// rt_host.h — host-side (no CUDA) preparation shared by librt_b200 (rt_b200.cu) and the test-only
+// host build of the kernel body (tests/hostsim): validation + packing of rt_scene_desc into the slot
+// layout of rt_common.h, the camera scan tables, and the once-per-frame start state.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "rt_common.h"
+
+struct RtHostScene {
+	std::vector<RtF4> node_geom;
+	std::vector<RtI4> node_link;
+	std::vector<int> node_child;
+	std::vector<RtF4> slot_geom;
+	std::vector<RtD4> slot_geom64;
+	std::vector<RtI4> slot_attr;
+	std::vector<RtMaterial> materials;
+	std::vector<RtTexture> textures;
+	std::vector<double> substances;
+	std::vector<uint8_t> texels;
+	double root_pos[3] = {0, 0, 0};
+	double root_size = 1;
+	float err_l = 0;
+	bool any_transmission = false;
+};
+
+inline std::string rt_format(const char* fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	return buf;
+}
+
+// Validates `sc` and fills `hs`.  On failure returns the status and a message in `err`.
+inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::string& err) {
+#define RT_FAIL(st, ...)              \
+	do {                              \
+		err = rt_format(__VA_ARGS__); \
+		return st;                    \
+	} while (0)
+	if (!sc) RT_FAIL(RT_ERR_INVALID, "rt_scene_upload: scene is NULL");
+	if (sc->struct_size != sizeof(rt_scene_desc))
+		RT_FAIL(RT_ERR_INVALID, "rt_scene_upload: struct_size %u != %zu (ABI mismatch)", sc->struct_size,
+		        sizeof(rt_scene_desc));
+	const uint32_t N = sc->n_nodes, L = sc->n_list, E = sc->n_entities;
+	if (N == 0) RT_FAIL(RT_ERR_INVALID, "scene has no root node");
+	if (!sc->node_pos || !sc->node_size || !sc->node_child || !sc->node_parent || !sc->node_octant || !sc->node_list_off)
+		RT_FAIL(RT_ERR_INVALID, "node arrays must not be NULL");
+	if (L && !sc->list_entity) RT_FAIL(RT_ERR_INVALID, "list_entity is NULL");
+	if (E && (!sc->ent_type || !sc->ent_pos || !sc->ent_extent || !sc->ent_material || !sc->ent_texture || !sc->ent_substance))
+		RT_FAIL(RT_ERR_INVALID, "entity arrays must not be NULL");
+	if (sc->n_materials && (!sc->mat_response || !sc->mat_light || !sc->mat_mirror || !sc->mat_roughness))
+		RT_FAIL(RT_ERR_INVALID, "material arrays must not be NULL");
+	if (sc->n_textures && (!sc->tex_kind || !sc->tex_color)) RT_FAIL(RT_ERR_INVALID, "texture arrays must not be NULL");
+	if (sc->n_substances && !sc->sub_refractive_index) RT_FAIL(RT_ERR_INVALID, "substance array is NULL");
+	if (sc->n_materials >= (1u << RT_ATTR_TYPE_SHIFT)) RT_FAIL(RT_ERR_UNSUPPORTED, "too many materials");
+	if (sc->node_parent[0] != -1)
+		RT_FAIL(RT_ERR_UNSUPPORTED, "unsupported octree: node 0 must be the absolute root (tree.parent == undefined)");
+	if (sc->node_list_off[0] != 0 || sc->node_list_off[N] != L)
+		RT_FAIL(RT_ERR_INVALID, "node_list_off must start at 0 and end at n_list");
+
+	hs.node_geom.resize(N);
+	hs.node_link.resize(N);
+	hs.node_child.resize((size_t)N * 8);
+	double scale = 0;
+	for (uint32_t i = 0; i < N; i++) {
+		const double* p = sc->node_pos + 3 * (size_t)i;
+		const double s = sc->node_size[i];
+		if (!(s > 0) || !std::isfinite(s)) RT_FAIL(RT_ERR_INVALID, "node %u: bad size", i);
+		hs.node_geom[i] = RtF4{(float)p[0], (float)p[1], (float)p[2], (float)s};
+		if (sc->node_list_off[i + 1] < sc->node_list_off[i]) RT_FAIL(RT_ERR_INVALID, "node %u: list offsets not monotone", i);
+		const int par = sc->node_parent[i];
+		if (i > 0 && (par < 0 || (uint32_t)par >= N)) RT_FAIL(RT_ERR_INVALID, "node %u: bad parent %d", i, par);
+		const int oc = sc->node_octant[i];
+		if (i > 0 && (oc < 0 || oc > 7)) RT_FAIL(RT_ERR_INVALID, "node %u: bad octant %d", i, oc);
+		hs.node_link[i] = RtI4{par, i > 0 ? oc : -1, (int)sc->node_list_off[i],
+		                       (int)(sc->node_list_off[i + 1] - sc->node_list_off[i])};
+		for (int c = 0; c < 8; c++) {
+			const int ch = sc->node_child[(size_t)i * 8 + c];
+			if (ch < -1 || ch >= (int)N || ch == 0) RT_FAIL(RT_ERR_INVALID, "node %u: bad child %d", i, ch);
+			if (ch > 0 && sc->node_parent[ch] != (int)i) RT_FAIL(RT_ERR_INVALID, "node %u: child %d does not point back", i, ch);
+			hs.node_child[(size_t)i * 8 + c] = ch;
+		}
+		for (int k = 0; k < 3; k++) scale = std::max(scale, std::fabs(p[k]) + s);
+	}
+	hs.slot_geom.resize(L);
+	hs.slot_geom64.resize(L);
+	hs.slot_attr.resize(L);
+	std::vector<uint8_t> seen(E, 0);
+	for (uint32_t s = 0; s < L; s++) {
+		const uint32_t e = sc->list_entity[s];
+		if (e >= E) RT_FAIL(RT_ERR_INVALID, "list slot %u: entity %u out of range", s, e);
+		if (seen[e]) RT_FAIL(RT_ERR_INVALID, "entity %u is listed in more than one node", e);
+		seen[e] = 1;
+		const double* p = sc->ent_pos + 3 * (size_t)e;
+		const double ext = sc->ent_extent[e];
+		const uint32_t type = sc->ent_type[e];
+		if (type > RT_ENTITY_BOX) RT_FAIL(RT_ERR_UNSUPPORTED, "unsupported Entity subclass (type %u) for entity %u", type, e);
+		if (!(ext > 0) || !std::isfinite(ext)) RT_FAIL(RT_ERR_INVALID, "entity %u: bad extent", e);
+		const int m = sc->ent_material[e], t = sc->ent_texture[e], sb = sc->ent_substance[e];
+		if (m < 0 || (uint32_t)m >= sc->n_materials) RT_FAIL(RT_ERR_INVALID, "entity %u: material %d", e, m);
+		if (t < 0 || (uint32_t)t >= sc->n_textures) RT_FAIL(RT_ERR_INVALID, "entity %u: texture %d", e, t);
+		if (sb < -1 || sb >= (int)sc->n_substances) RT_FAIL(RT_ERR_INVALID, "entity %u: substance %d", e, sb);
+		const float w = type == RT_ENTITY_SPHERE ? (float)(ext / 2) : -(float)(ext / 2);
+		hs.slot_geom[s] = RtF4{(float)p[0], (float)p[1], (float)p[2], w};
+		hs.slot_geom64[s] = RtD4{p[0], p[1], p[2], ext};
+		hs.slot_attr[s] = RtI4{(int)e, m | (int)(type << RT_ATTR_TYPE_SHIFT), t, sb};
+		for (int k = 0; k < 3; k++) scale = std::max(scale, std::fabs(p[k]) + ext);
+	}
+	hs.materials.resize(sc->n_materials);
+	hs.any_transmission = false;
+	for (uint32_t i = 0; i < sc->n_materials; i++) {
+		if (sc->mat_response[i] > RT_RESPONSE_BOTH) RT_FAIL(RT_ERR_INVALID, "material %u: response", i);
+		hs.materials[i].flags =
+		    sc->mat_response[i] | (sc->mat_light[i] ? RT_MAT_LIGHT : 0u) | (sc->mat_mirror[i] ? RT_MAT_MIRROR : 0u);
+		hs.materials[i]._pad = 0;
+		hs.materials[i].roughness = sc->mat_roughness[i];
+		hs.any_transmission |= sc->mat_response[i] == RT_RESPONSE_TRANSMISSION;
+	}
+	hs.textures.resize(sc->n_textures);
+	for (uint32_t i = 0; i < sc->n_textures; i++) {
+		RtTexture& T = hs.textures[i];
+		memset(&T, 0, sizeof T);
+		T.r = sc->tex_color[4 * (size_t)i];
+		T.g = sc->tex_color[4 * (size_t)i + 1];
+		T.b = sc->tex_color[4 * (size_t)i + 2];
+		if (sc->tex_kind[i] > RT_TEXTURE_IMAGE) RT_FAIL(RT_ERR_UNSUPPORTED, "unsupported Texture subclass (kind %u)", sc->tex_kind[i]);
+		if (sc->tex_kind[i] == RT_TEXTURE_IMAGE && sc->tex_loaded && sc->tex_loaded[i]) {
+			if (!sc->tex_width || !sc->tex_height || !sc->tex_texel_off || !sc->texels)
+				RT_FAIL(RT_ERR_INVALID, "image texture arrays must not be NULL");
+			const int64_t w = sc->tex_width[i], h = sc->tex_height[i];
+			if (w <= 0 || h <= 0 || sc->tex_texel_off[i] + (uint64_t)(w * h) > sc->n_texels)
+				RT_FAIL(RT_ERR_INVALID, "texture %u: %lldx%lld texels out of the pool", i, (long long)w, (long long)h);
+			T.image = 1;
+			T.width = (int)w;
+			T.height = (int)h;
+			T.texel_off = sc->tex_texel_off[i];
+		}
+	}
+	hs.substances.assign(sc->sub_refractive_index, sc->sub_refractive_index + sc->n_substances);
+	hs.texels.assign(sc->texels, sc->texels + (sc->texels ? sc->n_texels * 3 : 0));
+	for (int k = 0; k < 3; k++) hs.root_pos[k] = sc->node_pos[k];
+	hs.root_size = sc->node_size[0];
+	// bound on the float32 error of a centre-to-line distance for coordinates up to `scale`
+	hs.err_l = (float)(16.0 * 1.1920929e-7 * scale);
+	return RT_OK;
+#undef RT_FAIL
+}
+
+// ---- host float64 restatements used once per frame (src/raytracer.ts:309-313) -----------------
+// node_at_pos (src/octree_space.ts:61-93)
+inline bool rt_host_node_at_pos(const RtHostScene& c, const double* p, int& node, int& octant) {
+	double np[3] = {c.root_pos[0], c.root_pos[1], c.root_pos[2]};
+	double ns = c.root_size;
+	for (int i = 0; i < 3; i++)
+		if (!(p[i] >= np[i] && p[i] < np[i] + ns)) return false;
+	int cur = 0, next = 0, idx = 0;
+	while (next >= 0) {
+		const double k = 2.0 / ns;
+		const int ix = (int)((p[0] - np[0]) * k), iy = (int)((p[1] - np[1]) * k), iz = (int)((p[2] - np[2]) * k);
+		cur = next;
+		idx = (iz << 2) + (iy << 1) + ix;
+		if (idx < 0 || idx > 7) return false;
+		next = c.node_child[(size_t)cur * 8 + idx];
+		ns = ns / 2.0;
+		np[0] += ix * ns;
+		np[1] += iy * ns;
+		np[2] += iz * ns;
+	}
+	node = cur;
+	octant = idx;
+	return true;
+}
+// entity_at_pos (src/octree_entity.ts:191-202) -> slot or -1
+inline int rt_host_entity_at_pos(const RtHostScene& c, const double* p) {
+	int node, octant;
+	if (!rt_host_node_at_pos(c, p, node, octant)) return -1;
+	while (node >= 0) {
+		const RtI4 link = c.node_link[node];
+		for (int s = link.z; s < link.z + link.w; s++) {
+			const RtD4& g = c.slot_geom64[s];
+			const int type = c.slot_attr[s].y >> RT_ATTR_TYPE_SHIFT;
+			bool within;
+			if (type == 0) {  // entity_sphere.ts:63-66
+				const double d0 = p[0] - g.x, d1 = p[1] - g.y, d2 = p[2] - g.z;
+				double s2 = 0;
+				s2 += d0 * d0;
+				s2 += d1 * d1;
+				s2 += d2 * d2;
+				within = s2 <= g.w * g.w / 4;
+			} else {  // entity_box.ts:47-52
+				within = p[0] >= g.x && p[0] < g.x + g.w && p[1] >= g.y && p[1] < g.y + g.w && p[2] >= g.z &&
+				         p[2] < g.z + g.w;
+			}
+			if (within) return s;
+		}
+		node = link.x;
+	}
+	return -1;
+}
+
+// The accumulated scan rotations of Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250).
+// Rows: fr rotated towards up, iterated exactly like iter_v.  Columns: the 2x2 rotation the
+// generator applies to (fr_row, lf), iterated like iter_h on the coefficient pairs.
+inline void rt_build_camera_tables(const rt_camera& cam, std::vector<RtD2>& col, std::vector<RtD4>& row) {
+	const int W = (int)cam.width, H = (int)cam.height;
+	col.assign(W, RtD2{1, 0});
+	row.assign(H, RtD4{0, 0, 0, 0});
+	const double rad_h = cam.fov_h / W, rad_v = cam.fov_v / H;
+	const double ch = std::cos(rad_h), sh = std::sin(rad_h), cv = std::cos(rad_v), sv = std::sin(rad_v);
+	auto rot3 = [](double* bx, double* by, double c, double s) {  // rotate_vectors vector.ts:318-323
+		for (int k = 0; k < 3; k++) {
+			const double x = bx[k] * c + by[k] * s;
+			const double y = bx[k] * -s + by[k] * c;
+			bx[k] = x;
+			by[k] = y;
+		}
+	};
+	{
+		const int y0 = H >> 1;
+		double fr[3] = {cam.fr[0], cam.fr[1], cam.fr[2]}, up[3] = {cam.up[0], cam.up[1], cam.up[2]};
+		for (int y = y0; y < H; y++) {
+			row[y] = RtD4{fr[0], fr[1], fr[2], 0};
+			rot3(fr, up, cv, sv);
+		}
+		double fr2[3] = {cam.fr[0], cam.fr[1], cam.fr[2]}, up2[3] = {cam.up[0], cam.up[1], cam.up[2]};
+		rot3(fr2, up2, cv, -sv);
+		for (int y = y0 - 1; y >= 0; y--) {
+			row[y] = RtD4{fr2[0], fr2[1], fr2[2], 0};
+			rot3(fr2, up2, cv, -sv);
+		}
+	}
+	{
+		const int x0 = W >> 1;
+		auto step = [](double* a, double c, double s) {  // (alpha,beta | gamma,delta)
+			const double al = a[0] * c + a[2] * s, be = a[1] * c + a[3] * s;
+			const double ga = a[0] * -s + a[2] * c, de = a[1] * -s + a[3] * c;
+			a[0] = al;
+			a[1] = be;
+			a[2] = ga;
+			a[3] = de;
+		};
+		double a[4] = {1, 0, 0, 1};
+		for (int x = x0; x < W; x++) {
+			col[x] = RtD2{a[0], a[1]};
+			step(a, ch, sh);
+		}
+		double b[4] = {1, 0, 0, 1};
+		step(b, ch, -sh);
+		for (int x = x0 - 1; x >= 0; x--) {
+			col[x] = RtD2{b[0], b[1]};
+			step(b, ch, -sh);
+		}
+	}
+}
+
+// Argument checks shared by every render entry point.
+inline rt_status rt_check_render_args(bool has_scene, uint32_t n_textures, uint32_t n_substances, const rt_camera* cam,
+                                      const rt_params* prm, std::string& err) {
+	if (!cam || !prm) { err = "rt_render: camera and params must not be NULL"; return RT_ERR_INVALID; }
+	if (!has_scene) { err = "rt_render: no scene uploaded"; return RT_ERR_NO_SCENE; }
+	if (cam->width == 0 || cam->height == 0 || cam->width > 65536 || cam->height > 65536) {
+		err = rt_format("rt_render: bad frame size %ux%u", cam->width, cam->height);
+		return RT_ERR_INVALID;
+	}
+	if ((cam->flags & RT_CAM_REFERENCE_EXTENTS) && cam->width != cam->height) {
+		err = "x or y out of bounds";
+		return RT_ERR_BOUNDS;
+	}
+	if (prm->precision != RT_PRECISION_F32) { err = rt_format("unsupported precision %u", prm->precision); return RT_ERR_UNSUPPORTED; }
+	if (prm->n_frames == 0) { err = "rt_render: n_frames must be >= 1"; return RT_ERR_INVALID; }
+	if (prm->sky_texture < 0 || (uint32_t)prm->sky_texture >= n_textures) {
+		err = rt_format("rt_render: sky_texture %d out of range", prm->sky_texture);
+		return RT_ERR_INVALID;
+	}
+	if (prm->default_substance < 0 || (uint32_t)prm->default_substance >= n_substances) {
+		err = rt_format("rt_render: default_substance %d out of range", prm->default_substance);
+		return RT_ERR_INVALID;
+	}
+	return RT_OK;
+}
+
+// Fills the camera / start-state / config part of an RtFrame (pointers are left to the caller).
+inline rt_status rt_fill_frame(const RtHostScene& hs, const rt_camera* cam, const rt_params* prm, RtFrame& F,
+                               std::string& err) {
+	for (int i = 0; i < 3; i++) {
+		F.pos[i] = cam->pos[i];
+		F.lf[i] = cam->lf[i];
+	}
+	F.width = (int)cam->width;
+	F.height = (int)cam->height;
+	int node = -1, octant = -1;
+	if (!rt_host_node_at_pos(hs, cam->pos, node, octant)) {
+		node = -1;
+		octant = -1;
+	}
+	F.start_node = node;
+	F.start_octant = octant;
+	const int start_slot = rt_host_entity_at_pos(hs, cam->pos);
+	F.start_substance = start_slot >= 0 ? hs.slot_attr[start_slot].w : prm->default_substance;
+	if (F.start_substance < 0) {
+		if (hs.any_transmission) {
+			err = "camera is inside an entity whose substance is undefined and the scene has TRANSMISSION materials "
+			      "(the reference throws a TypeError at the first refraction)";
+			return RT_ERR_UNSUPPORTED;
+		}
+		F.start_substance = prm->default_substance;
+	}
+	F.refmax = prm->refmax;
+	F.sky_texture = prm->sky_texture;
+	F.default_substance = prm->default_substance;
+	F.attenuation = prm->distance_attenuation_factor;
+	F.n_frames = prm->n_frames;
+	F.frame_first = prm->frame_first;
+	F.rng_seed = prm->rng_seed;
+	return RT_OK;
+}

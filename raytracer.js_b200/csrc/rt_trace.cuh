@@ -1,0 +1,624 @@
+// rt_trace.cuh — the per-ray hot path: octree walk in the reference's visit order, entity hit tests,
+// shading, bounces.  Everything is RT_HD so that the same source is the CUDA kernel body and (for
+// logic tests on a box without a GPU) a test-only host build; the shipped library only ever runs it
+// on the device.
+//
+// Precision model ("float search, float64 confirm"):
+//  * the octree walk and the scan of the entity lists run in float32 on conservative (inflated)
+//    bounds: they can only produce false candidates, never lose a hit by more than rounding noise;
+//  * every candidate is confirmed in float64 with the reference's own formula and operation order
+//    (src/math/intersection.ts:109-128,150-204), so hit/miss decisions, hit points, normals, path
+//    lengths and colours are the reference's float64 values;
+//  * ray state (origin, direction, colour, path length, RNG) is float64; the float copies are
+//    re-derived per segment.
+//
+// Reference citations are relative to /root/reference.
+#pragma once
+#include <math.h>
+
+#include "rt_common.h"
+
+#define RT_JS_EPSILON 2.220446049250313e-16
+#define RT_JS_PI 3.141592653589793
+
+// ------------------------------------------------------------------ exact float64 primitives
+// No FMA contraction: the reference rounds after every multiply and add.
+#if defined(__CUDA_ARCH__)
+RT_HD double xmul(double a, double b) { return __dmul_rn(a, b); }
+RT_HD double xadd(double a, double b) { return __dadd_rn(a, b); }
+RT_HD double xsub(double a, double b) { return __dsub_rn(a, b); }
+RT_HD double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+RT_HD double xsqrt(double a) { return __dsqrt_rn(a); }
+#else
+// host build: compiled with -ffp-contract=off
+RT_HD double xmul(double a, double b) { return a * b; }
+RT_HD double xadd(double a, double b) { return a + b; }
+RT_HD double xsub(double a, double b) { return a - b; }
+RT_HD double xdiv(double a, double b) { return a / b; }
+RT_HD double xsqrt(double a) { return sqrt(a); }
+#endif
+
+// ------------------------------------------------------------------ loads (read-only path, 16 B)
+RT_HD RtF4 ld(const RtF4* p) {
+#if defined(__CUDA_ARCH__)
+	const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+	return RtF4{v.x, v.y, v.z, v.w};
+#else
+	return *p;
+#endif
+}
+RT_HD RtI4 ld(const RtI4* p) {
+#if defined(__CUDA_ARCH__)
+	const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+	return RtI4{v.x, v.y, v.z, v.w};
+#else
+	return *p;
+#endif
+}
+RT_HD RtD2 ld(const RtD2* p) {
+#if defined(__CUDA_ARCH__)
+	const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+	return RtD2{v.x, v.y};
+#else
+	return *p;
+#endif
+}
+RT_HD RtD4 ld(const RtD4* p) {
+#if defined(__CUDA_ARCH__)
+	const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+	const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+	return RtD4{a.x, a.y, b.x, b.y};
+#else
+	return *p;
+#endif
+}
+RT_HD int ld(const int* p) {
+#if defined(__CUDA_ARCH__)
+	return __ldg(p);
+#else
+	return *p;
+#endif
+}
+
+// vector.dot (src/math/vector.ts:76-84): sum starts at 0, left to right
+RT_HD double dot3(const double* a, const double* b) {
+	double s = 0.0;
+	s = xadd(s, xmul(a[0], b[0]));
+	s = xadd(s, xmul(a[1], b[1]));
+	s = xadd(s, xmul(a[2], b[2]));
+	return s;
+}
+RT_HD double js_sign(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : x); }
+RT_HD bool js_is_negative(double x) { return x < 0 || (x == 0 && signbit(x)); }  // mathutils.ts:45-47
+
+struct RtCollision {
+	double point[3];
+	double normal[3];
+};
+
+struct RtCounts {
+	unsigned int segments, nodes, tests, shades, confirms;
+};
+
+// ------------------------------------------------------------------ float64 confirmations
+// Box.line_intersection (src/math/intersection.ts:150-204).  Returns false for `[]`.
+RT_HD bool exact_box_params(const double* c, double size, const double* o, const double* d, double& u1,
+                            double& u2, int& i1, int& i2) {
+	double p[6], q[6];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const double tl = xsub(c[k], xmul(size, 0.5));
+		p[2 * k] = -d[k];
+		p[2 * k + 1] = d[k];
+		q[2 * k] = xsub(o[k], tl);
+		q[2 * k + 1] = xsub(xadd(tl, size), o[k]);
+	}
+	u1 = -INFINITY;
+	u2 = INFINITY;
+	i1 = -1;
+	i2 = -1;
+#pragma unroll
+	for (int i = 0; i < 6; i++) {
+		const double u = xdiv(q[i], p[i]);
+		if (js_is_negative(p[i])) {
+			if (u > u1) { u1 = u; i1 = i; }
+		} else {
+			if (u < u2) { u2 = u; i2 = i; }
+		}
+	}
+	return !(u1 > u2);
+}
+
+// SphereEntity.collision_info (src/entities/entity_sphere.ts:68-88) over
+// Sphere.line_intersection (src/math/intersection.ts:109-128), FORWARD selection (:207-216)
+RT_HD bool exact_sphere(const RtD4& g, const double* o, const double* d, RtCollision& col) {
+	const double pos[3] = {g.x, g.y, g.z};
+	const double radius = xdiv(g.w, 2.0);
+	const double radius_sq = xmul(radius, radius);
+	const double dot_pp = dot3(pos, pos);
+	const double dist[3] = {xsub(o[0], pos[0]), xsub(o[1], pos[1]), xsub(o[2], pos[2])};
+	const double a = dot3(d, d);
+	const double b = xmul(dot3(dist, d), 2.0);
+	const double c = xsub(xsub(xadd(dot3(o, o), dot_pp), xmul(dot3(o, pos), 2.0)), radius_sq);
+	const double delta = xsub(xmul(b, b), xmul(xmul(a, c), 4.0));
+	if (delta < 0) return false;
+	const double s_delta = xsqrt(delta);
+	const double a2 = xmul(a, 2.0);
+	const double tmp1 = xdiv(-b, a2);
+	const double tmp2 = xdiv(s_delta, a2);
+	const double t1 = xsub(tmp1, tmp2);
+	const double t2 = xadd(tmp1, tmp2);
+	double t;
+	if (t1 >= 0) t = t1;
+	else if (t2 >= 0) t = t2;
+	else return false;
+	const double k = xdiv(2.0, g.w);
+#pragma unroll
+	for (int i = 0; i < 3; i++) {
+		col.point[i] = xadd(o[i], xmul(d[i], t));
+		col.normal[i] = xmul(xsub(col.point[i], pos[i]), k);
+	}
+	const double sg = -js_sign(dot3(d, col.normal));
+#pragma unroll
+	for (int i = 0; i < 3; i++) col.normal[i] = xmul(col.normal[i], sg);
+	return true;
+}
+
+// BoxEntity.collision_info (src/entities/entity_box.ts:54-73)
+RT_HD bool exact_box(const RtD4& g, const double* o, const double* d, RtCollision& col) {
+	const double pos[3] = {g.x, g.y, g.z};
+	double u1, u2;
+	int i1, i2;
+	if (!exact_box_params(pos, g.w, o, d, u1, u2, i1, i2)) return false;
+	double t;
+	int face;
+	if (u1 >= 0) { t = u1; face = i1; }
+	else if (u2 >= 0) { t = u2; face = i2; }
+	else return false;
+#pragma unroll
+	for (int i = 0; i < 3; i++) {
+		col.point[i] = xadd(o[i], xmul(d[i], t));
+		col.normal[i] = 0.0;
+	}
+	if (face >= 0) {
+		double n[3] = {0.0, 0.0, 0.0};
+		n[face >> 1] = (face & 1) ? 1.0 : -1.0;
+		const double sg = -js_sign(dot3(d, n));
+#pragma unroll
+		for (int i = 0; i < 3; i++) col.normal[i] = xmul(n[i], sg);
+	}
+	return true;
+}
+
+// ------------------------------------------------------------------ float32 candidate filters
+struct RtRayF {
+	float ox, oy, oz;
+	float dx, dy, dz;
+	float ix, iy, iz;  // 1/d (±inf for zero components)
+	float inv_a;       // 1/(d.d)
+};
+
+RT_HD RtRayF make_ray_f(const double* o, const double* d) {
+	RtRayF r;
+	r.ox = (float)o[0]; r.oy = (float)o[1]; r.oz = (float)o[2];
+	r.dx = (float)d[0]; r.dy = (float)d[1]; r.dz = (float)d[2];
+	r.ix = 1.0f / r.dx; r.iy = 1.0f / r.dy; r.iz = 1.0f / r.dz;
+	r.inv_a = 1.0f / (r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
+	return r;
+}
+
+// true if the entity MAY have a forward intersection (conservative by err_l)
+RT_HD bool candidate(const RtF4& g, const RtRayF& r, float err_l) {
+	const float cx = g.x - r.ox, cy = g.y - r.oy, cz = g.z - r.oz;
+	if (g.w > 0.0f) {
+		// sphere: squared distance from the centre to the ray's line against (radius + err)^2
+		const float tca = cx * r.dx + cy * r.dy + cz * r.dz;
+		const float s = tca * r.inv_a;
+		const float lx = cx - s * r.dx, ly = cy - s * r.dy, lz = cz - s * r.dz;
+		const float l2 = lx * lx + ly * ly + lz * lz;
+		const float rr = g.w + err_l;
+		const float rr2 = rr * rr;
+		if (l2 > rr2) return false;
+		if (tca >= 0.0f) return true;
+		return cx * cx + cy * cy + cz * cz <= rr2;  // origin inside: the far root is forward
+	}
+	// box: slab test on the inflated box
+	const float h = err_l - g.w;
+	float t0 = (cx - h) * r.ix, t1 = (cx + h) * r.ix;
+	float tmin = fminf(t0, t1), tmax = fmaxf(t0, t1);
+	t0 = (cy - h) * r.iy; t1 = (cy + h) * r.iy;
+	tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1));
+	t0 = (cz - h) * r.iz; t1 = (cz + h) * r.iz;
+	tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1));
+	const float slack = err_l * fmaxf(fabsf(r.ix), fmaxf(fabsf(r.iy), fabsf(r.iz)));
+	return !(tmin > tmax + slack) && !(tmax < -slack);
+}
+
+// ------------------------------------------------------------------ point location (float64)
+// node_at_pos (src/octree_space.ts:61-93), half-open cube test of src/space.ts:55-66
+RT_HD bool node_at_pos(const RtDevScene& S, const double* p, int& node, int& octant) {
+	double np[3] = {S.root_pos[0], S.root_pos[1], S.root_pos[2]};
+	double ns = S.root_size;
+#pragma unroll
+	for (int i = 0; i < 3; i++)
+		if (!(p[i] >= np[i] && p[i] < xadd(np[i], ns))) return false;
+	int cur = 0, next = 0, idx = 0;
+	while (next >= 0) {
+		const double k = xdiv(2.0, ns);
+		const int ix = (int)xmul(xsub(p[0], np[0]), k);
+		const int iy = (int)xmul(xsub(p[1], np[1]), k);
+		const int iz = (int)xmul(xsub(p[2], np[2]), k);
+		cur = next;
+		idx = (iz << 2) + (iy << 1) + ix;
+		if (idx < 0 || idx > 7) return false;  // the reference's Octree.get() would throw here
+		next = ld(S.node_child + cur * 8 + idx);
+		ns = xdiv(ns, 2.0);
+		np[0] = xadd(np[0], xmul((double)ix, ns));
+		np[1] = xadd(np[1], xmul((double)iy, ns));
+		np[2] = xadd(np[2], xmul((double)iz, ns));
+	}
+	node = cur;
+	octant = idx;
+	return true;
+}
+
+// entity_at_pos (src/octree_entity.ts:191-202) -> slot or -1
+RT_HD int entity_at_pos(const RtDevScene& S, const double* p) {
+	int node, octant;
+	if (!node_at_pos(S, p, node, octant)) return -1;
+	while (node >= 0) {
+		const RtI4 link = ld(S.node_link + node);
+		for (int s = link.z; s < link.z + link.w; s++) {
+			const RtD4 g = ld(S.slot_geom64 + s);
+			const int type = ld(&S.slot_attr[s].y) >> RT_ATTR_TYPE_SHIFT;
+			bool within;
+			if (type == 0) {  // SphereEntity.is_within, entity_sphere.ts:63-66 (_radius_sq = d*d/4)
+				const double dist[3] = {xsub(p[0], g.x), xsub(p[1], g.y), xsub(p[2], g.z)};
+				within = dot3(dist, dist) <= xdiv(xmul(g.w, g.w), 4.0);
+			} else {  // BoxEntity.is_within, entity_box.ts:47-52: [pos, pos+size) from the *centre*
+				within = p[0] >= g.x && p[0] < xadd(g.x, g.w) && p[1] >= g.y && p[1] < xadd(g.y, g.w) &&
+				         p[2] >= g.z && p[2] < xadd(g.z, g.w);
+			}
+			if (within) return s;
+		}
+		node = link.x;
+	}
+	return -1;
+}
+
+// ------------------------------------------------------------------ the walk
+// Scans one node's entity list in insertion order; returns the slot of the first entity whose
+// float64 collision_info is non-null (src/raytracer.ts:186-195), or -1.
+template <bool COUNT>
+RT_HD int scan_list(const RtDevScene& S, int node, const RtRayF& r, const double* o, const double* d,
+                    RtCollision& col, RtCounts& cnt) {
+	const RtI4 link = ld(S.node_link + node);
+	const int beg = link.z, end = link.z + link.w;
+	int s = beg;
+	while (true) {
+		for (; s < end; ++s)
+			if (candidate(ld(S.slot_geom + s), r, S.err_l)) break;
+		if (s >= end) break;
+		const RtD4 g = ld(S.slot_geom64 + s);
+		const bool hit = ld(S.slot_geom + s).w > 0.0f ? exact_sphere(g, o, d, col) : exact_box(g, o, d, col);
+		if (COUNT) cnt.confirms++;
+		if (hit) {
+			if (COUNT) cnt.tests += (unsigned)(s - beg + 1);
+			return s;
+		}
+		++s;
+	}
+	if (COUNT) cnt.tests += (unsigned)(end - beg);
+	return -1;
+}
+
+// OctreeWalker.next() (src/octree_space.ts:316-361) fused with the list scan of Ray.trace
+// (src/raytracer.ts:179-195).  State names follow the reference.  (node, octant) is the start
+// position: node_at_pos of the origin, or octant < 0 for "origin outside the root: root only"
+// (src/octree_space.ts:272-275,283-287).  Returns the hit slot or -1.
+template <bool COUNT>
+RT_HD int walk_and_scan(const RtDevScene& S, int node, int octant, const double* o, const double* d,
+                        RtCollision& col, RtCounts& cnt) {
+	const RtRayF r = make_ray_f(o, d);
+	bool cur_returned = false, stepped_in = false, ahead = false;
+	int depth = 0;
+	float npx = r.ox, npy = r.oy, npz = r.oz;  // next_pos[0]
+	int face = 0;                               // next_pos[1] as a face index (axis*2 + positive)
+	RtF4 g = ld(S.node_geom + node);
+	while (true) {
+		const int child = octant >= 0 ? ld(S.node_child + node * 8 + octant) : node;
+		if (!cur_returned && child >= 0) {
+			cur_returned = true;
+			if (COUNT) cnt.nodes++;
+			const int s = scan_list<COUNT>(S, child, r, o, d, col, cnt);
+			if (s >= 0) return s;
+		}
+		if (octant >= 0) {
+			if (!ahead) {
+				if (!stepped_in && child >= 0) {  // step_in: octant_adj_pos(child, next_pos[0]) :41-50
+					g = ld(S.node_geom + child);
+					const float h = g.w * 0.5f;
+					octant = (npx >= g.x + h ? 1 : 0) | (npy >= g.y + h ? 2 : 0) | (npz >= g.z + h ? 4 : 0);
+					node = child;
+					depth++;
+					cur_returned = false;
+					continue;
+				}
+				// update_next_pos :369-384: exit parameter and face of the cell (node, octant);
+				// strict comparisons in face order -x,+x,-y,+y,-z,+z  =>  ties go x, then y, then z
+				const float h = g.w * 0.5f;
+				const float lox = g.x + ((octant & 1) ? h : 0.0f);
+				const float loy = g.y + ((octant & 2) ? h : 0.0f);
+				const float loz = g.z + ((octant & 4) ? h : 0.0f);
+				const float tx = r.dx != 0.0f ? ((r.dx > 0.0f ? lox + h : lox) - r.ox) * r.ix : INFINITY;
+				const float ty = r.dy != 0.0f ? ((r.dy > 0.0f ? loy + h : loy) - r.oy) * r.iy : INFINITY;
+				const float tz = r.dz != 0.0f ? ((r.dz > 0.0f ? loz + h : loz) - r.oz) * r.iz : INFINITY;
+				float t = tx;
+				face = r.dx > 0.0f ? 1 : 0;
+				if (ty < t) { t = ty; face = r.dy > 0.0f ? 3 : 2; }
+				if (tz < t) { t = tz; face = r.dz > 0.0f ? 5 : 4; }
+				npx = r.ox + r.dx * t;
+				npy = r.oy + r.dy * t;
+				npz = r.oz + r.dz * t;
+			}
+			const int axis = face >> 1;
+			const int bit = (octant >> axis) & 1;
+			if (bit != (face & 1)) {  // neighbour octant inside the parent cube :344-352
+				octant ^= 1 << axis;
+				cur_returned = false;
+				stepped_in = false;
+				ahead = false;
+				continue;
+			}
+			ahead = true;
+		}
+		// step_back :280-308
+		stepped_in = true;
+		if (octant < 0) break;
+		if (depth > 0) { depth--; cur_returned = true; }
+		else cur_returned = false;
+		const RtI4 link = ld(S.node_link + node);
+		if (link.x >= 0) {
+			octant = link.y;
+			node = link.x;
+			g = ld(S.node_geom + node);
+		} else {
+			octant = -1;
+		}
+	}
+	return -1;
+}
+
+// ------------------------------------------------------------------ shading helpers
+// uv_map_sphere (src/math/uv_mapping.ts:19-25)
+RT_HD void uv_map_sphere(const double* v, double& u, double& w) {
+	u = xsub(xadd(xdiv(xdiv(atan2(v[1], v[0]), RT_JS_PI), 2.0), 0.5), RT_JS_EPSILON);
+	double s = 0.0;
+	s = xadd(s, xmul(v[0], v[0]));
+	s = xadd(s, xmul(v[1], v[1]));
+	w = xsub(xadd(xdiv(atan2(v[2], xsqrt(s)), RT_JS_PI), 0.5), RT_JS_EPSILON);
+}
+
+// Texture.get_color: texture_solid.ts:33-35, texture_image.ts:40-63
+RT_HD bool texture_color(const RtDevScene& S, int tex, bool is_sphere, const double* v, double* rgb) {
+	const RtTexture* T = S.textures + tex;
+	if (!T->image) {
+		rgb[0] = T->r; rgb[1] = T->g; rgb[2] = T->b;
+		return true;
+	}
+	double u = 0.0, w = 0.0;  // BoxEntity.map_uv returns [0,0] (entity_box.ts:104-107)
+	if (is_sphere) uv_map_sphere(v, u, w);
+	if (u < 0 - RT_JS_EPSILON || u > 1 - RT_JS_EPSILON || w < 0 - RT_JS_EPSILON || w > 1 - RT_JS_EPSILON) {
+		rgb[0] = rgb[1] = rgb[2] = NAN;
+		return false;
+	}
+	const long long ui = (long long)xmul(u, (double)T->width);   // (u*width) << 0
+	const long long vi = (long long)xmul(w, (double)T->height);
+	const uint8_t* px = S.texels + (T->texel_off + (unsigned long long)(vi * T->width + ui)) * 3ull;
+	rgb[0] = xdiv((double)px[0], 255.0);
+	rgb[1] = xdiv((double)px[1], 255.0);
+	rgb[2] = xdiv((double)px[2], 255.0);
+	return true;
+}
+
+// FpLcg (src/math/rng/fp-lcg.ts:20-82); `% 1.0` on non-negative values == x - floor(x), exact
+struct RtRng {
+	double s1, s2, s3;
+	bool seeded;
+};
+#define RT_LCG_MUL1 (3532205053565347.0 / 3768278866164713.0)
+#define RT_LCG_TERM1 (3773467585272041.0 / 4435662911655887.0)
+#define RT_LCG_MUL2 (3632519696538149.0 / 4496133748415501.0)
+#define RT_LCG_TERM2 (3396159042346757.0 / 4429161683464229.0)
+#define RT_LCG_MUL3 (4056279137291581.0 / 4272384783187219.0)
+#define RT_LCG_TERM3 (3685311960670787.0 / 3909517015383373.0)
+RT_HD double frac1(double x) { return xsub(x, floor(x)); }
+RT_HD void rng_seed(RtRng& g, double seed) {
+	g.s1 = seed;
+	g.s2 = xmul(seed, RT_LCG_MUL3);
+	g.s3 = xmul(seed, RT_LCG_MUL2);
+	g.seeded = true;
+}
+RT_HD double rng_next(RtRng& g) {
+	const double a = frac1(xadd(xmul(g.s1, RT_LCG_MUL1), RT_LCG_TERM1));
+	const double b = frac1(xadd(xmul(g.s2, RT_LCG_MUL2), RT_LCG_TERM2));
+	const double c = frac1(xadd(xmul(g.s3, RT_LCG_MUL3), RT_LCG_TERM3));
+	g.s1 = xadd(b, c);
+	g.s2 = c;
+	g.s3 = xadd(a, b);
+	return frac1(xadd(xadd(a, b), c));
+}
+
+// ------------------------------------------------------------------ Ray.trace (src/raytracer.ts:168-277)
+// One path for one pixel of one exposure frame.  `dir` is the camera direction (un-normalised, as
+// the reference passes it).  Returns the path colour in `out`, and the entity of the first collision.
+template <bool COUNT>
+RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_in, double pixel_seed,
+                      double* out, int& first_entity, RtCounts& cnt, uint32_t& err) {
+	double refpoint[3] = {F.pos[0], F.pos[1], F.pos[2]};
+	double dir[3] = {dir_in[0], dir_in[1], dir_in[2]};
+	double col[3] = {1.0, 1.0, 1.0};
+	double path_distance = 0.0;
+	int refcount = 0;
+	int cur_substance = F.start_substance;
+	RtRng rng;
+	rng.seeded = false;
+	first_entity = -1;
+
+	int node = F.start_node, octant = F.start_octant;
+	bool have_node = F.start_node >= 0;
+	bool light_hit = false;
+	while (true) {
+		// walker.set_pos_and_dir -> set_position -> setup_cur_node (src/octree_space.ts:188-205,251-278)
+		if (COUNT) cnt.segments++;
+		if (!have_node) {
+			// origin outside the root cube: the root alone, if the ray meets its box going forward
+			const double c[3] = {xadd(S.root_pos[0], xmul(0.5, S.root_size)), xadd(S.root_pos[1], xmul(0.5, S.root_size)),
+			                     xadd(S.root_pos[2], xmul(0.5, S.root_size))};
+			double u1, u2;
+			int i1, i2;
+			if (!exact_box_params(c, S.root_size, refpoint, dir, u1, u2, i1, i2) || !(u1 >= 0 || u2 >= 0)) break;
+			node = 0;
+			octant = -1;
+		}
+		RtCollision ci;
+		const int slot = walk_and_scan<COUNT>(S, node, octant, refpoint, dir, ci, cnt);
+		if (slot < 0) break;  // miss: sky
+		const RtI4 attr = ld(S.slot_attr + slot);
+		if (first_entity < 0) first_entity = attr.x;
+		if (dot3(dir, ci.normal) >= 0) {  // :200-203
+			err |= RT_ERRFLAG_ACUTE;
+			out[0] = col[0]; out[1] = col[1]; out[2] = col[2];
+			return;
+		}
+		const bool is_sphere = (attr.y >> RT_ATTR_TYPE_SHIFT) == 0;
+		const RtMaterial m = S.materials[attr.y & RT_ATTR_MAT_MASK];
+		refcount++;
+		{  // SolidMaterial.alter_ray (src/materials/material_solid.ts:30-36)
+			const RtD4 g = ld(S.slot_geom64 + slot);
+			const double rel[3] = {xsub(ci.point[0], g.x), xsub(ci.point[1], g.y), xsub(ci.point[2], g.z)};
+			double tc[3];
+			if (!texture_color(S, attr.z, is_sphere, rel, tc)) err |= RT_ERRFLAG_TEXTURE;
+			col[0] = xmul(col[0], tc[0]); col[1] = xmul(col[1], tc[1]); col[2] = xmul(col[2], tc[2]);
+			if (COUNT) cnt.shades++;
+		}
+		{
+			const double dd[3] = {xsub(ci.point[0], refpoint[0]), xsub(ci.point[1], refpoint[1]),
+			                      xsub(ci.point[2], refpoint[2])};
+			path_distance = xadd(path_distance, xsqrt(dot3(dd, dd)));  // :210
+		}
+		refpoint[0] = ci.point[0]; refpoint[1] = ci.point[1]; refpoint[2] = ci.point[2];  // :212
+		if (m.flags & RT_MAT_LIGHT) {  // :215-218
+			light_hit = true;
+			break;
+		}
+		const uint32_t response = m.flags & RT_MAT_RESPONSE_MASK;
+		if (response == 0u) {  // REFLECTION :221-237
+			if (!(m.flags & RT_MAT_MIRROR)) {
+				out[0] = col[0]; out[1] = col[1]; out[2] = col[2];
+				return;
+			}
+			{  // vector.reflection (src/math/vector.ts:263-268)
+				const double k = xmul(-dot3(dir, ci.normal), 2.0);
+				dir[0] = xadd(dir[0], xmul(ci.normal[0], k));
+				dir[1] = xadd(dir[1], xmul(ci.normal[1], k));
+				dir[2] = xadd(dir[2], xmul(ci.normal[2], k));
+			}
+			if (m.roughness > 0.0) {  // scatter_ray :121-133, isotropic_sphere_sample vector_utils.ts:8-14
+				if (!rng.seeded) rng_seed(rng, pixel_seed);
+				double rv[3];
+				do {
+					rv[0] = xsub(xmul(rng_next(rng), 2.0), 1.0);
+					rv[1] = xsub(xmul(rng_next(rng), 2.0), 1.0);
+					rv[2] = xsub(xmul(rng_next(rng), 2.0), 1.0);
+				} while (dot3(rv, rv) > 1);
+				if (dot3(rv, ci.normal) < 0) { rv[0] = -rv[0]; rv[1] = -rv[1]; rv[2] = -rv[2]; }
+				const double ka = xsub(1.0, m.roughness);
+				double rf[3] = {xadd(xmul(dir[0], ka), xmul(rv[0], m.roughness)),
+				                xadd(xmul(dir[1], ka), xmul(rv[1], m.roughness)),
+				                xadd(xmul(dir[2], ka), xmul(rv[2], m.roughness))};
+				const double inv = xdiv(1.0, xsqrt(dot3(rf, rf)));
+				dir[0] = xmul(rf[0], inv); dir[1] = xmul(rf[1], inv); dir[2] = xmul(rf[2], inv);
+			}
+			// move_slightly_forward :158-164
+			refpoint[0] = xadd(refpoint[0], xmul(dir[0], 1e-3));
+			refpoint[1] = xadd(refpoint[1], xmul(dir[1], 1e-3));
+			refpoint[2] = xadd(refpoint[2], xmul(dir[2], 1e-3));
+		} else if (response == 1u) {  // TRANSMISSION :238-249
+			refpoint[0] = xadd(refpoint[0], xmul(dir[0], 1e-3));
+			refpoint[1] = xadd(refpoint[1], xmul(dir[1], 1e-3));
+			refpoint[2] = xadd(refpoint[2], xmul(dir[2], 1e-3));
+			const int rf_slot = entity_at_pos(S, refpoint);
+			const int substance = rf_slot >= 0 ? ld(&S.slot_attr[rf_slot].w) : F.default_substance;
+			if (substance >= 0) {  // refract_ray :135-150
+				const double r_ratio = xdiv(S.substances[cur_substance], S.substances[substance]);
+				const double r_ratio_sq = xmul(r_ratio, r_ratio);
+				const double cosine = dot3(dir, ci.normal);
+				const double cosine_sq = xmul(cosine, cosine);
+				const double ref_sine_sq = xmul(xsub(1.0, cosine_sq), r_ratio_sq);
+				if (ref_sine_sq <= 1) {
+					const double ref_cosine = xsqrt(xsub(1.0, ref_sine_sq));
+					const double k = xsub(ref_cosine, cosine);
+					dir[0] = xsub(xmul(dir[0], r_ratio), xmul(ci.normal[0], k));
+					dir[1] = xsub(xmul(dir[1], r_ratio), xmul(ci.normal[1], k));
+					dir[2] = xsub(xmul(dir[2], r_ratio), xmul(ci.normal[2], k));
+				} else {
+					const double k = xmul(-dot3(dir, ci.normal), 2.0);
+					dir[0] = xadd(dir[0], xmul(ci.normal[0], k));
+					dir[1] = xadd(dir[1], xmul(ci.normal[1], k));
+					dir[2] = xadd(dir[2], xmul(ci.normal[2], k));
+				}
+				cur_substance = substance;
+			}
+		} else {  // BOTH / default :250-251
+			out[0] = col[0]; out[1] = col[1]; out[2] = col[2];
+			return;
+		}
+		if (refcount >= F.refmax) {  // :256-263
+			out[0] = out[1] = out[2] = 0.0;
+			return;
+		}
+		have_node = node_at_pos(S, refpoint, node, octant);  // :254 (re-seed from the root)
+	}
+	if (!light_hit) {  // :267-271, SkySphere.get_color (src/sky/sky_sphere.ts:22-27)
+		double sc[3];
+		if (!texture_color(S, F.sky_texture, true, dir, sc)) err |= RT_ERRFLAG_TEXTURE;
+		out[0] = xmul(col[0], sc[0]); out[1] = xmul(col[1], sc[1]); out[2] = xmul(col[2], sc[2]);
+		return;
+	}
+	// inverse square law :273-275
+	const double t = xmul(path_distance, F.attenuation);
+	const double isl = xdiv(1.0, xadd(RT_JS_EPSILON, xmul(t, t)));
+	out[0] = xmul(col[0], isl); out[1] = xmul(col[1], isl); out[2] = xmul(col[2], isl);
+}
+
+// ------------------------------------------------------------------ one pixel, all exposure frames
+// Raytracer.trace_frame body (src/raytracer.ts:318-329) + ExposureBuffer.set_color_i
+// (src/view/exposure_buffer.ts:77-91) for n_frames consecutive frames.
+template <bool COUNT>
+RT_HD void render_pixel(const RtDevScene& S, const RtFrame& F, int x, int y, RtCounts& cnt, uint32_t& err) {
+	// camera direction: get_dir_for_each_pixel (src/view/camera.ts:207-250) through the host-built
+	// tables of the accumulated scan rotations
+	const RtD4 fr = ld(F.row_fr + y);
+	const RtD2 cs = ld(F.col_cs + x);
+	const double dir[3] = {xadd(xmul(fr.x, cs.x), xmul(F.lf[0], cs.y)), xadd(xmul(fr.y, cs.x), xmul(F.lf[1], cs.y)),
+	                       xadd(xmul(fr.z, cs.x), xmul(F.lf[2], cs.y))};
+	const size_t pix = (size_t)y * F.width + x;
+	float* o = F.rgb + pix * 3;
+	float px[3] = {0.f, 0.f, 0.f};
+	if (F.frame_first > 0) { px[0] = o[0]; px[1] = o[1]; px[2] = o[2]; }
+	int first_entity = -1;
+	for (uint32_t f = 0; f < F.n_frames; f++) {
+		const uint32_t frame_count = F.frame_first + f;
+		const double seed = xadd(xadd(F.rng_seed, (double)pix),
+		                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
+		double c[3];
+		trace_path<COUNT>(S, F, dir, seed, c, first_entity, cnt, err);
+		const double w = xdiv(1.0, (double)(1u + frame_count));
+		const double w1 = xsub(1.0, w);
+#pragma unroll
+		for (int k = 0; k < 3; k++) px[k] = (float)xadd(xmul(c[k], w), xmul((double)px[k], w1));
+	}
+	o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
+	if (F.first_ids) F.first_ids[pix] = first_entity;
+}

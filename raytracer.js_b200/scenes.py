@@ -1,0 +1,106 @@
+"""Synthetic scene recipes of the measurement plan: harness code, deterministic through
+FpLcg so that the same scene can be rebuilt anywhere (tests feed the same entity list to the oracle)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from .camera import Camera, CameraConfig
+from .color import Color
+from .entity import BoxEntity, Entity, SphereEntity
+from .geometry import point
+from .material import ResponseType, SolidMaterial
+from .octree import Octree
+from .octree_entity import add_entity_to_octree, new_entity_octree
+from .octree_space import OctreeDim
+from .rng import FpLcg
+from .sky import SkySphere
+from .substance import SUBSTANCE_AIR, SUBSTANCE_GLASS, SUBSTANCE_WATER, Substance
+from .texture import ImageTexture, SolidTexture, Texture
+
+BENCH_CAMERA_POS = (0.5013, 0.4987, 0.5021)  # strictly inside the root, off dyadic planes
+
+
+@dataclass
+class SceneBundle:
+    tree: Octree
+    entities: List[Entity]          # insertion order == entity id of the oracle
+    sky: SkySphere
+    default_substance: Substance
+    refmax: int
+    materials: List[SolidMaterial] = field(default_factory=list)
+    description: str = ""
+
+
+def bench_camera(width: int, height: int, pos=BENCH_CAMERA_POS, yaw_deg: float = 30.0, pitch: float = 0.0) -> Camera:
+    """The demo pose (src/main.ts:353-366): 90 x 90 degrees, yaw 30 degrees."""
+    conf = CameraConfig(fov_v=math.pi * 0.5, fov_h=math.pi * 0.5, screen_w=width, screen_h=height,
+                        rot_v=math.pi / 30, rot_h=math.pi / 30, flags={"vertical_locked": True})
+    return Camera(conf, point(*pos), pitch, math.pi / 180 * yaw_deg)
+
+
+def _new_root() -> Octree:
+    return new_entity_octree(OctreeDim(point(0, 0, 0), 1.0), None)
+
+
+DIFFUSE = dict(response=ResponseType.REFLECTION, light=False, mirror=False, roughness=0.0)
+
+
+def random_spheres(n: int, dmin: float = 0.002, dmax: float = 0.006, seed: float = 42.0, mix: str = "diffuse",
+                   box_fraction: float = 0.0, textures: Optional[List[Texture]] = None,
+                   max_in_depth: int = 16) -> SceneBundle:
+    """Config 1/2/4 generator.  Per entity the draws are, in order: d, cx, cy, cz, [kind], material pick,
+    texture colour r,g,b (or texture pick).  Sphere i: d = dmin + u*(dmax-dmin), centre = d/2 + u*(1-d)
+    per axis (AABB inside the unit root, as max_out_depth: 0 requires).
+    mix 'diffuse': every material is SolidMaterial(REFLECTION, light=False, mirror=False, 0) (config 1);
+    mix 'mirrors': 70% smooth mirror, 15% diffuse, 10% rough mirror 0.5, 5% lights x5 (config 2/4)."""
+    rng = FpLcg(seed)
+    tree = _new_root()
+    if mix == "diffuse":
+        mats = [SolidMaterial(ResponseType.REFLECTION, False, False, 0.0)]
+        cum = [1.0]
+    elif mix == "mirrors":
+        mats = [SolidMaterial(ResponseType.REFLECTION, False, True, 0.0),
+                SolidMaterial(ResponseType.REFLECTION, False, False, 0.0),
+                SolidMaterial(ResponseType.REFLECTION, False, True, 0.5),
+                SolidMaterial(ResponseType.REFLECTION, True, False, 0.0)]
+        cum = [0.70, 0.85, 0.95, 1.0]
+    else:
+        raise ValueError(mix)
+    entities: List[Entity] = []
+    cfg = {"max_in_depth": max_in_depth, "max_out_depth": 0}
+    for _ in range(n):
+        d = dmin + rng.next() * (dmax - dmin)
+        c = [d / 2 + rng.next() * (1 - d) for _ in range(3)]
+        is_box = box_fraction > 0 and rng.next() < box_fraction
+        mi = 0
+        if len(mats) > 1:
+            u = rng.next()
+            while mi < len(cum) - 1 and u > cum[mi]:
+                mi += 1
+        mat = mats[mi]
+        if textures and not mat.light_source and not is_box:
+            tex = textures[int(rng.next() * len(textures))]
+        else:
+            k = 5.0 if mat.light_source else 1.0
+            tex = SolidTexture(Color(rng.next() * k, rng.next() * k, rng.next() * k, 1.0))
+        cls = BoxEntity if is_box else SphereEntity
+        e = cls(None, mat, tex, SUBSTANCE_AIR, point(*c), d)
+        add_entity_to_octree(tree, e, cfg)
+        entities.append(e)
+    sky = SkySphere(SolidTexture(Color(0.2, 0.2, 0.7, 1.0)))  # the demo's fallback sky colour (main.ts:378)
+    return SceneBundle(tree, entities, sky, SUBSTANCE_AIR, refmax=1 if mix == "diffuse" else 4, materials=mats,
+                       description=f"{n} random spheres d in [{dmin},{dmax}], seed {seed}, mix {mix}")
+
+
+def checker_texture(width: int, height: int, seed: int = 1) -> ImageTexture:
+    """Array-backed image texture: random-colour checker with per-texel noise (no file IO)."""
+    rs = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:height, 0:width]
+    cells = ((xx // 16) + (yy // 16)) % 2
+    a, b = rs.randint(32, 255, 3), rs.randint(32, 255, 3)
+    img = np.where(cells[..., None] == 0, a, b).astype(np.int32) + rs.randint(-16, 16, (height, width, 3))
+    return ImageTexture(np.clip(img, 0, 255).astype(np.uint8), Color(0, 0, 0, 1))

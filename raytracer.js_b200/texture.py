@@ -1,0 +1,53 @@
+"""Textures (src/texture/texture.ts, texture_solid.ts, texture_image.ts).
+
+The nearest-texel lookup itself (texture_image.ts:40-63) runs on the GPU; the host objects only carry
+the data.  ImageTexture here is array-backed: the reference's decoder (`new Image()` + canvas,
+texture_image.ts:76-136) is browser-only and out of scope."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .color import Color
+
+
+class TextureError(Exception):
+    pass
+
+
+class Texture:
+    def get_size(self) -> Optional[Tuple[int, int]]:
+        return None
+
+
+class SolidTexture(Texture):
+    def __init__(self, color: Color):
+        self.color = color
+
+    def get_color(self, _u: float = 0.0, _v: float = 0.0) -> Color:
+        return self.color
+
+
+class ImageTexture(Texture):
+    """`pixels`: uint8 array [height, width, 3] as load_image would have decoded it (row 0 first), or
+    None for an image that is not (yet) loaded, which answers with the fallback colour."""
+
+    def __init__(self, pixels: Optional[np.ndarray], fallback_color: Color, horizontal_flip=False,
+                 vertical_flip=False):
+        self.fallback_color = fallback_color
+        self.image_data: Optional[np.ndarray] = None
+        self.width = self.height = 0
+        if pixels is not None:
+            px = np.ascontiguousarray(pixels, dtype=np.uint8)
+            if px.ndim != 3 or px.shape[2] != 3:
+                raise TextureError("pixels must be uint8 [height, width, 3]")
+            if horizontal_flip:
+                px = px[:, ::-1]
+            if vertical_flip:
+                px = px[::-1]
+            self.image_data = np.ascontiguousarray(px)
+            self.height, self.width = px.shape[:2]
+
+    def get_size(self):
+        return (self.width, self.height) if self.image_data is not None else None

@@ -1,0 +1,69 @@
+// tests/hostsim/rt_hostsim.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE, NOT A FALLBACK.
+//
+// Compiles the kernel body of librt_b200 (raytracer.js_b200/csrc/rt_trace.cuh, all RT_HD) for the
+// host so that its traversal / confirmation / shading logic can be checked against the oracle on a
+// box without a GPU (`pytest -m "not gpu"`).  It is built only by tests/ into tests/hostsim/, is never
+// linked into or loaded by the package, and the C ABI in include/rt_b200.h has no path to it.
+#include <thread>
+
+#include "../../raytracer.js_b200/csrc/rt_host.h"
+#include "../../raytracer.js_b200/csrc/rt_trace.cuh"
+
+extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, const rt_params* prm, int n_threads,
+                              float* rgb, int32_t* ids, rt_counters* counters, char* errbuf, int errlen) {
+	std::string err;
+	RtHostScene hs;
+	rt_status st = rt_pack_scene(sc, hs, err);
+	if (!st) st = rt_check_render_args(true, (uint32_t)hs.textures.size(), (uint32_t)hs.substances.size(), cam, prm, err);
+	RtFrame F{};
+	if (!st) st = rt_fill_frame(hs, cam, prm, F, err);
+	if (st) {
+		snprintf(errbuf, errlen, "%s", err.c_str());
+		return (int)st;
+	}
+	std::vector<RtD2> col;
+	std::vector<RtD4> row;
+	rt_build_camera_tables(*cam, col, row);
+	RtDevScene S{};
+	S.node_geom = hs.node_geom.data(); S.node_link = hs.node_link.data(); S.node_child = hs.node_child.data();
+	S.slot_geom = hs.slot_geom.data(); S.slot_geom64 = hs.slot_geom64.data(); S.slot_attr = hs.slot_attr.data();
+	S.materials = hs.materials.data(); S.textures = hs.textures.data(); S.substances = hs.substances.data();
+	S.texels = hs.texels.data();
+	for (int k = 0; k < 3; k++) S.root_pos[k] = hs.root_pos[k];
+	S.root_size = hs.root_size;
+	S.n_nodes = (int)hs.node_geom.size();
+	S.n_slots = (int)hs.slot_geom.size();
+	S.err_l = hs.err_l;
+	F.col_cs = col.data();
+	F.row_fr = row.data();
+	F.rgb = rgb;
+	F.first_ids = ids;
+	F.tile_rank = 0;
+	F.tile_world = 1;
+	if (n_threads < 1) n_threads = 1;
+	std::vector<RtCounts> part(n_threads, RtCounts{0, 0, 0, 0, 0});
+	std::vector<uint32_t> errs(n_threads, 0);
+	auto work = [&](int t) {
+		for (int y = t; y < F.height; y += n_threads)
+			for (int x = 0; x < F.width; x++) {
+				RtCounts c = {0, 0, 0, 0, 0};
+				render_pixel<true>(S, F, x, y, c, errs[t]);
+				part[t].segments += c.segments; part[t].nodes += c.nodes; part[t].tests += c.tests;
+				part[t].shades += c.shades; part[t].confirms += c.confirms;
+			}
+	};
+	std::vector<std::thread> th;
+	for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+	for (auto& t : th) t.join();
+	if (counters) {
+		memset(counters, 0, sizeof *counters);
+		counters->paths = (uint64_t)F.width * F.height * F.n_frames;
+		for (int t = 0; t < n_threads; t++) {
+			counters->segments += part[t].segments; counters->nodes += part[t].nodes; counters->tests += part[t].tests;
+			counters->shades += part[t].shades; counters->confirms += part[t].confirms;
+			if (errs[t] & RT_ERRFLAG_TEXTURE) counters->texture_errors = 1;
+			if (errs[t] & RT_ERRFLAG_ACUTE) counters->acute_warnings = 1;
+		}
+	}
+	return 0;
+}

@@ -1,0 +1,127 @@
+"""Kernel-body logic against the oracle WITHOUT a GPU: tests/hostsim compiles csrc/rt_trace.cuh (the
+RT_HD functions the CUDA kernel calls) for the host.  Test infrastructure only; the GPU parity tests
+proper are tests/test_gpu_parity.py (-m gpu)."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle as orc
+import raytracer_js_b200 as rt
+from raytracer_js_b200 import scenes
+
+from util import compare, flat_of, hostsim_render, insertion_ids, make_params, oracle_render, oracle_scene
+
+
+def cameras(width, height, pos=scenes.BENCH_CAMERA_POS, yaw=30.0, pitch=0.0):
+    cam = scenes.bench_camera(width, height, pos, yaw, pitch)
+    ocam = orc.Camera(fov_v=math.pi / 2, fov_h=math.pi / 2, screen_w=width, screen_h=height, pos=pos,
+                      init_v_angle=pitch, init_h_angle=math.pi / 180 * yaw, vertical_locked=True)
+    b = ocam.basis()
+    assert list(b["fr"]) == cam.norm_fr.v and list(b["lf"]) == cam.norm_lf.v and list(b["up"]) == cam.norm_up.v
+    return cam, ocam
+
+
+def run_both(bundle, width, height, n_frames=1, frame_first=0, pos=scenes.BENCH_CAMERA_POS, yaw=30.0, pitch=0.0,
+             refmax=None):
+    flat = flat_of(bundle)
+    cam, ocam = cameras(width, height, pos, yaw, pitch)
+    prm = make_params(flat, bundle, n_frames=n_frames, frame_first=frame_first, refmax=refmax)
+    rgb, ids, cnt = hostsim_render(flat, cam, prm)
+    ids = insertion_ids(flat, bundle, ids)
+    os_ = oracle_scene(flat, bundle)
+    orgb, oids, _, tot = oracle_render(os_, ocam, flat, bundle, prm, fixed_extents=True)
+    return compare(rgb, ids, orgb, oids), cnt, tot, (rgb, ids, orgb, oids)
+
+
+def test_camera_tables_match_generator():
+    """The closed scan tables (rt_host.h: rt_build_camera_tables) against the iterated generator."""
+    W = H = 64
+    cam, ocam = cameras(W, H)
+    xy, d, n = ocam.dirs(fixed_extents=False)
+    assert n == W * H
+    # host generator of the product's Camera yields the same sequence as the oracle's
+    mine = list(cam.get_dir_for_each_pixel())
+    assert [(x, y) for x, y, _ in mine] == [tuple(p) for p in xy.tolist()]
+    np.testing.assert_array_equal(np.array([v.v for _, _, v in mine]), d)
+
+
+def test_diffuse_spheres_primary(oracle):
+    b = scenes.random_spheres(1500, 0.01, 0.04, seed=42.0, mix="diffuse")
+    res, cnt, tot, _ = run_both(b, 96, 96)
+    assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0, res
+    assert res["rgb_max_abs"] < 1e-6
+    # the work counters the roofline is built from are the oracle's
+    for k in ("segments", "nodes", "tests", "shades"):
+        assert cnt[k] == tot[k], (k, cnt[k], tot[k])
+    assert tot["would_throw"] == 0
+
+
+def test_mirrors_lights_rough_boxes_multiframe(oracle):
+    b = scenes.random_spheres(800, 0.02, 0.08, seed=11.0, mix="mirrors", box_fraction=0.25)
+    res, cnt, tot, (rgb, ids, orgb, oids) = run_both(b, 80, 80, n_frames=3)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
+    assert cnt["segments"] == tot["segments"] and cnt["shades"] == tot["shades"]
+    assert (oids >= 0).mean() > 0.3  # the scene is actually hit
+
+
+def test_camera_outside_root_sees_only_root_list(oracle):
+    # origin outside the root cube => only the root's own list is tested
+    b = scenes.random_spheres(400, 0.02, 0.2, seed=3.0, mix="diffuse")
+    res, cnt, tot, (rgb, ids, orgb, oids) = run_both(b, 48, 48, pos=(-0.5, 0.5, 0.5), yaw=0.0)
+    assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0
+    root_entities = {i for i, e in enumerate(b.entities) if e.octree is b.tree}
+    assert set(np.unique(oids[oids >= 0]).tolist()) <= root_entities
+    assert cnt["nodes"] == tot["nodes"]
+
+
+def test_transmission_and_substances(oracle):
+    """TRANSMISSION materials, entity_at_pos lookups, undefined substances (src/raytracer.ts:238-249)."""
+    rng = rt.FpLcg(5.0)
+    tree = rt.new_entity_octree(rt.OctreeDim(rt.point(0, 0, 0), 1.0), None)
+    glass = rt.SolidMaterial(rt.ResponseType.TRANSMISSION, False, False, 0)
+    mirror = rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0)
+    light = rt.SolidMaterial(rt.ResponseType.REFLECTION, True, False, 0)
+    both = rt.SolidMaterial(rt.ResponseType.BOTH, False, False, 0)
+    subs = [rt.SUBSTANCE_AIR, rt.SUBSTANCE_WATER, rt.SUBSTANCE_GLASS, None]
+    ents = []
+    for i in range(300):
+        d = 0.03 + rng.next() * 0.12
+        c = [d / 2 + rng.next() * (1 - d) for _ in range(3)]
+        m = [glass, glass, mirror, light, both][int(rng.next() * 5)]
+        tex = rt.SolidTexture(rt.Color(0.3 + rng.next(), 0.3 + rng.next(), 0.3 + rng.next(), 1))
+        cls = rt.BoxEntity if rng.next() < 0.3 else rt.SphereEntity
+        e = cls(None, m, tex, subs[int(rng.next() * 4)], rt.point(*c), d)
+        rt.add_entity_to_octree(tree, e, {"max_in_depth": 16, "max_out_depth": 0})
+        ents.append(e)
+    b = scenes.SceneBundle(tree, ents, rt.SkySphere(rt.SolidTexture(rt.Color(0.2, 0.2, 0.7, 1))), rt.SUBSTANCE_AIR, 6)
+    res, cnt, tot, _ = run_both(b, 72, 72, pos=(0.013, 0.487, 0.021), yaw=10.0)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
+    assert cnt["segments"] == tot["segments"]
+    assert tot["within_tests"] > 0
+
+
+def test_image_textures_and_sky(oracle):
+    texs = [scenes.checker_texture(64, 32, seed=s) for s in (1, 2, 3)]
+    b = scenes.random_spheres(600, 0.03, 0.1, seed=9.0, mix="mirrors", textures=texs)
+    b.sky = rt.SkySphere(scenes.checker_texture(128, 64, seed=4))
+    res, cnt, tot, _ = run_both(b, 80, 80)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
+    assert tot["texture_errors"] == 0
+
+
+def test_reference_extents_flag(oracle):
+    b = scenes.random_spheres(50, 0.05, 0.2, seed=1.0)
+    flat = flat_of(b)
+    cam = scenes.bench_camera(64, 48)
+    prm = make_params(flat, b)
+    with pytest.raises(IndexError):  # ExposureBuffer.check_bounds, exposure_buffer.ts:181-186
+        hostsim_render(flat, cam, prm, reference_extents=True)
+    rgb, ids, _ = hostsim_render(flat, cam, prm)  # the intent mapping renders non-square frames
+    os_ = oracle_scene(flat, b)
+    ocam = orc.Camera(math.pi / 2, math.pi / 2, 64, 48, scenes.BENCH_CAMERA_POS, 0.0, math.pi / 6, vertical_locked=True)
+    with pytest.raises(IndexError):
+        oracle_render(os_, ocam, flat, b, prm, fixed_extents=False)
+    orgb, oids, _, _ = oracle_render(os_, ocam, flat, b, prm, fixed_extents=True)
+    res = compare(rgb, insertion_ids(flat, b, ids), orgb, oids)
+    assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0
