@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s and frame ms of the per-pixel ray hot path on BASELINE.json's headline config:
+1920x1080, 1 spp, 10 000 random spheres (d in [0.002,0.006], FpLcg seed 42), octree from the host
+builder, diffuse + sky, refmax 1.  A "step" is one trace_frame() of that frame.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU): the frame is cut into interleaved 16x16 tiles, every
+rank renders its tiles from a replica of the scene (flat buffers broadcast from rank 0 with NCCL), the
+tile buffers are all-gathered over NCCL/NVLink and rank 0 de-interleaves them ("scaling": "strong").
+Prints ONE JSON line on rank 0.  See DESIGN.md §Measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 1920, 1080
+N_SPHERES, DMIN, DMAX, SCENE_SEED = 10000, 0.002, 0.006, 42.0
+WORKLOAD = "configs[1]: 1920x1080, 1 spp, 10k random spheres d in [0.002,0.006] (FpLcg seed 42), octree, diffuse + sky, refmax 1"
+METRIC = "Mrays/s (ray segments traced per second), 1080p 10k-sphere octree scene"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_bundle():
+    from raytracer_js_b200 import scenes
+    return scenes.random_spheres(N_SPHERES, DMIN, DMAX, seed=SCENE_SEED, mix="diffuse")
+
+
+def oracle_setup(bundle, flat, n_frames=1):
+    """cpu_baseline / --impl reference only: the CPU restatement of the reference on the same scene."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle as orc
+    from raytracer_js_b200 import scenes
+    from util import make_params, oracle_scene
+    orc.build()
+    oscene = oracle_scene(flat, bundle)
+    ocam = orc.Camera(math.pi / 2, math.pi / 2, WIDTH, HEIGHT, scenes.BENCH_CAMERA_POS, 0.0, math.pi / 6,
+                      vertical_locked=True)
+    prm = make_params(flat, bundle, n_frames=n_frames)
+    return orc, oscene, ocam, prm
+
+
+def time_oracle(bundle, flat, threads: int, steps: int, warmup: int):
+    from util import oracle_render  # noqa: E402  (tests/ is on sys.path after oracle_setup)
+    orc, oscene, ocam, prm = oracle_setup(bundle, flat)
+    for _ in range(warmup):
+        oracle_render(oscene, ocam, flat, bundle, prm, fixed_extents=True, n_threads=threads)
+    t0 = time.perf_counter()
+    seg = 0
+    for _ in range(steps):
+        _, _, _, tot = oracle_render(oscene, ocam, flat, bundle, prm, fixed_extents=True, n_threads=threads)
+        seg += tot["segments"]
+    dt = time.perf_counter() - t0
+    return seg / dt / 1e6, dt / steps * 1e3, tot
+
+
+def run_reference(args, rank: int):
+    """The reference's own CPU implementation of the path (no JS runtime exists here or on the GPU box,
+    so this is the double-precision C++ restatement, oracle/), all host threads, same config."""
+    if rank != 0:
+        return
+    import raytracer_js_b200 as rt
+    bundle = build_bundle()
+    flat = rt.flatten_scene(bundle.tree, extra_textures=[bundle.sky.texture], extra_substances=[bundle.default_substance])
+    cores = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    mrays, ms, _ = time_oracle(bundle, flat, cores, args.steps, args.warmup)
+    sample = f"each step = the full {WIDTH}x{HEIGHT} frame ({WIDTH * HEIGHT} primary rays), {cores} threads over pixel chunks"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "restated C++ float64 port of the TypeScript reference (oracle/), not Node"},
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import raytracer_js_b200 as rt
+    from raytracer_js_b200 import _native as N
+    from raytracer_js_b200 import scenes
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = N.load()
+    ctx = C.c_void_p()
+    N.check(None, lib.rt_create(local_rank, C.byref(ctx)))
+    stream = torch.cuda.current_stream()
+    N.check(ctx, lib.rt_set_stream(ctx, C.c_void_p(stream.cuda_stream)))
+
+    # ---- scene: built on rank 0 by the host API, flat buffers broadcast with NCCL, one replica per GPU
+    bundle = flat = None
+    if rank == 0:
+        bundle = build_bundle()
+        flat = rt.flatten_scene(bundle.tree, extra_textures=[bundle.sky.texture],
+                                extra_substances=[bundle.default_substance])
+        sky_tex = flat.texture_index(bundle.sky.texture)
+        def_sub = flat.substance_index(bundle.default_substance)
+    scene_bcast_bytes = 0
+    if world > 1:
+        meta = [None]
+        if rank == 0:
+            names = sorted(flat.arrays)
+            meta = [{"names": names, "dtypes": [str(flat.arrays[n].dtype) for n in names],
+                     "shapes": [flat.arrays[n].shape for n in names], "sky": sky_tex, "sub": def_sub}]
+        dist.broadcast_object_list(meta, src=0)
+        m = meta[0]
+        sizes = [int(np.prod(s)) * np.dtype(d).itemsize for s, d in zip(m["shapes"], m["dtypes"])]
+        offs = np.concatenate([[0], np.cumsum([(s + 15) // 16 * 16 for s in sizes])]).astype(np.int64)
+        payload = torch.empty(int(offs[-1]), dtype=torch.uint8, device=dev)
+        if rank == 0:
+            host = np.zeros(int(offs[-1]), np.uint8)
+            for n, o, s in zip(m["names"], offs, sizes):
+                host[o:o + s] = np.ascontiguousarray(flat.arrays[n]).view(np.uint8).reshape(-1)
+            payload.copy_(torch.from_numpy(host))
+        dist.broadcast(payload, src=0)  # NCCL over NVLink
+        scene_bcast_bytes = int(offs[-1])
+        if rank != 0:
+            host = payload.cpu().numpy()
+            flat = rt.FlatScene()
+            for n, o, s, d, shp in zip(m["names"], offs, sizes, m["dtypes"], m["shapes"]):
+                flat.arrays[n] = host[o:o + s].view(np.dtype(d)).reshape(shp).copy()
+            sky_tex, def_sub = m["sky"], m["sub"]
+    desc = flat.desc()
+    N.check(ctx, lib.rt_scene_upload(ctx, C.byref(desc)))
+
+    cam = scenes.bench_camera(WIDTH, HEIGHT)
+    cd = rt.camera_desc(cam)
+    prm = N.Params()
+    prm.refmax, prm.sky_texture, prm.default_substance = 1, sky_tex, def_sub
+    prm.distance_attenuation_factor, prm.n_frames, prm.frame_first, prm.rng_seed = 1.0, 1, 0, 1.0
+    prm.precision = N.RT_PRECISION_F32
+
+    npx = WIDTH * HEIGHT
+    frame = torch.zeros(npx * 3, dtype=torch.float32, device=dev)
+    tpr = lib.rt_tiles_per_rank(WIDTH, HEIGHT, world)
+    tiles = torch.zeros(tpr * 256 * 3, dtype=torch.float32, device=dev) if world > 1 else None
+    gathered = torch.zeros(world * tpr * 256 * 3, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(flags=0):
+        """One frame with everything resident in HBM."""
+        if world == 1:
+            N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), flags, C.c_void_p(frame.data_ptr()), None))
+        else:
+            N.check(ctx, lib.rt_render_tiles_device(ctx, C.byref(cd), C.byref(prm), flags, rank, world,
+                                                    C.c_void_p(tiles.data_ptr()), None))
+            dist.all_gather_into_tensor(gathered, tiles)  # tile exchange over NCCL / NVLink
+            if rank == 0:
+                N.check(ctx, lib.rt_untile_device(ctx, WIDTH, HEIGHT, world, C.c_void_p(gathered.data_ptr()),
+                                                  C.c_void_p(frame.data_ptr())))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- work counters of one frame (untimed, counting kernel variant): what the roofline is built from
+    step(N.RT_RENDER_COUNTERS)
+    cnt = N.Counters()
+    N.check(ctx, lib.rt_get_counters(ctx, C.byref(cnt)))
+    c = torch.tensor([cnt.paths, cnt.segments, cnt.nodes, cnt.tests, cnt.shades], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(c)
+    paths, segments, nodes, tests, shades = (int(x) for x in c.tolist())
+    # ALGORITHMIC bytes: 64 B per node returned by the walker order, 16 B per entity hit
+    # test, 16 B per shaded hit, 12 B per pixel store.  The counters count the REFERENCE's access pattern
+    # (tests/test_gpu_parity.py asserts they equal the oracle's), not this kernel's own traffic.
+    algo_bytes = 64 * nodes + 16 * tests + 16 * shades + 12 * paths
+    bytes_per_segment = algo_bytes / segments
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, per-step CUDA events on the launching stream, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.rt_launch_count(ctx)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in evs:
+        N.check(ctx, lib.rt_flush_l2(ctx))
+        a.record(stream)
+        step()
+        b.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = int(lib.rt_launch_count(ctx) - l0)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    tot_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tot_ms.item()) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    value = segments / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with HOST buffers: camera tables H2D + kernel + full frame D2H
+    e2e = None
+    if world == 1:
+        host_rgb = np.zeros(npx * 3, np.float32)
+        N.check(ctx, lib.rt_host_register(ctx, host_rgb.ctypes.data, host_rgb.nbytes))  # pinned, as the N-API shim does
+        for _ in range(3):
+            N.check(ctx, lib.rt_render(ctx, C.byref(cd), C.byref(prm), 0, host_rgb.ctypes.data, None, None))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            N.check(ctx, lib.rt_render(ctx, C.byref(cd), C.byref(prm), 0, host_rgb.ctypes.data, None, None))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert np.array_equal(host_rgb, frame.cpu().numpy()), "host path and device path disagree"
+        N.check(ctx, lib.rt_host_unregister(ctx, host_rgb.ctypes.data))
+        e2e = {"value": segments * args.steps / dt / 1e6, "unit": "Mrays/s", "frame_ms": dt / args.steps * 1e3,
+               "h2d_bytes_per_step": WIDTH * 16 + HEIGHT * 32 + 80, "d2h_bytes_per_step": npx * 12 + 68}
+    else:
+        # multi-GPU end to end: frame assembled on rank 0 and read back to pinned host memory every step
+        host_t = torch.empty(npx * 3, dtype=torch.float32, pin_memory=True) if rank == 0 else None
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+            if rank == 0:
+                host_t.copy_(frame, non_blocking=False)
+        barrier()
+        dt = time.perf_counter() - t0
+        e2e = {"value": segments * args.steps / dt / 1e6, "unit": "Mrays/s", "frame_ms": dt / args.steps * 1e3,
+               "h2d_bytes_per_step": (WIDTH * 16 + HEIGHT * 32 + 80) * world, "d2h_bytes_per_step": npx * 12}
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    kernel_ms = ms_per_step  # at N=1 the step IS the one render kernel
+    achieved = algo_bytes / world / (kernel_ms * 1e-3) / 1e9 if world == 1 else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("rt_render_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": "flushed (256 MiB memset) before every timed step, outside its event pair",
+                   "timing": "per-step CUDA events on the launching stream, summed over K steps, max over ranks",
+                   "parallelism": f"interleaved 16x16 tiles over {world} GPU(s), scene replicated",
+                   "segments_per_step": segments, "primary_paths_per_s": paths / (ms_per_step * 1e-3),
+                   "frame_ms_kernel": ms_per_step, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+                   "scene_broadcast_bytes": scene_bcast_bytes,
+                   "precision": "float32 search + float64 confirmation/shading of the found hit"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_segment": bytes_per_segment,
+                     "per_segment": {"nodes": nodes / segments, "tests": tests / segments, "shades": shades / segments},
+                     "note": "algorithmic bytes follow the REFERENCE's access pattern (64 B/node + 16 B/test + 16 B/shade + "
+                             "12 B/pixel); the scene (~1 MB) is L2/L1 resident, so achieved may exceed the HBM peak"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        mrays, ms, tot = time_oracle(bundle, flat, 1, 1, 0)
+        out["cpu_baseline"] = {"value": mrays, "unit": "Mrays/s", "cores": 1, "kind": "port", "frame_ms": ms,
+                               "sample": f"one full {WIDTH}x{HEIGHT} frame ({tot['segments']} segments), 1 thread "
+                                         "(the reference renderer is single-threaded)"}
+        same = all(tot[k] == v for k, v in (("segments", segments), ("nodes", nodes), ("tests", tests), ("shades", shades)))
+        out["roofline"]["counters_equal_oracle"] = bool(same)
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

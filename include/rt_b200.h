@@ -190,7 +190,29 @@ rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* p
 rt_status rt_get_counters(rt_ctx* ctx, rt_counters* counters);
 rt_status rt_synchronize(rt_ctx* ctx);
 
+/* ---- multi-GPU tile sharding ------------------------------------------------------------------ */
+/* The frame is cut into 16x16-pixel tiles numbered row-major; rank r of `world` owns the tiles t with
+ * t % world == r (interleaved, to balance sky against dense regions).  One ctx (one process) per GPU
+ * holds a replica of the scene.  rt_render_tiles_device writes this rank's tiles tile-major:
+ * tiles_dev[k][16*16][3] for its k-th tile (t = r + k*world), rt_tiles_per_rank() tiles in all (the
+ * last may be unused); exposure accumulation (frame_first > 0) stays local in that buffer.  After the
+ * ranks' buffers were gathered rank-major (an NCCL all-gather / gather over NVLink, done by the
+ * caller), rt_untile_device scatters them into the [height][width][3] frame. */
+uint32_t rt_tiles_per_rank(uint32_t width, uint32_t height, uint32_t world);
+rt_status rt_render_tiles_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* params, uint32_t render_flags,
+                                 uint32_t rank, uint32_t world, float* tiles_dev, int32_t* tile_ids_dev);
+rt_status rt_untile_device(rt_ctx* ctx, uint32_t width, uint32_t height, uint32_t world, const float* gathered_dev,
+                           float* rgb_dev);
+
+/* ---- host buffer pinning ---------------------------------------------------------------------- */
+/* Page-lock a caller-owned buffer (e.g. the ExposureBuffer's Float32Array backing store) so that
+ * rt_render's copies run at full PCIe rate.  Optional; unregister before freeing the buffer. */
+rt_status rt_host_register(rt_ctx* ctx, void* ptr, size_t bytes);
+rt_status rt_host_unregister(rt_ctx* ctx, void* ptr);
+
 /* ---- device timing on the ctx stream (CUDA events) ------------------------------------------- */
+/* Benchmark hygiene: overwrite a scratch buffer larger than the 126 MB L2 on the ctx stream. */
+rt_status rt_flush_l2(rt_ctx* ctx);
 rt_status rt_timer_start(rt_ctx* ctx);
 rt_status rt_timer_stop(rt_ctx* ctx, float* elapsed_ms); /* synchronises */
 /* Number of kernels this library launched on the ctx since rt_create. */

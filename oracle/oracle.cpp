@@ -1151,8 +1151,10 @@ int32_t orc_render(void* scene_h, void* camera_h, const orc_config* cfg_in, int3
 			FpLcg local_rng;
 			Totals& tot = part[tid];
 			const size_t n = px.size();
-			const size_t lo = n * tid / n_threads, hi = n * (tid + 1) / n_threads;
-			for (size_t i = lo; i < hi; i++) {
+			// rng_mode 1 only: pixels are independent, so threads take interleaved chunks of the scan order
+			const size_t chunk = 256;
+			for (size_t i = 0; i < n; i++) {
+				if (n_threads > 1 && (i / chunk) % (size_t)n_threads != (size_t)tid) continue;
 				const CamPixel& p = px[i];
 				const size_t pix = (size_t)p.y * W + p.x;
 				FpLcg* rng = &shared_rng;

@@ -72,6 +72,13 @@ EXPORTS = {
     "rt_timer_start": (C.c_int, [C.c_void_p]),
     "rt_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rt_launch_count": (C.c_uint64, [C.c_void_p]),
+    "rt_tiles_per_rank": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32]),
+    "rt_render_tiles_device": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32,
+                                         C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "rt_untile_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "rt_flush_l2": (C.c_int, [C.c_void_p]),
+    "rt_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "rt_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -26,7 +26,9 @@ __global__ void __launch_bounds__(RT_BLOCK) rt_render_kernel(const __grid_consta
 	RtCounts cnt = {0, 0, 0, 0, 0};
 	uint32_t err = 0;
 	const bool inside = x < F.width && y < F.height;
-	if (inside) render_pixel<COUNT>(S, F, x, y, cnt, err);
+	const size_t out_index = F.tile_compact ? (size_t)blockIdx.x * RT_BLOCK + ((y & (RT_TILE_H - 1)) * RT_TILE_W + (x & (RT_TILE_W - 1)))
+	                                        : (size_t)y * F.width + x;
+	if (inside) render_pixel<COUNT>(S, F, x, y, out_index, cnt, err);
 	if (COUNT) {
 		unsigned long long v[6] = {inside ? (unsigned long long)F.n_frames : 0ull, cnt.segments, cnt.nodes,
 		                           cnt.tests, cnt.shades, cnt.confirms};
@@ -38,6 +40,20 @@ __global__ void __launch_bounds__(RT_BLOCK) rt_render_kernel(const __grid_consta
 		}
 	}
 	if (err) atomicOr(F.error_flags, err);
+}
+
+// Tile-major buffers of all ranks, concatenated [world][tiles_per_rank][16*16][3]  ->  frame [H][W][3].
+__global__ void rt_untile_kernel(const float* __restrict__ gathered, float* __restrict__ rgb, int width, int height,
+                                 int tiles_x, int world, int tiles_per_rank) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= width || y >= height) return;
+	const int tile = (y / RT_TILE_H) * tiles_x + (x / RT_TILE_W);
+	const int rank = tile % world, k = tile / world;
+	const size_t src = ((size_t)(rank * tiles_per_rank + k) * RT_BLOCK + (y % RT_TILE_H) * RT_TILE_W + (x % RT_TILE_W)) * 3;
+	const size_t dst = ((size_t)y * width + x) * 3;
+	rgb[dst] = gathered[src];
+	rgb[dst + 1] = gathered[src + 1];
+	rgb[dst + 2] = gathered[src + 2];
 }
 
 // ================================================================== host side
@@ -96,6 +112,7 @@ struct rt_ctx {
 	DevBuf<uint32_t> errflags;
 	std::vector<RtD2> h_col_cs;
 	std::vector<RtD4> h_row_fr;
+	DevBuf<uint8_t> l2_scratch;
 };
 
 namespace {
@@ -131,7 +148,7 @@ rt_status check_args(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm) {
 
 // Builds the RtFrame (camera tables, start state) and launches the kernel on the ctx stream.
 rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb_dev,
-                        int* ids_dev, int tile_rank, int tile_world) {
+                        int* ids_dev, int tile_rank, int tile_world, bool tile_compact = false) {
 	rt_build_camera_tables(*cam, ctx->h_col_cs, ctx->h_row_fr);
 	if (rt_status st = upload(ctx, ctx->col_cs, ctx->h_col_cs)) return st;
 	if (rt_status st = upload(ctx, ctx->row_fr, ctx->h_row_fr)) return st;
@@ -144,6 +161,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	F.first_ids = ids_dev;
 	F.tile_rank = tile_rank;
 	F.tile_world = tile_world;
+	F.tile_compact = tile_compact ? 1 : 0;
 	RT_CUDA(ctx, ctx->errflags.alloc(1));
 	RT_CUDA(ctx, cudaMemsetAsync(ctx->errflags.p, 0, sizeof(uint32_t), ctx->stream));
 	F.error_flags = ctx->errflags.p;
@@ -225,7 +243,7 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
-	ctx->counters.release(); ctx->errflags.release();
+	ctx->counters.release(); ctx->errflags.release(); ctx->l2_scratch.release();
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -261,6 +279,26 @@ rt_status rt_timer_stop(rt_ctx* ctx, float* elapsed_ms) {
 }
 
 uint64_t rt_launch_count(const rt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+rt_status rt_flush_l2(rt_ctx* ctx) {
+	if (!ctx) return RT_ERR_INVALID;
+	const size_t bytes = 256u << 20;
+	RT_CUDA(ctx, ctx->l2_scratch.alloc(bytes));
+	RT_CUDA(ctx, cudaMemsetAsync(ctx->l2_scratch.p, 0x5a, bytes, ctx->stream));
+	return RT_OK;
+}
+
+rt_status rt_host_register(rt_ctx* ctx, void* ptr, size_t bytes) {
+	if (!ctx || !ptr || !bytes) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+	return RT_OK;
+}
+
+rt_status rt_host_unregister(rt_ctx* ctx, void* ptr) {
+	if (!ctx || !ptr) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaHostUnregister(ptr));
+	return RT_OK;
+}
 
 rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	if (!ctx) return RT_ERR_INVALID;
@@ -299,6 +337,35 @@ rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* p
 	if (!rgb_dev) return fail(ctx, RT_ERR_INVALID, "rt_render_device: rgb_dev is NULL");
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
 	return launch_render(ctx, cam, prm, flags, rgb_dev, ids_dev, 0, 1);
+}
+
+uint32_t rt_tiles_per_rank(uint32_t width, uint32_t height, uint32_t world) {
+	if (!world) return 0;
+	const uint32_t n = ((width + RT_TILE_W - 1) / RT_TILE_W) * ((height + RT_TILE_H - 1) / RT_TILE_H);
+	return (n + world - 1) / world;
+}
+
+rt_status rt_render_tiles_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags,
+                                 uint32_t rank, uint32_t world, float* tiles_dev, int32_t* tile_ids_dev) {
+	if (rt_status st = check_args(ctx, cam, prm)) return st;
+	if (!tiles_dev) return fail(ctx, RT_ERR_INVALID, "rt_render_tiles_device: tiles_dev is NULL");
+	if (world == 0 || rank >= world) return fail(ctx, RT_ERR_INVALID, rt_format("bad tile shard %u of %u", rank, world));
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	return launch_render(ctx, cam, prm, flags, tiles_dev, tile_ids_dev, (int)rank, (int)world, true);
+}
+
+rt_status rt_untile_device(rt_ctx* ctx, uint32_t width, uint32_t height, uint32_t world, const float* gathered_dev,
+                           float* rgb_dev) {
+	if (!ctx) return RT_ERR_INVALID;
+	if (!gathered_dev || !rgb_dev || !world || !width || !height) return fail(ctx, RT_ERR_INVALID, "rt_untile_device: bad arguments");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	const int tiles_x = (width + RT_TILE_W - 1) / RT_TILE_W;
+	const dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
+	rt_untile_kernel<<<grid, block, 0, ctx->stream>>>(gathered_dev, rgb_dev, (int)width, (int)height, tiles_x, (int)world,
+	                                                  (int)rt_tiles_per_rank(width, height, world));
+	ctx->launches++;
+	RT_CUDA(ctx, cudaGetLastError());
+	return RT_OK;
 }
 
 rt_status rt_get_counters(rt_ctx* ctx, rt_counters* out) {

@@ -90,6 +90,7 @@ struct RtFrame {
 	uint32_t* error_flags;
 	// pixel subset for tile-sharded rendering: tiles t with t % tile_world == tile_rank
 	int tile_rank, tile_world;
+	int tile_compact;  // 1: outputs are tile-major [own tile k][16*16] instead of [height][width]
 };
 
 #define RT_ERRFLAG_TEXTURE 1u

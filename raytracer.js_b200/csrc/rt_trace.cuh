@@ -596,7 +596,8 @@ RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_i
 // Raytracer.trace_frame body (src/raytracer.ts:318-329) + ExposureBuffer.set_color_i
 // (src/view/exposure_buffer.ts:77-91) for n_frames consecutive frames.
 template <bool COUNT>
-RT_HD void render_pixel(const RtDevScene& S, const RtFrame& F, int x, int y, RtCounts& cnt, uint32_t& err) {
+RT_HD void render_pixel(const RtDevScene& S, const RtFrame& F, int x, int y, size_t out_index, RtCounts& cnt,
+                        uint32_t& err) {
 	// camera direction: get_dir_for_each_pixel (src/view/camera.ts:207-250) through the host-built
 	// tables of the accumulated scan rotations
 	const RtD4 fr = ld(F.row_fr + y);
@@ -604,7 +605,7 @@ RT_HD void render_pixel(const RtDevScene& S, const RtFrame& F, int x, int y, RtC
 	const double dir[3] = {xadd(xmul(fr.x, cs.x), xmul(F.lf[0], cs.y)), xadd(xmul(fr.y, cs.x), xmul(F.lf[1], cs.y)),
 	                       xadd(xmul(fr.z, cs.x), xmul(F.lf[2], cs.y))};
 	const size_t pix = (size_t)y * F.width + x;
-	float* o = F.rgb + pix * 3;
+	float* o = F.rgb + out_index * 3;  // frame order, or tile-major when tile-sharded (seed stays per frame pixel)
 	float px[3] = {0.f, 0.f, 0.f};
 	if (F.frame_first > 0) { px[0] = o[0]; px[1] = o[1]; px[2] = o[2]; }
 	int first_entity = -1;
@@ -620,5 +621,5 @@ RT_HD void render_pixel(const RtDevScene& S, const RtFrame& F, int x, int y, RtC
 		for (int k = 0; k < 3; k++) px[k] = (float)xadd(xmul(c[k], w), xmul((double)px[k], w1));
 	}
 	o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
-	if (F.first_ids) F.first_ids[pix] = first_entity;
+	if (F.first_ids) F.first_ids[out_index] = first_entity;
 }

@@ -47,7 +47,7 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 		for (int y = t; y < F.height; y += n_threads)
 			for (int x = 0; x < F.width; x++) {
 				RtCounts c = {0, 0, 0, 0, 0};
-				render_pixel<true>(S, F, x, y, c, errs[t]);
+				render_pixel<true>(S, F, x, y, (size_t)y * F.width + x, c, errs[t]);
 				part[t].segments += c.segments; part[t].nodes += c.nodes; part[t].tests += c.tests;
 				part[t].shades += c.shades; part[t].confirms += c.confirms;
 			}

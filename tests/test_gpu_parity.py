@@ -1,0 +1,182 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (GpuRaytracer -> rt_render),
+against the oracle on the same seeded scenes and cameras.  Gate (BASELINE.json): primary-hit entity
+ids equal on >= 99.99 % of pixels, RGB within 1/255 per channel on id-equal pixels (relative to
+max(1,|ref|) for over-range light pixels).  Parity is asserted on square frames (the reference
+throws on non-square ones); non-square frames use the intent mapping on both sides."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import oracle as orc
+import raytracer_js_b200 as rt
+from raytracer_js_b200 import _native as N
+from raytracer_js_b200 import scenes
+
+from util import compare, flat_of, insertion_ids, make_params, oracle_render, oracle_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_render(bundle, width, height, n_frames=1, pos=scenes.BENCH_CAMERA_POS, yaw=30.0, pitch=0.0, refmax=None,
+               reference_extents=False, frames_as_calls=False):
+    cam = scenes.bench_camera(width, height, pos, yaw, pitch)
+    eb = rt.ExposureBuffer(width, height)
+    cfg = rt.RaytracerConfig(bundle.refmax if refmax is None else refmax, bundle.sky, bundle.default_substance, 1.0)
+    tracer = rt.GpuRaytracer(cfg, bundle.tree, cam, eb, rt.FpLcg(1.0), reference_extents=reference_extents)
+    assert tracer.lib.rt_launch_count(tracer.ctx) == 0
+    if frames_as_calls:
+        for f in range(n_frames):  # the reference's own loop: tick(); next_frame(); tick(); ...
+            if f:
+                eb.next_frame()
+            tracer.trace_frame(want_ids=True, want_counters=True)
+    else:
+        tracer.trace_frame(n_frames=n_frames, want_ids=True, want_counters=True)
+    assert tracer.lib.rt_launch_count(tracer.ctx) >= 1  # our kernel ran, not a fallback
+    ids = insertion_ids(tracer.flat, bundle, tracer.last_first_ids)
+    return eb.image().copy(), ids, tracer.last_counters, tracer
+
+
+def oracle_for(tracer, bundle, width, height, n_frames=1, pos=scenes.BENCH_CAMERA_POS, yaw=30.0, pitch=0.0,
+               refmax=None, want_counters=False):
+    flat = tracer.flat
+    ocam = orc.Camera(math.pi / 2, math.pi / 2, width, height, pos, pitch, math.pi / 180 * yaw, vertical_locked=True)
+    prm = make_params(flat, bundle, n_frames=n_frames, refmax=refmax)
+    return oracle_render(oracle_scene(flat, bundle), ocam, flat, bundle, prm, fixed_extents=True,
+                         want_counters=want_counters)
+
+
+def test_config1_diffuse_spheres_square(oracle):
+    """BASELINE config 1 scene (10 k spheres, diffuse + sky, refmax 1) on a 1080 x 1080 frame."""
+    b = scenes.random_spheres(10000, 0.002, 0.006, seed=42.0, mix="diffuse")
+    rgb, ids, cnt, tr = gpu_render(b, 1080, 1080)
+    orgb, oids, _, tot = oracle_for(tr, b, 1080, 1080)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
+    for k in ("segments", "nodes", "tests", "shades"):
+        assert abs(cnt[k] - tot[k]) <= 1e-4 * tot[k], (k, cnt[k], tot[k])
+    assert (oids >= 0).sum() > 10000
+
+
+def test_small_dense_scene_exact(oracle):
+    b = scenes.random_spheres(1500, 0.01, 0.04, seed=42.0, mix="diffuse")
+    rgb, ids, cnt, tr = gpu_render(b, 256, 256)
+    orgb, oids, _, tot = oracle_for(tr, b, 256, 256)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0, res
+    assert {k: cnt[k] for k in ("segments", "nodes", "tests", "shades")} == {k: tot[k] for k in ("segments", "nodes", "tests", "shades")}
+
+
+def test_config2_mirrors_lights_rough_multiframe(oracle):
+    """Config-2 material mix (mirrors, rough mirrors with per-pixel-reseeded FpLcg, lights), 4 spp."""
+    b = scenes.random_spheres(20000, 0.004, 0.012, seed=42.0, mix="mirrors", box_fraction=0.1)
+    rgb, ids, cnt, tr = gpu_render(b, 400, 400, n_frames=4)
+    orgb, oids, _, tot = oracle_for(tr, b, 400, 400, n_frames=4)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 2, res
+    assert abs(cnt["segments"] - tot["segments"]) <= 1e-4 * tot["segments"]
+    # n_frames in one call == the reference's call-per-frame loop with next_frame() in between
+    rgb2, ids2, _, _ = gpu_render(b, 400, 400, n_frames=4, frames_as_calls=True)
+    np.testing.assert_array_equal(rgb, rgb2)
+    np.testing.assert_array_equal(ids, ids2)
+
+
+def test_transmission_substances_boxes(oracle):
+    rng = rt.FpLcg(5.0)
+    tree = rt.new_entity_octree(rt.OctreeDim(rt.point(0, 0, 0), 1.0), None)
+    glass = rt.SolidMaterial(rt.ResponseType.TRANSMISSION, False, False, 0)
+    mirror = rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0)
+    light = rt.SolidMaterial(rt.ResponseType.REFLECTION, True, False, 0)
+    both = rt.SolidMaterial(rt.ResponseType.BOTH, False, False, 0)
+    subs = [rt.SUBSTANCE_AIR, rt.SUBSTANCE_WATER, rt.SUBSTANCE_GLASS, None]
+    ents = []
+    for _ in range(300):
+        d = 0.03 + rng.next() * 0.12
+        c = [d / 2 + rng.next() * (1 - d) for _ in range(3)]
+        m = [glass, glass, mirror, light, both][int(rng.next() * 5)]
+        tex = rt.SolidTexture(rt.Color(0.3 + rng.next(), 0.3 + rng.next(), 0.3 + rng.next(), 1))
+        cls = rt.BoxEntity if rng.next() < 0.3 else rt.SphereEntity
+        e = cls(None, m, tex, subs[int(rng.next() * 4)], rt.point(*c), d)
+        rt.add_entity_to_octree(tree, e, {"max_in_depth": 16, "max_out_depth": 0})
+        ents.append(e)
+    b = scenes.SceneBundle(tree, ents, rt.SkySphere(rt.SolidTexture(rt.Color(0.2, 0.2, 0.7, 1))), rt.SUBSTANCE_AIR, 6)
+    pos = (0.013, 0.487, 0.021)
+    rgb, ids, cnt, tr = gpu_render(b, 200, 200, pos=pos, yaw=10.0)
+    orgb, oids, _, tot = oracle_for(tr, b, 200, 200, pos=pos, yaw=10.0)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
+    assert tot["within_tests"] > 0
+
+
+def test_image_textures_and_sky(oracle):
+    texs = [scenes.checker_texture(256, 128, seed=s) for s in (1, 2, 3)]
+    b = scenes.random_spheres(3000, 0.02, 0.08, seed=9.0, mix="mirrors", textures=texs)
+    b.sky = rt.SkySphere(scenes.checker_texture(512, 256, seed=4))
+    rgb, ids, cnt, tr = gpu_render(b, 300, 300)
+    orgb, oids, _, tot = oracle_for(tr, b, 300, 300)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 2, res
+
+
+def test_camera_outside_root(oracle):
+    b = scenes.random_spheres(400, 0.02, 0.2, seed=3.0, mix="diffuse")
+    rgb, ids, cnt, tr = gpu_render(b, 96, 96, pos=(-0.5, 0.5, 0.5), yaw=0.0)
+    orgb, oids, _, tot = oracle_for(tr, b, 96, 96, pos=(-0.5, 0.5, 0.5), yaw=0.0)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0
+    assert cnt["nodes"] == tot["nodes"]
+
+
+def test_empty_scene_and_ragged_frame(oracle):
+    """Empty octree (sky everywhere) and a frame that is not a multiple of the 16x16 tile."""
+    b = scenes.random_spheres(0)
+    rgb, ids, cnt, tr = gpu_render(b, 50, 50)
+    assert (ids == -1).all()
+    np.testing.assert_allclose(rgb, np.broadcast_to(np.float32([0.2, 0.2, 0.7]), rgb.shape))
+    b = scenes.random_spheres(200, 0.05, 0.2, seed=2.0)
+    rgb, ids, cnt, tr = gpu_render(b, 77, 45)  # non-square: intent mapping on both sides
+    orgb, oids, _, _ = oracle_for(tr, b, 77, 45)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0
+    with pytest.raises(IndexError):  # the reference's behaviour on non-square frames
+        gpu_render(b, 77, 45, reference_extents=True)
+
+
+def test_full_size_properties():
+    """1920x1080 (BASELINE config 1 frame): size-independent properties where the oracle is too slow to
+    be run in full: determinism, exposure-blend linearity, every pixel written, ids within range."""
+    b = scenes.random_spheres(10000, 0.002, 0.006, seed=42.0, mix="diffuse")
+    rgb1, ids1, cnt1, tr = gpu_render(b, 1920, 1080)
+    rgb2, ids2, cnt2, _ = gpu_render(b, 1920, 1080, n_frames=3)
+    np.testing.assert_array_equal(ids1, ids2)
+    np.testing.assert_allclose(rgb1, rgb2, atol=1e-6)  # no roughness: every frame is the same sample
+    assert cnt1["paths"] == 1920 * 1080 and cnt2["paths"] == 3 * 1920 * 1080
+    assert cnt1["segments"] == 1920 * 1080 and cnt2["tests"] == 3 * cnt1["tests"]
+    assert ids1.min() >= -1 and ids1.max() < 10000 and np.isfinite(rgb1).all()
+    sky = np.float32([0.2, 0.2, 0.7])
+    assert (np.abs(rgb1[ids1 < 0] - sky) < 1e-6).all()  # misses are exactly the sky colour
+
+
+def test_error_behaviour():
+    lib = N.load()
+    ctx = C.c_void_p()
+    N.check(None, lib.rt_create(-1, C.byref(ctx)))
+    cam = rt.camera_desc(scenes.bench_camera(16, 16))
+    p = N.Params()
+    p.n_frames = 1
+    buf = np.zeros(16 * 16 * 3, np.float32)
+    assert lib.rt_render(ctx, C.byref(cam), C.byref(p), 0, buf.ctypes.data, None, None) == N.RT_ERR_NO_SCENE
+    assert b"no scene" in lib.rt_last_error(ctx)
+    d = N.SceneDesc()
+    assert lib.rt_scene_upload(ctx, C.byref(d)) == N.RT_ERR_INVALID  # struct_size mismatch
+    flat = flat_of(scenes.random_spheres(20, 0.05, 0.1))
+    good = flat.desc()
+    N.check(ctx, lib.rt_scene_upload(ctx, C.byref(good)))
+    p.sky_texture = 99
+    assert lib.rt_render(ctx, C.byref(cam), C.byref(p), 0, buf.ctypes.data, None, None) == N.RT_ERR_INVALID
+    flat.arrays["list_entity"][1] = flat.arrays["list_entity"][0]  # an entity listed twice
+    bad = flat.desc()
+    assert lib.rt_scene_upload(ctx, C.byref(bad)) == N.RT_ERR_INVALID
+    assert b"more than one node" in lib.rt_last_error(ctx)
+    lib.rt_destroy(ctx)
