@@ -154,7 +154,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     lib = N.load()
     ctx = C.c_void_p()
     N.check(None, lib.rt_create(local_rank, C.byref(ctx)))
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream carries our kernels, the NCCL collectives and the timing events
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     N.check(ctx, lib.rt_set_stream(ctx, C.c_void_p(stream.cuda_stream)))
 
     # ---- scene: built on rank 0 by the host API, flat buffers broadcast with NCCL, one replica per GPU
@@ -333,8 +336,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         out["cpu_baseline"] = {"value": mrays, "unit": "Mrays/s", "cores": 1, "kind": "port", "frame_ms": ms,
                                "sample": f"one full {WIDTH}x{HEIGHT} frame ({tot['segments']} segments), 1 thread "
                                          "(the reference renderer is single-threaded)"}
-        same = all(tot[k] == v for k, v in (("segments", segments), ("nodes", nodes), ("tests", tests), ("shades", shades)))
-        out["roofline"]["counters_equal_oracle"] = bool(same)
+        # the same counters from the oracle (float64 walk): equal up to rare float32 cell-boundary ties
+        out["roofline"]["oracle_counters_rel_diff"] = {
+            k: (v - tot[k]) / max(tot[k], 1) for k, v in (("segments", segments), ("nodes", nodes), ("tests", tests),
+                                                          ("shades", shades))}
     print(json.dumps(out))
 
 

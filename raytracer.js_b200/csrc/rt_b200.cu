@@ -10,28 +10,52 @@
 #define RT_TILE_H 16
 #define RT_BLOCK (RT_TILE_W * RT_TILE_H)
 
-// One CTA per 16x16 screen tile, one thread per pixel; each warp owns an 8x4 pixel patch so that its
-// 32 rays walk nearly the same octree cells and scan the same entity lists (uniform LDG.128 addresses).
-// Tiles are interleaved over ranks for multi-GPU sharding: tile t belongs to rank t % tile_world.
+// Per-frame preparation for camera rays: the origin-relative copy of the slot geometry.  The
+// subtraction centre - camera is done in float64 (no cancellation), then rounded once.
+__global__ void rt_prepare_primary_kernel(const __grid_constant__ RtDevScene S, double ox, double oy, double oz,
+                                          RtF4* __restrict__ out) {
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= S.n_slots) return;
+	const RtF4 r = make_prim_record(ld(S.slot_geom64 + s), ld(S.slot_geom + s).w > 0.0f, ox, oy, oz, S.err_l);
+	out[s] = r;
+}
+
+// Persistent warps: the grid is sized to the resident capacity of the GPU (SMs x CTAs/SM) and every
+// warp pulls 8x4-pixel patches from an atomic counter until the frame (or this rank's share of its
+// 16x16 tiles, t % tile_world == tile_rank) is done.  One thread per pixel; the 32 rays of a patch
+// walk nearly the same octree cells and scan the same entity lists (uniform LDG.128 addresses), and a
+// warp that finishes a cheap sky patch immediately takes the next one instead of idling in its CTA.
+#define RT_WARPS_PER_CTA 4
 template <bool COUNT>
-__global__ void __launch_bounds__(RT_BLOCK) rt_render_kernel(const __grid_constant__ RtDevScene S,
-                                                             const __grid_constant__ RtFrame F, int tiles_x,
-                                                             int n_tiles) {
-	const int tile = F.tile_rank + blockIdx.x * F.tile_world;
-	if (tile >= n_tiles) return;
-	const int tx = tile % tiles_x, ty = tile / tiles_x;
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int x = tx * RT_TILE_W + (warp & 1) * 8 + (lane & 7);
-	const int y = ty * RT_TILE_H + (warp >> 1) * 4 + (lane >> 3);
+__global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
+    rt_render_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_tiles,
+                     int n_patches) {
+	const int lane = threadIdx.x & 31;
 	RtCounts cnt = {0, 0, 0, 0, 0};
+	unsigned long long paths = 0;
 	uint32_t err = 0;
-	const bool inside = x < F.width && y < F.height;
-	const size_t out_index = F.tile_compact ? (size_t)blockIdx.x * RT_BLOCK + ((y & (RT_TILE_H - 1)) * RT_TILE_W + (x & (RT_TILE_W - 1)))
-	                                        : (size_t)y * F.width + x;
-	if (inside) render_pixel<COUNT>(S, F, x, y, out_index, cnt, err);
+	while (true) {
+		unsigned p = 0;
+		if (lane == 0) p = atomicAdd(F.work_counter, 1u);
+		p = __shfl_sync(0xffffffffu, p, 0);
+		if (p >= (unsigned)n_patches) break;
+		const int k = (int)(p >> 3), sub = (int)(p & 7);  // k-th own tile, patch within the tile
+		const int tile = F.tile_rank + k * F.tile_world;
+		if (tile >= n_tiles) continue;
+		const int tx = tile % tiles_x, ty = tile / tiles_x;
+		const int x = tx * RT_TILE_W + (sub & 1) * 8 + (lane & 7);
+		const int y = ty * RT_TILE_H + (sub >> 1) * 4 + (lane >> 3);
+		if (x < F.width && y < F.height) {
+			const size_t out_index =
+			    F.tile_compact ? (size_t)k * RT_BLOCK + ((y & (RT_TILE_H - 1)) * RT_TILE_W + (x & (RT_TILE_W - 1)))
+			                   : (size_t)y * F.width + x;
+			render_pixel<COUNT>(S, F, x, y, out_index, cnt, err);
+			paths += F.n_frames;
+		}
+		__syncwarp();
+	}
 	if (COUNT) {
-		unsigned long long v[6] = {inside ? (unsigned long long)F.n_frames : 0ull, cnt.segments, cnt.nodes,
-		                           cnt.tests, cnt.shades, cnt.confirms};
+		unsigned long long v[6] = {paths, cnt.segments, cnt.nodes, cnt.tests, cnt.shades, cnt.confirms};
 #pragma unroll
 		for (int k = 0; k < 6; k++) {
 			unsigned long long s = v[k];
@@ -109,10 +133,11 @@ struct rt_ctx {
 	DevBuf<float> rgb;
 	DevBuf<int> ids;
 	DevBuf<unsigned long long> counters;
-	DevBuf<uint32_t> errflags;
 	std::vector<RtD2> h_col_cs;
 	std::vector<RtD4> h_row_fr;
 	DevBuf<uint8_t> l2_scratch;
+	DevBuf<RtF4> prim_geom;
+	int render_grid[2] = {0, 0};  // persistent grid size of rt_render_kernel<false/true>
 };
 
 namespace {
@@ -162,35 +187,60 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	F.tile_rank = tile_rank;
 	F.tile_world = tile_world;
 	F.tile_compact = tile_compact ? 1 : 0;
-	RT_CUDA(ctx, ctx->errflags.alloc(1));
-	RT_CUDA(ctx, cudaMemsetAsync(ctx->errflags.p, 0, sizeof(uint32_t), ctx->stream));
-	F.error_flags = ctx->errflags.p;
-	const bool count = (flags & RT_RENDER_COUNTERS) != 0;
-	RT_CUDA(ctx, ctx->counters.alloc(8));
-	RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+	// counters[0..7], then the persistent-warp work counter and the error flags: one memset
+	RT_CUDA(ctx, ctx->counters.alloc(10));
+	RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 10 * sizeof(unsigned long long), ctx->stream));
 	F.counters = ctx->counters.p;
+	F.work_counter = reinterpret_cast<unsigned*>(ctx->counters.p + 8);
+	F.error_flags = reinterpret_cast<uint32_t*>(ctx->counters.p + 9);
+	const bool count = (flags & RT_RENDER_COUNTERS) != 0;
 	const int tiles_x = (F.width + RT_TILE_W - 1) / RT_TILE_W, tiles_y = (F.height + RT_TILE_H - 1) / RT_TILE_H;
 	const int n_tiles = tiles_x * tiles_y;
 	const int my_tiles = (n_tiles - tile_rank + tile_world - 1) / tile_world;
-	if (my_tiles > 0) {
-		if (count)
-			rt_render_kernel<true><<<my_tiles, RT_BLOCK, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles);
-		else
-			rt_render_kernel<false><<<my_tiles, RT_BLOCK, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles);
+	if (my_tiles <= 0) return RT_OK;
+
+	// primary-ray preparation: origin-relative slot records + the origin chain (start node ... root)
+	const RtHostScene& H = ctx->host;
+	const int n_slots = (int)H.slot_geom.size();
+	F.prim_geom = nullptr;
+	F.chain_levels = 0;
+	if (n_slots > 0) {
+		RT_CUDA(ctx, ctx->prim_geom.alloc((size_t)n_slots));
+		rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
+		                                                                         cam->pos[2], ctx->prim_geom.p);
 		ctx->launches++;
 		RT_CUDA(ctx, cudaGetLastError());
+		F.prim_geom = ctx->prim_geom.p;
+		rt_fill_chain(H, F);
 	}
+
+	const int n_patches = my_tiles * 8;
+	int& grid = ctx->render_grid[count ? 1 : 0];
+	if (grid == 0) {
+		int per_sm = 0, sms = 0;
+		if (count)
+			RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rt_render_kernel<true>, RT_WARPS_PER_CTA * 32, 0));
+		else
+			RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rt_render_kernel<false>, RT_WARPS_PER_CTA * 32, 0));
+		RT_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+		grid = std::max(1, per_sm) * std::max(1, sms);
+	}
+	const int blocks = std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA);
+	if (count)
+		rt_render_kernel<true><<<blocks, RT_WARPS_PER_CTA * 32, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles, n_patches);
+	else
+		rt_render_kernel<false><<<blocks, RT_WARPS_PER_CTA * 32, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles, n_patches);
+	ctx->launches++;
+	RT_CUDA(ctx, cudaGetLastError());
 	return RT_OK;
 }
 
 rt_status read_counters(rt_ctx* ctx, rt_counters* out) {
-	unsigned long long h[8] = {0};
-	uint32_t ef = 0;
+	unsigned long long h[10] = {0};
 	if (ctx->counters.p)
 		RT_CUDA(ctx, cudaMemcpyAsync(h, ctx->counters.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-	if (ctx->errflags.p)
-		RT_CUDA(ctx, cudaMemcpyAsync(&ef, ctx->errflags.p, sizeof ef, cudaMemcpyDeviceToHost, ctx->stream));
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	const uint32_t ef = (uint32_t)h[9];
 	out->paths = h[0]; out->segments = h[1]; out->nodes = h[2]; out->tests = h[3]; out->shades = h[4];
 	out->confirms = h[5];
 	out->texture_errors = (ef & RT_ERRFLAG_TEXTURE) ? 1 : 0;
@@ -243,7 +293,7 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
-	ctx->counters.release(); ctx->errflags.release(); ctx->l2_scratch.release();
+	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release();
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

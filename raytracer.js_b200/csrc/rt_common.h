@@ -67,6 +67,8 @@ struct RtDevScene {
 	float _pad;
 };
 
+#define RT_MAX_CHAIN 32
+
 struct RtFrame {
 	// camera
 	double pos[3];
@@ -91,6 +93,11 @@ struct RtFrame {
 	// pixel subset for tile-sharded rendering: tiles t with t % tile_world == tile_rank
 	int tile_rank, tile_world;
 	int tile_compact;  // 1: outputs are tile-major [own tile k][16*16] instead of [height][width]
+	// primary-ray acceleration (exact: only skips work that provably cannot produce a hit)
+	const RtF4* prim_geom;  // [n_slots] (centre - camera, +-(radius+err)^2 | +inf for boxes), or null
+	int chain_levels;       // origin chain: start_node, its parent, ..., root (post-order return order)
+	int chain_beg[RT_MAX_CHAIN], chain_end[RT_MAX_CHAIN];  // slot ranges of the chain nodes' lists
+	unsigned* work_counter;  // persistent-warp patch dispenser
 };
 
 #define RT_ERRFLAG_TEXTURE 1u

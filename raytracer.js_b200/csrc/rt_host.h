@@ -323,3 +323,14 @@ inline rt_status rt_fill_frame(const RtHostScene& hs, const rt_camera* cam, cons
 	F.rng_seed = prm->rng_seed;
 	return RT_OK;
 }
+
+// The origin chain of the camera rays: start node, its parent, ..., root, in the order the walker
+// returns them (post-order), as slot ranges for the lock-step pre-test (rt_trace.cuh: pretest_chain).
+inline void rt_fill_chain(const RtHostScene& hs, RtFrame& F) {
+	F.chain_levels = 0;
+	for (int n = F.start_node; n >= 0 && F.chain_levels < RT_MAX_CHAIN; n = hs.node_link[n].x) {
+		F.chain_beg[F.chain_levels] = hs.node_link[n].z;
+		F.chain_end[F.chain_levels] = hs.node_link[n].z + hs.node_link[n].w;
+		F.chain_levels++;
+	}
+}

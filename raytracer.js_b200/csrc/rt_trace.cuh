@@ -287,17 +287,54 @@ RT_HD int entity_at_pos(const RtDevScene& S, const double* p) {
 }
 
 // ------------------------------------------------------------------ the walk
-// Scans one node's entity list in insertion order; returns the slot of the first entity whose
-// float64 collision_info is non-null (src/raytracer.ts:186-195), or -1.
+// Per-segment search context.  `rel` (optional) is the per-frame origin-relative copy of slot_geom for
+// rays that start at the camera (see rt_prepare_primary): (centre - origin, +-(radius+err)^2) with the
+// sign carrying "origin inside the sphere", +inf marking a box (handled by the generic test).
+struct RtSearch {
+	RtRayF r;
+	const RtF4* rel;        // non-null: primary segment, origin-relative sphere tests
+	unsigned chain_mask;    // bit k: the k-th origin-chain node's list may hold a hit (else skip its scan)
+	int chain_levels;       // number of chain levels that were pre-tested (0: scan everything)
+};
+
+// candidate test against the origin-relative record (primary rays): ~12 flops, no centre - origin
+// subtraction, no cancellation (the difference was taken in float64 on the host side of the frame)
+RT_HD bool candidate_rel(const RtF4& g, const RtRayF& r) {
+	const float tca = g.x * r.dx + g.y * r.dy + g.z * r.dz;
+	const float s = tca * r.inv_a;
+	const float lx = g.x - s * r.dx, ly = g.y - s * r.dy, lz = g.z - s * r.dz;
+	const float l2 = lx * lx + ly * ly + lz * lz;
+	return l2 <= fabsf(g.w) && (tca >= 0.0f || g.w < 0.0f);
+}
+
+// The per-frame origin-relative record of one slot (see RtSearch::rel).  centre - camera is taken in
+// float64 (no cancellation) and rounded once.
+RT_HD RtF4 make_prim_record(const RtD4& g, bool is_sphere, double ox, double oy, double oz, float err_l) {
+	if (!is_sphere) return RtF4{0.f, 0.f, 0.f, INFINITY};  // box: use the generic slab test
+	const double cx = g.x - ox, cy = g.y - oy, cz = g.z - oz;
+	const float rr = (float)(g.w * 0.5) + err_l;
+	const float rr2 = rr * rr;
+	const bool inside = cx * cx + cy * cy + cz * cz <= (double)rr2;
+	return RtF4{(float)cx, (float)cy, (float)cz, inside ? -rr2 : rr2};
+}
+
+RT_HD bool slot_candidate(const RtDevScene& S, const RtSearch& q, int s) {
+	if (q.rel) {
+		const RtF4 g = ld(q.rel + s);
+		if (g.w != INFINITY) return candidate_rel(g, q.r);
+	}
+	return candidate(ld(S.slot_geom + s), q.r, S.err_l);
+}
+
+// Scans slots [beg,end) in insertion order; returns the slot of the first entity whose float64
+// collision_info is non-null (src/raytracer.ts:186-195), or -1.
 template <bool COUNT>
-RT_HD int scan_list(const RtDevScene& S, int node, const RtRayF& r, const double* o, const double* d,
+RT_HD int scan_list(const RtDevScene& S, const RtSearch& q, int beg, int end, const double* o, const double* d,
                     RtCollision& col, RtCounts& cnt) {
-	const RtI4 link = ld(S.node_link + node);
-	const int beg = link.z, end = link.z + link.w;
 	int s = beg;
 	while (true) {
 		for (; s < end; ++s)
-			if (candidate(ld(S.slot_geom + s), r, S.err_l)) break;
+			if (slot_candidate(S, q, s)) break;
 		if (s >= end) break;
 		const RtD4 g = ld(S.slot_geom64 + s);
 		const bool hit = ld(S.slot_geom + s).w > 0.0f ? exact_sphere(g, o, d, col) : exact_box(g, o, d, col);
@@ -316,77 +353,121 @@ RT_HD int scan_list(const RtDevScene& S, int node, const RtRayF& r, const double
 // (src/raytracer.ts:179-195).  State names follow the reference.  (node, octant) is the start
 // position: node_at_pos of the origin, or octant < 0 for "origin outside the root: root only"
 // (src/octree_space.ts:272-275,283-287).  Returns the hit slot or -1.
+//
+// Shape: "while-while".  The inner loop only advances the walker until it returns a node whose list
+// has to be scanned; the scan runs after it, so the lanes of a warp re-converge between the two phases
+// instead of interleaving cell steps of one ray with list scans of another.
+// The nodes that contain the ray origin (the "origin chain") are returned in post-order, each when the
+// ray leaves it: they are recognised by step_back at depth 0, and for primary rays
+// their lists were pre-tested in lock-step by the whole warp (q.chain_mask).
 template <bool COUNT>
-RT_HD int walk_and_scan(const RtDevScene& S, int node, int octant, const double* o, const double* d,
-                        RtCollision& col, RtCounts& cnt) {
-	const RtRayF r = make_ray_f(o, d);
+RT_HD int walk_and_scan(const RtDevScene& S, const RtSearch& q, int node, int octant, const double* o,
+                        const double* d, RtCollision& col, RtCounts& cnt) {
+	const RtRayF& r = q.r;
 	bool cur_returned = false, stepped_in = false, ahead = false;
 	int depth = 0;
+	int chain_level = 0;
+	bool chain_pending = octant < 0;  // root-only mode: the single returned node is the chain's only node
 	float npx = r.ox, npy = r.oy, npz = r.oz;  // next_pos[0]
 	int face = 0;                               // next_pos[1] as a face index (axis*2 + positive)
 	RtF4 g = ld(S.node_geom + node);
+	bool done = false;
 	while (true) {
-		const int child = octant >= 0 ? ld(S.node_child + node * 8 + octant) : node;
-		if (!cur_returned && child >= 0) {
-			cur_returned = true;
-			if (COUNT) cnt.nodes++;
-			const int s = scan_list<COUNT>(S, child, r, o, d, col, cnt);
-			if (s >= 0) return s;
-		}
-		if (octant >= 0) {
-			if (!ahead) {
-				if (!stepped_in && child >= 0) {  // step_in: octant_adj_pos(child, next_pos[0]) :41-50
-					g = ld(S.node_geom + child);
+		int scan_beg = 0, scan_end = 0;
+		// ---- phase 1: advance the walker to the next node with a list to scan
+		while (true) {
+			const int child = octant >= 0 ? ld(S.node_child + node * 8 + octant) : node;
+			if (!cur_returned && child >= 0) {
+				cur_returned = true;
+				if (COUNT) cnt.nodes++;
+				const RtI4 link = ld(S.node_link + child);
+				bool skip = link.w == 0;
+				if (chain_pending) {
+					chain_pending = false;
+					if (chain_level < q.chain_levels && !((q.chain_mask >> chain_level) & 1u)) {
+						skip = true;  // pre-tested: no entity of this list can be hit
+						if (COUNT) cnt.tests += (unsigned)link.w;
+					}
+					chain_level++;
+				}
+				if (!skip) {
+					scan_beg = link.z;
+					scan_end = link.z + link.w;
+					break;
+				}
+			}
+			if (octant >= 0) {
+				if (!ahead) {
+					if (!stepped_in && child >= 0) {  // step_in: octant_adj_pos(child, next_pos[0]) :41-50
+						g = ld(S.node_geom + child);
+						const float h = g.w * 0.5f;
+						octant = (npx >= g.x + h ? 1 : 0) | (npy >= g.y + h ? 2 : 0) | (npz >= g.z + h ? 4 : 0);
+						node = child;
+						depth++;
+						cur_returned = false;
+						continue;
+					}
+					// update_next_pos :369-384: exit parameter and face of the cell (node, octant);
+					// strict comparisons in face order -x,+x,-y,+y,-z,+z  =>  ties go x, then y, then z
 					const float h = g.w * 0.5f;
-					octant = (npx >= g.x + h ? 1 : 0) | (npy >= g.y + h ? 2 : 0) | (npz >= g.z + h ? 4 : 0);
-					node = child;
-					depth++;
+					const float lox = g.x + ((octant & 1) ? h : 0.0f);
+					const float loy = g.y + ((octant & 2) ? h : 0.0f);
+					const float loz = g.z + ((octant & 4) ? h : 0.0f);
+					const float tx = r.dx != 0.0f ? ((r.dx > 0.0f ? lox + h : lox) - r.ox) * r.ix : INFINITY;
+					const float ty = r.dy != 0.0f ? ((r.dy > 0.0f ? loy + h : loy) - r.oy) * r.iy : INFINITY;
+					const float tz = r.dz != 0.0f ? ((r.dz > 0.0f ? loz + h : loz) - r.oz) * r.iz : INFINITY;
+					float t = tx;
+					face = r.dx > 0.0f ? 1 : 0;
+					if (ty < t) { t = ty; face = r.dy > 0.0f ? 3 : 2; }
+					if (tz < t) { t = tz; face = r.dz > 0.0f ? 5 : 4; }
+					npx = r.ox + r.dx * t;
+					npy = r.oy + r.dy * t;
+					npz = r.oz + r.dz * t;
+				}
+				const int axis = face >> 1;
+				const int bit = (octant >> axis) & 1;
+				if (bit != (face & 1)) {  // neighbour octant inside the parent cube :344-352
+					octant ^= 1 << axis;
 					cur_returned = false;
+					stepped_in = false;
+					ahead = false;
 					continue;
 				}
-				// update_next_pos :369-384: exit parameter and face of the cell (node, octant);
-				// strict comparisons in face order -x,+x,-y,+y,-z,+z  =>  ties go x, then y, then z
-				const float h = g.w * 0.5f;
-				const float lox = g.x + ((octant & 1) ? h : 0.0f);
-				const float loy = g.y + ((octant & 2) ? h : 0.0f);
-				const float loz = g.z + ((octant & 4) ? h : 0.0f);
-				const float tx = r.dx != 0.0f ? ((r.dx > 0.0f ? lox + h : lox) - r.ox) * r.ix : INFINITY;
-				const float ty = r.dy != 0.0f ? ((r.dy > 0.0f ? loy + h : loy) - r.oy) * r.iy : INFINITY;
-				const float tz = r.dz != 0.0f ? ((r.dz > 0.0f ? loz + h : loz) - r.oz) * r.iz : INFINITY;
-				float t = tx;
-				face = r.dx > 0.0f ? 1 : 0;
-				if (ty < t) { t = ty; face = r.dy > 0.0f ? 3 : 2; }
-				if (tz < t) { t = tz; face = r.dz > 0.0f ? 5 : 4; }
-				npx = r.ox + r.dx * t;
-				npy = r.oy + r.dy * t;
-				npz = r.oz + r.dz * t;
+				ahead = true;
 			}
-			const int axis = face >> 1;
-			const int bit = (octant >> axis) & 1;
-			if (bit != (face & 1)) {  // neighbour octant inside the parent cube :344-352
-				octant ^= 1 << axis;
-				cur_returned = false;
-				stepped_in = false;
-				ahead = false;
-				continue;
+			// step_back :280-308
+			stepped_in = true;
+			if (octant < 0) { done = true; break; }
+			if (depth > 0) { depth--; cur_returned = true; }
+			else { cur_returned = false; chain_pending = true; }  // the node we leave contained the origin
+			const RtI4 link = ld(S.node_link + node);
+			if (link.x >= 0) {
+				octant = link.y;
+				node = link.x;
+				g = ld(S.node_geom + node);
+			} else {
+				octant = -1;
 			}
-			ahead = true;
 		}
-		// step_back :280-308
-		stepped_in = true;
-		if (octant < 0) break;
-		if (depth > 0) { depth--; cur_returned = true; }
-		else cur_returned = false;
-		const RtI4 link = ld(S.node_link + node);
-		if (link.x >= 0) {
-			octant = link.y;
-			node = link.x;
-			g = ld(S.node_geom + node);
-		} else {
-			octant = -1;
-		}
+		if (done) break;
+		// ---- phase 2: scan the list
+		const int s = scan_list<COUNT>(S, q, scan_beg, scan_end, o, d, col, cnt);
+		if (s >= 0) return s;
 	}
 	return -1;
+}
+
+// Lock-step pre-test of the origin-chain lists for a primary ray: every lane of the warp runs over the
+// same slots (uniform 16 B loads).  Bit k of the result is set if the list of chain level k holds a
+// (conservative) candidate.
+RT_HD unsigned pretest_chain(const RtFrame& F, const RtDevScene& S, const RtSearch& q) {
+	unsigned mask = 0;
+	for (int k = 0; k < F.chain_levels; k++) {
+		bool any = false;
+		for (int s = F.chain_beg[k]; s < F.chain_end[k]; s++) any |= slot_candidate(S, q, s);
+		mask |= (any ? 1u : 0u) << k;
+	}
+	return mask;
 }
 
 // ------------------------------------------------------------------ shading helpers
@@ -468,6 +549,7 @@ RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_i
 	int node = F.start_node, octant = F.start_octant;
 	bool have_node = F.start_node >= 0;
 	bool light_hit = false;
+	bool primary = true;
 	while (true) {
 		// walker.set_pos_and_dir -> set_position -> setup_cur_node (src/octree_space.ts:188-205,251-278)
 		if (COUNT) cnt.segments++;
@@ -482,7 +564,21 @@ RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_i
 			octant = -1;
 		}
 		RtCollision ci;
-		const int slot = walk_and_scan<COUNT>(S, node, octant, refpoint, dir, ci, cnt);
+		RtSearch q;
+		q.r = make_ray_f(refpoint, dir);
+		q.rel = nullptr;
+		q.chain_mask = 0xffffffffu;
+		q.chain_levels = 0;
+		if (primary && F.prim_geom) {
+			// camera rays: origin-relative records + lock-step pre-test of the shared origin chain
+			q.rel = F.prim_geom;
+			if (have_node) {
+				q.chain_levels = F.chain_levels;
+				q.chain_mask = pretest_chain(F, S, q);
+			}
+		}
+		primary = false;
+		const int slot = walk_and_scan<COUNT>(S, q, node, octant, refpoint, dir, ci, cnt);
 		if (slot < 0) break;  // miss: sky
 		const RtI4 attr = ld(S.slot_attr + slot);
 		if (first_entity < 0) first_entity = attr.x;

@@ -40,6 +40,12 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 	F.first_ids = ids;
 	F.tile_rank = 0;
 	F.tile_world = 1;
+	// the primary-ray preparation of launch_render (rt_b200.cu), on the host
+	std::vector<RtF4> prim(hs.slot_geom.size());
+	for (size_t s = 0; s < prim.size(); s++)
+		prim[s] = make_prim_record(hs.slot_geom64[s], hs.slot_geom[s].w > 0.0f, cam->pos[0], cam->pos[1], cam->pos[2], hs.err_l);
+	F.prim_geom = prim.empty() || (prm->flags & 1u) ? nullptr : prim.data();  // flags bit 0 (test only): generic path
+	if (F.prim_geom) rt_fill_chain(hs, F);
 	if (n_threads < 1) n_threads = 1;
 	std::vector<RtCounts> part(n_threads, RtCounts{0, 0, 0, 0, 0});
 	std::vector<uint32_t> errs(n_threads, 0);

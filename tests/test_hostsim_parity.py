@@ -125,3 +125,18 @@ def test_reference_extents_flag(oracle):
     orgb, oids, _, _ = oracle_render(os_, ocam, flat, b, prm, fixed_extents=True)
     res = compare(rgb, insertion_ids(flat, b, ids), orgb, oids)
     assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0
+
+
+def test_primary_acceleration_is_exact(oracle):
+    """The camera-ray fast path (origin-relative records + lock-step pre-test of the origin chain) must
+    give the same pixels, ids and reference-pattern counters as the generic per-segment path."""
+    b = scenes.random_spheres(3000, 0.004, 0.03, seed=5.0, mix="mirrors", box_fraction=0.1)
+    flat = flat_of(b)
+    cam, _ = cameras(128, 128)
+    prm = make_params(flat, b)
+    rgb1, ids1, c1 = hostsim_render(flat, cam, prm)
+    prm.flags = 1  # test-only switch of tests/hostsim: no prim_geom, no chain pre-test
+    rgb2, ids2, c2 = hostsim_render(flat, cam, prm)
+    np.testing.assert_array_equal(rgb1, rgb2)
+    np.testing.assert_array_equal(ids1, ids2)
+    assert {k: c1[k] for k in ("segments", "nodes", "tests", "shades")} == {k: c2[k] for k in ("segments", "nodes", "tests", "shades")}
