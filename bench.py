@@ -170,29 +170,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         def_sub = flat.substance_index(bundle.default_substance)
     scene_bcast_bytes = 0
     if world > 1:
-        meta = [None]
-        if rank == 0:
-            names = sorted(flat.arrays)
-            meta = [{"names": names, "dtypes": [str(flat.arrays[n].dtype) for n in names],
-                     "shapes": [flat.arrays[n].shape for n in names], "sky": sky_tex, "sub": def_sub}]
-        dist.broadcast_object_list(meta, src=0)
-        m = meta[0]
-        sizes = [int(np.prod(s)) * np.dtype(d).itemsize for s, d in zip(m["shapes"], m["dtypes"])]
-        offs = np.concatenate([[0], np.cumsum([(s + 15) // 16 * 16 for s in sizes])]).astype(np.int64)
-        payload = torch.empty(int(offs[-1]), dtype=torch.uint8, device=dev)
-        if rank == 0:
-            host = np.zeros(int(offs[-1]), np.uint8)
-            for n, o, s in zip(m["names"], offs, sizes):
-                host[o:o + s] = np.ascontiguousarray(flat.arrays[n]).view(np.uint8).reshape(-1)
-            payload.copy_(torch.from_numpy(host))
-        dist.broadcast(payload, src=0)  # NCCL over NVLink
-        scene_bcast_bytes = int(offs[-1])
-        if rank != 0:
-            host = payload.cpu().numpy()
-            flat = rt.FlatScene()
-            for n, o, s, d, shp in zip(m["names"], offs, sizes, m["dtypes"], m["shapes"]):
-                flat.arrays[n] = host[o:o + s].view(np.dtype(d)).reshape(shp).copy()
-            sky_tex, def_sub = m["sky"], m["sub"]
+        from raytracer_js_b200 import parallel
+        extra = {"sky": sky_tex, "sub": def_sub} if rank == 0 else None
+        flat, extra, scene_bcast_bytes = parallel.broadcast_flat_scene(flat, 0, dev, extra)  # NCCL over NVLink
+        sky_tex, def_sub = extra["sky"], extra["sub"]
     desc = flat.desc()
     N.check(ctx, lib.rt_scene_upload(ctx, C.byref(desc)))
 

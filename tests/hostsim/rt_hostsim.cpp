@@ -9,8 +9,11 @@
 #include "../../raytracer.js_b200/csrc/rt_host.h"
 #include "../../raytracer.js_b200/csrc/rt_trace.cuh"
 
+// tile_world <= 1: full frame into rgb[height][width][3].  tile_world > 1: only the tiles of tile_rank,
+// tile-major into rgb[k][16*16][3] (the layout of rt_render_tiles_device).
 extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, const rt_params* prm, int n_threads,
-                              float* rgb, int32_t* ids, rt_counters* counters, char* errbuf, int errlen) {
+                              int tile_rank, int tile_world, float* rgb, int32_t* ids, rt_counters* counters,
+                              char* errbuf, int errlen) {
 	std::string err;
 	RtHostScene hs;
 	rt_status st = rt_pack_scene(sc, hs, err);
@@ -38,8 +41,10 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 	F.row_fr = row.data();
 	F.rgb = rgb;
 	F.first_ids = ids;
-	F.tile_rank = 0;
-	F.tile_world = 1;
+	const bool tiled = tile_world > 1;
+	F.tile_rank = tiled ? tile_rank : 0;
+	F.tile_world = tiled ? tile_world : 1;
+	F.tile_compact = tiled ? 1 : 0;
 	// the primary-ray preparation of launch_render (rt_b200.cu), on the host
 	std::vector<RtF4> prim(hs.slot_geom.size());
 	for (size_t s = 0; s < prim.size(); s++)
@@ -53,7 +58,14 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 		for (int y = t; y < F.height; y += n_threads)
 			for (int x = 0; x < F.width; x++) {
 				RtCounts c = {0, 0, 0, 0, 0};
-				render_pixel<true>(S, F, x, y, (size_t)y * F.width + x, c, errs[t]);
+				size_t out_index = (size_t)y * F.width + x;
+				if (tiled) {  // same mapping as rt_render_kernel
+					const int tiles_x = (F.width + 15) / 16;
+					const int tile = (y / 16) * tiles_x + (x / 16);
+					if (tile % tile_world != tile_rank) continue;
+					out_index = (size_t)(tile / tile_world) * 256 + (y % 16) * 16 + (x % 16);
+				}
+				render_pixel<true>(S, F, x, y, out_index, c, errs[t]);
 				part[t].segments += c.segments; part[t].nodes += c.nodes; part[t].tests += c.tests;
 				part[t].shades += c.shades; part[t].confirms += c.confirms;
 			}

@@ -180,3 +180,32 @@ def test_error_behaviour():
     assert lib.rt_scene_upload(ctx, C.byref(bad)) == N.RT_ERR_INVALID
     assert b"more than one node" in lib.rt_last_error(ctx)
     lib.rt_destroy(ctx)
+
+
+def test_tile_sharded_render_equals_full_frame():
+    """rt_render_tiles_device for every rank of a 3-way split + rt_untile_device == rt_render_device
+    (all on one GPU here; bench.py --gpus N runs one rank per GPU with an NCCL all-gather in between)."""
+    import torch
+    from raytracer_js_b200 import parallel
+    W, H, world = 200, 120, 3
+    b = scenes.random_spheres(3000, 0.01, 0.05, seed=8.0, mix="mirrors", box_fraction=0.1)
+    cam = scenes.bench_camera(W, H)
+    tracer = rt.GpuRaytracer(rt.RaytracerConfig(b.refmax, b.sky, b.default_substance, 1.0), b.tree, cam,
+                             rt.ExposureBuffer(W, H), rt.FpLcg(1.0))
+    lib, ctx = tracer.lib, tracer.ctx
+    cd, prm = rt.camera_desc(cam), tracer.params(n_frames=2)
+    dev = torch.device("cuda")
+    full = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
+    N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), 0, C.c_void_p(full.data_ptr()), None))
+    tpr = lib.rt_tiles_per_rank(W, H, world)
+    assert tpr == parallel.tiles_per_rank(W, H, world)
+    gathered = torch.zeros(world * tpr * 256 * 3, dtype=torch.float32, device=dev)
+    for r in range(world):
+        part = gathered[r * tpr * 256 * 3:]
+        N.check(ctx, lib.rt_render_tiles_device(ctx, C.byref(cd), C.byref(prm), 0, r, world, C.c_void_p(part.data_ptr()), None))
+    frame = torch.zeros_like(full)
+    N.check(ctx, lib.rt_untile_device(ctx, W, H, world, C.c_void_p(gathered.data_ptr()), C.c_void_p(frame.data_ptr())))
+    N.check(ctx, lib.rt_synchronize(ctx))
+    torch.cuda.synchronize()
+    assert torch.equal(frame, full)
+    np.testing.assert_array_equal(parallel.untile_numpy(gathered.cpu().numpy(), W, H, world).reshape(-1), full.cpu().numpy())
