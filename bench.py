@@ -183,6 +183,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     prm.refmax, prm.sky_texture, prm.default_substance = 1, sky_tex, def_sub
     prm.distance_attenuation_factor, prm.n_frames, prm.frame_first, prm.rng_seed = 1.0, 1, 0, 1.0
     prm.precision = N.RT_PRECISION_F32
+    prm.flags = 2 if args.path == "per-ray" else 0  # RT_PARAM_PER_RAY: the round-1 ray-by-ray kernel, for A/B runs
 
     npx = WIDTH * HEIGHT
     frame = torch.zeros(npx * 3, dtype=torch.float32, device=dev)
@@ -302,7 +303,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "segments_per_step": segments, "primary_paths_per_s": paths / (ms_per_step * 1e-3),
                    "frame_ms_kernel": ms_per_step, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
                    "scene_broadcast_bytes": scene_bcast_bytes,
-                   "precision": "float32 search + float64 confirmation/shading of the found hit"},
+                   "precision": "float32 search + float64 confirmation/shading of the found hit",
+                   "path": args.path},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -331,6 +333,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="pipeline", choices=["pipeline", "per-ray"],
+                    help="pipeline (default): packet primary stage + bounce stage; per-ray: every ray walked alone")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

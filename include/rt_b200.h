@@ -127,6 +127,10 @@ typedef struct rt_camera {
 
 #define RT_PRECISION_F32 0u /* float search + float64 confirmation/shading of the found hit (default) */
 
+/* rt_params.flags (validation / A-B measurement switches; results are identical either way) */
+#define RT_PARAM_NO_PRIMARY_RECORDS 1u /* no per-frame origin-relative records: every ray takes the generic path */
+#define RT_PARAM_PER_RAY 2u            /* camera rays are walked one by one too (no packet stage) */
+
 /* RaytracerConfig (src/raytracer.ts:33-43) + exposure state + the harness RNG policy */
 typedef struct rt_params {
 	int32_t refmax;

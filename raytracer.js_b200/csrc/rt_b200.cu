@@ -66,6 +66,77 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 	if (err) atomicOr(F.error_flags, err);
 }
 
+// ---- the two-stage pipeline (default): primary stage = packet walk, bounce stage = per-ray paths
+// Primary stage.  Same persistent-warp patch dispenser as above; every warp walks the octree ONCE for the
+// 32 camera rays of its patch (rt_trace.cuh: packet_primary_hits), finishes the pixels whose path ends at
+// the first hit and appends the others to the continuation queue with one warp-aggregated atomic.
+#define RT_A_WARPS 4
+__global__ void __launch_bounds__(RT_A_WARPS * 32)
+    rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_tiles,
+                      int n_patches) {
+	__shared__ int stacks[RT_A_WARPS][RT_PACKET_STACK];
+	const int lane = threadIdx.x & 31;
+	int* stack = stacks[threadIdx.x >> 5];
+	uint32_t err = 0;
+	while (true) {
+		unsigned p = 0;
+		if (lane == 0) p = atomicAdd(F.work_counter, 1u);
+		p = __shfl_sync(0xffffffffu, p, 0);
+		if (p >= (unsigned)n_patches) break;
+		const int k = (int)(p >> 3), sub = (int)(p & 7);
+		const int tile = F.tile_rank + k * F.tile_world;
+		if (tile >= n_tiles) continue;
+		const int tx = tile % tiles_x, ty = tile / tiles_x;
+		const int x[1] = {tx * RT_TILE_W + (sub & 1) * 8 + (lane & 7)};
+		const int y[1] = {ty * RT_TILE_H + (sub >> 1) * 4 + (lane >> 3)};
+		const bool valid[1] = {x[0] < F.width && y[0] < F.height};
+		const size_t out_index[1] = {
+		    F.tile_compact ? (size_t)k * RT_BLOCK + ((y[0] & (RT_TILE_H - 1)) * RT_TILE_W + (x[0] & (RT_TILE_W - 1)))
+		                   : (size_t)y[0] * F.width + x[0]};
+		bool enqueue[1];
+		int qslot[1];
+		primary_patch(S, F, x, y, valid, out_index, stack, enqueue, qslot, err);
+		const unsigned m = __ballot_sync(0xffffffffu, enqueue[0]);
+		if (m) {
+			unsigned base = 0;
+			if (lane == 0) base = atomicAdd(F.queue_count, (unsigned)__popc(m));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (enqueue[0])
+				F.queue[base + __popc(m & ((1u << lane) - 1u))] = RtQueueItem{((uint32_t)y[0] << 16) | (uint32_t)x[0], qslot[0]};
+		}
+	}
+	if (err) atomicOr(F.error_flags, err);
+}
+
+// Bounce stage.  Persistent warps drain the continuation queue 32 items at a time, one path per thread:
+// the queue is a compaction of the pixels that still have work, so every warp starts full.
+__global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
+    rt_bounce_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
+	const int lane = threadIdx.x & 31;
+	const unsigned n = *F.queue_count;
+	RtCounts cnt = {0, 0, 0, 0, 0};
+	uint32_t err = 0;
+	while (true) {
+		unsigned base = 0;
+		if (lane == 0) base = atomicAdd(F.queue_taken, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= n) break;
+		const unsigned i = base + lane;
+		if (i < n) {
+			const RtQueueItem it = F.queue[i];
+			const int x = (int)(it.xy & 0xffffu), y = (int)(it.xy >> 16);
+			size_t out_index = (size_t)y * F.width + x;
+			if (F.tile_compact) {
+				const int tile = (y / RT_TILE_H) * tiles_x + (x / RT_TILE_W);
+				out_index = (size_t)(tile / F.tile_world) * RT_BLOCK + ((y & (RT_TILE_H - 1)) * RT_TILE_W + (x & (RT_TILE_W - 1)));
+			}
+			render_pixel<false>(S, F, x, y, out_index, cnt, err, it.slot);
+		}
+		__syncwarp();
+	}
+	if (err) atomicOr(F.error_flags, err);
+}
+
 // Tile-major buffers of all ranks, concatenated [world][tiles_per_rank][16*16][3]  ->  frame [H][W][3].
 __global__ void rt_untile_kernel(const float* __restrict__ gathered, float* __restrict__ rgb, int width, int height,
                                  int tiles_x, int world, int tiles_per_rank) {
@@ -137,7 +208,8 @@ struct rt_ctx {
 	std::vector<RtD4> h_row_fr;
 	DevBuf<uint8_t> l2_scratch;
 	DevBuf<RtF4> prim_geom;
-	int render_grid[2] = {0, 0};  // persistent grid size of rt_render_kernel<false/true>
+	DevBuf<RtQueueItem> queue;
+	int render_grid[4] = {0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, primary, bounce
 };
 
 namespace {
@@ -187,12 +259,14 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	F.tile_rank = tile_rank;
 	F.tile_world = tile_world;
 	F.tile_compact = tile_compact ? 1 : 0;
-	// counters[0..7], then the persistent-warp work counter and the error flags: one memset
-	RT_CUDA(ctx, ctx->counters.alloc(10));
-	RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 10 * sizeof(unsigned long long), ctx->stream));
+	// counters[0..7], then the patch dispenser, the error flags and the two queue cursors: one memset
+	RT_CUDA(ctx, ctx->counters.alloc(12));
+	RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 12 * sizeof(unsigned long long), ctx->stream));
 	F.counters = ctx->counters.p;
 	F.work_counter = reinterpret_cast<unsigned*>(ctx->counters.p + 8);
 	F.error_flags = reinterpret_cast<uint32_t*>(ctx->counters.p + 9);
+	F.queue_count = reinterpret_cast<unsigned*>(ctx->counters.p + 10);
+	F.queue_taken = reinterpret_cast<unsigned*>(ctx->counters.p + 11);
 	const bool count = (flags & RT_RENDER_COUNTERS) != 0;
 	const int tiles_x = (F.width + RT_TILE_W - 1) / RT_TILE_W, tiles_y = (F.height + RT_TILE_H - 1) / RT_TILE_H;
 	const int n_tiles = tiles_x * tiles_y;
@@ -204,7 +278,8 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	const int n_slots = (int)H.slot_geom.size();
 	F.prim_geom = nullptr;
 	F.chain_levels = 0;
-	if (n_slots > 0) {
+	F.packet_ok = 0;
+	if (n_slots > 0 && !(prm->flags & RT_PARAM_NO_PRIMARY_RECORDS)) {
 		RT_CUDA(ctx, ctx->prim_geom.alloc((size_t)n_slots));
 		rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
 		                                                                         cam->pos[2], ctx->prim_geom.p);
@@ -215,28 +290,51 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	}
 
 	const int n_patches = my_tiles * 8;
-	int& grid = ctx->render_grid[count ? 1 : 0];
-	if (grid == 0) {
-		int per_sm = 0, sms = 0;
-		if (count)
-			RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rt_render_kernel<true>, RT_WARPS_PER_CTA * 32, 0));
-		else
-			RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rt_render_kernel<false>, RT_WARPS_PER_CTA * 32, 0));
-		RT_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-		grid = std::max(1, per_sm) * std::max(1, sms);
+	auto grid_of = [&](int which, const void* kernel, int threads, int& out) -> rt_status {
+		int& grid = ctx->render_grid[which];
+		if (grid == 0) {
+			int per_sm = 0, sms = 0;
+			RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+			RT_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+			grid = std::max(1, per_sm) * std::max(1, sms);
+		}
+		out = grid;
+		return RT_OK;
+	};
+	int grid = 0;
+	if (F.packet_ok && !count && !(prm->flags & RT_PARAM_PER_RAY)) {
+		// two-stage pipeline: packet walk for the camera segment, per-ray bounce stage for what continues
+		RT_CUDA(ctx, ctx->queue.alloc((size_t)my_tiles * RT_BLOCK));
+		F.queue = ctx->queue.p;
+		if (rt_status st = grid_of(2, (const void*)rt_primary_kernel, RT_A_WARPS * 32, grid)) return st;
+		rt_primary_kernel<<<std::min(grid, (n_patches + RT_A_WARPS - 1) / RT_A_WARPS), RT_A_WARPS * 32, 0, ctx->stream>>>(
+		    ctx->dev, F, tiles_x, n_tiles, n_patches);
+		ctx->launches++;
+		RT_CUDA(ctx, cudaGetLastError());
+		if (rt_status st = grid_of(3, (const void*)rt_bounce_kernel, RT_WARPS_PER_CTA * 32, grid)) return st;
+		rt_bounce_kernel<<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
+		                   ctx->stream>>>(ctx->dev, F, tiles_x);
+		ctx->launches++;
+		RT_CUDA(ctx, cudaGetLastError());
+		return RT_OK;
 	}
-	const int blocks = std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA);
-	if (count)
-		rt_render_kernel<true><<<blocks, RT_WARPS_PER_CTA * 32, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles, n_patches);
-	else
-		rt_render_kernel<false><<<blocks, RT_WARPS_PER_CTA * 32, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles, n_patches);
+	F.packet_ok = 0;
+	if (count) {
+		if (rt_status st = grid_of(1, (const void*)rt_render_kernel<true>, RT_WARPS_PER_CTA * 32, grid)) return st;
+		rt_render_kernel<true><<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
+		                         ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles, n_patches);
+	} else {
+		if (rt_status st = grid_of(0, (const void*)rt_render_kernel<false>, RT_WARPS_PER_CTA * 32, grid)) return st;
+		rt_render_kernel<false><<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
+		                          ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles, n_patches);
+	}
 	ctx->launches++;
 	RT_CUDA(ctx, cudaGetLastError());
 	return RT_OK;
 }
 
 rt_status read_counters(rt_ctx* ctx, rt_counters* out) {
-	unsigned long long h[10] = {0};
+	unsigned long long h[12] = {0};
 	if (ctx->counters.p)
 		RT_CUDA(ctx, cudaMemcpyAsync(h, ctx->counters.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -293,7 +391,7 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
-	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release();
+	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release();
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

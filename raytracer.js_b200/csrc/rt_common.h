@@ -8,8 +8,10 @@
 #pragma once
 #include <stdint.h>
 
+// The kernel body (rt_trace.cuh) is device code in the shipped library; the same source is compiled as
+// plain inline C++ by the test-only host build (tests/hostsim), which has no nvcc in the loop.
 #if defined(__CUDACC__)
-#define RT_HD __host__ __device__ __forceinline__
+#define RT_HD __device__ __forceinline__
 #define RT_D __device__ __forceinline__
 #else
 #define RT_HD inline
@@ -69,6 +71,15 @@ struct RtDevScene {
 
 #define RT_MAX_CHAIN 32
 
+// One pixel handed from the primary stage to the bounce stage: its path continues after the first hit
+// (mirror / transmission), or the primary search itself has to be done per ray (slot == RT_SLOT_UNKNOWN).
+struct alignas(8) RtQueueItem {
+	uint32_t xy;  // y << 16 | x
+	int32_t slot; // first-hit slot of the camera ray, or RT_SLOT_UNKNOWN
+};
+#define RT_SLOT_UNKNOWN (-2)
+#define RT_PACKET_STACK 192  // node stack of the packet walk: 7 siblings per level + 8
+
 struct RtFrame {
 	// camera
 	double pos[3];
@@ -94,10 +105,17 @@ struct RtFrame {
 	int tile_rank, tile_world;
 	int tile_compact;  // 1: outputs are tile-major [own tile k][16*16] instead of [height][width]
 	// primary-ray acceleration (exact: only skips work that provably cannot produce a hit)
-	const RtF4* prim_geom;  // [n_slots] (centre - camera, +-(radius+err)^2 | +inf for boxes), or null
+	const RtF4* prim_geom;  // [n_slots] origin-relative records (make_prim_record), or null
 	int chain_levels;       // origin chain: start_node, its parent, ..., root (post-order return order)
 	int chain_beg[RT_MAX_CHAIN], chain_end[RT_MAX_CHAIN];  // slot ranges of the chain nodes' lists
+	int chain_node[RT_MAX_CHAIN];  // the chain nodes themselves
+	int chain_oct[RT_MAX_CHAIN];   // octant of chain_node[k] that holds the origin (k = 0: the start cell)
+	int packet_ok;           // 1: camera rays may use the packet stage (chain complete, tree depth fits the stack)
 	unsigned* work_counter;  // persistent-warp patch dispenser
+	// continuation queue between the primary (packet) stage and the bounce stage
+	RtQueueItem* queue;      // [capacity]
+	unsigned* queue_count;   // items appended by the primary stage
+	unsigned* queue_taken;   // consumer cursor of the bounce stage
 };
 
 #define RT_ERRFLAG_TEXTURE 1u

@@ -28,6 +28,7 @@ struct RtHostScene {
 	double root_size = 1;
 	float err_l = 0;
 	bool any_transmission = false;
+	int max_depth = 0;  // deepest node level (root = 0)
 };
 
 inline std::string rt_format(const char* fmt, ...) {
@@ -90,6 +91,15 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 			hs.node_child[(size_t)i * 8 + c] = ch;
 		}
 		for (int k = 0; k < 3; k++) scale = std::max(scale, std::fabs(p[k]) + s);
+	}
+	{
+		std::vector<int> depth(N, 0);
+		hs.max_depth = 0;
+		for (uint32_t i = 1; i < N; i++) {
+			if ((uint32_t)sc->node_parent[i] >= i) RT_FAIL(RT_ERR_INVALID, "node %u: nodes must be numbered parent-first", i);
+			depth[i] = depth[sc->node_parent[i]] + 1;
+			hs.max_depth = std::max(hs.max_depth, depth[i]);
+		}
 	}
 	hs.slot_geom.resize(L);
 	hs.slot_geom64.resize(L);
@@ -328,9 +338,16 @@ inline rt_status rt_fill_frame(const RtHostScene& hs, const rt_camera* cam, cons
 // returns them (post-order), as slot ranges for the lock-step pre-test (rt_trace.cuh: pretest_chain).
 inline void rt_fill_chain(const RtHostScene& hs, RtFrame& F) {
 	F.chain_levels = 0;
-	for (int n = F.start_node; n >= 0 && F.chain_levels < RT_MAX_CHAIN; n = hs.node_link[n].x) {
-		F.chain_beg[F.chain_levels] = hs.node_link[n].z;
-		F.chain_end[F.chain_levels] = hs.node_link[n].z + hs.node_link[n].w;
-		F.chain_levels++;
+	F.packet_ok = 0;
+	int n = F.start_node, oct = F.start_octant;
+	for (; n >= 0 && F.chain_levels < RT_MAX_CHAIN; n = hs.node_link[n].x) {
+		const int k = F.chain_levels++;
+		F.chain_beg[k] = hs.node_link[n].z;
+		F.chain_end[k] = hs.node_link[n].z + hs.node_link[n].w;
+		F.chain_node[k] = n;
+		F.chain_oct[k] = oct;
+		oct = hs.node_link[n].y;
 	}
+	// the packet stage needs the whole chain (up to the root) and a node stack that cannot overflow
+	F.packet_ok = (F.start_node >= 0 && n < 0 && 7 * hs.max_depth + 8 <= RT_PACKET_STACK) ? 1 : 0;
 }

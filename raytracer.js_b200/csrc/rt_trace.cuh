@@ -23,7 +23,7 @@
 
 // ------------------------------------------------------------------ exact float64 primitives
 // No FMA contraction: the reference rounds after every multiply and add.
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 RT_HD double xmul(double a, double b) { return __dmul_rn(a, b); }
 RT_HD double xadd(double a, double b) { return __dadd_rn(a, b); }
 RT_HD double xsub(double a, double b) { return __dsub_rn(a, b); }
@@ -40,7 +40,7 @@ RT_HD double xsqrt(double a) { return sqrt(a); }
 
 // ------------------------------------------------------------------ loads (read-only path, 16 B)
 RT_HD RtF4 ld(const RtF4* p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 	const float4 v = __ldg(reinterpret_cast<const float4*>(p));
 	return RtF4{v.x, v.y, v.z, v.w};
 #else
@@ -48,7 +48,7 @@ RT_HD RtF4 ld(const RtF4* p) {
 #endif
 }
 RT_HD RtI4 ld(const RtI4* p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 	const int4 v = __ldg(reinterpret_cast<const int4*>(p));
 	return RtI4{v.x, v.y, v.z, v.w};
 #else
@@ -56,7 +56,7 @@ RT_HD RtI4 ld(const RtI4* p) {
 #endif
 }
 RT_HD RtD2 ld(const RtD2* p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 	const double2 v = __ldg(reinterpret_cast<const double2*>(p));
 	return RtD2{v.x, v.y};
 #else
@@ -64,7 +64,7 @@ RT_HD RtD2 ld(const RtD2* p) {
 #endif
 }
 RT_HD RtD4 ld(const RtD4* p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 	const double2 a = __ldg(reinterpret_cast<const double2*>(p));
 	const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
 	return RtD4{a.x, a.y, b.x, b.y};
@@ -73,7 +73,7 @@ RT_HD RtD4 ld(const RtD4* p) {
 #endif
 }
 RT_HD int ld(const int* p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 	return __ldg(p);
 #else
 	return *p;
@@ -288,8 +288,7 @@ RT_HD int entity_at_pos(const RtDevScene& S, const double* p) {
 
 // ------------------------------------------------------------------ the walk
 // Per-segment search context.  `rel` (optional) is the per-frame origin-relative copy of slot_geom for
-// rays that start at the camera (see rt_prepare_primary): (centre - origin, +-(radius+err)^2) with the
-// sign carrying "origin inside the sphere", +inf marking a box (handled by the generic test).
+// rays that start at the camera (see make_prim_record / rt_prepare_primary).
 struct RtSearch {
 	RtRayF r;
 	const RtF4* rel;        // non-null: primary segment, origin-relative sphere tests
@@ -297,31 +296,34 @@ struct RtSearch {
 	int chain_levels;       // number of chain levels that were pre-tested (0: scan everything)
 };
 
-// candidate test against the origin-relative record (primary rays): ~12 flops, no centre - origin
-// subtraction, no cancellation (the difference was taken in float64 on the host side of the frame)
+// The per-frame origin-relative record of one slot, for rays that start at the camera:
+//   xyz = centre - camera, taken in float64 (no cancellation) and rounded once;
+//   w   = +(radius+err)^2          sphere, camera outside it: the quick test of candidate_rel applies
+//         -(bounding radius+err)^2 box, camera outside its bounding sphere: packet cull on the bounding
+//                                  sphere, per-ray test = the generic slab test on slot_geom
+//         +inf                     camera inside the (bounding) sphere: always a candidate
+RT_HD RtF4 make_prim_record(const RtD4& g, bool is_sphere, double ox, double oy, double oz, float err_l) {
+	const double cx = g.x - ox, cy = g.y - oy, cz = g.z - oz;
+	const float rr = (is_sphere ? (float)(g.w * 0.5) : (float)(g.w * 0.8660254037844387) * 1.000001f) + err_l;
+	const float rr2 = rr * rr;
+	const bool inside = cx * cx + cy * cy + cz * cz <= (double)rr2 * 1.000001;
+	return RtF4{(float)cx, (float)cy, (float)cz, inside ? INFINITY : (is_sphere ? rr2 : -rr2)};
+}
+
+// candidate test against the origin-relative sphere record (w finite, > 0): ~12 flops, no
+// centre - origin subtraction
 RT_HD bool candidate_rel(const RtF4& g, const RtRayF& r) {
 	const float tca = g.x * r.dx + g.y * r.dy + g.z * r.dz;
 	const float s = tca * r.inv_a;
 	const float lx = g.x - s * r.dx, ly = g.y - s * r.dy, lz = g.z - s * r.dz;
 	const float l2 = lx * lx + ly * ly + lz * lz;
-	return l2 <= fabsf(g.w) && (tca >= 0.0f || g.w < 0.0f);
-}
-
-// The per-frame origin-relative record of one slot (see RtSearch::rel).  centre - camera is taken in
-// float64 (no cancellation) and rounded once.
-RT_HD RtF4 make_prim_record(const RtD4& g, bool is_sphere, double ox, double oy, double oz, float err_l) {
-	if (!is_sphere) return RtF4{0.f, 0.f, 0.f, INFINITY};  // box: use the generic slab test
-	const double cx = g.x - ox, cy = g.y - oy, cz = g.z - oz;
-	const float rr = (float)(g.w * 0.5) + err_l;
-	const float rr2 = rr * rr;
-	const bool inside = cx * cx + cy * cy + cz * cz <= (double)rr2;
-	return RtF4{(float)cx, (float)cy, (float)cz, inside ? -rr2 : rr2};
+	return l2 <= g.w && tca >= 0.0f;  // camera outside the sphere: a forward root needs the centre ahead
 }
 
 RT_HD bool slot_candidate(const RtDevScene& S, const RtSearch& q, int s) {
 	if (q.rel) {
 		const RtF4 g = ld(q.rel + s);
-		if (g.w != INFINITY) return candidate_rel(g, q.r);
+		if (g.w > 0.0f && g.w != INFINITY) return candidate_rel(g, q.r);
 	}
 	return candidate(ld(S.slot_geom + s), q.r, S.err_l);
 }
@@ -470,6 +472,306 @@ RT_HD unsigned pretest_chain(const RtFrame& F, const RtDevScene& S, const RtSear
 	return mask;
 }
 
+// ------------------------------------------------------------------ the packet walk (camera rays)
+// All camera rays share one origin, so the 32 rays of an 8x4-pixel patch form a narrow packet.  The
+// reference's visit order does not depend on the individual ray once the signs of the
+// direction components are fixed: among the octants of a node a ray can only move from octant a to
+// octant b if (a ^ neg) is a bitwise subset of (b ^ neg) (neg = mask of negative direction signs), so
+// "children in ascending (octant ^ neg), pre-order" is a linear extension of every ray's own order, and
+// the nodes that contain the origin are returned after everything below them (post-order).  A node the
+// packet visits but one ray does not pierce cannot hold a hit for that ray (every entity lies inside its
+// node's cube, src/octree_entity.ts:60-79), so visiting the UNION of the rays' nodes in that order gives
+// every ray its own first hit.  The warp therefore walks ONE node sequence in lock-step, and the lanes
+// are used twice over:
+//   * list scan: lane j tests slot base+j against the packet's bounding cone (coalesced 16-byte loads,
+//     one vote), and only the survivors are tested ray by ray (one uniform 16-byte load each);
+//   * child selection: lanes 0..7 test the 8 octants of the popped node against the packet's slab
+//     intervals and push the survivors with one vote.
+// Written once for both builds: per-lane values are arrays of RT_NL elements (1 on the device, where a
+// lane is a thread; 32 in the test-only host build, where a lane is a loop iteration).
+#if defined(__CUDACC__)
+#define RT_NL 1
+#define RT_LANES(l, lane) for (int l = 0, lane = (int)(threadIdx.x & 31u); l < 1; ++l)
+#else
+#define RT_NL 32
+#define RT_LANES(l, lane) for (int l = 0, lane = 0; l < 32; ++l, ++lane)
+#endif
+
+RT_HD unsigned warp_ballot(const bool (&p)[RT_NL]) {
+#if defined(__CUDACC__)
+	return __ballot_sync(0xffffffffu, p[0]);
+#else
+	unsigned m = 0;
+	for (int l = 0; l < 32; l++) m |= (p[l] ? 1u : 0u) << l;
+	return m;
+#endif
+}
+// min / max of NON-NEGATIVE floats (their bit patterns order like unsigned integers): one redux.sync
+RT_HD float warp_min_pos(const float (&v)[RT_NL]) {
+#if defined(__CUDACC__)
+	return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v[0])));
+#else
+	float m = v[0];
+	for (int l = 1; l < 32; l++) m = v[l] < m ? v[l] : m;
+	return m;
+#endif
+}
+RT_HD float warp_max_pos(const float (&v)[RT_NL]) {
+#if defined(__CUDACC__)
+	return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v[0])));
+#else
+	float m = v[0];
+	for (int l = 1; l < 32; l++) m = v[l] > m ? v[l] : m;
+	return m;
+#endif
+}
+RT_HD float warp_get(const float (&v)[RT_NL], int src) {
+#if defined(__CUDACC__)
+	return __shfl_sync(0xffffffffu, v[0], src);
+#else
+	return v[src];
+#endif
+}
+RT_HD int warp_get(const int (&v)[RT_NL], int src) {
+#if defined(__CUDACC__)
+	return __shfl_sync(0xffffffffu, v[0], src);
+#else
+	return v[src];
+#endif
+}
+RT_HD void warp_sync() {
+#if defined(__CUDACC__)
+	__syncwarp();
+#endif
+}
+RT_HD int popc32(unsigned m) {
+#if defined(__CUDACC__)
+	return __popc(m);
+#else
+	return __builtin_popcount(m);
+#endif
+}
+RT_HD int ffs32(unsigned m) {  // index of the lowest set bit, m != 0
+#if defined(__CUDACC__)
+	return __ffs((int)m) - 1;
+#else
+	return __builtin_ctz(m);
+#endif
+}
+
+// Warp-uniform bounds of the packet.
+struct RtPacket {
+	float ox, oy, oz;      // the shared origin
+	float ax, ay, az;      // unit axis of the bounding cone
+	float sin_h, cos2_h;   // half-angle of the cone (inflated)
+	float inv_lo[3];       // min over the lanes of |1/d_k|
+	float inv_hi[3];       // max over the lanes of |1/d_k|
+	int neg;               // bit k: d_k < 0 (for every lane)
+	float err_l;
+};
+
+// Conservative "may any ray of the packet pierce the cube [lo, lo+h]^3" by slab intervals.  With a
+// shared origin the entry/exit parameters of axis k are u * |1/d_k| with u the signed distance to the
+// near / far plane along the direction of travel, so their extremes over the packet are u times the
+// extremes of |1/d_k|.
+RT_HD bool packet_pierces_cube(const RtPacket& P, float lox, float loy, float loz, float h) {
+	const float lo[3] = {lox, loy, loz};
+	const float o[3] = {P.ox, P.oy, P.oz};
+	float tnear = 0.0f, tfar = INFINITY;
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const float un = (((P.neg >> k) & 1) ? o[k] - (lo[k] + h) : lo[k] - o[k]) - P.err_l;
+		const float uf = un + h + 2.0f * P.err_l;
+		const float tn = un * (un >= 0.0f ? P.inv_lo[k] : P.inv_hi[k]);
+		const float tf = uf * (uf >= 0.0f ? P.inv_hi[k] : P.inv_lo[k]);
+		tnear = fmaxf(tnear, tn);
+		tfar = fminf(tfar, tf);
+	}
+	return tnear <= tfar * 1.00001f;
+}
+
+// Conservative "may the (bounding) sphere of this origin-relative record meet the packet's cone".
+// Distance from the centre to the cone's lateral surface is perp*cos - t*sin (t along the axis, perp
+// across it) wherever that surface is the nearest part of the cone, and never more than the true
+// distance elsewhere.
+RT_HD bool packet_meets_record(const RtPacket& P, const RtF4& g) {
+	if (g.w == INFINITY) return true;
+	const float t = g.x * P.ax + g.y * P.ay + g.z * P.az;
+	const float px = g.x - t * P.ax, py = g.y - t * P.ay, pz = g.z - t * P.az;
+	const float perp2 = px * px + py * py + pz * pz;
+	const float rhs = sqrtf(fabsf(g.w)) + t * P.sin_h;
+	return rhs >= 0.0f && perp2 * P.cos2_h <= rhs * rhs * 1.00001f;
+}
+
+// bit k of the result = bit (k ^ x) of m (8-bit mask): octant mask -> visit-order mask
+RT_HD unsigned xor_permute8(unsigned m, int x) {
+	if (x & 1) m = ((m & 0x55u) << 1) | ((m & 0xaau) >> 1);
+	if (x & 2) m = ((m & 0x33u) << 2) | ((m & 0xccu) >> 2);
+	if (x & 4) m = ((m & 0x0fu) << 4) | ((m & 0xf0u) >> 4);
+	return m;
+}
+
+// First-hit slot of every lane's camera ray (direction dir[l], float64) in the reference's visit order, or
+// -1.  Lanes with skip[l] set (pixels outside the frame) take no part but must carry a valid direction.
+// `stack` is RT_PACKET_STACK ints private to the warp.  A patch whose rays differ in the sign of a
+// direction component (it straddles one of the three great circles through the axes) is walked once per
+// sign class.  unresolved[l] is set for lanes that cannot take part in any lock-step walk (a zero
+// direction component; node stack overflow): the caller searches those ray by ray.
+RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const double (&dir)[RT_NL][3], const RtRayF (&r)[RT_NL],
+                             const RtPacket& P, bool (&done)[RT_NL], int* stack, int (&hit_slot)[RT_NL], bool& overflow);
+
+RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const double (&dir)[RT_NL][3], const bool (&skip)[RT_NL],
+                               int* stack, int (&hit_slot)[RT_NL], bool (&unresolved)[RT_NL]) {
+	RtRayF r[RT_NL];
+	int neg[RT_NL];
+	bool todo[RT_NL];
+	float ix[RT_NL], iy[RT_NL], iz[RT_NL], nx[RT_NL], ny[RT_NL], nz[RT_NL];
+	RT_LANES(l, lane) {
+		(void)lane;
+		r[l] = make_ray_f(F.pos, dir[l]);
+		neg[l] = (r[l].dx < 0.0f ? 1 : 0) | (r[l].dy < 0.0f ? 2 : 0) | (r[l].dz < 0.0f ? 4 : 0);
+		ix[l] = fabsf(r[l].ix); iy[l] = fabsf(r[l].iy); iz[l] = fabsf(r[l].iz);
+		const float k = sqrtf(r[l].inv_a);
+		nx[l] = r[l].dx * k; ny[l] = r[l].dy * k; nz[l] = r[l].dz * k;
+		hit_slot[l] = -1;
+		unresolved[l] = !skip[l] && !(r[l].dx != 0.0f && r[l].dy != 0.0f && r[l].dz != 0.0f && ix[l] < 1e30f &&
+		                              iy[l] < 1e30f && iz[l] < 1e30f);
+		todo[l] = !skip[l] && !unresolved[l];
+	}
+	unsigned todo_mask = warp_ballot(todo);
+	while (todo_mask) {
+		// ---- one sign class: the lanes whose direction signs equal those of the first lane still to do
+		RtPacket P;
+		const int first = ffs32(todo_mask);
+		P.neg = warp_get(neg, first);
+		bool in_class[RT_NL], done[RT_NL];
+		RT_LANES(l, lane) { (void)lane; in_class[l] = todo[l] && neg[l] == P.neg; }
+		const unsigned class_mask = warp_ballot(in_class);
+		int last = 31;
+		while (!((class_mask >> last) & 1u)) last--;
+		{
+			float lo[RT_NL], hi[RT_NL];
+#define RT_RANGE(src, k)                                                           \
+	RT_LANES(l, lane) { (void)lane; lo[l] = in_class[l] ? src[l] : INFINITY; hi[l] = in_class[l] ? src[l] : 0.0f; } \
+	P.inv_lo[k] = warp_min_pos(lo) * 0.99999f;                                     \
+	P.inv_hi[k] = warp_max_pos(hi) * 1.00001f;
+			RT_RANGE(ix, 0)
+			RT_RANGE(iy, 1)
+			RT_RANGE(iz, 2)
+#undef RT_RANGE
+			// cone axis: bisector of the first and the last ray of the class; half-angle: the widest lane
+			const float ax = warp_get(nx, first) + warp_get(nx, last), ay = warp_get(ny, first) + warp_get(ny, last),
+			            az = warp_get(nz, first) + warp_get(nz, last);
+			const float k = 1.0f / sqrtf(ax * ax + ay * ay + az * az);
+			P.ax = ax * k; P.ay = ay * k; P.az = az * k;
+			RT_LANES(l, lane) {
+				(void)lane;
+				const float t = nx[l] * P.ax + ny[l] * P.ay + nz[l] * P.az;
+				const float px = nx[l] - t * P.ax, py = ny[l] - t * P.ay, pz = nz[l] - t * P.az;
+				hi[l] = in_class[l] ? sqrtf(px * px + py * py + pz * pz) : 0.0f;
+			}
+			P.sin_h = warp_max_pos(hi) * 1.0001f + 1e-6f;
+			P.cos2_h = 1.0f - P.sin_h * P.sin_h;
+			P.ox = (float)F.pos[0]; P.oy = (float)F.pos[1]; P.oz = (float)F.pos[2];
+			P.err_l = S.err_l;
+		}
+		bool overflow = !(P.sin_h < 0.5f);  // not a narrow packet (tiny frames): ray by ray
+		RT_LANES(l, lane) { (void)lane; done[l] = !in_class[l]; }
+		if (!overflow) packet_walk_class(S, F, dir, r, P, done, stack, hit_slot, overflow);
+		RT_LANES(l, lane) {
+			(void)lane;
+			if (in_class[l]) {
+				todo[l] = false;
+				if (overflow) { unresolved[l] = true; hit_slot[l] = -1; }
+			}
+		}
+		todo_mask &= ~class_mask;
+	}
+}
+
+RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const double (&dir)[RT_NL][3], const RtRayF (&r)[RT_NL],
+                             const RtPacket& P, bool (&done)[RT_NL], int* stack, int (&hit_slot)[RT_NL], bool& overflow) {
+	int sp = 0;
+	// pushes the children of node n (cube g) the packet may pierce, last-visited first; after_oct >= 0:
+	// only the octants a ray can still reach from octant after_oct (the origin's cell / the chain child)
+	auto push_children = [&](int n, const RtF4& g, int after_oct) {
+		bool ok[RT_NL];
+		int child[RT_NL];
+		const float h = g.w * 0.5f;
+		const int want = after_oct >= 0 ? (after_oct ^ P.neg) : 0;
+		RT_LANES(l, lane) {
+			const int o = lane & 7;
+			child[l] = ld(S.node_child + n * 8 + o);
+			const int key = o ^ P.neg;
+			ok[l] = lane < 8 && child[l] >= 0 && (key & want) == want && o != after_oct &&
+			        packet_pierces_cube(P, g.x + ((o & 1) ? h : 0.0f), g.y + ((o & 2) ? h : 0.0f),
+			                            g.z + ((o & 4) ? h : 0.0f), h);
+		}
+		const unsigned m = warp_ballot(ok) & 0xffu;
+		if (!m) return;
+		if (sp + 8 > RT_PACKET_STACK) { overflow = true; return; }
+		const unsigned mk = xor_permute8(m, P.neg);  // bit = visit key
+		RT_LANES(l, lane) {
+			if (ok[l]) {
+				const int key = (lane & 7) ^ P.neg;
+				stack[sp + popc32(mk >> (key + 1))] = child[l];  // smaller key = popped earlier = higher
+			}
+		}
+		sp += popc32(m);
+		warp_sync();
+	};
+	// scans slots [beg,end) in list order; returns true when every lane has its hit
+	auto scan = [&](int beg, int end) -> bool {
+		for (int base = beg; base < end; base += 32) {
+			bool pass[RT_NL];
+			RT_LANES(l, lane) {
+				const int s = base + lane;
+				pass[l] = s < end && packet_meets_record(P, ld(F.prim_geom + s));
+			}
+			unsigned m = warp_ballot(pass);
+			if (!m) continue;
+			while (m) {
+				const int slot = base + ffs32(m);
+				m &= m - 1;
+				const RtF4 g = ld(F.prim_geom + slot);
+				RT_LANES(l, lane) {
+					(void)lane;
+					if (!done[l]) {
+						const bool quick = g.w > 0.0f && g.w != INFINITY;
+						const bool cand = quick ? candidate_rel(g, r[l]) : candidate(ld(S.slot_geom + slot), r[l], S.err_l);
+						if (cand) {
+							RtCollision col;
+							const RtD4 g64 = ld(S.slot_geom64 + slot);
+							const bool hit = ld(S.slot_geom + slot).w > 0.0f ? exact_sphere(g64, F.pos, dir[l], col)
+							                                                  : exact_box(g64, F.pos, dir[l], col);
+							if (hit) {
+								hit_slot[l] = slot;
+								done[l] = true;
+							}
+						}
+					}
+				}
+			}
+			if (warp_ballot(done) == 0xffffffffu) return true;
+		}
+		return false;
+	};
+
+	for (int k = 0; k < F.chain_levels; k++) {
+		const int A = F.chain_node[k];
+		push_children(A, ld(S.node_geom + A), F.chain_oct[k]);
+		while (sp > 0 && !overflow) {
+			const int n = stack[--sp];
+			warp_sync();
+			const RtI4 link = ld(S.node_link + n);
+			if (link.w > 0 && scan(link.z, link.z + link.w)) return;
+			push_children(n, ld(S.node_geom + n), -1);
+		}
+		if (overflow) return;
+		if (F.chain_end[k] > F.chain_beg[k] && scan(F.chain_beg[k], F.chain_end[k])) return;
+	}
+}
+
 // ------------------------------------------------------------------ shading helpers
 // uv_map_sphere (src/math/uv_mapping.ts:19-25)
 RT_HD void uv_map_sphere(const double* v, double& u, double& w) {
@@ -533,8 +835,10 @@ RT_HD double rng_next(RtRng& g) {
 // ------------------------------------------------------------------ Ray.trace (src/raytracer.ts:168-277)
 // One path for one pixel of one exposure frame.  `dir` is the camera direction (un-normalised, as
 // the reference passes it).  Returns the path colour in `out`, and the entity of the first collision.
+// `primary_slot`: the first-hit slot of the camera segment when the primary stage already found it
+// (>= 0), or RT_SLOT_UNKNOWN to search here.
 template <bool COUNT>
-RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_in, double pixel_seed,
+RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_in, double pixel_seed, int primary_slot,
                       double* out, int& first_entity, RtCounts& cnt, uint32_t& err) {
 	double refpoint[3] = {F.pos[0], F.pos[1], F.pos[2]};
 	double dir[3] = {dir_in[0], dir_in[1], dir_in[2]};
@@ -564,21 +868,30 @@ RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_i
 			octant = -1;
 		}
 		RtCollision ci;
-		RtSearch q;
-		q.r = make_ray_f(refpoint, dir);
-		q.rel = nullptr;
-		q.chain_mask = 0xffffffffu;
-		q.chain_levels = 0;
-		if (primary && F.prim_geom) {
-			// camera rays: origin-relative records + lock-step pre-test of the shared origin chain
-			q.rel = F.prim_geom;
-			if (have_node) {
-				q.chain_levels = F.chain_levels;
-				q.chain_mask = pretest_chain(F, S, q);
+		int slot;
+		if (primary && primary_slot >= 0) {
+			// found by the packet stage: only the collision itself is recomputed (same float64 formula)
+			slot = primary_slot;
+			const RtD4 g = ld(S.slot_geom64 + slot);
+			const bool hit = ld(S.slot_geom + slot).w > 0.0f ? exact_sphere(g, refpoint, dir, ci) : exact_box(g, refpoint, dir, ci);
+			if (!hit) break;  // cannot happen: the packet stage confirmed it with the same formula
+		} else {
+			RtSearch q;
+			q.r = make_ray_f(refpoint, dir);
+			q.rel = nullptr;
+			q.chain_mask = 0xffffffffu;
+			q.chain_levels = 0;
+			if (primary && F.prim_geom) {
+				// camera rays: origin-relative records + lock-step pre-test of the shared origin chain
+				q.rel = F.prim_geom;
+				if (have_node) {
+					q.chain_levels = F.chain_levels;
+					q.chain_mask = pretest_chain(F, S, q);
+				}
 			}
+			slot = walk_and_scan<COUNT>(S, q, node, octant, refpoint, dir, ci, cnt);
 		}
 		primary = false;
-		const int slot = walk_and_scan<COUNT>(S, q, node, octant, refpoint, dir, ci, cnt);
 		if (slot < 0) break;  // miss: sky
 		const RtI4 attr = ld(S.slot_attr + slot);
 		if (first_entity < 0) first_entity = attr.x;
@@ -693,7 +1006,7 @@ RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_i
 // (src/view/exposure_buffer.ts:77-91) for n_frames consecutive frames.
 template <bool COUNT>
 RT_HD void render_pixel(const RtDevScene& S, const RtFrame& F, int x, int y, size_t out_index, RtCounts& cnt,
-                        uint32_t& err) {
+                        uint32_t& err, int primary_slot = RT_SLOT_UNKNOWN) {
 	// camera direction: get_dir_for_each_pixel (src/view/camera.ts:207-250) through the host-built
 	// tables of the accumulated scan rotations
 	const RtD4 fr = ld(F.row_fr + y);
@@ -710,7 +1023,7 @@ RT_HD void render_pixel(const RtDevScene& S, const RtFrame& F, int x, int y, siz
 		const double seed = xadd(xadd(F.rng_seed, (double)pix),
 		                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
 		double c[3];
-		trace_path<COUNT>(S, F, dir, seed, c, first_entity, cnt, err);
+		trace_path<COUNT>(S, F, dir, seed, primary_slot, c, first_entity, cnt, err);
 		const double w = xdiv(1.0, (double)(1u + frame_count));
 		const double w1 = xsub(1.0, w);
 #pragma unroll
@@ -718,4 +1031,115 @@ RT_HD void render_pixel(const RtDevScene& S, const RtFrame& F, int x, int y, siz
 	}
 	o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
 	if (F.first_ids) F.first_ids[out_index] = first_entity;
+}
+
+// ------------------------------------------------------------------ primary stage: one 8x4 patch of camera rays
+// The first iteration of Ray.trace (src/raytracer.ts:179-263) for a camera ray whose first-hit slot is
+// known, when the path ENDS there: miss -> sky (:267-271), acute-normal guard (:200-203), light (:215-218,
+// :273-275), non-mirror REFLECTION (:222-225), BOTH/default (:250-251), refmax reached (:256-263).
+// Returns false when the path continues (mirror bounce or transmission): the bounce stage traces it.
+RT_HD bool primary_terminal(const RtDevScene& S, const RtFrame& F, const double* dir, int slot, double* out,
+                            int& first_entity, uint32_t& err) {
+	first_entity = -1;
+	if (slot < 0) {  // SkySphere.get_color (src/sky/sky_sphere.ts:22-27); colour starts at (1,1,1)
+		double sc[3];
+		if (!texture_color(S, F.sky_texture, true, dir, sc)) err |= RT_ERRFLAG_TEXTURE;
+		out[0] = xmul(1.0, sc[0]); out[1] = xmul(1.0, sc[1]); out[2] = xmul(1.0, sc[2]);
+		return true;
+	}
+	const RtI4 attr = ld(S.slot_attr + slot);
+	const RtMaterial m = S.materials[attr.y & RT_ATTR_MAT_MASK];
+	const uint32_t response = m.flags & RT_MAT_RESPONSE_MASK;
+	const bool bounces = !(m.flags & RT_MAT_LIGHT) && ((response == 0u && (m.flags & RT_MAT_MIRROR)) || response == 1u);
+	if (bounces && F.refmax > 1) return false;
+	first_entity = attr.x;
+	const bool is_sphere = (attr.y >> RT_ATTR_TYPE_SHIFT) == 0;
+	const RtD4 g = ld(S.slot_geom64 + slot);
+	RtCollision ci;
+	const bool hit = is_sphere ? exact_sphere(g, F.pos, dir, ci) : exact_box(g, F.pos, dir, ci);
+	if (!hit) return false;  // cannot happen (same formula as the confirmation); let the bounce stage decide
+	if (dot3(dir, ci.normal) >= 0) {
+		err |= RT_ERRFLAG_ACUTE;
+		out[0] = out[1] = out[2] = 1.0;
+		return true;
+	}
+	const double rel[3] = {xsub(ci.point[0], g.x), xsub(ci.point[1], g.y), xsub(ci.point[2], g.z)};
+	double tc[3];
+	if (!texture_color(S, attr.z, is_sphere, rel, tc)) err |= RT_ERRFLAG_TEXTURE;
+	double col[3] = {xmul(1.0, tc[0]), xmul(1.0, tc[1]), xmul(1.0, tc[2])};
+	if (m.flags & RT_MAT_LIGHT) {
+		const double dd[3] = {xsub(ci.point[0], F.pos[0]), xsub(ci.point[1], F.pos[1]), xsub(ci.point[2], F.pos[2])};
+		const double t = xmul(xadd(0.0, xsqrt(dot3(dd, dd))), F.attenuation);
+		const double isl = xdiv(1.0, xadd(RT_JS_EPSILON, xmul(t, t)));
+		col[0] = xmul(col[0], isl); col[1] = xmul(col[1], isl); col[2] = xmul(col[2], isl);
+	} else if (bounces) {  // refcount (1) >= refmax
+		col[0] = col[1] = col[2] = 0.0;
+	}
+	out[0] = col[0]; out[1] = col[1]; out[2] = col[2];
+	return true;
+}
+
+// ExposureBuffer.set_color_i (src/view/exposure_buffer.ts:77-91) for n_frames frames of the SAME sample
+// (a path that ends at its first hit never draws from the RNG, and there is no pixel jitter: SURVEY.md F6).
+RT_HD void store_constant_sample(const RtFrame& F, size_t out_index, const double* c, int first_entity) {
+	float* o = F.rgb + out_index * 3;
+	float px[3] = {0.f, 0.f, 0.f};
+	if (F.frame_first > 0) { px[0] = o[0]; px[1] = o[1]; px[2] = o[2]; }
+	for (uint32_t f = 0; f < F.n_frames; f++) {
+		const double w = xdiv(1.0, (double)(1u + F.frame_first + f));
+		const double w1 = xsub(1.0, w);
+#pragma unroll
+		for (int k = 0; k < 3; k++) px[k] = (float)xadd(xmul(c[k], w), xmul((double)px[k], w1));
+	}
+	o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
+	if (F.first_ids) F.first_ids[out_index] = first_entity;
+}
+
+// Camera direction of pixel (x,y): get_dir_for_each_pixel (src/view/camera.ts:207-250) through the
+// host-built tables of the accumulated scan rotations.
+RT_HD void pixel_dir(const RtFrame& F, int x, int y, double* dir) {
+	const RtD4 fr = ld(F.row_fr + y);
+	const RtD2 cs = ld(F.col_cs + x);
+	dir[0] = xadd(xmul(fr.x, cs.x), xmul(F.lf[0], cs.y));
+	dir[1] = xadd(xmul(fr.y, cs.x), xmul(F.lf[1], cs.y));
+	dir[2] = xadd(xmul(fr.z, cs.x), xmul(F.lf[2], cs.y));
+}
+
+// The whole primary stage for one patch.  Pixels whose path ends at the first hit are finished here;
+// for the others enqueue[l] is set and qslot[l] holds the known first-hit slot (or RT_SLOT_UNKNOWN when
+// the packet could not be walked in lock-step).
+RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const int (&x)[RT_NL], const int (&y)[RT_NL],
+                         const bool (&valid)[RT_NL], const size_t (&out_index)[RT_NL], int* stack, bool (&enqueue)[RT_NL],
+                         int (&qslot)[RT_NL], uint32_t& err) {
+	double dir[RT_NL][3];
+	bool skip[RT_NL], unresolved[RT_NL];
+	int hit_slot[RT_NL];
+	RT_LANES(l, lane) {
+		(void)lane;
+		// lanes outside the frame ride along with the direction of the nearest pixel inside it
+		pixel_dir(F, x[l] < F.width ? x[l] : F.width - 1, y[l] < F.height ? y[l] : F.height - 1, dir[l]);
+		skip[l] = !valid[l];
+		unresolved[l] = valid[l];
+		hit_slot[l] = -1;
+	}
+	if (F.packet_ok) packet_primary_hits(S, F, dir, skip, stack, hit_slot, unresolved);
+	RT_LANES(l, lane) {
+		(void)lane;
+		enqueue[l] = false;
+		qslot[l] = RT_SLOT_UNKNOWN;
+		if (valid[l]) {
+			if (unresolved[l]) {
+				enqueue[l] = true;
+			} else {
+				double c[3];
+				int first_entity;
+				if (primary_terminal(S, F, dir[l], hit_slot[l], c, first_entity, err)) {
+					store_constant_sample(F, out_index[l], c, first_entity);
+				} else {
+					enqueue[l] = true;
+					qslot[l] = hit_slot[l];
+				}
+			}
+		}
+	}
 }

@@ -11,9 +11,12 @@
 
 // tile_world <= 1: full frame into rgb[height][width][3].  tile_world > 1: only the tiles of tile_rank,
 // tile-major into rgb[k][16*16][3] (the layout of rt_render_tiles_device).
+// pipeline != 0: the two-stage pipeline of rt_b200.cu (primary_patch per 8x4 patch with the 32 lanes as loop
+// iterations, then the bounce stage over the continuation queue); no work counters in that mode.
+// pipeline == 0: every path ray by ray with the counting variant (what rt_render_kernel<true> runs).
 extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, const rt_params* prm, int n_threads,
-                              int tile_rank, int tile_world, float* rgb, int32_t* ids, rt_counters* counters,
-                              char* errbuf, int errlen) {
+                              int tile_rank, int tile_world, int pipeline, float* rgb, int32_t* ids,
+                              rt_counters* counters, char* errbuf, int errlen) {
 	std::string err;
 	RtHostScene hs;
 	rt_status st = rt_pack_scene(sc, hs, err);
@@ -49,9 +52,71 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 	std::vector<RtF4> prim(hs.slot_geom.size());
 	for (size_t s = 0; s < prim.size(); s++)
 		prim[s] = make_prim_record(hs.slot_geom64[s], hs.slot_geom[s].w > 0.0f, cam->pos[0], cam->pos[1], cam->pos[2], hs.err_l);
-	F.prim_geom = prim.empty() || (prm->flags & 1u) ? nullptr : prim.data();  // flags bit 0 (test only): generic path
+	F.prim_geom = prim.empty() || (prm->flags & RT_PARAM_NO_PRIMARY_RECORDS) ? nullptr : prim.data();
+	F.packet_ok = 0;
 	if (F.prim_geom) rt_fill_chain(hs, F);
 	if (n_threads < 1) n_threads = 1;
+	if (pipeline && F.packet_ok && !(prm->flags & RT_PARAM_PER_RAY)) {
+		// ---- primary stage, patch by patch in the kernel's own patch geometry
+		const int tiles_x = (F.width + 15) / 16, tiles_y = (F.height + 15) / 16, n_tiles = tiles_x * tiles_y;
+		const int my_tiles = (n_tiles - F.tile_rank + F.tile_world - 1) / F.tile_world;
+		std::vector<std::vector<RtQueueItem>> queues(n_threads);
+		std::vector<uint32_t> errs(n_threads, 0);
+		auto out_index_of = [&](int x, int y, int k) {
+			return F.tile_compact ? (size_t)k * 256 + ((y & 15) * 16 + (x & 15)) : (size_t)y * F.width + x;
+		};
+		auto stage_a = [&](int t) {
+			std::vector<int> stack(RT_PACKET_STACK);
+			for (int p = t; p < my_tiles * 8; p += n_threads) {
+				const int k = p >> 3, sub = p & 7;
+				const int tile = F.tile_rank + k * F.tile_world;
+				if (tile >= n_tiles) continue;
+				const int tx = tile % tiles_x, ty = tile / tiles_x;
+				int x[32], y[32], qslot[32];
+				bool valid[32], enqueue[32];
+				size_t out_index[32];
+				for (int lane = 0; lane < 32; lane++) {
+					x[lane] = tx * 16 + (sub & 1) * 8 + (lane & 7);
+					y[lane] = ty * 16 + (sub >> 1) * 4 + (lane >> 3);
+					valid[lane] = x[lane] < F.width && y[lane] < F.height;
+					out_index[lane] = out_index_of(x[lane], y[lane], k);
+				}
+				primary_patch(S, F, x, y, valid, out_index, stack.data(), enqueue, qslot, errs[t]);
+				for (int lane = 0; lane < 32; lane++)
+					if (enqueue[lane]) queues[t].push_back(RtQueueItem{((uint32_t)y[lane] << 16) | (uint32_t)x[lane], qslot[lane]});
+			}
+		};
+		std::vector<std::thread> th;
+		for (int t = 0; t < n_threads; t++) th.emplace_back(stage_a, t);
+		for (auto& t : th) t.join();
+		th.clear();
+		// ---- bounce stage over the continuation queue
+		uint64_t queued = 0;
+		auto stage_b = [&](int t) {
+			for (const RtQueueItem& it : queues[t]) {
+				const int x = (int)(it.xy & 0xffffu), y = (int)(it.xy >> 16);
+				const int tile = (y / 16) * tiles_x + (x / 16);
+				RtCounts c = {0, 0, 0, 0, 0};
+				render_pixel<false>(S, F, x, y, out_index_of(x, y, tile / F.tile_world), c, errs[t], it.slot);
+			}
+		};
+		for (int t = 0; t < n_threads; t++) {
+			queued += queues[t].size();
+			th.emplace_back(stage_b, t);
+		}
+		for (auto& t : th) t.join();
+		if (counters) {
+			memset(counters, 0, sizeof *counters);
+			counters->paths = (uint64_t)F.width * F.height * F.n_frames;
+			counters->confirms = queued;  // (test hook) number of pixels that went through the queue
+			for (int t = 0; t < n_threads; t++) {
+				if (errs[t] & RT_ERRFLAG_TEXTURE) counters->texture_errors = 1;
+				if (errs[t] & RT_ERRFLAG_ACUTE) counters->acute_warnings = 1;
+			}
+		}
+		return 0;
+	}
+	F.packet_ok = 0;
 	std::vector<RtCounts> part(n_threads, RtCounts{0, 0, 0, 0, 0});
 	std::vector<uint32_t> errs(n_threads, 0);
 	auto work = [&](int t) {

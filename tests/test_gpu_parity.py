@@ -21,21 +21,29 @@ pytestmark = pytest.mark.gpu
 
 def gpu_render(bundle, width, height, n_frames=1, pos=scenes.BENCH_CAMERA_POS, yaw=30.0, pitch=0.0, refmax=None,
                reference_extents=False, frames_as_calls=False):
+    """Renders the frame twice through rt_render: (1) the default path, the two-stage pipeline (packet
+    primary stage + bounce stage); (2) the counting variant, which walks every ray one by one and returns
+    the reference-pattern work counters.  Both must give the same pixels; the pipeline's are returned."""
     cam = scenes.bench_camera(width, height, pos, yaw, pitch)
-    eb = rt.ExposureBuffer(width, height)
     cfg = rt.RaytracerConfig(bundle.refmax if refmax is None else refmax, bundle.sky, bundle.default_substance, 1.0)
-    tracer = rt.GpuRaytracer(cfg, bundle.tree, cam, eb, rt.FpLcg(1.0), reference_extents=reference_extents)
-    assert tracer.lib.rt_launch_count(tracer.ctx) == 0
-    if frames_as_calls:
-        for f in range(n_frames):  # the reference's own loop: tick(); next_frame(); tick(); ...
-            if f:
-                eb.next_frame()
-            tracer.trace_frame(want_ids=True, want_counters=True)
-    else:
-        tracer.trace_frame(n_frames=n_frames, want_ids=True, want_counters=True)
-    assert tracer.lib.rt_launch_count(tracer.ctx) >= 1  # our kernel ran, not a fallback
-    ids = insertion_ids(tracer.flat, bundle, tracer.last_first_ids)
-    return eb.image().copy(), ids, tracer.last_counters, tracer
+    out = []
+    for want_counters in (False, True):
+        eb = rt.ExposureBuffer(width, height)
+        tracer = rt.GpuRaytracer(cfg, bundle.tree, cam, eb, rt.FpLcg(1.0), reference_extents=reference_extents)
+        assert tracer.lib.rt_launch_count(tracer.ctx) == 0
+        if frames_as_calls:
+            for f in range(n_frames):  # the reference's own loop: tick(); next_frame(); tick(); ...
+                if f:
+                    eb.next_frame()
+                tracer.trace_frame(want_ids=True, want_counters=want_counters)
+        else:
+            tracer.trace_frame(n_frames=n_frames, want_ids=True, want_counters=want_counters)
+        assert tracer.lib.rt_launch_count(tracer.ctx) >= 1  # our kernels ran, not a fallback
+        out.append((eb.image().copy(), tracer.last_first_ids.copy(), tracer.last_counters, tracer))
+    (rgb, ids, _, tracer), (rgb_c, ids_c, cnt, _) = out
+    np.testing.assert_array_equal(ids, ids_c)
+    np.testing.assert_array_equal(rgb, rgb_c)
+    return rgb, insertion_ids(tracer.flat, bundle, ids), cnt, tracer
 
 
 def oracle_for(tracer, bundle, width, height, n_frames=1, pos=scenes.BENCH_CAMERA_POS, yaw=30.0, pitch=0.0,
@@ -117,6 +125,22 @@ def test_image_textures_and_sky(oracle):
     orgb, oids, _, tot = oracle_for(tr, b, 300, 300)
     res = compare(rgb, ids, orgb, oids)
     assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 2, res
+
+
+@pytest.mark.parametrize("pos,yaw,pitch", [
+    (scenes.BENCH_CAMERA_POS, 0.0, 0.0),      # axis-aligned: a pixel row and a column with exactly-zero components
+    ((0.5, 0.5, 0.5), 45.0, 0.3),             # on the root's centre planes (the demo pose, src/main.ts:364)
+    ((0.031, 0.967, 0.5021), 20.0, -0.7),     # near a corner, looking down into the cube
+    ((0.25, 0.75, 0.125), 135.0, 1.2),        # on dyadic planes of deeper levels
+])
+def test_packet_stage_from_many_poses(oracle, pos, yaw, pitch):
+    """The packet walk must reproduce the reference's visit order for every direction-sign class."""
+    b = scenes.random_spheres(6000, 0.004, 0.04, seed=21.0, mix="mirrors", box_fraction=0.15)
+    rgb, ids, cnt, tr = gpu_render(b, 320, 320, n_frames=2, pos=pos, yaw=yaw, pitch=pitch)
+    orgb, oids, _, tot = oracle_for(tr, b, 320, 320, n_frames=2, pos=pos, yaw=yaw, pitch=pitch)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 1, res
+    assert (oids >= 0).mean() > 0.1
 
 
 def test_camera_outside_root(oracle):

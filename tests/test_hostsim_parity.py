@@ -28,6 +28,11 @@ def run_both(bundle, width, height, n_frames=1, frame_first=0, pos=scenes.BENCH_
     cam, ocam = cameras(width, height, pos, yaw, pitch)
     prm = make_params(flat, bundle, n_frames=n_frames, frame_first=frame_first, refmax=refmax)
     rgb, ids, cnt = hostsim_render(flat, cam, prm)
+    # the default GPU path (packet primary stage + bounce stage over the continuation queue) must give the
+    # very same pixels as the ray-by-ray path
+    rgb_p, ids_p, _ = hostsim_render(flat, cam, prm, pipeline=True)
+    np.testing.assert_array_equal(ids_p, ids)
+    np.testing.assert_array_equal(rgb_p, rgb)
     ids = insertion_ids(flat, bundle, ids)
     os_ = oracle_scene(flat, bundle)
     orgb, oids, _, tot = oracle_render(os_, ocam, flat, bundle, prm, fixed_extents=True)
@@ -140,3 +145,40 @@ def test_primary_acceleration_is_exact(oracle):
     np.testing.assert_array_equal(rgb1, rgb2)
     np.testing.assert_array_equal(ids1, ids2)
     assert {k: c1[k] for k in ("segments", "nodes", "tests", "shades")} == {k: c2[k] for k in ("segments", "nodes", "tests", "shades")}
+
+
+@pytest.mark.parametrize("pos,yaw,pitch", [
+    (scenes.BENCH_CAMERA_POS, 30.0, 0.0),
+    (scenes.BENCH_CAMERA_POS, 0.0, 0.0),      # axis-aligned: a pixel row and a column with exactly-zero components
+    ((0.5, 0.5, 0.5), 45.0, 0.3),             # on the root's centre planes (the demo pose, src/main.ts:364)
+    ((0.031, 0.967, 0.5021), 20.0, -0.7),     # near a corner, looking down into the cube
+    ((0.25, 0.75, 0.125), 135.0, 1.2),        # on dyadic planes of deeper levels
+])
+def test_packet_stage_matches_oracle_from_many_poses(oracle, pos, yaw, pitch):
+    """Packet walk (one lock-step octree walk per 8x4 patch, per sign class) against the oracle: the
+    reference's visit order must come out for every ray of the packet, whatever the direction signs."""
+    b = scenes.random_spheres(4000, 0.004, 0.05, seed=21.0, mix="mirrors", box_fraction=0.15)
+    flat = flat_of(b)
+    W, H = 120, 88
+    cam, ocam = cameras(W, H, pos, yaw, pitch)
+    prm = make_params(flat, b, n_frames=2)
+    rgb, ids, cnt = hostsim_render(flat, cam, prm, pipeline=True)
+    assert 0 < cnt["confirms"] < W * H  # some paths end at the first hit, some continue through the queue
+    orgb, oids, _, _ = oracle_render(oracle_scene(flat, b), ocam, flat, b, prm, fixed_extents=True)
+    res = compare(rgb, insertion_ids(flat, b, ids), orgb, oids)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
+    rgb1, ids1, _ = hostsim_render(flat, cam, prm, pipeline=False)
+    assert (ids1 != ids).sum() <= 1 and np.abs(rgb1 - rgb).max() <= (0 if (ids1 == ids).all() else 10)
+
+
+def test_packet_stage_tile_sharded(oracle):
+    """The tile-major output of the pipeline for every rank of a 3-way split == the full frame."""
+    from raytracer_js_b200.parallel import untile_numpy
+    b = scenes.random_spheres(1500, 0.01, 0.06, seed=4.0, mix="mirrors")
+    flat = flat_of(b)
+    W, H, world = 100, 52, 3
+    cam, _ = cameras(W, H)
+    prm = make_params(flat, b)
+    full, ids, _ = hostsim_render(flat, cam, prm, pipeline=True)
+    parts = [hostsim_render(flat, cam, prm, pipeline=True, tile_rank=r, tile_world=world)[0] for r in range(world)]
+    np.testing.assert_array_equal(untile_numpy(np.stack(parts), W, H, world), full)

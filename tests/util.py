@@ -36,8 +36,8 @@ def hostsim():
         L = C.CDLL(build_hostsim())
         L.hostsim_render.restype = C.c_int
         L.hostsim_render.argtypes = [C.POINTER(N.SceneDesc), C.POINTER(N.CameraDesc), C.POINTER(N.Params), C.c_int,
-                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(N.Counters), C.c_char_p,
-                                     C.c_int]
+                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(N.Counters),
+                                     C.c_char_p, C.c_int]
         _hostsim = L
     return _hostsim
 
@@ -66,7 +66,10 @@ def insertion_ids(flat, bundle, flat_ids: np.ndarray) -> np.ndarray:
     return lut[flat_ids]
 
 
-def hostsim_render(flat, camera, params, n_threads=8, reference_extents=False, rgb=None, tile_rank=0, tile_world=1):
+def hostsim_render(flat, camera, params, n_threads=8, reference_extents=False, rgb=None, tile_rank=0, tile_world=1,
+                   pipeline=False):
+    """pipeline=False: ray by ray with work counters (rt_render_kernel<true>'s body); pipeline=True: the
+    packet primary stage + bounce stage (the default GPU path), counters['confirms'] = queued pixels."""
     W, H = camera.conf.screen_w, camera.conf.screen_h
     if tile_world > 1:
         from raytracer_js_b200.parallel import tiles_per_rank
@@ -81,8 +84,8 @@ def hostsim_render(flat, camera, params, n_threads=8, reference_extents=False, r
     err = C.create_string_buffer(512)
     d = flat.desc()
     cd = rt.camera_desc(camera, reference_extents)
-    st = hostsim().hostsim_render(C.byref(d), C.byref(cd), C.byref(params), n_threads, tile_rank, tile_world, rgb.ctypes.data,
-                                  ids.ctypes.data, C.byref(cnt), err, 512)
+    st = hostsim().hostsim_render(C.byref(d), C.byref(cd), C.byref(params), n_threads, tile_rank, tile_world,
+                                  1 if pipeline else 0, rgb.ctypes.data, ids.ctypes.data, C.byref(cnt), err, 512)
     if st == N.RT_ERR_BOUNDS:
         raise IndexError(err.value.decode())
     if st != 0:
