@@ -1,0 +1,204 @@
+/* rt_napi.c — Node N-API addon over the C ABI of librt_b200.so (include/rt_b200.h).
+ *
+ * This is the binding a maintainer of Dark565/raytracer.js adds on the reference side; the TypeScript
+ * class that uses it (gpu_raytracer.ts) drops in for `Raytracer` (src/raytracer.ts:281-339).  The addon is
+ * deliberately thin: every typed array is passed by pointer (zero copy: the Float32Array of the
+ * ExposureBuffer is the render target, page-locked once with rt_host_register), every non-zero rt_status
+ * becomes a thrown JS Error carrying rt_last_error(), and the process is never aborted.
+ *
+ * Build where Node exists:   cc -shared -fPIC -o rt_b200.node rt_napi.c -I$(NODE)/include/node -L. -lrt_b200
+ * Build check here (no Node): gcc -fsyntax-only -Wall -I../../include rt_napi.c   (uses node_api_min.h)
+ *
+ * Exports:  create(device) -> ctx      (freed by the finalizer of the external)
+ *           uploadScene(ctx, flat)     flat = the object gpu_raytracer.ts: flatten() builds (typed arrays)
+ *           render(ctx, camera, params, pixels: Float32Array, ids?: Int32Array) -> counters | undefined
+ *           pin(ctx, Float32Array)     unpin(ctx, Float32Array)
+ */
+#if defined(__has_include)
+#if __has_include(<node_api.h>)
+#include <node_api.h>
+#else
+#include "node_api_min.h"
+#endif
+#else
+#include "node_api_min.h"
+#endif
+#include <string.h>
+
+#include "rt_b200.h"
+
+#define RT_NAPI_TRY(env, call)                                  \
+	do {                                                        \
+		if ((call) != napi_ok) {                                \
+			napi_throw_error((env), NULL, "rt_b200: bad argument (" #call ")"); \
+			return NULL;                                        \
+		}                                                       \
+	} while (0)
+
+static napi_value throw_rt(napi_env env, rt_ctx* ctx, rt_status st) {
+	const char* msg = rt_last_error(ctx);
+	/* keep the reference's own messages: "x or y out of bounds", "Texture coordinates out of bounds" */
+	napi_throw_error(env, st == RT_ERR_BOUNDS ? "ERR_OUT_OF_RANGE" : NULL, msg && *msg ? msg : "rt_b200 failed");
+	return NULL;
+}
+
+static rt_ctx* ctx_of(napi_env env, napi_value v) {
+	void* p = NULL;
+	if (napi_get_value_external(env, v, &p) != napi_ok) return NULL;
+	return (rt_ctx*)p;
+}
+
+/* typed array property `name` of `obj` -> data pointer (+ element count) */
+static void* ta(napi_env env, napi_value obj, const char* name, size_t* len) {
+	napi_value v;
+	bool is = false;
+	void* data = NULL;
+	size_t n = 0;
+	napi_typedarray_type t;
+	if (napi_get_named_property(env, obj, name, &v) != napi_ok || napi_is_typedarray(env, v, &is) != napi_ok || !is) return NULL;
+	if (napi_get_typedarray_info(env, v, &t, &n, &data, NULL, NULL) != napi_ok) return NULL;
+	if (len) *len = n;
+	return data;
+}
+static double num(napi_env env, napi_value obj, const char* name) {
+	napi_value v;
+	double d = 0;
+	if (napi_get_named_property(env, obj, name, &v) == napi_ok) napi_get_value_double(env, v, &d);
+	return d;
+}
+static void vec3(napi_env env, napi_value obj, const char* name, double* out) {
+	size_t n = 0;
+	const double* p = (const double*)ta(env, obj, name, &n); /* Float64Array(3) */
+	if (p && n >= 3) memcpy(out, p, 3 * sizeof(double));
+}
+
+static void finalize_ctx(napi_env env, void* data, void* hint) {
+	(void)env; (void)hint;
+	rt_destroy((rt_ctx*)data);
+}
+
+static napi_value Create(napi_env env, napi_callback_info info) {
+	size_t argc = 1;
+	napi_value argv[1], out;
+	int32_t device = -1;
+	rt_ctx* ctx = NULL;
+	RT_NAPI_TRY(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc >= 1) napi_get_value_int32(env, argv[0], &device);
+	rt_status st = rt_create(device, &ctx);
+	if (st != RT_OK) return throw_rt(env, NULL, st); /* no CUDA device => Error: there is no CPU fallback */
+	RT_NAPI_TRY(env, napi_create_external(env, ctx, finalize_ctx, NULL, &out));
+	return out;
+}
+
+static napi_value UploadScene(napi_env env, napi_callback_info info) {
+	size_t argc = 2, n = 0;
+	napi_value argv[2], flat;
+	RT_NAPI_TRY(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	rt_ctx* ctx = ctx_of(env, argv[0]);
+	flat = argv[1];
+	rt_scene_desc d;
+	memset(&d, 0, sizeof d);
+	d.struct_size = (uint32_t)sizeof d;
+	d.node_pos = (const double*)ta(env, flat, "node_pos", NULL);
+	d.node_size = (const double*)ta(env, flat, "node_size", &n);             d.n_nodes = (uint32_t)n;
+	d.node_child = (const int32_t*)ta(env, flat, "node_child", NULL);
+	d.node_parent = (const int32_t*)ta(env, flat, "node_parent", NULL);
+	d.node_octant = (const int32_t*)ta(env, flat, "node_octant", NULL);
+	d.node_list_off = (const uint32_t*)ta(env, flat, "node_list_off", NULL);
+	d.list_entity = (const uint32_t*)ta(env, flat, "list_entity", &n);       d.n_list = (uint32_t)n;
+	d.ent_type = (const uint8_t*)ta(env, flat, "ent_type", &n);              d.n_entities = (uint32_t)n;
+	d.ent_pos = (const double*)ta(env, flat, "ent_pos", NULL);
+	d.ent_extent = (const double*)ta(env, flat, "ent_extent", NULL);
+	d.ent_material = (const int32_t*)ta(env, flat, "ent_material", NULL);
+	d.ent_texture = (const int32_t*)ta(env, flat, "ent_texture", NULL);
+	d.ent_substance = (const int32_t*)ta(env, flat, "ent_substance", NULL);
+	d.mat_response = (const uint8_t*)ta(env, flat, "mat_response", &n);      d.n_materials = (uint32_t)n;
+	d.mat_light = (const uint8_t*)ta(env, flat, "mat_light", NULL);
+	d.mat_mirror = (const uint8_t*)ta(env, flat, "mat_mirror", NULL);
+	d.mat_roughness = (const double*)ta(env, flat, "mat_roughness", NULL);
+	d.tex_kind = (const uint8_t*)ta(env, flat, "tex_kind", &n);              d.n_textures = (uint32_t)n;
+	d.tex_color = (const double*)ta(env, flat, "tex_color", NULL);
+	d.tex_width = (const int32_t*)ta(env, flat, "tex_width", NULL);
+	d.tex_height = (const int32_t*)ta(env, flat, "tex_height", NULL);
+	d.tex_loaded = (const uint8_t*)ta(env, flat, "tex_loaded", NULL);
+	d.tex_texel_off = (const uint64_t*)ta(env, flat, "tex_texel_off", NULL); /* BigUint64Array */
+	d.texels = (const uint8_t*)ta(env, flat, "texels", &n);                  d.n_texels = n / 3;
+	d.sub_refractive_index = (const double*)ta(env, flat, "sub_refractive_index", &n); d.n_substances = (uint32_t)n;
+	rt_status st = rt_scene_upload(ctx, &d);
+	if (st != RT_OK) return throw_rt(env, ctx, st);
+	return NULL;
+}
+
+static napi_value Render(napi_env env, napi_callback_info info) {
+	size_t argc = 5, npx = 0, nid = 0;
+	napi_value argv[5], out = NULL, v;
+	napi_typedarray_type t;
+	void *rgb = NULL, *ids = NULL;
+	bool want_counters;
+	RT_NAPI_TRY(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	rt_ctx* ctx = ctx_of(env, argv[0]);
+	rt_camera cam;
+	rt_params prm;
+	memset(&cam, 0, sizeof cam);
+	memset(&prm, 0, sizeof prm);
+	vec3(env, argv[1], "pos", cam.pos); vec3(env, argv[1], "fr", cam.fr);
+	vec3(env, argv[1], "lf", cam.lf);   vec3(env, argv[1], "up", cam.up);
+	cam.fov_h = num(env, argv[1], "fov_h"); cam.fov_v = num(env, argv[1], "fov_v");
+	cam.width = (uint32_t)num(env, argv[1], "width"); cam.height = (uint32_t)num(env, argv[1], "height");
+	cam.flags = (uint32_t)num(env, argv[1], "flags");
+	prm.refmax = (int32_t)num(env, argv[2], "refmax");
+	prm.sky_texture = (int32_t)num(env, argv[2], "sky_texture");
+	prm.default_substance = (int32_t)num(env, argv[2], "default_substance");
+	prm.distance_attenuation_factor = num(env, argv[2], "distance_attenuation_factor");
+	prm.n_frames = (uint32_t)num(env, argv[2], "n_frames");
+	prm.frame_first = (uint32_t)num(env, argv[2], "frame_first");
+	prm.rng_seed = num(env, argv[2], "rng_seed");
+	prm.precision = RT_PRECISION_F32;
+	want_counters = num(env, argv[2], "want_counters") != 0;
+	RT_NAPI_TRY(env, napi_get_typedarray_info(env, argv[3], &t, &npx, &rgb, NULL, NULL));
+	if (t != napi_float32_array || npx != (size_t)cam.width * cam.height * 3) {
+		napi_throw_error(env, "ERR_OUT_OF_RANGE", "x or y out of bounds"); /* ExposureBuffer.check_bounds */
+		return NULL;
+	}
+	if (argc >= 5) {
+		bool is = false;
+		if (napi_is_typedarray(env, argv[4], &is) == napi_ok && is)
+			RT_NAPI_TRY(env, napi_get_typedarray_info(env, argv[4], &t, &nid, &ids, NULL, NULL));
+	}
+	rt_counters cnt;
+	rt_status st = rt_render(ctx, &cam, &prm, 0, (float*)rgb, (int32_t*)ids, want_counters ? &cnt : NULL);
+	if (st != RT_OK) return throw_rt(env, ctx, st);
+	if (!want_counters) return NULL;
+	RT_NAPI_TRY(env, napi_create_object(env, &out));
+#define PUT(name) napi_create_double(env, (double)cnt.name, &v); napi_set_named_property(env, out, #name, v)
+	PUT(paths); PUT(segments); PUT(nodes); PUT(tests); PUT(shades); PUT(confirms);
+#undef PUT
+	return out;
+}
+
+static napi_value PinOrUnpin(napi_env env, napi_callback_info info, int pin) {
+	size_t argc = 2, n = 0;
+	napi_value argv[2];
+	napi_typedarray_type t;
+	void* data = NULL;
+	RT_NAPI_TRY(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	rt_ctx* ctx = ctx_of(env, argv[0]);
+	RT_NAPI_TRY(env, napi_get_typedarray_info(env, argv[1], &t, &n, &data, NULL, NULL));
+	rt_status st = pin ? rt_host_register(ctx, data, n * sizeof(float)) : rt_host_unregister(ctx, data);
+	if (st != RT_OK) return throw_rt(env, ctx, st);
+	return NULL;
+}
+static napi_value Pin(napi_env env, napi_callback_info info) { return PinOrUnpin(env, info, 1); }
+static napi_value Unpin(napi_env env, napi_callback_info info) { return PinOrUnpin(env, info, 0); }
+
+napi_value napi_register_module_v1(napi_env env, napi_value exports) {
+	const napi_property_descriptor props[] = {
+	    {"create", NULL, Create, NULL, NULL, NULL, napi_default, NULL},
+	    {"uploadScene", NULL, UploadScene, NULL, NULL, NULL, napi_default, NULL},
+	    {"render", NULL, Render, NULL, NULL, NULL, napi_default, NULL},
+	    {"pin", NULL, Pin, NULL, NULL, NULL, napi_default, NULL},
+	    {"unpin", NULL, Unpin, NULL, NULL, NULL, napi_default, NULL},
+	};
+	napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
+	return exports;
+}

@@ -615,8 +615,9 @@ RT_HD unsigned xor_permute8(unsigned m, int x) {
 // -1.  Lanes with skip[l] set (pixels outside the frame) take no part but must carry a valid direction.
 // `stack` is RT_PACKET_STACK ints private to the warp.  A patch whose rays differ in the sign of a
 // direction component (it straddles one of the three great circles through the axes) is walked once per
-// sign class.  unresolved[l] is set for lanes that cannot take part in any lock-step walk (a zero
-// direction component; node stack overflow): the caller searches those ray by ray.
+// sign class (a zero component counts as positive: such a ray never crosses a plane of that axis, so
+// either order is its own).  unresolved[l] is set for lanes that cannot take part in a lock-step walk
+// (non-finite direction; node stack overflow): the caller searches those ray by ray.
 RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const double (&dir)[RT_NL][3], const RtRayF (&r)[RT_NL],
                              const RtPacket& P, bool (&done)[RT_NL], int* stack, int (&hit_slot)[RT_NL], bool& overflow);
 
@@ -634,8 +635,9 @@ RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const doub
 		const float k = sqrtf(r[l].inv_a);
 		nx[l] = r[l].dx * k; ny[l] = r[l].dy * k; nz[l] = r[l].dz * k;
 		hit_slot[l] = -1;
-		unresolved[l] = !skip[l] && !(r[l].dx != 0.0f && r[l].dy != 0.0f && r[l].dz != 0.0f && ix[l] < 1e30f &&
-		                              iy[l] < 1e30f && iz[l] < 1e30f);
+		// a zero component (|1/d_k| = inf) is fine: the slab products become +-inf (conservative) or NaN,
+		// which fminf/fmaxf drop; only a non-finite direction cannot be walked
+		unresolved[l] = !skip[l] && !(r[l].inv_a > 0.0f && r[l].inv_a < INFINITY);
 		todo[l] = !skip[l] && !unresolved[l];
 	}
 	unsigned todo_mask = warp_ballot(todo);

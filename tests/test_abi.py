@@ -78,3 +78,15 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "hostsim" not in text.replace("tests/hostsim", ""), f
+
+
+def test_napi_shim_compiles_against_the_abi():
+    """bindings/node/rt_napi.c (the reference-side N-API addon) is valid C against include/rt_b200.h and
+    Node's N-API prototypes (hand-declared in node_api_min.h: the image has no Node headers), and every
+    rt_* function it calls is declared by the header."""
+    import subprocess
+    shim = os.path.join(ROOT, "bindings", "node", "rt_napi.c")
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), shim])
+    used = set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", open(shim).read(), flags=re.S)))
+    assert used <= set(declared_functions()), used - set(declared_functions())
+    assert {"rt_create", "rt_scene_upload", "rt_render", "rt_destroy"} <= used
