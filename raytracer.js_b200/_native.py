@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(HERE, "librt_b200.so")  # env: tuning builds only
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NO_SCENE, RT_ERR_UNSUPPORTED, RT_ERR_BOUNDS, RT_ERR_TEXTURE = range(7)
 RT_ENTITY_SPHERE, RT_ENTITY_BOX = 0, 1

@@ -2,6 +2,9 @@
 // No PyTorch, no CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <functional>
+
 #include "rt_host.h"
 #include "rt_trace.cuh"
 
@@ -28,8 +31,7 @@ __global__ void rt_prepare_primary_kernel(const __grid_constant__ RtDevScene S, 
 #define RT_WARPS_PER_CTA 4
 template <bool COUNT>
 __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
-    rt_render_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_tiles,
-                     int n_patches) {
+    rt_render_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_patches) {
 	const int lane = threadIdx.x & 31;
 	RtCounts cnt = {0, 0, 0, 0, 0};
 	unsigned long long paths = 0;
@@ -40,8 +42,8 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 		p = __shfl_sync(0xffffffffu, p, 0);
 		if (p >= (unsigned)n_patches) break;
 		const int k = (int)(p >> 3), sub = (int)(p & 7);  // k-th own tile, patch within the tile
-		const int tile = F.tile_rank + k * F.tile_world;
-		if (tile >= n_tiles) continue;
+		const int tile = F.tile_begin + F.tile_rank + k * F.tile_world;
+		if (tile >= F.tile_end) continue;
 		const int tx = tile % tiles_x, ty = tile / tiles_x;
 		const int x = tx * RT_TILE_W + (sub & 1) * 8 + (lane & 7);
 		const int y = ty * RT_TILE_H + (sub >> 1) * 4 + (lane >> 3);
@@ -71,10 +73,17 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 // 32 camera rays of its patch (rt_trace.cuh: packet_primary_hits), finishes the pixels whose path ends at
 // the first hit and appends the others to the continuation queue with one warp-aggregated atomic.
 #define RT_A_WARPS 4
-__global__ void __launch_bounds__(RT_A_WARPS * 32)
-    rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_tiles,
-                      int n_patches) {
+#ifndef RT_PPL
+#define RT_PPL 4  // rays per lane in the primary stage: a packet is RT_PPL 8x4 sub-patches of a 16x16 tile
+#endif
+#ifndef RT_A_MINB
+#define RT_A_MINB 3
+#endif
+template <int PPL>
+__global__ void __launch_bounds__(RT_A_WARPS * 32, RT_A_MINB)
+    rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_packets) {
 	__shared__ int stacks[RT_A_WARPS][RT_PACKET_STACK];
+	constexpr int PER_TILE = 8 / PPL;
 	const int lane = threadIdx.x & 31;
 	int* stack = stacks[threadIdx.x >> 5];
 	uint32_t err = 0;
@@ -82,28 +91,54 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32)
 		unsigned p = 0;
 		if (lane == 0) p = atomicAdd(F.work_counter, 1u);
 		p = __shfl_sync(0xffffffffu, p, 0);
-		if (p >= (unsigned)n_patches) break;
-		const int k = (int)(p >> 3), sub = (int)(p & 7);
-		const int tile = F.tile_rank + k * F.tile_world;
-		if (tile >= n_tiles) continue;
-		const int tx = tile % tiles_x, ty = tile / tiles_x;
-		const int x[1] = {tx * RT_TILE_W + (sub & 1) * 8 + (lane & 7)};
-		const int y[1] = {ty * RT_TILE_H + (sub >> 1) * 4 + (lane >> 3)};
-		const bool valid[1] = {x[0] < F.width && y[0] < F.height};
-		const size_t out_index[1] = {
-		    F.tile_compact ? (size_t)k * RT_BLOCK + ((y[0] & (RT_TILE_H - 1)) * RT_TILE_W + (x[0] & (RT_TILE_W - 1)))
-		                   : (size_t)y[0] * F.width + x[0]};
-		bool enqueue[1];
-		int qslot[1];
-		primary_patch(S, F, x, y, valid, out_index, stack, enqueue, qslot, err);
-		const unsigned m = __ballot_sync(0xffffffffu, enqueue[0]);
-		if (m) {
-			unsigned base = 0;
-			if (lane == 0) base = atomicAdd(F.queue_count, (unsigned)__popc(m));
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if (enqueue[0])
-				F.queue[base + __popc(m & ((1u << lane) - 1u))] = RtQueueItem{((uint32_t)y[0] << 16) | (uint32_t)x[0], qslot[0]};
+		if (p >= (unsigned)n_packets) break;
+		const int k = (int)(p / PER_TILE);
+		const int tile = F.tile_begin + F.tile_rank + k * F.tile_world;
+		if (tile >= F.tile_end) continue;
+		RtPatch pt;
+		pt.x0 = (tile % tiles_x) * RT_TILE_W;
+		pt.y0 = (tile / tiles_x) * RT_TILE_H;
+		pt.sub0 = (int)(p % PER_TILE) * PPL;
+		pt.out_base = (size_t)k * RT_BLOCK;
+		primary_patch<PPL>(S, F, pt, stack);
+	}
+}
+
+// Shade stage: one thread per pixel of this rank (output order, coalesced).  Turns the first-hit slot into
+// the pixel's colour when the path ends there (miss -> sky, diffuse, light, ...: primary_terminal), else
+// appends the pixel to the continuation queue with one warp-aggregated atomic.
+__global__ void __launch_bounds__(256)
+    rt_shade_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, size_t n_out) {
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t i = F.out_first + t;
+	const int lane = threadIdx.x & 31;
+	uint32_t err = 0;
+	bool enqueue = false;
+	int x = 0, y = 0, slot = -1;
+	if (t < n_out) {
+		bool valid = true;
+		if (F.tile_compact) {
+			const int k = (int)(i / RT_BLOCK), in = (int)(i % RT_BLOCK);
+			const int tile = F.tile_begin + F.tile_rank + k * F.tile_world;
+			valid = tile < F.tile_end;
+			x = (tile % tiles_x) * RT_TILE_W + (in & (RT_TILE_W - 1));
+			y = (tile / tiles_x) * RT_TILE_H + (in / RT_TILE_W);
+			valid = valid && x < F.width && y < F.height;
+		} else {
+			y = (int)(i / F.width);
+			x = (int)(i % F.width);
 		}
+		if (valid) {
+			slot = F.hit_slots[i];
+			enqueue = slot == RT_SLOT_UNKNOWN || !primary_finish(S, F, x, y, slot, i, err);
+		}
+	}
+	const unsigned m = __ballot_sync(0xffffffffu, enqueue);
+	if (m) {
+		unsigned base = 0;
+		if (lane == 0) base = atomicAdd(F.queue_count, (unsigned)__popc(m));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (enqueue) F.queue[base + __popc(m & ((1u << lane) - 1u))] = RtQueueItem{((uint32_t)y << 16) | (uint32_t)x, slot};
 	}
 	if (err) atomicOr(F.error_flags, err);
 }
@@ -181,6 +216,12 @@ struct rt_ctx {
 	int device = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaStream_t copy_stream = nullptr;          // device->host band copies of rt_render
+	cudaEvent_t band_done[16] = {};              // band b rendered (RT_MAX_BANDS)
+	cudaEvent_t stage_free = nullptr;            // camera-table staging may be rewritten
+	void* stage = nullptr;                       // pinned staging of the camera scan tables
+	size_t stage_cap = 0;
+	int n_bands = 4;                             // rt_render: bands of tile rows (tuning knob RT_B200_BANDS)
 	std::string err;
 	uint64_t launches = 0;
 	bool has_scene = false;
@@ -189,6 +230,7 @@ struct rt_ctx {
 	DevBuf<RtF4> node_geom;
 	DevBuf<RtI4> node_link;
 	DevBuf<int> node_child;
+	DevBuf<RtPNode> node_pk;
 	DevBuf<RtF4> slot_geom;
 	DevBuf<RtD4> slot_geom64;
 	DevBuf<RtI4> slot_attr;
@@ -209,7 +251,9 @@ struct rt_ctx {
 	DevBuf<uint8_t> l2_scratch;
 	DevBuf<RtF4> prim_geom;
 	DevBuf<RtQueueItem> queue;
-	int render_grid[4] = {0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, primary, bounce
+	DevBuf<int> hit_slots;
+	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
+	int ppl = RT_PPL;
 };
 
 namespace {
@@ -244,11 +288,35 @@ rt_status check_args(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm) {
 }
 
 // Builds the RtFrame (camera tables, start state) and launches the kernel on the ctx stream.
+// Builds the RtFrame (camera tables, start state) and enqueues the kernels on the ctx stream.  The frame
+// can be cut into `n_bands` groups of whole tile rows, each rendered by its own launches; after_band(b,
+// row_begin, row_end) is called right after band b's kernels were enqueued (rt_render uses it to start the
+// device->host copy of that band behind an event while the next band renders).
+typedef std::function<rt_status(int, int, int)> BandHook;
+#define RT_MAX_BANDS 16
 rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb_dev,
-                        int* ids_dev, int tile_rank, int tile_world, bool tile_compact = false) {
+                        int* ids_dev, int tile_rank, int tile_world, bool tile_compact = false, int n_bands = 1,
+                        const BandHook& after_band = BandHook()) {
+	// camera scan tables: built on the host into pinned staging, then one async copy each
+	const size_t n_col = cam->width, n_row = cam->height;
+	if (ctx->stage_cap < n_col * sizeof(RtD2) + n_row * sizeof(RtD4)) {
+		if (ctx->stage) cudaFreeHost(ctx->stage);
+		ctx->stage = nullptr;
+		ctx->stage_cap = 0;
+		RT_CUDA(ctx, cudaMallocHost(&ctx->stage, n_col * sizeof(RtD2) + n_row * sizeof(RtD4)));
+		ctx->stage_cap = n_col * sizeof(RtD2) + n_row * sizeof(RtD4);
+	}
+	RT_CUDA(ctx, cudaEventSynchronize(ctx->stage_free));  // the previous frame's table copies have left the staging
 	rt_build_camera_tables(*cam, ctx->h_col_cs, ctx->h_row_fr);
-	if (rt_status st = upload(ctx, ctx->col_cs, ctx->h_col_cs)) return st;
-	if (rt_status st = upload(ctx, ctx->row_fr, ctx->h_row_fr)) return st;
+	RtD4* st_row = reinterpret_cast<RtD4*>(ctx->stage);
+	RtD2* st_col = reinterpret_cast<RtD2*>(st_row + n_row);
+	memcpy(st_row, ctx->h_row_fr.data(), n_row * sizeof(RtD4));
+	memcpy(st_col, ctx->h_col_cs.data(), n_col * sizeof(RtD2));
+	RT_CUDA(ctx, ctx->col_cs.alloc(n_col));
+	RT_CUDA(ctx, ctx->row_fr.alloc(n_row));
+	RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, st_row, n_row * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
+	RT_CUDA(ctx, cudaMemcpyAsync(ctx->col_cs.p, st_col, n_col * sizeof(RtD2), cudaMemcpyHostToDevice, ctx->stream));
+	RT_CUDA(ctx, cudaEventRecord(ctx->stage_free, ctx->stream));
 	RtFrame F{};
 	std::string err;
 	if (rt_status st = rt_fill_frame(ctx->host, cam, prm, F, err)) return fail(ctx, st, err);
@@ -259,19 +327,19 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	F.tile_rank = tile_rank;
 	F.tile_world = tile_world;
 	F.tile_compact = tile_compact ? 1 : 0;
-	// counters[0..7], then the patch dispenser, the error flags and the two queue cursors: one memset
-	RT_CUDA(ctx, ctx->counters.alloc(12));
-	RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 12 * sizeof(unsigned long long), ctx->stream));
+	// u64 cells: [0..7] work counters, [8] error flags, then per band {patch dispenser, queue count, queue cursor}
+	n_bands = std::max(1, std::min(n_bands, RT_MAX_BANDS));
+	const size_t n_cells = 9 + 3 * RT_MAX_BANDS;
+	RT_CUDA(ctx, ctx->counters.alloc(n_cells));
+	RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, n_cells * sizeof(unsigned long long), ctx->stream));
 	F.counters = ctx->counters.p;
-	F.work_counter = reinterpret_cast<unsigned*>(ctx->counters.p + 8);
-	F.error_flags = reinterpret_cast<uint32_t*>(ctx->counters.p + 9);
-	F.queue_count = reinterpret_cast<unsigned*>(ctx->counters.p + 10);
-	F.queue_taken = reinterpret_cast<unsigned*>(ctx->counters.p + 11);
+	F.error_flags = reinterpret_cast<uint32_t*>(ctx->counters.p + 8);
 	const bool count = (flags & RT_RENDER_COUNTERS) != 0;
 	const int tiles_x = (F.width + RT_TILE_W - 1) / RT_TILE_W, tiles_y = (F.height + RT_TILE_H - 1) / RT_TILE_H;
 	const int n_tiles = tiles_x * tiles_y;
-	const int my_tiles = (n_tiles - tile_rank + tile_world - 1) / tile_world;
-	if (my_tiles <= 0) return RT_OK;
+	if ((n_tiles - tile_rank + tile_world - 1) / tile_world <= 0) return RT_OK;
+	if (tile_compact || tile_world > 1) n_bands = 1;
+	n_bands = std::min(n_bands, tiles_y);
 
 	// primary-ray preparation: origin-relative slot records + the origin chain (start node ... root)
 	const RtHostScene& H = ctx->host;
@@ -288,8 +356,15 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 		F.prim_geom = ctx->prim_geom.p;
 		rt_fill_chain(H, F);
 	}
+	const bool pipeline = F.packet_ok && !count && !(prm->flags & RT_PARAM_PER_RAY);
+	if (!pipeline) F.packet_ok = 0;
+	if (pipeline) {
+		const size_t cap = tile_compact ? (size_t)((n_tiles - tile_rank + tile_world - 1) / tile_world) * RT_BLOCK
+		                                : (size_t)F.width * F.height;
+		RT_CUDA(ctx, ctx->queue.alloc(cap));
+		RT_CUDA(ctx, ctx->hit_slots.alloc(cap));
+	}
 
-	const int n_patches = my_tiles * 8;
 	auto grid_of = [&](int which, const void* kernel, int threads, int& out) -> rt_status {
 		int& grid = ctx->render_grid[which];
 		if (grid == 0) {
@@ -301,44 +376,65 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 		out = grid;
 		return RT_OK;
 	};
-	int grid = 0;
-	if (F.packet_ok && !count && !(prm->flags & RT_PARAM_PER_RAY)) {
-		// two-stage pipeline: packet walk for the camera segment, per-ray bounce stage for what continues
-		RT_CUDA(ctx, ctx->queue.alloc((size_t)my_tiles * RT_BLOCK));
-		F.queue = ctx->queue.p;
-		if (rt_status st = grid_of(2, (const void*)rt_primary_kernel, RT_A_WARPS * 32, grid)) return st;
-		rt_primary_kernel<<<std::min(grid, (n_patches + RT_A_WARPS - 1) / RT_A_WARPS), RT_A_WARPS * 32, 0, ctx->stream>>>(
-		    ctx->dev, F, tiles_x, n_tiles, n_patches);
+	for (int band = 0; band < n_bands; band++) {
+		const int row_begin = (int)((long long)tiles_y * band / n_bands), row_end = (int)((long long)tiles_y * (band + 1) / n_bands);
+		F.tile_begin = row_begin * tiles_x;
+		F.tile_end = row_end * tiles_x;
+		const int band_tiles = F.tile_end - F.tile_begin;
+		const int my_tiles = (band_tiles - tile_rank + tile_world - 1) / tile_world;
+		if (my_tiles <= 0) continue;
+		const int y_begin = row_begin * RT_TILE_H, y_end = std::min(F.height, row_end * RT_TILE_H);
+		F.out_first = tile_compact ? 0ull : (unsigned long long)y_begin * F.width;
+		const size_t n_out = tile_compact ? (size_t)my_tiles * RT_BLOCK : (size_t)(y_end - y_begin) * F.width;
+		unsigned long long* cells = ctx->counters.p + 9 + 3 * band;
+		F.work_counter = reinterpret_cast<unsigned*>(cells);
+		F.queue_count = reinterpret_cast<unsigned*>(cells + 1);
+		F.queue_taken = reinterpret_cast<unsigned*>(cells + 2);
+		const int n_patches = my_tiles * 8;
+		int grid = 0;
+		if (pipeline) {
+			// primary stage (packet walk) -> shade stage -> bounce stage over the continuation queue
+			F.queue = ctx->queue.p + F.out_first;
+			F.hit_slots = ctx->hit_slots.p;
+			// rays per lane of the packet stage (tuning knob: RT_B200_PPL=1|2|4|8 in the environment)
+			const int ppl = ctx->ppl;
+			const int n_packets = my_tiles * (8 / ppl);
+			const void* kern = ppl == 1 ? (const void*)rt_primary_kernel<1> : ppl == 2 ? (const void*)rt_primary_kernel<2>
+			                 : ppl == 4 ? (const void*)rt_primary_kernel<4> : (const void*)rt_primary_kernel<8>;
+			if (rt_status st = grid_of(4 + (ppl == 1 ? 0 : ppl == 2 ? 1 : ppl == 4 ? 2 : 3), kern, RT_A_WARPS * 32, grid)) return st;
+			const int blocks = std::min(grid, (n_packets + RT_A_WARPS - 1) / RT_A_WARPS);
+			void* args[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x, (void*)&n_packets};
+			RT_CUDA(ctx, cudaLaunchKernel(kern, dim3(blocks), dim3(RT_A_WARPS * 32), args, 0, ctx->stream));
+			ctx->launches++;
+			rt_shade_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_out);
+			ctx->launches++;
+			RT_CUDA(ctx, cudaGetLastError());
+			if (rt_status st = grid_of(3, (const void*)rt_bounce_kernel, RT_WARPS_PER_CTA * 32, grid)) return st;
+			rt_bounce_kernel<<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
+			                   ctx->stream>>>(ctx->dev, F, tiles_x);
+		} else if (count) {
+			if (rt_status st = grid_of(1, (const void*)rt_render_kernel<true>, RT_WARPS_PER_CTA * 32, grid)) return st;
+			rt_render_kernel<true><<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
+			                         ctx->stream>>>(ctx->dev, F, tiles_x, n_patches);
+		} else {
+			if (rt_status st = grid_of(0, (const void*)rt_render_kernel<false>, RT_WARPS_PER_CTA * 32, grid)) return st;
+			rt_render_kernel<false><<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
+			                          ctx->stream>>>(ctx->dev, F, tiles_x, n_patches);
+		}
 		ctx->launches++;
 		RT_CUDA(ctx, cudaGetLastError());
-		if (rt_status st = grid_of(3, (const void*)rt_bounce_kernel, RT_WARPS_PER_CTA * 32, grid)) return st;
-		rt_bounce_kernel<<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
-		                   ctx->stream>>>(ctx->dev, F, tiles_x);
-		ctx->launches++;
-		RT_CUDA(ctx, cudaGetLastError());
-		return RT_OK;
+		if (after_band)
+			if (rt_status st = after_band(band, y_begin, y_end)) return st;
 	}
-	F.packet_ok = 0;
-	if (count) {
-		if (rt_status st = grid_of(1, (const void*)rt_render_kernel<true>, RT_WARPS_PER_CTA * 32, grid)) return st;
-		rt_render_kernel<true><<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
-		                         ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles, n_patches);
-	} else {
-		if (rt_status st = grid_of(0, (const void*)rt_render_kernel<false>, RT_WARPS_PER_CTA * 32, grid)) return st;
-		rt_render_kernel<false><<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
-		                          ctx->stream>>>(ctx->dev, F, tiles_x, n_tiles, n_patches);
-	}
-	ctx->launches++;
-	RT_CUDA(ctx, cudaGetLastError());
 	return RT_OK;
 }
 
 rt_status read_counters(rt_ctx* ctx, rt_counters* out) {
-	unsigned long long h[12] = {0};
+	unsigned long long h[9] = {0};
 	if (ctx->counters.p)
 		RT_CUDA(ctx, cudaMemcpyAsync(h, ctx->counters.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	const uint32_t ef = (uint32_t)h[9];
+	const uint32_t ef = (uint32_t)h[8];
 	out->paths = h[0]; out->segments = h[1]; out->nodes = h[2]; out->tests = h[3]; out->shades = h[4];
 	out->confirms = h[5];
 	out->texture_errors = (ef & RT_ERRFLAG_TEXTURE) ? 1 : 0;
@@ -372,13 +468,26 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	if (e != cudaSuccess) return fail(nullptr, RT_ERR_CUDA, rt_format("cudaSetDevice(%d): %s", device, cudaGetErrorString(e)));
 	rt_ctx* ctx = new rt_ctx();
 	ctx->device = device;
-	if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-	    (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+	e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->stage_free, cudaEventDisableTiming);
+	for (int b = 0; b < RT_MAX_BANDS && e == cudaSuccess; b++) e = cudaEventCreateWithFlags(&ctx->band_done[b], cudaEventDisableTiming);
+	if (e != cudaSuccess) {
 		rt_status st = fail(nullptr, RT_ERR_CUDA, rt_format("rt_create: %s", cudaGetErrorString(e)));
-		delete ctx;
+		rt_destroy(ctx);
 		return st;
 	}
 	ctx->stream = ctx->own_stream;
+	if (const char* e = getenv("RT_B200_BANDS")) {
+		const int v = atoi(e);
+		if (v >= 1 && v <= RT_MAX_BANDS) ctx->n_bands = v;
+	}
+	if (const char* e = getenv("RT_B200_PPL")) {
+		const int v = atoi(e);
+		if (v == 1 || v == 2 || v == 4 || v == 8) ctx->ppl = v;
+	}
 	*out = ctx;
 	return RT_OK;
 }
@@ -387,11 +496,16 @@ void rt_destroy(rt_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release();
+	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release();
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
-	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release();
+	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->hit_slots.release();
+	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+	for (int b = 0; b < RT_MAX_BANDS; b++)
+		if (ctx->band_done[b]) cudaEventDestroy(ctx->band_done[b]);
+	if (ctx->stage_free) cudaEventDestroy(ctx->stage_free);
+	if (ctx->stage) cudaFreeHost(ctx->stage);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -459,14 +573,14 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	const RtHostScene& H = ctx->host;
 	rt_status st;
 	if ((st = upload(ctx, ctx->node_geom, H.node_geom)) || (st = upload(ctx, ctx->node_link, H.node_link)) ||
-	    (st = upload(ctx, ctx->node_child, H.node_child)) || (st = upload(ctx, ctx->slot_geom, H.slot_geom)) ||
+	    (st = upload(ctx, ctx->node_child, H.node_child)) || (st = upload(ctx, ctx->node_pk, H.node_pk)) || (st = upload(ctx, ctx->slot_geom, H.slot_geom)) ||
 	    (st = upload(ctx, ctx->slot_geom64, H.slot_geom64)) || (st = upload(ctx, ctx->slot_attr, H.slot_attr)) ||
 	    (st = upload(ctx, ctx->materials, H.materials)) || (st = upload(ctx, ctx->textures, H.textures)) ||
 	    (st = upload(ctx, ctx->substances, H.substances)) || (st = upload(ctx, ctx->texels, H.texels)))
 		return st;
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	RtDevScene& D = ctx->dev;
-	D.node_geom = ctx->node_geom.p; D.node_link = ctx->node_link.p; D.node_child = ctx->node_child.p;
+	D.node_geom = ctx->node_geom.p; D.node_link = ctx->node_link.p; D.node_child = ctx->node_child.p; D.node_pk = ctx->node_pk.p;
 	D.slot_geom = ctx->slot_geom.p; D.slot_geom64 = ctx->slot_geom64.p; D.slot_attr = ctx->slot_attr.p;
 	D.materials = ctx->materials.p; D.textures = ctx->textures.p; D.substances = ctx->substances.p;
 	D.texels = ctx->texels.p;
@@ -532,10 +646,22 @@ rt_status rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uin
 	if (prm->frame_first > 0)
 		RT_CUDA(ctx, cudaMemcpyAsync(ctx->rgb.p, rgb, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
 	if (counters) flags |= RT_RENDER_COUNTERS;
-	if (rt_status st = launch_render(ctx, cam, prm, flags, ctx->rgb.p, first_ids ? ctx->ids.p : nullptr, 0, 1)) return st;
-	RT_CUDA(ctx, cudaMemcpyAsync(rgb, ctx->rgb.p, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-	if (first_ids)
-		RT_CUDA(ctx, cudaMemcpyAsync(first_ids, ctx->ids.p, npx * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	// The frame is rendered in bands of tile rows; each finished band starts its way to the host on the copy
+	// stream (behind an event) while the next band renders, so the PCIe transfer overlaps the kernels.
+	const size_t W = cam->width;
+	const BandHook copy_band = [&](int band, int y_begin, int y_end) -> rt_status {
+		RT_CUDA(ctx, cudaEventRecord(ctx->band_done[band], ctx->stream));
+		RT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->band_done[band], 0));
+		const size_t off = (size_t)y_begin * W, n = (size_t)(y_end - y_begin) * W;
+		RT_CUDA(ctx, cudaMemcpyAsync(rgb + off * 3, ctx->rgb.p + off * 3, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+		if (first_ids)
+			RT_CUDA(ctx, cudaMemcpyAsync(first_ids + off, ctx->ids.p + off, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
+		return RT_OK;
+	};
+	if (rt_status st = launch_render(ctx, cam, prm, flags, ctx->rgb.p, first_ids ? ctx->ids.p : nullptr, 0, 1, false,
+	                                 ctx->n_bands, copy_band))
+		return st;
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
 	rt_counters tmp;
 	if (rt_status st = read_counters(ctx, &tmp)) return st;  // also synchronises and fetches the error flags
 	if (counters) *counters = tmp;

@@ -13,9 +13,11 @@
 #if defined(__CUDACC__)
 #define RT_HD __device__ __forceinline__
 #define RT_D __device__ __forceinline__
+#define RT_COLD __device__ __noinline__  // rarely executed float64 blocks: keep them out of the hot loop's registers
 #else
 #define RT_HD inline
 #define RT_D inline
+#define RT_COLD inline
 #endif
 
 struct alignas(16) RtF4 { float x, y, z, w; };
@@ -24,6 +26,14 @@ struct alignas(16) RtD2 { double x, y; };
 struct alignas(32) RtD4 { double x, y, z, w; };
 struct RtD3 { double x, y, z; };
 struct RtF3 { float x, y, z; };
+
+// Packet-walk node record.  Nodes are renumbered breadth-first at upload, so the existing children of a
+// node are consecutive: child of octant o = child_base + popc(child_mask & ((1 << o) - 1)).
+struct alignas(32) RtPNode {
+	float x, y, z, size;  // cube
+	int list_off, list_cnt;
+	int child_base, child_mask;
+};
 
 // material flags
 #define RT_MAT_RESPONSE_MASK 3u
@@ -53,6 +63,7 @@ struct RtDevScene {
 	const RtF4* node_geom;   // pos.xyz, size  (float copy of OctreeDim)
 	const RtI4* node_link;   // parent, index_within_parent, list_off, list_cnt
 	const int* node_child;   // [n*8], -1 none
+	const RtPNode* node_pk;  // the same nodes as one 32-byte record each, for the packet walk
 	// entity lists, slot order
 	const RtF4* slot_geom;   // centre.xyz, w = radius (>0, sphere) | -half_size (<0, box)
 	const RtD4* slot_geom64; // centre.xyz, w = diameter | size  (the reference's float64 values)
@@ -104,6 +115,10 @@ struct RtFrame {
 	// pixel subset for tile-sharded rendering: tiles t with t % tile_world == tile_rank
 	int tile_rank, tile_world;
 	int tile_compact;  // 1: outputs are tile-major [own tile k][16*16] instead of [height][width]
+	// band of the frame this launch covers: tiles [tile_begin, tile_end) (row-major tile numbers, whole tile
+	// rows), so that a finished band can travel to the host while the next one is rendered
+	int tile_begin, tile_end;
+	unsigned long long out_first;  // index of the band's first output pixel (frame order; 0 when tile-compact)
 	// primary-ray acceleration (exact: only skips work that provably cannot produce a hit)
 	const RtF4* prim_geom;  // [n_slots] origin-relative records (make_prim_record), or null
 	int chain_levels;       // origin chain: start_node, its parent, ..., root (post-order return order)
@@ -112,7 +127,8 @@ struct RtFrame {
 	int chain_oct[RT_MAX_CHAIN];   // octant of chain_node[k] that holds the origin (k = 0: the start cell)
 	int packet_ok;           // 1: camera rays may use the packet stage (chain complete, tree depth fits the stack)
 	unsigned* work_counter;  // persistent-warp patch dispenser
-	// continuation queue between the primary (packet) stage and the bounce stage
+	int* hit_slots;          // [pixels of this rank, output order] first-hit slots: primary stage -> shade stage
+	// continuation queue between the shade stage and the bounce stage
 	RtQueueItem* queue;      // [capacity]
 	unsigned* queue_count;   // items appended by the primary stage
 	unsigned* queue_taken;   // consumer cursor of the bounce stage

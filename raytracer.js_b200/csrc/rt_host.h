@@ -17,6 +17,7 @@ struct RtHostScene {
 	std::vector<RtF4> node_geom;
 	std::vector<RtI4> node_link;
 	std::vector<int> node_child;
+	std::vector<RtPNode> node_pk;
 	std::vector<RtF4> slot_geom;
 	std::vector<RtD4> slot_geom64;
 	std::vector<RtI4> slot_attr;
@@ -68,36 +69,70 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 	if (sc->node_list_off[0] != 0 || sc->node_list_off[N] != L)
 		RT_FAIL(RT_ERR_INVALID, "node_list_off must start at 0 and end at n_list");
 
-	hs.node_geom.resize(N);
-	hs.node_link.resize(N);
-	hs.node_child.resize((size_t)N * 8);
-	double scale = 0;
+	// ---- validate the links, then renumber breadth-first (children of a node become consecutive)
 	for (uint32_t i = 0; i < N; i++) {
-		const double* p = sc->node_pos + 3 * (size_t)i;
 		const double s = sc->node_size[i];
 		if (!(s > 0) || !std::isfinite(s)) RT_FAIL(RT_ERR_INVALID, "node %u: bad size", i);
-		hs.node_geom[i] = RtF4{(float)p[0], (float)p[1], (float)p[2], (float)s};
 		if (sc->node_list_off[i + 1] < sc->node_list_off[i]) RT_FAIL(RT_ERR_INVALID, "node %u: list offsets not monotone", i);
 		const int par = sc->node_parent[i];
 		if (i > 0 && (par < 0 || (uint32_t)par >= N)) RT_FAIL(RT_ERR_INVALID, "node %u: bad parent %d", i, par);
 		const int oc = sc->node_octant[i];
 		if (i > 0 && (oc < 0 || oc > 7)) RT_FAIL(RT_ERR_INVALID, "node %u: bad octant %d", i, oc);
-		hs.node_link[i] = RtI4{par, i > 0 ? oc : -1, (int)sc->node_list_off[i],
-		                       (int)(sc->node_list_off[i + 1] - sc->node_list_off[i])};
+		if (i > 0 && sc->node_child[(size_t)par * 8 + oc] != (int)i)
+			RT_FAIL(RT_ERR_INVALID, "node %u: parent %d does not list it as child %d", i, par, oc);
 		for (int c = 0; c < 8; c++) {
 			const int ch = sc->node_child[(size_t)i * 8 + c];
 			if (ch < -1 || ch >= (int)N || ch == 0) RT_FAIL(RT_ERR_INVALID, "node %u: bad child %d", i, ch);
-			if (ch > 0 && sc->node_parent[ch] != (int)i) RT_FAIL(RT_ERR_INVALID, "node %u: child %d does not point back", i, ch);
-			hs.node_child[(size_t)i * 8 + c] = ch;
+			if (ch > 0 && (sc->node_parent[ch] != (int)i || sc->node_octant[ch] != c))
+				RT_FAIL(RT_ERR_INVALID, "node %u: child %d does not point back", i, ch);
 		}
+	}
+	std::vector<int> perm(N, -1), order;  // perm[old] = new, order[new] = old
+	order.reserve(N);
+	order.push_back(0);
+	perm[0] = 0;
+	for (size_t head = 0; head < order.size(); head++) {
+		const int i = order[head];
+		for (int c = 0; c < 8; c++) {
+			const int ch = sc->node_child[(size_t)i * 8 + c];
+			if (ch > 0) {
+				if (perm[ch] >= 0) RT_FAIL(RT_ERR_INVALID, "node %d is reachable twice", ch);
+				perm[ch] = (int)order.size();
+				order.push_back(ch);
+			}
+		}
+	}
+	if (order.size() != N) RT_FAIL(RT_ERR_INVALID, "%zu of %u nodes are not reachable from the root", (size_t)N - order.size(), N);
+	hs.node_geom.resize(N);
+	hs.node_link.resize(N);
+	hs.node_child.resize((size_t)N * 8);
+	hs.node_pk.resize(N);
+	double scale = 0;
+	for (uint32_t ni = 0; ni < N; ni++) {
+		const int i = order[ni];
+		const double* p = sc->node_pos + 3 * (size_t)i;
+		const double s = sc->node_size[i];
+		hs.node_geom[ni] = RtF4{(float)p[0], (float)p[1], (float)p[2], (float)s};
+		const int par = sc->node_parent[i];
+		const int off = (int)sc->node_list_off[i], cnt = (int)(sc->node_list_off[i + 1] - sc->node_list_off[i]);
+		hs.node_link[ni] = RtI4{i > 0 ? perm[par] : -1, i > 0 ? sc->node_octant[i] : -1, off, cnt};
+		int base = -1, mask = 0;
+		for (int c = 0; c < 8; c++) {
+			const int ch = sc->node_child[(size_t)i * 8 + c];
+			hs.node_child[(size_t)ni * 8 + c] = ch > 0 ? perm[ch] : -1;
+			if (ch > 0) {
+				if (base < 0) base = perm[ch];
+				mask |= 1 << c;
+			}
+		}
+		hs.node_pk[ni] = RtPNode{(float)p[0], (float)p[1], (float)p[2], (float)s, off, cnt, base, mask};
 		for (int k = 0; k < 3; k++) scale = std::max(scale, std::fabs(p[k]) + s);
 	}
 	{
-		std::vector<int> depth(N, 0);
+		std::vector<int> depth(N, 0);  // breadth-first numbering: a parent always precedes its children
 		hs.max_depth = 0;
 		for (uint32_t i = 1; i < N; i++) {
-			if ((uint32_t)sc->node_parent[i] >= i) RT_FAIL(RT_ERR_INVALID, "node %u: nodes must be numbered parent-first", i);
-			depth[i] = depth[sc->node_parent[i]] + 1;
+			depth[i] = depth[hs.node_link[i].x] + 1;
 			hs.max_depth = std::max(hs.max_depth, depth[i]);
 		}
 	}

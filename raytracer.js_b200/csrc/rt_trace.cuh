@@ -525,6 +525,18 @@ RT_HD float warp_max_pos(const float (&v)[RT_NL]) {
 	return m;
 #endif
 }
+RT_HD float warp_sum(const float (&v)[RT_NL]) {
+#if defined(__CUDACC__)
+	float s = v[0];
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	return s;
+#else
+	float s = 0.0f;
+	for (int l = 0; l < 32; l++) s += v[l];
+	return s;
+#endif
+}
 RT_HD float warp_get(const float (&v)[RT_NL], int src) {
 #if defined(__CUDACC__)
 	return __shfl_sync(0xffffffffu, v[0], src);
@@ -564,16 +576,22 @@ struct RtPacket {
 	float ox, oy, oz;      // the shared origin
 	float ax, ay, az;      // unit axis of the bounding cone
 	float sin_h, cos2_h;   // half-angle of the cone (inflated)
-	float inv_lo[3];       // min over the lanes of |1/d_k|
-	float inv_hi[3];       // max over the lanes of |1/d_k|
-	int neg;               // bit k: d_k < 0 (for every lane)
+	float inv_lo[3];       // min over the rays of |1/d_k|
+	float inv_hi[3];       // max over the rays of |1/d_k|
+	int neg;               // bit k: d_k < 0 (for every ray of the class)
 	float err_l;
+};
+
+// One camera ray of the packet (float copy; the float64 direction is re-derived from the scan tables
+// when a candidate has to be confirmed).
+struct RtPRay {
+	float dx, dy, dz, inv_a;
 };
 
 // Conservative "may any ray of the packet pierce the cube [lo, lo+h]^3" by slab intervals.  With a
 // shared origin the entry/exit parameters of axis k are u * |1/d_k| with u the signed distance to the
 // near / far plane along the direction of travel, so their extremes over the packet are u times the
-// extremes of |1/d_k|.
+// extremes of |1/d_k|.  (0 * inf = NaN is dropped by fminf/fmaxf.)
 RT_HD bool packet_pierces_cube(const RtPacket& P, float lox, float loy, float loz, float h) {
 	const float lo[3] = {lox, loy, loz};
 	const float o[3] = {P.ox, P.oy, P.oz};
@@ -611,103 +629,78 @@ RT_HD unsigned xor_permute8(unsigned m, int x) {
 	return m;
 }
 
-// First-hit slot of every lane's camera ray (direction dir[l], float64) in the reference's visit order, or
-// -1.  Lanes with skip[l] set (pixels outside the frame) take no part but must carry a valid direction.
-// `stack` is RT_PACKET_STACK ints private to the warp.  A patch whose rays differ in the sign of a
-// direction component (it straddles one of the three great circles through the axes) is walked once per
-// sign class (a zero component counts as positive: such a ray never crosses a plane of that axis, so
-// either order is its own).  unresolved[l] is set for lanes that cannot take part in a lock-step walk
-// (non-finite direction; node stack overflow): the caller searches those ray by ray.
-RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const double (&dir)[RT_NL][3], const RtRayF (&r)[RT_NL],
-                             const RtPacket& P, bool (&done)[RT_NL], int* stack, int (&hit_slot)[RT_NL], bool& overflow);
-
-RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const double (&dir)[RT_NL][3], const bool (&skip)[RT_NL],
-                               int* stack, int (&hit_slot)[RT_NL], bool (&unresolved)[RT_NL]) {
-	RtRayF r[RT_NL];
-	int neg[RT_NL];
-	bool todo[RT_NL];
-	float ix[RT_NL], iy[RT_NL], iz[RT_NL], nx[RT_NL], ny[RT_NL], nz[RT_NL];
-	RT_LANES(l, lane) {
-		(void)lane;
-		r[l] = make_ray_f(F.pos, dir[l]);
-		neg[l] = (r[l].dx < 0.0f ? 1 : 0) | (r[l].dy < 0.0f ? 2 : 0) | (r[l].dz < 0.0f ? 4 : 0);
-		ix[l] = fabsf(r[l].ix); iy[l] = fabsf(r[l].iy); iz[l] = fabsf(r[l].iz);
-		const float k = sqrtf(r[l].inv_a);
-		nx[l] = r[l].dx * k; ny[l] = r[l].dy * k; nz[l] = r[l].dz * k;
-		hit_slot[l] = -1;
-		// a zero component (|1/d_k| = inf) is fine: the slab products become +-inf (conservative) or NaN,
-		// which fminf/fmaxf drop; only a non-finite direction cannot be walked
-		unresolved[l] = !skip[l] && !(r[l].inv_a > 0.0f && r[l].inv_a < INFINITY);
-		todo[l] = !skip[l] && !unresolved[l];
-	}
-	unsigned todo_mask = warp_ballot(todo);
-	while (todo_mask) {
-		// ---- one sign class: the lanes whose direction signs equal those of the first lane still to do
-		RtPacket P;
-		const int first = ffs32(todo_mask);
-		P.neg = warp_get(neg, first);
-		bool in_class[RT_NL], done[RT_NL];
-		RT_LANES(l, lane) { (void)lane; in_class[l] = todo[l] && neg[l] == P.neg; }
-		const unsigned class_mask = warp_ballot(in_class);
-		int last = 31;
-		while (!((class_mask >> last) & 1u)) last--;
-		{
-			float lo[RT_NL], hi[RT_NL];
-#define RT_RANGE(src, k)                                                           \
-	RT_LANES(l, lane) { (void)lane; lo[l] = in_class[l] ? src[l] : INFINITY; hi[l] = in_class[l] ? src[l] : 0.0f; } \
-	P.inv_lo[k] = warp_min_pos(lo) * 0.99999f;                                     \
-	P.inv_hi[k] = warp_max_pos(hi) * 1.00001f;
-			RT_RANGE(ix, 0)
-			RT_RANGE(iy, 1)
-			RT_RANGE(iz, 2)
-#undef RT_RANGE
-			// cone axis: bisector of the first and the last ray of the class; half-angle: the widest lane
-			const float ax = warp_get(nx, first) + warp_get(nx, last), ay = warp_get(ny, first) + warp_get(ny, last),
-			            az = warp_get(nz, first) + warp_get(nz, last);
-			const float k = 1.0f / sqrtf(ax * ax + ay * ay + az * az);
-			P.ax = ax * k; P.ay = ay * k; P.az = az * k;
-			RT_LANES(l, lane) {
-				(void)lane;
-				const float t = nx[l] * P.ax + ny[l] * P.ay + nz[l] * P.az;
-				const float px = nx[l] - t * P.ax, py = ny[l] - t * P.ay, pz = nz[l] - t * P.az;
-				hi[l] = in_class[l] ? sqrtf(px * px + py * py + pz * pz) : 0.0f;
-			}
-			P.sin_h = warp_max_pos(hi) * 1.0001f + 1e-6f;
-			P.cos2_h = 1.0f - P.sin_h * P.sin_h;
-			P.ox = (float)F.pos[0]; P.oy = (float)F.pos[1]; P.oz = (float)F.pos[2];
-			P.err_l = S.err_l;
-		}
-		bool overflow = !(P.sin_h < 0.5f);  // not a narrow packet (tiny frames): ray by ray
-		RT_LANES(l, lane) { (void)lane; done[l] = !in_class[l]; }
-		if (!overflow) packet_walk_class(S, F, dir, r, P, done, stack, hit_slot, overflow);
-		RT_LANES(l, lane) {
-			(void)lane;
-			if (in_class[l]) {
-				todo[l] = false;
-				if (overflow) { unresolved[l] = true; hit_slot[l] = -1; }
-			}
-		}
-		todo_mask &= ~class_mask;
-	}
+RT_HD RtPNode ld(const RtPNode* p) {
+#if defined(__CUDACC__)
+	const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+	const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+	return RtPNode{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#else
+	return *p;
+#endif
 }
 
-RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const double (&dir)[RT_NL][3], const RtRayF (&r)[RT_NL],
-                             const RtPacket& P, bool (&done)[RT_NL], int* stack, int (&hit_slot)[RT_NL], bool& overflow) {
+// Geometry of a packet: RT_PPL rays per lane, ray j of lane `lane` is the pixel (lane & 7, lane >> 3) of
+// the j-th 8x4 sub-patch; sub-patch q of a 16x16 tile sits at (8 * (q & 1), 4 * (q >> 1)).
+struct RtPatch {
+	int x0, y0;       // tile origin in the frame
+	int sub0;         // first sub-patch of this packet within the tile
+	size_t out_base;  // tile-compact output: index of the tile's first pixel
+};
+RT_HD int patch_x(const RtPatch& pt, int lane, int j) { return pt.x0 + (((pt.sub0 + j) & 1) << 3) + (lane & 7); }
+RT_HD int patch_y(const RtPatch& pt, int lane, int j) { return pt.y0 + (((pt.sub0 + j) >> 1) << 2) + (lane >> 3); }
+
+// Camera direction of pixel (x,y): get_dir_for_each_pixel (src/view/camera.ts:207-250) through the
+// host-built tables of the accumulated scan rotations.
+RT_HD void pixel_dir(const RtFrame& F, int x, int y, double* dir) {
+	const RtD4 fr = ld(F.row_fr + y);
+	const RtD2 cs = ld(F.col_cs + x);
+	dir[0] = xadd(xmul(fr.x, cs.x), xmul(F.lf[0], cs.y));
+	dir[1] = xadd(xmul(fr.y, cs.x), xmul(F.lf[1], cs.y));
+	dir[2] = xadd(xmul(fr.z, cs.x), xmul(F.lf[2], cs.y));
+}
+// pixels outside the frame ride along with the direction of the nearest pixel inside it
+RT_HD void pixel_dir_clamped(const RtFrame& F, int x, int y, double* dir) {
+	pixel_dir(F, x < F.width ? x : F.width - 1, y < F.height ? y : F.height - 1, dir);
+}
+
+// float64 confirmation of a float32 candidate for the camera ray of pixel (x,y): collision_info != null
+RT_COLD bool packet_confirm(const RtDevScene& S, const RtFrame& F, int x, int y, int slot) {
+	double dir[3];
+	pixel_dir_clamped(F, x, y, dir);
+	RtCollision col;
+	const RtD4 g64 = ld(S.slot_geom64 + slot);
+	return ld(S.slot_geom + slot).w > 0.0f ? exact_sphere(g64, F.pos, dir, col) : exact_box(g64, F.pos, dir, col);
+}
+
+// One lock-step walk for the rays of one direction-sign class (those with !done on entry).
+template <int PPL>
+RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const RtPRay (&r)[RT_NL][PPL],
+                             const RtPacket& P, bool (&done)[RT_NL][PPL], int* stack, int (&hit_slot)[RT_NL][PPL],
+                             bool& overflow) {
 	int sp = 0;
-	// pushes the children of node n (cube g) the packet may pierce, last-visited first; after_oct >= 0:
-	// only the octants a ray can still reach from octant after_oct (the origin's cell / the chain child)
-	auto push_children = [&](int n, const RtF4& g, int after_oct) {
+	auto all_done = [&]() -> bool {
+		bool open[RT_NL];
+		RT_LANES(l, lane) {
+			(void)lane;
+			open[l] = false;
+#pragma unroll
+			for (int j = 0; j < PPL; j++) open[l] = open[l] || !done[l][j];
+		}
+		return warp_ballot(open) == 0u;
+	};
+	// pushes the children of node nd the packet may pierce, last-visited first; after_oct >= 0: only the
+	// octants a ray can still reach from octant after_oct (the origin's cell / the chain child)
+	auto push_children = [&](const RtPNode& nd, int after_oct) {
+		if (!nd.child_mask) return;
 		bool ok[RT_NL];
-		int child[RT_NL];
-		const float h = g.w * 0.5f;
+		const float h = nd.size * 0.5f;
 		const int want = after_oct >= 0 ? (after_oct ^ P.neg) : 0;
 		RT_LANES(l, lane) {
 			const int o = lane & 7;
-			child[l] = ld(S.node_child + n * 8 + o);
 			const int key = o ^ P.neg;
-			ok[l] = lane < 8 && child[l] >= 0 && (key & want) == want && o != after_oct &&
-			        packet_pierces_cube(P, g.x + ((o & 1) ? h : 0.0f), g.y + ((o & 2) ? h : 0.0f),
-			                            g.z + ((o & 4) ? h : 0.0f), h);
+			ok[l] = lane < 8 && ((nd.child_mask >> o) & 1) && (key & want) == want && o != after_oct &&
+			        packet_pierces_cube(P, nd.x + ((o & 1) ? h : 0.0f), nd.y + ((o & 2) ? h : 0.0f),
+			                            nd.z + ((o & 4) ? h : 0.0f), h);
 		}
 		const unsigned m = warp_ballot(ok) & 0xffu;
 		if (!m) return;
@@ -715,14 +708,16 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const double
 		const unsigned mk = xor_permute8(m, P.neg);  // bit = visit key
 		RT_LANES(l, lane) {
 			if (ok[l]) {
-				const int key = (lane & 7) ^ P.neg;
-				stack[sp + popc32(mk >> (key + 1))] = child[l];  // smaller key = popped earlier = higher
+				const int o = lane & 7;
+				const int key = o ^ P.neg;
+				// smaller key = popped earlier = higher on the stack
+				stack[sp + popc32(mk >> (key + 1))] = nd.child_base + popc32(nd.child_mask & ((1u << o) - 1u));
 			}
 		}
 		sp += popc32(m);
 		warp_sync();
 	};
-	// scans slots [beg,end) in list order; returns true when every lane has its hit
+	// scans slots [beg,end) in list order; returns true when every ray has its hit
 	auto scan = [&](int beg, int end) -> bool {
 		for (int base = beg; base < end; base += 32) {
 			bool pass[RT_NL];
@@ -736,41 +731,163 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const double
 				const int slot = base + ffs32(m);
 				m &= m - 1;
 				const RtF4 g = ld(F.prim_geom + slot);
+				const bool quick = g.w > 0.0f && g.w != INFINITY;
 				RT_LANES(l, lane) {
-					(void)lane;
-					if (!done[l]) {
-						const bool quick = g.w > 0.0f && g.w != INFINITY;
-						const bool cand = quick ? candidate_rel(g, r[l]) : candidate(ld(S.slot_geom + slot), r[l], S.err_l);
-						if (cand) {
-							RtCollision col;
-							const RtD4 g64 = ld(S.slot_geom64 + slot);
-							const bool hit = ld(S.slot_geom + slot).w > 0.0f ? exact_sphere(g64, F.pos, dir[l], col)
-							                                                  : exact_box(g64, F.pos, dir[l], col);
-							if (hit) {
-								hit_slot[l] = slot;
-								done[l] = true;
-							}
+#pragma unroll
+					for (int j = 0; j < PPL; j++) {
+						if (done[l][j]) continue;
+						const RtPRay& q = r[l][j];
+						bool cand;
+						if (quick) {  // candidate_rel
+							const float tca = g.x * q.dx + g.y * q.dy + g.z * q.dz;
+							const float sc = tca * q.inv_a;
+							const float lx = g.x - sc * q.dx, ly = g.y - sc * q.dy, lz = g.z - sc * q.dz;
+							cand = lx * lx + ly * ly + lz * lz <= g.w && tca >= 0.0f;
+						} else {
+							RtRayF rf;
+							rf.ox = P.ox; rf.oy = P.oy; rf.oz = P.oz;
+							rf.dx = q.dx; rf.dy = q.dy; rf.dz = q.dz;
+							rf.ix = 1.0f / q.dx; rf.iy = 1.0f / q.dy; rf.iz = 1.0f / q.dz;
+							rf.inv_a = q.inv_a;
+							cand = candidate(ld(S.slot_geom + slot), rf, S.err_l);
+						}
+						if (cand && packet_confirm(S, F, patch_x(pt, lane, j), patch_y(pt, lane, j), slot)) {
+							hit_slot[l][j] = slot;
+							done[l][j] = true;
 						}
 					}
 				}
 			}
-			if (warp_ballot(done) == 0xffffffffu) return true;
+			if (all_done()) return true;
 		}
 		return false;
 	};
 
 	for (int k = 0; k < F.chain_levels; k++) {
-		const int A = F.chain_node[k];
-		push_children(A, ld(S.node_geom + A), F.chain_oct[k]);
+		push_children(ld(S.node_pk + F.chain_node[k]), F.chain_oct[k]);
 		while (sp > 0 && !overflow) {
 			const int n = stack[--sp];
 			warp_sync();
-			const RtI4 link = ld(S.node_link + n);
-			if (link.w > 0 && scan(link.z, link.z + link.w)) return;
-			push_children(n, ld(S.node_geom + n), -1);
+			const RtPNode nd = ld(S.node_pk + n);
+			if (nd.list_cnt > 0 && scan(nd.list_off, nd.list_off + nd.list_cnt)) return;
+			push_children(nd, -1);
 		}
 		if (overflow) return;
 		if (F.chain_end[k] > F.chain_beg[k] && scan(F.chain_beg[k], F.chain_end[k])) return;
+	}
+}
+
+// First-hit slot of every camera ray of the packet in the reference's visit order, or -1.  Rays with
+// skip[l][j] set (pixels outside the frame) take no part.  `stack` is RT_PACKET_STACK ints private to
+// the warp.  A packet whose rays differ in the sign of a direction component (it straddles one of the
+// three great circles through the axes) is walked once per sign class (a zero component counts as
+// positive: such a ray never crosses a plane of that axis, so either order is its own).  unresolved[l][j]
+// is set for rays that cannot take part in a lock-step walk (non-finite direction; node stack overflow):
+// the caller searches those ray by ray.
+template <int PPL>
+RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const bool (&skip)[RT_NL][PPL],
+                               int* stack, int (&hit_slot)[RT_NL][PPL], bool (&unresolved)[RT_NL][PPL]) {
+	RtPRay r[RT_NL][PPL];
+	int neg[RT_NL][PPL];
+	bool todo[RT_NL][PPL];
+	RT_LANES(l, lane) {
+#pragma unroll
+		for (int j = 0; j < PPL; j++) {
+			double dir[3];
+			pixel_dir_clamped(F, patch_x(pt, lane, j), patch_y(pt, lane, j), dir);
+			RtPRay& q = r[l][j];
+			q.dx = (float)dir[0]; q.dy = (float)dir[1]; q.dz = (float)dir[2];
+			q.inv_a = 1.0f / (q.dx * q.dx + q.dy * q.dy + q.dz * q.dz);
+			neg[l][j] = (q.dx < 0.0f ? 1 : 0) | (q.dy < 0.0f ? 2 : 0) | (q.dz < 0.0f ? 4 : 0);
+			hit_slot[l][j] = -1;
+			unresolved[l][j] = !skip[l][j] && !(q.inv_a > 0.0f && q.inv_a < INFINITY);
+			todo[l][j] = !skip[l][j] && !unresolved[l][j];
+		}
+	}
+	while (true) {
+		// ---- next sign class: that of the first ray still to do (lowest lane, then lowest j)
+		int first_j[RT_NL];
+		bool any[RT_NL];
+		RT_LANES(l, lane) {
+			(void)lane;
+			first_j[l] = -1;
+#pragma unroll
+			for (int j = PPL - 1; j >= 0; j--)
+				if (todo[l][j]) first_j[l] = j;
+			any[l] = first_j[l] >= 0;
+		}
+		const unsigned todo_mask = warp_ballot(any);
+		if (!todo_mask) break;
+		const int first_lane = ffs32(todo_mask);
+		RtPacket P;
+		{
+			int cls[RT_NL];
+			RT_LANES(l, lane) { (void)lane; cls[l] = first_j[l] >= 0 ? neg[l][first_j[l]] : 0; }
+			P.neg = warp_get(cls, first_lane);
+		}
+		bool done[RT_NL][PPL];
+		float lo[3][RT_NL], hi[3][RT_NL], sx[RT_NL], sy[RT_NL], sz[RT_NL];
+		RT_LANES(l, lane) {
+			(void)lane;
+			lo[0][l] = lo[1][l] = lo[2][l] = INFINITY;
+			hi[0][l] = hi[1][l] = hi[2][l] = 0.0f;
+			sx[l] = sy[l] = sz[l] = 0.0f;
+#pragma unroll
+			for (int j = 0; j < PPL; j++) {
+				const bool in_class = todo[l][j] && neg[l][j] == P.neg;
+				done[l][j] = !in_class;
+				if (in_class) {
+					const RtPRay& q = r[l][j];
+					const float ix = fabsf(1.0f / q.dx), iy = fabsf(1.0f / q.dy), iz = fabsf(1.0f / q.dz);
+					lo[0][l] = fminf(lo[0][l], ix); hi[0][l] = fmaxf(hi[0][l], ix);
+					lo[1][l] = fminf(lo[1][l], iy); hi[1][l] = fmaxf(hi[1][l], iy);
+					lo[2][l] = fminf(lo[2][l], iz); hi[2][l] = fmaxf(hi[2][l], iz);
+					const float k = sqrtf(q.inv_a);  // sum of the unit directions: the cone axis
+					sx[l] += q.dx * k; sy[l] += q.dy * k; sz[l] += q.dz * k;
+				}
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			P.inv_lo[k] = warp_min_pos(lo[k]) * 0.99999f;
+			P.inv_hi[k] = warp_max_pos(hi[k]) * 1.00001f;
+		}
+		{
+			const float ax = warp_sum(sx), ay = warp_sum(sy), az = warp_sum(sz);
+			const float k = 1.0f / sqrtf(ax * ax + ay * ay + az * az);
+			P.ax = ax * k; P.ay = ay * k; P.az = az * k;
+			float sn[RT_NL];
+			RT_LANES(l, lane) {
+				(void)lane;
+				sn[l] = 0.0f;
+#pragma unroll
+				for (int j = 0; j < PPL; j++) {
+					if (done[l][j]) continue;
+					const RtPRay& q = r[l][j];
+					const float kk = sqrtf(q.inv_a);
+					const float nx = q.dx * kk, ny = q.dy * kk, nz = q.dz * kk;
+					const float t = nx * P.ax + ny * P.ay + nz * P.az;
+					const float px = nx - t * P.ax, py = ny - t * P.ay, pz = nz - t * P.az;
+					sn[l] = fmaxf(sn[l], sqrtf(px * px + py * py + pz * pz));
+				}
+			}
+			P.sin_h = warp_max_pos(sn) * 1.0001f + 1e-6f;
+			P.cos2_h = 1.0f - P.sin_h * P.sin_h;
+			P.ox = (float)F.pos[0]; P.oy = (float)F.pos[1]; P.oz = (float)F.pos[2];
+			P.err_l = S.err_l;
+		}
+		bool overflow = !(P.sin_h < 0.5f);  // not a narrow packet (tiny frames, huge fov): ray by ray
+		if (!overflow) packet_walk_class<PPL>(S, F, pt, r, P, done, stack, hit_slot, overflow);
+		RT_LANES(l, lane) {
+			(void)lane;
+#pragma unroll
+			for (int j = 0; j < PPL; j++) {
+				if (todo[l][j] && neg[l][j] == P.neg) {
+					todo[l][j] = false;
+					if (overflow) { unresolved[l][j] = true; hit_slot[l][j] = -1; }
+				}
+			}
+		}
 	}
 }
 
@@ -1097,51 +1214,40 @@ RT_HD void store_constant_sample(const RtFrame& F, size_t out_index, const doubl
 	if (F.first_ids) F.first_ids[out_index] = first_entity;
 }
 
-// Camera direction of pixel (x,y): get_dir_for_each_pixel (src/view/camera.ts:207-250) through the
-// host-built tables of the accumulated scan rotations.
-RT_HD void pixel_dir(const RtFrame& F, int x, int y, double* dir) {
-	const RtD4 fr = ld(F.row_fr + y);
-	const RtD2 cs = ld(F.col_cs + x);
-	dir[0] = xadd(xmul(fr.x, cs.x), xmul(F.lf[0], cs.y));
-	dir[1] = xadd(xmul(fr.y, cs.x), xmul(F.lf[1], cs.y));
-	dir[2] = xadd(xmul(fr.z, cs.x), xmul(F.lf[2], cs.y));
+// Finishes pixel (x,y) if its path ends at the first hit `slot`; false: the bounce stage continues it.
+RT_HD bool primary_finish(const RtDevScene& S, const RtFrame& F, int x, int y, int slot, size_t out_index, uint32_t& err) {
+	double dir[3], c[3];
+	int first_entity;
+	pixel_dir(F, x, y, dir);
+	if (!primary_terminal(S, F, dir, slot, c, first_entity, err)) return false;
+	store_constant_sample(F, out_index, c, first_entity);
+	return true;
 }
 
-// The whole primary stage for one patch.  Pixels whose path ends at the first hit are finished here;
-// for the others enqueue[l] is set and qslot[l] holds the known first-hit slot (or RT_SLOT_UNKNOWN when
-// the packet could not be walked in lock-step).
-RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const int (&x)[RT_NL], const int (&y)[RT_NL],
-                         const bool (&valid)[RT_NL], const size_t (&out_index)[RT_NL], int* stack, bool (&enqueue)[RT_NL],
-                         int (&qslot)[RT_NL], uint32_t& err) {
-	double dir[RT_NL][3];
-	bool skip[RT_NL], unresolved[RT_NL];
-	int hit_slot[RT_NL];
+// The primary stage for one packet of RT_PPL sub-patches: writes the first-hit slot of every pixel of the
+// packet (or -1: miss; RT_SLOT_UNKNOWN: the ray could not take part in a lock-step walk) to F.hit_slots.
+// The shade stage (primary_finish per pixel) turns the slots into colours or queue entries.
+template <int PPL>
+RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, int* stack) {
+	bool skip[RT_NL][PPL], unresolved[RT_NL][PPL];
+	int hit_slot[RT_NL][PPL];
 	RT_LANES(l, lane) {
-		(void)lane;
-		// lanes outside the frame ride along with the direction of the nearest pixel inside it
-		pixel_dir(F, x[l] < F.width ? x[l] : F.width - 1, y[l] < F.height ? y[l] : F.height - 1, dir[l]);
-		skip[l] = !valid[l];
-		unresolved[l] = valid[l];
-		hit_slot[l] = -1;
+#pragma unroll
+		for (int j = 0; j < PPL; j++) {
+			const bool valid = patch_x(pt, lane, j) < F.width && patch_y(pt, lane, j) < F.height;
+			skip[l][j] = !valid;
+			unresolved[l][j] = valid;
+			hit_slot[l][j] = -1;
+		}
 	}
-	if (F.packet_ok) packet_primary_hits(S, F, dir, skip, stack, hit_slot, unresolved);
+	if (F.packet_ok) packet_primary_hits<PPL>(S, F, pt, skip, stack, hit_slot, unresolved);
 	RT_LANES(l, lane) {
-		(void)lane;
-		enqueue[l] = false;
-		qslot[l] = RT_SLOT_UNKNOWN;
-		if (valid[l]) {
-			if (unresolved[l]) {
-				enqueue[l] = true;
-			} else {
-				double c[3];
-				int first_entity;
-				if (primary_terminal(S, F, dir[l], hit_slot[l], c, first_entity, err)) {
-					store_constant_sample(F, out_index[l], c, first_entity);
-				} else {
-					enqueue[l] = true;
-					qslot[l] = hit_slot[l];
-				}
-			}
+#pragma unroll
+		for (int j = 0; j < PPL; j++) {
+			if (skip[l][j]) continue;
+			const int x = patch_x(pt, lane, j), y = patch_y(pt, lane, j);
+			const size_t out_index = F.tile_compact ? pt.out_base + (size_t)((y & 15) * 16 + (x & 15)) : (size_t)y * F.width + x;
+			F.hit_slots[out_index] = unresolved[l][j] ? RT_SLOT_UNKNOWN : hit_slot[l][j];
 		}
 	}
 }

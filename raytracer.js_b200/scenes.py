@@ -104,3 +104,70 @@ def checker_texture(width: int, height: int, seed: int = 1) -> ImageTexture:
     a, b = rs.randint(32, 255, 3), rs.randint(32, 255, 3)
     img = np.where(cells[..., None] == 0, a, b).astype(np.int32) + rs.randint(-16, 16, (height, width, 3))
     return ImageTexture(np.clip(img, 0, 255).astype(np.uint8), Color(0, 0, 0, 1))
+
+
+DEMO_CAMERA_POS = (0.5, 0.5, 0.5)  # reset_pos, src/main.ts:364
+
+
+def _js_int32(x: float) -> int:
+    """`x << 0` for the non-negative doubles this generator meets."""
+    return int(x)
+
+
+def demo_scene(seed: float = 0.0, n_entities: int = 16) -> SceneBundle:
+    """BASELINE config 0: the reference's own demo scene (src/main.ts:97-147,389-408) as a headless run
+    builds it: `generate_some_aligned_entities(otree, prng, 16, 0.0, [1,1,1,1], textures)` then the
+    enclosing rough unit box added last to the root; image assets are not in the tree, so every texture is
+    a SolidTexture and the sky is the ImageTexture's fallback colour (0.2,0.2,0.7) (:378).  The default
+    seed of the page is 0 (`Number(null) ?? 42`, :149-152,350).  refmax 4 (:48)."""
+    from .geometry import Vector, length, scale
+    from .material import (SIMPLE_LIGHT_MATERIAL, SIMPLE_ROUGH_MATERIAL, SIMPLE_SMOOTH_MATERIAL,
+                           SIMPLE_TRANSPARENT_MATERIAL)
+    rng = FpLcg(seed)
+    tree = _new_root()
+    substances = [SUBSTANCE_AIR, SUBSTANCE_WATER, SUBSTANCE_GLASS]
+    materials = [SIMPLE_LIGHT_MATERIAL, SIMPLE_ROUGH_MATERIAL, SIMPLE_SMOOTH_MATERIAL, SIMPLE_TRANSPARENT_MATERIAL]
+    classes = [SphereEntity, BoxEntity]
+    entities: List[Entity] = []
+    existing = []
+    for _ in range(n_entities):
+        level = 1 + math.floor(rng.next() * 7)
+        n_quant = 1 << level
+        size = 1 / n_quant
+        q = [_js_int32(rng.next() * n_quant) for _ in range(3)]
+        x, y, z = (qq * size + size / 2 for qq in q)
+        if q in existing:
+            continue
+        existing.append(q)
+        cls = classes[_js_int32(rng.next() * 2)]
+        substance = substances[_js_int32(rng.next() * 3)]
+        # get_random_element_with_weights (:77-94) with weights [1,1,1,1]: the one-argument comparator of
+        # :84 leaves the index array in order, so this is a cumulative pick in index order
+        wn = 1.0 * (1 / (((0 + 1.0) + 1.0) + 1.0 + 1.0))
+        rnd = rng.next()
+        weight, mi = 0.0, 3
+        for k in range(3):
+            weight += wn
+            if rnd <= weight:
+                mi = k
+                break
+        material = materials[mi]
+        intensity = 5.0 if material is SIMPLE_LIGHT_MATERIAL else 1.0
+        rnd = rng.next()  # get_random_texture (:67-76) with probability 0: an image only for rnd == 0
+        if rnd <= 0.0:
+            rng.next()
+            tex = SolidTexture(Color(0.0, 0.0, 0.0, 1.0))  # the unloaded ImageTexture's fallback (:56)
+        else:
+            c = Vector((rng.next(), rng.next(), rng.next()))
+            c = scale(scale(c, 1.0 / length(c)), intensity)
+            tex = SolidTexture(Color(c.v[0], c.v[1], c.v[2], 1.0))
+        e = cls(None, material, tex, substance, point(x, y, z), size)
+        add_entity_to_octree(tree, e, {"max_in_depth": 16, "max_out_depth": 0})
+        entities.append(e)
+    box = BoxEntity(None, SIMPLE_ROUGH_MATERIAL, SolidTexture(Color(1.0, 1.0, 1.0, 1.0)), SUBSTANCE_AIR,
+                    point(0.5, 0.5, 0.5), 1.0)
+    add_entity_to_octree(tree, box, {"max_in_depth": 1, "max_out_depth": 0})
+    entities.append(box)
+    sky = SkySphere(SolidTexture(Color(0.2, 0.2, 0.7, 1.0)))
+    return SceneBundle(tree, entities, sky, SUBSTANCE_AIR, refmax=4, materials=materials,
+                       description=f"demo scene of src/main.ts, FpLcg({seed}), {n_entities} attempts")

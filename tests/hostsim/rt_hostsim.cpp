@@ -6,6 +6,10 @@
 // linked into or loaded by the package, and the C ABI in include/rt_b200.h has no path to it.
 #include <thread>
 
+#ifndef HOSTSIM_PPL
+#define HOSTSIM_PPL 4  // rays per lane of the packet stage, as RT_PPL in rt_b200.cu
+#endif
+
 #include "../../raytracer.js_b200/csrc/rt_host.h"
 #include "../../raytracer.js_b200/csrc/rt_trace.cuh"
 
@@ -31,7 +35,7 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 	std::vector<RtD4> row;
 	rt_build_camera_tables(*cam, col, row);
 	RtDevScene S{};
-	S.node_geom = hs.node_geom.data(); S.node_link = hs.node_link.data(); S.node_child = hs.node_child.data();
+	S.node_geom = hs.node_geom.data(); S.node_link = hs.node_link.data(); S.node_child = hs.node_child.data(); S.node_pk = hs.node_pk.data();
 	S.slot_geom = hs.slot_geom.data(); S.slot_geom64 = hs.slot_geom64.data(); S.slot_attr = hs.slot_attr.data();
 	S.materials = hs.materials.data(); S.textures = hs.textures.data(); S.substances = hs.substances.data();
 	S.texels = hs.texels.data();
@@ -65,29 +69,43 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 		auto out_index_of = [&](int x, int y, int k) {
 			return F.tile_compact ? (size_t)k * 256 + ((y & 15) * 16 + (x & 15)) : (size_t)y * F.width + x;
 		};
+		constexpr int PPL = HOSTSIM_PPL, PER_TILE = 8 / PPL;
 		auto stage_a = [&](int t) {
 			std::vector<int> stack(RT_PACKET_STACK);
-			for (int p = t; p < my_tiles * 8; p += n_threads) {
-				const int k = p >> 3, sub = p & 7;
+			for (int p = t; p < my_tiles * PER_TILE; p += n_threads) {
+				const int k = p / PER_TILE;
 				const int tile = F.tile_rank + k * F.tile_world;
 				if (tile >= n_tiles) continue;
-				const int tx = tile % tiles_x, ty = tile / tiles_x;
-				int x[32], y[32], qslot[32];
-				bool valid[32], enqueue[32];
-				size_t out_index[32];
-				for (int lane = 0; lane < 32; lane++) {
-					x[lane] = tx * 16 + (sub & 1) * 8 + (lane & 7);
-					y[lane] = ty * 16 + (sub >> 1) * 4 + (lane >> 3);
-					valid[lane] = x[lane] < F.width && y[lane] < F.height;
-					out_index[lane] = out_index_of(x[lane], y[lane], k);
-				}
-				primary_patch(S, F, x, y, valid, out_index, stack.data(), enqueue, qslot, errs[t]);
-				for (int lane = 0; lane < 32; lane++)
-					if (enqueue[lane]) queues[t].push_back(RtQueueItem{((uint32_t)y[lane] << 16) | (uint32_t)x[lane], qslot[lane]});
+				RtPatch pt;
+				pt.x0 = (tile % tiles_x) * 16;
+				pt.y0 = (tile / tiles_x) * 16;
+				pt.sub0 = (p % PER_TILE) * PPL;
+				pt.out_base = (size_t)k * 256;
+				primary_patch<PPL>(S, F, pt, stack.data());
 			}
 		};
+		// shade stage: per pixel of this rank, primary_finish or queue
+		auto stage_shade = [&](int t) {
+			for (int k = t; k < my_tiles; k += n_threads) {
+				const int tile = F.tile_rank + k * F.tile_world;
+				if (tile >= n_tiles) continue;
+				for (int in = 0; in < 256; in++) {
+					const int x = (tile % tiles_x) * 16 + (in & 15), y = (tile / tiles_x) * 16 + (in >> 4);
+					if (x >= F.width || y >= F.height) continue;
+					const size_t oi = out_index_of(x, y, k);
+					const int slot = F.hit_slots[oi];
+					if (slot == RT_SLOT_UNKNOWN || !primary_finish(S, F, x, y, slot, oi, errs[t]))
+						queues[t].push_back(RtQueueItem{((uint32_t)y << 16) | (uint32_t)x, slot});
+				}
+			}
+		};
+		std::vector<int> hit_slots(tiled ? (size_t)my_tiles * 256 : (size_t)F.width * F.height, -1);
+		F.hit_slots = hit_slots.data();
 		std::vector<std::thread> th;
 		for (int t = 0; t < n_threads; t++) th.emplace_back(stage_a, t);
+		for (auto& t : th) t.join();
+		th.clear();
+		for (int t = 0; t < n_threads; t++) th.emplace_back(stage_shade, t);
 		for (auto& t : th) t.join();
 		th.clear();
 		// ---- bounce stage over the continuation queue

@@ -233,3 +233,21 @@ def test_tile_sharded_render_equals_full_frame():
     torch.cuda.synchronize()
     assert torch.equal(frame, full)
     np.testing.assert_array_equal(parallel.untile_numpy(gathered.cpu().numpy(), W, H, world).reshape(-1), full.cpu().numpy())
+
+
+@pytest.mark.parametrize("size,n_frames", [(128, 3), (240, 1)])
+def test_config0_demo_scene(oracle, size, n_frames):
+    """BASELINE config 0: the reference's own demo scene (src/main.ts:97-147,389-408, seed 0, refmax 4,
+    camera on the root's centre planes) at the demo page's 128x128 (dist/test.html:10) and at 240x240,
+    with the reference's own scan extents; the oracle builds the scene from ITS restatement of main.ts."""
+    from test_hostsim_parity import demo_pair
+    b, flat, cam, prm, orgb, oids, tot = demo_pair(size, size, n_frames)
+    rgb, ids, cnt, tr = gpu_render(b, size, size, n_frames=n_frames, pos=scenes.DEMO_CAMERA_POS, reference_extents=True)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 2, res
+    assert abs(cnt["segments"] - tot["segments"]) <= 1e-3 * tot["segments"]
+    # the literal 320x240 of BASELINE.json is not renderable by the reference (F4): it throws, and so do we
+    with pytest.raises(IndexError):
+        gpu_render(b, 320, 240, pos=scenes.DEMO_CAMERA_POS, reference_extents=True)
+    rgb2, ids2, _, _ = gpu_render(b, 320, 240, pos=scenes.DEMO_CAMERA_POS)  # intent mapping: renders
+    assert np.isfinite(rgb2).all() and (ids2 >= 0).all()

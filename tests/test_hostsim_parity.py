@@ -182,3 +182,39 @@ def test_packet_stage_tile_sharded(oracle):
     full, ids, _ = hostsim_render(flat, cam, prm, pipeline=True)
     parts = [hostsim_render(flat, cam, prm, pipeline=True, tile_rank=r, tile_world=world)[0] for r in range(world)]
     np.testing.assert_array_equal(untile_numpy(np.stack(parts), W, H, world), full)
+
+
+def demo_pair(width, height, n_frames, seed=0.0):
+    """BASELINE config 0 on both sides: the oracle builds the demo scene from ITS restatement of
+    src/main.ts:97-147,389-396, the product's host mirror from its own (scenes.demo_scene); entity ids are
+    insertion indices on both sides."""
+    b = scenes.demo_scene(seed)
+    flat = flat_of(b)
+    os_ = orc.Scene((0.0, 0.0, 0.0), 1.0)
+    n, sky = os_.build_demo_scene(seed, 16)
+    assert n == len(b.entities)
+    ents = os_.entities()
+    for mine, theirs in zip(b.entities, ents):  # the two generators agree on every draw
+        assert tuple(mine.get_pos().v) == theirs["pos"]
+        assert (mine.get_diameter() if isinstance(mine, rt.SphereEntity) else mine.get_size()) == theirs["extent"]
+        assert isinstance(mine, rt.BoxEntity) == (theirs["type"] == 1)
+        assert os_.textures()[theirs["texture"]]["color"][:3] == (mine.get_texture().color.r, mine.get_texture().color.g, mine.get_texture().color.b)
+    cam, ocam = cameras(width, height, scenes.DEMO_CAMERA_POS, 30.0, 0.0)
+    prm = make_params(flat, b, n_frames=n_frames)
+    orgb, oids, _, tot = orc.render(os_, ocam, refmax=4, sky_texture=sky, default_substance=0,
+                                    distance_attenuation_factor=1.0, fixed_extents=False, n_frames=n_frames,
+                                    frame_first=0, rng_mode=1, seed=prm.rng_seed, n_threads=8)
+    return b, flat, cam, prm, orgb, oids, tot
+
+
+def test_config0_demo_scene(oracle):
+    """The reference's own demo scene (seed 0, camera on the root's centre planes, rough enclosing box,
+    lights, glass, mirrors, refmax 4) at the demo page's 128x128 (dist/test.html:10), 2 exposure frames,
+    with the reference's own (swapped, square-only) scan extents."""
+    b, flat, cam, prm, orgb, oids, tot = demo_pair(128, 128, 2)
+    for pipeline in (False, True):
+        rgb, ids, cnt = hostsim_render(flat, cam, prm, reference_extents=True, pipeline=pipeline)
+        res = compare(rgb, insertion_ids(flat, b, ids), orgb, oids)
+        assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 2, (pipeline, res)
+    assert (oids >= 0).all()  # the enclosing box: every ray hits something
+    assert tot["segments"] > 2 * 128 * 128 * 1.5  # mirrors and glass: paths really bounce
