@@ -186,15 +186,28 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     prm.flags = 2 if args.path == "per-ray" else 0  # RT_PARAM_PER_RAY: the round-1 ray-by-ray kernel, for A/B runs
 
     npx = WIDTH * HEIGHT
-    frame = torch.zeros(npx * 3, dtype=torch.float32, device=dev)
+    peer = None
+    if world > 1 and args.gather == "peer":
+        # ONE frame on rank 0; every rank's kernels store their tiles into it across NVLink (CUDA IPC mapping)
+        from raytracer_js_b200 import parallel
+        peer = parallel.PeerFrame(lib, ctx, rank, world, npx * 3, dst=0)
+        frame = peer.tensor() if rank == 0 else None
+    else:
+        frame = torch.zeros(npx * 3, dtype=torch.float32, device=dev)
     tpr = lib.rt_tiles_per_rank(WIDTH, HEIGHT, world)
-    tiles = torch.zeros(tpr * 256 * 3, dtype=torch.float32, device=dev) if world > 1 else None
-    gathered = torch.zeros(world * tpr * 256 * 3, dtype=torch.float32, device=dev) if world > 1 else None
+    nccl_gather = world > 1 and peer is None
+    tiles = torch.zeros(tpr * 256 * 3, dtype=torch.float32, device=dev) if nccl_gather else None
+    gathered = torch.zeros(world * tpr * 256 * 3, dtype=torch.float32, device=dev) if nccl_gather else None
 
     def step(flags=0):
         """One frame with everything resident in HBM."""
         if world == 1:
             N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), flags, C.c_void_p(frame.data_ptr()), None))
+        elif peer is not None:
+            # fused render + gather: pixels go straight into rank 0's frame over NVLink; the barrier closes it
+            N.check(ctx, lib.rt_render_shard_device(ctx, C.byref(cd), C.byref(prm), flags, rank, world,
+                                                    C.c_void_p(peer.frame_ptr), None))
+            peer.barrier()
         else:
             N.check(ctx, lib.rt_render_tiles_device(ctx, C.byref(cd), C.byref(prm), flags, rank, world,
                                                     C.c_void_p(tiles.data_ptr()), None))
@@ -270,17 +283,31 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     else:
         # multi-GPU end to end: frame assembled on rank 0 and read back to pinned host memory every step
         host_t = torch.empty(npx * 3, dtype=torch.float32, pin_memory=True) if rank == 0 else None
+        if rank == 0:
+            # the sharded frame must be the single-GPU frame, bit for bit
+            step()
+            torch.cuda.synchronize()
+            ref = torch.zeros(npx * 3, dtype=torch.float32, device=dev)
+            N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), 0, C.c_void_p(ref.data_ptr()), None))
+            torch.cuda.synchronize()
+            assert torch.equal(ref, frame), "sharded frame differs from the single-GPU frame"
+        else:
+            step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step()
             if rank == 0:
-                host_t.copy_(frame, non_blocking=False)
+                host_t.copy_(frame, non_blocking=True)
+            if peer is not None:
+                peer.barrier()  # nobody stores into the next frame before rank 0 has read this one
         barrier()
         dt = time.perf_counter() - t0
         e2e = {"value": segments * args.steps / dt / 1e6, "unit": "Mrays/s", "frame_ms": dt / args.steps * 1e3,
                "h2d_bytes_per_step": (WIDTH * 16 + HEIGHT * 32 + 80) * world, "d2h_bytes_per_step": npx * 12}
 
+    if peer is not None:
+        peer.close()
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -299,7 +326,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": "flushed (256 MiB memset) before every timed step, outside its event pair",
                    "timing": "per-step CUDA events on the launching stream, summed over K steps, max over ranks",
-                   "parallelism": f"interleaved 16x16 tiles over {world} GPU(s), scene replicated",
+                   "parallelism": f"interleaved 16x16 tiles over {world} GPU(s), scene replicated"
+                                  + ("" if world == 1 else ", tiles stored straight into rank 0's frame over NVLink peer memory + flag barrier"
+                                     if peer is not None else ", NCCL all-gather of tile buffers + de-interleave"),
                    "segments_per_step": segments, "primary_paths_per_s": paths / (ms_per_step * 1e-3),
                    "frame_ms_kernel": ms_per_step, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
                    "scene_broadcast_bytes": scene_bcast_bytes,
@@ -333,6 +362,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = kernels store into rank 0's frame over NVLink (CUDA IPC); nccl = all-gather + untile")
     ap.add_argument("--path", default="pipeline", choices=["pipeline", "per-ray"],
                     help="pipeline (default): packet primary stage + bounce stage; per-ray: every ray walked alone")
     args = ap.parse_args()

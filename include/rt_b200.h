@@ -208,6 +208,28 @@ rt_status rt_render_tiles_device(rt_ctx* ctx, const rt_camera* cam, const rt_par
 rt_status rt_untile_device(rt_ctx* ctx, uint32_t width, uint32_t height, uint32_t world, const float* gathered_dev,
                            float* rgb_dev);
 
+/* ---- multi-GPU without a gather step: every rank writes its tiles straight into ONE frame over NVLink -- */
+/* rt_render_shard_device renders the tiles of `rank` (t % world == rank) into a buffer in FRAME layout
+ * ([height][width][3], ids [height][width]) and touches no other pixel.  frame_dev may be a peer-mapped
+ * pointer into another GPU's memory (rt_peer_open): the kernels then store their pixels across NVLink /
+ * NVSwitch as they are produced, so the "gather" is fused into the render and no tile exchange or
+ * de-interleave pass is needed.  rt_peer_barrier closes the frame: it returns (in stream order) once every
+ * rank's stores have arrived. */
+rt_status rt_render_shard_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* params, uint32_t render_flags,
+                                 uint32_t rank, uint32_t world, float* frame_dev, int32_t* ids_dev);
+#define RT_PEER_HANDLE_BYTES 64
+/* cudaMalloc'ed, zero-filled device memory that other processes on this node can map (CUDA IPC). */
+rt_status rt_peer_alloc(rt_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char handle_out[RT_PEER_HANDLE_BYTES]);
+rt_status rt_peer_free(rt_ctx* ctx, void* dev_ptr);
+/* Map / unmap an allocation of another rank (its handle travels through any host channel). */
+rt_status rt_peer_open(rt_ctx* ctx, const unsigned char handle[RT_PEER_HANDLE_BYTES], void** dev_ptr);
+rt_status rt_peer_close(rt_ctx* ctx, void* dev_ptr);
+/* All-ranks barrier on the ctx stream, one rank per GPU.  flags[r] = device pointer (own or peer-mapped) to
+ * rank r's flag array of `world` uint32 (rt_peer_alloc gives zeroed memory); epoch must grow by one per
+ * call, identically on every rank, starting at 1.  Everything enqueued before it on any rank's stream is
+ * visible to whatever is enqueued after it on every rank. */
+rt_status rt_peer_barrier(rt_ctx* ctx, uint32_t rank, uint32_t world, uint32_t* const* flags, uint32_t epoch);
+
 /* ---- host buffer pinning ---------------------------------------------------------------------- */
 /* Page-lock a caller-owned buffer (e.g. the ExposureBuffer's Float32Array backing store) so that
  * rt_render's copies run at full PCIe rate.  Optional; unregister before freeing the buffer. */

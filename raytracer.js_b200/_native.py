@@ -76,6 +76,13 @@ EXPORTS = {
     "rt_render_tiles_device": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32,
                                          C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "rt_untile_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "rt_render_shard_device": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32,
+                                         C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "rt_peer_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "rt_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_peer_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "rt_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_peer_barrier": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32]),
     "rt_flush_l2": (C.c_int, [C.c_void_p]),
     "rt_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rt_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -186,6 +186,23 @@ __global__ void rt_untile_kernel(const float* __restrict__ gathered, float* __re
 	rgb[dst + 2] = gathered[src + 2];
 }
 
+// All-ranks barrier over peer-mapped flags (one rank per GPU, one CTA of `world` threads per rank).
+// Thread t tells rank t "rank `rank` has reached epoch e" with a system-scope release store into rank t's
+// flag array, then waits until rank t has told us the same.  The fence orders every store this GPU issued
+// before (the pixels written into the peer's frame) ahead of the flag.
+__global__ void rt_peer_barrier_kernel(uint32_t* const* __restrict__ flags, int rank, int world, uint32_t epoch) {
+	const int t = threadIdx.x;
+	if (t >= world) return;
+	__threadfence_system();
+	uint32_t* theirs = flags[t] + rank;
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+	const uint32_t* mine = flags[rank] + t;
+	uint32_t v;
+	do {
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+	} while ((int32_t)(v - epoch) < 0);
+}
+
 // ================================================================== host side
 namespace {
 
@@ -252,6 +269,8 @@ struct rt_ctx {
 	DevBuf<RtF4> prim_geom;
 	DevBuf<RtQueueItem> queue;
 	DevBuf<int> hit_slots;
+	DevBuf<uint32_t*> peer_flags;
+	std::vector<uint32_t*> peer_flags_host;
 	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
 	int ppl = RT_PPL;
 };
@@ -500,7 +519,7 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
-	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->hit_slots.release();
+	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->hit_slots.release(); ctx->peer_flags.release();
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	for (int b = 0; b < RT_MAX_BANDS; b++)
 		if (ctx->band_done[b]) cudaEventDestroy(ctx->band_done[b]);
@@ -614,6 +633,73 @@ rt_status rt_render_tiles_device(rt_ctx* ctx, const rt_camera* cam, const rt_par
 	if (world == 0 || rank >= world) return fail(ctx, RT_ERR_INVALID, rt_format("bad tile shard %u of %u", rank, world));
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
 	return launch_render(ctx, cam, prm, flags, tiles_dev, tile_ids_dev, (int)rank, (int)world, true);
+}
+
+rt_status rt_render_shard_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, uint32_t rank,
+                                 uint32_t world, float* frame_dev, int32_t* ids_dev) {
+	if (rt_status st = check_args(ctx, cam, prm)) return st;
+	if (!frame_dev) return fail(ctx, RT_ERR_INVALID, "rt_render_shard_device: frame_dev is NULL");
+	if (world == 0 || rank >= world) return fail(ctx, RT_ERR_INVALID, rt_format("bad tile shard %u of %u", rank, world));
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	return launch_render(ctx, cam, prm, flags, frame_dev, ids_dev, (int)rank, (int)world, false);
+}
+
+rt_status rt_peer_alloc(rt_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char handle_out[RT_PEER_HANDLE_BYTES]) {
+	static_assert(sizeof(cudaIpcMemHandle_t) == RT_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+	if (!ctx || !dev_ptr || !handle_out || !bytes) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	void* p = nullptr;
+	RT_CUDA(ctx, cudaMalloc(&p, bytes));
+	cudaError_t e = cudaMemset(p, 0, bytes);
+	cudaIpcMemHandle_t h;
+	if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+	if (e != cudaSuccess) {
+		cudaFree(p);
+		return fail(ctx, RT_ERR_CUDA, rt_format("rt_peer_alloc: %s", cudaGetErrorString(e)));
+	}
+	memcpy(handle_out, &h, sizeof h);
+	*dev_ptr = p;
+	return RT_OK;
+}
+
+rt_status rt_peer_free(rt_ctx* ctx, void* dev_ptr) {
+	if (!ctx || !dev_ptr) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	RT_CUDA(ctx, cudaFree(dev_ptr));
+	return RT_OK;
+}
+
+rt_status rt_peer_open(rt_ctx* ctx, const unsigned char handle[RT_PEER_HANDLE_BYTES], void** dev_ptr) {
+	if (!ctx || !handle || !dev_ptr) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof h);
+	RT_CUDA(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return RT_OK;
+}
+
+rt_status rt_peer_close(rt_ctx* ctx, void* dev_ptr) {
+	if (!ctx || !dev_ptr) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	RT_CUDA(ctx, cudaIpcCloseMemHandle(dev_ptr));
+	return RT_OK;
+}
+
+rt_status rt_peer_barrier(rt_ctx* ctx, uint32_t rank, uint32_t world, uint32_t* const* flags, uint32_t epoch) {
+	if (!ctx || !flags || world == 0 || world > 64 || rank >= world) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	RT_CUDA(ctx, ctx->peer_flags.alloc(64));
+	if (ctx->peer_flags_host.size() != world || memcmp(ctx->peer_flags_host.data(), flags, world * sizeof(uint32_t*)) != 0) {
+		ctx->peer_flags_host.assign(flags, flags + world);
+		RT_CUDA(ctx, cudaMemcpyAsync(ctx->peer_flags.p, ctx->peer_flags_host.data(), world * sizeof(uint32_t*),
+		                             cudaMemcpyHostToDevice, ctx->stream));
+	}
+	rt_peer_barrier_kernel<<<1, 64, 0, ctx->stream>>>(ctx->peer_flags.p, (int)rank, (int)world, epoch);
+	ctx->launches++;
+	RT_CUDA(ctx, cudaGetLastError());
+	return RT_OK;
 }
 
 rt_status rt_untile_device(rt_ctx* ctx, uint32_t width, uint32_t height, uint32_t world, const float* gathered_dev,

@@ -75,3 +75,81 @@ def untile_numpy(gathered: np.ndarray, width: int, height: int, world: int, chan
         ty, tx = divmod(t, tiles_x)
         out[ty * TILE_H:(ty + 1) * TILE_H, tx * TILE_W:(tx + 1) * TILE_W] = g[t % world, t // world]
     return out[:height, :width]
+
+
+class _DevArray:
+    """Wraps a raw device pointer so that torch.as_tensor(...) can view it (CUDA array interface)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+class PeerFrame:
+    """The multi-GPU frame without a gather step: ONE frame buffer lives on rank `dst`; every rank maps it
+    through CUDA IPC (rt_peer_open) and its render kernels store their tiles into it across NVLink as they
+    are produced (rt_render_shard_device).  `barrier()` closes the frame (rt_peer_barrier: system-scope
+    flags in peer memory, one tiny kernel per rank on the ctx stream).  Handles travel through
+    torch.distributed (all_gather_object); one process per GPU."""
+
+    def __init__(self, lib, ctx, rank: int, world: int, n_floats: int, dst: int = 0):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from . import _native as N
+        self.lib, self.ctx, self.rank, self.world, self.dst, self.n_floats = lib, ctx, rank, world, dst, n_floats
+        self.epoch = 0
+        self._own, self._mapped = [], []
+        h = C.create_string_buffer(64)
+        flags_ptr = C.c_void_p()
+        N.check(ctx, lib.rt_peer_alloc(ctx, 4 * max(world, 1), C.byref(flags_ptr), h))
+        self._own.append(flags_ptr)
+        mine = {"flags": bytes(h.raw)}
+        frame_ptr = None
+        if rank == dst:
+            frame_ptr = C.c_void_p()
+            N.check(ctx, lib.rt_peer_alloc(ctx, 4 * n_floats, C.byref(frame_ptr), h))
+            self._own.append(frame_ptr)
+            mine["frame"] = bytes(h.raw)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        self.flag_ptrs = (C.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                self.flag_ptrs[r] = flags_ptr.value
+            else:
+                p = C.c_void_p()
+                N.check(ctx, lib.rt_peer_open(ctx, everyone[r]["flags"], C.byref(p)))
+                self._mapped.append(p)
+                self.flag_ptrs[r] = p.value
+        if rank == dst:
+            self.frame_ptr = frame_ptr.value
+        else:
+            p = C.c_void_p()
+            N.check(ctx, lib.rt_peer_open(ctx, everyone[dst]["frame"], C.byref(p)))
+            self._mapped.append(p)
+            self.frame_ptr = p.value
+        dist.barrier()
+
+    def barrier(self) -> None:
+        from . import _native as N
+        self.epoch += 1
+        N.check(self.ctx, self.lib.rt_peer_barrier(self.ctx, self.rank, self.world, self.flag_ptrs, self.epoch))
+
+    def tensor(self):
+        """torch view of the frame (only meaningful on rank dst, where the memory is local)."""
+        import torch
+        return torch.as_tensor(_DevArray(self.frame_ptr, self.n_floats), device="cuda")
+
+    def close(self) -> None:
+        import torch.distributed as dist
+
+        from . import _native as N
+        N.check(self.ctx, self.lib.rt_synchronize(self.ctx))
+        dist.barrier()  # nobody unmaps while a peer may still be storing
+        for p in self._mapped:
+            N.check(self.ctx, self.lib.rt_peer_close(self.ctx, p))
+        dist.barrier()
+        for p in self._own:
+            N.check(self.ctx, self.lib.rt_peer_free(self.ctx, p))
+        self._mapped, self._own = [], []

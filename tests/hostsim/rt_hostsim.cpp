@@ -48,9 +48,11 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 	F.row_fr = row.data();
 	F.rgb = rgb;
 	F.first_ids = ids;
-	const bool tiled = tile_world > 1;
-	F.tile_rank = tiled ? tile_rank : 0;
-	F.tile_world = tiled ? tile_world : 1;
+	// bit 1 of `pipeline`: a shard (tile_world > 1) writes into a FRAME-layout buffer (rt_render_shard_device)
+	const bool tiled = tile_world > 1 && !(pipeline & 2);
+	pipeline &= 1;
+	F.tile_rank = tile_world > 1 ? tile_rank : 0;
+	F.tile_world = tile_world > 1 ? tile_world : 1;
 	F.tile_compact = tiled ? 1 : 0;
 	// the primary-ray preparation of launch_render (rt_b200.cu), on the host
 	std::vector<RtF4> prim(hs.slot_geom.size());
@@ -142,11 +144,11 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 			for (int x = 0; x < F.width; x++) {
 				RtCounts c = {0, 0, 0, 0, 0};
 				size_t out_index = (size_t)y * F.width + x;
-				if (tiled) {  // same mapping as rt_render_kernel
+				if (F.tile_world > 1) {  // same mapping as rt_render_kernel
 					const int tiles_x = (F.width + 15) / 16;
 					const int tile = (y / 16) * tiles_x + (x / 16);
 					if (tile % tile_world != tile_rank) continue;
-					out_index = (size_t)(tile / tile_world) * 256 + (y % 16) * 16 + (x % 16);
+					if (tiled) out_index = (size_t)(tile / tile_world) * 256 + (y % 16) * 16 + (x % 16);
 				}
 				render_pixel<true>(S, F, x, y, out_index, c, errs[t]);
 				part[t].segments += c.segments; part[t].nodes += c.nodes; part[t].tests += c.tests;

@@ -218,3 +218,23 @@ def test_config0_demo_scene(oracle):
         assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 2, (pipeline, res)
     assert (oids >= 0).all()  # the enclosing box: every ray hits something
     assert tot["segments"] > 2 * 128 * 128 * 1.5  # mirrors and glass: paths really bounce
+
+
+@pytest.mark.parametrize("pipeline", [False, True])
+def test_shards_write_one_frame(oracle, pipeline):
+    """rt_render_shard_device's contract: every rank of a 3-way split renders its tiles into the SAME
+    frame-layout buffer and touches no other pixel; together they give the full frame."""
+    b = scenes.random_spheres(1500, 0.01, 0.06, seed=4.0, mix="mirrors")
+    flat = flat_of(b)
+    W, H, world = 100, 52, 3
+    cam, _ = cameras(W, H)
+    prm = make_params(flat, b)
+    full, ids, _ = hostsim_render(flat, cam, prm, pipeline=pipeline)
+    frame = np.full((H, W, 3), -7.0, np.float32)
+    for r in range(world):
+        before = frame.copy()
+        hostsim_render(flat, cam, prm, pipeline=pipeline, tile_rank=r, tile_world=world, shard_frame_layout=True, rgb=frame)
+        ty, tx = np.mgrid[0:H, 0:W]
+        mine = ((ty // 16) * ((W + 15) // 16) + tx // 16) % world == r
+        np.testing.assert_array_equal(frame[~mine], before[~mine])
+    np.testing.assert_array_equal(frame, full)

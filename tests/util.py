@@ -67,11 +67,11 @@ def insertion_ids(flat, bundle, flat_ids: np.ndarray) -> np.ndarray:
 
 
 def hostsim_render(flat, camera, params, n_threads=8, reference_extents=False, rgb=None, tile_rank=0, tile_world=1,
-                   pipeline=False):
+                   pipeline=False, shard_frame_layout=False):
     """pipeline=False: ray by ray with work counters (rt_render_kernel<true>'s body); pipeline=True: the
     packet primary stage + bounce stage (the default GPU path), counters['confirms'] = queued pixels."""
     W, H = camera.conf.screen_w, camera.conf.screen_h
-    if tile_world > 1:
+    if tile_world > 1 and not shard_frame_layout:
         from raytracer_js_b200.parallel import tiles_per_rank
         tpr = tiles_per_rank(W, H, tile_world)
         rgb = np.zeros((tpr * 256, 3), np.float32)
@@ -85,7 +85,7 @@ def hostsim_render(flat, camera, params, n_threads=8, reference_extents=False, r
     d = flat.desc()
     cd = rt.camera_desc(camera, reference_extents)
     st = hostsim().hostsim_render(C.byref(d), C.byref(cd), C.byref(params), n_threads, tile_rank, tile_world,
-                                  1 if pipeline else 0, rgb.ctypes.data, ids.ctypes.data, C.byref(cnt), err, 512)
+                                  (1 if pipeline else 0) | (2 if shard_frame_layout else 0), rgb.ctypes.data, ids.ctypes.data, C.byref(cnt), err, 512)
     if st == N.RT_ERR_BOUNDS:
         raise IndexError(err.value.decode())
     if st != 0:
