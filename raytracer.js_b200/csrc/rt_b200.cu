@@ -110,20 +110,23 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, RT_A_MINB)
 __global__ void __launch_bounds__(256)
     rt_shade_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, size_t n_out) {
 	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const size_t i = F.out_first + t;
+	size_t i = F.out_first + t;
 	const int lane = threadIdx.x & 31;
 	uint32_t err = 0;
 	bool enqueue = false;
 	int x = 0, y = 0, slot = -1;
 	if (t < n_out) {
 		bool valid = true;
-		if (F.tile_compact) {
-			const int k = (int)(i / RT_BLOCK), in = (int)(i % RT_BLOCK);
+		if (F.tile_compact || F.tile_world > 1) {
+			// sharded: thread t = pixel (t % 256) of this rank's k-th tile; the output index is tile-major
+			// (compact) or the pixel's place in the frame (a shard of ONE frame, possibly in peer memory)
+			const int k = (int)(t / RT_BLOCK), in = (int)(t % RT_BLOCK);
 			const int tile = F.tile_begin + F.tile_rank + k * F.tile_world;
 			valid = tile < F.tile_end;
 			x = (tile % tiles_x) * RT_TILE_W + (in & (RT_TILE_W - 1));
 			y = (tile / tiles_x) * RT_TILE_H + (in / RT_TILE_W);
 			valid = valid && x < F.width && y < F.height;
+			i = F.tile_compact ? t : (size_t)y * F.width + x;
 		} else {
 			y = (int)(i / F.width);
 			x = (int)(i % F.width);
@@ -229,6 +232,18 @@ struct DevBuf {
 
 }  // namespace
 
+// Identity of a device-resident render call: equal keys enqueue byte-identical work.
+struct RenderKey {
+	rt_camera cam;
+	rt_params prm;
+	uint32_t flags;
+	int rank, world, compact;
+	void* rgb;
+	void* ids;
+	uint64_t scene_version;
+	void* stream;
+};
+
 struct rt_ctx {
 	int device = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -238,6 +253,11 @@ struct rt_ctx {
 	cudaEvent_t stage_free = nullptr;            // camera-table staging may be rewritten
 	void* stage = nullptr;                       // pinned staging of the camera scan tables
 	size_t stage_cap = 0;
+	// CUDA-graph cache of the last device-resident render call (launch_render)
+	RenderKey last_key;
+	bool key_valid = false, last_was_graph = false, use_graphs = true;
+	cudaGraphExec_t graph_exec = nullptr;
+	uint64_t graph_kernels = 0, scene_version = 0;
 	int n_bands = 4;                             // rt_render: bands of tile rows (tuning knob RT_B200_BANDS)
 	std::string err;
 	uint64_t launches = 0;
@@ -311,12 +331,44 @@ rt_status check_args(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm) {
 // can be cut into `n_bands` groups of whole tile rows, each rendered by its own launches; after_band(b,
 // row_begin, row_end) is called right after band b's kernels were enqueued (rt_render uses it to start the
 // device->host copy of that band behind an event while the next band renders).
+//
+// Device-resident entry points (no band hook) repeat byte-identical work whenever the camera stands still
+// (exposure accumulation of identical frames, multi-GPU frames): the second identical call is captured
+// into a CUDA graph and later ones replay it with one launch, which takes the per-launch CPU cost (two
+// table copies, a memset, four kernels) out of the frame time.
 typedef std::function<rt_status(int, int, int)> BandHook;
 #define RT_MAX_BANDS 16
 rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb_dev,
                         int* ids_dev, int tile_rank, int tile_world, bool tile_compact = false, int n_bands = 1,
                         const BandHook& after_band = BandHook()) {
-	// camera scan tables: built on the host into pinned staging, then one async copy each
+	// ---- graph cache
+	RenderKey key;
+	memset(&key, 0, sizeof key);
+	key.cam = *cam; key.prm = *prm; key.flags = flags; key.rank = tile_rank; key.world = tile_world;
+	key.compact = tile_compact ? 1 : 0; key.rgb = rgb_dev; key.ids = ids_dev; key.scene_version = ctx->scene_version;
+	key.stream = ctx->stream;
+	const bool cacheable = ctx->use_graphs && !after_band && prm->frame_first == 0;
+	const bool same = cacheable && ctx->key_valid && memcmp(&key, &ctx->last_key, sizeof key) == 0;
+	if (same && ctx->graph_exec) {
+		RT_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+		ctx->launches += ctx->graph_kernels;
+		ctx->last_was_graph = true;
+		return RT_OK;
+	}
+	if (ctx->graph_exec) {
+		cudaGraphExecDestroy(ctx->graph_exec);
+		ctx->graph_exec = nullptr;
+	}
+	ctx->last_key = key;
+	ctx->key_valid = cacheable;
+	const bool capture = same;  // second identical call in a row
+	if (ctx->last_was_graph) {
+		// a replayed graph may still be reading the table staging
+		RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ctx->last_was_graph = false;
+	}
+
+	// ---- host preparation and every allocation (nothing below this block allocates: it may be captured)
 	const size_t n_col = cam->width, n_row = cam->height;
 	if (ctx->stage_cap < n_col * sizeof(RtD2) + n_row * sizeof(RtD4)) {
 		if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -333,9 +385,6 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	memcpy(st_col, ctx->h_col_cs.data(), n_col * sizeof(RtD2));
 	RT_CUDA(ctx, ctx->col_cs.alloc(n_col));
 	RT_CUDA(ctx, ctx->row_fr.alloc(n_row));
-	RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, st_row, n_row * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
-	RT_CUDA(ctx, cudaMemcpyAsync(ctx->col_cs.p, st_col, n_col * sizeof(RtD2), cudaMemcpyHostToDevice, ctx->stream));
-	RT_CUDA(ctx, cudaEventRecord(ctx->stage_free, ctx->stream));
 	RtFrame F{};
 	std::string err;
 	if (rt_status st = rt_fill_frame(ctx->host, cam, prm, F, err)) return fail(ctx, st, err);
@@ -350,7 +399,6 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	n_bands = std::max(1, std::min(n_bands, RT_MAX_BANDS));
 	const size_t n_cells = 9 + 3 * RT_MAX_BANDS;
 	RT_CUDA(ctx, ctx->counters.alloc(n_cells));
-	RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, n_cells * sizeof(unsigned long long), ctx->stream));
 	F.counters = ctx->counters.p;
 	F.error_flags = reinterpret_cast<uint32_t*>(ctx->counters.p + 8);
 	const bool count = (flags & RT_RENDER_COUNTERS) != 0;
@@ -359,19 +407,15 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	if ((n_tiles - tile_rank + tile_world - 1) / tile_world <= 0) return RT_OK;
 	if (tile_compact || tile_world > 1) n_bands = 1;
 	n_bands = std::min(n_bands, tiles_y);
-
 	// primary-ray preparation: origin-relative slot records + the origin chain (start node ... root)
 	const RtHostScene& H = ctx->host;
 	const int n_slots = (int)H.slot_geom.size();
+	const bool prim = n_slots > 0 && !(prm->flags & RT_PARAM_NO_PRIMARY_RECORDS);
 	F.prim_geom = nullptr;
 	F.chain_levels = 0;
 	F.packet_ok = 0;
-	if (n_slots > 0 && !(prm->flags & RT_PARAM_NO_PRIMARY_RECORDS)) {
+	if (prim) {
 		RT_CUDA(ctx, ctx->prim_geom.alloc((size_t)n_slots));
-		rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
-		                                                                         cam->pos[2], ctx->prim_geom.p);
-		ctx->launches++;
-		RT_CUDA(ctx, cudaGetLastError());
 		F.prim_geom = ctx->prim_geom.p;
 		rt_fill_chain(H, F);
 	}
@@ -383,7 +427,6 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 		RT_CUDA(ctx, ctx->queue.alloc(cap));
 		RT_CUDA(ctx, ctx->hit_slots.alloc(cap));
 	}
-
 	auto grid_of = [&](int which, const void* kernel, int threads, int& out) -> rt_status {
 		int& grid = ctx->render_grid[which];
 		if (grid == 0) {
@@ -395,56 +438,103 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 		out = grid;
 		return RT_OK;
 	};
-	for (int band = 0; band < n_bands; band++) {
-		const int row_begin = (int)((long long)tiles_y * band / n_bands), row_end = (int)((long long)tiles_y * (band + 1) / n_bands);
-		F.tile_begin = row_begin * tiles_x;
-		F.tile_end = row_end * tiles_x;
-		const int band_tiles = F.tile_end - F.tile_begin;
-		const int my_tiles = (band_tiles - tile_rank + tile_world - 1) / tile_world;
-		if (my_tiles <= 0) continue;
-		const int y_begin = row_begin * RT_TILE_H, y_end = std::min(F.height, row_end * RT_TILE_H);
-		F.out_first = tile_compact ? 0ull : (unsigned long long)y_begin * F.width;
-		const size_t n_out = tile_compact ? (size_t)my_tiles * RT_BLOCK : (size_t)(y_end - y_begin) * F.width;
-		unsigned long long* cells = ctx->counters.p + 9 + 3 * band;
-		F.work_counter = reinterpret_cast<unsigned*>(cells);
-		F.queue_count = reinterpret_cast<unsigned*>(cells + 1);
-		F.queue_taken = reinterpret_cast<unsigned*>(cells + 2);
-		const int n_patches = my_tiles * 8;
-		int grid = 0;
-		if (pipeline) {
-			// primary stage (packet walk) -> shade stage -> bounce stage over the continuation queue
-			F.queue = ctx->queue.p + F.out_first;
-			F.hit_slots = ctx->hit_slots.p;
-			// rays per lane of the packet stage (tuning knob: RT_B200_PPL=1|2|4|8 in the environment)
-			const int ppl = ctx->ppl;
-			const int n_packets = my_tiles * (8 / ppl);
-			const void* kern = ppl == 1 ? (const void*)rt_primary_kernel<1> : ppl == 2 ? (const void*)rt_primary_kernel<2>
-			                 : ppl == 4 ? (const void*)rt_primary_kernel<4> : (const void*)rt_primary_kernel<8>;
-			if (rt_status st = grid_of(4 + (ppl == 1 ? 0 : ppl == 2 ? 1 : ppl == 4 ? 2 : 3), kern, RT_A_WARPS * 32, grid)) return st;
-			const int blocks = std::min(grid, (n_packets + RT_A_WARPS - 1) / RT_A_WARPS);
-			void* args[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x, (void*)&n_packets};
-			RT_CUDA(ctx, cudaLaunchKernel(kern, dim3(blocks), dim3(RT_A_WARPS * 32), args, 0, ctx->stream));
-			ctx->launches++;
-			rt_shade_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_out);
+	// rays per lane of the packet stage (tuning knob: RT_B200_PPL=1|2|4|8 in the environment)
+	const int ppl = ctx->ppl;
+	const void* primary_kernel = ppl == 1 ? (const void*)rt_primary_kernel<1> : ppl == 2 ? (const void*)rt_primary_kernel<2>
+	                           : ppl == 4 ? (const void*)rt_primary_kernel<4> : (const void*)rt_primary_kernel<8>;
+	int grid_primary = 0, grid_bounce = 0, grid_ray = 0;
+	if (pipeline) {
+		if (rt_status st = grid_of(4 + (ppl == 1 ? 0 : ppl == 2 ? 1 : ppl == 4 ? 2 : 3), primary_kernel, RT_A_WARPS * 32, grid_primary)) return st;
+		if (rt_status st = grid_of(3, (const void*)rt_bounce_kernel, RT_WARPS_PER_CTA * 32, grid_bounce)) return st;
+	} else if (count) {
+		if (rt_status st = grid_of(1, (const void*)rt_render_kernel<true>, RT_WARPS_PER_CTA * 32, grid_ray)) return st;
+	} else {
+		if (rt_status st = grid_of(0, (const void*)rt_render_kernel<false>, RT_WARPS_PER_CTA * 32, grid_ray)) return st;
+	}
+
+	// ---- the stream work
+	const uint64_t launches_before = ctx->launches;
+	auto enqueue = [&]() -> rt_status {
+		RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, st_row, n_row * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
+		RT_CUDA(ctx, cudaMemcpyAsync(ctx->col_cs.p, st_col, n_col * sizeof(RtD2), cudaMemcpyHostToDevice, ctx->stream));
+		if (!capture) RT_CUDA(ctx, cudaEventRecord(ctx->stage_free, ctx->stream));
+		RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, n_cells * sizeof(unsigned long long), ctx->stream));
+		if (prim) {
+			rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
+			                                                                         cam->pos[2], ctx->prim_geom.p);
 			ctx->launches++;
 			RT_CUDA(ctx, cudaGetLastError());
-			if (rt_status st = grid_of(3, (const void*)rt_bounce_kernel, RT_WARPS_PER_CTA * 32, grid)) return st;
-			rt_bounce_kernel<<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
-			                   ctx->stream>>>(ctx->dev, F, tiles_x);
-		} else if (count) {
-			if (rt_status st = grid_of(1, (const void*)rt_render_kernel<true>, RT_WARPS_PER_CTA * 32, grid)) return st;
-			rt_render_kernel<true><<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
-			                         ctx->stream>>>(ctx->dev, F, tiles_x, n_patches);
-		} else {
-			if (rt_status st = grid_of(0, (const void*)rt_render_kernel<false>, RT_WARPS_PER_CTA * 32, grid)) return st;
-			rt_render_kernel<false><<<std::min(grid, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
-			                          ctx->stream>>>(ctx->dev, F, tiles_x, n_patches);
 		}
-		ctx->launches++;
-		RT_CUDA(ctx, cudaGetLastError());
-		if (after_band)
-			if (rt_status st = after_band(band, y_begin, y_end)) return st;
+		for (int band = 0; band < n_bands; band++) {
+			const int row_begin = (int)((long long)tiles_y * band / n_bands), row_end = (int)((long long)tiles_y * (band + 1) / n_bands);
+			F.tile_begin = row_begin * tiles_x;
+			F.tile_end = row_end * tiles_x;
+			const int band_tiles = F.tile_end - F.tile_begin;
+			const int my_tiles = (band_tiles - tile_rank + tile_world - 1) / tile_world;
+			if (my_tiles <= 0) continue;
+			const int y_begin = row_begin * RT_TILE_H, y_end = std::min(F.height, row_end * RT_TILE_H);
+			F.out_first = tile_compact ? 0ull : (unsigned long long)y_begin * F.width;
+			const size_t n_out = (tile_compact || tile_world > 1) ? (size_t)my_tiles * RT_BLOCK : (size_t)(y_end - y_begin) * F.width;
+			unsigned long long* cells = ctx->counters.p + 9 + 3 * band;
+			F.work_counter = reinterpret_cast<unsigned*>(cells);
+			F.queue_count = reinterpret_cast<unsigned*>(cells + 1);
+			F.queue_taken = reinterpret_cast<unsigned*>(cells + 2);
+			const int n_patches = my_tiles * 8;
+			if (pipeline) {
+				// primary stage (packet walk) -> shade stage -> bounce stage over the continuation queue
+				F.queue = ctx->queue.p + F.out_first;
+				F.hit_slots = ctx->hit_slots.p;
+				const int n_packets = my_tiles * (8 / ppl);
+				const int blocks = std::min(grid_primary, (n_packets + RT_A_WARPS - 1) / RT_A_WARPS);
+				void* args[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x, (void*)&n_packets};
+				RT_CUDA(ctx, cudaLaunchKernel(primary_kernel, dim3(blocks), dim3(RT_A_WARPS * 32), args, 0, ctx->stream));
+				ctx->launches++;
+				rt_shade_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_out);
+				ctx->launches++;
+				RT_CUDA(ctx, cudaGetLastError());
+				rt_bounce_kernel<<<std::min(grid_bounce, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
+				                   ctx->stream>>>(ctx->dev, F, tiles_x);
+			} else if (count) {
+				rt_render_kernel<true><<<std::min(grid_ray, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
+				                         ctx->stream>>>(ctx->dev, F, tiles_x, n_patches);
+			} else {
+				rt_render_kernel<false><<<std::min(grid_ray, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
+				                          ctx->stream>>>(ctx->dev, F, tiles_x, n_patches);
+			}
+			ctx->launches++;
+			RT_CUDA(ctx, cudaGetLastError());
+			if (after_band)
+				if (rt_status st = after_band(band, y_begin, y_end)) return st;
+		}
+		return RT_OK;
+	};
+	if (!capture) return enqueue();
+	RT_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+	const rt_status st = enqueue();
+	cudaGraph_t graph = nullptr;
+	const cudaError_t e_end = cudaStreamEndCapture(ctx->stream, &graph);
+	ctx->graph_kernels = ctx->launches - launches_before;
+	if (st != RT_OK || e_end != cudaSuccess || !graph) {
+		if (graph) cudaGraphDestroy(graph);
+		cudaGetLastError();
+		ctx->use_graphs = false;  // capture is not possible in this environment: stay eager from now on
+		ctx->key_valid = false;
+		ctx->launches = launches_before;
+		if (st != RT_OK) return st;
+		return enqueue();
 	}
+	const cudaError_t e_inst = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+	cudaGraphDestroy(graph);
+	if (e_inst != cudaSuccess) {
+		ctx->graph_exec = nullptr;
+		ctx->use_graphs = false;
+		ctx->key_valid = false;
+		ctx->launches = launches_before;
+		cudaGetLastError();
+		return enqueue();
+	}
+	RT_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+	ctx->last_was_graph = true;
 	return RT_OK;
 }
 
@@ -499,6 +589,7 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 		return st;
 	}
 	ctx->stream = ctx->own_stream;
+	if (const char* e = getenv("RT_B200_GRAPHS")) ctx->use_graphs = atoi(e) != 0;
 	if (const char* e = getenv("RT_B200_BANDS")) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= RT_MAX_BANDS) ctx->n_bands = v;
@@ -520,6 +611,7 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
 	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->hit_slots.release(); ctx->peer_flags.release();
+	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	for (int b = 0; b < RT_MAX_BANDS; b++)
 		if (ctx->band_done[b]) cudaEventDestroy(ctx->band_done[b]);
@@ -588,6 +680,8 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	RtHostScene hs;
 	if (rt_status st = rt_pack_scene(sc, hs, err)) return fail(ctx, st, err);
 	ctx->has_scene = false;
+	ctx->scene_version++;
+	ctx->key_valid = false;
 	ctx->host = std::move(hs);
 	const RtHostScene& H = ctx->host;
 	rt_status st;

@@ -251,3 +251,64 @@ def test_config0_demo_scene(oracle, size, n_frames):
         gpu_render(b, 320, 240, pos=scenes.DEMO_CAMERA_POS, reference_extents=True)
     rgb2, ids2, _, _ = gpu_render(b, 320, 240, pos=scenes.DEMO_CAMERA_POS)  # intent mapping: renders
     assert np.isfinite(rgb2).all() and (ids2 >= 0).all()
+
+
+@pytest.mark.parametrize("flags", [0, N.RT_RENDER_COUNTERS])
+def test_shards_store_into_one_frame(flags):
+    """rt_render_shard_device for every rank of a 3-way split, all into ONE frame-layout buffer (the
+    multi-GPU path stores into rank 0's frame over NVLink; here the three shards run on one GPU) ==
+    rt_render_device, and no shard touches another shard's pixels."""
+    import torch
+    W, H, world = 200, 120, 3
+    b = scenes.random_spheres(3000, 0.01, 0.05, seed=8.0, mix="mirrors", box_fraction=0.1)
+    cam = scenes.bench_camera(W, H)
+    tracer = rt.GpuRaytracer(rt.RaytracerConfig(b.refmax, b.sky, b.default_substance, 1.0), b.tree, cam,
+                             rt.ExposureBuffer(W, H), rt.FpLcg(1.0))
+    lib, ctx = tracer.lib, tracer.ctx
+    cd, prm = rt.camera_desc(cam), tracer.params(n_frames=2)
+    dev = torch.device("cuda")
+    full = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
+    ids_full = torch.zeros(H * W, dtype=torch.int32, device=dev)
+    N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), 0, C.c_void_p(full.data_ptr()), C.c_void_p(ids_full.data_ptr())))
+    frame = torch.full((H * W * 3,), -7.0, dtype=torch.float32, device=dev)
+    ids = torch.full((H * W,), -9, dtype=torch.int32, device=dev)
+    ty, tx = np.mgrid[0:H, 0:W]
+    owner = torch.from_numpy(((ty // 16) * ((W + 15) // 16) + tx // 16) % world).to(dev).reshape(-1)
+    for r in range(world):
+        N.check(ctx, lib.rt_render_shard_device(ctx, C.byref(cd), C.byref(prm), flags, r, world,
+                                                C.c_void_p(frame.data_ptr()), C.c_void_p(ids.data_ptr())))
+        N.check(ctx, lib.rt_synchronize(ctx))
+        done = owner <= r
+        assert bool((ids[~done] == -9).all()) and bool((frame.view(-1, 3)[~done] == -7.0).all())
+    assert torch.equal(frame, full) and torch.equal(ids, ids_full)
+
+
+def test_repeated_device_renders_replay_a_graph():
+    """Identical rt_render_device calls in a row are captured into a CUDA graph (2nd call) and replayed
+    (3rd...); a different camera in between must drop the graph.  Every call must produce the frame an
+    eager call produces, and the library's launch counter keeps counting the replayed kernels."""
+    import torch
+    W, H = 320, 200
+    b = scenes.random_spheres(3000, 0.01, 0.05, seed=8.0, mix="mirrors", box_fraction=0.1)
+    cam_a, cam_b = scenes.bench_camera(W, H), scenes.bench_camera(W, H, yaw_deg=75.0)
+    tracer = rt.GpuRaytracer(rt.RaytracerConfig(b.refmax, b.sky, b.default_substance, 1.0), b.tree, cam_a,
+                             rt.ExposureBuffer(W, H), rt.FpLcg(1.0))
+    lib, ctx = tracer.lib, tracer.ctx
+    prm = tracer.params(n_frames=2)
+    dev = torch.device("cuda")
+    out = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
+    frames, launches = {}, []
+    for name, cam in [("a", cam_a), ("a", cam_a), ("a", cam_a), ("a", cam_a), ("b", cam_b), ("a", cam_a), ("a", cam_a), ("a", cam_a)]:
+        cd = rt.camera_desc(cam)
+        out.fill_(-1.0)
+        before = lib.rt_launch_count(ctx)
+        N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), 0, C.c_void_p(out.data_ptr()), None))
+        N.check(ctx, lib.rt_synchronize(ctx))
+        torch.cuda.synchronize()
+        launches.append(lib.rt_launch_count(ctx) - before)
+        if name in frames:
+            assert torch.equal(frames[name], out), f"call with camera {name} differs from its first render"
+        else:
+            frames[name] = out.clone()
+    assert not torch.equal(frames["a"], frames["b"])
+    assert len(set(launches)) == 1 and launches[0] >= 3, launches
