@@ -230,6 +230,25 @@ rt_status rt_peer_close(rt_ctx* ctx, void* dev_ptr);
  * visible to whatever is enqueued after it on every rank. */
 rt_status rt_peer_barrier(rt_ctx* ctx, uint32_t rank, uint32_t world, uint32_t* const* flags, uint32_t epoch);
 
+/* ---- host-side helpers (no GPU work): bulk scene construction ------------------------------------ */
+/* Bulk restatement of add_entity_to_octree (src/octree_entity.ts:174-188) with max_out_depth = 0: inserts
+ * the entities in index order into an empty octree rooted at (root_pos, root_size) and keeps the result in
+ * an rt_tree.  Same nodes, same float64 node positions and same per-node insertion order as the host API
+ * builds one entity at a time, without a pointer tree (1 M entities in well under a second).  Fails with
+ * RT_ERR_UNSUPPORTED where the reference throws TreeOutsideGrowError (an entity that does not fit the root);
+ * the message is rt_last_error(NULL). */
+typedef struct rt_tree rt_tree;
+rt_status rt_tree_build(const double root_pos[3], double root_size, uint32_t n_entities, const uint8_t* ent_type,
+                        const double* ent_pos, const double* ent_extent, uint32_t max_in_depth, rt_tree** out);
+uint32_t rt_tree_node_count(const rt_tree* t);
+/* Fills the node arrays of an rt_scene_desc (sizes from rt_tree_node_count / n_entities); entity ids in
+ * list_entity are the indices of the arrays given to rt_tree_build. */
+void rt_tree_export(const rt_tree* t, double* node_pos, double* node_size, int32_t* node_child, int32_t* node_parent,
+                    int32_t* node_octant, uint32_t* node_list_off, uint32_t* list_entity);
+void rt_tree_free(rt_tree* t);
+/* FpLcg (src/math/rng/fp-lcg.ts:62-82): seed(seed), then n x next() into out. */
+void rt_fplcg_fill(double seed, uint64_t n, double* out);
+
 /* ---- host buffer pinning ---------------------------------------------------------------------- */
 /* Page-lock a caller-owned buffer (e.g. the ExposureBuffer's Float32Array backing store) so that
  * rt_render's copies run at full PCIe rate.  Optional; unregister before freeing the buffer. */

@@ -9,12 +9,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librt_b200.so")
 SOURCES = ["rt_b200.cu"]
-HEADERS = ["rt_common.h", "rt_host.h", "rt_trace.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
+HEADERS = ["rt_common.h", "rt_host.h", "rt_build.h", "rt_trace.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-ffp-contract=off",  # host float64 (camera tables, tree builder, FpLcg) must round like a JS engine
     "-cudart", "static",
 ]
 

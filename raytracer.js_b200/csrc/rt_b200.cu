@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <functional>
 
+#include "rt_build.h"
 #include "rt_host.h"
 #include "rt_trace.cuh"
 
@@ -77,16 +78,15 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 #define RT_PPL 4  // rays per lane in the primary stage: a packet is RT_PPL 8x4 sub-patches of a 16x16 tile
 #endif
 #ifndef RT_A_MINB
-#define RT_A_MINB 3
+#define RT_A_MINB 4
 #endif
 template <int PPL>
 __global__ void __launch_bounds__(RT_A_WARPS * 32, RT_A_MINB)
     rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_packets) {
-	__shared__ int stacks[RT_A_WARPS][RT_PACKET_STACK];
+	__shared__ RtPNode stacks[RT_A_WARPS][RT_PACKET_STACK];
 	constexpr int PER_TILE = 8 / PPL;
 	const int lane = threadIdx.x & 31;
-	int* stack = stacks[threadIdx.x >> 5];
-	uint32_t err = 0;
+	RtPNode* stack = stacks[threadIdx.x >> 5];
 	while (true) {
 		unsigned p = 0;
 		if (lane == 0) p = atomicAdd(F.work_counter, 1u);
@@ -794,6 +794,52 @@ rt_status rt_peer_barrier(rt_ctx* ctx, uint32_t rank, uint32_t world, uint32_t* 
 	ctx->launches++;
 	RT_CUDA(ctx, cudaGetLastError());
 	return RT_OK;
+}
+
+rt_status rt_tree_build(const double root_pos[3], double root_size, uint32_t n, const uint8_t* type, const double* pos,
+                        const double* extent, uint32_t max_in_depth, rt_tree** out) {
+	if (!out) return fail(nullptr, RT_ERR_INVALID, "rt_tree_build: out is NULL");
+	*out = nullptr;
+	if (!root_pos || !(root_size > 0) || (n && (!type || !pos || !extent)))
+		return fail(nullptr, RT_ERR_INVALID, "rt_tree_build: bad arguments");
+	rt_tree* t = new rt_tree();
+	std::string err;
+	if (!rt_tree_build_impl(*t, root_pos, root_size, n, type, pos, extent, max_in_depth, err)) {
+		delete t;
+		return fail(nullptr, RT_ERR_UNSUPPORTED, err);
+	}
+	*out = t;
+	return RT_OK;
+}
+
+uint32_t rt_tree_node_count(const rt_tree* t) { return t ? (uint32_t)t->size.size() : 0; }
+
+void rt_tree_export(const rt_tree* t, double* node_pos, double* node_size, int32_t* node_child, int32_t* node_parent,
+                    int32_t* node_octant, uint32_t* node_list_off, uint32_t* list_entity) {
+	if (!t) return;
+	if (node_pos) memcpy(node_pos, t->pos.data(), t->pos.size() * sizeof(double));
+	if (node_size) memcpy(node_size, t->size.data(), t->size.size() * sizeof(double));
+	if (node_child) memcpy(node_child, t->child.data(), t->child.size() * sizeof(int32_t));
+	if (node_parent) memcpy(node_parent, t->parent.data(), t->parent.size() * sizeof(int32_t));
+	if (node_octant) memcpy(node_octant, t->octant.data(), t->octant.size() * sizeof(int32_t));
+	if (node_list_off) memcpy(node_list_off, t->list_off.data(), t->list_off.size() * sizeof(uint32_t));
+	if (list_entity && !t->list_entity.empty()) memcpy(list_entity, t->list_entity.data(), t->list_entity.size() * sizeof(uint32_t));
+}
+
+void rt_tree_free(rt_tree* t) { delete t; }
+
+void rt_fplcg_fill(double seed, uint64_t n, double* out) {
+	// host restatement of FpLcg (src/math/rng/fp-lcg.ts:62-82); `% 1.0` on non-negative values
+	double s1 = seed, s2 = seed * RT_LCG_MUL3, s3 = seed * RT_LCG_MUL2;
+	for (uint64_t i = 0; i < n; i++) {
+		const double a = fmod(s1 * RT_LCG_MUL1 + RT_LCG_TERM1, 1.0);
+		const double b = fmod(s2 * RT_LCG_MUL2 + RT_LCG_TERM2, 1.0);
+		const double c = fmod(s3 * RT_LCG_MUL3 + RT_LCG_TERM3, 1.0);
+		s1 = b + c;
+		s2 = c;
+		s3 = a + b;
+		out[i] = fmod(a + b + c, 1.0);
+	}
 }
 
 rt_status rt_untile_device(rt_ctx* ctx, uint32_t width, uint32_t height, uint32_t world, const float* gathered_dev,

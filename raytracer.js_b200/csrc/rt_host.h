@@ -136,29 +136,38 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 			hs.max_depth = std::max(hs.max_depth, depth[i]);
 		}
 	}
+	// Slots follow the breadth-first node numbering (each node's run keeps its insertion order), so the lists
+	// of sibling nodes are neighbours in memory, like their records.
 	hs.slot_geom.resize(L);
 	hs.slot_geom64.resize(L);
 	hs.slot_attr.resize(L);
 	std::vector<uint8_t> seen(E, 0);
-	for (uint32_t s = 0; s < L; s++) {
-		const uint32_t e = sc->list_entity[s];
-		if (e >= E) RT_FAIL(RT_ERR_INVALID, "list slot %u: entity %u out of range", s, e);
-		if (seen[e]) RT_FAIL(RT_ERR_INVALID, "entity %u is listed in more than one node", e);
-		seen[e] = 1;
-		const double* p = sc->ent_pos + 3 * (size_t)e;
-		const double ext = sc->ent_extent[e];
-		const uint32_t type = sc->ent_type[e];
-		if (type > RT_ENTITY_BOX) RT_FAIL(RT_ERR_UNSUPPORTED, "unsupported Entity subclass (type %u) for entity %u", type, e);
-		if (!(ext > 0) || !std::isfinite(ext)) RT_FAIL(RT_ERR_INVALID, "entity %u: bad extent", e);
-		const int m = sc->ent_material[e], t = sc->ent_texture[e], sb = sc->ent_substance[e];
-		if (m < 0 || (uint32_t)m >= sc->n_materials) RT_FAIL(RT_ERR_INVALID, "entity %u: material %d", e, m);
-		if (t < 0 || (uint32_t)t >= sc->n_textures) RT_FAIL(RT_ERR_INVALID, "entity %u: texture %d", e, t);
-		if (sb < -1 || sb >= (int)sc->n_substances) RT_FAIL(RT_ERR_INVALID, "entity %u: substance %d", e, sb);
-		const float w = type == RT_ENTITY_SPHERE ? (float)(ext / 2) : -(float)(ext / 2);
-		hs.slot_geom[s] = RtF4{(float)p[0], (float)p[1], (float)p[2], w};
-		hs.slot_geom64[s] = RtD4{p[0], p[1], p[2], ext};
-		hs.slot_attr[s] = RtI4{(int)e, m | (int)(type << RT_ATTR_TYPE_SHIFT), t, sb};
-		for (int k = 0; k < 3; k++) scale = std::max(scale, std::fabs(p[k]) + ext);
+	uint32_t s = 0;
+	for (uint32_t ni = 0; ni < N; ni++) {
+		const int i = order[ni];
+		const uint32_t beg = sc->node_list_off[i], end = sc->node_list_off[i + 1];
+		hs.node_link[ni].z = (int)s;
+		hs.node_pk[ni].list_off = (int)s;
+		for (uint32_t li = beg; li < end; li++, s++) {
+			const uint32_t e = sc->list_entity[li];
+			if (e >= E) RT_FAIL(RT_ERR_INVALID, "list slot %u: entity %u out of range", li, e);
+			if (seen[e]) RT_FAIL(RT_ERR_INVALID, "entity %u is listed in more than one node", e);
+			seen[e] = 1;
+			const double* p = sc->ent_pos + 3 * (size_t)e;
+			const double ext = sc->ent_extent[e];
+			const uint32_t type = sc->ent_type[e];
+			if (type > RT_ENTITY_BOX) RT_FAIL(RT_ERR_UNSUPPORTED, "unsupported Entity subclass (type %u) for entity %u", type, e);
+			if (!(ext > 0) || !std::isfinite(ext)) RT_FAIL(RT_ERR_INVALID, "entity %u: bad extent", e);
+			const int m = sc->ent_material[e], t = sc->ent_texture[e], sb = sc->ent_substance[e];
+			if (m < 0 || (uint32_t)m >= sc->n_materials) RT_FAIL(RT_ERR_INVALID, "entity %u: material %d", e, m);
+			if (t < 0 || (uint32_t)t >= sc->n_textures) RT_FAIL(RT_ERR_INVALID, "entity %u: texture %d", e, t);
+			if (sb < -1 || sb >= (int)sc->n_substances) RT_FAIL(RT_ERR_INVALID, "entity %u: substance %d", e, sb);
+			const float w = type == RT_ENTITY_SPHERE ? (float)(ext / 2) : -(float)(ext / 2);
+			hs.slot_geom[s] = RtF4{(float)p[0], (float)p[1], (float)p[2], w};
+			hs.slot_geom64[s] = RtD4{p[0], p[1], p[2], ext};
+			hs.slot_attr[s] = RtI4{(int)e, m | (int)(type << RT_ATTR_TYPE_SHIFT), t, sb};
+			for (int k = 0; k < 3; k++) scale = std::max(scale, std::fabs(p[k]) + ext);
+		}
 	}
 	hs.materials.resize(sc->n_materials);
 	hs.any_transmission = false;

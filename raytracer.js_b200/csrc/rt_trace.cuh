@@ -629,6 +629,13 @@ RT_HD unsigned xor_permute8(unsigned m, int x) {
 	return m;
 }
 
+RT_HD void prefetch_l1(const void* p) {
+#if defined(__CUDACC__)
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+	(void)p;
+#endif
+}
 RT_HD RtPNode ld(const RtPNode* p) {
 #if defined(__CUDACC__)
 	const float4 a = __ldg(reinterpret_cast<const float4*>(p));
@@ -675,7 +682,7 @@ RT_COLD bool packet_confirm(const RtDevScene& S, const RtFrame& F, int x, int y,
 // One lock-step walk for the rays of one direction-sign class (those with !done on entry).
 template <int PPL>
 RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const RtPRay (&r)[RT_NL][PPL],
-                             const RtPacket& P, bool (&done)[RT_NL][PPL], int* stack, int (&hit_slot)[RT_NL][PPL],
+                             const RtPacket& P, bool (&done)[RT_NL][PPL], RtPNode* stack, int (&hit_slot)[RT_NL][PPL],
                              bool& overflow) {
 	int sp = 0;
 	auto all_done = [&]() -> bool {
@@ -710,8 +717,13 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 			if (ok[l]) {
 				const int o = lane & 7;
 				const int key = o ^ P.neg;
-				// smaller key = popped earlier = higher on the stack
-				stack[sp + popc32(mk >> (key + 1))] = nd.child_base + popc32(nd.child_mask & ((1u << o) - 1u));
+				// The stack holds the children's RECORDS, not their indices: the (up to 8) records are
+				// consecutive in memory (breadth-first numbering), so this is one coalesced fetch whose
+				// latency is paid once per push instead of once per pop; and since the slots follow the same
+				// order, the children's lists are neighbours too and can be prefetched right here.
+				const RtPNode rec = ld(S.node_pk + nd.child_base + popc32(nd.child_mask & ((1u << o) - 1u)));
+				if (rec.list_cnt > 0) prefetch_l1(F.prim_geom + rec.list_off);
+				stack[sp + popc32(mk >> (key + 1))] = rec;  // smaller key = popped earlier = higher on the stack
 			}
 		}
 		sp += popc32(m);
@@ -766,9 +778,8 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 	for (int k = 0; k < F.chain_levels; k++) {
 		push_children(ld(S.node_pk + F.chain_node[k]), F.chain_oct[k]);
 		while (sp > 0 && !overflow) {
-			const int n = stack[--sp];
+			const RtPNode nd = stack[--sp];
 			warp_sync();
-			const RtPNode nd = ld(S.node_pk + n);
 			if (nd.list_cnt > 0 && scan(nd.list_off, nd.list_off + nd.list_cnt)) return;
 			push_children(nd, -1);
 		}
@@ -786,7 +797,7 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 // the caller searches those ray by ray.
 template <int PPL>
 RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const bool (&skip)[RT_NL][PPL],
-                               int* stack, int (&hit_slot)[RT_NL][PPL], bool (&unresolved)[RT_NL][PPL]) {
+                               RtPNode* stack, int (&hit_slot)[RT_NL][PPL], bool (&unresolved)[RT_NL][PPL]) {
 	RtPRay r[RT_NL][PPL];
 	int neg[RT_NL][PPL];
 	bool todo[RT_NL][PPL];
@@ -1228,7 +1239,7 @@ RT_HD bool primary_finish(const RtDevScene& S, const RtFrame& F, int x, int y, i
 // packet (or -1: miss; RT_SLOT_UNKNOWN: the ray could not take part in a lock-step walk) to F.hit_slots.
 // The shade stage (primary_finish per pixel) turns the slots into colours or queue entries.
 template <int PPL>
-RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, int* stack) {
+RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, RtPNode* stack) {
 	bool skip[RT_NL][PPL], unresolved[RT_NL][PPL];
 	int hit_slot[RT_NL][PPL];
 	RT_LANES(l, lane) {

@@ -200,3 +200,55 @@ def flatten_scene(tree: Octree, extra_textures=(), extra_substances=()) -> FlatS
     a["ent_substance"] = np.array(ent_sub, np.int32)
     fs.finalize_tables()
     return fs
+
+
+def flat_from_arrays(ent_type, ent_pos, ent_extent, ent_material, ent_texture, ent_substance, materials, textures,
+                     substances, root_pos=(0.0, 0.0, 0.0), root_size=1.0, max_in_depth=16) -> FlatScene:
+    """Bulk path for big scenes: the octree is built by the native restatement of add_entity_to_octree
+    (rt_tree_build in librt_b200, csrc/rt_build.h) straight from entity arrays, without Python entity
+    objects or a pointer tree.  Entity ids are the array indices (= insertion order).  `materials`,
+    `textures`, `substances` are lists of the host API's objects, indexed by the ent_* index arrays."""
+    lib = N.load()
+    fs = FlatScene()
+    for m in materials:
+        fs.material_index(m)
+    for t in textures:
+        fs.texture_index(t)
+    for s in substances:
+        fs.substance_index(s)
+    a = fs.arrays
+    a["ent_type"] = np.ascontiguousarray(ent_type, np.uint8)
+    a["ent_pos"] = np.ascontiguousarray(ent_pos, np.float64).reshape(-1, 3)
+    a["ent_extent"] = np.ascontiguousarray(ent_extent, np.float64)
+    a["ent_material"] = np.ascontiguousarray(ent_material, np.int32)
+    a["ent_texture"] = np.ascontiguousarray(ent_texture, np.int32)
+    a["ent_substance"] = np.ascontiguousarray(ent_substance, np.int32)
+    n = len(a["ent_extent"])
+    rp = np.ascontiguousarray(root_pos, np.float64)
+    tree = C.c_void_p()
+    st = lib.rt_tree_build(rp.ctypes.data_as(N._dp), float(root_size), n, a["ent_type"].ctypes.data_as(N._bp),
+                           a["ent_pos"].ctypes.data_as(N._dp), a["ent_extent"].ctypes.data_as(N._dp), int(max_in_depth),
+                           C.byref(tree))
+    if st != N.RT_OK:
+        from .octree_entity import TreeOutsideGrowError
+        msg = lib.rt_last_error(None).decode()
+        if st == N.RT_ERR_UNSUPPORTED:
+            raise TreeOutsideGrowError(None, msg)
+        raise N.RtError(st, msg)
+    try:
+        nn = lib.rt_tree_node_count(tree)
+        a["node_pos"] = np.zeros((nn, 3))
+        a["node_size"] = np.zeros(nn)
+        a["node_child"] = np.zeros((nn, 8), np.int32)
+        a["node_parent"] = np.zeros(nn, np.int32)
+        a["node_octant"] = np.zeros(nn, np.int32)
+        a["node_list_off"] = np.zeros(nn + 1, np.uint32)
+        a["list_entity"] = np.zeros(n, np.uint32)
+        lib.rt_tree_export(tree, a["node_pos"].ctypes.data_as(N._dp), a["node_size"].ctypes.data_as(N._dp),
+                           a["node_child"].ctypes.data_as(N._ip), a["node_parent"].ctypes.data_as(N._ip),
+                           a["node_octant"].ctypes.data_as(N._ip), a["node_list_off"].ctypes.data_as(N._up),
+                           a["list_entity"].ctypes.data_as(N._up))
+    finally:
+        lib.rt_tree_free(tree)
+    fs.finalize_tables()
+    return fs

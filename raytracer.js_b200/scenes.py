@@ -171,3 +171,85 @@ def demo_scene(seed: float = 0.0, n_entities: int = 16) -> SceneBundle:
     sky = SkySphere(SolidTexture(Color(0.2, 0.2, 0.7, 1.0)))
     return SceneBundle(tree, entities, sky, SUBSTANCE_AIR, refmax=4, materials=materials,
                        description=f"demo scene of src/main.ts, FpLcg({seed}), {n_entities} attempts")
+
+
+@dataclass
+class FlatBundle:
+    """A big scene that only exists as flat arrays (no Python entity objects, no pointer tree)."""
+    flat: "FlatScene"
+    sky_texture: int
+    default_substance: int
+    refmax: int
+    n_entities: int
+    description: str = ""
+
+
+def fplcg_draws(seed: float, n: int) -> np.ndarray:
+    """n consecutive FpLcg(seed).next() values (native restatement in librt_b200: rt_fplcg_fill)."""
+    from . import _native as N
+    out = np.zeros(int(n), np.float64)
+    N.load().rt_fplcg_fill(float(seed), int(n), out.ctypes.data_as(N._dp))
+    return out
+
+
+def random_spheres_flat(n: int, dmin: float = 0.002, dmax: float = 0.006, seed: float = 42.0, mix: str = "diffuse",
+                        box_fraction: float = 0.0, textures: Optional[List[Texture]] = None,
+                        max_in_depth: int = 16) -> FlatBundle:
+    """The same scenes as random_spheres() (same draws in the same order, so the same entities), built in
+    bulk: draws from the native FpLcg, octree from the native restatement of add_entity_to_octree
+    (flatten.flat_from_arrays).  This is how the 100 k - 1 M entity configs are built in seconds."""
+    from .flatten import flat_from_arrays
+    if mix == "diffuse":
+        mats = [SolidMaterial(ResponseType.REFLECTION, False, False, 0.0)]
+        cum = np.array([1.0])
+    elif mix == "mirrors":
+        mats = [SolidMaterial(ResponseType.REFLECTION, False, True, 0.0),
+                SolidMaterial(ResponseType.REFLECTION, False, False, 0.0),
+                SolidMaterial(ResponseType.REFLECTION, False, True, 0.5),
+                SolidMaterial(ResponseType.REFLECTION, True, False, 0.0)]
+        cum = np.array([0.70, 0.85, 0.95, 1.0])
+    else:
+        raise ValueError(mix)
+    has_kind, has_pick = box_fraction > 0, len(mats) > 1
+    sky = SolidTexture(Color(0.2, 0.2, 0.7, 1.0))
+    if not textures:
+        k = 4 + int(has_kind) + int(has_pick) + 3
+        u = fplcg_draws(seed, n * k).reshape(n, k)
+        d = dmin + u[:, 0] * (dmax - dmin)
+        pos = d[:, None] / 2 + u[:, 1:4] * (1 - d[:, None])
+        col = 4
+        is_box = np.zeros(n, bool)
+        if has_kind:
+            is_box = u[:, col] < box_fraction
+            col += 1
+        mi = np.zeros(n, np.int64)
+        if has_pick:
+            mi = np.minimum(np.searchsorted(cum, u[:, col], side="left"), len(cum) - 1)  # first i with u <= cum[i]
+            col += 1
+        kcol = np.where(np.array([m.light_source for m in mats])[mi], 5.0, 1.0)
+        rgb = u[:, col:col + 3] * kcol[:, None]
+        tex_objs = [sky] + [SolidTexture(Color(float(r), float(g), float(b), 1.0)) for r, g, b in rgb]
+        ent_tex = np.arange(1, n + 1)
+    else:
+        # variable number of draws per entity: sequential (medium-sized textured scenes only)
+        rng = FpLcg(seed)
+        d, pos, is_box, mi, ent_tex = np.zeros(n), np.zeros((n, 3)), np.zeros(n, bool), np.zeros(n, np.int64), np.zeros(n, np.int64)
+        tex_objs = [sky] + list(textures)
+        for i in range(n):
+            d[i] = dmin + rng.next() * (dmax - dmin)
+            pos[i] = [d[i] / 2 + rng.next() * (1 - d[i]) for _ in range(3)]
+            is_box[i] = has_kind and rng.next() < box_fraction
+            if has_pick:
+                u = rng.next()
+                while mi[i] < len(cum) - 1 and u > cum[mi[i]]:
+                    mi[i] += 1
+            if not mats[mi[i]].light_source and not is_box[i]:
+                ent_tex[i] = 1 + int(rng.next() * len(textures))
+            else:
+                kk = 5.0 if mats[mi[i]].light_source else 1.0
+                tex_objs.append(SolidTexture(Color(rng.next() * kk, rng.next() * kk, rng.next() * kk, 1.0)))
+                ent_tex[i] = len(tex_objs) - 1
+    flat = flat_from_arrays(is_box.astype(np.uint8), pos, d, mi, ent_tex, np.zeros(n, np.int32), mats, tex_objs,
+                            [SUBSTANCE_AIR], max_in_depth=max_in_depth)
+    return FlatBundle(flat, 0, 0, 1 if mix == "diffuse" else 4, n,
+                      f"{n} random spheres d in [{dmin},{dmax}], seed {seed}, mix {mix} (bulk build)")

@@ -73,7 +73,7 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 		};
 		constexpr int PPL = HOSTSIM_PPL, PER_TILE = 8 / PPL;
 		auto stage_a = [&](int t) {
-			std::vector<int> stack(RT_PACKET_STACK);
+			std::vector<RtPNode> stack(RT_PACKET_STACK);
 			for (int p = t; p < my_tiles * PER_TILE; p += n_threads) {
 				const int k = p / PER_TILE;
 				const int tile = F.tile_rank + k * F.tile_world;

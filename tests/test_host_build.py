@@ -85,3 +85,49 @@ def test_outside_growth_and_error(oracle):
     # dimensions of the passed tree and of the absolute root in that case)
     with pytest.raises(ValueError):
         rt.flatten_scene(tree)
+
+
+def canonical_tree(a):
+    """Numbering-independent description of a flat tree: {(pos, size): (sorted child octants, entity list)}."""
+    out = {}
+    for i in range(len(a["node_size"])):
+        key = (tuple(a["node_pos"][i].tolist()), float(a["node_size"][i]))
+        beg, end = int(a["node_list_off"][i]), int(a["node_list_off"][i + 1])
+        out[key] = (tuple(int(c >= 0) for c in a["node_child"][i]), beg, end)
+    return out
+
+
+@pytest.mark.parametrize("mix,box_fraction", [("diffuse", 0.0), ("mirrors", 0.2)])
+def test_bulk_builder_equals_one_by_one_insertion(mix, box_fraction):
+    """rt_tree_build (native bulk restatement of add_entity_to_octree) against the host API inserting the
+    same entities one at a time: same nodes (float64 positions and sizes), same per-node entity order, same
+    entity / material / texture tables."""
+    from raytracer_js_b200 import scenes
+    n = 3000
+    b = scenes.random_spheres(n, 0.004, 0.05, seed=7.0, mix=mix, box_fraction=box_fraction)
+    ref = rt.flatten_scene(b.tree, extra_textures=[b.sky.texture], extra_substances=[b.default_substance])
+    fb = scenes.random_spheres_flat(n, 0.004, 0.05, seed=7.0, mix=mix, box_fraction=box_fraction)
+    A, B = ref.arrays, fb.flat.arrays
+    order = {id(e): i for i, e in enumerate(b.entities)}
+    ins = np.array([order[id(e)] for e in ref.entities])  # flattener id -> insertion index
+    np.testing.assert_array_equal(B["ent_pos"][ins], A["ent_pos"])
+    np.testing.assert_array_equal(B["ent_extent"][ins], A["ent_extent"])
+    np.testing.assert_array_equal(B["ent_type"][ins], A["ent_type"])
+    np.testing.assert_array_equal(B["tex_color"][B["ent_texture"][ins]], A["tex_color"][A["ent_texture"]])
+    np.testing.assert_array_equal(B["mat_mirror"][B["ent_material"][ins]], A["mat_mirror"][A["ent_material"]])
+    np.testing.assert_array_equal(B["mat_light"][B["ent_material"][ins]], A["mat_light"][A["ent_material"]])
+    ta, tb = canonical_tree(A), canonical_tree(B)
+    assert ta.keys() == tb.keys()
+    for key in ta:
+        ca, ba, ea = ta[key]
+        cb, bb, eb = tb[key]
+        assert ca == cb
+        assert ins[A["list_entity"][ba:ea]].tolist() == B["list_entity"][bb:eb].tolist(), key
+
+
+def test_bulk_builder_rejects_entities_outside_the_root():
+    from raytracer_js_b200.flatten import flat_from_arrays
+    mat = rt.SolidMaterial(rt.ResponseType.REFLECTION, False, False, 0)
+    tex = rt.SolidTexture(rt.Color(1, 1, 1, 1))
+    with pytest.raises(rt.TreeOutsideGrowError):
+        flat_from_arrays([0], [[0.99, 0.5, 0.5]], [0.1], [0], [0], [0], [mat], [tex], [rt.SUBSTANCE_AIR])

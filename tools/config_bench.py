@@ -1,0 +1,107 @@
+"""Times the non-headline BASELINE configs (parity-test cases, not bench lines) on one GPU and prints one
+JSON line each.  usage: python tools/config_bench.py c2 [c3 c4 ...] [--spp N] [--steps K]
+
+  c2: 1920x1080, 16 spp, 100 k spheres d in [0.002,0.006], 70% mirrors / 15% diffuse / 10% rough / 5% lights, refmax 4
+  c3: 3840x2160, 4 spp, 1 M entities (10% boxes) d in [0.0005,0.002], 4 image textures 1024x512, refmax 4
+  c4: 7680x4320, 64 spp, 1 M spheres d in [0.0005,0.002], config-2 material mix, refmax 4
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import raytracer_js_b200 as rt
+from raytracer_js_b200 import _native as N
+from raytracer_js_b200 import scenes
+
+CONFIGS = {
+    "c2": dict(w=1920, h=1080, spp=16, n=100000, dmin=0.002, dmax=0.006, mix="mirrors", box=0.0, tex=False),
+    "c3": dict(w=3840, h=2160, spp=4, n=1000000, dmin=0.0005, dmax=0.002, mix="mirrors", box=0.1, tex=True),
+    "c4": dict(w=7680, h=4320, spp=64, n=1000000, dmin=0.0005, dmax=0.002, mix="mirrors", box=0.0, tex=False),
+}
+
+
+def build(cfg):
+    t0 = time.perf_counter()
+    if cfg["tex"]:
+        # textured entities share 4 image textures; the draws per entity vary, so the generator is sequential:
+        # build the geometry in bulk and pick textures with a second stream of draws
+        texs = [scenes.checker_texture(1024, 512, seed=s) for s in (1, 2, 3, 4)]
+        fb = scenes.random_spheres_flat(cfg["n"], cfg["dmin"], cfg["dmax"], 42.0, cfg["mix"], cfg["box"])
+        a = fb.flat.arrays
+        base = len(fb.flat.textures)
+        for t in texs:
+            fb.flat.texture_index(t)
+        pick = (scenes.fplcg_draws(43.0, cfg["n"]) * 4).astype(np.int32)
+        light = a["mat_light"][a["ent_material"]].astype(bool)
+        textured = (~light) & (a["ent_type"] == 0)
+        a["ent_texture"] = np.where(textured, base + pick, a["ent_texture"]).astype(np.int32)
+        fb.flat.finalize_tables()
+    else:
+        fb = scenes.random_spheres_flat(cfg["n"], cfg["dmin"], cfg["dmax"], 42.0, cfg["mix"], cfg["box"])
+    return fb, time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="+")
+    ap.add_argument("--spp", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--per-ray", action="store_true")
+    args = ap.parse_args()
+    lib = N.load()
+    ctx = C.c_void_p()
+    N.check(None, lib.rt_create(0, C.byref(ctx)))
+    for name in args.configs:
+        cfg = dict(CONFIGS[name])
+        if args.spp:
+            cfg["spp"] = args.spp
+        fb, t_build = build(cfg)
+        d = fb.flat.desc()
+        t0 = time.perf_counter()
+        N.check(ctx, lib.rt_scene_upload(ctx, C.byref(d)))
+        t_upload = time.perf_counter() - t0
+        W, H = cfg["w"], cfg["h"]
+        cd = rt.camera_desc(scenes.bench_camera(W, H))
+        prm = N.Params()
+        prm.refmax, prm.sky_texture, prm.default_substance = fb.refmax, fb.sky_texture, fb.default_substance
+        prm.distance_attenuation_factor, prm.n_frames, prm.frame_first, prm.rng_seed = 1.0, 1, 0, 1.0
+        prm.flags = 2 if args.per_ray else 0
+        frame = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda")
+        # work counters of one frame (counting variant, 1 spp): segments per path
+        N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), N.RT_RENDER_COUNTERS, C.c_void_p(frame.data_ptr()), None))
+        cnt = N.Counters()
+        N.check(ctx, lib.rt_get_counters(ctx, C.byref(cnt)))
+        c1 = cnt.as_dict()
+        prm.n_frames = cfg["spp"]
+        ms = []
+        for i in range(args.steps + 1):
+            el = C.c_float()
+            N.check(ctx, lib.rt_flush_l2(ctx))
+            N.check(ctx, lib.rt_timer_start(ctx))
+            N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), 0, C.c_void_p(frame.data_ptr()), None))
+            N.check(ctx, lib.rt_timer_stop(ctx, C.byref(el)))
+            if i:
+                ms.append(el.value)
+        ms.sort()
+        med = ms[len(ms) // 2]
+        seg_per_path = c1["segments"] / c1["paths"]
+        paths = W * H * cfg["spp"]
+        algo = 64 * c1["nodes"] + 16 * c1["tests"] + 16 * c1["shades"] + 12 * c1["paths"]
+        print(json.dumps({"config": name, "frame": f"{W}x{H}x{cfg['spp']}spp", "entities": cfg["n"], "nodes": int(d.n_nodes),
+                          "frame_ms": med, "Mpaths_per_s": paths / med / 1e3, "Mrays_per_s": paths * seg_per_path / med / 1e3,
+                          "segments_per_path": seg_per_path, "nodes_per_segment": c1["nodes"] / c1["segments"],
+                          "tests_per_segment": c1["tests"] / c1["segments"], "algorithmic_bytes_per_segment": algo / c1["segments"],
+                          "algorithmic_GBps": algo / c1["paths"] * paths / med / 1e6, "path": "per-ray" if args.per_ray else "pipeline",
+                          "scene_build_s": t_build, "scene_upload_s": t_upload, "finite": bool(torch.isfinite(frame).all())}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
