@@ -268,6 +268,9 @@ struct rt_ctx {
 	DevBuf<RtI4> node_link;
 	DevBuf<int> node_child;
 	DevBuf<RtPNode> node_pk;
+	DevBuf<int> node_bvh;
+	DevBuf<RtBvhNode> bvh_nodes;
+	DevBuf<int> bvh_slots;
 	DevBuf<RtF4> slot_geom;
 	DevBuf<RtD4> slot_geom64;
 	DevBuf<RtI4> slot_attr;
@@ -606,7 +609,7 @@ void rt_destroy(rt_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release();
+	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release();
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
@@ -686,14 +689,15 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	const RtHostScene& H = ctx->host;
 	rt_status st;
 	if ((st = upload(ctx, ctx->node_geom, H.node_geom)) || (st = upload(ctx, ctx->node_link, H.node_link)) ||
-	    (st = upload(ctx, ctx->node_child, H.node_child)) || (st = upload(ctx, ctx->node_pk, H.node_pk)) || (st = upload(ctx, ctx->slot_geom, H.slot_geom)) ||
+	    (st = upload(ctx, ctx->node_child, H.node_child)) || (st = upload(ctx, ctx->node_pk, H.node_pk)) || (st = upload(ctx, ctx->node_bvh, H.node_bvh)) ||
+	    (st = upload(ctx, ctx->bvh_nodes, H.bvh_nodes)) || (st = upload(ctx, ctx->bvh_slots, H.bvh_slots)) || (st = upload(ctx, ctx->slot_geom, H.slot_geom)) ||
 	    (st = upload(ctx, ctx->slot_geom64, H.slot_geom64)) || (st = upload(ctx, ctx->slot_attr, H.slot_attr)) ||
 	    (st = upload(ctx, ctx->materials, H.materials)) || (st = upload(ctx, ctx->textures, H.textures)) ||
 	    (st = upload(ctx, ctx->substances, H.substances)) || (st = upload(ctx, ctx->texels, H.texels)))
 		return st;
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	RtDevScene& D = ctx->dev;
-	D.node_geom = ctx->node_geom.p; D.node_link = ctx->node_link.p; D.node_child = ctx->node_child.p; D.node_pk = ctx->node_pk.p;
+	D.node_geom = ctx->node_geom.p; D.node_link = ctx->node_link.p; D.node_child = ctx->node_child.p; D.node_pk = ctx->node_pk.p; D.node_bvh = ctx->node_bvh.p; D.bvh_nodes = ctx->bvh_nodes.p; D.bvh_slots = ctx->bvh_slots.p;
 	D.slot_geom = ctx->slot_geom.p; D.slot_geom64 = ctx->slot_geom64.p; D.slot_attr = ctx->slot_attr.p;
 	D.materials = ctx->materials.p; D.textures = ctx->textures.p; D.substances = ctx->substances.p;
 	D.texels = ctx->texels.p;

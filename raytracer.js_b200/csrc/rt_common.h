@@ -35,6 +35,20 @@ struct alignas(32) RtPNode {
 	int child_base, child_mask;
 };
 
+// Per-list bounding volume hierarchy.  The reference scans a node's entity list linearly and takes the FIRST
+// entity (in insertion order) the ray hits; any structure that finds every hit entity of the list and keeps
+// the lowest slot gives the same answer.  Lists of RT_BVH_MIN_LIST or more entries (the big straddler lists
+// near the root) get a binary BVH over the entities' float32 boxes (inflated by err_l): a ray then tests a
+// few dozen boxes instead of hundreds or thousands of entities.
+struct alignas(16) RtBvhNode {
+	float lo[3], hi[3];
+	int a;  // inner: index of the left child (right = a + 1); leaf: first entry in bvh_slots
+	int b;  // inner: 0; leaf: number of entries (> 0), ascending slot numbers
+};
+#define RT_BVH_MIN_LIST 24
+#define RT_BVH_LEAF 4
+#define RT_BVH_STACK 40
+
 // material flags
 #define RT_MAT_RESPONSE_MASK 3u
 #define RT_MAT_LIGHT 4u
@@ -64,6 +78,9 @@ struct RtDevScene {
 	const RtI4* node_link;   // parent, index_within_parent, list_off, list_cnt
 	const int* node_child;   // [n*8], -1 none
 	const RtPNode* node_pk;  // the same nodes as one 32-byte record each, for the packet walk
+	const int* node_bvh;     // [n] root of the node's list BVH in bvh_nodes, or -1 (short list)
+	const RtBvhNode* bvh_nodes;
+	const int* bvh_slots;    // leaf entries
 	// entity lists, slot order
 	const RtF4* slot_geom;   // centre.xyz, w = radius (>0, sphere) | -half_size (<0, box)
 	const RtD4* slot_geom64; // centre.xyz, w = diameter | size  (the reference's float64 values)

@@ -18,6 +18,9 @@ struct RtHostScene {
 	std::vector<RtI4> node_link;
 	std::vector<int> node_child;
 	std::vector<RtPNode> node_pk;
+	std::vector<int> node_bvh;
+	std::vector<RtBvhNode> bvh_nodes;
+	std::vector<int> bvh_slots;
 	std::vector<RtF4> slot_geom;
 	std::vector<RtD4> slot_geom64;
 	std::vector<RtI4> slot_attr;
@@ -39,6 +42,87 @@ inline std::string rt_format(const char* fmt, ...) {
 	vsnprintf(buf, sizeof buf, fmt, ap);
 	va_end(ap);
 	return buf;
+}
+
+// Binary BVHs over the long entity lists (rt_common.h: RtBvhNode).  Median split of the centres along the
+// widest axis; boxes are the entities' float64 boxes inflated by err_l and rounded outwards to float32.
+inline void rt_build_list_bvhs(RtHostScene& hs) {
+	const size_t N = hs.node_link.size();
+	hs.node_bvh.assign(N, -1);
+	hs.bvh_nodes.clear();
+	hs.bvh_slots.clear();
+	struct Box { float lo[3], hi[3]; };
+	const double infl = (double)hs.err_l;
+	auto box_of = [&](int s) {
+		const RtD4& g = hs.slot_geom64[s];
+		const double h = (hs.slot_geom[s].w > 0.0f ? g.w * 0.5 : g.w / 2) + infl;
+		const double c[3] = {g.x, g.y, g.z};
+		Box b;
+		for (int k = 0; k < 3; k++) {
+			b.lo[k] = std::nextafter((float)(c[k] - h), -INFINITY);
+			b.hi[k] = std::nextafter((float)(c[k] + h), INFINITY);
+		}
+		return b;
+	};
+	std::vector<int> idx;
+	struct Job { int node, beg, end; };
+	std::vector<Job> jobs;
+	for (size_t n = 0; n < N; n++) {
+		const int off = hs.node_link[n].z, cnt = hs.node_link[n].w;
+		if (cnt < RT_BVH_MIN_LIST) continue;
+		idx.resize(cnt);
+		for (int i = 0; i < cnt; i++) idx[i] = off + i;
+		hs.node_bvh[n] = (int)hs.bvh_nodes.size();
+		hs.bvh_nodes.push_back(RtBvhNode{});
+		jobs.clear();
+		jobs.push_back(Job{hs.node_bvh[n], 0, cnt});
+		while (!jobs.empty()) {
+			const Job j = jobs.back();
+			jobs.pop_back();
+			Box bb;
+			double cmin[3] = {1e300, 1e300, 1e300}, cmax[3] = {-1e300, -1e300, -1e300};
+			for (int k = 0; k < 3; k++) { bb.lo[k] = INFINITY; bb.hi[k] = -INFINITY; }
+			for (int i = j.beg; i < j.end; i++) {
+				const Box b = box_of(idx[i]);
+				const RtD4& g = hs.slot_geom64[idx[i]];
+				const double c[3] = {g.x, g.y, g.z};
+				for (int k = 0; k < 3; k++) {
+					bb.lo[k] = std::min(bb.lo[k], b.lo[k]);
+					bb.hi[k] = std::max(bb.hi[k], b.hi[k]);
+					cmin[k] = std::min(cmin[k], c[k]);
+					cmax[k] = std::max(cmax[k], c[k]);
+				}
+			}
+			RtBvhNode nd;
+			for (int k = 0; k < 3; k++) { nd.lo[k] = bb.lo[k]; nd.hi[k] = bb.hi[k]; }
+			const int count = j.end - j.beg;
+			int axis = 0;
+			for (int k = 1; k < 3; k++)
+				if (cmax[k] - cmin[k] > cmax[axis] - cmin[axis]) axis = k;
+			if (count <= RT_BVH_LEAF || !(cmax[axis] > cmin[axis])) {
+				std::sort(idx.begin() + j.beg, idx.begin() + j.end);  // ascending slots: list order within the leaf
+				nd.a = (int)hs.bvh_slots.size();
+				nd.b = count;
+				hs.bvh_slots.insert(hs.bvh_slots.end(), idx.begin() + j.beg, idx.begin() + j.end);
+			} else {
+				const int mid = j.beg + count / 2;
+				std::nth_element(idx.begin() + j.beg, idx.begin() + mid, idx.begin() + j.end, [&](int p, int q) {
+					const double a = axis == 0 ? hs.slot_geom64[p].x : axis == 1 ? hs.slot_geom64[p].y : hs.slot_geom64[p].z;
+					const double b = axis == 0 ? hs.slot_geom64[q].x : axis == 1 ? hs.slot_geom64[q].y : hs.slot_geom64[q].z;
+					return a < b || (a == b && p < q);
+				});
+				nd.a = (int)hs.bvh_nodes.size();
+				nd.b = 0;
+				hs.bvh_nodes.push_back(RtBvhNode{});
+				hs.bvh_nodes.push_back(RtBvhNode{});
+				jobs.push_back(Job{nd.a, j.beg, mid});
+				jobs.push_back(Job{nd.a + 1, mid, j.end});
+			}
+			hs.bvh_nodes[j.node] = nd;
+		}
+	}
+	if (hs.bvh_nodes.empty()) hs.bvh_nodes.push_back(RtBvhNode{});
+	if (hs.bvh_slots.empty()) hs.bvh_slots.push_back(0);
 }
 
 // Validates `sc` and fills `hs`.  On failure returns the status and a message in `err`.
@@ -169,6 +253,8 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 			for (int k = 0; k < 3; k++) scale = std::max(scale, std::fabs(p[k]) + ext);
 		}
 	}
+	hs.err_l = (float)(16.0 * 1.1920929e-7 * scale);
+	rt_build_list_bvhs(hs);
 	hs.materials.resize(sc->n_materials);
 	hs.any_transmission = false;
 	for (uint32_t i = 0; i < sc->n_materials; i++) {

@@ -15,6 +15,7 @@
 // Reference citations are relative to /root/reference.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #include "rt_common.h"
 
@@ -77,6 +78,16 @@ RT_HD int ld(const int* p) {
 	return __ldg(p);
 #else
 	return *p;
+#endif
+}
+
+RT_HD float int_as_float(int v) {
+#if defined(__CUDACC__)
+	return __int_as_float(v);
+#else
+	float f;
+	memcpy(&f, &v, sizeof f);
+	return f;
 #endif
 }
 
@@ -328,18 +339,78 @@ RT_HD bool slot_candidate(const RtDevScene& S, const RtSearch& q, int s) {
 	return candidate(ld(S.slot_geom + s), q.r, S.err_l);
 }
 
-// Scans slots [beg,end) in insertion order; returns the slot of the first entity whose float64
-// collision_info is non-null (src/raytracer.ts:186-195), or -1.
+// float64 confirmation of slot s: Entity.collision_info(ray) != null, collision in `col`
+RT_HD bool confirm_slot(const RtDevScene& S, int s, const double* o, const double* d, RtCollision& col) {
+	const RtD4 g = ld(S.slot_geom64 + s);
+	return ld(S.slot_geom + s).w > 0.0f ? exact_sphere(g, o, d, col) : exact_box(g, o, d, col);
+}
+
+// Long lists: every entity of the list the ray hits is found through the list's BVH and the lowest slot
+// (= first in insertion order) wins, which is what the reference's linear scan with `break` returns.
+RT_HD int scan_list_bvh(const RtDevScene& S, const RtSearch& q, int root, const double* o, const double* d,
+                        RtCollision& col) {
+	const RtRayF& r = q.r;
+	int stack[RT_BVH_STACK];
+	int sp = 0, best = 0x7fffffff;
+	stack[sp++] = root;
+	const float slack = S.err_l * fmaxf(fabsf(r.ix), fmaxf(fabsf(r.iy), fabsf(r.iz)));
+	while (sp > 0) {
+		const RtBvhNode* np = S.bvh_nodes + stack[--sp];
+		const RtF4 n0 = ld(reinterpret_cast<const RtF4*>(np));
+		const RtI4 n1 = ld(reinterpret_cast<const RtI4*>(np) + 1);
+		// n0 = lo.xyz, hi.x ; n1 = hi.y, hi.z (as bits), a, b
+		const float hy = int_as_float(n1.x), hz = int_as_float(n1.y);
+		float t0 = (n0.x - r.ox) * r.ix, t1 = (n0.w - r.ox) * r.ix;
+		float tmin = fminf(t0, t1), tmax = fmaxf(t0, t1);
+		t0 = (n0.y - r.oy) * r.iy; t1 = (hy - r.oy) * r.iy;
+		tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1));
+		t0 = (n0.z - r.oz) * r.iz; t1 = (hz - r.oz) * r.iz;
+		tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1));
+		if (tmin > tmax + slack || tmax < -slack) continue;  // (NaN from 0 * inf compares false: kept)
+		if (n1.w == 0) {
+			if (sp + 2 <= RT_BVH_STACK) {
+				stack[sp++] = n1.z;
+				stack[sp++] = n1.z + 1;
+			}
+			continue;
+		}
+		for (int k = 0; k < n1.w; k++) {
+			const int s = ld(S.bvh_slots + n1.z + k);
+			if (s >= best) break;  // ascending within the leaf
+			if (slot_candidate(S, q, s)) {
+				RtCollision c;
+				if (confirm_slot(S, s, o, d, c)) {
+					best = s;
+					col = c;
+					break;
+				}
+			}
+		}
+	}
+	return best == 0x7fffffff ? -1 : best;
+}
+
+// Scans the list of `node`, slots [beg,end) in insertion order; returns the slot of the first entity whose
+// float64 collision_info is non-null (src/raytracer.ts:186-195), or -1.
 template <bool COUNT>
-RT_HD int scan_list(const RtDevScene& S, const RtSearch& q, int beg, int end, const double* o, const double* d,
+RT_HD int scan_list(const RtDevScene& S, const RtSearch& q, int node, int beg, int end, const double* o, const double* d,
                     RtCollision& col, RtCounts& cnt) {
+	const int bvh = ld(S.node_bvh + node);
+	if (bvh >= 0) {
+		const int s = scan_list_bvh(S, q, bvh, o, d, col);
+		// the counters count the reference's linear scan: up to and including the hit, or the whole list
+		if (COUNT) {
+			cnt.tests += (unsigned)(s >= 0 ? s - beg + 1 : end - beg);
+			cnt.confirms++;
+		}
+		return s;
+	}
 	int s = beg;
 	while (true) {
 		for (; s < end; ++s)
 			if (slot_candidate(S, q, s)) break;
 		if (s >= end) break;
-		const RtD4 g = ld(S.slot_geom64 + s);
-		const bool hit = ld(S.slot_geom + s).w > 0.0f ? exact_sphere(g, o, d, col) : exact_box(g, o, d, col);
+		const bool hit = confirm_slot(S, s, o, d, col);
 		if (COUNT) cnt.confirms++;
 		if (hit) {
 			if (COUNT) cnt.tests += (unsigned)(s - beg + 1);
@@ -375,7 +446,7 @@ RT_HD int walk_and_scan(const RtDevScene& S, const RtSearch& q, int node, int oc
 	RtF4 g = ld(S.node_geom + node);
 	bool done = false;
 	while (true) {
-		int scan_beg = 0, scan_end = 0;
+		int scan_beg = 0, scan_end = 0, scan_node = 0;
 		// ---- phase 1: advance the walker to the next node with a list to scan
 		while (true) {
 			const int child = octant >= 0 ? ld(S.node_child + node * 8 + octant) : node;
@@ -393,6 +464,7 @@ RT_HD int walk_and_scan(const RtDevScene& S, const RtSearch& q, int node, int oc
 					chain_level++;
 				}
 				if (!skip) {
+					scan_node = child;
 					scan_beg = link.z;
 					scan_end = link.z + link.w;
 					break;
@@ -453,7 +525,7 @@ RT_HD int walk_and_scan(const RtDevScene& S, const RtSearch& q, int node, int oc
 		}
 		if (done) break;
 		// ---- phase 2: scan the list
-		const int s = scan_list<COUNT>(S, q, scan_beg, scan_end, o, d, col, cnt);
+		const int s = scan_list<COUNT>(S, q, scan_node, scan_beg, scan_end, o, d, col, cnt);
 		if (s >= 0) return s;
 	}
 	return -1;
@@ -967,8 +1039,10 @@ RT_HD double rng_next(RtRng& g) {
 // the reference passes it).  Returns the path colour in `out`, and the entity of the first collision.
 // `primary_slot`: the first-hit slot of the camera segment when the primary stage already found it
 // (>= 0), or RT_SLOT_UNKNOWN to search here.
+// Returns true when the path drew from the RNG (a rough surface scattered it): only such paths can differ
+// from one exposure frame to the next (there is no pixel jitter).
 template <bool COUNT>
-RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_in, double pixel_seed, int primary_slot,
+RT_HD bool trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_in, double pixel_seed, int primary_slot,
                       double* out, int& first_entity, RtCounts& cnt, uint32_t& err) {
 	double refpoint[3] = {F.pos[0], F.pos[1], F.pos[2]};
 	double dir[3] = {dir_in[0], dir_in[1], dir_in[2]};
@@ -1028,7 +1102,7 @@ RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_i
 		if (dot3(dir, ci.normal) >= 0) {  // :200-203
 			err |= RT_ERRFLAG_ACUTE;
 			out[0] = col[0]; out[1] = col[1]; out[2] = col[2];
-			return;
+			return rng.seeded;
 		}
 		const bool is_sphere = (attr.y >> RT_ATTR_TYPE_SHIFT) == 0;
 		const RtMaterial m = S.materials[attr.y & RT_ATTR_MAT_MASK];
@@ -1055,7 +1129,7 @@ RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_i
 		if (response == 0u) {  // REFLECTION :221-237
 			if (!(m.flags & RT_MAT_MIRROR)) {
 				out[0] = col[0]; out[1] = col[1]; out[2] = col[2];
-				return;
+				return rng.seeded;
 			}
 			{  // vector.reflection (src/math/vector.ts:263-268)
 				const double k = xmul(-dot3(dir, ci.normal), 2.0);
@@ -1111,11 +1185,11 @@ RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_i
 			}
 		} else {  // BOTH / default :250-251
 			out[0] = col[0]; out[1] = col[1]; out[2] = col[2];
-			return;
+			return rng.seeded;
 		}
 		if (refcount >= F.refmax) {  // :256-263
 			out[0] = out[1] = out[2] = 0.0;
-			return;
+			return rng.seeded;
 		}
 		have_node = node_at_pos(S, refpoint, node, octant);  // :254 (re-seed from the root)
 	}
@@ -1123,12 +1197,13 @@ RT_HD void trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_i
 		double sc[3];
 		if (!texture_color(S, F.sky_texture, true, dir, sc)) err |= RT_ERRFLAG_TEXTURE;
 		out[0] = xmul(col[0], sc[0]); out[1] = xmul(col[1], sc[1]); out[2] = xmul(col[2], sc[2]);
-		return;
+		return rng.seeded;
 	}
 	// inverse square law :273-275
 	const double t = xmul(path_distance, F.attenuation);
 	const double isl = xdiv(1.0, xadd(RT_JS_EPSILON, xmul(t, t)));
 	out[0] = xmul(col[0], isl); out[1] = xmul(col[1], isl); out[2] = xmul(col[2], isl);
+	return rng.seeded;
 }
 
 // ------------------------------------------------------------------ one pixel, all exposure frames
@@ -1148,12 +1223,27 @@ RT_HD void render_pixel(const RtDevScene& S, const RtFrame& F, int x, int y, siz
 	float px[3] = {0.f, 0.f, 0.f};
 	if (F.frame_first > 0) { px[0] = o[0]; px[1] = o[1]; px[2] = o[2]; }
 	int first_entity = -1;
+	double c[3];
+	bool varies = true;  // until proven otherwise by the first frame
+	RtCounts per_frame = {0, 0, 0, 0, 0};
 	for (uint32_t f = 0; f < F.n_frames; f++) {
 		const uint32_t frame_count = F.frame_first + f;
-		const double seed = xadd(xadd(F.rng_seed, (double)pix),
-		                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
-		double c[3];
-		trace_path<COUNT>(S, F, dir, seed, primary_slot, c, first_entity, cnt, err);
+		if (varies) {
+			const double seed = xadd(xadd(F.rng_seed, (double)pix),
+			                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
+			const RtCounts before = cnt;
+			varies = trace_path<COUNT>(S, F, dir, seed, primary_slot, c, first_entity, cnt, err);
+			if (COUNT && !varies) {
+				per_frame.segments = cnt.segments - before.segments; per_frame.nodes = cnt.nodes - before.nodes;
+				per_frame.tests = cnt.tests - before.tests; per_frame.shades = cnt.shades - before.shades;
+				per_frame.confirms = cnt.confirms - before.confirms;
+			}
+		} else if (COUNT) {
+			// a path that never drew from the RNG is the same path in every frame: the sample is reused, and
+			// the counters keep counting what the reference would trace again
+			cnt.segments += per_frame.segments; cnt.nodes += per_frame.nodes; cnt.tests += per_frame.tests;
+			cnt.shades += per_frame.shades; cnt.confirms += per_frame.confirms;
+		}
 		const double w = xdiv(1.0, (double)(1u + frame_count));
 		const double w1 = xsub(1.0, w);
 #pragma unroll
