@@ -146,31 +146,105 @@ __global__ void __launch_bounds__(256)
 	if (err) atomicOr(F.error_flags, err);
 }
 
-// Bounce stage.  Persistent warps drain the continuation queue 32 items at a time, one path per thread:
-// the queue is a compaction of the pixels that still have work, so every warp starts full.
+// Bounce stage: persistent wavefront with a per-warp ray queue.  Every lane owns one pixel job (all its
+// exposure frames) and advances it ONE ray segment per iteration (path_segment); between segments the warp
+// votes on which lanes have finished their pixel and refills exactly those lanes from the continuation
+// queue (one atomic per refill, ranks by popc of the vote), so a path that bounces four times does not hold
+// 31 finished lanes hostage.  Frames whose path never drew from the RNG reuse the first frame's sample.
 __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
     rt_bounce_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
 	const int lane = threadIdx.x & 31;
+	const unsigned lt_mask = (1u << lane) - 1u;
 	const unsigned n = *F.queue_count;
 	RtCounts cnt = {0, 0, 0, 0, 0};
 	uint32_t err = 0;
+	// the lane's pixel job
+	bool active = false;
+	int x = 0, y = 0, slot = RT_SLOT_UNKNOWN;
+	size_t out_index = 0;
+	uint32_t frame = 0;
+	float px[3] = {0.f, 0.f, 0.f};
+	RtPath P;
+	RtWalk W;
+	bool exhausted = n == 0;
 	while (true) {
-		unsigned base = 0;
-		if (lane == 0) base = atomicAdd(F.queue_taken, 32u);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= n) break;
-		const unsigned i = base + lane;
-		if (i < n) {
-			const RtQueueItem it = F.queue[i];
-			const int x = (int)(it.xy & 0xffffu), y = (int)(it.xy >> 16);
-			size_t out_index = (size_t)y * F.width + x;
-			if (F.tile_compact) {
-				const int tile = (y / RT_TILE_H) * tiles_x + (x / RT_TILE_W);
-				out_index = (size_t)(tile / F.tile_world) * RT_BLOCK + ((y & (RT_TILE_H - 1)) * RT_TILE_W + (x & (RT_TILE_W - 1)));
+		// ---- refill the idle lanes
+		const unsigned idle = __ballot_sync(0xffffffffu, !active);
+		if (idle && !exhausted) {
+			const unsigned want = (unsigned)__popc(idle);
+			unsigned base = 0;
+			if (lane == 0) base = atomicAdd(F.queue_taken, want);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			exhausted = base + want >= n;
+			const unsigned i = base + (unsigned)__popc(idle & lt_mask);
+			if (!active && i < n) {
+				const RtQueueItem it = F.queue[i];
+				x = (int)(it.xy & 0xffffu);
+				y = (int)(it.xy >> 16);
+				slot = it.slot;
+				out_index = (size_t)y * F.width + x;
+				if (F.tile_compact) {
+					const int tile = (y / RT_TILE_H) * tiles_x + (x / RT_TILE_W);
+					out_index = (size_t)(tile / F.tile_world) * RT_BLOCK + ((y & (RT_TILE_H - 1)) * RT_TILE_W + (x & (RT_TILE_W - 1)));
+				}
+				frame = 0;
+				px[0] = px[1] = px[2] = 0.f;
+				if (F.frame_first > 0) {
+					const float* o = F.rgb + out_index * 3;
+					px[0] = o[0]; px[1] = o[1]; px[2] = o[2];
+				}
+				double dir[3];
+				pixel_dir(F, x, y, dir);
+				path_begin(F, dir, P);
+				active = true;
 			}
-			render_pixel<false>(S, F, x, y, out_index, cnt, err, it.slot);
 		}
-		__syncwarp();
+		if (__ballot_sync(0xffffffffu, active) == 0u) break;
+		// ---- one segment for every active lane: (1) re-seed, (2) the ordered walk in lock-step - every lane
+		// that is still searching handles ONE octree node per iteration, and the vote at the top keeps the 32
+		// independent rays converged -, (3) the material's response
+		const uint32_t frame_count = F.frame_first + frame;
+		const double seed = xadd(xadd(F.rng_seed, (double)((size_t)y * F.width + x)),
+		                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
+		double c[3];
+		int hit = -1;
+		RtCollision ci;
+		int state = RT_SEG_DONE;
+		bool finished = false;
+		if (active) {
+			state = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
+			finished = state == RT_SEG_DONE;
+		}
+		bool walking = active && state == RT_SEG_WALK;
+		while (__any_sync(0xffffffffu, walking)) {
+			if (walking) walking = walk_step(S, W, P.refpoint, P.dir);
+		}
+		if (active && !finished) {
+			if (state == RT_SEG_WALK) segment_found(S, P, W, hit, ci);
+			finished = segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err);
+		}
+		if (active && finished) {
+			// ExposureBuffer.set_color_i (src/view/exposure_buffer.ts:77-91) for this frame, and for all
+			// remaining ones when the path cannot change (it never drew from the RNG)
+			const bool varies = P.rng.seeded;
+			const uint32_t last = varies ? frame + 1 : F.n_frames;
+			for (; frame < last; frame++) {
+				const double w = xdiv(1.0, (double)(1u + F.frame_first + frame));
+				const double w1 = xsub(1.0, w);
+#pragma unroll
+				for (int k = 0; k < 3; k++) px[k] = (float)xadd(xmul(c[k], w), xmul((double)px[k], w1));
+			}
+			if (frame < F.n_frames) {
+				double dir[3];
+				pixel_dir(F, x, y, dir);
+				path_begin(F, dir, P);
+			} else {
+				float* o = F.rgb + out_index * 3;
+				o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
+				if (F.first_ids) F.first_ids[out_index] = P.first_entity;
+				active = false;
+			}
+		}
 	}
 	if (err) atomicOr(F.error_flags, err);
 }
@@ -706,6 +780,7 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	D.n_nodes = (int)H.node_geom.size();
 	D.n_slots = (int)H.slot_geom.size();
 	D.err_l = H.err_l;
+	D.ordered_ok = 7 * H.max_depth + 8 <= RT_WALK_STACK ? 1 : 0;
 	ctx->has_scene = true;
 	return RT_OK;
 }

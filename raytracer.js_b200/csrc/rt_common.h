@@ -93,6 +93,7 @@ struct RtDevScene {
 	double root_pos[3];
 	double root_size;
 	int n_nodes, n_slots;
+	int ordered_ok;          // 1: the tree depth fits RT_WALK_STACK, rays may use the ordered walk
 	float err_l;             // bound on the float error of a point-to-line distance in this scene
 	float _pad;
 };
@@ -107,6 +108,7 @@ struct alignas(8) RtQueueItem {
 };
 #define RT_SLOT_UNKNOWN (-2)
 #define RT_PACKET_STACK 192  // node stack of the packet walk: 7 siblings per level + 8
+#define RT_WALK_STACK 128    // node stack of the per-ray ordered walk (bounce stage), same bound
 
 struct RtFrame {
 	// camera

@@ -1034,176 +1034,347 @@ RT_HD double rng_next(RtRng& g) {
 	return frac1(xadd(xadd(a, b), c));
 }
 
+// ------------------------------------------------------------------ the ordered walk (single ray, bounce stage)
+// The same order argument as the packet walk, for ONE ray: with the direction signs fixed, the reference
+// visits the children a ray pierces in ascending (octant ^ neg), subtrees in pre-order, and the nodes that
+// contain the ray origin in post-order.  Unlike the state machine of walk_and_scan (which follows the
+// reference's walker step by step and is kept for the counting kernel), this formulation does the same work
+// for every node - pop, scan the list, push the pierced children - so the 32 independent rays of a warp in
+// the bounce stage run it in lock-step, one node per iteration (walk_step), instead of serialising on the
+// branches of 32 different walker states.  A conservative (slack) pierce test can only add nodes, which cannot
+// change a first hit (entities lie inside their node's cube).
+struct RtWalk {
+	RtSearch q;
+	int neg;         // bit k: d_k < 0
+	int sp;
+	int chain_node;  // origin-chain node to be returned once the stack is empty; < 0: walk over
+	int chain_oct;   // octant of chain_node the ray leaves (its children before it cannot be reached)
+	int hit;         // first-hit slot, -1 while none
+	float slack;
+	int stack[RT_WALK_STACK];
+};
+
+// pushes the children of `nd` the ray may pierce, last-visited first
+RT_HD void walk_push_children(RtWalk& W, const RtPNode& nd, int after_oct) {
+	if (!nd.child_mask) return;
+	const RtRayF& r = W.q.r;
+	const float h = nd.size * 0.5f;
+	// per axis: parameter intervals of the lower and the upper half of the cube
+	float nr[3][2], fr[3][2];
+	{
+		const float lo[3] = {nd.x, nd.y, nd.z}, o[3] = {r.ox, r.oy, r.oz}, inv[3] = {r.ix, r.iy, r.iz};
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			const float ta = (lo[k] - o[k]) * inv[k], tm = (lo[k] + h - o[k]) * inv[k], tb = (lo[k] + nd.size - o[k]) * inv[k];
+			nr[k][0] = fminf(ta, tm); fr[k][0] = fmaxf(ta, tm);
+			nr[k][1] = fminf(tm, tb); fr[k][1] = fmaxf(tm, tb);
+		}
+	}
+	const int want = after_oct >= 0 ? (after_oct ^ W.neg) : 0;
+#pragma unroll
+	for (int key = 7; key >= 0; key--) {
+		const int o = key ^ W.neg;
+		if (!((nd.child_mask >> o) & 1) || (key & want) != want || o == after_oct) continue;
+		const float tnear = fmaxf(fmaxf(nr[0][o & 1], nr[1][(o >> 1) & 1]), fmaxf(nr[2][(o >> 2) & 1], 0.0f));
+		const float tfar = fminf(fminf(fr[0][o & 1], fr[1][(o >> 1) & 1]), fr[2][(o >> 2) & 1]);
+		if (tnear <= tfar * 1.00001f + W.slack && W.sp < RT_WALK_STACK)
+			W.stack[W.sp++] = nd.child_base + popc32((unsigned)nd.child_mask & ((1u << o) - 1u));
+	}
+}
+
+// (node, octant): node_at_pos of the ray origin, or octant < 0 for "origin outside the root: root only"
+RT_HD void walk_begin(const RtDevScene& S, RtWalk& W, int node, int octant) {
+	const RtRayF& r = W.q.r;
+	W.neg = (r.dx < 0.0f ? 1 : 0) | (r.dy < 0.0f ? 2 : 0) | (r.dz < 0.0f ? 4 : 0);
+	W.sp = 0;
+	W.hit = -1;
+	W.slack = S.err_l * fminf(fmaxf(fabsf(r.ix), fmaxf(fabsf(r.iy), fabsf(r.iz))), 1e7f);
+	W.chain_node = node;
+	W.chain_oct = octant;
+	if (octant >= 0) walk_push_children(W, ld(S.node_pk + node), octant);
+}
+
+// One node of the walk.  Returns false when the walk is over (W.hit = slot or -1).
+RT_HD bool walk_step(const RtDevScene& S, RtWalk& W, const double* o, const double* d) {
+	RtCollision col;
+	RtCounts none = {0, 0, 0, 0, 0};
+	if (W.sp > 0) {
+		const int n = W.stack[--W.sp];
+		const RtPNode nd = ld(S.node_pk + n);
+		if (nd.list_cnt > 0) {
+			const int s = scan_list<false>(S, W.q, n, nd.list_off, nd.list_off + nd.list_cnt, o, d, col, none);
+			if (s >= 0) {
+				W.hit = s;
+				return false;
+			}
+		}
+		walk_push_children(W, nd, -1);
+		return true;
+	}
+	// stack empty: the ray leaves the current origin-chain node, which is returned now (post-order)
+	const int A = W.chain_node;
+	const RtI4 link = ld(S.node_link + A);
+	if (link.w > 0) {
+		const int s = scan_list<false>(S, W.q, A, link.z, link.z + link.w, o, d, col, none);
+		if (s >= 0) {
+			W.hit = s;
+			return false;
+		}
+	}
+	if (W.chain_oct < 0 || link.x < 0) return false;  // root-only mode, or the root has been returned
+	W.chain_node = link.x;
+	W.chain_oct = link.y;
+	walk_push_children(W, ld(S.node_pk + link.x), link.y);
+	return true;
+}
+
 // ------------------------------------------------------------------ Ray.trace (src/raytracer.ts:168-277)
-// One path for one pixel of one exposure frame.  `dir` is the camera direction (un-normalised, as
-// the reference passes it).  Returns the path colour in `out`, and the entity of the first collision.
-// `primary_slot`: the first-hit slot of the camera segment when the primary stage already found it
-// (>= 0), or RT_SLOT_UNKNOWN to search here.
-// Returns true when the path drew from the RNG (a rough surface scattered it): only such paths can differ
-// from one exposure frame to the next (there is no pixel jitter).
+// One path for one pixel of one exposure frame, as an explicit state machine: path_begin(), then
+// path_segment() once per ray segment (walker re-seed + traversal to the first hit + the material's
+// response) until it returns true.  The bounce stage keeps one RtPath per lane and refills finished lanes
+// from the continuation queue between segments; trace_path() below is the plain loop.
+struct RtPath {
+	double refpoint[3], dir[3], col[3];
+	double path_distance;
+	int refcount, cur_substance;
+	int node, octant;   // walker start: node_at_pos of refpoint
+	bool have_node;     // false: refpoint outside the root cube
+	bool light_hit, primary;
+	int first_entity;   // entity of the first collision, -1 none
+	RtRng rng;          // rng.seeded: the path drew from the RNG (a rough surface scattered it)
+};
+
+// `dir_in` is the camera direction (un-normalised, as the reference passes it).
+RT_HD void path_begin(const RtFrame& F, const double* dir_in, RtPath& P) {
+	for (int k = 0; k < 3; k++) {
+		P.refpoint[k] = F.pos[k];
+		P.dir[k] = dir_in[k];
+		P.col[k] = 1.0;
+	}
+	P.path_distance = 0.0;
+	P.refcount = 0;
+	P.cur_substance = F.start_substance;
+	P.rng.seeded = false;
+	P.first_entity = -1;
+	P.node = F.start_node;
+	P.octant = F.start_octant;
+	P.have_node = F.start_node >= 0;
+	P.light_hit = false;
+	P.primary = true;
+}
+
+// The end of Ray.trace after its loop: sky on a miss (:267-271), inverse square law on a light (:273-275).
+RT_HD bool path_finish(const RtDevScene& S, const RtFrame& F, RtPath& P, double* out, uint32_t& err) {
+	if (!P.light_hit) {  // :267-271, SkySphere.get_color (src/sky/sky_sphere.ts:22-27)
+		double sc[3];
+		if (!texture_color(S, F.sky_texture, true, P.dir, sc)) err |= RT_ERRFLAG_TEXTURE;
+		out[0] = xmul(P.col[0], sc[0]); out[1] = xmul(P.col[1], sc[1]); out[2] = xmul(P.col[2], sc[2]);
+		return true;
+	}
+	// inverse square law :273-275
+	const double t = xmul(P.path_distance, F.attenuation);
+	const double isl = xdiv(1.0, xadd(RT_JS_EPSILON, xmul(t, t)));
+	out[0] = xmul(P.col[0], isl); out[1] = xmul(P.col[1], isl); out[2] = xmul(P.col[2], isl);
+	return true;
+}
+
+// A segment in three parts, so that the bounce stage can run the search of 32 independent rays in lock-step:
+//   segment_begin  walker re-seed; returns RT_SEG_DONE (path ended, colour in `out`), RT_SEG_SLOT (`slot` and
+//                  `ci` are known: camera segment found by the primary stage, or searched right here with the
+//                  reference-order state machine when W == nullptr), or RT_SEG_WALK (W is set up: the caller
+//                  runs walk_step() until it returns false, then calls segment_found());
+//   segment_end    the material's response to the hit (or the sky / light ending); true when the path ended.
+// `primary_slot`: the first-hit slot of the camera segment when the primary stage already found it (>= 0), or
+// RT_SLOT_UNKNOWN to search.
+#define RT_SEG_DONE 0
+#define RT_SEG_SLOT 1
+#define RT_SEG_WALK 2
+template <bool COUNT>
+RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int primary_slot, double* out, RtCounts& cnt,
+                        uint32_t& err, RtWalk* W, int& slot, RtCollision& ci) {
+	// walker.set_pos_and_dir -> set_position -> setup_cur_node (src/octree_space.ts:188-205,251-278)
+	if (COUNT) cnt.segments++;
+	slot = -1;
+	if (!P.have_node) {
+		// origin outside the root cube: the root alone, if the ray meets its box going forward
+		const double c[3] = {xadd(S.root_pos[0], xmul(0.5, S.root_size)), xadd(S.root_pos[1], xmul(0.5, S.root_size)),
+		                     xadd(S.root_pos[2], xmul(0.5, S.root_size))};
+		double u1, u2;
+		int i1, i2;
+		if (!exact_box_params(c, S.root_size, P.refpoint, P.dir, u1, u2, i1, i2) || !(u1 >= 0 || u2 >= 0)) {
+			path_finish(S, F, P, out, err);
+			return RT_SEG_DONE;
+		}
+		P.node = 0;
+		P.octant = -1;
+	}
+	if (P.primary && primary_slot >= 0) {
+		// found by the packet stage: only the collision itself is recomputed (same float64 formula)
+		slot = confirm_slot(S, primary_slot, P.refpoint, P.dir, ci) ? primary_slot : -1;
+		return RT_SEG_SLOT;
+	}
+	RtSearch q;
+	q.r = make_ray_f(P.refpoint, P.dir);
+	q.rel = nullptr;
+	q.chain_mask = 0xffffffffu;
+	q.chain_levels = 0;
+	if (P.primary && F.prim_geom) q.rel = F.prim_geom;  // camera rays: origin-relative records
+	if (W) {
+		W->q = q;
+		walk_begin(S, *W, P.node, P.octant);
+		return RT_SEG_WALK;
+	}
+	if (q.rel && P.have_node) {  // lock-step pre-test of the shared origin chain
+		q.chain_levels = F.chain_levels;
+		q.chain_mask = pretest_chain(F, S, q);
+	}
+	slot = walk_and_scan<COUNT>(S, q, P.node, P.octant, P.refpoint, P.dir, ci, cnt);
+	return RT_SEG_SLOT;
+}
+
+// after the ordered walk: the collision of the slot it found
+RT_HD void segment_found(const RtDevScene& S, const RtPath& P, const RtWalk& W, int& slot, RtCollision& ci) {
+	slot = W.hit;
+	if (slot >= 0 && !confirm_slot(S, slot, P.refpoint, P.dir, ci)) slot = -1;  // (same formula as in the walk: cannot fail)
+}
+
+template <bool COUNT>
+RT_HD bool segment_end(const RtDevScene& S, const RtFrame& F, RtPath& P, double pixel_seed, int slot, const RtCollision& ci,
+                       double* out, RtCounts& cnt, uint32_t& err) {
+	P.primary = false;
+	if (slot < 0) return path_finish(S, F, P, out, err);  // miss: sky
+	const RtI4 attr = ld(S.slot_attr + slot);
+	if (P.first_entity < 0) P.first_entity = attr.x;
+	if (dot3(P.dir, ci.normal) >= 0) {  // :200-203
+		err |= RT_ERRFLAG_ACUTE;
+		out[0] = P.col[0]; out[1] = P.col[1]; out[2] = P.col[2];
+		return true;
+	}
+	const bool is_sphere = (attr.y >> RT_ATTR_TYPE_SHIFT) == 0;
+	const RtMaterial m = S.materials[attr.y & RT_ATTR_MAT_MASK];
+	P.refcount++;
+	{  // SolidMaterial.alter_ray (src/materials/material_solid.ts:30-36)
+		const RtD4 g = ld(S.slot_geom64 + slot);
+		const double rel[3] = {xsub(ci.point[0], g.x), xsub(ci.point[1], g.y), xsub(ci.point[2], g.z)};
+		double tc[3];
+		if (!texture_color(S, attr.z, is_sphere, rel, tc)) err |= RT_ERRFLAG_TEXTURE;
+		P.col[0] = xmul(P.col[0], tc[0]); P.col[1] = xmul(P.col[1], tc[1]); P.col[2] = xmul(P.col[2], tc[2]);
+		if (COUNT) cnt.shades++;
+	}
+	{
+		const double dd[3] = {xsub(ci.point[0], P.refpoint[0]), xsub(ci.point[1], P.refpoint[1]),
+		                      xsub(ci.point[2], P.refpoint[2])};
+		P.path_distance = xadd(P.path_distance, xsqrt(dot3(dd, dd)));  // :210
+	}
+	P.refpoint[0] = ci.point[0]; P.refpoint[1] = ci.point[1]; P.refpoint[2] = ci.point[2];  // :212
+	if (m.flags & RT_MAT_LIGHT) {  // :215-218
+		P.light_hit = true;
+		return path_finish(S, F, P, out, err);
+	}
+	const uint32_t response = m.flags & RT_MAT_RESPONSE_MASK;
+	if (response == 0u) {  // REFLECTION :221-237
+		if (!(m.flags & RT_MAT_MIRROR)) {
+			out[0] = P.col[0]; out[1] = P.col[1]; out[2] = P.col[2];
+			return true;
+		}
+		{  // vector.reflection (src/math/vector.ts:263-268)
+			const double k = xmul(-dot3(P.dir, ci.normal), 2.0);
+			P.dir[0] = xadd(P.dir[0], xmul(ci.normal[0], k));
+			P.dir[1] = xadd(P.dir[1], xmul(ci.normal[1], k));
+			P.dir[2] = xadd(P.dir[2], xmul(ci.normal[2], k));
+		}
+		if (m.roughness > 0.0) {  // scatter_ray :121-133, isotropic_sphere_sample vector_utils.ts:8-14
+			if (!P.rng.seeded) rng_seed(P.rng, pixel_seed);
+			double rv[3];
+			do {
+				rv[0] = xsub(xmul(rng_next(P.rng), 2.0), 1.0);
+				rv[1] = xsub(xmul(rng_next(P.rng), 2.0), 1.0);
+				rv[2] = xsub(xmul(rng_next(P.rng), 2.0), 1.0);
+			} while (dot3(rv, rv) > 1);
+			if (dot3(rv, ci.normal) < 0) { rv[0] = -rv[0]; rv[1] = -rv[1]; rv[2] = -rv[2]; }
+			const double ka = xsub(1.0, m.roughness);
+			double rf[3] = {xadd(xmul(P.dir[0], ka), xmul(rv[0], m.roughness)),
+			                xadd(xmul(P.dir[1], ka), xmul(rv[1], m.roughness)),
+			                xadd(xmul(P.dir[2], ka), xmul(rv[2], m.roughness))};
+			const double inv = xdiv(1.0, xsqrt(dot3(rf, rf)));
+			P.dir[0] = xmul(rf[0], inv); P.dir[1] = xmul(rf[1], inv); P.dir[2] = xmul(rf[2], inv);
+		}
+		// move_slightly_forward :158-164
+		P.refpoint[0] = xadd(P.refpoint[0], xmul(P.dir[0], 1e-3));
+		P.refpoint[1] = xadd(P.refpoint[1], xmul(P.dir[1], 1e-3));
+		P.refpoint[2] = xadd(P.refpoint[2], xmul(P.dir[2], 1e-3));
+	} else if (response == 1u) {  // TRANSMISSION :238-249
+		P.refpoint[0] = xadd(P.refpoint[0], xmul(P.dir[0], 1e-3));
+		P.refpoint[1] = xadd(P.refpoint[1], xmul(P.dir[1], 1e-3));
+		P.refpoint[2] = xadd(P.refpoint[2], xmul(P.dir[2], 1e-3));
+		const int rf_slot = entity_at_pos(S, P.refpoint);
+		const int substance = rf_slot >= 0 ? ld(&S.slot_attr[rf_slot].w) : F.default_substance;
+		if (substance >= 0) {  // refract_ray :135-150
+			const double r_ratio = xdiv(S.substances[P.cur_substance], S.substances[substance]);
+			const double r_ratio_sq = xmul(r_ratio, r_ratio);
+			const double cosine = dot3(P.dir, ci.normal);
+			const double cosine_sq = xmul(cosine, cosine);
+			const double ref_sine_sq = xmul(xsub(1.0, cosine_sq), r_ratio_sq);
+			if (ref_sine_sq <= 1) {
+				const double ref_cosine = xsqrt(xsub(1.0, ref_sine_sq));
+				const double k = xsub(ref_cosine, cosine);
+				P.dir[0] = xsub(xmul(P.dir[0], r_ratio), xmul(ci.normal[0], k));
+				P.dir[1] = xsub(xmul(P.dir[1], r_ratio), xmul(ci.normal[1], k));
+				P.dir[2] = xsub(xmul(P.dir[2], r_ratio), xmul(ci.normal[2], k));
+			} else {
+				const double k = xmul(-dot3(P.dir, ci.normal), 2.0);
+				P.dir[0] = xadd(P.dir[0], xmul(ci.normal[0], k));
+				P.dir[1] = xadd(P.dir[1], xmul(ci.normal[1], k));
+				P.dir[2] = xadd(P.dir[2], xmul(ci.normal[2], k));
+			}
+			P.cur_substance = substance;
+		}
+	} else {  // BOTH / default :250-251
+		out[0] = P.col[0]; out[1] = P.col[1]; out[2] = P.col[2];
+		return true;
+	}
+	if (P.refcount >= F.refmax) {  // :256-263
+		out[0] = out[1] = out[2] = 0.0;
+		return true;
+	}
+	P.have_node = node_at_pos(S, P.refpoint, P.node, P.octant);  // :254 (re-seed from the root)
+	return false;
+}
+
+// One whole segment on one thread (per-ray kernels, host build).  The counting variant follows the
+// reference's walker step by step (its counters are the reference's access pattern); the plain variant uses
+// the ordered walk, like the bounce stage.
+template <bool COUNT>
+RT_HD bool path_segment(const RtDevScene& S, const RtFrame& F, RtPath& P, double pixel_seed, int primary_slot, double* out,
+                        RtCounts& cnt, uint32_t& err) {
+	int slot;
+	RtCollision ci;
+	if (!COUNT && S.ordered_ok) {
+		RtWalk W;
+		const int r = segment_begin<COUNT>(S, F, P, primary_slot, out, cnt, err, &W, slot, ci);
+		if (r == RT_SEG_DONE) return true;
+		if (r == RT_SEG_WALK) {
+			while (walk_step(S, W, P.refpoint, P.dir)) {
+			}
+			segment_found(S, P, W, slot, ci);
+		}
+	} else {
+		if (segment_begin<COUNT>(S, F, P, primary_slot, out, cnt, err, nullptr, slot, ci) == RT_SEG_DONE) return true;
+	}
+	return segment_end<COUNT>(S, F, P, pixel_seed, slot, ci, out, cnt, err);
+}
+
+// Returns true when the path drew from the RNG: only such paths can differ from one exposure frame to the
+// next (there is no pixel jitter).
 template <bool COUNT>
 RT_HD bool trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_in, double pixel_seed, int primary_slot,
                       double* out, int& first_entity, RtCounts& cnt, uint32_t& err) {
-	double refpoint[3] = {F.pos[0], F.pos[1], F.pos[2]};
-	double dir[3] = {dir_in[0], dir_in[1], dir_in[2]};
-	double col[3] = {1.0, 1.0, 1.0};
-	double path_distance = 0.0;
-	int refcount = 0;
-	int cur_substance = F.start_substance;
-	RtRng rng;
-	rng.seeded = false;
-	first_entity = -1;
-
-	int node = F.start_node, octant = F.start_octant;
-	bool have_node = F.start_node >= 0;
-	bool light_hit = false;
-	bool primary = true;
-	while (true) {
-		// walker.set_pos_and_dir -> set_position -> setup_cur_node (src/octree_space.ts:188-205,251-278)
-		if (COUNT) cnt.segments++;
-		if (!have_node) {
-			// origin outside the root cube: the root alone, if the ray meets its box going forward
-			const double c[3] = {xadd(S.root_pos[0], xmul(0.5, S.root_size)), xadd(S.root_pos[1], xmul(0.5, S.root_size)),
-			                     xadd(S.root_pos[2], xmul(0.5, S.root_size))};
-			double u1, u2;
-			int i1, i2;
-			if (!exact_box_params(c, S.root_size, refpoint, dir, u1, u2, i1, i2) || !(u1 >= 0 || u2 >= 0)) break;
-			node = 0;
-			octant = -1;
-		}
-		RtCollision ci;
-		int slot;
-		if (primary && primary_slot >= 0) {
-			// found by the packet stage: only the collision itself is recomputed (same float64 formula)
-			slot = primary_slot;
-			const RtD4 g = ld(S.slot_geom64 + slot);
-			const bool hit = ld(S.slot_geom + slot).w > 0.0f ? exact_sphere(g, refpoint, dir, ci) : exact_box(g, refpoint, dir, ci);
-			if (!hit) break;  // cannot happen: the packet stage confirmed it with the same formula
-		} else {
-			RtSearch q;
-			q.r = make_ray_f(refpoint, dir);
-			q.rel = nullptr;
-			q.chain_mask = 0xffffffffu;
-			q.chain_levels = 0;
-			if (primary && F.prim_geom) {
-				// camera rays: origin-relative records + lock-step pre-test of the shared origin chain
-				q.rel = F.prim_geom;
-				if (have_node) {
-					q.chain_levels = F.chain_levels;
-					q.chain_mask = pretest_chain(F, S, q);
-				}
-			}
-			slot = walk_and_scan<COUNT>(S, q, node, octant, refpoint, dir, ci, cnt);
-		}
-		primary = false;
-		if (slot < 0) break;  // miss: sky
-		const RtI4 attr = ld(S.slot_attr + slot);
-		if (first_entity < 0) first_entity = attr.x;
-		if (dot3(dir, ci.normal) >= 0) {  // :200-203
-			err |= RT_ERRFLAG_ACUTE;
-			out[0] = col[0]; out[1] = col[1]; out[2] = col[2];
-			return rng.seeded;
-		}
-		const bool is_sphere = (attr.y >> RT_ATTR_TYPE_SHIFT) == 0;
-		const RtMaterial m = S.materials[attr.y & RT_ATTR_MAT_MASK];
-		refcount++;
-		{  // SolidMaterial.alter_ray (src/materials/material_solid.ts:30-36)
-			const RtD4 g = ld(S.slot_geom64 + slot);
-			const double rel[3] = {xsub(ci.point[0], g.x), xsub(ci.point[1], g.y), xsub(ci.point[2], g.z)};
-			double tc[3];
-			if (!texture_color(S, attr.z, is_sphere, rel, tc)) err |= RT_ERRFLAG_TEXTURE;
-			col[0] = xmul(col[0], tc[0]); col[1] = xmul(col[1], tc[1]); col[2] = xmul(col[2], tc[2]);
-			if (COUNT) cnt.shades++;
-		}
-		{
-			const double dd[3] = {xsub(ci.point[0], refpoint[0]), xsub(ci.point[1], refpoint[1]),
-			                      xsub(ci.point[2], refpoint[2])};
-			path_distance = xadd(path_distance, xsqrt(dot3(dd, dd)));  // :210
-		}
-		refpoint[0] = ci.point[0]; refpoint[1] = ci.point[1]; refpoint[2] = ci.point[2];  // :212
-		if (m.flags & RT_MAT_LIGHT) {  // :215-218
-			light_hit = true;
-			break;
-		}
-		const uint32_t response = m.flags & RT_MAT_RESPONSE_MASK;
-		if (response == 0u) {  // REFLECTION :221-237
-			if (!(m.flags & RT_MAT_MIRROR)) {
-				out[0] = col[0]; out[1] = col[1]; out[2] = col[2];
-				return rng.seeded;
-			}
-			{  // vector.reflection (src/math/vector.ts:263-268)
-				const double k = xmul(-dot3(dir, ci.normal), 2.0);
-				dir[0] = xadd(dir[0], xmul(ci.normal[0], k));
-				dir[1] = xadd(dir[1], xmul(ci.normal[1], k));
-				dir[2] = xadd(dir[2], xmul(ci.normal[2], k));
-			}
-			if (m.roughness > 0.0) {  // scatter_ray :121-133, isotropic_sphere_sample vector_utils.ts:8-14
-				if (!rng.seeded) rng_seed(rng, pixel_seed);
-				double rv[3];
-				do {
-					rv[0] = xsub(xmul(rng_next(rng), 2.0), 1.0);
-					rv[1] = xsub(xmul(rng_next(rng), 2.0), 1.0);
-					rv[2] = xsub(xmul(rng_next(rng), 2.0), 1.0);
-				} while (dot3(rv, rv) > 1);
-				if (dot3(rv, ci.normal) < 0) { rv[0] = -rv[0]; rv[1] = -rv[1]; rv[2] = -rv[2]; }
-				const double ka = xsub(1.0, m.roughness);
-				double rf[3] = {xadd(xmul(dir[0], ka), xmul(rv[0], m.roughness)),
-				                xadd(xmul(dir[1], ka), xmul(rv[1], m.roughness)),
-				                xadd(xmul(dir[2], ka), xmul(rv[2], m.roughness))};
-				const double inv = xdiv(1.0, xsqrt(dot3(rf, rf)));
-				dir[0] = xmul(rf[0], inv); dir[1] = xmul(rf[1], inv); dir[2] = xmul(rf[2], inv);
-			}
-			// move_slightly_forward :158-164
-			refpoint[0] = xadd(refpoint[0], xmul(dir[0], 1e-3));
-			refpoint[1] = xadd(refpoint[1], xmul(dir[1], 1e-3));
-			refpoint[2] = xadd(refpoint[2], xmul(dir[2], 1e-3));
-		} else if (response == 1u) {  // TRANSMISSION :238-249
-			refpoint[0] = xadd(refpoint[0], xmul(dir[0], 1e-3));
-			refpoint[1] = xadd(refpoint[1], xmul(dir[1], 1e-3));
-			refpoint[2] = xadd(refpoint[2], xmul(dir[2], 1e-3));
-			const int rf_slot = entity_at_pos(S, refpoint);
-			const int substance = rf_slot >= 0 ? ld(&S.slot_attr[rf_slot].w) : F.default_substance;
-			if (substance >= 0) {  // refract_ray :135-150
-				const double r_ratio = xdiv(S.substances[cur_substance], S.substances[substance]);
-				const double r_ratio_sq = xmul(r_ratio, r_ratio);
-				const double cosine = dot3(dir, ci.normal);
-				const double cosine_sq = xmul(cosine, cosine);
-				const double ref_sine_sq = xmul(xsub(1.0, cosine_sq), r_ratio_sq);
-				if (ref_sine_sq <= 1) {
-					const double ref_cosine = xsqrt(xsub(1.0, ref_sine_sq));
-					const double k = xsub(ref_cosine, cosine);
-					dir[0] = xsub(xmul(dir[0], r_ratio), xmul(ci.normal[0], k));
-					dir[1] = xsub(xmul(dir[1], r_ratio), xmul(ci.normal[1], k));
-					dir[2] = xsub(xmul(dir[2], r_ratio), xmul(ci.normal[2], k));
-				} else {
-					const double k = xmul(-dot3(dir, ci.normal), 2.0);
-					dir[0] = xadd(dir[0], xmul(ci.normal[0], k));
-					dir[1] = xadd(dir[1], xmul(ci.normal[1], k));
-					dir[2] = xadd(dir[2], xmul(ci.normal[2], k));
-				}
-				cur_substance = substance;
-			}
-		} else {  // BOTH / default :250-251
-			out[0] = col[0]; out[1] = col[1]; out[2] = col[2];
-			return rng.seeded;
-		}
-		if (refcount >= F.refmax) {  // :256-263
-			out[0] = out[1] = out[2] = 0.0;
-			return rng.seeded;
-		}
-		have_node = node_at_pos(S, refpoint, node, octant);  // :254 (re-seed from the root)
+	RtPath P;
+	path_begin(F, dir_in, P);
+	while (!path_segment<COUNT>(S, F, P, pixel_seed, primary_slot, out, cnt, err)) {
 	}
-	if (!light_hit) {  // :267-271, SkySphere.get_color (src/sky/sky_sphere.ts:22-27)
-		double sc[3];
-		if (!texture_color(S, F.sky_texture, true, dir, sc)) err |= RT_ERRFLAG_TEXTURE;
-		out[0] = xmul(col[0], sc[0]); out[1] = xmul(col[1], sc[1]); out[2] = xmul(col[2], sc[2]);
-		return rng.seeded;
-	}
-	// inverse square law :273-275
-	const double t = xmul(path_distance, F.attenuation);
-	const double isl = xdiv(1.0, xadd(RT_JS_EPSILON, xmul(t, t)));
-	out[0] = xmul(col[0], isl); out[1] = xmul(col[1], isl); out[2] = xmul(col[2], isl);
-	return rng.seeded;
+	first_entity = P.first_entity;
+	return P.rng.seeded;
 }
 
 // ------------------------------------------------------------------ one pixel, all exposure frames

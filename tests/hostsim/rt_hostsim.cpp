@@ -44,6 +44,7 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 	S.n_nodes = (int)hs.node_geom.size();
 	S.n_slots = (int)hs.slot_geom.size();
 	S.err_l = hs.err_l;
+	S.ordered_ok = 7 * hs.max_depth + 8 <= RT_WALK_STACK ? 1 : 0;
 	F.col_cs = col.data();
 	F.row_fr = row.data();
 	F.rgb = rgb;
