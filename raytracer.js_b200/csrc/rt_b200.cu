@@ -147,10 +147,21 @@ __global__ void __launch_bounds__(256)
 }
 
 // Bounce stage: persistent wavefront with a per-warp ray queue.  Every lane owns one pixel job (all its
-// exposure frames) and advances it ONE ray segment per iteration (path_segment); between segments the warp
-// votes on which lanes have finished their pixel and refills exactly those lanes from the continuation
-// queue (one atomic per refill, ranks by popc of the vote), so a path that bounces four times does not hold
-// 31 finished lanes hostage.  Frames whose path never drew from the RNG reuse the first frame's sample.
+// exposure frames) and is in one of four states:
+//   IDLE   no job: refilled from the continuation queue (one atomic per refill, ranks by popc of the vote);
+//   BEGIN  a ray segment starts: walker re-seed (segment_begin);
+//   WALK   the ordered walk, run by the whole warp in lock-step (walk_iter: every lane does one node step
+//          and/or one list-BVH step per iteration, phases re-converged);
+//   END    the search is over: collision + the material's response (segment_end), which starts the next
+//          segment (BEGIN), the next exposure frame, or ends the job (IDLE).
+// The warp leaves the walk loop as soon as a quarter of the lanes that entered it have finished (or fewer
+// than F.bounce_min_walking are left), so that a path that bounces four times or crosses a long list does
+// not hold finished lanes hostage: those shade, start their next segment or fetch a new pixel, and re-join.
+// Frames whose path never drew from the RNG reuse the first frame's sample.
+#define RT_ST_IDLE 0
+#define RT_ST_BEGIN 1
+#define RT_ST_WALK 2
+#define RT_ST_END 3
 __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
     rt_bounce_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
 	const int lane = threadIdx.x & 31;
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 	RtCounts cnt = {0, 0, 0, 0, 0};
 	uint32_t err = 0;
 	// the lane's pixel job
-	bool active = false;
+	int st = RT_ST_IDLE;
 	int x = 0, y = 0, slot = RT_SLOT_UNKNOWN;
 	size_t out_index = 0;
 	uint32_t frame = 0;
@@ -167,9 +178,33 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 	RtPath P;
 	RtWalk W;
 	bool exhausted = n == 0;
+	// a sample (path colour c) of exposure frame `frame` is complete: ExposureBuffer.set_color_i
+	// (src/view/exposure_buffer.ts:77-91) for this frame, and for all remaining ones when the path cannot
+	// change (it never drew from the RNG); then the next frame's path, or the end of the job
+	auto sample_done = [&](const double* c) {
+		const bool varies = P.rng.seeded;
+		const uint32_t last = varies ? frame + 1 : F.n_frames;
+		for (; frame < last; frame++) {
+			const double w = xdiv(1.0, (double)(1u + F.frame_first + frame));
+			const double w1 = xsub(1.0, w);
+#pragma unroll
+			for (int k = 0; k < 3; k++) px[k] = (float)xadd(xmul(c[k], w), xmul((double)px[k], w1));
+		}
+		if (frame < F.n_frames) {
+			double dir[3];
+			pixel_dir(F, x, y, dir);
+			path_begin(F, dir, P);
+			st = RT_ST_BEGIN;
+		} else {
+			float* o = F.rgb + out_index * 3;
+			o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
+			if (F.first_ids) F.first_ids[out_index] = P.first_entity;
+			st = RT_ST_IDLE;
+		}
+	};
 	while (true) {
 		// ---- refill the idle lanes
-		const unsigned idle = __ballot_sync(0xffffffffu, !active);
+		const unsigned idle = __ballot_sync(0xffffffffu, st == RT_ST_IDLE);
 		if (idle && !exhausted) {
 			const unsigned want = (unsigned)__popc(idle);
 			unsigned base = 0;
@@ -177,7 +212,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 			base = __shfl_sync(0xffffffffu, base, 0);
 			exhausted = base + want >= n;
 			const unsigned i = base + (unsigned)__popc(idle & lt_mask);
-			if (!active && i < n) {
+			if (st == RT_ST_IDLE && i < n) {
 				const RtQueueItem it = F.queue[i];
 				x = (int)(it.xy & 0xffffu);
 				y = (int)(it.xy >> 16);
@@ -196,55 +231,52 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 				double dir[3];
 				pixel_dir(F, x, y, dir);
 				path_begin(F, dir, P);
-				active = true;
+				st = RT_ST_BEGIN;
 			}
 		}
-		if (__ballot_sync(0xffffffffu, active) == 0u) break;
-		// ---- one segment for every active lane: (1) re-seed, (2) the ordered walk in lock-step - every lane
-		// that is still searching handles ONE octree node per iteration, and the vote at the top keeps the 32
-		// independent rays converged -, (3) the material's response
-		const uint32_t frame_count = F.frame_first + frame;
-		const double seed = xadd(xadd(F.rng_seed, (double)((size_t)y * F.width + x)),
-		                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
-		double c[3];
-		int hit = -1;
-		RtCollision ci;
-		int state = RT_SEG_DONE;
-		bool finished = false;
-		if (active) {
-			state = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
-			finished = state == RT_SEG_DONE;
-		}
-		bool walking = active && state == RT_SEG_WALK;
-		while (__any_sync(0xffffffffu, walking)) {
-			if (walking) walking = walk_step(S, W, P.refpoint, P.dir);
-		}
-		if (active && !finished) {
-			if (state == RT_SEG_WALK) segment_found(S, P, W, hit, ci);
-			finished = segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err);
-		}
-		if (active && finished) {
-			// ExposureBuffer.set_color_i (src/view/exposure_buffer.ts:77-91) for this frame, and for all
-			// remaining ones when the path cannot change (it never drew from the RNG)
-			const bool varies = P.rng.seeded;
-			const uint32_t last = varies ? frame + 1 : F.n_frames;
-			for (; frame < last; frame++) {
-				const double w = xdiv(1.0, (double)(1u + F.frame_first + frame));
-				const double w1 = xsub(1.0, w);
-#pragma unroll
-				for (int k = 0; k < 3; k++) px[k] = (float)xadd(xmul(c[k], w), xmul((double)px[k], w1));
-			}
-			if (frame < F.n_frames) {
-				double dir[3];
-				pixel_dir(F, x, y, dir);
-				path_begin(F, dir, P);
+		if (__ballot_sync(0xffffffffu, st != RT_ST_IDLE) == 0u) break;
+		// ---- BEGIN: walker re-seed
+		if (st == RT_ST_BEGIN) {
+			double c[3];
+			int hit = -1;
+			RtCollision ci;
+			const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
+			if (r == RT_SEG_DONE) {
+				sample_done(c);
+			} else if (r == RT_SEG_WALK) {
+				st = RT_ST_WALK;
 			} else {
-				float* o = F.rgb + out_index * 3;
-				o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
-				if (F.first_ids) F.first_ids[out_index] = P.first_entity;
-				active = false;
+				W.hit = hit;  // known from the primary stage (or searched by the fallback walker)
+				st = RT_ST_END;
 			}
 		}
+		__syncwarp();
+		// ---- WALK in lock-step
+		{
+			bool walking = st == RT_ST_WALK;
+			int nw = __popc(__ballot_sync(0xffffffffu, walking));
+			if (nw > 0) {
+				const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
+				do {
+					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking);
+					nw = __popc(__ballot_sync(0xffffffffu, walking));
+				} while (nw >= limit);
+				if (st == RT_ST_WALK && !walking) st = RT_ST_END;
+			}
+		}
+		// ---- END: collision, material response
+		if (st == RT_ST_END) {
+			const uint32_t frame_count = F.frame_first + frame;
+			const double seed = xadd(xadd(F.rng_seed, (double)((size_t)y * F.width + x)),
+			                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
+			double c[3];
+			int hit = W.hit;
+			RtCollision ci;
+			if (hit >= 0 && !confirm_slot(S, hit, P.refpoint, P.dir, ci)) hit = -1;  // (same formula as in the search: cannot fail)
+			if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
+			else st = RT_ST_BEGIN;
+		}
+		__syncwarp();
 	}
 	if (err) atomicOr(F.error_flags, err);
 }
@@ -345,6 +377,7 @@ struct rt_ctx {
 	DevBuf<int> node_bvh;
 	DevBuf<RtBvhNode> bvh_nodes;
 	DevBuf<int> bvh_slots;
+	DevBuf<RtF4> bvh_geom;
 	DevBuf<RtF4> slot_geom;
 	DevBuf<RtD4> slot_geom64;
 	DevBuf<RtI4> slot_attr;
@@ -370,6 +403,7 @@ struct rt_ctx {
 	std::vector<uint32_t*> peer_flags_host;
 	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
 	int ppl = RT_PPL;
+	int bounce_min_walking = 24;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
 };
 
 namespace {
@@ -472,6 +506,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	F.tile_rank = tile_rank;
 	F.tile_world = tile_world;
 	F.tile_compact = tile_compact ? 1 : 0;
+	F.bounce_min_walking = ctx->bounce_min_walking;
 	// u64 cells: [0..7] work counters, [8] error flags, then per band {patch dispenser, queue count, queue cursor}
 	n_bands = std::max(1, std::min(n_bands, RT_MAX_BANDS));
 	const size_t n_cells = 9 + 3 * RT_MAX_BANDS;
@@ -671,6 +706,10 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= RT_MAX_BANDS) ctx->n_bands = v;
 	}
+	if (const char* e = getenv("RT_B200_BOUNCE_MIN")) {
+		const int v = atoi(e);
+		if (v >= 1 && v <= 32) ctx->bounce_min_walking = v;
+	}
 	if (const char* e = getenv("RT_B200_PPL")) {
 		const int v = atoi(e);
 		if (v == 1 || v == 2 || v == 4 || v == 8) ctx->ppl = v;
@@ -683,7 +722,7 @@ void rt_destroy(rt_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release();
+	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release(); ctx->bvh_geom.release();
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
@@ -764,14 +803,14 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	rt_status st;
 	if ((st = upload(ctx, ctx->node_geom, H.node_geom)) || (st = upload(ctx, ctx->node_link, H.node_link)) ||
 	    (st = upload(ctx, ctx->node_child, H.node_child)) || (st = upload(ctx, ctx->node_pk, H.node_pk)) || (st = upload(ctx, ctx->node_bvh, H.node_bvh)) ||
-	    (st = upload(ctx, ctx->bvh_nodes, H.bvh_nodes)) || (st = upload(ctx, ctx->bvh_slots, H.bvh_slots)) || (st = upload(ctx, ctx->slot_geom, H.slot_geom)) ||
+	    (st = upload(ctx, ctx->bvh_nodes, H.bvh_nodes)) || (st = upload(ctx, ctx->bvh_slots, H.bvh_slots)) || (st = upload(ctx, ctx->bvh_geom, H.bvh_geom)) || (st = upload(ctx, ctx->slot_geom, H.slot_geom)) ||
 	    (st = upload(ctx, ctx->slot_geom64, H.slot_geom64)) || (st = upload(ctx, ctx->slot_attr, H.slot_attr)) ||
 	    (st = upload(ctx, ctx->materials, H.materials)) || (st = upload(ctx, ctx->textures, H.textures)) ||
 	    (st = upload(ctx, ctx->substances, H.substances)) || (st = upload(ctx, ctx->texels, H.texels)))
 		return st;
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	RtDevScene& D = ctx->dev;
-	D.node_geom = ctx->node_geom.p; D.node_link = ctx->node_link.p; D.node_child = ctx->node_child.p; D.node_pk = ctx->node_pk.p; D.node_bvh = ctx->node_bvh.p; D.bvh_nodes = ctx->bvh_nodes.p; D.bvh_slots = ctx->bvh_slots.p;
+	D.node_geom = ctx->node_geom.p; D.node_link = ctx->node_link.p; D.node_child = ctx->node_child.p; D.node_pk = ctx->node_pk.p; D.node_bvh = ctx->node_bvh.p; D.bvh_nodes = ctx->bvh_nodes.p; D.bvh_slots = ctx->bvh_slots.p; D.bvh_geom = ctx->bvh_geom.p;
 	D.slot_geom = ctx->slot_geom.p; D.slot_geom64 = ctx->slot_geom64.p; D.slot_attr = ctx->slot_attr.p;
 	D.materials = ctx->materials.p; D.textures = ctx->textures.p; D.substances = ctx->substances.p;
 	D.texels = ctx->texels.p;
@@ -780,7 +819,7 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	D.n_nodes = (int)H.node_geom.size();
 	D.n_slots = (int)H.slot_geom.size();
 	D.err_l = H.err_l;
-	D.ordered_ok = 7 * H.max_depth + 8 <= RT_WALK_STACK ? 1 : 0;
+	D.ordered_ok = rt_ordered_walk_fits(H);
 	ctx->has_scene = true;
 	return RT_OK;
 }

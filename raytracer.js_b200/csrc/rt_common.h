@@ -37,13 +37,16 @@ struct alignas(32) RtPNode {
 
 // Per-list bounding volume hierarchy.  The reference scans a node's entity list linearly and takes the FIRST
 // entity (in insertion order) the ray hits; any structure that finds every hit entity of the list and keeps
-// the lowest slot gives the same answer.  Lists of RT_BVH_MIN_LIST or more entries (the big straddler lists
-// near the root) get a binary BVH over the entities' float32 boxes (inflated by err_l): a ray then tests a
-// few dozen boxes instead of hundreds or thousands of entities.
+// the lowest slot gives the same answer.  Every non-empty list has a binary BVH over the entities' float32
+// boxes (inflated by err_l): a ray then tests a few dozen boxes instead of hundreds or thousands of entities
+// of the big straddler lists near the root.  The bounce stage walks every list through its BVH (one uniform
+// kind of step for the 32 independent rays of a warp); the ray-by-ray kernels use it for lists of
+// RT_BVH_MIN_LIST or more entries and scan shorter ones linearly.
 struct alignas(16) RtBvhNode {
 	float lo[3], hi[3];
-	int a;  // inner: index of the left child (right = a + 1); leaf: first entry in bvh_slots
-	int b;  // inner: 0; leaf: number of entries (> 0), ascending slot numbers
+	int a;  // inner: index of the left child (right = a + 1), the left one holds the lowest slot;
+	        // leaf: first entry in bvh_slots / bvh_geom
+	int b;  // inner: -(lowest slot below this node + 1) (< 0); leaf: number of entries (> 0), ascending slots
 };
 #define RT_BVH_MIN_LIST 24
 #define RT_BVH_LEAF 4
@@ -80,7 +83,8 @@ struct RtDevScene {
 	const RtPNode* node_pk;  // the same nodes as one 32-byte record each, for the packet walk
 	const int* node_bvh;     // [n] root of the node's list BVH in bvh_nodes, or -1 (short list)
 	const RtBvhNode* bvh_nodes;
-	const int* bvh_slots;    // leaf entries
+	const int* bvh_slots;    // leaf entries: slot numbers
+	const RtF4* bvh_geom;    // leaf entries: copy of slot_geom in leaf order (no indirection in the leaf test)
 	// entity lists, slot order
 	const RtF4* slot_geom;   // centre.xyz, w = radius (>0, sphere) | -half_size (<0, box)
 	const RtD4* slot_geom64; // centre.xyz, w = diameter | size  (the reference's float64 values)
@@ -108,7 +112,7 @@ struct alignas(8) RtQueueItem {
 };
 #define RT_SLOT_UNKNOWN (-2)
 #define RT_PACKET_STACK 192  // node stack of the packet walk: 7 siblings per level + 8
-#define RT_WALK_STACK 128    // node stack of the per-ray ordered walk (bounce stage), same bound
+#define RT_WALK_STACK 160    // stack of the per-ray ordered walk (bounce stage): octree nodes (same bound) + one list BVH on top
 
 struct RtFrame {
 	// camera
@@ -151,6 +155,7 @@ struct RtFrame {
 	RtQueueItem* queue;      // [capacity]
 	unsigned* queue_count;   // items appended by the primary stage
 	unsigned* queue_taken;   // consumer cursor of the bounce stage
+	int bounce_min_walking;  // bounce stage: leave the lock-step walk when fewer lanes than this are still walking
 };
 
 #define RT_ERRFLAG_TEXTURE 1u

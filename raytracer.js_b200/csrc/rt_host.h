@@ -21,6 +21,8 @@ struct RtHostScene {
 	std::vector<int> node_bvh;
 	std::vector<RtBvhNode> bvh_nodes;
 	std::vector<int> bvh_slots;
+	std::vector<RtF4> bvh_geom;
+	int max_bvh_depth = 0;  // deepest list-BVH level (root = 0)
 	std::vector<RtF4> slot_geom;
 	std::vector<RtD4> slot_geom64;
 	std::vector<RtI4> slot_attr;
@@ -44,13 +46,18 @@ inline std::string rt_format(const char* fmt, ...) {
 	return buf;
 }
 
-// Binary BVHs over the long entity lists (rt_common.h: RtBvhNode).  Median split of the centres along the
-// widest axis; boxes are the entities' float64 boxes inflated by err_l and rounded outwards to float32.
+// Binary BVHs over the entity lists (rt_common.h: RtBvhNode), one per non-empty list.  Median split of the
+// centres along the widest axis; boxes are the entities' float64 boxes inflated by err_l and rounded outwards
+// to float32.  Every inner node records the lowest slot below it, and its LEFT child is the one that holds
+// that slot: a traversal that keeps the lowest hit slot so far skips whole subtrees that cannot beat it, and
+// reaches the low slots first.
 inline void rt_build_list_bvhs(RtHostScene& hs) {
 	const size_t N = hs.node_link.size();
 	hs.node_bvh.assign(N, -1);
 	hs.bvh_nodes.clear();
 	hs.bvh_slots.clear();
+	hs.bvh_geom.clear();
+	hs.max_bvh_depth = 0;
 	struct Box { float lo[3], hi[3]; };
 	const double infl = (double)hs.err_l;
 	auto box_of = [&](int s) {
@@ -65,27 +72,30 @@ inline void rt_build_list_bvhs(RtHostScene& hs) {
 		return b;
 	};
 	std::vector<int> idx;
-	struct Job { int node, beg, end; };
+	struct Job { int node, beg, end, depth; };
 	std::vector<Job> jobs;
 	for (size_t n = 0; n < N; n++) {
 		const int off = hs.node_link[n].z, cnt = hs.node_link[n].w;
-		if (cnt < RT_BVH_MIN_LIST) continue;
+		if (cnt <= 0) continue;
 		idx.resize(cnt);
 		for (int i = 0; i < cnt; i++) idx[i] = off + i;
 		hs.node_bvh[n] = (int)hs.bvh_nodes.size();
 		hs.bvh_nodes.push_back(RtBvhNode{});
 		jobs.clear();
-		jobs.push_back(Job{hs.node_bvh[n], 0, cnt});
+		jobs.push_back(Job{hs.node_bvh[n], 0, cnt, 0});
 		while (!jobs.empty()) {
 			const Job j = jobs.back();
 			jobs.pop_back();
+			hs.max_bvh_depth = std::max(hs.max_bvh_depth, j.depth);
 			Box bb;
 			double cmin[3] = {1e300, 1e300, 1e300}, cmax[3] = {-1e300, -1e300, -1e300};
+			int min_slot = 0x7fffffff;
 			for (int k = 0; k < 3; k++) { bb.lo[k] = INFINITY; bb.hi[k] = -INFINITY; }
 			for (int i = j.beg; i < j.end; i++) {
 				const Box b = box_of(idx[i]);
 				const RtD4& g = hs.slot_geom64[idx[i]];
 				const double c[3] = {g.x, g.y, g.z};
+				min_slot = std::min(min_slot, idx[i]);
 				for (int k = 0; k < 3; k++) {
 					bb.lo[k] = std::min(bb.lo[k], b.lo[k]);
 					bb.hi[k] = std::max(bb.hi[k], b.hi[k]);
@@ -104,6 +114,7 @@ inline void rt_build_list_bvhs(RtHostScene& hs) {
 				nd.a = (int)hs.bvh_slots.size();
 				nd.b = count;
 				hs.bvh_slots.insert(hs.bvh_slots.end(), idx.begin() + j.beg, idx.begin() + j.end);
+				for (int i = j.beg; i < j.end; i++) hs.bvh_geom.push_back(hs.slot_geom[idx[i]]);
 			} else {
 				const int mid = j.beg + count / 2;
 				std::nth_element(idx.begin() + j.beg, idx.begin() + mid, idx.begin() + j.end, [&](int p, int q) {
@@ -111,18 +122,26 @@ inline void rt_build_list_bvhs(RtHostScene& hs) {
 					const double b = axis == 0 ? hs.slot_geom64[q].x : axis == 1 ? hs.slot_geom64[q].y : hs.slot_geom64[q].z;
 					return a < b || (a == b && p < q);
 				});
+				const bool min_left = std::find(idx.begin() + j.beg, idx.begin() + mid, min_slot) != idx.begin() + mid;
 				nd.a = (int)hs.bvh_nodes.size();
-				nd.b = 0;
+				nd.b = -(min_slot + 1);
 				hs.bvh_nodes.push_back(RtBvhNode{});
 				hs.bvh_nodes.push_back(RtBvhNode{});
-				jobs.push_back(Job{nd.a, j.beg, mid});
-				jobs.push_back(Job{nd.a + 1, mid, j.end});
+				jobs.push_back(Job{nd.a + (min_left ? 0 : 1), j.beg, mid, j.depth + 1});
+				jobs.push_back(Job{nd.a + (min_left ? 1 : 0), mid, j.end, j.depth + 1});
 			}
 			hs.bvh_nodes[j.node] = nd;
 		}
 	}
 	if (hs.bvh_nodes.empty()) hs.bvh_nodes.push_back(RtBvhNode{});
 	if (hs.bvh_slots.empty()) hs.bvh_slots.push_back(0);
+	if (hs.bvh_geom.empty()) hs.bvh_geom.push_back(RtF4{0, 0, 0, 0});
+}
+
+// 1 when the stack of the bounce stage's ordered walk (RT_WALK_STACK entries) holds the deepest case: up to 7
+// siblings per octree level + 8, and one list BVH on top (depth + 1 entries, binary DFS)
+inline int rt_ordered_walk_fits(const RtHostScene& hs) {
+	return 7 * hs.max_depth + 8 + hs.max_bvh_depth + 2 <= RT_WALK_STACK ? 1 : 0;
 }
 
 // Validates `sc` and fills `hs`.  On failure returns the status and a message in `err`.

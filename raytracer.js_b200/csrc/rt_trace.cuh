@@ -367,10 +367,11 @@ RT_HD int scan_list_bvh(const RtDevScene& S, const RtSearch& q, int root, const 
 		t0 = (n0.z - r.oz) * r.iz; t1 = (hz - r.oz) * r.iz;
 		tmin = fmaxf(tmin, fminf(t0, t1)); tmax = fminf(tmax, fmaxf(t0, t1));
 		if (tmin > tmax + slack || tmax < -slack) continue;  // (NaN from 0 * inf compares false: kept)
-		if (n1.w == 0) {
+		if (n1.w < 0) {
+			if (-(n1.w + 1) >= best) continue;  // nothing below this node can beat the hit we have
 			if (sp + 2 <= RT_BVH_STACK) {
-				stack[sp++] = n1.z;
 				stack[sp++] = n1.z + 1;
+				stack[sp++] = n1.z;  // the child with the lowest slot first
 			}
 			continue;
 		}
@@ -395,9 +396,8 @@ RT_HD int scan_list_bvh(const RtDevScene& S, const RtSearch& q, int root, const 
 template <bool COUNT>
 RT_HD int scan_list(const RtDevScene& S, const RtSearch& q, int node, int beg, int end, const double* o, const double* d,
                     RtCollision& col, RtCounts& cnt) {
-	const int bvh = ld(S.node_bvh + node);
-	if (bvh >= 0) {
-		const int s = scan_list_bvh(S, q, bvh, o, d, col);
+	if (end - beg >= RT_BVH_MIN_LIST) {
+		const int s = scan_list_bvh(S, q, ld(S.node_bvh + node), o, d, col);
 		// the counters count the reference's linear scan: up to and including the hit, or the whole list
 		if (COUNT) {
 			cnt.tests += (unsigned)(s >= 0 ? s - beg + 1 : end - beg);
@@ -1038,45 +1038,66 @@ RT_HD double rng_next(RtRng& g) {
 // The same order argument as the packet walk, for ONE ray: with the direction signs fixed, the reference
 // visits the children a ray pierces in ascending (octant ^ neg), subtrees in pre-order, and the nodes that
 // contain the ray origin in post-order.  Unlike the state machine of walk_and_scan (which follows the
-// reference's walker step by step and is kept for the counting kernel), this formulation does the same work
-// for every node - pop, scan the list, push the pierced children - so the 32 independent rays of a warp in
-// the bounce stage run it in lock-step, one node per iteration (walk_step), instead of serialising on the
-// branches of 32 different walker states.  A conservative (slack) pierce test can only add nodes, which cannot
-// change a first hit (entities lie inside their node's cube).
+// reference's walker step by step and is kept for the counting kernel), this formulation is a stack machine
+// with two kinds of step only, so that the 32 independent rays of a warp in the bounce stage run it in
+// lock-step (walk_iter) instead of serialising on the branches of 32 different walker states:
+//   node step  pop the next octree node (or, with the stack empty, go one level up the origin chain), push
+//              the children the ray pierces - last-visited first - and then the root of the node's list BVH;
+//   list step  pop one node of the current list's BVH: slab test, then push its two children (inner) or test
+//              its up to RT_BVH_LEAF entities (leaf), keeping the LOWEST hit slot = the first entity in list
+//              order the ray hits (src/raytracer.ts:186-195).
+// The list BVH sits on top of the octree entries, so a list is finished before the next node is popped, and
+// the walk ends at the first list that holds a hit.  A conservative (slack) pierce test can only add nodes,
+// which cannot change a first hit (entities lie inside their node's cube).
+#define RT_NO_SLOT 0x7fffffff
 struct RtWalk {
-	RtSearch q;
-	int neg;         // bit k: d_k < 0
+	RtRayF r;
+	int neg;          // bit k: d_k < 0
 	int sp;
-	int chain_node;  // origin-chain node to be returned once the stack is empty; < 0: walk over
-	int chain_oct;   // octant of chain_node the ray leaves (its children before it cannot be reached)
-	int hit;         // first-hit slot, -1 while none
+	int floor;        // stack height below the current list's BVH entries
+	int in_list;      // 1: the entries above `floor` are BVH nodes of the current list
+	int chain_node;   // origin-chain node whose list is returned once the stack is empty
+	int chain_oct;    // octant of chain_node the ray leaves (its children before it cannot be reached); < 0: root only
+	int chain_listed; // 1: chain_node's list has been scanned, next is its parent
+	int best;         // lowest hit slot of the current list, RT_NO_SLOT while none
+	int hit;          // result: first-hit slot, -1 none
 	float slack;
 	int stack[RT_WALK_STACK];
 };
 
-// pushes the children of `nd` the ray may pierce, last-visited first
+// pushes the children of `nd` the ray may pierce, last-visited first.  In the ray's own frame (axis k
+// mirrored when d_k < 0) the half of the cube entered first is "half 0": key bit k of a child says which
+// half it is in, so the parameter interval of a child is a static selection among three plane parameters
+// per axis.
 RT_HD void walk_push_children(RtWalk& W, const RtPNode& nd, int after_oct) {
 	if (!nd.child_mask) return;
-	const RtRayF& r = W.q.r;
+	const RtRayF& r = W.r;
 	const float h = nd.size * 0.5f;
-	// per axis: parameter intervals of the lower and the upper half of the cube
-	float nr[3][2], fr[3][2];
+	float t0[3], tm[3], t1[3];  // entry plane, mid plane, exit plane along the direction of travel
 	{
 		const float lo[3] = {nd.x, nd.y, nd.z}, o[3] = {r.ox, r.oy, r.oz}, inv[3] = {r.ix, r.iy, r.iz};
 #pragma unroll
 		for (int k = 0; k < 3; k++) {
-			const float ta = (lo[k] - o[k]) * inv[k], tm = (lo[k] + h - o[k]) * inv[k], tb = (lo[k] + nd.size - o[k]) * inv[k];
-			nr[k][0] = fminf(ta, tm); fr[k][0] = fmaxf(ta, tm);
-			nr[k][1] = fminf(tm, tb); fr[k][1] = fmaxf(tm, tb);
+			const float ta = (lo[k] - o[k]) * inv[k], tb = (lo[k] + nd.size - o[k]) * inv[k];
+			tm[k] = (lo[k] + h - o[k]) * inv[k];
+			t0[k] = fminf(ta, tb);  // (NaN from 0 * inf is dropped by fminf / fmaxf)
+			t1[k] = fmaxf(ta, tb);
+			// a zero component: the ray stays in the half that holds its origin; both halves keep the whole
+			// interval (conservative), +-inf parameters order themselves
 		}
 	}
 	const int want = after_oct >= 0 ? (after_oct ^ W.neg) : 0;
+	const unsigned mask_k = xor_permute8((unsigned)nd.child_mask, W.neg);  // bit key = child of octant key ^ neg exists
 #pragma unroll
 	for (int key = 7; key >= 0; key--) {
+		if (!((mask_k >> key) & 1u) || (key & want) != want) continue;
 		const int o = key ^ W.neg;
-		if (!((nd.child_mask >> o) & 1) || (key & want) != want || o == after_oct) continue;
-		const float tnear = fmaxf(fmaxf(nr[0][o & 1], nr[1][(o >> 1) & 1]), fmaxf(nr[2][(o >> 2) & 1], 0.0f));
-		const float tfar = fminf(fminf(fr[0][o & 1], fr[1][(o >> 1) & 1]), fr[2][(o >> 2) & 1]);
+		if (o == after_oct) continue;
+		const float nx = (key & 1) ? fminf(tm[0], t1[0]) : fminf(t0[0], tm[0]), fx = (key & 1) ? fmaxf(tm[0], t1[0]) : fmaxf(t0[0], tm[0]);
+		const float ny = (key & 2) ? fminf(tm[1], t1[1]) : fminf(t0[1], tm[1]), fy = (key & 2) ? fmaxf(tm[1], t1[1]) : fmaxf(t0[1], tm[1]);
+		const float nz = (key & 4) ? fminf(tm[2], t1[2]) : fminf(t0[2], tm[2]), fz = (key & 4) ? fmaxf(tm[2], t1[2]) : fmaxf(t0[2], tm[2]);
+		const float tnear = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
+		const float tfar = fminf(fminf(fx, fy), fz);
 		if (tnear <= tfar * 1.00001f + W.slack && W.sp < RT_WALK_STACK)
 			W.stack[W.sp++] = nd.child_base + popc32((unsigned)nd.child_mask & ((1u << o) - 1u));
 	}
@@ -1084,48 +1105,111 @@ RT_HD void walk_push_children(RtWalk& W, const RtPNode& nd, int after_oct) {
 
 // (node, octant): node_at_pos of the ray origin, or octant < 0 for "origin outside the root: root only"
 RT_HD void walk_begin(const RtDevScene& S, RtWalk& W, int node, int octant) {
-	const RtRayF& r = W.q.r;
+	const RtRayF& r = W.r;
 	W.neg = (r.dx < 0.0f ? 1 : 0) | (r.dy < 0.0f ? 2 : 0) | (r.dz < 0.0f ? 4 : 0);
 	W.sp = 0;
+	W.floor = 0;
+	W.in_list = 0;
+	W.best = RT_NO_SLOT;
 	W.hit = -1;
 	W.slack = S.err_l * fminf(fmaxf(fabsf(r.ix), fmaxf(fabsf(r.iy), fabsf(r.iz))), 1e7f);
 	W.chain_node = node;
 	W.chain_oct = octant;
+	W.chain_listed = 0;
 	if (octant >= 0) walk_push_children(W, ld(S.node_pk + node), octant);
 }
 
-// One node of the walk.  Returns false when the walk is over (W.hit = slot or -1).
-RT_HD bool walk_step(const RtDevScene& S, RtWalk& W, const double* o, const double* d) {
+// float64 confirmation without the collision record (the caller recomputes it for the one slot it keeps)
+RT_HD bool confirm_hit(const RtDevScene& S, int s, bool is_sphere, const double* o, const double* d) {
 	RtCollision col;
-	RtCounts none = {0, 0, 0, 0, 0};
-	if (W.sp > 0) {
-		const int n = W.stack[--W.sp];
-		const RtPNode nd = ld(S.node_pk + n);
-		if (nd.list_cnt > 0) {
-			const int s = scan_list<false>(S, W.q, n, nd.list_off, nd.list_off + nd.list_cnt, o, d, col, none);
-			if (s >= 0) {
-				W.hit = s;
-				return false;
+	const RtD4 g = ld(S.slot_geom64 + s);
+	return is_sphere ? exact_sphere(g, o, d, col) : exact_box(g, o, d, col);
+}
+
+// One iteration of the walk for every lane of the warp (`walking`: this lane takes part).  Returns false
+// when this lane's walk is over (W.hit = slot or -1).  LOCKSTEP: all 32 lanes of the warp call this together
+// (bounce stage) and the phases re-converge the warp between them; without it the caller may be one lane of a
+// diverged warp (ray-by-ray kernels) and no warp-wide barrier is used.
+template <bool LOCKSTEP>
+RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const double* d, bool walking) {
+	// ---- node step
+	if (walking && !W.in_list) {
+		int push_node = -1, after = -1, list_of = -1;
+		if (W.sp > 0) {
+			push_node = list_of = W.stack[--W.sp];
+		} else if (!W.chain_listed) {
+			// stack empty: the ray leaves the current origin-chain node, which is returned now (post-order)
+			W.chain_listed = 1;
+			list_of = W.chain_node;
+		} else {
+			const RtI4 link = ld(S.node_link + W.chain_node);
+			if (W.chain_oct < 0 || link.x < 0) {
+				walking = false;  // root-only mode, or the root has been returned: miss
+			} else {
+				W.chain_node = push_node = link.x;
+				W.chain_oct = after = link.y;
+				W.chain_listed = 0;
 			}
 		}
-		walk_push_children(W, nd, -1);
-		return true;
-	}
-	// stack empty: the ray leaves the current origin-chain node, which is returned now (post-order)
-	const int A = W.chain_node;
-	const RtI4 link = ld(S.node_link + A);
-	if (link.w > 0) {
-		const int s = scan_list<false>(S, W.q, A, link.z, link.z + link.w, o, d, col, none);
-		if (s >= 0) {
-			W.hit = s;
-			return false;
+		if (push_node >= 0) walk_push_children(W, ld(S.node_pk + push_node), after);
+		if (list_of >= 0) {
+			const int root = ld(S.node_bvh + list_of);
+			if (root >= 0) {
+				W.floor = W.sp;
+				W.stack[W.sp++] = root;  // (room for the list BVH is part of RT_WALK_STACK: rt_ordered_walk_fits)
+				W.in_list = 1;
+				W.best = RT_NO_SLOT;
+			}
 		}
 	}
-	if (W.chain_oct < 0 || link.x < 0) return false;  // root-only mode, or the root has been returned
-	W.chain_node = link.x;
-	W.chain_oct = link.y;
-	walk_push_children(W, ld(S.node_pk + link.x), link.y);
-	return true;
+	if (LOCKSTEP) warp_sync();
+	// ---- list step
+	int leaf_a = 0, leaf_n = 0;
+	if (walking && W.in_list) {
+		const RtRayF& r = W.r;
+		const RtBvhNode* np = S.bvh_nodes + W.stack[--W.sp];
+		const RtF4 n0 = ld(reinterpret_cast<const RtF4*>(np));
+		const RtI4 n1 = ld(reinterpret_cast<const RtI4*>(np) + 1);
+		// n0 = lo.xyz, hi.x ; n1 = hi.y, hi.z (as bits), a, b
+		const float hy = int_as_float(n1.x), hz = int_as_float(n1.y);
+		float ta = (n0.x - r.ox) * r.ix, tb = (n0.w - r.ox) * r.ix;
+		float tmin = fminf(ta, tb), tmax = fmaxf(ta, tb);
+		ta = (n0.y - r.oy) * r.iy; tb = (hy - r.oy) * r.iy;
+		tmin = fmaxf(tmin, fminf(ta, tb)); tmax = fminf(tmax, fmaxf(ta, tb));
+		ta = (n0.z - r.oz) * r.iz; tb = (hz - r.oz) * r.iz;
+		tmin = fmaxf(tmin, fminf(ta, tb)); tmax = fminf(tmax, fmaxf(ta, tb));
+		if (!(tmin > tmax + W.slack || tmax < -W.slack)) {  // (NaN from 0 * inf compares false: kept)
+			if (n1.w < 0) {
+				if (-(n1.w + 1) < W.best) {  // else: nothing below this node can beat the hit we have
+					W.stack[W.sp++] = n1.z + 1;
+					W.stack[W.sp++] = n1.z;  // the child with the lowest slot first
+				}
+			} else {
+				leaf_a = n1.z;
+				leaf_n = n1.w;
+			}
+		}
+	}
+	if (LOCKSTEP) warp_sync();
+	// ---- leaf entries, ascending slots
+	for (int k = 0; k < leaf_n; k++) {
+		const int s = ld(S.bvh_slots + leaf_a + k);
+		if (s >= W.best) break;
+		const RtF4 g = ld(S.bvh_geom + leaf_a + k);
+		if (candidate(g, W.r, S.err_l) && confirm_hit(S, s, g.w > 0.0f, o, d)) {
+			W.best = s;
+			break;
+		}
+	}
+	if (LOCKSTEP) warp_sync();
+	if (walking && W.in_list && W.sp == W.floor) {  // the list is finished
+		W.in_list = 0;
+		if (W.best != RT_NO_SLOT) {
+			W.hit = W.best;
+			walking = false;
+		}
+	}
+	return walking;
 }
 
 // ------------------------------------------------------------------ Ray.trace (src/raytracer.ts:168-277)
@@ -1182,7 +1266,7 @@ RT_HD bool path_finish(const RtDevScene& S, const RtFrame& F, RtPath& P, double*
 //   segment_begin  walker re-seed; returns RT_SEG_DONE (path ended, colour in `out`), RT_SEG_SLOT (`slot` and
 //                  `ci` are known: camera segment found by the primary stage, or searched right here with the
 //                  reference-order state machine when W == nullptr), or RT_SEG_WALK (W is set up: the caller
-//                  runs walk_step() until it returns false, then calls segment_found());
+//                  runs walk_iter() until it returns false, then calls segment_found());
 //   segment_end    the material's response to the hit (or the sky / light ending); true when the path ended.
 // `primary_slot`: the first-hit slot of the camera segment when the primary stage already found it (>= 0), or
 // RT_SLOT_UNKNOWN to search.
@@ -1220,7 +1304,7 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 	q.chain_levels = 0;
 	if (P.primary && F.prim_geom) q.rel = F.prim_geom;  // camera rays: origin-relative records
 	if (W) {
-		W->q = q;
+		W->r = q.r;
 		walk_begin(S, *W, P.node, P.octant);
 		return RT_SEG_WALK;
 	}
@@ -1354,7 +1438,7 @@ RT_HD bool path_segment(const RtDevScene& S, const RtFrame& F, RtPath& P, double
 		const int r = segment_begin<COUNT>(S, F, P, primary_slot, out, cnt, err, &W, slot, ci);
 		if (r == RT_SEG_DONE) return true;
 		if (r == RT_SEG_WALK) {
-			while (walk_step(S, W, P.refpoint, P.dir)) {
+			while (walk_iter<false>(S, W, P.refpoint, P.dir, true)) {
 			}
 			segment_found(S, P, W, slot, ci);
 		}
