@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 			if (nw > 0) {
 				const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
 				do {
-					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking);
+					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
 					nw = __popc(__ballot_sync(0xffffffffu, walking));
 				} while (nw >= limit);
 				if (st == RT_ST_WALK && !walking) st = RT_ST_END;
@@ -404,6 +404,7 @@ struct rt_ctx {
 	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
 	int ppl = RT_PPL;
 	int bounce_min_walking = 24;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
+	int bounce_node_batch = 8;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
 };
 
 namespace {
@@ -507,6 +508,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	F.tile_world = tile_world;
 	F.tile_compact = tile_compact ? 1 : 0;
 	F.bounce_min_walking = ctx->bounce_min_walking;
+	F.bounce_node_batch = ctx->bounce_node_batch;
 	// u64 cells: [0..7] work counters, [8] error flags, then per band {patch dispenser, queue count, queue cursor}
 	n_bands = std::max(1, std::min(n_bands, RT_MAX_BANDS));
 	const size_t n_cells = 9 + 3 * RT_MAX_BANDS;
@@ -709,6 +711,10 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	if (const char* e = getenv("RT_B200_BOUNCE_MIN")) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= 32) ctx->bounce_min_walking = v;
+	}
+	if (const char* e = getenv("RT_B200_NODE_BATCH")) {
+		const int v = atoi(e);
+		if (v >= 1 && v <= 32) ctx->bounce_node_batch = v;
 	}
 	if (const char* e = getenv("RT_B200_PPL")) {
 		const int v = atoi(e);

@@ -156,6 +156,7 @@ struct RtFrame {
 	unsigned* queue_count;   // items appended by the primary stage
 	unsigned* queue_taken;   // consumer cursor of the bounce stage
 	int bounce_min_walking;  // bounce stage: leave the lock-step walk when fewer lanes than this are still walking
+	int bounce_node_batch;   // bounce stage: lanes that need a node step wait until this many do
 };
 
 #define RT_ERRFLAG_TEXTURE 1u

@@ -109,7 +109,7 @@ inline void rt_build_list_bvhs(RtHostScene& hs) {
 			int axis = 0;
 			for (int k = 1; k < 3; k++)
 				if (cmax[k] - cmin[k] > cmax[axis] - cmin[axis]) axis = k;
-			if (count <= RT_BVH_LEAF || !(cmax[axis] > cmin[axis])) {
+			if (count <= RT_BVH_LEAF) {  // (leaves never hold more: the leaf test is unrolled over RT_BVH_LEAF entries)
 				std::sort(idx.begin() + j.beg, idx.begin() + j.end);  // ascending slots: list order within the leaf
 				nd.a = (int)hs.bvh_slots.size();
 				nd.b = count;
@@ -117,6 +117,7 @@ inline void rt_build_list_bvhs(RtHostScene& hs) {
 				for (int i = j.beg; i < j.end; i++) hs.bvh_geom.push_back(hs.slot_geom[idx[i]]);
 			} else {
 				const int mid = j.beg + count / 2;
+				// (coincident centres: the comparator falls back to the slot numbers, any split is as good)
 				std::nth_element(idx.begin() + j.beg, idx.begin() + mid, idx.begin() + j.end, [&](int p, int q) {
 					const double a = axis == 0 ? hs.slot_geom64[p].x : axis == 1 ? hs.slot_geom64[p].y : hs.slot_geom64[p].z;
 					const double b = axis == 0 ? hs.slot_geom64[q].x : axis == 1 ? hs.slot_geom64[q].y : hs.slot_geom64[q].z;

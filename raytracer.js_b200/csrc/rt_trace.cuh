@@ -635,6 +635,22 @@ RT_HD int popc32(unsigned m) {
 	return __builtin_popcount(m);
 #endif
 }
+RT_HD int clz32(unsigned m) {  // m != 0
+#if defined(__CUDACC__)
+	return __clz((int)m);
+#else
+	return __builtin_clz(m);
+#endif
+}
+// vote of a predicate over the warp; the host build (and ray-by-ray device callers, which pass LOCKSTEP =
+// false and never reach it) see a single lane
+RT_HD unsigned lane_vote(bool p) {
+#if defined(__CUDACC__)
+	return __ballot_sync(0xffffffffu, p);
+#else
+	return p ? 1u : 0u;
+#endif
+}
 RT_HD int ffs32(unsigned m) {  // index of the lowest set bit, m != 0
 #if defined(__CUDACC__)
 	return __ffs((int)m) - 1;
@@ -1067,39 +1083,50 @@ struct RtWalk {
 
 // pushes the children of `nd` the ray may pierce, last-visited first.  In the ray's own frame (axis k
 // mirrored when d_k < 0) the half of the cube entered first is "half 0": key bit k of a child says which
-// half it is in, so the parameter interval of a child is a static selection among three plane parameters
-// per axis.
+// half it is in, so the parameter interval of a child is a static selection among the intervals of the two
+// halves per axis.  The eight interval tests are predicates only (no branches); the loop runs once per child
+// actually pushed.
 RT_HD void walk_push_children(RtWalk& W, const RtPNode& nd, int after_oct) {
-	if (!nd.child_mask) return;
 	const RtRayF& r = W.r;
 	const float h = nd.size * 0.5f;
-	float t0[3], tm[3], t1[3];  // entry plane, mid plane, exit plane along the direction of travel
+	float n0[3], f0[3], n1[3], f1[3];  // [near, far] of half 0 and of half 1, per axis
 	{
 		const float lo[3] = {nd.x, nd.y, nd.z}, o[3] = {r.ox, r.oy, r.oz}, inv[3] = {r.ix, r.iy, r.iz};
 #pragma unroll
 		for (int k = 0; k < 3; k++) {
-			const float ta = (lo[k] - o[k]) * inv[k], tb = (lo[k] + nd.size - o[k]) * inv[k];
-			tm[k] = (lo[k] + h - o[k]) * inv[k];
-			t0[k] = fminf(ta, tb);  // (NaN from 0 * inf is dropped by fminf / fmaxf)
-			t1[k] = fmaxf(ta, tb);
-			// a zero component: the ray stays in the half that holds its origin; both halves keep the whole
-			// interval (conservative), +-inf parameters order themselves
+			const bool ng = (W.neg >> k) & 1;
+			const float te = ((ng ? lo[k] + nd.size : lo[k]) - o[k]) * inv[k];  // entry plane
+			const float tm = (lo[k] + h - o[k]) * inv[k];                        // mid plane
+			const float tx = ((ng ? lo[k] : lo[k] + nd.size) - o[k]) * inv[k];  // exit plane
+			// sorted pairs: robust against zero components of either sign (+-inf parameters), and NaN from
+			// 0 * inf is dropped by fminf / fmaxf (the half then keeps the other bound: conservative)
+			n0[k] = fminf(te, tm); f0[k] = fmaxf(te, tm);
+			n1[k] = fminf(tm, tx); f1[k] = fmaxf(tm, tx);
 		}
 	}
-	const int want = after_oct >= 0 ? (after_oct ^ W.neg) : 0;
-	const unsigned mask_k = xor_permute8((unsigned)nd.child_mask, W.neg);  // bit key = child of octant key ^ neg exists
+	// x/y combinations shared by the two z halves
+	const float nxy[4] = {fmaxf(n0[0], n0[1]), fmaxf(n1[0], n0[1]), fmaxf(n0[0], n1[1]), fmaxf(n1[0], n1[1])};
+	const float fxy[4] = {fminf(f0[0], f0[1]), fminf(f1[0], f0[1]), fminf(f0[0], f1[1]), fminf(f1[0], f1[1])};
+	const float nz[2] = {fmaxf(n0[2], 0.0f), fmaxf(n1[2], 0.0f)};
+	const float fz[2] = {f0[2], f1[2]};
+	unsigned m = 0;
 #pragma unroll
-	for (int key = 7; key >= 0; key--) {
-		if (!((mask_k >> key) & 1u) || (key & want) != want) continue;
+	for (int key = 0; key < 8; key++) {
+		const float tnear = fmaxf(nxy[key & 3], nz[key >> 2]);
+		const float tfar = fminf(fxy[key & 3], fz[key >> 2]);
+		m |= (tnear <= tfar * 1.00001f + W.slack ? 1u : 0u) << key;
+	}
+	m &= xor_permute8((unsigned)nd.child_mask, W.neg);  // bit key = the child of octant key ^ neg exists
+	if (after_oct >= 0) {
+		// only the octants a ray can still reach from after_oct: keys that are proper supersets of its key
+		const int want = after_oct ^ W.neg;
+		m &= ((want & 1) ? 0xaau : 0xffu) & ((want & 2) ? 0xccu : 0xffu) & ((want & 4) ? 0xf0u : 0xffu) & ~(1u << want);
+	}
+	while (m && W.sp < RT_WALK_STACK) {
+		const int key = 31 - clz32(m);
+		m ^= 1u << key;
 		const int o = key ^ W.neg;
-		if (o == after_oct) continue;
-		const float nx = (key & 1) ? fminf(tm[0], t1[0]) : fminf(t0[0], tm[0]), fx = (key & 1) ? fmaxf(tm[0], t1[0]) : fmaxf(t0[0], tm[0]);
-		const float ny = (key & 2) ? fminf(tm[1], t1[1]) : fminf(t0[1], tm[1]), fy = (key & 2) ? fmaxf(tm[1], t1[1]) : fmaxf(t0[1], tm[1]);
-		const float nz = (key & 4) ? fminf(tm[2], t1[2]) : fminf(t0[2], tm[2]), fz = (key & 4) ? fmaxf(tm[2], t1[2]) : fmaxf(t0[2], tm[2]);
-		const float tnear = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
-		const float tfar = fminf(fminf(fx, fy), fz);
-		if (tnear <= tfar * 1.00001f + W.slack && W.sp < RT_WALK_STACK)
-			W.stack[W.sp++] = nd.child_base + popc32((unsigned)nd.child_mask & ((1u << o) - 1u));
+		W.stack[W.sp++] = nd.child_base + popc32((unsigned)nd.child_mask & ((1u << o) - 1u));
 	}
 }
 
@@ -1131,9 +1158,15 @@ RT_HD bool confirm_hit(const RtDevScene& S, int s, bool is_sphere, const double*
 // (bounce stage) and the phases re-converge the warp between them; without it the caller may be one lane of a
 // diverged warp (ray-by-ray kernels) and no warp-wide barrier is used.
 template <bool LOCKSTEP>
-RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const double* d, bool walking) {
-	// ---- node step
-	if (walking && !W.in_list) {
+RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const double* d, bool walking, int node_batch = 1) {
+	// ---- node step.  It is several times the cost of a list step, so in lock-step the lanes that need one
+	// wait until `node_batch` of them do (or no lane is inside a list), and then take it together.
+	bool node_step = walking && !W.in_list;
+	if (LOCKSTEP) {
+		const unsigned need = lane_vote(node_step), busy = lane_vote(walking && W.in_list);
+		if (busy != 0u && popc32(need) < node_batch) node_step = false;
+	}
+	if (node_step) {
 		int push_node = -1, after = -1, list_of = -1;
 		if (W.sp > 0) {
 			push_node = list_of = W.stack[--W.sp];
@@ -1191,14 +1224,27 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 		}
 	}
 	if (LOCKSTEP) warp_sync();
-	// ---- leaf entries, ascending slots
-	for (int k = 0; k < leaf_n; k++) {
-		const int s = ld(S.bvh_slots + leaf_a + k);
-		if (s >= W.best) break;
-		const RtF4 g = ld(S.bvh_geom + leaf_a + k);
-		if (candidate(g, W.r, S.err_l) && confirm_hit(S, s, g.w > 0.0f, o, d)) {
-			W.best = s;
-			break;
+	// ---- leaf entries, ascending slots: the float32 tests of all (up to RT_BVH_LEAF = 4) entries first -
+	// independent loads -, then the float64 confirmation of the candidates in slot order
+	if (leaf_n) {
+		unsigned cand = 0, spheres = 0;
+#pragma unroll
+		for (int k = 0; k < RT_BVH_LEAF; k++) {
+			if (k < leaf_n) {
+				const RtF4 g = ld(S.bvh_geom + leaf_a + k);
+				cand |= (candidate(g, W.r, S.err_l) ? 1u : 0u) << k;
+				spheres |= (g.w > 0.0f ? 1u : 0u) << k;
+			}
+		}
+		while (cand) {
+			const int k = ffs32(cand);
+			cand &= cand - 1;
+			const int s = ld(S.bvh_slots + leaf_a + k);
+			if (s >= W.best) break;
+			if (confirm_hit(S, s, (spheres >> k) & 1u, o, d)) {
+				W.best = s;
+				break;
+			}
 		}
 	}
 	if (LOCKSTEP) warp_sync();
