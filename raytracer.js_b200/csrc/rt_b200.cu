@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(256)
 #define RT_ST_BEGIN 1
 #define RT_ST_WALK 2
 #define RT_ST_END 3
-__global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
+template <int MINB>
+__global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
     rt_bounce_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
@@ -374,6 +375,7 @@ struct rt_ctx {
 	DevBuf<RtI4> node_link;
 	DevBuf<int> node_child;
 	DevBuf<RtPNode> node_pk;
+	DevBuf<RtWNode> node_walk;
 	DevBuf<int> node_bvh;
 	DevBuf<RtBvhNode> bvh_nodes;
 	DevBuf<int> bvh_slots;
@@ -404,6 +406,7 @@ struct rt_ctx {
 	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
 	int ppl = RT_PPL;
 	int bounce_min_walking = 24;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
+	int bounce_minb = 4;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
 	int bounce_node_batch = 8;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
 };
 
@@ -556,10 +559,14 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	const int ppl = ctx->ppl;
 	const void* primary_kernel = ppl == 1 ? (const void*)rt_primary_kernel<1> : ppl == 2 ? (const void*)rt_primary_kernel<2>
 	                           : ppl == 4 ? (const void*)rt_primary_kernel<4> : (const void*)rt_primary_kernel<8>;
+	// resident CTAs per SM the bounce stage is compiled for (tuning knob: RT_B200_BOUNCE_MINB=4|5|6|8)
+	const int minb = ctx->bounce_minb;
+	const void* bounce_kernel = minb == 4 ? (const void*)rt_bounce_kernel<4> : minb == 5 ? (const void*)rt_bounce_kernel<5>
+	                          : minb == 6 ? (const void*)rt_bounce_kernel<6> : (const void*)rt_bounce_kernel<8>;
 	int grid_primary = 0, grid_bounce = 0, grid_ray = 0;
 	if (pipeline) {
 		if (rt_status st = grid_of(4 + (ppl == 1 ? 0 : ppl == 2 ? 1 : ppl == 4 ? 2 : 3), primary_kernel, RT_A_WARPS * 32, grid_primary)) return st;
-		if (rt_status st = grid_of(3, (const void*)rt_bounce_kernel, RT_WARPS_PER_CTA * 32, grid_bounce)) return st;
+		if (rt_status st = grid_of(3, bounce_kernel, RT_WARPS_PER_CTA * 32, grid_bounce)) return st;
 	} else if (count) {
 		if (rt_status st = grid_of(1, (const void*)rt_render_kernel<true>, RT_WARPS_PER_CTA * 32, grid_ray)) return st;
 	} else {
@@ -606,8 +613,9 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				rt_shade_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_out);
 				ctx->launches++;
 				RT_CUDA(ctx, cudaGetLastError());
-				rt_bounce_kernel<<<std::min(grid_bounce, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
-				                   ctx->stream>>>(ctx->dev, F, tiles_x);
+				void* bargs[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x};
+				RT_CUDA(ctx, cudaLaunchKernel(bounce_kernel, dim3(std::min(grid_bounce, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA)),
+				                              dim3(RT_WARPS_PER_CTA * 32), bargs, 0, ctx->stream));
 			} else if (count) {
 				rt_render_kernel<true><<<std::min(grid_ray, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
 				                         ctx->stream>>>(ctx->dev, F, tiles_x, n_patches);
@@ -712,6 +720,10 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= 32) ctx->bounce_min_walking = v;
 	}
+	if (const char* e = getenv("RT_B200_BOUNCE_MINB")) {
+		const int v = atoi(e);
+		if (v == 4 || v == 5 || v == 6 || v == 8) ctx->bounce_minb = v;
+	}
 	if (const char* e = getenv("RT_B200_NODE_BATCH")) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= 32) ctx->bounce_node_batch = v;
@@ -728,7 +740,7 @@ void rt_destroy(rt_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release(); ctx->bvh_geom.release();
+	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_walk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release(); ctx->bvh_geom.release();
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
@@ -808,7 +820,7 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	const RtHostScene& H = ctx->host;
 	rt_status st;
 	if ((st = upload(ctx, ctx->node_geom, H.node_geom)) || (st = upload(ctx, ctx->node_link, H.node_link)) ||
-	    (st = upload(ctx, ctx->node_child, H.node_child)) || (st = upload(ctx, ctx->node_pk, H.node_pk)) || (st = upload(ctx, ctx->node_bvh, H.node_bvh)) ||
+	    (st = upload(ctx, ctx->node_child, H.node_child)) || (st = upload(ctx, ctx->node_pk, H.node_pk)) || (st = upload(ctx, ctx->node_walk, H.node_walk)) || (st = upload(ctx, ctx->node_bvh, H.node_bvh)) ||
 	    (st = upload(ctx, ctx->bvh_nodes, H.bvh_nodes)) || (st = upload(ctx, ctx->bvh_slots, H.bvh_slots)) || (st = upload(ctx, ctx->bvh_geom, H.bvh_geom)) || (st = upload(ctx, ctx->slot_geom, H.slot_geom)) ||
 	    (st = upload(ctx, ctx->slot_geom64, H.slot_geom64)) || (st = upload(ctx, ctx->slot_attr, H.slot_attr)) ||
 	    (st = upload(ctx, ctx->materials, H.materials)) || (st = upload(ctx, ctx->textures, H.textures)) ||
@@ -816,7 +828,7 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 		return st;
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	RtDevScene& D = ctx->dev;
-	D.node_geom = ctx->node_geom.p; D.node_link = ctx->node_link.p; D.node_child = ctx->node_child.p; D.node_pk = ctx->node_pk.p; D.node_bvh = ctx->node_bvh.p; D.bvh_nodes = ctx->bvh_nodes.p; D.bvh_slots = ctx->bvh_slots.p; D.bvh_geom = ctx->bvh_geom.p;
+	D.node_geom = ctx->node_geom.p; D.node_link = ctx->node_link.p; D.node_child = ctx->node_child.p; D.node_pk = ctx->node_pk.p; D.node_walk = ctx->node_walk.p; D.node_bvh = ctx->node_bvh.p; D.bvh_nodes = ctx->bvh_nodes.p; D.bvh_slots = ctx->bvh_slots.p; D.bvh_geom = ctx->bvh_geom.p;
 	D.slot_geom = ctx->slot_geom.p; D.slot_geom64 = ctx->slot_geom64.p; D.slot_attr = ctx->slot_attr.p;
 	D.materials = ctx->materials.p; D.textures = ctx->textures.p; D.substances = ctx->substances.p;
 	D.texels = ctx->texels.p;

@@ -35,6 +35,17 @@ struct alignas(32) RtPNode {
 	int child_base, child_mask;
 };
 
+// Octree node record of the bounce stage's ordered walk: the cube, the children (breadth-first numbering, as
+// in RtPNode), the root of the list's BVH and the way up.  Same size and box-first layout as RtBvhNode, so a
+// lane of the walk runs one kind of step - load 32 bytes, slab test, expand - on either.
+struct alignas(32) RtWNode {
+	float x, y, z, size;
+	int child_base, child_mask;
+	int bvh_root;  // root of the list's BVH in bvh_nodes, -1: empty list
+	int up;        // parent | index_within_parent << 28, -1: root
+};
+#define RT_WNODE_PARENT_MASK 0x0fffffff
+
 // Per-list bounding volume hierarchy.  The reference scans a node's entity list linearly and takes the FIRST
 // entity (in insertion order) the ray hits; any structure that finds every hit entity of the list and keeps
 // the lowest slot gives the same answer.  Every non-empty list has a binary BVH over the entities' float32
@@ -45,12 +56,14 @@ struct alignas(32) RtPNode {
 struct alignas(16) RtBvhNode {
 	float lo[3], hi[3];
 	int a;  // inner: index of the left child (right = a + 1), the left one holds the lowest slot;
-	        // leaf: first entry in bvh_slots / bvh_geom
+	        // leaf: first entry in bvh_slots / bvh_geom (a multiple of RT_BVH_LEAF: leaves are padded to
+	        // RT_BVH_LEAF entries, the padding carries slot RT_NO_SLOT)
 	int b;  // inner: -(lowest slot below this node + 1) (< 0); leaf: number of entries (> 0), ascending slots
 };
 #define RT_BVH_MIN_LIST 24
 #define RT_BVH_LEAF 4
 #define RT_BVH_STACK 40
+#define RT_NO_SLOT 0x7fffffff
 
 // material flags
 #define RT_MAT_RESPONSE_MASK 3u
@@ -81,6 +94,7 @@ struct RtDevScene {
 	const RtI4* node_link;   // parent, index_within_parent, list_off, list_cnt
 	const int* node_child;   // [n*8], -1 none
 	const RtPNode* node_pk;  // the same nodes as one 32-byte record each, for the packet walk
+	const RtWNode* node_walk; // ... and for the bounce stage's ordered walk
 	const int* node_bvh;     // [n] root of the node's list BVH in bvh_nodes, or -1 (short list)
 	const RtBvhNode* bvh_nodes;
 	const int* bvh_slots;    // leaf entries: slot numbers

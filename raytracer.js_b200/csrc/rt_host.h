@@ -18,6 +18,7 @@ struct RtHostScene {
 	std::vector<RtI4> node_link;
 	std::vector<int> node_child;
 	std::vector<RtPNode> node_pk;
+	std::vector<RtWNode> node_walk;
 	std::vector<int> node_bvh;
 	std::vector<RtBvhNode> bvh_nodes;
 	std::vector<int> bvh_slots;
@@ -113,8 +114,11 @@ inline void rt_build_list_bvhs(RtHostScene& hs) {
 				std::sort(idx.begin() + j.beg, idx.begin() + j.end);  // ascending slots: list order within the leaf
 				nd.a = (int)hs.bvh_slots.size();
 				nd.b = count;
-				hs.bvh_slots.insert(hs.bvh_slots.end(), idx.begin() + j.beg, idx.begin() + j.end);
-				for (int i = j.beg; i < j.end; i++) hs.bvh_geom.push_back(hs.slot_geom[idx[i]]);
+				for (int i = 0; i < RT_BVH_LEAF; i++) {  // padded to RT_BVH_LEAF entries (finite geometry, slot = none)
+					const bool real = j.beg + i < j.end;
+					hs.bvh_slots.push_back(real ? idx[j.beg + i] : RT_NO_SLOT);
+					hs.bvh_geom.push_back(hs.slot_geom[idx[real ? j.beg + i : j.beg]]);
+				}
 			} else {
 				const int mid = j.beg + count / 2;
 				// (coincident centres: the comparator falls back to the slot numbers, any split is as good)
@@ -135,13 +139,22 @@ inline void rt_build_list_bvhs(RtHostScene& hs) {
 		}
 	}
 	if (hs.bvh_nodes.empty()) hs.bvh_nodes.push_back(RtBvhNode{});
-	if (hs.bvh_slots.empty()) hs.bvh_slots.push_back(0);
-	if (hs.bvh_geom.empty()) hs.bvh_geom.push_back(RtF4{0, 0, 0, 0});
+	if (hs.bvh_slots.empty()) hs.bvh_slots.assign(RT_BVH_LEAF, RT_NO_SLOT);
+	if (hs.bvh_geom.empty()) hs.bvh_geom.assign(RT_BVH_LEAF, RtF4{0, 0, 0, 0});
+	// the walk records (rt_common.h: RtWNode)
+	hs.node_walk.resize(N);
+	for (size_t n = 0; n < N; n++) {
+		const RtPNode& pk = hs.node_pk[n];
+		const RtI4& link = hs.node_link[n];
+		hs.node_walk[n] = RtWNode{pk.x, pk.y, pk.z, pk.size, pk.child_base, pk.child_mask, hs.node_bvh[n],
+		                          link.x < 0 ? -1 : (int)((unsigned)link.x | ((unsigned)link.y << 28))};
+	}
 }
 
 // 1 when the stack of the bounce stage's ordered walk (RT_WALK_STACK entries) holds the deepest case: up to 7
 // siblings per octree level + 8, and one list BVH on top (depth + 1 entries, binary DFS)
 inline int rt_ordered_walk_fits(const RtHostScene& hs) {
+	if (hs.node_link.size() > (size_t)RT_WNODE_PARENT_MASK) return 0;  // RtWNode.up packs the parent in 28 bits
 	return 7 * hs.max_depth + 8 + hs.max_bvh_depth + 2 <= RT_WALK_STACK ? 1 : 0;
 }
 

@@ -734,6 +734,16 @@ RT_HD RtPNode ld(const RtPNode* p) {
 #endif
 }
 
+RT_HD RtWNode ld(const RtWNode* p) {
+#if defined(__CUDACC__)
+	const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+	const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+	return RtWNode{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#else
+	return *p;
+#endif
+}
+
 // Geometry of a packet: RT_PPL rays per lane, ray j of lane `lane` is the pixel (lane & 7, lane >> 3) of
 // the j-th 8x4 sub-patch; sub-patch q of a 16x16 tile sits at (8 * (q & 1), 4 * (q >> 1)).
 struct RtPatch {
@@ -1065,7 +1075,6 @@ RT_HD double rng_next(RtRng& g) {
 // The list BVH sits on top of the octree entries, so a list is finished before the next node is popped, and
 // the walk ends at the first list that holds a hit.  A conservative (slack) pierce test can only add nodes,
 // which cannot change a first hit (entities lie inside their node's cube).
-#define RT_NO_SLOT 0x7fffffff
 struct RtWalk {
 	RtRayF r;
 	int neg;          // bit k: d_k < 0
@@ -1075,6 +1084,7 @@ struct RtWalk {
 	int chain_node;   // origin-chain node whose list is returned once the stack is empty
 	int chain_oct;    // octant of chain_node the ray leaves (its children before it cannot be reached); < 0: root only
 	int chain_listed; // 1: chain_node's list has been scanned, next is its parent
+	int chain_up;     // RtWNode.up of chain_node (known once its list has been started)
 	int best;         // lowest hit slot of the current list, RT_NO_SLOT while none
 	int hit;          // result: first-hit slot, -1 none
 	float slack;
@@ -1086,7 +1096,7 @@ struct RtWalk {
 // half it is in, so the parameter interval of a child is a static selection among the intervals of the two
 // halves per axis.  The eight interval tests are predicates only (no branches); the loop runs once per child
 // actually pushed.
-RT_HD void walk_push_children(RtWalk& W, const RtPNode& nd, int after_oct) {
+RT_HD void walk_push_children(RtWalk& W, const RtWNode& nd, int after_oct) {
 	const RtRayF& r = W.r;
 	const float h = nd.size * 0.5f;
 	float n0[3], f0[3], n1[3], f1[3];  // [near, far] of half 0 and of half 1, per axis
@@ -1143,7 +1153,8 @@ RT_HD void walk_begin(const RtDevScene& S, RtWalk& W, int node, int octant) {
 	W.chain_node = node;
 	W.chain_oct = octant;
 	W.chain_listed = 0;
-	if (octant >= 0) walk_push_children(W, ld(S.node_pk + node), octant);
+	W.chain_up = -1;
+	if (octant >= 0) walk_push_children(W, ld(S.node_walk + node), octant);
 }
 
 // float64 confirmation without the collision record (the caller recomputes it for the one slot it keeps)
@@ -1151,6 +1162,19 @@ RT_HD bool confirm_hit(const RtDevScene& S, int s, bool is_sphere, const double*
 	RtCollision col;
 	const RtD4 g = ld(S.slot_geom64 + s);
 	return is_sphere ? exact_sphere(g, o, d, col) : exact_box(g, o, d, col);
+}
+
+// candidate() on the bounding sphere of the entity (the sphere itself, or the sphere around a box): one
+// branch-free test for the entries of a leaf
+RT_HD bool candidate_bounding(const RtF4& g, const RtRayF& r, float err_l) {
+	const float cx = g.x - r.ox, cy = g.y - r.oy, cz = g.z - r.oz;
+	const float tca = cx * r.dx + cy * r.dy + cz * r.dz;
+	const float sc = tca * r.inv_a;
+	const float lx = cx - sc * r.dx, ly = cy - sc * r.dy, lz = cz - sc * r.dz;
+	const float l2 = lx * lx + ly * ly + lz * lz;
+	const float rr = (g.w > 0.0f ? g.w : g.w * -1.7320526f) + err_l;
+	const float rr2 = rr * rr;
+	return l2 <= rr2 && (tca >= 0.0f || cx * cx + cy * cy + cz * cz <= rr2);
 }
 
 // One iteration of the walk for every lane of the warp (`walking`: this lane takes part).  Returns false
@@ -1166,33 +1190,38 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 		const unsigned need = lane_vote(node_step), busy = lane_vote(walking && W.in_list);
 		if (busy != 0u && popc32(need) < node_batch) node_step = false;
 	}
+	// (a) which node: the next one on the stack, or - stack empty - the next move along the origin chain
+	int rec_node = -1, after = -1;
+	bool push = false, list = false;
 	if (node_step) {
-		int push_node = -1, after = -1, list_of = -1;
 		if (W.sp > 0) {
-			push_node = list_of = W.stack[--W.sp];
+			rec_node = W.stack[--W.sp];
+			push = list = true;
 		} else if (!W.chain_listed) {
-			// stack empty: the ray leaves the current origin-chain node, which is returned now (post-order)
+			// the ray leaves the current origin-chain node, which is returned now (post-order)
 			W.chain_listed = 1;
-			list_of = W.chain_node;
+			rec_node = W.chain_node;
+			list = true;
+		} else if (W.chain_oct < 0 || W.chain_up < 0) {
+			walking = false;  // root-only mode, or the root has been returned: miss
 		} else {
-			const RtI4 link = ld(S.node_link + W.chain_node);
-			if (W.chain_oct < 0 || link.x < 0) {
-				walking = false;  // root-only mode, or the root has been returned: miss
-			} else {
-				W.chain_node = push_node = link.x;
-				W.chain_oct = after = link.y;
-				W.chain_listed = 0;
-			}
+			W.chain_node = rec_node = W.chain_up & RT_WNODE_PARENT_MASK;
+			W.chain_oct = after = (int)((unsigned)W.chain_up >> 28);
+			W.chain_listed = 0;
+			push = true;
 		}
-		if (push_node >= 0) walk_push_children(W, ld(S.node_pk + push_node), after);
-		if (list_of >= 0) {
-			const int root = ld(S.node_bvh + list_of);
-			if (root >= 0) {
-				W.floor = W.sp;
-				W.stack[W.sp++] = root;  // (room for the list BVH is part of RT_WALK_STACK: rt_ordered_walk_fits)
-				W.in_list = 1;
-				W.best = RT_NO_SLOT;
-			}
+	}
+	if (LOCKSTEP) warp_sync();
+	// (b) its record: children, list
+	if (rec_node >= 0) {
+		const RtWNode nd = ld(S.node_walk + rec_node);
+		if (push) walk_push_children(W, nd, after);
+		else W.chain_up = nd.up;
+		if (list && nd.bvh_root >= 0) {
+			W.floor = W.sp;
+			W.stack[W.sp++] = nd.bvh_root;  // (room for the list BVH is part of RT_WALK_STACK: rt_ordered_walk_fits)
+			W.in_list = 1;
+			W.best = RT_NO_SLOT;
 		}
 	}
 	if (LOCKSTEP) warp_sync();
@@ -1224,25 +1253,24 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 		}
 	}
 	if (LOCKSTEP) warp_sync();
-	// ---- leaf entries, ascending slots: the float32 tests of all (up to RT_BVH_LEAF = 4) entries first -
-	// independent loads -, then the float64 confirmation of the candidates in slot order
+	// ---- leaf entries (padded to RT_BVH_LEAF, ascending slots): the float32 tests of all of them first -
+	// independent loads, no branches -, then the float64 confirmation of the candidates in slot order
 	if (leaf_n) {
+		const RtI4 sl = ld(reinterpret_cast<const RtI4*>(S.bvh_slots + leaf_a));
+		const int slots[RT_BVH_LEAF] = {sl.x, sl.y, sl.z, sl.w};
 		unsigned cand = 0, spheres = 0;
 #pragma unroll
 		for (int k = 0; k < RT_BVH_LEAF; k++) {
-			if (k < leaf_n) {
-				const RtF4 g = ld(S.bvh_geom + leaf_a + k);
-				cand |= (candidate(g, W.r, S.err_l) ? 1u : 0u) << k;
-				spheres |= (g.w > 0.0f ? 1u : 0u) << k;
-			}
+			const RtF4 g = ld(S.bvh_geom + leaf_a + k);
+			cand |= (slots[k] < W.best && candidate_bounding(g, W.r, S.err_l) ? 1u : 0u) << k;
+			spheres |= (g.w > 0.0f ? 1u : 0u) << k;
 		}
 		while (cand) {
 			const int k = ffs32(cand);
 			cand &= cand - 1;
-			const int s = ld(S.bvh_slots + leaf_a + k);
-			if (s >= W.best) break;
+			const int s = k == 0 ? slots[0] : k == 1 ? slots[1] : k == 2 ? slots[2] : slots[3];
 			if (confirm_hit(S, s, (spheres >> k) & 1u, o, d)) {
-				W.best = s;
+				W.best = s;  // ascending slots: the later candidates of this leaf cannot beat it
 				break;
 			}
 		}

@@ -35,7 +35,7 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 	std::vector<RtD4> row;
 	rt_build_camera_tables(*cam, col, row);
 	RtDevScene S{};
-	S.node_geom = hs.node_geom.data(); S.node_link = hs.node_link.data(); S.node_child = hs.node_child.data(); S.node_pk = hs.node_pk.data(); S.node_bvh = hs.node_bvh.data(); S.bvh_nodes = hs.bvh_nodes.data(); S.bvh_slots = hs.bvh_slots.data(); S.bvh_geom = hs.bvh_geom.data();
+	S.node_geom = hs.node_geom.data(); S.node_link = hs.node_link.data(); S.node_child = hs.node_child.data(); S.node_pk = hs.node_pk.data(); S.node_walk = hs.node_walk.data(); S.node_bvh = hs.node_bvh.data(); S.bvh_nodes = hs.bvh_nodes.data(); S.bvh_slots = hs.bvh_slots.data(); S.bvh_geom = hs.bvh_geom.data();
 	S.slot_geom = hs.slot_geom.data(); S.slot_geom64 = hs.slot_geom64.data(); S.slot_attr = hs.slot_attr.data();
 	S.materials = hs.materials.data(); S.textures = hs.textures.data(); S.substances = hs.substances.data();
 	S.texels = hs.texels.data();
