@@ -107,14 +107,20 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, RT_A_MINB)
 // Shade stage: one thread per pixel of this rank (output order, coalesced).  Turns the first-hit slot into
 // the pixel's colour when the path ends there (miss -> sky, diffuse, light, ...: primary_terminal), else
 // appends the pixel to the continuation queue with one warp-aggregated atomic.
+// The colours leave through shared memory: 16 consecutive pixels are 192 contiguous bytes of the frame, which
+// 12 lanes store as whole 16-byte words - full sectors instead of three strided 4-byte stores per lane, which
+// is what matters when the frame lives in another GPU's memory (rt_render_shard_device: every store is an
+// NVLink write).
 __global__ void __launch_bounds__(256)
     rt_shade_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, size_t n_out) {
+	__shared__ __align__(16) float stage[256 * 3];
 	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	size_t i = F.out_first + t;
 	const int lane = threadIdx.x & 31;
 	uint32_t err = 0;
-	bool enqueue = false;
-	int x = 0, y = 0, slot = -1;
+	bool enqueue = false, done = false;
+	int x = 0, y = 0, slot = -1, first_entity = -1;
+	float px[3] = {0.f, 0.f, 0.f};
 	if (t < n_out) {
 		bool valid = true;
 		if (F.tile_compact || F.tile_world > 1) {
@@ -133,8 +139,30 @@ __global__ void __launch_bounds__(256)
 		}
 		if (valid) {
 			slot = F.hit_slots[i];
-			enqueue = slot == RT_SLOT_UNKNOWN || !primary_finish(S, F, x, y, slot, i, err);
+			done = slot != RT_SLOT_UNKNOWN && primary_finish_px(S, F, x, y, slot, i, err, px, first_entity);
+			enqueue = !done;
 		}
+	}
+	// ---- colours: 16 pixels at a time
+	{
+		const int l16 = lane & 15;
+		const unsigned half = 0xffffu << (lane & 16);
+		const unsigned long long base = __shfl_sync(0xffffffffu, (unsigned long long)i, lane & 16);
+		const bool in_run = done && i == base + (unsigned)l16;
+		const bool wide = (__ballot_sync(0xffffffffu, in_run) & half) == half && (base & 3ull) == 0 &&
+		                  (reinterpret_cast<uintptr_t>(F.rgb) & 15u) == 0;
+		if (wide) {
+			stage[threadIdx.x * 3] = px[0]; stage[threadIdx.x * 3 + 1] = px[1]; stage[threadIdx.x * 3 + 2] = px[2];
+		}
+		__syncwarp();
+		if (wide) {
+			if (l16 < 12)
+				reinterpret_cast<float4*>(F.rgb + base * 3)[l16] = reinterpret_cast<const float4*>(stage + (threadIdx.x & ~15) * 3)[l16];
+		} else if (done) {
+			float* o = F.rgb + i * 3;
+			o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
+		}
+		if (done && F.first_ids) F.first_ids[i] = first_entity;
 	}
 	const unsigned m = __ballot_sync(0xffffffffu, enqueue);
 	if (m) {
@@ -576,11 +604,15 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	// ---- the stream work
 	const uint64_t launches_before = ctx->launches;
 	auto enqueue = [&]() -> rt_status {
-		RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, st_row, n_row * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
-		RT_CUDA(ctx, cudaMemcpyAsync(ctx->col_cs.p, st_col, n_col * sizeof(RtD2), cudaMemcpyHostToDevice, ctx->stream));
-		if (!capture) RT_CUDA(ctx, cudaEventRecord(ctx->stage_free, ctx->stream));
+		// A captured frame repeats the call before it (same camera, same scene): the scan tables and the
+		// origin-relative records that call left on the device are this frame's, so the graph holds neither.
+		if (!capture) {
+			RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, st_row, n_row * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
+			RT_CUDA(ctx, cudaMemcpyAsync(ctx->col_cs.p, st_col, n_col * sizeof(RtD2), cudaMemcpyHostToDevice, ctx->stream));
+			RT_CUDA(ctx, cudaEventRecord(ctx->stage_free, ctx->stream));
+		}
 		RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, n_cells * sizeof(unsigned long long), ctx->stream));
-		if (prim) {
+		if (prim && !capture) {
 			rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
 			                                                                         cam->pos[2], ctx->prim_geom.p);
 			ctx->launches++;

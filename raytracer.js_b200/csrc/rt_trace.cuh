@@ -1629,28 +1629,41 @@ RT_HD bool primary_terminal(const RtDevScene& S, const RtFrame& F, const double*
 }
 
 // ExposureBuffer.set_color_i (src/view/exposure_buffer.ts:77-91) for n_frames frames of the SAME sample
-// (a path that ends at its first hit never draws from the RNG, and there is no pixel jitter: SURVEY.md F6).
-RT_HD void store_constant_sample(const RtFrame& F, size_t out_index, const double* c, int first_entity) {
-	float* o = F.rgb + out_index * 3;
-	float px[3] = {0.f, 0.f, 0.f};
-	if (F.frame_first > 0) { px[0] = o[0]; px[1] = o[1]; px[2] = o[2]; }
+// (a path that ends at its first hit never draws from the RNG, and there is no pixel jitter: SURVEY.md F6):
+// the blended pixel in px (not stored yet).
+RT_HD void blend_constant_sample(const RtFrame& F, size_t out_index, const double* c, float* px) {
+	px[0] = px[1] = px[2] = 0.f;
+	if (F.frame_first > 0) {
+		const float* o = F.rgb + out_index * 3;
+		px[0] = o[0]; px[1] = o[1]; px[2] = o[2];
+	}
 	for (uint32_t f = 0; f < F.n_frames; f++) {
 		const double w = xdiv(1.0, (double)(1u + F.frame_first + f));
 		const double w1 = xsub(1.0, w);
 #pragma unroll
 		for (int k = 0; k < 3; k++) px[k] = (float)xadd(xmul(c[k], w), xmul((double)px[k], w1));
 	}
-	o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
-	if (F.first_ids) F.first_ids[out_index] = first_entity;
 }
 
-// Finishes pixel (x,y) if its path ends at the first hit `slot`; false: the bounce stage continues it.
-RT_HD bool primary_finish(const RtDevScene& S, const RtFrame& F, int x, int y, int slot, size_t out_index, uint32_t& err) {
+// The pixel (x,y) whose camera ray has the first hit `slot`, if its path ends there: blended colour in px and
+// the first-hit entity, nothing stored; false: the bounce stage continues it.
+RT_HD bool primary_finish_px(const RtDevScene& S, const RtFrame& F, int x, int y, int slot, size_t out_index, uint32_t& err,
+                             float* px, int& first_entity) {
 	double dir[3], c[3];
-	int first_entity;
 	pixel_dir(F, x, y, dir);
 	if (!primary_terminal(S, F, dir, slot, c, first_entity, err)) return false;
-	store_constant_sample(F, out_index, c, first_entity);
+	blend_constant_sample(F, out_index, c, px);
+	return true;
+}
+
+// ... and stored.
+RT_HD bool primary_finish(const RtDevScene& S, const RtFrame& F, int x, int y, int slot, size_t out_index, uint32_t& err) {
+	float px[3];
+	int first_entity;
+	if (!primary_finish_px(S, F, x, y, slot, out_index, err, px, first_entity)) return false;
+	float* o = F.rgb + out_index * 3;
+	o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
+	if (F.first_ids) F.first_ids[out_index] = first_entity;
 	return true;
 }
 

@@ -311,4 +311,6 @@ def test_repeated_device_renders_replay_a_graph():
         else:
             frames[name] = out.clone()
     assert not torch.equal(frames["a"], frames["b"])
-    assert len(set(launches)) == 1 and launches[0] >= 3, launches
+    # an eager call launches prepare + primary + shade + bounce; a replayed graph leaves out the per-camera
+    # preparation (the call it repeats left its result on the device)
+    assert min(launches) >= 3 and max(launches) - min(launches) <= 1 and launches[2] == launches[3], launches
