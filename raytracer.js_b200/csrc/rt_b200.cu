@@ -212,6 +212,12 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 	// change (it never drew from the RNG); then the next frame's path, or the end of the job
 	auto sample_done = [&](const double* c) {
 		const bool varies = P.rng.seeded;
+		if (varies && F.vqueue && F.n_frames > 1) {
+			// every frame of this pixel is a different path: the resample stage traces them 32 at a time
+			F.vqueue[atomicAdd(F.vqueue_count, 1u)] = RtQueueItem{((uint32_t)y << 16) | (uint32_t)x, slot};
+			st = RT_ST_IDLE;
+			return;
+		}
 		const uint32_t last = varies ? frame + 1 : F.n_frames;
 		for (; frame < last; frame++) {
 			const double w = xdiv(1.0, (double)(1u + F.frame_first + frame));
@@ -304,6 +310,139 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			if (hit >= 0 && !confirm_slot(S, hit, P.refpoint, P.dir, ci)) hit = -1;  // (same formula as in the search: cannot fail)
 			if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
 			else st = RT_ST_BEGIN;
+		}
+		__syncwarp();
+	}
+	if (err) atomicOr(F.error_flags, err);
+}
+
+// Resample stage (n_frames > 1).  A pixel whose path scatters off a rough surface is a different path in
+// every exposure frame, and ExposureBuffer.set_color_i (src/view/exposure_buffer.ts:77-91) blends the frames
+// one after the other into a float32 pixel.  One lane tracing all frames of such a pixel in a row is the
+// longest job of the whole render (n_frames x bounces walks of ~0.5 ms each) and would be its tail on any
+// number of GPUs.  Here the job is one (pixel, frame) sample: a warp takes a group of G pixels from the
+// resample queue (G x n_frames >= 256 samples when it can), its lanes run the bounce stage's state machine
+// over that pool - IDLE lanes take the next sample, BEGIN / lock-step WALK / END as in rt_bounce_kernel - and
+// park every path colour as float64 in the warp's sample buffer; when the pool is done, lane g blends the
+// samples of pixel g in frame order, so the pixel is the sequential one, bit for bit.
+#define RT_RESAMPLE_POOL 256
+template <int MINB>
+__global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
+    rt_resample_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
+	const int lane = threadIdx.x & 31;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const unsigned n = *F.vqueue_count;
+	const unsigned nf = F.n_frames;
+	const unsigned G = min(32u, max(1u, RT_RESAMPLE_POOL / nf));  // pixels per group
+	const size_t warp_id = (size_t)blockIdx.x * RT_WARPS_PER_CTA + (threadIdx.x >> 5);
+	double* const samples = F.samples + warp_id * F.samples_per_warp;  // [G][nf][3] behind a header of 32 ints
+	int* const group_entity = reinterpret_cast<int*>(samples);
+	double* const colour = samples + 16;
+	RtCounts cnt = {0, 0, 0, 0, 0};
+	uint32_t err = 0;
+	while (true) {
+		// ---- the next group of pixels
+		unsigned g0 = 0;
+		if (lane == 0) g0 = atomicAdd(F.vqueue_taken, G);
+		g0 = __shfl_sync(0xffffffffu, g0, 0);
+		if (g0 >= n) break;
+		const unsigned g_cnt = min(G, n - g0), pool = g_cnt * nf;
+		unsigned next = 0;  // warp-uniform cursor into the pool
+		int st = RT_ST_IDLE;
+		unsigned job = 0;
+		int x = 0, y = 0, slot = RT_SLOT_UNKNOWN;
+		RtPath P;
+		RtWalk W;
+		auto sample_done = [&](const double* c) {
+			double* o = colour + (size_t)job * 3;
+			o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
+			if (job % nf == 0) group_entity[job / nf] = P.first_entity;
+			st = RT_ST_IDLE;
+		};
+		while (true) {
+			// ---- idle lanes take the next samples of the pool
+			const unsigned idle = __ballot_sync(0xffffffffu, st == RT_ST_IDLE);
+			if (idle && next < pool) {
+				const unsigned j = next + (unsigned)__popc(idle & lt_mask);
+				next += (unsigned)__popc(idle);
+				if (st == RT_ST_IDLE && j < pool) {
+					job = j;
+					const RtQueueItem it = F.vqueue[g0 + j / nf];
+					x = (int)(it.xy & 0xffffu);
+					y = (int)(it.xy >> 16);
+					slot = it.slot;
+					double dir[3];
+					pixel_dir(F, x, y, dir);
+					path_begin(F, dir, P);
+					st = RT_ST_BEGIN;
+				}
+			}
+			if (__ballot_sync(0xffffffffu, st != RT_ST_IDLE) == 0u) break;
+			// ---- BEGIN: walker re-seed
+			if (st == RT_ST_BEGIN) {
+				double c[3];
+				int hit = -1;
+				RtCollision ci;
+				const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
+				if (r == RT_SEG_DONE) {
+					sample_done(c);
+				} else if (r == RT_SEG_WALK) {
+					st = RT_ST_WALK;
+				} else {
+					W.hit = hit;
+					st = RT_ST_END;
+				}
+			}
+			__syncwarp();
+			// ---- WALK in lock-step
+			{
+				bool walking = st == RT_ST_WALK;
+				int nw = __popc(__ballot_sync(0xffffffffu, walking));
+				if (nw > 0) {
+					const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
+					do {
+						walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
+						nw = __popc(__ballot_sync(0xffffffffu, walking));
+					} while (nw >= limit);
+					if (st == RT_ST_WALK && !walking) st = RT_ST_END;
+				}
+			}
+			// ---- END: collision, material response
+			if (st == RT_ST_END) {
+				const uint32_t frame_count = F.frame_first + job % nf;
+				const double seed = xadd(xadd(F.rng_seed, (double)((size_t)y * F.width + x)),
+				                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
+				double c[3];
+				int hit = W.hit;
+				RtCollision ci;
+				if (hit >= 0 && !confirm_slot(S, hit, P.refpoint, P.dir, ci)) hit = -1;  // (same formula as in the search: cannot fail)
+				if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
+				else st = RT_ST_BEGIN;
+			}
+			__syncwarp();
+		}
+		// ---- ExposureBuffer.set_color_i, frame after frame: lane g owns pixel g of the group
+		__syncwarp();
+		if ((unsigned)lane < g_cnt) {
+			const RtQueueItem it = F.vqueue[g0 + lane];
+			const int px_x = (int)(it.xy & 0xffffu), px_y = (int)(it.xy >> 16);
+			size_t out_index = (size_t)px_y * F.width + px_x;
+			if (F.tile_compact) {
+				const int tile = (px_y / RT_TILE_H) * tiles_x + (px_x / RT_TILE_W);
+				out_index = (size_t)(tile / F.tile_world) * RT_BLOCK + ((px_y & (RT_TILE_H - 1)) * RT_TILE_W + (px_x & (RT_TILE_W - 1)));
+			}
+			float* o = F.rgb + out_index * 3;
+			float px[3] = {0.f, 0.f, 0.f};
+			if (F.frame_first > 0) { px[0] = o[0]; px[1] = o[1]; px[2] = o[2]; }
+			const double* c = colour + (size_t)lane * nf * 3;
+			for (unsigned f = 0; f < nf; f++, c += 3) {
+				const double w = xdiv(1.0, (double)(1u + F.frame_first + f));
+				const double w1 = xsub(1.0, w);
+#pragma unroll
+				for (int q = 0; q < 3; q++) px[q] = (float)xadd(xmul(c[q], w), xmul((double)px[q], w1));
+			}
+			o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
+			if (F.first_ids) F.first_ids[out_index] = group_entity[lane];
 		}
 		__syncwarp();
 	}
@@ -428,12 +567,15 @@ struct rt_ctx {
 	DevBuf<uint8_t> l2_scratch;
 	DevBuf<RtF4> prim_geom;
 	DevBuf<RtQueueItem> queue;
+	DevBuf<RtQueueItem> vqueue;
+	DevBuf<double> samples;
 	DevBuf<int> hit_slots;
 	DevBuf<uint32_t*> peer_flags;
 	std::vector<uint32_t*> peer_flags_host;
 	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
 	int ppl = RT_PPL;
 	int bounce_min_walking = 24;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
+	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
 	int bounce_minb = 8;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
 	int bounce_node_batch = 8;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
 };
@@ -540,9 +682,10 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	F.tile_compact = tile_compact ? 1 : 0;
 	F.bounce_min_walking = ctx->bounce_min_walking;
 	F.bounce_node_batch = ctx->bounce_node_batch;
-	// u64 cells: [0..7] work counters, [8] error flags, then per band {patch dispenser, queue count, queue cursor}
+	// u64 cells: [0..7] work counters, [8] error flags, then per band {patch dispenser, queue count, queue cursor,
+	// resample queue count, resample queue cursor}
 	n_bands = std::max(1, std::min(n_bands, RT_MAX_BANDS));
-	const size_t n_cells = 9 + 3 * RT_MAX_BANDS;
+	const size_t n_cells = 9 + 5 * RT_MAX_BANDS;
 	RT_CUDA(ctx, ctx->counters.alloc(n_cells));
 	F.counters = ctx->counters.p;
 	F.error_flags = reinterpret_cast<uint32_t*>(ctx->counters.p + 8);
@@ -566,10 +709,12 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	}
 	const bool pipeline = F.packet_ok && !count && !(prm->flags & RT_PARAM_PER_RAY);
 	if (!pipeline) F.packet_ok = 0;
+	const bool resample = pipeline && prm->n_frames > 1 && ctx->resample;  // rough pixels: frames traced 32 at a time by a warp
 	if (pipeline) {
 		const size_t cap = tile_compact ? (size_t)((n_tiles - tile_rank + tile_world - 1) / tile_world) * RT_BLOCK
 		                                : (size_t)F.width * F.height;
 		RT_CUDA(ctx, ctx->queue.alloc(cap));
+		if (resample) RT_CUDA(ctx, ctx->vqueue.alloc(cap));
 		RT_CUDA(ctx, ctx->hit_slots.alloc(cap));
 	}
 	auto grid_of = [&](int which, const void* kernel, int threads, int& out) -> rt_status {
@@ -591,10 +736,19 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	const int minb = ctx->bounce_minb;
 	const void* bounce_kernel = minb == 4 ? (const void*)rt_bounce_kernel<4> : minb == 5 ? (const void*)rt_bounce_kernel<5>
 	                          : minb == 6 ? (const void*)rt_bounce_kernel<6> : (const void*)rt_bounce_kernel<8>;
-	int grid_primary = 0, grid_bounce = 0, grid_ray = 0;
+	const void* resample_kernel = minb == 4 ? (const void*)rt_resample_kernel<4> : minb == 5 ? (const void*)rt_resample_kernel<5>
+	                            : minb == 6 ? (const void*)rt_resample_kernel<6> : (const void*)rt_resample_kernel<8>;
+	int grid_primary = 0, grid_bounce = 0, grid_ray = 0, grid_resample = 0;
 	if (pipeline) {
 		if (rt_status st = grid_of(4 + (ppl == 1 ? 0 : ppl == 2 ? 1 : ppl == 4 ? 2 : 3), primary_kernel, RT_A_WARPS * 32, grid_primary)) return st;
 		if (rt_status st = grid_of(3, bounce_kernel, RT_WARPS_PER_CTA * 32, grid_bounce)) return st;
+		if (resample) {
+			if (rt_status st = grid_of(2, resample_kernel, RT_WARPS_PER_CTA * 32, grid_resample)) return st;
+			// per warp: a header of 32 ints + [pool][3] float64 path colours (rt_resample_kernel)
+			F.samples_per_warp = 16 + 3 * (unsigned long long)std::max<uint32_t>(RT_RESAMPLE_POOL, prm->n_frames);
+			RT_CUDA(ctx, ctx->samples.alloc((size_t)grid_resample * RT_WARPS_PER_CTA * F.samples_per_warp));
+			F.samples = ctx->samples.p;
+		}
 	} else if (count) {
 		if (rt_status st = grid_of(1, (const void*)rt_render_kernel<true>, RT_WARPS_PER_CTA * 32, grid_ray)) return st;
 	} else {
@@ -628,14 +782,17 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 			const int y_begin = row_begin * RT_TILE_H, y_end = std::min(F.height, row_end * RT_TILE_H);
 			F.out_first = tile_compact ? 0ull : (unsigned long long)y_begin * F.width;
 			const size_t n_out = (tile_compact || tile_world > 1) ? (size_t)my_tiles * RT_BLOCK : (size_t)(y_end - y_begin) * F.width;
-			unsigned long long* cells = ctx->counters.p + 9 + 3 * band;
+			unsigned long long* cells = ctx->counters.p + 9 + 5 * band;
 			F.work_counter = reinterpret_cast<unsigned*>(cells);
 			F.queue_count = reinterpret_cast<unsigned*>(cells + 1);
 			F.queue_taken = reinterpret_cast<unsigned*>(cells + 2);
+			F.vqueue_count = reinterpret_cast<unsigned*>(cells + 3);
+			F.vqueue_taken = reinterpret_cast<unsigned*>(cells + 4);
 			const int n_patches = my_tiles * 8;
 			if (pipeline) {
 				// primary stage (packet walk) -> shade stage -> bounce stage over the continuation queue
 				F.queue = ctx->queue.p + F.out_first;
+				F.vqueue = resample ? ctx->vqueue.p + F.out_first : nullptr;
 				F.hit_slots = ctx->hit_slots.p;
 				const int n_packets = my_tiles * (8 / ppl);
 				const int blocks = std::min(grid_primary, (n_packets + RT_A_WARPS - 1) / RT_A_WARPS);
@@ -648,6 +805,11 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				void* bargs[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x};
 				RT_CUDA(ctx, cudaLaunchKernel(bounce_kernel, dim3(std::min(grid_bounce, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA)),
 				                              dim3(RT_WARPS_PER_CTA * 32), bargs, 0, ctx->stream));
+				if (resample) {
+					ctx->launches++;
+					RT_CUDA(ctx, cudaLaunchKernel(resample_kernel, dim3(std::min(grid_resample, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA)),
+					                              dim3(RT_WARPS_PER_CTA * 32), bargs, 0, ctx->stream));
+				}
 			} else if (count) {
 				rt_render_kernel<true><<<std::min(grid_ray, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
 				                         ctx->stream>>>(ctx->dev, F, tiles_x, n_patches);
@@ -752,6 +914,7 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= 32) ctx->bounce_min_walking = v;
 	}
+	if (const char* e = getenv("RT_B200_RESAMPLE")) ctx->resample = atoi(e) != 0;
 	if (const char* e = getenv("RT_B200_BOUNCE_MINB")) {
 		const int v = atoi(e);
 		if (v == 4 || v == 5 || v == 6 || v == 8) ctx->bounce_minb = v;
@@ -776,7 +939,7 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
-	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->hit_slots.release(); ctx->peer_flags.release();
+	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->samples.release(); ctx->hit_slots.release(); ctx->peer_flags.release();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	for (int b = 0; b < RT_MAX_BANDS; b++)

@@ -169,6 +169,13 @@ struct RtFrame {
 	RtQueueItem* queue;      // [capacity]
 	unsigned* queue_count;   // items appended by the primary stage
 	unsigned* queue_taken;   // consumer cursor of the bounce stage
+	// resample queue between the bounce stage and the resample stage (n_frames > 1): the pixels whose path
+	// draws from the RNG, i.e. whose every exposure frame is a different path
+	RtQueueItem* vqueue;     // [capacity], or null: the bounce stage traces all frames of such a pixel itself
+	unsigned* vqueue_count;
+	unsigned* vqueue_taken;
+	double* samples;         // resample stage: per-warp sample buffers
+	unsigned long long samples_per_warp;  // doubles per warp
 	int bounce_min_walking;  // bounce stage: leave the lock-step walk when fewer lanes than this are still walking
 	int bounce_node_batch;   // bounce stage: lanes that need a node step wait until this many do
 };
