@@ -311,13 +311,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if rank != 0:
         return
     peak, peak_src = peaks()
-    kernel_ms = ms_per_step  # at N=1 the step IS the one render kernel
+    kernel_ms = ms_per_step  # the step's kernels back to back on one stream (CUDA events around them)
     achieved = algo_bytes / world / (kernel_ms * 1e-3) / 1e9 if world == 1 else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("rt_render_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     out = {
@@ -339,8 +339,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_segment": bytes_per_segment,
                      "per_segment": {"nodes": nodes / segments, "tests": tests / segments, "shades": shades / segments},
+                     "kernel": "the step's launches together (prepare + primary + shade + bounce); rt_primary_kernel is ~80% of "
+                               "the step in profiles/*_launches.csv and `traffic` is its DRAM bytes per launch (ncu --set full)",
                      "note": "algorithmic bytes follow the REFERENCE's access pattern (64 B/node + 16 B/test + 16 B/shade + "
-                             "12 B/pixel); the scene (~1 MB) is L2/L1 resident, so achieved may exceed the HBM peak"},
+                             "12 B/pixel); the scene (~1 MB) is L2/L1 resident and a packet shares every fetch among its "
+                             "rays, so achieved exceeds the HBM peak: see DESIGN.md 4.2 for the issue-slot figures that "
+                             "bound the kernel"},
     }
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
