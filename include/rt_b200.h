@@ -194,6 +194,43 @@ rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* p
 rt_status rt_get_counters(rt_ctx* ctx, rt_counters* counters);
 rt_status rt_synchronize(rt_ctx* ctx);
 
+/* ---- present: View.draw_ebuffer() (src/view/view.ts:34-38) on the device -------------------------- */
+/* The step right after trace_frame(): exposure statistics (ExposureBuffer.get_mean / get_variance /
+ * get_absolute_dev, src/view/exposure_buffer.ts:93-142), the tone mapper's dynamic range
+ * (src/view/tone_mapping.ts:24-79) and the range compression to 8-bit pixels
+ * (ExposureBuffer.discretize_to_screen, src/view/exposure_buffer.ts:145-158, into CanvasScreen.set_pixel_i /
+ * convert_color, src/view/screen_canvas.ts:45-56,101-103), so that only RGBA8 leaves the GPU.  The output is
+ * the CanvasScreen's ImageData: [height][width][4] bytes, alpha 255, and - as the reference is written at
+ * HEAD (`pixels.slice(i, i+2)`) - blue 0.  The frame-wide sums are deterministic parallel float64
+ * reductions (the reference adds the pixels one by one; the results agree to ~1e-13 relative). */
+#define RT_TONE_IDENTITY 0u /* ToneMapper_Identity: [0, 1] */
+#define RT_TONE_STDDEV 1u   /* ToneMapper_StdDevAroundMean */
+#define RT_TONE_ABSDEV 2u   /* ToneMapper_AbsDevAroundMean */
+typedef struct rt_tone {
+	uint32_t kind;          /* RT_TONE_* */
+	uint32_t dynamic_range; /* stops: dynamic_coef = 1 << dynamic_range (Screen.dynamic_range, 8 for a canvas) */
+	double min_dynamic, max_dynamic;
+} rt_tone;
+typedef struct rt_exposure_stats {
+	double mean, variance, absolute_dev; /* of the luma Y = 0.299 R + 0.587 G + 0.114 B */
+	double drange_low, drange_high;      /* ToneMapper.get_dynamic_range */
+} rt_exposure_stats;
+/* Device buffers, asynchronous on the ctx stream.  rgb_dev: float32 [height][width][3]; rgba_dev: [height][width][4]. */
+rt_status rt_present_device(rt_ctx* ctx, const float* rgb_dev, uint32_t width, uint32_t height, const rt_tone* tone,
+                            uint8_t* rgba_dev);
+/* Statistics and range of the last rt_present_device (synchronises the stream). */
+rt_status rt_present_stats(rt_ctx* ctx, rt_exposure_stats* out);
+/* Host buffers: H2D of the float frame, present, D2H of the RGBA8 image.  Synchronous.  stats may be NULL. */
+rt_status rt_present(rt_ctx* ctx, const float* rgb, uint32_t width, uint32_t height, const rt_tone* tone, uint8_t* rgba,
+                     rt_exposure_stats* stats);
+/* trace_frame() + draw_ebuffer() with the ExposureBuffer RESIDENT on the device: the float frame stays in HBM
+ * between calls (frame_first > 0 continues it; the first call of an exposure must use frame_first = 0) and only
+ * the 8-bit image travels to the host.  Synchronous.  stats and counters may be NULL. */
+rt_status rt_render_present(rt_ctx* ctx, const rt_camera* cam, const rt_params* params, uint32_t render_flags,
+                            const rt_tone* tone, uint8_t* rgba, rt_exposure_stats* stats, rt_counters* counters);
+/* Copies the resident ExposureBuffer to the host (float32 [height][width][3]).  Synchronous. */
+rt_status rt_exposure_download(rt_ctx* ctx, float* rgb, uint32_t width, uint32_t height);
+
 /* ---- multi-GPU tile sharding ------------------------------------------------------------------ */
 /* The frame is cut into 16x16-pixel tiles numbered row-major; rank r of `world` owns the tiles t with
  * t % world == r (interleaved, to balance sky against dense regions).  One ctx (one process) per GPU

@@ -109,6 +109,9 @@ def lib():
         "orc_texture_get": (None, [vp, i32, ip, dp, ip, ip, ip]),
         "orc_substance_count": (i32, [vp]),
         "orc_substance_get": (f64, [vp, i32]),
+        "orc_exposure_stats": (None, [C.POINTER(C.c_float), C.c_int64, dp]),
+        "orc_dynamic_range": (None, [i32, i32, f64, f64, dp, dp]),
+        "orc_discretize": (None, [C.POINTER(C.c_float), C.c_int64, f64, f64, C.c_void_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -354,3 +357,32 @@ def box_line(center, size, pos, direction):
     f = np.zeros(2, np.int32)
     n = lib().orc_box_line(_dp(_v3(center)), _dp(_v3(size)), _dp(_v3(pos)), _dp(_v3(direction)), _dp(u), _ip(f))
     return n, u, f
+
+
+# ---- View.draw_ebuffer (src/view/view.ts:34-38): exposure statistics, tone mapper, 8-bit screen
+TONE_IDENTITY, TONE_STDDEV, TONE_ABSDEV = 0, 1, 2
+
+
+def exposure_stats(pixels):
+    """ExposureBuffer.get_mean / get_variance / get_absolute_dev -> (mean, variance, absdev)."""
+    px = np.ascontiguousarray(pixels, dtype=np.float32).reshape(-1)
+    out = np.zeros(3)
+    lib().orc_exposure_stats(px.ctypes.data_as(C.POINTER(C.c_float)), px.size // 3, _dp(out))
+    return tuple(float(v) for v in out)
+
+
+def dynamic_range(kind, dynamic_range_stops, min_dynamic, max_dynamic, stats):
+    """ToneMapper.get_dynamic_range -> (drange_min, drange_max)."""
+    st = np.ascontiguousarray(stats, dtype=np.float64)
+    out = np.zeros(2)
+    lib().orc_dynamic_range(int(kind), int(dynamic_range_stops), float(min_dynamic), float(max_dynamic), _dp(st), _dp(out))
+    return float(out[0]), float(out[1])
+
+
+def discretize(pixels, drange_low, drange_high):
+    """ExposureBuffer.discretize_to_screen into a CanvasScreen image -> uint8 [n_pixels, 4] (RGBA)."""
+    px = np.ascontiguousarray(pixels, dtype=np.float32).reshape(-1)
+    out = np.zeros((px.size // 3, 4), np.uint8)
+    lib().orc_discretize(px.ctypes.data_as(C.POINTER(C.c_float)), px.size // 3, float(drange_low), float(drange_high),
+                         out.ctypes.data)
+    return out

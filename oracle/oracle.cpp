@@ -1312,4 +1312,69 @@ void orc_texture_get(void* h, int32_t i, int32_t* kind, double* color, int32_t* 
 int32_t orc_substance_count(void* h) { return (int32_t)((Scene*)h)->substances.size(); }
 double orc_substance_get(void* h, int32_t i) { return ((Scene*)h)->substances[i]; }
 
+// ------------------------------------------------------------------ View.draw_ebuffer (src/view/view.ts:34-38)
+// ExposureBuffer.rgb_to_y (src/view/exposure_buffer.ts:161-173): float64 arithmetic on the float32 pixels
+static inline double rgb_to_y(const float* px) { return 0.299 * (double)px[0] + 0.587 * (double)px[1] + 0.114 * (double)px[2]; }
+// mathutils.clamp (src/math/mathutils.ts:18-20) = Math.max(Math.min(x, max), min): NaN propagates
+static inline double js_math_min(double a, double b) { return (std::isnan(a) || std::isnan(b)) ? NAN : (a < b ? a : b); }
+static inline double js_math_max(double a, double b) { return (std::isnan(a) || std::isnan(b)) ? NAN : (a > b ? a : b); }
+static inline double js_clamp(double x, double lo, double hi) { return js_math_max(js_math_min(x, hi), lo); }
+
+// ExposureBuffer.get_mean / get_variance / get_absolute_dev (src/view/exposure_buffer.ts:93-142): sequential
+// float64 sums in pixel order (the `_mean` style caches are never filled, so every call recomputes).
+// out = {mean, variance, absolute deviation}
+void orc_exposure_stats(const float* pixels, int64_t n_pixels, double* out) {
+	double mean = 0;
+	for (int64_t i = 0; i < n_pixels * 3; i += 3) mean += rgb_to_y(pixels + i);
+	mean /= (double)n_pixels;
+	double variance = 0, dev = 0;
+	for (int64_t i = 0; i < n_pixels * 3; i += 3) {
+		const double delta = rgb_to_y(pixels + i) - mean;
+		variance += delta * delta;
+		dev += std::fabs(delta);
+	}
+	out[0] = mean;
+	out[1] = variance / (double)n_pixels;
+	out[2] = dev / (double)n_pixels;
+}
+
+// ToneMapper.get_dynamic_range (src/view/tone_mapping.ts:24-79).  kind 0 ToneMapper_Identity, 1
+// ToneMapper_StdDevAroundMean, 2 ToneMapper_AbsDevAroundMean; dynamic_coef = 1 << dynamic_range (:42).
+void orc_dynamic_range(int32_t kind, int32_t dynamic_range, double min_dynamic, double max_dynamic, const double* stats,
+                       double* out) {
+	if (kind == 0) { out[0] = 0; out[1] = 1; return; }
+	const double dynamic_coef = (double)(int32_t)(1u << (dynamic_range & 31));
+	const double mean_br = stats[0];
+	const double dev_br = kind == 1 ? std::sqrt(stats[1]) : stats[2];
+	double drange_max = js_math_min(mean_br + dev_br, max_dynamic);
+	double drange_min = drange_max / dynamic_coef;
+	if (drange_min < min_dynamic) {
+		drange_min = min_dynamic;
+		drange_max = drange_min * dynamic_coef;
+	}
+	out[0] = drange_min;
+	out[1] = drange_max;
+}
+
+// ExposureBuffer.discretize_to_screen (src/view/exposure_buffer.ts:145-158) into CanvasScreen.set_pixel_i /
+// convert_color (src/view/screen_canvas.ts:45-56,101-103).  As written at HEAD: `pixels.slice(i, i+2)` keeps
+// TWO channels, `.map` on a Float32Array rounds the clamped products to float32, and convert_color's third
+// element is undefined, which a Uint8ClampedArray stores as 0 - the blue channel of every pixel is 0
+// (SURVEY.md 8f N2).  rgba: [n_pixels][4] bytes.
+void orc_discretize(const float* pixels, int64_t n_pixels, double drange_low, double drange_high, uint8_t* rgba) {
+	const double drange = drange_high - drange_low;
+	for (int64_t px_i = 0, i = 0; px_i < n_pixels; ++px_i, i += 3) {
+		const double px_brightness = rgb_to_y(pixels + i);
+		const double cmpr_brightness = (px_brightness - drange_low) / drange;
+		const double scale_coef = cmpr_brightness / (px_brightness + std::numeric_limits<double>::epsilon());
+		for (int k = 0; k < 2; k++) {
+			const float compressed = (float)js_clamp((double)pixels[i + k] * scale_coef, 0.0, 1.0);  // Float32Array.map
+			const double v = js_clamp((double)compressed, 0.0, 1.0) * 255.0;
+			rgba[px_i * 4 + k] = (uint8_t)js_int32(v);  // (x*255) << 0, NaN -> 0
+		}
+		rgba[px_i * 4 + 2] = 0;
+		rgba[px_i * 4 + 3] = 0xff;
+	}
+}
+
 }  // extern "C"

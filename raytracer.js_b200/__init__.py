@@ -21,6 +21,8 @@ from .rng import PRNG, RNG, FpLcg
 from .sky import Sky, SkySphere
 from .substance import SUBSTANCE_AIR, SUBSTANCE_GLASS, SUBSTANCE_WATER, Substance
 from .texture import ImageTexture, SolidTexture, Texture, TextureError
+from .view import (GpuView, Screen, ToneMapper, ToneMapper_AbsDevAroundMean, ToneMapper_DRLimited, ToneMapper_Identity,
+                   ToneMapper_StdDevAroundMean, View)
 
 Raytracer = GpuRaytracer  # the drop-in name
 

@@ -15,6 +15,7 @@ RT_CAM_REFERENCE_EXTENTS = 1
 RT_PRECISION_F32 = 0
 RT_RENDER_COUNTERS = 1
 RT_B200_ABI_VERSION = 1
+RT_TONE_IDENTITY, RT_TONE_STDDEV, RT_TONE_ABSDEV = 0, 1, 2
 
 _dp, _ip, _up, _bp, _qp = (C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint32),
                            C.POINTER(C.c_uint8), C.POINTER(C.c_uint64))
@@ -56,6 +57,17 @@ class Counters(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class Tone(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("dynamic_range", C.c_uint32), ("min_dynamic", C.c_double), ("max_dynamic", C.c_double)]
+
+
+class ExposureStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("mean", "variance", "absolute_dev", "drange_low", "drange_high")]
+
+    def as_dict(self):
+        return {n: float(getattr(self, n)) for n, _ in self._fields_}
+
+
 EXPORTS = {
     "rt_abi_version": (C.c_uint32, []),
     "rt_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
@@ -68,6 +80,13 @@ EXPORTS = {
     "rt_render_device": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32, C.c_void_p,
                                    C.c_void_p]),
     "rt_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
+    "rt_present_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Tone), C.c_void_p]),
+    "rt_present_stats": (C.c_int, [C.c_void_p, C.POINTER(ExposureStats)]),
+    "rt_present": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Tone), C.c_void_p,
+                             C.POINTER(ExposureStats)]),
+    "rt_render_present": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32, C.POINTER(Tone),
+                                    C.c_void_p, C.POINTER(ExposureStats), C.POINTER(Counters)]),
+    "rt_exposure_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
     "rt_synchronize": (C.c_int, [C.c_void_p]),
     "rt_timer_start": (C.c_int, [C.c_void_p]),
     "rt_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

@@ -480,6 +480,99 @@ __global__ void rt_peer_barrier_kernel(uint32_t* const* __restrict__ flags, int 
 	} while ((int32_t)(v - epoch) < 0);
 }
 
+// ---- present: View.draw_ebuffer() (src/view/view.ts:34-38) ------------------------------------------
+// Three HBM-bound passes over the float32 frame (12 B/pixel read each; the frame stays in the 126 MB L2
+// between them up to 4K): luma sum, deviation sums, range compression to RGBA8.  Every block reduces its
+// share in a fixed order and every consumer adds the block partials in index order, so the results do not
+// depend on scheduling.
+#define RT_PRESENT_THREADS 256
+RT_D double luma(const float* px) {  // ExposureBuffer.rgb_to_y (src/view/exposure_buffer.ts:161-173), float64, no FMA
+	return xadd(xadd(xmul(0.299, (double)px[0]), xmul(0.587, (double)px[1])), xmul(0.114, (double)px[2]));
+}
+RT_D double block_sum(double v, double* sh) {  // fixed tree: xor shuffles inside a warp, warps in order
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = 0.0;
+	for (int w = 0; w < RT_PRESENT_THREADS / 32; w++) s += sh[w];
+	__syncthreads();
+	return s;
+}
+RT_D double partial_sum(const double* partial, int n_blocks, double* sh) {  // the same value in every block
+	double v = 0.0;
+	for (int i = threadIdx.x; i < n_blocks; i += RT_PRESENT_THREADS) v += partial[i];
+	return block_sum(v, sh);
+}
+__global__ void __launch_bounds__(RT_PRESENT_THREADS)
+    rt_luma_sum_kernel(const float* __restrict__ rgb, size_t n_pixels, double* __restrict__ partial) {
+	__shared__ double sh[RT_PRESENT_THREADS / 32];
+	double v = 0.0;
+	for (size_t i = (size_t)blockIdx.x * RT_PRESENT_THREADS + threadIdx.x; i < n_pixels; i += (size_t)gridDim.x * RT_PRESENT_THREADS)
+		v += luma(rgb + i * 3);
+	const double s = block_sum(v, sh);
+	if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// ExposureBuffer.get_variance / get_absolute_dev (:111-142): sums of (y - mean)^2 and |y - mean|
+__global__ void __launch_bounds__(RT_PRESENT_THREADS)
+    rt_luma_dev_kernel(const float* __restrict__ rgb, size_t n_pixels, const double* __restrict__ partial_sum_in,
+                       double* __restrict__ partial_var, double* __restrict__ partial_abs) {
+	__shared__ double sh[RT_PRESENT_THREADS / 32];
+	const double mean = xdiv(partial_sum(partial_sum_in, gridDim.x, sh), (double)n_pixels);
+	double v = 0.0, a = 0.0;
+	for (size_t i = (size_t)blockIdx.x * RT_PRESENT_THREADS + threadIdx.x; i < n_pixels; i += (size_t)gridDim.x * RT_PRESENT_THREADS) {
+		const double delta = xsub(luma(rgb + i * 3), mean);
+		v += xmul(delta, delta);
+		a += fabs(delta);
+	}
+	const double sv = block_sum(v, sh), sa = block_sum(a, sh);
+	if (threadIdx.x == 0) { partial_var[blockIdx.x] = sv; partial_abs[blockIdx.x] = sa; }
+}
+// mathutils.clamp = Math.max(Math.min(x, max), min) (src/math/mathutils.ts:18-20): NaN propagates
+RT_D double js_clamp01(double x) {
+	if (x != x) return x;
+	return x > 1.0 ? 1.0 : (x < 0.0 ? 0.0 : x);
+}
+// ToneMapper.get_dynamic_range (src/view/tone_mapping.ts:24-79) + ExposureBuffer.discretize_to_screen
+// (src/view/exposure_buffer.ts:145-158) + CanvasScreen.convert_color (src/view/screen_canvas.ts:101-103)
+__global__ void __launch_bounds__(RT_PRESENT_THREADS)
+    rt_discretize_kernel(const float* __restrict__ rgb, size_t n_pixels, const double* __restrict__ partial, int n_partial,
+                         rt_tone tone, uchar4* __restrict__ rgba, double* __restrict__ stats_out) {
+	__shared__ double sh[RT_PRESENT_THREADS / 32];
+	const double mean = xdiv(partial_sum(partial, n_partial, sh), (double)n_pixels);
+	const double variance = xdiv(partial_sum(partial + n_partial, n_partial, sh), (double)n_pixels);
+	const double absdev = xdiv(partial_sum(partial + 2 * n_partial, n_partial, sh), (double)n_pixels);
+	double lo = 0.0, hi = 1.0;
+	if (tone.kind != RT_TONE_IDENTITY) {
+		const double coef = (double)(int)(1u << (tone.dynamic_range & 31u));
+		const double dev = tone.kind == RT_TONE_STDDEV ? xsqrt(variance) : absdev;
+		const double m = xadd(mean, dev);
+		hi = (m != m || tone.max_dynamic != tone.max_dynamic) ? NAN : (m < tone.max_dynamic ? m : tone.max_dynamic);  // Math.min
+		lo = xdiv(hi, coef);
+		if (lo < tone.min_dynamic) {
+			lo = tone.min_dynamic;
+			hi = xmul(lo, coef);
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		stats_out[0] = mean; stats_out[1] = variance; stats_out[2] = absdev; stats_out[3] = lo; stats_out[4] = hi;
+	}
+	const double drange = xsub(hi, lo);
+	for (size_t i = (size_t)blockIdx.x * RT_PRESENT_THREADS + threadIdx.x; i < n_pixels; i += (size_t)gridDim.x * RT_PRESENT_THREADS) {
+		const float* px = rgb + i * 3;
+		const double y = luma(px);
+		const double scale = xdiv(xdiv(xsub(y, lo), drange), xadd(y, RT_JS_EPSILON));
+		unsigned char out[2];
+#pragma unroll
+		for (int k = 0; k < 2; k++) {  // `pixels.slice(i, i+2)`: two channels
+			const float compressed = (float)js_clamp01(xmul((double)px[k], scale));  // Float32Array.prototype.map
+			const double v = xmul(js_clamp01((double)compressed), 255.0);
+			out[k] = v != v ? 0 : (unsigned char)(int)v;  // (x * 255) << 0
+		}
+		rgba[i] = make_uchar4(out[0], out[1], 0, 0xff);  // convert_color()[2] is undefined -> 0 in the Uint8ClampedArray
+	}
+}
+
 // ================================================================== host side
 namespace {
 
@@ -568,6 +661,10 @@ struct rt_ctx {
 	DevBuf<RtF4> prim_geom;
 	DevBuf<RtQueueItem> queue;
 	DevBuf<RtQueueItem> vqueue;
+	DevBuf<double> present_partial;              // 3 x blocks partial sums + 8 stats (rt_present_device)
+	DevBuf<uint8_t> rgba;                        // RGBA8 image of rt_present / rt_render_present
+	int present_blocks = 0;
+	uint32_t exposure_w = 0, exposure_h = 0;     // size of the resident ExposureBuffer in ctx->rgb (rt_render_present)
 	DevBuf<double> samples;
 	DevBuf<int> hit_slots;
 	DevBuf<uint32_t*> peer_flags;
@@ -939,7 +1036,7 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
-	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->samples.release(); ctx->hit_slots.release(); ctx->peer_flags.release();
+	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->hit_slots.release(); ctx->peer_flags.release();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	for (int b = 0; b < RT_MAX_BANDS; b++)
@@ -1192,6 +1289,91 @@ rt_status rt_get_counters(rt_ctx* ctx, rt_counters* out) {
 	return read_counters(ctx, out);
 }
 
+rt_status rt_present_device(rt_ctx* ctx, const float* rgb_dev, uint32_t width, uint32_t height, const rt_tone* tone,
+                            uint8_t* rgba_dev) {
+	if (!ctx || !rgb_dev || !rgba_dev || !tone) return fail(ctx, RT_ERR_INVALID, "rt_present_device: NULL argument");
+	if (!width || !height) return fail(ctx, RT_ERR_INVALID, "rt_present_device: empty frame");
+	if (tone->kind > RT_TONE_ABSDEV) return fail(ctx, RT_ERR_UNSUPPORTED, rt_format("unsupported ToneMapper subclass (kind %u)", tone->kind));
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (ctx->present_blocks == 0) {
+		int sms = 0;
+		RT_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+		ctx->present_blocks = std::max(1, sms) * 8;  // 8 CTAs of 256 threads per SM: a multiple of the SM count
+	}
+	const size_t npx = (size_t)width * height;
+	const int blocks = (int)std::min<size_t>((size_t)ctx->present_blocks, (npx + RT_PRESENT_THREADS - 1) / RT_PRESENT_THREADS);
+	RT_CUDA(ctx, ctx->present_partial.alloc((size_t)3 * ctx->present_blocks + 8));
+	double* part = ctx->present_partial.p;
+	rt_luma_sum_kernel<<<blocks, RT_PRESENT_THREADS, 0, ctx->stream>>>(rgb_dev, npx, part);
+	rt_luma_dev_kernel<<<blocks, RT_PRESENT_THREADS, 0, ctx->stream>>>(rgb_dev, npx, part, part + blocks, part + 2 * blocks);
+	rt_discretize_kernel<<<blocks, RT_PRESENT_THREADS, 0, ctx->stream>>>(rgb_dev, npx, part, blocks, *tone, reinterpret_cast<uchar4*>(rgba_dev),
+	                                                                     part + (size_t)3 * ctx->present_blocks);
+	ctx->launches += 3;
+	RT_CUDA(ctx, cudaGetLastError());
+	return RT_OK;
+}
+
+rt_status rt_present_stats(rt_ctx* ctx, rt_exposure_stats* out) {
+	if (!ctx || !out) return RT_ERR_INVALID;
+	if (!ctx->present_partial.p) return fail(ctx, RT_ERR_INVALID, "rt_present_stats: nothing was presented yet");
+	double h[5];
+	RT_CUDA(ctx, cudaMemcpyAsync(h, ctx->present_partial.p + (size_t)3 * ctx->present_blocks, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	out->mean = h[0]; out->variance = h[1]; out->absolute_dev = h[2]; out->drange_low = h[3]; out->drange_high = h[4];
+	return RT_OK;
+}
+
+rt_status rt_present(rt_ctx* ctx, const float* rgb, uint32_t width, uint32_t height, const rt_tone* tone, uint8_t* rgba,
+                     rt_exposure_stats* stats) {
+	if (!ctx || !rgb || !rgba) return fail(ctx, RT_ERR_INVALID, "rt_present: NULL argument");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t npx = (size_t)width * height;
+	RT_CUDA(ctx, ctx->rgb.alloc(npx * 3));
+	RT_CUDA(ctx, ctx->rgba.alloc(npx * 4));
+	ctx->exposure_w = ctx->exposure_h = 0;  // ctx->rgb no longer holds a resident exposure
+	RT_CUDA(ctx, cudaMemcpyAsync(ctx->rgb.p, rgb, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	if (rt_status st = rt_present_device(ctx, ctx->rgb.p, width, height, tone, ctx->rgba.p)) return st;
+	RT_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->rgba.p, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (stats) return rt_present_stats(ctx, stats);
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return RT_OK;
+}
+
+rt_status rt_render_present(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, const rt_tone* tone,
+                            uint8_t* rgba, rt_exposure_stats* stats, rt_counters* counters) {
+	if (rt_status st = check_args(ctx, cam, prm)) return st;
+	if (!rgba || !tone) return fail(ctx, RT_ERR_INVALID, "rt_render_present: NULL argument");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t npx = (size_t)cam->width * cam->height;
+	if (prm->frame_first > 0 && (ctx->exposure_w != cam->width || ctx->exposure_h != cam->height))
+		return fail(ctx, RT_ERR_INVALID, "rt_render_present: frame_first > 0 but no resident ExposureBuffer of this size (start the exposure with frame_first = 0)");
+	RT_CUDA(ctx, ctx->rgb.alloc(npx * 3));
+	RT_CUDA(ctx, ctx->rgba.alloc(npx * 4));
+	ctx->exposure_w = cam->width;
+	ctx->exposure_h = cam->height;
+	if (counters) flags |= RT_RENDER_COUNTERS;
+	if (rt_status st = launch_render(ctx, cam, prm, flags, ctx->rgb.p, nullptr, 0, 1)) return st;
+	if (rt_status st = rt_present_device(ctx, ctx->rgb.p, cam->width, cam->height, tone, ctx->rgba.p)) return st;
+	RT_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->rgba.p, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (stats)
+		if (rt_status st = rt_present_stats(ctx, stats)) return st;
+	rt_counters tmp;
+	if (rt_status st = read_counters(ctx, &tmp)) return st;  // also synchronises and fetches the error flags
+	if (counters) *counters = tmp;
+	if (tmp.texture_errors) return fail(ctx, RT_ERR_TEXTURE, "Texture coordinates out of bounds");
+	return RT_OK;
+}
+
+rt_status rt_exposure_download(rt_ctx* ctx, float* rgb, uint32_t width, uint32_t height) {
+	if (!ctx || !rgb) return RT_ERR_INVALID;
+	if (!ctx->exposure_w || ctx->exposure_w != width || ctx->exposure_h != height)
+		return fail(ctx, RT_ERR_INVALID, "rt_exposure_download: no resident ExposureBuffer of this size");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	RT_CUDA(ctx, cudaMemcpyAsync(rgb, ctx->rgb.p, (size_t)width * height * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return RT_OK;
+}
+
 rt_status rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb,
                     int32_t* first_ids, rt_counters* counters) {
 	if (rt_status st = check_args(ctx, cam, prm)) return st;
@@ -1199,6 +1381,7 @@ rt_status rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uin
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
 	const size_t npx = (size_t)cam->width * cam->height;
 	RT_CUDA(ctx, ctx->rgb.alloc(npx * 3));
+	ctx->exposure_w = ctx->exposure_h = 0;  // ctx->rgb is this call's staging, not a resident exposure
 	if (first_ids) RT_CUDA(ctx, ctx->ids.alloc(npx));
 	if (prm->frame_first > 0)
 		RT_CUDA(ctx, cudaMemcpyAsync(ctx->rgb.p, rgb, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));

@@ -1,6 +1,6 @@
 """ExposureBuffer (src/view/exposure_buffer.ts:26-91): the float32 running-mean frame store that
 trace_frame() writes.  The GPU renderer updates `pixels` in bulk with the same blend
-(col_weight = 1/(1+frame_count)); statistics / tone mapping are out of scope."""
+(col_weight = 1/(1+frame_count)); statistics and tone mapping run on the device (view.py)."""
 from __future__ import annotations
 
 import numpy as np

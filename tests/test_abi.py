@@ -37,13 +37,15 @@ def test_exports_match_header(lib):
 def test_struct_sizes_match_header(lib, tmp_path):
     """sizeof of the ctypes mirrors == sizeof in C (compiled from the header with gcc)."""
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "rt_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
-                   'sizeof(rt_scene_desc),sizeof(rt_camera),sizeof(rt_params),sizeof(rt_counters));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "rt_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(rt_scene_desc),sizeof(rt_camera),sizeof(rt_params),sizeof(rt_counters),sizeof(rt_tone),'
+                   'sizeof(rt_exposure_stats));return 0;}\n')
     exe = tmp_path / "sz"
     import subprocess
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    assert sizes == [C.sizeof(N.SceneDesc), C.sizeof(N.CameraDesc), C.sizeof(N.Params), C.sizeof(N.Counters)]
+    assert sizes == [C.sizeof(N.SceneDesc), C.sizeof(N.CameraDesc), C.sizeof(N.Params), C.sizeof(N.Counters),
+                     C.sizeof(N.Tone), C.sizeof(N.ExposureStats)]
 
 
 def _have_gpu():
