@@ -265,6 +265,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- end to end through the C ABI with HOST buffers: camera tables H2D + kernel + full frame D2H
     e2e = None
+    present = None
     if world == 1:
         host_rgb = np.zeros(npx * 3, np.float32)
         N.check(ctx, lib.rt_host_register(ctx, host_rgb.ctypes.data, host_rgb.nbytes))  # pinned, as the N-API shim does
@@ -280,6 +281,39 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         N.check(ctx, lib.rt_host_unregister(ctx, host_rgb.ctypes.data))
         e2e = {"value": segments * args.steps / dt / 1e6, "unit": "Mrays/s", "frame_ms": dt / args.steps * 1e3,
                "h2d_bytes_per_step": WIDTH * 16 + HEIGHT * 32 + 80, "d2h_bytes_per_step": npx * 12 + 68}
+        # ---- the step after the path: View.draw_ebuffer() on the device.  (a) the three
+        # present kernels alone on the resident frame, (b) trace_frame + draw_ebuffer end to end with the
+        # ExposureBuffer resident in HBM: only the RGBA8 screen travels to the host.
+        tone = N.Tone(N.RT_TONE_STDDEV, 8, 1.0 / 256, 8.0)  # the demo's mapper (src/main.ts:369)
+        rgba_dev = torch.zeros(npx * 4, dtype=torch.uint8, device=dev)
+        pevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for _ in range(3):
+            N.check(ctx, lib.rt_present_device(ctx, C.c_void_p(frame.data_ptr()), WIDTH, HEIGHT, C.byref(tone), C.c_void_p(rgba_dev.data_ptr())))
+        for a, b in pevs:
+            N.check(ctx, lib.rt_flush_l2(ctx))
+            a.record(stream)
+            N.check(ctx, lib.rt_present_device(ctx, C.c_void_p(frame.data_ptr()), WIDTH, HEIGHT, C.byref(tone), C.c_void_p(rgba_dev.data_ptr())))
+            b.record(stream)
+        torch.cuda.synchronize()
+        present_ms = sum(a.elapsed_time(b) for a, b in pevs) / args.steps
+        host_rgba = np.zeros(npx * 4, np.uint8)
+        N.check(ctx, lib.rt_host_register(ctx, host_rgba.ctypes.data, host_rgba.nbytes))
+        for _ in range(3):
+            N.check(ctx, lib.rt_render_present(ctx, C.byref(cd), C.byref(prm), 0, C.byref(tone), host_rgba.ctypes.data, None, None))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            N.check(ctx, lib.rt_render_present(ctx, C.byref(cd), C.byref(prm), 0, C.byref(tone), host_rgba.ctypes.data, None, None))
+        dtp = time.perf_counter() - t0
+        assert np.array_equal(host_rgba, rgba_dev.cpu().numpy()), "resident present and device present disagree"
+        N.check(ctx, lib.rt_host_unregister(ctx, host_rgba.ctypes.data))
+        # algorithmic bytes of draw_ebuffer: get_mean, get_variance and discretize_to_screen each read the
+        # 12 B pixel, the screen gets 4 B (src/view/exposure_buffer.ts:93-158)
+        present_bytes = npx * (3 * 12 + 4)
+        present = {"kernels_ms": present_ms, "algorithmic_bytes": present_bytes, "achieved_GBps": present_bytes / (present_ms * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": present_bytes / (present_ms * 1e-3) / 1e9 / peaks()[0], "tone_mapper": "ToneMapper_StdDevAroundMean(8, 1/256, 8)",
+                   "e2e_render_present": {"value": segments * args.steps / dtp / 1e6, "unit": "Mrays/s", "frame_ms": dtp / args.steps * 1e3,
+                                          "h2d_bytes_per_step": WIDTH * 16 + HEIGHT * 32 + 80, "d2h_bytes_per_step": npx * 4 + 68,
+                                          "note": "trace_frame() + View.draw_ebuffer() with the ExposureBuffer resident on the device; RGBA8 out"}}
     else:
         # multi-GPU end to end: frame assembled on rank 0 and read back to pinned host memory every step
         host_t = torch.empty(npx * 3, dtype=torch.float32, pin_memory=True) if rank == 0 else None
@@ -334,7 +368,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "scene_broadcast_bytes": scene_bcast_bytes,
                    "precision": "float32 search + float64 confirmation/shading of the found hit",
                    "path": args.path},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clocks, "e2e": e2e, "present": present, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_segment": bytes_per_segment,

@@ -164,3 +164,34 @@ export class GpuRaytracer {
 
 	get rng() { return this._rng; }
 }
+
+/** View (src/view/view.ts:24-41) with draw_ebuffer() on the GPU: exposure statistics, the tone mapper's
+ *  dynamic range and the range compression run in librt_b200 (rt_present), and the CanvasScreen's ImageData is
+ *  filled in place.  Same constructor arguments as View plus the GpuRaytracer whose context does the work.
+ *  Unknown ToneMapper subclasses throw (no CPU fallback). */
+export class GpuView {
+	ebuffer: GpuExposureBuffer;
+	screen: any;          // CanvasScreen: `image` (ImageData) and `flush()` are reached with a cast, like the camera's fields
+	tone_mapper: any;     // ToneMapper_Identity | ToneMapper_StdDevAroundMean | ToneMapper_AbsDevAroundMean
+	last_stats?: { mean: number, variance: number, absolute_dev: number, drange_low: number, drange_high: number };
+	private raytracer: GpuRaytracer;
+
+	constructor(ebuffer: GpuExposureBuffer, screen: any, tone_mapper: any, raytracer: GpuRaytracer) {
+		this.ebuffer = ebuffer; this.screen = screen; this.tone_mapper = tone_mapper; this.raytracer = raytracer;
+	}
+
+	private tone() {
+		const tm = this.tone_mapper, name = tm.constructor.name;
+		if (name === 'ToneMapper_Identity') return { kind: 0, dynamic_range: 0, min_dynamic: 0, max_dynamic: 0 };
+		const kind = name === 'ToneMapper_StdDevAroundMean' ? 1 : name === 'ToneMapper_AbsDevAroundMean' ? 2 : -1;
+		if (kind < 0) throw Error(`unsupported ToneMapper subclass ${name}`);
+		return { kind, dynamic_range: Math.log2(tm.dynamic_coef), min_dynamic: tm.min_dynamic, max_dynamic: tm.max_dynamic };
+	}
+
+	/** View.draw_ebuffer() (src/view/view.ts:34-38) */
+	draw_ebuffer() {
+		const eb = this.ebuffer, image: ImageData = (this.screen as any).image;
+		this.last_stats = native.present((this.raytracer as any).ctx, eb.store, eb.w, eb.h, this.tone(), image.data);
+		if (!(this.screen as any).flags.buffer_pixels) this.screen.flush();
+	}
+}

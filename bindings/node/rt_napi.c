@@ -176,6 +176,41 @@ static napi_value Render(napi_env env, napi_callback_info info) {
 	return out;
 }
 
+/* present(ctx, pixels: Float32Array, width, height, tone: {kind, dynamic_range, min_dynamic, max_dynamic},
+ *         image: Uint8ClampedArray) -> {mean, variance, absolute_dev, drange_low, drange_high}
+ * View.draw_ebuffer() (src/view/view.ts:34-38): the ImageData backing store of the canvas is filled on the GPU. */
+static napi_value Present(napi_env env, napi_callback_info info) {
+	size_t argc = 6, npx = 0, nimg = 0;
+	napi_value argv[6], out = NULL, v;
+	napi_typedarray_type t;
+	void *rgb = NULL, *img = NULL;
+	RT_NAPI_TRY(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	rt_ctx* ctx = ctx_of(env, argv[0]);
+	uint32_t w = 0, h = 0;
+	RT_NAPI_TRY(env, napi_get_typedarray_info(env, argv[1], &t, &npx, &rgb, NULL, NULL));
+	RT_NAPI_TRY(env, napi_get_value_uint32(env, argv[2], &w));
+	RT_NAPI_TRY(env, napi_get_value_uint32(env, argv[3], &h));
+	rt_tone tone;
+	memset(&tone, 0, sizeof tone);
+	tone.kind = (uint32_t)num(env, argv[4], "kind");
+	tone.dynamic_range = (uint32_t)num(env, argv[4], "dynamic_range");
+	tone.min_dynamic = num(env, argv[4], "min_dynamic");
+	tone.max_dynamic = num(env, argv[4], "max_dynamic");
+	RT_NAPI_TRY(env, napi_get_typedarray_info(env, argv[5], &t, &nimg, &img, NULL, NULL));
+	if (npx != (size_t)w * h * 3 || nimg != (size_t)w * h * 4) {
+		napi_throw_error(env, "ERR_OUT_OF_RANGE", "x or y out of bounds");
+		return NULL;
+	}
+	rt_exposure_stats st;
+	rt_status rc = rt_present(ctx, (const float*)rgb, w, h, &tone, (uint8_t*)img, &st);
+	if (rc != RT_OK) return throw_rt(env, ctx, rc);
+	RT_NAPI_TRY(env, napi_create_object(env, &out));
+#define PUT(name) napi_create_double(env, st.name, &v); napi_set_named_property(env, out, #name, v)
+	PUT(mean); PUT(variance); PUT(absolute_dev); PUT(drange_low); PUT(drange_high);
+#undef PUT
+	return out;
+}
+
 static napi_value PinOrUnpin(napi_env env, napi_callback_info info, int pin) {
 	size_t argc = 2, n = 0;
 	napi_value argv[2];
@@ -196,6 +231,7 @@ napi_value napi_register_module_v1(napi_env env, napi_value exports) {
 	    {"create", NULL, Create, NULL, NULL, NULL, napi_default, NULL},
 	    {"uploadScene", NULL, UploadScene, NULL, NULL, NULL, napi_default, NULL},
 	    {"render", NULL, Render, NULL, NULL, NULL, napi_default, NULL},
+	    {"present", NULL, Present, NULL, NULL, NULL, napi_default, NULL},
 	    {"pin", NULL, Pin, NULL, NULL, NULL, napi_default, NULL},
 	    {"unpin", NULL, Unpin, NULL, NULL, NULL, napi_default, NULL},
 	};
