@@ -35,14 +35,17 @@ struct alignas(32) RtPNode {
 	int child_base, child_mask;
 };
 
-// Octree node record of the bounce stage's ordered walk: the cube, the children (breadth-first numbering, as
-// in RtPNode), the root of the list's BVH and the way up.  Same size and box-first layout as RtBvhNode, so a
-// lane of the walk runs one kind of step - load 32 bytes, slab test, expand - on either.
+// Octree node record of the bounce stage's ordered walk, 64 bytes: the cube, the children (breadth-first
+// numbering, as in RtPNode) and the way up, then the ROOT record of the node's list BVH (same layout as
+// RtBvhNode), so that a node step tests the list's bounding box without another dependent fetch.
 struct alignas(32) RtWNode {
 	float x, y, z, size;
 	int child_base, child_mask;
-	int bvh_root;  // root of the list's BVH in bvh_nodes, -1: empty list
 	int up;        // parent | index_within_parent << 28, -1: root
+	int _pad;
+	float lo[3], hi[3];  // box of the list's entities
+	int a;         // list BVH root: inner: index of its child pair; leaf: first entry in bvh_slots / bvh_geom
+	int b;         // 0: empty list; < 0 inner (-(lowest slot + 1)); > 0 leaf (entries)
 };
 #define RT_WNODE_PARENT_MASK 0x0fffffff
 
@@ -61,7 +64,9 @@ struct alignas(16) RtBvhNode {
 	int b;  // inner: -(lowest slot below this node + 1) (< 0); leaf: number of entries (> 0), ascending slots
 };
 #define RT_BVH_MIN_LIST 24
-#define RT_BVH_LEAF 4
+#ifndef RT_BVH_LEAF
+#define RT_BVH_LEAF 4  // entities per BVH leaf (2 or 4)
+#endif
 #define RT_BVH_STACK 40
 #define RT_NO_SLOT 0x7fffffff
 

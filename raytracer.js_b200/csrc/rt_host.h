@@ -146,8 +146,19 @@ inline void rt_build_list_bvhs(RtHostScene& hs) {
 	for (size_t n = 0; n < N; n++) {
 		const RtPNode& pk = hs.node_pk[n];
 		const RtI4& link = hs.node_link[n];
-		hs.node_walk[n] = RtWNode{pk.x, pk.y, pk.z, pk.size, pk.child_base, pk.child_mask, hs.node_bvh[n],
-		                          link.x < 0 ? -1 : (int)((unsigned)link.x | ((unsigned)link.y << 28))};
+		RtWNode w{};
+		w.x = pk.x; w.y = pk.y; w.z = pk.z; w.size = pk.size;
+		w.child_base = pk.child_base; w.child_mask = pk.child_mask;
+		w.up = link.x < 0 ? -1 : (int)((unsigned)link.x | ((unsigned)link.y << 28));
+		w.a = -1;
+		w.b = 0;
+		if (hs.node_bvh[n] >= 0) {
+			const RtBvhNode& r = hs.bvh_nodes[hs.node_bvh[n]];
+			for (int k = 0; k < 3; k++) { w.lo[k] = r.lo[k]; w.hi[k] = r.hi[k]; }
+			w.a = r.a;
+			w.b = r.b;
+		}
+		hs.node_walk[n] = w;
 	}
 }
 

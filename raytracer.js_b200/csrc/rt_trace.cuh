@@ -738,7 +738,14 @@ RT_HD RtWNode ld(const RtWNode* p) {
 #if defined(__CUDACC__)
 	const float4 a = __ldg(reinterpret_cast<const float4*>(p));
 	const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
-	return RtWNode{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+	const float4 c = __ldg(reinterpret_cast<const float4*>(p) + 2);
+	const int4 d = __ldg(reinterpret_cast<const int4*>(p) + 3);
+	RtWNode n;
+	n.x = a.x; n.y = a.y; n.z = a.z; n.size = a.w;
+	n.child_base = b.x; n.child_mask = b.y; n.up = b.z; n._pad = b.w;
+	n.lo[0] = c.x; n.lo[1] = c.y; n.lo[2] = c.z; n.hi[0] = c.w;
+	n.hi[1] = __int_as_float(d.x); n.hi[2] = __int_as_float(d.y); n.a = d.z; n.b = d.w;
+	return n;
 #else
 	return *p;
 #endif
@@ -1069,9 +1076,10 @@ RT_HD double rng_next(RtRng& g) {
 // lock-step (walk_iter) instead of serialising on the branches of 32 different walker states:
 //   node step  pop the next octree node (or, with the stack empty, go one level up the origin chain), push
 //              the children the ray pierces - last-visited first - and then the root of the node's list BVH;
-//   list step  pop one node of the current list's BVH: slab test, then push its two children (inner) or test
-//              its up to RT_BVH_LEAF entities (leaf), keeping the LOWEST hit slot = the first entity in list
-//              order the ray hits (src/raytracer.ts:186-195).
+//   list step  pop one node of the current list's BVH and fetch its two children together (64 bytes): slab
+//              tests, then push the inner ones that are hit and test the up to RT_BVH_LEAF entities of the
+//              leaves that are hit, keeping the LOWEST hit slot = the first entity in list order the ray hits
+//              (src/raytracer.ts:186-195).
 // The list BVH sits on top of the octree entries, so a list is finished before the next node is popped, and
 // the walk ends at the first list that holds a hit.  A conservative (slack) pierce test can only add nodes,
 // which cannot change a first hit (entities lie inside their node's cube).
@@ -1177,6 +1185,50 @@ RT_HD bool candidate_bounding(const RtF4& g, const RtRayF& r, float err_l) {
 	return l2 <= rr2 && (tca >= 0.0f || cx * cx + cy * cy + cz * cz <= rr2);
 }
 
+// slab test of a BVH box (conservative by W.slack; NaN from 0 * inf is dropped by fminf / fmaxf)
+RT_HD bool walk_hits_box(const RtWalk& W, float lx, float ly, float lz, float hx, float hy, float hz) {
+	const RtRayF& r = W.r;
+	float ta = (lx - r.ox) * r.ix, tb = (hx - r.ox) * r.ix;
+	float tmin = fminf(ta, tb), tmax = fmaxf(ta, tb);
+	ta = (ly - r.oy) * r.iy; tb = (hy - r.oy) * r.iy;
+	tmin = fmaxf(tmin, fminf(ta, tb)); tmax = fminf(tmax, fmaxf(ta, tb));
+	ta = (lz - r.oz) * r.iz; tb = (hz - r.oz) * r.iz;
+	tmin = fmaxf(tmin, fminf(ta, tb)); tmax = fminf(tmax, fmaxf(ta, tb));
+	return !(tmin > tmax + W.slack || tmax < -W.slack);
+}
+
+// The entities of one BVH leaf (padded to RT_BVH_LEAF, ascending slots): the float32 tests of all of them
+// first - independent loads, no branches -, then the float64 confirmation of the candidates in slot order.
+RT_HD void walk_leaf(const RtDevScene& S, RtWalk& W, int leaf_a, const double* o, const double* d) {
+#if RT_BVH_LEAF == 4
+	const RtI4 sl = ld(reinterpret_cast<const RtI4*>(S.bvh_slots + leaf_a));
+	const int slots[RT_BVH_LEAF] = {sl.x, sl.y, sl.z, sl.w};
+#else
+	int slots[RT_BVH_LEAF];
+#pragma unroll
+	for (int k = 0; k < RT_BVH_LEAF; k++) slots[k] = ld(S.bvh_slots + leaf_a + k);
+#endif
+	unsigned cand = 0, spheres = 0;
+#pragma unroll
+	for (int k = 0; k < RT_BVH_LEAF; k++) {
+		const RtF4 g = ld(S.bvh_geom + leaf_a + k);
+		cand |= (slots[k] < W.best && candidate_bounding(g, W.r, S.err_l) ? 1u : 0u) << k;
+		spheres |= (g.w > 0.0f ? 1u : 0u) << k;
+	}
+	while (cand) {
+		const int k = ffs32(cand);
+		cand &= cand - 1;
+		int s = slots[0];
+#pragma unroll
+		for (int q = 1; q < RT_BVH_LEAF; q++) s = k == q ? slots[q] : s;
+		if (s >= W.best) break;
+		if (confirm_hit(S, s, (spheres >> k) & 1u, o, d)) {
+			W.best = s;  // ascending slots: the later candidates of this leaf cannot beat it
+			break;
+		}
+	}
+}
+
 // One iteration of the walk for every lane of the warp (`walking`: this lane takes part).  Returns false
 // when this lane's walk is over (W.hit = slot or -1).  LOCKSTEP: all 32 lanes of the warp call this together
 // (bounce stage) and the phases re-converge the warp between them; without it the caller may be one lane of a
@@ -1212,69 +1264,53 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 		}
 	}
 	if (LOCKSTEP) warp_sync();
-	// (b) its record: children, list
+	// (b) its 64-byte record: children, then the root of the list's BVH (box test right here)
+	int leaf0 = -1, leaf1 = -1;  // leaves whose entities are to be tested in this iteration
 	if (rec_node >= 0) {
 		const RtWNode nd = ld(S.node_walk + rec_node);
 		if (push) walk_push_children(W, nd, after);
 		else W.chain_up = nd.up;
-		if (list && nd.bvh_root >= 0) {
+		if (list && nd.b != 0 && walk_hits_box(W, nd.lo[0], nd.lo[1], nd.lo[2], nd.hi[0], nd.hi[1], nd.hi[2])) {
 			W.floor = W.sp;
-			W.stack[W.sp++] = nd.bvh_root;  // (room for the list BVH is part of RT_WALK_STACK: rt_ordered_walk_fits)
 			W.in_list = 1;
 			W.best = RT_NO_SLOT;
+			if (nd.b < 0) W.stack[W.sp++] = nd.a;  // (room for the list BVH is part of RT_WALK_STACK: rt_ordered_walk_fits)
+			else leaf0 = nd.a;
 		}
 	}
 	if (LOCKSTEP) warp_sync();
-	// ---- list step
-	int leaf_a = 0, leaf_n = 0;
-	if (walking && W.in_list) {
-		const RtRayF& r = W.r;
+	// ---- list step: the two children of a BVH node are neighbours in memory and are fetched and tested
+	// together (half as many dependent fetches as one node per step)
+	if (walking && W.in_list && W.sp > W.floor) {
 		const RtBvhNode* np = S.bvh_nodes + W.stack[--W.sp];
-		const RtF4 n0 = ld(reinterpret_cast<const RtF4*>(np));
-		const RtI4 n1 = ld(reinterpret_cast<const RtI4*>(np) + 1);
-		// n0 = lo.xyz, hi.x ; n1 = hi.y, hi.z (as bits), a, b
-		const float hy = int_as_float(n1.x), hz = int_as_float(n1.y);
-		float ta = (n0.x - r.ox) * r.ix, tb = (n0.w - r.ox) * r.ix;
-		float tmin = fminf(ta, tb), tmax = fmaxf(ta, tb);
-		ta = (n0.y - r.oy) * r.iy; tb = (hy - r.oy) * r.iy;
-		tmin = fmaxf(tmin, fminf(ta, tb)); tmax = fminf(tmax, fmaxf(ta, tb));
-		ta = (n0.z - r.oz) * r.iz; tb = (hz - r.oz) * r.iz;
-		tmin = fmaxf(tmin, fminf(ta, tb)); tmax = fminf(tmax, fmaxf(ta, tb));
-		if (!(tmin > tmax + W.slack || tmax < -W.slack)) {  // (NaN from 0 * inf compares false: kept)
-			if (n1.w < 0) {
-				if (-(n1.w + 1) < W.best) {  // else: nothing below this node can beat the hit we have
-					W.stack[W.sp++] = n1.z + 1;
-					W.stack[W.sp++] = n1.z;  // the child with the lowest slot first
-				}
+		const RtF4 a0 = ld(reinterpret_cast<const RtF4*>(np));
+		const RtI4 a1 = ld(reinterpret_cast<const RtI4*>(np) + 1);
+		const RtF4 b0 = ld(reinterpret_cast<const RtF4*>(np) + 2);
+		const RtI4 b1 = ld(reinterpret_cast<const RtI4*>(np) + 3);
+		// x0 = lo.xyz, hi.x ; x1 = hi.y, hi.z (as bits), a, b
+		const bool hit_a = walk_hits_box(W, a0.x, a0.y, a0.z, a0.w, int_as_float(a1.x), int_as_float(a1.y));
+		const bool hit_b = walk_hits_box(W, b0.x, b0.y, b0.z, b0.w, int_as_float(b1.x), int_as_float(b1.y));
+		// the right sibling first, so that the left one - which holds the lowest slot - is popped first
+		if (hit_b) {
+			if (b1.w < 0) {
+				if (-(b1.w + 1) < W.best) W.stack[W.sp++] = b1.z;  // else: nothing below can beat the hit we have
 			} else {
-				leaf_a = n1.z;
-				leaf_n = n1.w;
+				leaf1 = b1.z;
+			}
+		}
+		if (hit_a) {
+			if (a1.w < 0) {
+				if (-(a1.w + 1) < W.best) W.stack[W.sp++] = a1.z;
+			} else {
+				leaf0 = a1.z;
 			}
 		}
 	}
 	if (LOCKSTEP) warp_sync();
-	// ---- leaf entries (padded to RT_BVH_LEAF, ascending slots): the float32 tests of all of them first -
-	// independent loads, no branches -, then the float64 confirmation of the candidates in slot order
-	if (leaf_n) {
-		const RtI4 sl = ld(reinterpret_cast<const RtI4*>(S.bvh_slots + leaf_a));
-		const int slots[RT_BVH_LEAF] = {sl.x, sl.y, sl.z, sl.w};
-		unsigned cand = 0, spheres = 0;
-#pragma unroll
-		for (int k = 0; k < RT_BVH_LEAF; k++) {
-			const RtF4 g = ld(S.bvh_geom + leaf_a + k);
-			cand |= (slots[k] < W.best && candidate_bounding(g, W.r, S.err_l) ? 1u : 0u) << k;
-			spheres |= (g.w > 0.0f ? 1u : 0u) << k;
-		}
-		while (cand) {
-			const int k = ffs32(cand);
-			cand &= cand - 1;
-			const int s = k == 0 ? slots[0] : k == 1 ? slots[1] : k == 2 ? slots[2] : slots[3];
-			if (confirm_hit(S, s, (spheres >> k) & 1u, o, d)) {
-				W.best = s;  // ascending slots: the later candidates of this leaf cannot beat it
-				break;
-			}
-		}
-	}
+	// ---- leaf entities
+	if (leaf0 >= 0) walk_leaf(S, W, leaf0, o, d);
+	if (LOCKSTEP) warp_sync();
+	if (leaf1 >= 0) walk_leaf(S, W, leaf1, o, d);
 	if (LOCKSTEP) warp_sync();
 	if (walking && W.in_list && W.sp == W.floor) {  // the list is finished
 		W.in_list = 0;
