@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, RT_A_MINB)
 // 12 lanes store as whole 16-byte words - full sectors instead of three strided 4-byte stores per lane, which
 // is what matters when the frame lives in another GPU's memory (rt_render_shard_device: every store is an
 // NVLink write).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
     rt_shade_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, size_t n_out) {
 	__shared__ __align__(16) float stage[256 * 3];
 	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(256)
 			y = (tile / tiles_x) * RT_TILE_H + (in / RT_TILE_W);
 			valid = valid && x < F.width && y < F.height;
 			i = F.tile_compact ? t : (size_t)y * F.width + x;
+		} else if (i <= 0xffffffffull) {  // (32-bit division: the 64-bit one is a long instruction sequence)
+			y = (int)((unsigned)i / (unsigned)F.width);
+			x = (int)((unsigned)i - (unsigned)y * (unsigned)F.width);
 		} else {
 			y = (int)(i / F.width);
 			x = (int)(i % F.width);

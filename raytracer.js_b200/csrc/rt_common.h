@@ -148,6 +148,7 @@ struct RtFrame {
 	double attenuation;
 	// exposure + rng
 	uint32_t n_frames, frame_first;
+	double w_first, w1_first;  // ExposureBuffer.col_weight of the first frame, 1/(1+frame_first), and 1 - it (host-computed: same IEEE ops)
 	double rng_seed;
 	// outputs
 	float* rgb;

@@ -504,6 +504,8 @@ inline rt_status rt_fill_frame(const RtHostScene& hs, const rt_camera* cam, cons
 	F.attenuation = prm->distance_attenuation_factor;
 	F.n_frames = prm->n_frames;
 	F.frame_first = prm->frame_first;
+	F.w_first = 1.0 / (double)(1u + prm->frame_first);  // ExposureBuffer.next_frame (src/view/exposure_buffer.ts:58)
+	F.w1_first = 1.0 - F.w_first;
 	F.rng_seed = prm->rng_seed;
 	return RT_OK;
 }

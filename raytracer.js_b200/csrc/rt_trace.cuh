@@ -1674,8 +1674,8 @@ RT_HD void blend_constant_sample(const RtFrame& F, size_t out_index, const doubl
 		px[0] = o[0]; px[1] = o[1]; px[2] = o[2];
 	}
 	for (uint32_t f = 0; f < F.n_frames; f++) {
-		const double w = xdiv(1.0, (double)(1u + F.frame_first + f));
-		const double w1 = xsub(1.0, w);
+		const double w = f == 0 ? F.w_first : xdiv(1.0, (double)(1u + F.frame_first + f));
+		const double w1 = f == 0 ? F.w1_first : xsub(1.0, w);
 #pragma unroll
 		for (int k = 0; k < 3; k++) px[k] = (float)xadd(xmul(c[k], w), xmul((double)px[k], w1));
 	}
