@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const unsigned n = *F.vqueue_count;
 	const unsigned nf = F.n_frames;
-	const unsigned G = min(32u, max(1u, RT_RESAMPLE_POOL / nf));  // pixels per group
+	const unsigned G_max = min(32u, max(1u, RT_RESAMPLE_POOL / nf));  // pixels per group
+	const unsigned n_warps = gridDim.x * RT_WARPS_PER_CTA;
 	const size_t warp_id = (size_t)blockIdx.x * RT_WARPS_PER_CTA + (threadIdx.x >> 5);
 	double* const samples = F.samples + warp_id * F.samples_per_warp;  // [G][nf][3] behind a header of 32 ints
 	int* const group_entity = reinterpret_cast<int*>(samples);
@@ -345,9 +346,17 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 	uint32_t err = 0;
 	while (true) {
 		// ---- the next group of pixels
-		unsigned g0 = 0;
-		if (lane == 0) g0 = atomicAdd(F.vqueue_taken, G);
+		// guided self-scheduling: full groups while the queue is long, smaller ones towards its end, so that
+		// the last pools - the tail of the frame - are short
+		unsigned g0 = 0, G = G_max;
+		if (lane == 0) {
+			const unsigned taken = *reinterpret_cast<volatile unsigned*>(F.vqueue_taken);
+			const unsigned left = taken < n ? n - taken : 0u;
+			G = max(1u, min(G_max, left / (2u * n_warps)));
+			g0 = atomicAdd(F.vqueue_taken, G);
+		}
 		g0 = __shfl_sync(0xffffffffu, g0, 0);
+		G = __shfl_sync(0xffffffffu, G, 0);
 		if (g0 >= n) break;
 		const unsigned g_cnt = min(G, n - g0), pool = g_cnt * nf;
 		unsigned next = 0;  // warp-uniform cursor into the pool
