@@ -277,6 +277,14 @@ rt_status rt_peer_barrier(rt_ctx* ctx, uint32_t rank, uint32_t world, uint32_t* 
 typedef struct rt_tree rt_tree;
 rt_status rt_tree_build(const double root_pos[3], double root_size, uint32_t n_entities, const uint8_t* ent_type,
                         const double* ent_pos, const double* ent_extent, uint32_t max_in_depth, rt_tree** out);
+/* The same builder on the GPU (max_in_depth <= 16): one thread per entity computes the path key of its node
+ * with the reference's float64 expressions, the node set is the sort + unique of all path prefixes (which is
+ * the depth-first pre-order, children 0..7), node positions are replayed per node, and a stable sort by node
+ * keeps the insertion order inside every list.  Same tree as rt_tree_build (same nodes, positions, lists);
+ * the node NUMBERING differs (pre-order here, creation order there), which rt_scene_upload does not care about.
+ * Errors as rt_tree_build, message in rt_last_error(ctx). */
+rt_status rt_tree_build_gpu(rt_ctx* ctx, const double root_pos[3], double root_size, uint32_t n_entities, const uint8_t* ent_type,
+                            const double* ent_pos, const double* ent_extent, uint32_t max_in_depth, rt_tree** out);
 uint32_t rt_tree_node_count(const rt_tree* t);
 /* Fills the node arrays of an rt_scene_desc (sizes from rt_tree_node_count / n_entities); entity ids in
  * list_entity are the indices of the arrays given to rt_tree_build. */

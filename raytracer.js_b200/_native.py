@@ -103,6 +103,7 @@ EXPORTS = {
     "rt_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_peer_barrier": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32]),
     "rt_tree_build": (C.c_int, [_dp, C.c_double, C.c_uint32, _bp, _dp, _dp, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "rt_tree_build_gpu": (C.c_int, [C.c_void_p, _dp, C.c_double, C.c_uint32, _bp, _dp, _dp, C.c_uint32, C.POINTER(C.c_void_p)]),
     "rt_tree_node_count": (C.c_uint32, [C.c_void_p]),
     "rt_tree_export": (None, [C.c_void_p, _dp, _dp, _ip, _ip, _ip, _up, _up]),
     "rt_tree_free": (None, [C.c_void_p]),

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librt_b200.so")
 SOURCES = ["rt_b200.cu"]
-HEADERS = ["rt_common.h", "rt_host.h", "rt_build.h", "rt_trace.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
+HEADERS = ["rt_common.h", "rt_host.h", "rt_build.h", "rt_build_gpu.cuh", "rt_trace.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -6,6 +6,7 @@
 #include <functional>
 
 #include "rt_build.h"
+#include "rt_build_gpu.cuh"
 #include "rt_host.h"
 #include "rt_trace.cuh"
 
@@ -1247,6 +1248,29 @@ rt_status rt_tree_build(const double root_pos[3], double root_size, uint32_t n, 
 	if (!rt_tree_build_impl(*t, root_pos, root_size, n, type, pos, extent, max_in_depth, err)) {
 		delete t;
 		return fail(nullptr, RT_ERR_UNSUPPORTED, err);
+	}
+	*out = t;
+	return RT_OK;
+}
+
+rt_status rt_tree_build_gpu(rt_ctx* ctx, const double root_pos[3], double root_size, uint32_t n, const uint8_t* type,
+                            const double* pos, const double* extent, uint32_t max_in_depth, rt_tree** out) {
+	if (!ctx) return RT_ERR_INVALID;
+	if (!out) return fail(ctx, RT_ERR_INVALID, "rt_tree_build_gpu: out is NULL");
+	*out = nullptr;
+	if (!root_pos || !(root_size > 0) || (n && (!type || !pos || !extent)))
+		return fail(ctx, RT_ERR_INVALID, "rt_tree_build_gpu: bad arguments");
+	if (max_in_depth > RT_GPU_BUILD_MAX_DEPTH)
+		return fail(ctx, RT_ERR_UNSUPPORTED, rt_format("rt_tree_build_gpu: max_in_depth %u > %d (path keys hold 16 levels); use rt_tree_build", max_in_depth, RT_GPU_BUILD_MAX_DEPTH));
+	if ((uint64_t)n * (max_in_depth + 1) + 1 > 0x7fffffffull)
+		return fail(ctx, RT_ERR_UNSUPPORTED, "rt_tree_build_gpu: too many entities for one sort");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	rt_tree* t = new rt_tree();
+	std::string err;
+	const int rc = rt_gpu_build::build(*t, ctx->stream, root_pos, root_size, n, type, pos, extent, max_in_depth, err, &ctx->launches);
+	if (rc != 0) {
+		delete t;
+		return fail(ctx, rc == 1 ? RT_ERR_UNSUPPORTED : RT_ERR_CUDA, err);
 	}
 	*out = t;
 	return RT_OK;

@@ -203,11 +203,13 @@ def flatten_scene(tree: Octree, extra_textures=(), extra_substances=()) -> FlatS
 
 
 def flat_from_arrays(ent_type, ent_pos, ent_extent, ent_material, ent_texture, ent_substance, materials, textures,
-                     substances, root_pos=(0.0, 0.0, 0.0), root_size=1.0, max_in_depth=16) -> FlatScene:
+                     substances, root_pos=(0.0, 0.0, 0.0), root_size=1.0, max_in_depth=16, gpu_ctx=None) -> FlatScene:
     """Bulk path for big scenes: the octree is built by the native restatement of add_entity_to_octree
     (rt_tree_build in librt_b200, csrc/rt_build.h) straight from entity arrays, without Python entity
     objects or a pointer tree.  Entity ids are the array indices (= insertion order).  `materials`,
-    `textures`, `substances` are lists of the host API's objects, indexed by the ent_* index arrays."""
+    `textures`, `substances` are lists of the host API's objects, indexed by the ent_* index arrays.
+    gpu_ctx: an rt_ctx (GpuRaytracer.ctx) -> the tree is built on that GPU (rt_tree_build_gpu, csrc/rt_build_gpu.cuh):
+    the same tree, nodes numbered in depth-first pre-order."""
     lib = N.load()
     fs = FlatScene()
     for m in materials:
@@ -226,13 +228,13 @@ def flat_from_arrays(ent_type, ent_pos, ent_extent, ent_material, ent_texture, e
     n = len(a["ent_extent"])
     rp = np.ascontiguousarray(root_pos, np.float64)
     tree = C.c_void_p()
-    st = lib.rt_tree_build(rp.ctypes.data_as(N._dp), float(root_size), n, a["ent_type"].ctypes.data_as(N._bp),
-                           a["ent_pos"].ctypes.data_as(N._dp), a["ent_extent"].ctypes.data_as(N._dp), int(max_in_depth),
-                           C.byref(tree))
+    args = (rp.ctypes.data_as(N._dp), float(root_size), n, a["ent_type"].ctypes.data_as(N._bp),
+            a["ent_pos"].ctypes.data_as(N._dp), a["ent_extent"].ctypes.data_as(N._dp), int(max_in_depth), C.byref(tree))
+    st = lib.rt_tree_build_gpu(gpu_ctx, *args) if gpu_ctx is not None else lib.rt_tree_build(*args)
     if st != N.RT_OK:
         from .octree_entity import TreeOutsideGrowError
-        msg = lib.rt_last_error(None).decode()
-        if st == N.RT_ERR_UNSUPPORTED:
+        msg = lib.rt_last_error(gpu_ctx).decode()
+        if st == N.RT_ERR_UNSUPPORTED and "outside-depth" in msg:
             raise TreeOutsideGrowError(None, msg)
         raise N.RtError(st, msg)
     try:
