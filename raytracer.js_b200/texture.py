@@ -1,8 +1,9 @@
 """Textures (src/texture/texture.ts, texture_solid.ts, texture_image.ts).
 
 The nearest-texel lookup itself (texture_image.ts:40-63) runs on the GPU; the host objects only carry
-the data.  ImageTexture here is array-backed: the reference's decoder (`new Image()` + canvas,
-texture_image.ts:76-136) is browser-only and out of scope."""
+the data.  ImageTexture here is array-backed; the reference's decoder (`new Image()` + canvas,
+texture_image.ts:76-136) is browser-only, ImageTexture.from_file stands in for it on the host with Pillow
+(SURVEY.md 8f N3): same RGB8 texels, same flip semantics."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -51,3 +52,18 @@ class ImageTexture(Texture):
 
     def get_size(self):
         return (self.width, self.height) if self.image_data is not None else None
+
+    @classmethod
+    def from_file(cls, image_url: str, fallback_color: Color, horizontal_flip=False, vertical_flip=False) -> "ImageTexture":
+        """`new ImageTexture(image_url, fallback_color, hflip, vflip)` (texture_image.ts:28-38) with the decode
+        done on the host: the image is drawn as the canvas would hold it (8-bit RGB, row 0 first; the alpha
+        channel is dropped like `image_data[index+3]` is never read), then flipped as load_image does
+        (:103-113).  A file that cannot be decoded leaves the texture unloaded: lookups answer the fallback
+        colour, as while the reference's loading promise is pending or rejected."""
+        try:
+            from PIL import Image
+            with Image.open(image_url) as im:
+                px = np.asarray(im.convert("RGB"), dtype=np.uint8)
+        except Exception:
+            return cls(None, fallback_color)
+        return cls(px, fallback_color, horizontal_flip, vertical_flip)

@@ -131,3 +131,19 @@ def test_bulk_builder_rejects_entities_outside_the_root():
     tex = rt.SolidTexture(rt.Color(1, 1, 1, 1))
     with pytest.raises(rt.TreeOutsideGrowError):
         flat_from_arrays([0], [[0.99, 0.5, 0.5]], [0.1], [0], [0], [0], [mat], [tex], [rt.SUBSTANCE_AIR])
+
+
+def test_image_texture_from_file(tmp_path):
+    """ImageTexture.from_file (host stand-in for the browser-only load_image, src/texture/texture_image.ts:76-136):
+    RGB8 texels in row order, flips as the reference's index arithmetic does them, fallback when undecodable."""
+    from PIL import Image
+    px = np.arange(2 * 3 * 3, dtype=np.uint8).reshape(2, 3, 3) * 10
+    rgba = np.dstack([px, np.full((2, 3, 1), 128, np.uint8)])
+    Image.fromarray(rgba, "RGBA").save(tmp_path / "t.png")
+    fb = rt.Color(1, 0, 1, 1)
+    t = rt.ImageTexture.from_file(str(tmp_path / "t.png"), fb)
+    assert t.get_size() == (3, 2) and np.array_equal(t.image_data, px)  # alpha dropped, rows top to bottom
+    t = rt.ImageTexture.from_file(str(tmp_path / "t.png"), fb, horizontal_flip=True, vertical_flip=True)
+    assert np.array_equal(t.image_data, px[::-1, ::-1])
+    missing = rt.ImageTexture.from_file(str(tmp_path / "nope.png"), fb)
+    assert missing.get_size() is None and missing.image_data is None and missing.fallback_color is fb
