@@ -684,10 +684,10 @@ struct rt_ctx {
 	std::vector<uint32_t*> peer_flags_host;
 	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
 	int ppl = RT_PPL;
-	int bounce_min_walking = 24;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
+	int bounce_min_walking = 12;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
 	int bounce_minb = 8;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
-	int bounce_node_batch = 8;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
+	int bounce_node_batch = 4;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
 };
 
 namespace {
