@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 	size_t out_index = 0;
 	uint32_t frame = 0;
 	float px[3] = {0.f, 0.f, 0.f};
-	RtPath P;
+	RtPath P = {};  // (set by path_begin before any use; value-initialised to keep the compiler quiet)
 	RtWalk W;
 	bool exhausted = n == 0;
 	// a sample (path colour c) of exposure frame `frame` is complete: ExposureBuffer.set_color_i
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 		int st = RT_ST_IDLE;
 		unsigned job = 0;
 		int x = 0, y = 0, slot = RT_SLOT_UNKNOWN;
-		RtPath P;
+		RtPath P = {};
 		RtWalk W;
 		auto sample_done = [&](const double* c) {
 			double* o = colour + (size_t)job * 3;
