@@ -298,6 +298,17 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 		}
 	}
 	hs.err_l = (float)(16.0 * 1.1920929e-7 * scale);
+	{
+		// The search runs in float32 (RT_PRECISION_F32): a cell's corners and centre must be distinct float32
+		// numbers at the scene's coordinate scale, or the walkers cannot tell neighbouring cells apart.  With a
+		// unit root that is 23 levels; the reference (float64 throughout) has no such limit.
+		double min_size = sc->node_size[0];
+		for (uint32_t i = 0; i < N; i++) min_size = std::min(min_size, sc->node_size[i]);
+		const double ulp = std::ldexp(1.0, std::ilogb(scale > 0 ? scale : 1.0) - 23);
+		if (min_size * 0.5 < ulp)
+			RT_FAIL(RT_ERR_UNSUPPORTED, "octree cells of size %.3g are below the float32 resolution of the search at coordinate scale %.3g "
+			                            "(a unit root allows 23 levels): lower max_in_depth", min_size, scale);
+	}
 	rt_build_list_bvhs(hs);
 	hs.materials.resize(sc->n_materials);
 	hs.any_transmission = false;

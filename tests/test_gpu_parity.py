@@ -314,3 +314,24 @@ def test_repeated_device_renders_replay_a_graph():
     # an eager call launches prepare + primary + shade + bounce; a replayed graph leaves out the per-camera
     # preparation (the call it repeats left its result on the device)
     assert min(launches) >= 3 and max(launches) - min(launches) <= 1 and launches[2] == launches[3], launches
+
+
+@pytest.mark.parametrize("max_in_depth", [20, 23])
+def test_deep_trees_take_the_fallback_walker(oracle, max_in_depth):
+    """An octree deeper than the bounce stage's walk stack (RT_WALK_STACK): secondary rays are searched by the
+    reference-order walker instead of the lock-step one; same pixels as the oracle.  Deeper than float32 can
+    resolve: refused (RT_ERR_UNSUPPORTED)."""
+    from test_hostsim_parity import deep_scene
+    b = deep_scene(max_in_depth)
+    rgb, ids, cnt, tracer = gpu_render(b, 64, 64, n_frames=2)
+    flat = tracer.flat
+    ocam = orc.Camera(math.pi / 2, math.pi / 2, 64, 64, scenes.BENCH_CAMERA_POS, 0.0, math.pi / 6, vertical_locked=True)
+    prm = make_params(flat, b, n_frames=2)
+    orgb, oids, _, tot = oracle_render(oracle_scene(flat, b, max_in_depth=max_in_depth), ocam, flat, b, prm, fixed_extents=True)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
+    if max_in_depth == 23:
+        deep = deep_scene(30)
+        with pytest.raises(N.RtError, match="float32 resolution"):
+            rt.GpuRaytracer(rt.RaytracerConfig(deep.refmax, deep.sky, deep.default_substance, 1.0), deep.tree,
+                            scenes.bench_camera(64, 64), rt.ExposureBuffer(64, 64), rt.FpLcg(1.0))

@@ -238,3 +238,58 @@ def test_shards_write_one_frame(oracle, pipeline):
         mine = ((ty // 16) * ((W + 15) // 16) + tx // 16) % world == r
         np.testing.assert_array_equal(frame[~mine], before[~mine])
     np.testing.assert_array_equal(frame, full)
+
+
+def deep_scene(max_in_depth):
+    """A mirror scene plus a few tiny mirror spheres close to the camera, small enough to sit `max_in_depth`
+    levels down: the octree is deeper than the bounce stage's walk stack allows (RT_WALK_STACK), so the
+    fallback walker does the work."""
+    b = scenes.random_spheres(400, 0.02, 0.08, seed=13.0, mix="mirrors", box_fraction=0.1)
+    mirror = rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0)
+    cam, _ = cameras(64, 64)
+    dirs = {(x, y): v.v for x, y, v in cam.get_dir_for_each_pixel()}
+    p0 = np.array(scenes.BENCH_CAMERA_POS)
+    tiny = 2.0 ** -(max_in_depth - 1)  # a sphere of this diameter fits cells down to about max_in_depth - 1
+    for k, (x, y) in enumerate([(20, 20), (40, 24), (32, 40), (12, 50)]):
+        d = np.array(dirs[(x, y)])
+        c = p0 + d / np.linalg.norm(d) * tiny * 12  # ~1/12 rad wide: a few pixels at 64 px over 90 degrees
+        e = rt.SphereEntity(None, mirror, rt.SolidTexture(rt.Color(0.9, 0.4 + 0.1 * k, 0.2, 1)), rt.SUBSTANCE_AIR, rt.point(*c), tiny)
+        rt.add_entity_to_octree(b.tree, e, {"max_in_depth": max_in_depth, "max_out_depth": 0})
+        b.entities.append(e)
+    return b
+
+
+def test_trees_below_float32_resolution_are_refused():
+    """Cells smaller than a float32 ulp of the coordinates cannot be searched in float32: the scene is refused
+    with a clear message instead of being rendered wrongly (the reference, float64 throughout, has no limit)."""
+    b = deep_scene(30)
+    flat = flat_of(b)
+    cam, _ = cameras(64, 64)
+    with pytest.raises(RuntimeError, match="float32 resolution"):
+        hostsim_render(flat, cam, make_params(flat, b))
+
+
+@pytest.mark.parametrize("max_in_depth", [20, 23])
+def test_trees_deeper_than_the_walk_stacks(oracle, max_in_depth):
+    b = deep_scene(max_in_depth)
+    flat = flat_of(b)
+    depth = 0
+    par = flat.arrays["node_parent"]
+    for i in range(len(par)):  # deepest node
+        d, j = 0, i
+        while par[j] >= 0:
+            j = par[j]
+            d += 1
+        depth = max(depth, d)
+    assert depth >= max_in_depth - 3, depth
+    cam, ocam = cameras(64, 64)
+    prm = make_params(flat, b, n_frames=2)
+    rgb, ids, cnt = hostsim_render(flat, cam, prm)
+    rgb_p, ids_p, _ = hostsim_render(flat, cam, prm, pipeline=True)
+    np.testing.assert_array_equal(ids_p, ids)
+    np.testing.assert_array_equal(rgb_p, rgb)
+    orgb, oids, _, tot = oracle_render(oracle_scene(flat, b, max_in_depth=max_in_depth), ocam, flat, b, prm, fixed_extents=True)
+    ids = insertion_ids(flat, b, ids)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
+    assert len(set(ids.ravel().tolist()) & set(range(len(b.entities) - 4, len(b.entities)))) >= 2  # the tiny spheres are seen
