@@ -354,6 +354,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # what actually bounds the dominant kernel (L1/L2-resident scene): issue slots, from the committed ncu capture
+    issue = None
+    try:
+        prof = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_summary.json"))[-1]
+        pk = json.load(open(os.path.join(ROOT, "profiles", prof)))["primary"]
+        issue = {"kernel": pk["kernel"], "issue_slot_utilisation_pct": pk["smsp__issue_active.avg.pct_of_peak_sustained_active"],
+                 "active_lanes_per_instruction": pk["smsp__thread_inst_executed_per_inst_executed.ratio"],
+                 "registers_per_thread": pk["launch__registers_per_thread"], "source": f"profiles/{prof} (ncu --set full, not live)"}
+    except Exception:
+        pass
     out = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -370,7 +380,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "path": args.path},
         "clocks": clocks, "e2e": e2e, "present": present, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src, "issue": issue,
                      "algorithmic_bytes_per_segment": bytes_per_segment,
                      "per_segment": {"nodes": nodes / segments, "tests": tests / segments, "shades": shades / segments},
                      "kernel": "the step's launches together (prepare + primary + shade + bounce); rt_primary_kernel is ~80% of "
