@@ -206,13 +206,19 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 		if (i > 0 && (par < 0 || (uint32_t)par >= N)) RT_FAIL(RT_ERR_INVALID, "node %u: bad parent %d", i, par);
 		const int oc = sc->node_octant[i];
 		if (i > 0 && (oc < 0 || oc > 7)) RT_FAIL(RT_ERR_INVALID, "node %u: bad octant %d", i, oc);
+		// node_octant is the reference's index_within_parent() (src/octree_space.ts:110-125), which derives the
+		// index from the cell positions ("FIXME: ... not merely by checking geometry"): for a root whose cell
+		// corners are not exactly representable it can disagree with the slot the node really sits in, and the
+		// reference's own walker then steps back into the wrong octant.  Such a tree is refused, not guessed at.
+#define RT_OCTANT_HINT "index_within_parent() disagrees with the child slot (src/octree_space.ts:110-125 computes it from positions): " \
+	"use a root cube whose size is a power of two, placed at a multiple of it"
 		if (i > 0 && sc->node_child[(size_t)par * 8 + oc] != (int)i)
-			RT_FAIL(RT_ERR_INVALID, "node %u: parent %d does not list it as child %d", i, par, oc);
+			RT_FAIL(RT_ERR_INVALID, "node %u: parent %d does not list it as child %d; " RT_OCTANT_HINT, i, par, oc);
 		for (int c = 0; c < 8; c++) {
 			const int ch = sc->node_child[(size_t)i * 8 + c];
 			if (ch < -1 || ch >= (int)N || ch == 0) RT_FAIL(RT_ERR_INVALID, "node %u: bad child %d", i, ch);
 			if (ch > 0 && (sc->node_parent[ch] != (int)i || sc->node_octant[ch] != c))
-				RT_FAIL(RT_ERR_INVALID, "node %u: child %d does not point back", i, ch);
+				RT_FAIL(RT_ERR_INVALID, "node %u: child %d does not point back; " RT_OCTANT_HINT, i, ch);
 		}
 	}
 	std::vector<int> perm(N, -1), order;  // perm[old] = new, order[new] = old

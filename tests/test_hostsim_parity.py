@@ -293,3 +293,42 @@ def test_trees_deeper_than_the_walk_stacks(oracle, max_in_depth):
     res = compare(rgb, ids, orgb, oids)
     assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
     assert len(set(ids.ravel().tolist()) & set(range(len(b.entities) - 4, len(b.entities)))) >= 2  # the tiny spheres are seen
+
+
+def _scene_in_root(root_pos, root_size, n=500):
+    rng = rt.FpLcg(5.0)
+    tree = rt.new_entity_octree(rt.OctreeDim(rt.point(*root_pos), root_size), None)
+    mats = [rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0.0), rt.SolidMaterial(rt.ResponseType.REFLECTION, False, False, 0.0),
+            rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0.5), rt.SolidMaterial(rt.ResponseType.REFLECTION, True, False, 0.0)]
+    ents = []
+    for _ in range(n):
+        d = 0.01 + rng.next() * 0.05
+        c = [d / 2 + rng.next() * (1 - d) for _ in range(3)]
+        m = mats[int(rng.next() * 4)]
+        tex = rt.SolidTexture(rt.Color(rng.next(), rng.next(), rng.next(), 1))
+        cls = rt.BoxEntity if rng.next() < 0.2 else rt.SphereEntity
+        e = cls(None, m, tex, rt.SUBSTANCE_AIR, rt.point(*[root_pos[k] + root_size * c[k] for k in range(3)]), d * root_size)
+        rt.add_entity_to_octree(tree, e, {"max_in_depth": 16, "max_out_depth": 0})
+        ents.append(e)
+    return scenes.SceneBundle(tree, ents, rt.SkySphere(rt.SolidTexture(rt.Color(0.2, 0.2, 0.7, 1))), rt.SUBSTANCE_AIR, 4)
+
+
+@pytest.mark.parametrize("root_pos,root_size", [((-1.0, -1.0, -1.0), 2.0), ((4.0, -8.0, 12.0), 4.0), ((0.25, 0.5, -0.75), 0.25)])
+def test_other_dyadic_roots(oracle, root_pos, root_size):
+    """Roots other than the demo's unit cube at the origin (power-of-two size at a multiple of it)."""
+    b = _scene_in_root(root_pos, root_size)
+    pos = tuple(root_pos[k] + root_size * scenes.BENCH_CAMERA_POS[k] for k in range(3))
+    res, cnt, tot, _ = run_both(b, 80, 80, n_frames=2, pos=pos)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
+    assert cnt["segments"] == tot["segments"]
+
+
+def test_roots_that_break_index_within_parent_are_refused():
+    """index_within_parent() (src/octree_space.ts:110-125, its own FIXME) takes the child index from the cell
+    positions; with a root like (-3.7, 2.1, 10.3) x 5.3 rounding makes it disagree with the slot a node sits in,
+    and the reference's walker steps back into the wrong octant.  The tree is refused with that explanation."""
+    b = _scene_in_root((-3.7, 2.1, 10.3), 5.3)
+    flat = flat_of(b)
+    cam, _ = cameras(32, 32)
+    with pytest.raises(RuntimeError, match="index_within_parent"):
+        hostsim_render(flat, cam, make_params(flat, b))
