@@ -685,6 +685,7 @@ struct rt_ctx {
 	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
 	int ppl = RT_PPL;
 	int bounce_min_walking = 12;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
+	int resample_min_frames = 8;                 // tuning knob RT_B200_RESAMPLE_MIN
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
 	int bounce_minb = 8;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
 	int bounce_node_batch = 4;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
@@ -819,7 +820,10 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	}
 	const bool pipeline = F.packet_ok && !count && !(prm->flags & RT_PARAM_PER_RAY);
 	if (!pipeline) F.packet_ok = 0;
-	const bool resample = pipeline && prm->n_frames > 1 && ctx->resample;  // rough pixels: frames traced 32 at a time by a warp
+	// rough pixels: from RT_RESAMPLE_MIN_FRAMES exposure frames on, their frames are traced as independent samples
+	// by the resample stage (below that the bounce stage's lane traces them in a row: re-tracing the first frame
+	// and pooling cost more than the short tail they remove)
+	const bool resample = pipeline && prm->n_frames >= (uint32_t)ctx->resample_min_frames && ctx->resample;
 	if (pipeline) {
 		const size_t cap = tile_compact ? (size_t)((n_tiles - tile_rank + tile_world - 1) / tile_world) * RT_BLOCK
 		                                : (size_t)F.width * F.height;
@@ -1025,6 +1029,7 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 		if (v >= 1 && v <= 32) ctx->bounce_min_walking = v;
 	}
 	if (const char* e = getenv("RT_B200_RESAMPLE")) ctx->resample = atoi(e) != 0;
+	if (const char* e = getenv("RT_B200_RESAMPLE_MIN")) ctx->resample_min_frames = std::max(2, atoi(e));
 	if (const char* e = getenv("RT_B200_BOUNCE_MINB")) {
 		const int v = atoi(e);
 		if (v == 4 || v == 5 || v == 6 || v == 8) ctx->bounce_minb = v;

@@ -335,3 +335,37 @@ def test_deep_trees_take_the_fallback_walker(oracle, max_in_depth):
         with pytest.raises(N.RtError, match="float32 resolution"):
             rt.GpuRaytracer(rt.RaytracerConfig(deep.refmax, deep.sky, deep.default_substance, 1.0), deep.tree,
                             scenes.bench_camera(64, 64), rt.ExposureBuffer(64, 64), rt.FpLcg(1.0))
+
+
+def test_resample_stage_equals_frames_in_a_row(oracle, monkeypatch):
+    """From 8 exposure frames on, the frames of a rough pixel are traced as independent (pixel, frame) samples by
+    the resample stage and blended in frame order: the same pixels, bit for bit, as one lane tracing them in a row
+    (RT_B200_RESAMPLE=0), as the reference's call-per-frame loop, and - within the gate - as the oracle.  Also on a
+    continued exposure (frame_first > 0) and for a frame count that is not a multiple of the pool geometry."""
+    b = scenes.random_spheres(1200, 0.02, 0.07, seed=17.0, mix="mirrors", box_fraction=0.15)
+    W = H = 160
+    rgb, ids, cnt, tr = gpu_render(b, W, H, n_frames=11)
+    orgb, oids, _, tot = oracle_for(tr, b, W, H, n_frames=11)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
+    launches = tr.lib.rt_launch_count(tr.ctx)
+    monkeypatch.setenv("RT_B200_RESAMPLE", "0")
+    rgb0, ids0, _, tr0 = gpu_render(b, W, H, n_frames=11)
+    monkeypatch.delenv("RT_B200_RESAMPLE")
+    np.testing.assert_array_equal(rgb0, rgb)
+    np.testing.assert_array_equal(ids0, ids)
+    rgbc, idsc, _, _ = gpu_render(b, W, H, n_frames=11, frames_as_calls=True)
+    np.testing.assert_array_equal(rgbc, rgb)
+    # a continued exposure: 3 frames, then 9 more through the resample stage == 12 frames in a row
+    cam = scenes.bench_camera(W, H)
+    cfg = rt.RaytracerConfig(b.refmax, b.sky, b.default_substance, 1.0)
+    eb = rt.ExposureBuffer(W, H)
+    t = rt.GpuRaytracer(cfg, b.tree, cam, eb, rt.FpLcg(1.0))
+    t.trace_frame(n_frames=3)
+    eb.next_frame()
+    t.trace_frame(n_frames=9)
+    eb2 = rt.ExposureBuffer(W, H)
+    monkeypatch.setenv("RT_B200_RESAMPLE", "0")
+    t2 = rt.GpuRaytracer(cfg, b.tree, cam, eb2, rt.FpLcg(1.0))
+    t2.trace_frame(n_frames=12)
+    np.testing.assert_array_equal(eb.pixels, eb2.pixels)
