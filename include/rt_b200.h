@@ -299,6 +299,12 @@ void rt_fplcg_fill(double seed, uint64_t n, double* out);
  * rt_render's copies run at full PCIe rate.  Optional; unregister before freeing the buffer. */
 rt_status rt_host_register(rt_ctx* ctx, void* ptr, size_t bytes);
 rt_status rt_host_unregister(rt_ctx* ctx, void* ptr);
+/* Page-lock AND map a caller-owned host buffer into the device's address space (zero-copy): *dev_ptr can be
+ * handed to rt_render_device / rt_render_shard_device as the frame, and the kernels then store their pixels
+ * straight into host memory over PCIe.  With one process per GPU and the buffer in shared memory, every rank
+ * delivers its own tiles over its own PCIe link - N links instead of one gather plus one copy.  The pixels are
+ * complete on the host after rt_synchronize on every rank.  Release with rt_host_unregister. */
+rt_status rt_host_map(rt_ctx* ctx, void* ptr, size_t bytes, void** dev_ptr);
 
 /* ---- device timing on the ctx stream (CUDA events) ------------------------------------------- */
 /* Benchmark hygiene: overwrite a scratch buffer larger than the 126 MB L2 on the ctx stream. */

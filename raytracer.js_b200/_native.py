@@ -111,6 +111,7 @@ EXPORTS = {
     "rt_flush_l2": (C.c_int, [C.c_void_p]),
     "rt_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rt_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_host_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
 }
 
 _lib = None

@@ -1111,6 +1111,19 @@ rt_status rt_host_register(rt_ctx* ctx, void* ptr, size_t bytes) {
 	return RT_OK;
 }
 
+rt_status rt_host_map(rt_ctx* ctx, void* ptr, size_t bytes, void** dev_ptr) {
+	if (!ctx || !ptr || !bytes || !dev_ptr) return RT_ERR_INVALID;
+	*dev_ptr = nullptr;
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	RT_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+	const cudaError_t e = cudaHostGetDevicePointer(dev_ptr, ptr, 0);
+	if (e != cudaSuccess) {
+		cudaHostUnregister(ptr);
+		return fail(ctx, RT_ERR_CUDA, rt_format("cudaHostGetDevicePointer: %s", cudaGetErrorString(e)));
+	}
+	return RT_OK;
+}
+
 rt_status rt_host_unregister(rt_ctx* ctx, void* ptr) {
 	if (!ctx || !ptr) return RT_ERR_INVALID;
 	RT_CUDA(ctx, cudaHostUnregister(ptr));
