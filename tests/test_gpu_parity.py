@@ -369,3 +369,32 @@ def test_resample_stage_equals_frames_in_a_row(oracle, monkeypatch):
     t2 = rt.GpuRaytracer(cfg, b.tree, cam, eb2, rt.FpLcg(1.0))
     t2.trace_frame(n_frames=12)
     np.testing.assert_array_equal(eb.pixels, eb2.pixels)
+
+
+def test_zero_copy_host_frame(oracle):
+    """rt_host_map: the kernels store the pixels straight into a mapped host buffer (the delivery every rank of a
+    multi-GPU render uses for its own tiles); same frame as rt_render's copy path, also through the shard entry
+    point with two ranks writing into one host frame."""
+    b = scenes.random_spheres(2000, 0.01, 0.05, seed=8.0, mix="mirrors", box_fraction=0.1)
+    W, H = 320, 208
+    cam = scenes.bench_camera(W, H)
+    eb = rt.ExposureBuffer(W, H)
+    tracer = rt.GpuRaytracer(rt.RaytracerConfig(b.refmax, b.sky, b.default_substance, 1.0), b.tree, cam, eb, rt.FpLcg(1.0))
+    tracer.trace_frame(n_frames=2)
+    lib, ctx = tracer.lib, tracer.ctx
+    cd, prm = rt.camera_desc(cam), tracer.params(n_frames=2)
+    host = np.full(W * H * 3, -1.0, np.float32)
+    devp = C.c_void_p()
+    N.check(ctx, lib.rt_host_map(ctx, host.ctypes.data, host.nbytes, C.byref(devp)))
+    try:
+        assert devp.value
+        N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), 0, devp, None))
+        N.check(ctx, lib.rt_synchronize(ctx))
+        np.testing.assert_array_equal(host, eb.pixels)
+        host[:] = -1.0
+        for rank in (1, 0):
+            N.check(ctx, lib.rt_render_shard_device(ctx, C.byref(cd), C.byref(prm), 0, rank, 2, devp, None))
+        N.check(ctx, lib.rt_synchronize(ctx))
+        np.testing.assert_array_equal(host, eb.pixels)
+    finally:
+        N.check(ctx, lib.rt_host_unregister(ctx, host.ctypes.data))
