@@ -184,3 +184,42 @@ def test_first_hit_rule_and_blend_by_hand(oracle):
     corner = rgb3[0, 0]
     if ids[0, 0] < 0:  # a sky pixel: (0.2, 0.2, 0.7) three times
         assert corner[2] == px
+
+
+# ---- Box.line_intersection, transliterated (src/math/intersection.ts:150-204; isNegative: src/math/mathutils.ts:45-47)
+def box_line_by_the_book(centre, size, o, d):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tl = [centre[k] - size[k] * 0.5 for k in range(3)]
+        p = [-d[0], d[0], -d[1], d[1], -d[2], d[2]]
+        q = [o[0] - tl[0], tl[0] + size[0] - o[0], o[1] - tl[1], tl[1] + size[1] - o[1], o[2] - tl[2], tl[2] + size[2] - o[2]]
+        u1, u2, i1, i2 = -math.inf, math.inf, None, None
+        for i in range(6):
+            u = float(np.float64(q[i]) / np.float64(p[i]))  # JS division: x/0 = +-Infinity, 0/0 = NaN
+            if p[i] < 0 or (p[i] == 0 and math.copysign(1.0, p[i]) < 0):  # isNegative: includes -0
+                if u > u1:
+                    u1, i1 = u, i
+            elif u < u2:
+                u2, i2 = u, i
+        return None if u1 > u2 else (u1, u2, i1, i2)
+
+
+def test_box_line_against_the_transliterated_formula(oracle):
+    rng = np.random.default_rng(23)
+    hits = 0
+    for trial in range(3000):
+        c = rng.uniform(0.2, 0.8, 3).tolist()
+        sz = [float(rng.uniform(0.05, 0.4))] * 3
+        o = rng.uniform(0, 1, 3).tolist()
+        d = rng.normal(size=3)
+        if trial % 5 == 0:
+            d[rng.integers(0, 3)] = 0.0  # axis-parallel rays: +-0 components, infinite parameters
+        if trial % 10 == 0:
+            d[rng.integers(0, 3)] = -0.0
+        d = d.tolist()
+        want = box_line_by_the_book(c, sz, o, d)
+        n, u, f = oracle.box_line(c, sz, o, d)
+        assert (want is None) == (n == 0), (c, sz, o, d)
+        if want:
+            hits += 1
+            assert u.tolist() == [want[0], want[1]] and f.tolist() == [want[2], want[3]]
+    assert hits > 200
