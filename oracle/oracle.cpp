@@ -15,7 +15,10 @@
 // test/octree-entity.test.ts:52-64, test/view-camera.test.ts:17-49,
 // test/octree.test.ts:3-7).  Everything those suites do not cover (hit tests,
 // first-hit rule, shading, RNG values, blend) is pinned only by the source
-// lines cited below: "parity unpinned by tests" for those rows.
+// lines cited below: "parity unpinned by tests" for those rows.  They are cross-checked by
+// tests/test_oracle_by_hand.py (hand-derived known answers, independent transliterations of
+// single functions) and tests/test_oracle_vs_python_restatement.py (tests/pyref.py, a second
+// restatement of Ray.trace in plain Python that must agree bit for bit on small frames).
 //
 // Build: g++ -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile): IEEE
 // double everywhere, no FMA contraction, JS `%` == fmod, `x<<0` == ToInt32.
