@@ -17,8 +17,10 @@
 // first-hit rule, shading, RNG values, blend) is pinned only by the source
 // lines cited below: "parity unpinned by tests" for those rows.  They are cross-checked by
 // tests/test_oracle_by_hand.py (hand-derived known answers, independent transliterations of
-// single functions) and tests/test_oracle_vs_python_restatement.py (tests/pyref.py, a second
-// restatement of Ray.trace in plain Python that must agree bit for bit on small frames).
+// single functions), tests/test_oracle_vs_python_restatement.py and
+// tests/test_oracle_walker_vs_python.py (tests/pyref.py + tests/pywalker.py: a second restatement
+// of Ray.trace, the hit tests, the OctreeWalker and node_at_pos in plain Python that shares no
+// logic with this file and must agree bit for bit).
 //
 // Build: g++ -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile): IEEE
 // double everywhere, no FMA contraction, JS `%` == fmod, `x<<0` == ToInt32.

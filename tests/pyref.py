@@ -1,11 +1,14 @@
 """A second, independent restatement of Ray.trace() (src/raytracer.ts:168-277) in plain Python, used to
 cross-check the C++ oracle on small scenes: the path logic (guards, materials, reflect / scatter / refract,
 refmax, sky, inverse-square law), the hit tests and the blend are transliterated here line by line from the
-TypeScript; only two things are taken from the oracle because the reference's own jest vectors pin them there:
-the walker's node order (Scene.walk) and node_at_pos.  TEST INFRASTRUCTURE ONLY."""
+TypeScript, and the walker and node_at_pos come from tests/pywalker.py, the same kind of transliteration of
+src/octree_space.ts.  Nothing of the oracle's logic is used: only the tree it built (flat arrays), which
+tests/test_host_build.py checks against the host API's own builder.  TEST INFRASTRUCTURE ONLY."""
 import math
 
 import numpy as np
+
+import pywalker
 
 EPS = 2.220446049250313e-16
 BRANCHES = {}  # how often each branch of Ray.trace was taken (the tests assert that all of them are)
@@ -106,15 +109,20 @@ class Ent:
         return all(p[k] >= self.pos[k] and p[k] < self.pos[k] + self.extent for k in range(3))
 
 
-def trace(scene, flat, ents, cfg, rng, start, direction, start_substance):
+def trace(tree, flat, ents, cfg, rng, start, direction, start_substance):
     """Ray.trace(): returns (r, g, b), first-hit entity index or -1."""
     refpoint, d = list(start), list(direction)
+    walker = pywalker.Walker(tree)
+    first_segment = True
     col = [1.0, 1.0, 1.0]
     refcount, path_distance, cur_substance = 0, 0.0, start_substance
     light_hit, first = False, -1
     while True:
         hit = None
-        for _, _, node in scene.walk(refpoint, d):  # walker.set_pos_and_dir + next(): existing nodes in visit order
+        # walker.set_pos_and_dir(refpoint, dir[, startnode]) + next(): existing nodes in visit order
+        stops = walker.stops(refpoint, d, use_start_node=first_segment)
+        first_segment = False
+        for _, _, node in stops:
             for e in flat.list_entity[flat.node_list_off[node]:flat.node_list_off[node + 1]]:
                 ci = ents[e].collision_info(refpoint, d)
                 if ci is not None:  # the FIRST entity of the list that is hit, not the nearest (:186-195)
@@ -162,7 +170,7 @@ def trace(scene, flat, ents, cfg, rng, start, direction, start_substance):
             refpoint = [refpoint[i] + d[i] * 1e-3 for i in range(3)]  # move_slightly_forward
         elif m["response"] == 1:  # TRANSMISSION :238-249
             refpoint = [refpoint[i] + d[i] * 1e-3 for i in range(3)]
-            rf_entity = entity_at_pos(scene, flat, ents, refpoint)
+            rf_entity = entity_at_pos(tree, flat, ents, refpoint)
             substance = rf_entity.substance if rf_entity is not None else cfg["default_substance"]
             _took("undefined substance" if substance is None else ("transmission into an entity" if rf_entity is not None else "transmission into the default substance"))
             if substance is not None:  # refract_ray :135-150
@@ -192,8 +200,9 @@ def trace(scene, flat, ents, cfg, rng, start, direction, start_substance):
     return [c * isl for c in col], first
 
 
-def entity_at_pos(scene, flat, ents, p):  # src/octree_entity.ts:191-202
-    node, _ = scene.node_at_pos(p)
+def entity_at_pos(tree, flat, ents, p):  # src/octree_entity.ts:191-202
+    at = tree.node_at_pos(p)
+    node = at[0] if at is not None else -1
     while node >= 0:
         for e in flat.list_entity[flat.node_list_off[node]:flat.node_list_off[node + 1]]:
             if ents[e].is_within(p):
@@ -205,12 +214,13 @@ def entity_at_pos(scene, flat, ents, p):  # src/octree_entity.ts:191-202
 def render(scene, ents, cam, cfg, n_frames=1, seed=1.0):
     """Raytracer.trace_frame() x n_frames with next_frame() between them, the harness RNG policy (reseed per pixel)."""
     flat = scene.flat()
+    tree = pywalker.Tree(flat)
     xy, dirs, n = cam.dirs(fixed_extents=True)
     W, H = cam.screen_w, cam.screen_h
     rgb = np.zeros((H, W, 3), np.float32)
     ids = np.full((H, W), -1, np.int32)
     start = [float(v) for v in cam.basis()["pos"]]
-    start_ent = entity_at_pos(scene, flat, ents, start)
+    start_ent = entity_at_pos(tree, flat, ents, start)
     start_substance = start_ent.substance if start_ent is not None else cfg["default_substance"]
     rng = FpLcg()
     for f in range(n_frames):
@@ -218,7 +228,7 @@ def render(scene, ents, cam, cfg, n_frames=1, seed=1.0):
         for i in range(n):
             x, y = int(xy[i][0]), int(xy[i][1])
             rng.seed(seed + float(y * W + x) + float(f) * float(W) * float(H))
-            c, first = trace(scene, flat, ents, cfg, rng, start, [float(v) for v in dirs[i]], start_substance)
+            c, first = trace(tree, flat, ents, cfg, rng, start, [float(v) for v in dirs[i]], start_substance)
             for k in range(3):
                 rgb[y, x, k] = np.float32(c[k] * w + float(rgb[y, x, k]) * (1 - w))
             ids[y, x] = first

@@ -1,5 +1,5 @@
-"""The C++ oracle against tests/pyref.py, an independent plain-Python transliteration of Ray.trace() and the hit
-tests (sharing only the walker order and node_at_pos, which the reference's jest vectors pin): small frames of
+"""The C++ oracle against tests/pyref.py + tests/pywalker.py, an independent plain-Python transliteration of
+Ray.trace(), the hit tests, the OctreeWalker and node_at_pos (sharing no logic with the oracle): small frames of
 scenes that exercise every branch of the path - mirrors, rough mirrors (RNG), lights (inverse-square law), glass
 with defined and undefined substances, total internal reflection, boxes, refmax, the acute-normal guard - must
 come out bit for bit the same.  This is the pin for the rows of SURVEY.md 8c that no reference test covers."""
