@@ -52,6 +52,35 @@ class FpLcg:  # src/math/rng/fp-lcg.ts:49-82
         return math.fmod(a + b + c, 1.0)
 
 
+class TextureError(Exception):
+    pass
+
+
+def uv_map_sphere(v):  # src/math/uv_mapping.ts:19-25
+    u = math.atan2(v[1], v[0]) / math.pi / 2.0 + 0.5 - EPS
+    w = math.atan2(v[2], math.sqrt((0.0 + v[0] * v[0]) + v[1] * v[1])) / math.pi + 0.5 - EPS
+    return u, w
+
+
+class Image:
+    """ImageTexture (src/texture/texture_image.ts:28-63): image_data = byte / 255.0, nearest texel."""
+
+    def __init__(self, pixels_u8):  # uint8 [height, width, 3]
+        self.height, self.width = pixels_u8.shape[:2]
+        self.data = [float(b) / 255.0 for b in pixels_u8.reshape(-1)]
+
+    def get_color(self, u, v):
+        if u < 0 - EPS or u > 1 - EPS or v < 0 - EPS or v > 1 - EPS:
+            raise TextureError("Texture coordinates out of bounds")
+        ui, vi = pywalker.to_int32(u * self.width), pywalker.to_int32(v * self.height)
+        i = (vi * self.width + ui) * 3
+        return self.data[i], self.data[i + 1], self.data[i + 2]
+
+
+def texture_color(tex, u, v):
+    return tex.get_color(u, v) if isinstance(tex, Image) else tex  # SolidTexture.get_color ignores u, v
+
+
 class Ent:
     def __init__(self, kind, pos, extent, material, texture, substance):
         self.kind, self.pos, self.extent = kind, list(map(float, pos)), float(extent)
@@ -140,7 +169,10 @@ def trace(tree, flat, ents, cfg, rng, start, direction, start_substance):
             _took("acute")
             return col, first
         refcount += 1
-        col = [col[k] * ent.texture[k] for k in range(3)]  # SolidMaterial.alter_ray -> mul_color
+        # SolidMaterial.alter_ray (src/materials/material_solid.ts:30-36): entity.map_uv(p) -> texture.get_color -> mul_color
+        u, v = uv_map_sphere([point[k] - ent.pos[k] for k in range(3)]) if ent.kind == 0 else (0, 0)
+        tc = texture_color(ent.texture, u, v)
+        col = [col[k] * tc[k] for k in range(3)]
         dd = [point[k] - refpoint[k] for k in range(3)]
         path_distance += math.sqrt(dot(dd, dd))
         refpoint = list(point)
@@ -193,7 +225,7 @@ def trace(tree, flat, ents, cfg, rng, start, direction, start_substance):
             return [0.0, 0.0, 0.0], first
     if not light_hit:
         _took("sky")
-        sky = cfg["sky"]  # SkySphere over a SolidTexture
+        sky = texture_color(cfg["sky"], *uv_map_sphere(d))  # SkySphere.get_color (src/sky/sky_sphere.ts:22-27)
         return [col[k] * sky[k] for k in range(3)], first
     t = path_distance * cfg["attenuation"]
     isl = 1.0 / (EPS + t * t)

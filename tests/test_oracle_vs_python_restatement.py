@@ -66,3 +66,34 @@ def test_every_branch_of_ray_trace_was_taken():
             "transmission into the default substance", "refraction", "total internal reflection", "both", "refmax", "sky"}
     missing = want - set(pyref.BRANCHES)
     assert not missing, (missing, pyref.BRANCHES)
+
+
+def test_image_textures_and_image_sky(oracle):
+    """ImageTexture.get_color (nearest texel, value / 255) through uv_map_sphere for sphere hits and for the sky;
+    boxes map to (0, 0) (BoxEntity.map_uv is a stub in the reference: texel 0 of the image)."""
+    rng = np.random.default_rng(31)
+    s = oracle.Scene((0, 0, 0), 1.0)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for w, h in ((64, 32), (17, 9), (128, 64))]
+    tids = [s.add_texture_image(im.shape[1], im.shape[0], im) for im in imgs]
+    pimgs = [pyref.Image(im) for im in imgs]
+    mats = [dict(response=0, light=False, mirror=True, roughness=0.0), dict(response=0, light=False, mirror=False, roughness=0.0),
+            dict(response=0, light=True, mirror=False, roughness=0.0)]
+    mids = [s.add_material(m["response"], m["light"], m["mirror"], m["roughness"]) for m in mats]
+    air = s.add_substance(1.0)
+    ents = []
+    for i in range(70):
+        d = float(rng.uniform(0.05, 0.2))
+        c = (d / 2 + rng.uniform(0, 1, 3) * (1 - d)).tolist()
+        typ = int(rng.random() < 0.25)
+        k, mi = int(rng.integers(0, 2)), int(rng.integers(0, 3))
+        assert s.add_entity(typ, c, d, mids[mi], tids[k], air, max_in_depth=16, max_out_depth=0) == i
+        ents.append(pyref.Ent(typ, c, d, mats[mi], pimgs[k], 1.0))
+    W = H = 24
+    cam = oracle.Camera(math.pi / 2, math.pi / 2, W, H, (0.5013, 0.4987, 0.5021), -0.2, 1.1, vertical_locked=True)
+    cfg = dict(refmax=4, sky=pimgs[2], default_substance=1.0, attenuation=1.0)
+    prgb, pids = pyref.render(s, ents, cam, cfg, n_frames=1)
+    orgb, oids, _, tot = oracle.render(s, cam, refmax=4, sky_texture=tids[2], default_substance=air, fixed_extents=True, n_frames=1,
+                                       rng_mode=1, seed=1.0)
+    assert np.array_equal(pids, oids) and np.array_equal(prgb, orgb), np.abs(prgb - orgb).max()
+    assert tot["texture_errors"] == 0 and (oids < 0).any() and (oids >= 0).any()
+    assert len(np.unique(orgb.reshape(-1, 3), axis=0)) > 100  # really textured
