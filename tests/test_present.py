@@ -158,3 +158,60 @@ def test_present_full_size_properties(oracle):
     _check_image(oracle, px, tone, st1.as_dict(), out1)
     bad = N.Tone(7, 8, 0.0, 1.0)
     assert lib.rt_present(ctx, px.ctypes.data, W, H, C.byref(bad), out1.ctypes.data, None) == N.RT_ERR_UNSUPPORTED
+
+
+def test_oracle_present_against_a_python_transliteration(oracle):
+    """get_mean / get_variance / get_absolute_dev, the three tone mappers, discretize_to_screen and convert_color
+    transliterated in plain Python (sequential float64 sums, Float32Array rounding, Math.min/max NaN rules,
+    `<< 0`): the C++ oracle must give the same numbers and the same bytes."""
+    rng = np.random.default_rng(9)
+    px = (rng.random((37 * 23, 3), dtype=np.float32) * np.float32(3.0)).astype(np.float32)
+    px[5] = [0.0, 0.0, 0.0]
+    px[6] = [np.nan, 0.5, 0.5]  # a NaN pixel poisons the sums, as in the reference
+    for pixels in (px[:5].copy(), np.delete(px, 6, axis=0), px):
+        ys = [0.299 * float(p[0]) + 0.587 * float(p[1]) + 0.114 * float(p[2]) for p in pixels]
+        mean = 0.0
+        for y in ys:
+            mean += y
+        mean /= len(ys)
+        var = dev = 0.0
+        for y in ys:
+            delta = y - mean
+            var += delta * delta
+            dev += abs(delta)
+        var /= len(ys)
+        dev /= len(ys)
+        got = oracle.exposure_stats(pixels)
+        for g, w in zip(got, (mean, var, dev)):
+            assert g == w or (math.isnan(g) and math.isnan(w))
+
+        def js_min(a, b):
+            return math.nan if (math.isnan(a) or math.isnan(b)) else min(a, b)
+
+        def clamp(x, lo, hi):
+            m = js_min(x, hi)
+            return math.nan if (math.isnan(m) or math.isnan(lo)) else max(m, lo)
+
+        for kind, stops, lo_lim, hi_lim in ((orc.TONE_IDENTITY, 8, 0.0, 1.0), (orc.TONE_STDDEV, 8, 1 / 256, 8.0), (orc.TONE_ABSDEV, 5, 0.01, 0.9)):
+            if kind == orc.TONE_IDENTITY:
+                lo, hi = 0.0, 1.0
+            else:
+                coef = float(1 << stops)
+                d = math.sqrt(var) if kind == orc.TONE_STDDEV else dev
+                hi = js_min(mean + d, hi_lim)
+                lo = hi / coef
+                if lo < lo_lim:
+                    lo, hi = lo_lim, lo_lim * coef
+            glo, ghi = oracle.dynamic_range(kind, stops, lo_lim, hi_lim, (mean, var, dev))
+            assert (glo == lo or (math.isnan(glo) and math.isnan(lo))) and (ghi == hi or (math.isnan(ghi) and math.isnan(hi)))
+            drange = hi - lo
+            want = np.zeros((len(ys), 4), np.uint8)
+            for i, (p, y) in enumerate(zip(pixels, ys)):
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    scale = float(np.float64((y - lo) / drange if drange != 0 else np.float64(y - lo) / np.float64(drange)) / np.float64(y + 2.220446049250313e-16))
+                for k in range(2):
+                    c = float(np.float32(clamp(float(p[k]) * scale, 0.0, 1.0)))  # Float32Array.prototype.map
+                    v = clamp(c, 0.0, 1.0) * 255
+                    want[i, k] = 0 if math.isnan(v) else int(v)
+                want[i, 3] = 255
+            assert np.array_equal(oracle.discretize(pixels, lo, hi), want)
