@@ -18,7 +18,7 @@
 // lines cited below: "parity unpinned by tests" for those rows.  They are cross-checked by
 // tests/test_oracle_by_hand.py (hand-derived known answers, independent transliterations of
 // single functions), tests/test_oracle_vs_python_restatement.py and
-// tests/test_oracle_walker_vs_python.py (tests/pyref.py + tests/pywalker.py: a second restatement
+// tests/test_oracle_walker_vs_python.py (oracle/pyref.py + oracle/pywalker.py: a second restatement
 // of Ray.trace, the hit tests, the OctreeWalker and node_at_pos in plain Python that shares no
 // logic with this file and must agree bit for bit).
 //

@@ -1,14 +1,14 @@
 """A second, independent restatement of Ray.trace() (src/raytracer.ts:168-277) in plain Python, used to
 cross-check the C++ oracle on small scenes: the path logic (guards, materials, reflect / scatter / refract,
 refmax, sky, inverse-square law), the hit tests and the blend are transliterated here line by line from the
-TypeScript, and the walker and node_at_pos come from tests/pywalker.py, the same kind of transliteration of
+TypeScript, and the walker and node_at_pos come from oracle/pywalker.py, the same kind of transliteration of
 src/octree_space.ts.  Nothing of the oracle's logic is used: only the tree it built (flat arrays), which
 tests/test_host_build.py checks against the host API's own builder.  TEST INFRASTRUCTURE ONLY."""
 import math
 
 import numpy as np
 
-import pywalker
+from . import pywalker
 
 EPS = 2.220446049250313e-16
 BRANCHES = {}  # how often each branch of Ray.trace was taken (the tests assert that all of them are)

@@ -1,7 +1,7 @@
 """OctreeWalker (src/octree_space.ts:159-408), node_at_pos (:61-93), octant_adj_pos (:41-50), index_within_parent
 (:110-125), dim_relative_to_parent (:127-136) and Box.line_intersection (src/math/intersection.ts:150-204)
 transliterated into plain Python over a flat tree (arrays node_pos / node_size / node_child / node_parent), to
-check the C++ oracle's walker with code that shares nothing with it.  TEST INFRASTRUCTURE ONLY."""
+check the C++ oracle's walker with code that shares nothing with it.  TEST INFRASTRUCTURE ONLY (small cases: pure-Python loops)."""
 import math
 
 import numpy as np

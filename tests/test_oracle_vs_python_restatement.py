@@ -1,4 +1,4 @@
-"""The C++ oracle against tests/pyref.py + tests/pywalker.py, an independent plain-Python transliteration of
+"""The C++ oracle against oracle/pyref.py + oracle/pywalker.py, an independent plain-Python transliteration of
 Ray.trace(), the hit tests, the OctreeWalker and node_at_pos (sharing no logic with the oracle): small frames of
 scenes that exercise every branch of the path - mirrors, rough mirrors (RNG), lights (inverse-square law), glass
 with defined and undefined substances, total internal reflection, boxes, refmax, the acute-normal guard - must
@@ -8,7 +8,7 @@ import math
 import numpy as np
 import pytest
 
-import pyref
+from oracle import pyref
 
 
 def build(oracle, seed, n, kinds):

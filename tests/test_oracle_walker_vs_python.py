@@ -1,4 +1,4 @@
-"""The oracle's OctreeWalker and node_at_pos against tests/pywalker.py, a plain-Python transliteration of
+"""The oracle's OctreeWalker and node_at_pos against oracle/pywalker.py, a plain-Python transliteration of
 src/octree_space.ts that shares no code with it: identical stop sequences (tree, octant, node) on deep random
 trees for random rays, axis-parallel rays (zero and negative-zero components), origins on dyadic planes and on the
 root's faces, origins outside the root, with and without include_undefined.  The reference's own two-level jest
@@ -8,7 +8,7 @@ import math
 import numpy as np
 import pytest
 
-import pywalker
+from oracle import pywalker
 
 
 def random_tree(oracle, seed, n, dmin, dmax):
