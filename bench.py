@@ -102,7 +102,7 @@ def oracle_setup(bundle, flat, n_frames=1):
     return orc, oscene, ocam, prm
 
 
-def time_oracle(bundle, flat, threads: int, steps: int, warmup: int):
+def time_oracle(bundle, flat, threads: int, steps: int, warmup: int, keep_frame: bool = False):
     from util import oracle_render  # noqa: E402  (tests/ is on sys.path after oracle_setup)
     orc, oscene, ocam, prm = oracle_setup(bundle, flat)
     for _ in range(warmup):
@@ -110,9 +110,11 @@ def time_oracle(bundle, flat, threads: int, steps: int, warmup: int):
     t0 = time.perf_counter()
     seg = 0
     for _ in range(steps):
-        _, _, _, tot = oracle_render(oscene, ocam, flat, bundle, prm, fixed_extents=True, n_threads=threads)
+        rgb, ids, _, tot = oracle_render(oscene, ocam, flat, bundle, prm, fixed_extents=True, n_threads=threads)
         seg += tot["segments"]
     dt = time.perf_counter() - t0
+    if keep_frame:
+        return seg / dt / 1e6, dt / steps * 1e3, tot, rgb, ids
     return seg / dt / 1e6, dt / steps * 1e3, tot
 
 
@@ -136,6 +138,38 @@ def run_reference(args, rank: int):
         "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def source_fingerprint() -> str:
+    """sha256 over the kernel sources the shipped library is built from: profile numbers (ncu captures under
+    profiles/) are only quoted by bench.py when they were taken from exactly these sources."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "raytracer.js_b200", "csrc")
+    for f in sorted(os.listdir(csrc)) + [os.path.join("..", "..", "include", "rt_b200.h")]:
+        with open(os.path.normpath(os.path.join(csrc, f)), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
+def committed_profile(stage: str):
+    """The newest profiles/*_summary.json that holds `stage` ("primary", "c2_bounce", ...), with a flag telling
+    whether it was captured from the sources this run was built from."""
+    pdir = os.path.join(ROOT, "profiles")
+    best = None
+    for f in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if not f.endswith("_summary.json"):
+            continue
+        try:
+            d = json.load(open(os.path.join(pdir, f)))
+        except Exception:
+            continue
+        if stage in d:
+            best = (f, d)
+    if not best:
+        return None
+    f, d = best
+    return {"file": f"profiles/{f}", "stale": d.get("fingerprint") != source_fingerprint(), "data": d[stage]}
 
 
 def run_ours(args, rank: int, world: int, local_rank: int):
@@ -177,8 +211,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     desc = flat.desc()
     N.check(ctx, lib.rt_scene_upload(ctx, C.byref(desc)))
 
-    cam = scenes.bench_camera(WIDTH, HEIGHT)
-    cd = rt.camera_desc(cam)
+    # The camera MOVES between steps (yaw + 0.001 degree per step), as it does in the reference's interactive
+    # loop (src/main.ts:288-330): every step recomputes the scan tables and the origin-relative records, and no
+    # step is a CUDA-graph replay of the one before it.  Step 0 is the pose of SURVEY.md 8d (yaw 30 degrees).
+    n_cams = max(args.warmup, 3) + args.steps + 1
+    cds = [rt.camera_desc(scenes.bench_camera(WIDTH, HEIGHT, yaw_deg=30.0 + 1e-3 * i)) for i in range(n_cams)]
+    cd = cds[0]
     prm = N.Params()
     prm.refmax, prm.sky_texture, prm.default_substance = 1, sky_tex, def_sub
     prm.distance_attenuation_factor, prm.n_frames, prm.frame_first, prm.rng_seed = 1.0, 1, 0, 1.0
@@ -199,17 +237,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     tiles = torch.zeros(tpr * 256 * 3, dtype=torch.float32, device=dev) if nccl_gather else None
     gathered = torch.zeros(world * tpr * 256 * 3, dtype=torch.float32, device=dev) if nccl_gather else None
 
-    def step(flags=0):
+    def step(flags=0, cam=None):
         """One frame with everything resident in HBM."""
+        cam = cd if cam is None else cam
         if world == 1:
-            N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), flags, C.c_void_p(frame.data_ptr()), None))
+            N.check(ctx, lib.rt_render_device(ctx, C.byref(cam), C.byref(prm), flags, C.c_void_p(frame.data_ptr()), None))
         elif peer is not None:
             # fused render + gather: pixels go straight into rank 0's frame over NVLink; the barrier closes it
-            N.check(ctx, lib.rt_render_shard_device(ctx, C.byref(cd), C.byref(prm), flags, rank, world,
+            N.check(ctx, lib.rt_render_shard_device(ctx, C.byref(cam), C.byref(prm), flags, rank, world,
                                                     C.c_void_p(peer.frame_ptr), None))
             peer.barrier()
         else:
-            N.check(ctx, lib.rt_render_tiles_device(ctx, C.byref(cd), C.byref(prm), flags, rank, world,
+            N.check(ctx, lib.rt_render_tiles_device(ctx, C.byref(cam), C.byref(prm), flags, rank, world,
                                                     C.c_void_p(tiles.data_ptr()), None))
             dist.all_gather_into_tensor(gathered, tiles)  # tile exchange over NCCL / NVLink
             if rank == 0:
@@ -221,7 +260,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- work counters of one frame (untimed, counting kernel variant): what the roofline is built from
+    # ---- work counters of one frame (untimed, counting kernel variant): what the per-ray-bytes figure is built from
     step(N.RT_RENDER_COUNTERS)
     cnt = N.Counters()
     N.check(ctx, lib.rt_get_counters(ctx, C.byref(cnt)))
@@ -229,14 +268,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.all_reduce(c)
     paths, segments, nodes, tests, shades = (int(x) for x in c.tolist())
+    assert segments == npx  # refmax 1: one ray segment per pixel, whatever the camera looks at
     # ALGORITHMIC bytes: 64 B per node returned by the walker order, 16 B per entity hit
     # test, 16 B per shaded hit, 12 B per pixel store.  The counters count the REFERENCE's access pattern
     # (tests/test_gpu_parity.py asserts they equal the oracle's), not this kernel's own traffic.
     algo_bytes = 64 * nodes + 16 * tests + 16 * shades + 12 * paths
     bytes_per_segment = algo_bytes / segments
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        step(cam=cds[i])
     barrier()
 
     # ---- timed region: K steps, per-step CUDA events on the launching stream, L2 flushed between steps
@@ -247,10 +288,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
-    for a, b in evs:
+    for i, (a, b) in enumerate(evs):
         N.check(ctx, lib.rt_flush_l2(ctx))
         a.record(stream)
-        step()
+        step(cam=cds[warm + i])
         b.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -263,20 +304,54 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     clocks = sampler.stop() if rank == 0 else None
     value = segments / (ms_per_step * 1e-3) / 1e6
 
+    # ---- beside it: (a) the same K steps with a camera that stands still, which the library replays as a CUDA
+    # graph (no scan-table copies, no origin-relative records: NOT what `value` is); (b) the K steps again with
+    # CUDA events between the kernels (rt_set_profiling): the live duration of every stage
+    replay_ms = stage_ms = None
+    if world == 1:
+        for _ in range(3):
+            step()
+        revs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in revs:
+            N.check(ctx, lib.rt_flush_l2(ctx))
+            a.record(stream)
+            step()
+            b.record(stream)
+        torch.cuda.synchronize()
+        replay_ms = sum(a.elapsed_time(b) for a, b in revs) / args.steps
+        N.check(ctx, lib.rt_set_profiling(ctx, 1))
+        acc = [0.0] * 5
+        st = (C.c_float * 5)()
+        for i in range(args.steps):
+            N.check(ctx, lib.rt_flush_l2(ctx))
+            step(cam=cds[warm + i])
+            N.check(ctx, lib.rt_stage_times(ctx, st))
+            for k in range(5):
+                acc[k] += max(0.0, st[k])
+        N.check(ctx, lib.rt_set_profiling(ctx, 0))
+        stage_ms = dict(zip(("prepare", "primary", "shade", "bounce", "resample"), (v / args.steps for v in acc)))
+
     # ---- end to end through the C ABI with HOST buffers: camera tables H2D + kernel + full frame D2H
     e2e = None
     present = None
+    gpu_ids = None
     if world == 1:
         host_rgb = np.zeros(npx * 3, np.float32)
         N.check(ctx, lib.rt_host_register(ctx, host_rgb.ctypes.data, host_rgb.nbytes))  # pinned, as the N-API shim does
-        for _ in range(3):
-            N.check(ctx, lib.rt_render(ctx, C.byref(cd), C.byref(prm), 0, host_rgb.ctypes.data, None, None))
+        for i in range(3):
+            N.check(ctx, lib.rt_render(ctx, C.byref(cds[i]), C.byref(prm), 0, host_rgb.ctypes.data, None, None))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            N.check(ctx, lib.rt_render(ctx, C.byref(cd), C.byref(prm), 0, host_rgb.ctypes.data, None, None))
+        for i in range(args.steps):
+            N.check(ctx, lib.rt_render(ctx, C.byref(cds[warm + i]), C.byref(prm), 0, host_rgb.ctypes.data, None, None))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        # the frame of step 0's pose through the host path, with first-hit ids: compared with the device path here
+        # and with the oracle's frame below (`parity`)
+        gpu_ids = np.full(npx, -9, np.int32)
+        N.check(ctx, lib.rt_render(ctx, C.byref(cd), C.byref(prm), 0, host_rgb.ctypes.data, gpu_ids.ctypes.data, None))
+        step()
+        torch.cuda.synchronize()
         assert np.array_equal(host_rgb, frame.cpu().numpy()), "host path and device path disagree"
         N.check(ctx, lib.rt_host_unregister(ctx, host_rgb.ctypes.data))
         e2e = {"value": segments * args.steps / dt / 1e6, "unit": "Mrays/s", "frame_ms": dt / args.steps * 1e3,
@@ -301,9 +376,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         for _ in range(3):
             N.check(ctx, lib.rt_render_present(ctx, C.byref(cd), C.byref(prm), 0, C.byref(tone), host_rgba.ctypes.data, None, None))
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            N.check(ctx, lib.rt_render_present(ctx, C.byref(cd), C.byref(prm), 0, C.byref(tone), host_rgba.ctypes.data, None, None))
+        for i in range(args.steps):
+            N.check(ctx, lib.rt_render_present(ctx, C.byref(cds[warm + i]), C.byref(prm), 0, C.byref(tone), host_rgba.ctypes.data, None, None))
         dtp = time.perf_counter() - t0
+        N.check(ctx, lib.rt_render_present(ctx, C.byref(cd), C.byref(prm), 0, C.byref(tone), host_rgba.ctypes.data, None, None))
         assert np.array_equal(host_rgba, rgba_dev.cpu().numpy()), "resident present and device present disagree"
         N.check(ctx, lib.rt_host_unregister(ctx, host_rgba.ctypes.data))
         # algorithmic bytes of draw_ebuffer: get_mean, get_variance and discretize_to_screen each read the
@@ -329,8 +405,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             step()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step()
+        for i in range(args.steps):
+            step(cam=cds[warm + i])
             if rank == 0:
                 host_t.copy_(frame, non_blocking=True)
             if peer is not None:
@@ -362,20 +438,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             devp = C.c_void_p()
             N.check(ctx, lib.rt_host_map(ctx, host.ctypes.data, host.nbytes, C.byref(devp)))
 
-            def step_zc():
-                N.check(ctx, lib.rt_render_shard_device(ctx, C.byref(cd), C.byref(prm), 0, rank, world, devp, None))
+            def step_zc(cam):
+                N.check(ctx, lib.rt_render_shard_device(ctx, C.byref(cam), C.byref(prm), 0, rank, world, devp, None))
                 peer.barrier()
                 N.check(ctx, lib.rt_synchronize(ctx))
 
             for _ in range(3):
-                step_zc()
+                step_zc(cd)
             barrier()
             if rank == 0:
                 assert np.array_equal(host, ref.cpu().numpy()), "zero-copy host frame differs from the single-GPU frame"
             barrier()
             t0 = time.perf_counter()
-            for _ in range(args.steps):
-                step_zc()
+            for i in range(args.steps):
+                step_zc(cds[warm + i])
             barrier()
             dtz = time.perf_counter() - t0
             zc = {"value": segments * args.steps / dtz / 1e6, "unit": "Mrays/s", "frame_ms": dtz / args.steps * 1e3,
@@ -398,61 +474,80 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if rank != 0:
         return
     peak, peak_src = peaks()
-    kernel_ms = ms_per_step  # the step's kernels back to back on one stream (CUDA events around them)
-    achieved = algo_bytes / world / (kernel_ms * 1e-3) / 1e9 if world == 1 else None
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    # what actually bounds the dominant kernel (L1/L2-resident scene): issue slots, from the committed ncu capture
-    issue = None
-    try:
-        prof = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_summary.json"))[-1]
-        pk = json.load(open(os.path.join(ROOT, "profiles", prof)))["primary"]
-        issue = {"kernel": pk["kernel"], "issue_slot_utilisation_pct": pk["smsp__issue_active.avg.pct_of_peak_sustained_active"],
-                 "active_lanes_per_instruction": pk["smsp__thread_inst_executed_per_inst_executed.ratio"],
-                 "registers_per_thread": pk["launch__registers_per_thread"], "source": f"profiles/{prof} (ncu --set full, not live)"}
-    except Exception:
-        pass
+    # ---- roofline.  The survey's per-ray-bytes figure (algorithmic bytes of the REFERENCE's access pattern over
+    # the step time, against measured HBM bandwidth) is kept under `hbm`, but it is not a roofline fraction here:
+    # the scene is L1/L2 resident and a packet shares every fetch among its rays, so it exceeds 1 by construction.
+    # What bounds the dominant kernel is instruction issue: `achieved` = thread-instructions per second of the
+    # primary stage (instruction count of the committed ncu capture of THESE sources x the kernel's LIVE duration
+    # in this run), `peak` = SMs x 4 schedulers x 32 lanes x the SM clock sampled during this run.
+    hbm_achieved = algo_bytes / world / (ms_per_step * 1e-3) / 1e9 if world == 1 else None
+    roof = {"bound": "issue", "achieved": None, "peak": None, "unit": "Tthread-inst/s", "frac": None, "traffic": None,
+            "kernel": "rt_primary_kernel", "kernel_ms_live": stage_ms["primary"] if stage_ms else None,
+            "stage_ms_live": stage_ms, "source_fingerprint": source_fingerprint()}
+    prof = committed_profile("primary")
+    if prof and not prof["stale"] and stage_ms and stage_ms["primary"] > 0:
+        pk = prof["data"]
+        thread_inst = pk["smsp__inst_executed.sum"] * pk["smsp__thread_inst_executed_per_inst_executed.ratio"]
+        sm_hz = (clocks or {}).get("sm_mhz") or 0.0
+        roof["achieved"] = thread_inst / (stage_ms["primary"] * 1e-3) / 1e12
+        roof["peak"] = 148 * 4 * 32 * sm_hz * 1e6 / 1e12 if sm_hz else None
+        roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
+        roof["traffic"] = pk["dram__bytes_read.sum"] + pk["dram__bytes_write.sum"]
+        roof["ncu"] = {"file": prof["file"], "issue_slot_utilisation_pct": pk["smsp__issue_active.avg.pct_of_peak_sustained_active"],
+                       "active_lanes_per_instruction": pk["smsp__thread_inst_executed_per_inst_executed.ratio"],
+                       "issue_x_lanes": pk["smsp__issue_active.avg.pct_of_peak_sustained_active"] / 100 * pk["smsp__thread_inst_executed_per_inst_executed.ratio"] / 32,
+                       "registers_per_thread": pk["launch__registers_per_thread"], "kernel_us_under_ncu": pk["gpu__time_duration.sum"],
+                       "warp_instructions_per_launch": pk["smsp__inst_executed.sum"]}
+    else:
+        roof["stale_profile"] = (prof or {}).get("file", "no committed capture")
+        roof["note_stale"] = "no ncu capture of these exact sources is committed: issue figures withheld"
+    roof["hbm"] = {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                   "algorithmic_over_peak": (hbm_achieved / peak) if hbm_achieved else None,
+                   "dram_traffic_over_peak": (roof["traffic"] / (stage_ms["primary"] * 1e-3) / 1e9 / peak) if roof["traffic"] and stage_ms else None,
+                   "algorithmic_bytes_per_segment": bytes_per_segment,
+                   "per_segment": {"nodes": nodes / segments, "tests": tests / segments, "shades": shades / segments},
+                   "note": "algorithmic bytes follow the REFERENCE's access pattern (64 B/node + 16 B/test + 16 B/shade + 12 B/pixel) "
+                           "over the whole step; > 1 x peak because the scene is cache resident and a packet shares each fetch: "
+                           "not a roofline fraction, kept because SURVEY.md 8d defines it"}
     out = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": "flushed (256 MiB memset) before every timed step, outside its event pair",
                    "timing": "per-step CUDA events on the launching stream, summed over K steps, max over ranks",
+                   "camera": "moves every step (yaw + 0.001 degree): scan tables, origin-relative records and all kernels run "
+                             "in every timed step; no CUDA-graph replay",
                    "parallelism": f"interleaved 16x16 tiles over {world} GPU(s), scene replicated"
                                   + ("" if world == 1 else ", tiles stored straight into rank 0's frame over NVLink peer memory + flag barrier"
                                      if peer is not None else ", NCCL all-gather of tile buffers + de-interleave"),
                    "segments_per_step": segments, "primary_paths_per_s": paths / (ms_per_step * 1e-3),
                    "frame_ms_kernel": ms_per_step, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+                   "replay_ms_per_step_camera_standing_still": replay_ms,
                    "scene_broadcast_bytes": scene_bcast_bytes,
                    "precision": "float32 search + float64 confirmation/shading of the found hit",
                    "path": args.path},
-        "clocks": clocks, "e2e": e2e, "present": present, "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src, "issue": issue,
-                     "algorithmic_bytes_per_segment": bytes_per_segment,
-                     "per_segment": {"nodes": nodes / segments, "tests": tests / segments, "shades": shades / segments},
-                     "kernel": "the step's launches together (prepare + primary + shade + bounce); rt_primary_kernel is ~80% of "
-                               "the step in profiles/*_launches.csv and `traffic` is its DRAM bytes per launch (ncu --set full)",
-                     "note": "algorithmic bytes follow the REFERENCE's access pattern (64 B/node + 16 B/test + 16 B/shade + "
-                             "12 B/pixel); the scene (~1 MB) is L2/L1 resident and a packet shares every fetch among its "
-                             "rays, so achieved exceeds the HBM peak: see DESIGN.md 4.2 for the issue-slot figures that "
-                             "bound the kernel"},
+        "clocks": clocks, "e2e": e2e, "present": present, "gpu_launches": launches, "roofline": roof,
     }
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
-        mrays, ms, tot = time_oracle(bundle, flat, 1, 1, 0)
+        mrays, ms, tot, orgb, oids = time_oracle(bundle, flat, 1, 1, 0, keep_frame=True)
         out["cpu_baseline"] = {"value": mrays, "unit": "Mrays/s", "cores": 1, "kind": "port", "frame_ms": ms,
                                "sample": f"one full {WIDTH}x{HEIGHT} frame ({tot['segments']} segments), 1 thread "
                                          "(the reference renderer is single-threaded)"}
         # the same counters from the oracle (float64 walk): equal up to rare float32 cell-boundary ties
-        out["roofline"]["oracle_counters_rel_diff"] = {
+        out["roofline"]["hbm"]["oracle_counters_rel_diff"] = {
             k: (v - tot[k]) / max(tot[k], 1) for k, v in (("segments", segments), ("nodes", nodes), ("tests", tests),
                                                           ("shades", shades))}
+        # ---- parity of the very frame that was benchmarked (step 0's pose) against the oracle frame just rendered:
+        # first-hit ids and float32 pixels of all 1920x1080 pixels (non-square: the intent mapping on both sides)
+        from util import compare, insertion_ids
+        mine = insertion_ids(flat, bundle, gpu_ids.reshape(HEIGHT, WIDTH))
+        par = compare(host_rgb.reshape(HEIGHT, WIDTH, 3), mine, orgb, oids)
+        par["pixels"] = npx
+        par["hit_pixels"] = int((oids >= 0).sum())
+        par["gate"] = "ids equal on >= 99.99 % of pixels, RGB within 1/255 on id-equal pixels"
+        par["pass"] = bool(par["id_match"] >= 0.9999 and par["rgb_bad"] == 0)
+        out["parity"] = par
     print(json.dumps(out))
 
 

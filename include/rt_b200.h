@@ -313,6 +313,19 @@ rt_status rt_timer_start(rt_ctx* ctx);
 rt_status rt_timer_stop(rt_ctx* ctx, float* elapsed_ms); /* synchronises */
 /* Number of kernels this library launched on the ctx since rt_create. */
 uint64_t rt_launch_count(const rt_ctx* ctx);
+/* Per-stage device time of a frame (what the reference's tick handler brackets as ONE trace_frame() with
+ * performance.now(), src/main.ts:244-263, split by kernel): with profiling on, every non-replayed
+ * rt_render_device / rt_render_shard_device call records CUDA events between its kernels on the ctx stream, and
+ * rt_stage_times (synchronises) returns the milliseconds of each stage of the LAST such call, -1 for a stage that
+ * did not run.  The events add a little launch gap: keep it off in the timed region of a benchmark. */
+#define RT_STAGE_PREPARE 0  /* per-camera origin-relative records */
+#define RT_STAGE_PRIMARY 1  /* camera rays: packet walk + shading of the paths that end at their first hit */
+#define RT_STAGE_SHADE 2    /* (unused since ABI 2: the primary stage shades) */
+#define RT_STAGE_BOUNCE 3   /* continued paths */
+#define RT_STAGE_RESAMPLE 4 /* (pixel, frame) samples of rough pixels, n_frames >= 8 */
+#define RT_N_STAGES 5
+rt_status rt_set_profiling(rt_ctx* ctx, int32_t on);
+rt_status rt_stage_times(rt_ctx* ctx, float ms[RT_N_STAGES]);
 
 #ifdef __cplusplus
 }

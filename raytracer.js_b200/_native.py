@@ -91,6 +91,8 @@ EXPORTS = {
     "rt_timer_start": (C.c_int, [C.c_void_p]),
     "rt_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rt_launch_count": (C.c_uint64, [C.c_void_p]),
+    "rt_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
+    "rt_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rt_tiles_per_rank": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32]),
     "rt_render_tiles_device": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32,
                                          C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),

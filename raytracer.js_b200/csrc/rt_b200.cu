@@ -642,6 +642,10 @@ struct rt_ctx {
 	std::string err;
 	uint64_t launches = 0;
 	bool has_scene = false;
+	// per-stage device timing of the last eager render (rt_set_profiling / rt_stage_times)
+	bool profile = false;
+	cudaEvent_t stage_ev[RT_N_STAGES + 1] = {};
+	bool stage_ran[RT_N_STAGES] = {};
 
 	RtHostScene host;  // packed host copy (also serves the once-per-frame start state)
 	DevBuf<RtF4> node_geom;
@@ -880,12 +884,20 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 			RT_CUDA(ctx, cudaEventRecord(ctx->stage_free, ctx->stream));
 		}
 		RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, n_cells * sizeof(unsigned long long), ctx->stream));
+		const bool prof = ctx->profile && !capture && n_bands == 1;
+		for (int k = 0; k < RT_N_STAGES; k++) ctx->stage_ran[k] = false;
+		auto mark = [&](int stage) -> cudaError_t {  // event before stage `stage` (= after the one before it)
+			return prof ? cudaEventRecord(ctx->stage_ev[stage], ctx->stream) : cudaSuccess;
+		};
+		RT_CUDA(ctx, mark(0));
 		if (prim && !capture) {
 			rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
 			                                                                         cam->pos[2], ctx->prim_geom.p);
 			ctx->launches++;
+			ctx->stage_ran[0] = prof;
 			RT_CUDA(ctx, cudaGetLastError());
 		}
+		RT_CUDA(ctx, mark(1));
 		for (int band = 0; band < n_bands; band++) {
 			const int row_begin = (int)((long long)tiles_y * band / n_bands), row_end = (int)((long long)tiles_y * (band + 1) / n_bands);
 			F.tile_begin = row_begin * tiles_x;
@@ -913,17 +925,23 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				void* args[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x, (void*)&n_packets};
 				RT_CUDA(ctx, cudaLaunchKernel(primary_kernel, dim3(blocks), dim3(RT_A_WARPS * 32), args, 0, ctx->stream));
 				ctx->launches++;
+				RT_CUDA(ctx, mark(2));
 				rt_shade_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_out);
 				ctx->launches++;
 				RT_CUDA(ctx, cudaGetLastError());
+				RT_CUDA(ctx, mark(3));
 				void* bargs[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x};
 				RT_CUDA(ctx, cudaLaunchKernel(bounce_kernel, dim3(std::min(grid_bounce, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA)),
 				                              dim3(RT_WARPS_PER_CTA * 32), bargs, 0, ctx->stream));
+				RT_CUDA(ctx, mark(4));
+				ctx->stage_ran[1] = ctx->stage_ran[2] = ctx->stage_ran[3] = prof;
 				if (resample) {
 					ctx->launches++;
 					RT_CUDA(ctx, cudaLaunchKernel(resample_kernel, dim3(std::min(grid_resample, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA)),
 					                              dim3(RT_WARPS_PER_CTA * 32), bargs, 0, ctx->stream));
+					ctx->stage_ran[4] = prof;
 				}
+				RT_CUDA(ctx, mark(5));
 			} else if (count) {
 				rt_render_kernel<true><<<std::min(grid_ray, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA), RT_WARPS_PER_CTA * 32, 0,
 				                         ctx->stream>>>(ctx->dev, F, tiles_x, n_patches);
@@ -1013,6 +1031,7 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->stage_free, cudaEventDisableTiming);
 	for (int b = 0; b < RT_MAX_BANDS && e == cudaSuccess; b++) e = cudaEventCreateWithFlags(&ctx->band_done[b], cudaEventDisableTiming);
+	for (int k = 0; k <= RT_N_STAGES && e == cudaSuccess; k++) e = cudaEventCreate(&ctx->stage_ev[k]);
 	if (e != cudaSuccess) {
 		rt_status st = fail(nullptr, RT_ERR_CUDA, rt_format("rt_create: %s", cudaGetErrorString(e)));
 		rt_destroy(ctx);
@@ -1059,6 +1078,8 @@ void rt_destroy(rt_ctx* ctx) {
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	for (int b = 0; b < RT_MAX_BANDS; b++)
 		if (ctx->band_done[b]) cudaEventDestroy(ctx->band_done[b]);
+	for (int k = 0; k <= RT_N_STAGES; k++)
+		if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
 	if (ctx->stage_free) cudaEventDestroy(ctx->stage_free);
 	if (ctx->stage) cudaFreeHost(ctx->stage);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1096,6 +1117,23 @@ rt_status rt_timer_stop(rt_ctx* ctx, float* elapsed_ms) {
 }
 
 uint64_t rt_launch_count(const rt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+rt_status rt_set_profiling(rt_ctx* ctx, int32_t on) {
+	if (!ctx) return RT_ERR_INVALID;
+	ctx->profile = on != 0;
+	return RT_OK;
+}
+
+rt_status rt_stage_times(rt_ctx* ctx, float ms[RT_N_STAGES]) {
+	if (!ctx || !ms) return RT_ERR_INVALID;
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (int k = 0; k < RT_N_STAGES; k++) {
+		ms[k] = -1.0f;
+		if (ctx->stage_ran[k]) RT_CUDA(ctx, cudaEventElapsedTime(&ms[k], ctx->stage_ev[k], ctx->stage_ev[k + 1]));
+	}
+	return RT_OK;
+}
 
 rt_status rt_flush_l2(rt_ctx* ctx) {
 	if (!ctx) return RT_ERR_INVALID;

@@ -253,3 +253,33 @@ def random_spheres_flat(n: int, dmin: float = 0.002, dmax: float = 0.006, seed: 
                             [SUBSTANCE_AIR], max_in_depth=max_in_depth)
     return FlatBundle(flat, 0, 0, 1 if mix == "diffuse" else 4, n,
                       f"{n} random spheres d in [{dmin},{dmax}], seed {seed}, mix {mix} (bulk build)")
+
+
+# The non-headline BASELINE.json configs: frame, samples per pixel and scene recipe.
+#   c2: 1920x1080, 16 spp, 100 k spheres d in [0.002,0.006], 70% mirrors / 15% diffuse / 10% rough / 5% lights, refmax 4
+#   c3: 3840x2160, 4 spp, 1 M entities (10% boxes) d in [0.0005,0.002], 4 image textures 1024x512, refmax 4
+#   c4: 7680x4320, 64 spp, 1 M spheres d in [0.0005,0.002], config-2 material mix, refmax 4
+BASELINE_CONFIGS = {
+    "c2": dict(w=1920, h=1080, spp=16, n=100000, dmin=0.002, dmax=0.006, mix="mirrors", box=0.0, tex=False),
+    "c3": dict(w=3840, h=2160, spp=4, n=1000000, dmin=0.0005, dmax=0.002, mix="mirrors", box=0.1, tex=True),
+    "c4": dict(w=7680, h=4320, spp=64, n=1000000, dmin=0.0005, dmax=0.002, mix="mirrors", box=0.0, tex=False),
+}
+
+
+def build_config(cfg) -> FlatBundle:
+    """The scene of one BASELINE_CONFIGS entry, bulk-built (random_spheres_flat).  Textured configs: the
+    geometry and materials come from the bulk generator, the textured entities (spheres that are not lights)
+    pick one of 4 shared 1024x512 image textures with a second stream of draws, FpLcg(43)."""
+    fb = random_spheres_flat(cfg["n"], cfg["dmin"], cfg["dmax"], 42.0, cfg["mix"], cfg["box"])
+    if cfg["tex"]:
+        texs = [checker_texture(1024, 512, seed=s) for s in (1, 2, 3, 4)]
+        a = fb.flat.arrays
+        base = len(fb.flat.textures)
+        for t in texs:
+            fb.flat.texture_index(t)
+        pick = (fplcg_draws(43.0, cfg["n"]) * 4).astype(np.int32)
+        light = a["mat_light"][a["ent_material"]].astype(bool)
+        textured = (~light) & (a["ent_type"] == 0)
+        a["ent_texture"] = np.where(textured, base + pick, a["ent_texture"]).astype(np.int32)
+        fb.flat.finalize_tables()
+    return fb

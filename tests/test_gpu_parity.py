@@ -14,7 +14,7 @@ import raytracer_js_b200 as rt
 from raytracer_js_b200 import _native as N
 from raytracer_js_b200 import scenes
 
-from util import compare, flat_of, insertion_ids, make_params, oracle_render, oracle_scene
+from util import assert_parity, compare, flat_of, insertion_ids, make_params, oracle_render, oracle_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -46,10 +46,14 @@ def gpu_render(bundle, width, height, n_frames=1, pos=scenes.BENCH_CAMERA_POS, y
     return rgb, insertion_ids(tracer.flat, bundle, ids), cnt, tracer
 
 
+def ocam_for(width, height, pos=scenes.BENCH_CAMERA_POS, yaw=30.0, pitch=0.0):
+    return orc.Camera(math.pi / 2, math.pi / 2, width, height, pos, pitch, math.pi / 180 * yaw, vertical_locked=True)
+
+
 def oracle_for(tracer, bundle, width, height, n_frames=1, pos=scenes.BENCH_CAMERA_POS, yaw=30.0, pitch=0.0,
                refmax=None, want_counters=False):
     flat = tracer.flat
-    ocam = orc.Camera(math.pi / 2, math.pi / 2, width, height, pos, pitch, math.pi / 180 * yaw, vertical_locked=True)
+    ocam = ocam_for(width, height, pos, yaw, pitch)
     prm = make_params(flat, bundle, n_frames=n_frames, refmax=refmax)
     return oracle_render(oracle_scene(flat, bundle), ocam, flat, bundle, prm, fixed_extents=True,
                          want_counters=want_counters)
@@ -81,8 +85,7 @@ def test_config2_mirrors_lights_rough_multiframe(oracle):
     b = scenes.random_spheres(20000, 0.004, 0.012, seed=42.0, mix="mirrors", box_fraction=0.1)
     rgb, ids, cnt, tr = gpu_render(b, 400, 400, n_frames=4)
     orgb, oids, _, tot = oracle_for(tr, b, 400, 400, n_frames=4)
-    res = compare(rgb, ids, orgb, oids)
-    assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 2, res
+    assert_parity(rgb, ids, orgb, oids, scenes.BENCH_CAMERA_POS, ocam_for(400, 400))
     assert abs(cnt["segments"] - tot["segments"]) <= 1e-4 * tot["segments"]
     # n_frames in one call == the reference's call-per-frame loop with next_frame() in between
     rgb2, ids2, _, _ = gpu_render(b, 400, 400, n_frames=4, frames_as_calls=True)
@@ -123,8 +126,7 @@ def test_image_textures_and_sky(oracle):
     b.sky = rt.SkySphere(scenes.checker_texture(512, 256, seed=4))
     rgb, ids, cnt, tr = gpu_render(b, 300, 300)
     orgb, oids, _, tot = oracle_for(tr, b, 300, 300)
-    res = compare(rgb, ids, orgb, oids)
-    assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 2, res
+    assert_parity(rgb, ids, orgb, oids, scenes.BENCH_CAMERA_POS, ocam_for(300, 300), image_textures=True)
 
 
 @pytest.mark.parametrize("pos,yaw,pitch", [
@@ -138,8 +140,7 @@ def test_packet_stage_from_many_poses(oracle, pos, yaw, pitch):
     b = scenes.random_spheres(6000, 0.004, 0.04, seed=21.0, mix="mirrors", box_fraction=0.15)
     rgb, ids, cnt, tr = gpu_render(b, 320, 320, n_frames=2, pos=pos, yaw=yaw, pitch=pitch)
     orgb, oids, _, tot = oracle_for(tr, b, 320, 320, n_frames=2, pos=pos, yaw=yaw, pitch=pitch)
-    res = compare(rgb, ids, orgb, oids)
-    assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 1, res
+    assert_parity(rgb, ids, orgb, oids, pos, ocam_for(320, 320, pos, yaw, pitch))
     assert (oids >= 0).mean() > 0.1
 
 
@@ -243,8 +244,9 @@ def test_config0_demo_scene(oracle, size, n_frames):
     from test_hostsim_parity import demo_pair
     b, flat, cam, prm, orgb, oids, tot = demo_pair(size, size, n_frames)
     rgb, ids, cnt, tr = gpu_render(b, size, size, n_frames=n_frames, pos=scenes.DEMO_CAMERA_POS, reference_extents=True)
-    res = compare(rgb, ids, orgb, oids)
-    assert res["id_match"] >= 0.9999 and res["rgb_bad"] <= 2, res
+    # the demo pose sits on the root's centre planes (src/main.ts:364): the rays of the middle row run inside the
+    # plane z = 0.5, the one kind of id mismatch that is allowed - and it must be classified as such
+    assert_parity(rgb, ids, orgb, oids, scenes.DEMO_CAMERA_POS, ocam_for(size, size, scenes.DEMO_CAMERA_POS), fixed_extents=False)
     assert abs(cnt["segments"] - tot["segments"]) <= 1e-3 * tot["segments"]
     # the literal 320x240 of BASELINE.json is not renderable by the reference (F4): it throws, and so do we
     with pytest.raises(IndexError):

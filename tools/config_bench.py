@@ -21,31 +21,12 @@ import raytracer_js_b200 as rt
 from raytracer_js_b200 import _native as N
 from raytracer_js_b200 import scenes
 
-CONFIGS = {
-    "c2": dict(w=1920, h=1080, spp=16, n=100000, dmin=0.002, dmax=0.006, mix="mirrors", box=0.0, tex=False),
-    "c3": dict(w=3840, h=2160, spp=4, n=1000000, dmin=0.0005, dmax=0.002, mix="mirrors", box=0.1, tex=True),
-    "c4": dict(w=7680, h=4320, spp=64, n=1000000, dmin=0.0005, dmax=0.002, mix="mirrors", box=0.0, tex=False),
-}
+CONFIGS = scenes.BASELINE_CONFIGS
 
 
 def build(cfg):
     t0 = time.perf_counter()
-    if cfg["tex"]:
-        # textured entities share 4 image textures; the draws per entity vary, so the generator is sequential:
-        # build the geometry in bulk and pick textures with a second stream of draws
-        texs = [scenes.checker_texture(1024, 512, seed=s) for s in (1, 2, 3, 4)]
-        fb = scenes.random_spheres_flat(cfg["n"], cfg["dmin"], cfg["dmax"], 42.0, cfg["mix"], cfg["box"])
-        a = fb.flat.arrays
-        base = len(fb.flat.textures)
-        for t in texs:
-            fb.flat.texture_index(t)
-        pick = (scenes.fplcg_draws(43.0, cfg["n"]) * 4).astype(np.int32)
-        light = a["mat_light"][a["ent_material"]].astype(bool)
-        textured = (~light) & (a["ent_type"] == 0)
-        a["ent_texture"] = np.where(textured, base + pick, a["ent_texture"]).astype(np.int32)
-        fb.flat.finalize_tables()
-    else:
-        fb = scenes.random_spheres_flat(cfg["n"], cfg["dmin"], cfg["dmax"], 42.0, cfg["mix"], cfg["box"])
+    fb = scenes.build_config(cfg)
     return fb, time.perf_counter() - t0
 
 

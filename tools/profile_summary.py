@@ -29,7 +29,7 @@ def to_bytes(v, unit):
 
 
 summary = {}
-for name in ("primary", "c2_bounce", "c2_resample"):
+for name in ("primary", "c2_primary", "c2_bounce", "c2_resample"):
     rep = os.path.join(G, f"prof_{tag}_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -50,6 +50,11 @@ for name in ("primary", "c2_bounce", "c2_resample"):
     summary[name] = d
     reg = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), rep], capture_output=True, text=True).stdout
     open(os.path.join(P, f"{tag}_regions_{name}.txt"), "w").write(f"# {d['kernel']}\n# ncu --set full --import-source on, aggregated per function by tools/ncu_regions.py\n" + reg)
+# bench.py quotes these numbers only while the kernel sources are the ones they were captured from
+sys.path.insert(0, ROOT)
+import bench
+summary["fingerprint"] = bench.source_fingerprint()
+summary["fingerprint_of"] = "sha256[:16] over raytracer.js_b200/csrc/* + include/rt_b200.h (bench.source_fingerprint)"
 json.dump(summary, open(os.path.join(P, f"{tag}_summary.json"), "w"), indent=1)
 
 for f in (f"{tag}_launches.csv", f"{tag}_c2_launches.csv"):
@@ -71,4 +76,4 @@ if "primary" in summary:
                "source": f"profiles/{tag}_summary.json (ncu --set full, bench.py --steps 3 --warmup 3), L2 not flushed under ncu"},
               open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(json.dumps({k: {m: v for m, v in d.items() if m in ("gpu__time_duration.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
-                                                             "smsp__issue_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum")} for k, d in summary.items()}, indent=1))
+                                                             "smsp__issue_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum")} for k, d in summary.items() if isinstance(d, dict)}, indent=1))
