@@ -190,6 +190,11 @@ rt_status rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* params, 
  * the ExposureBuffer resident on the GPU (tone mapping on device, multi-GPU tile exchange). */
 rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* params, uint32_t render_flags,
                            float* rgb_dev, int32_t* first_ids_dev);
+/* Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250) alone: the direction the generator yields for every
+ * pixel, float64 [height][width][3], produced on the device by the same iterated rotations (bit for bit the
+ * generator's values; un-normalised, as Raytracer.trace_frame passes them on, src/raytracer.ts:323-324).  Host
+ * buffer, synchronous.  Every render call runs this pass itself; the entry point exists for checking it. */
+rt_status rt_camera_directions(rt_ctx* ctx, const rt_camera* cam, double* dirs);
 /* Counters of the last rt_render_device with RT_RENDER_COUNTERS (synchronises the stream). */
 rt_status rt_get_counters(rt_ctx* ctx, rt_counters* counters);
 rt_status rt_synchronize(rt_ctx* ctx);

@@ -30,6 +30,8 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -649,6 +651,9 @@ struct RayResult {
 	int first_entity;  // entity of the first non-null collision_info of the path, -1 = none
 };
 
+// ORC_DEBUG_PATHS=1 in the environment: every collision of every traced path is printed (debugging single pixels)
+static const bool g_debug_paths = getenv("ORC_DEBUG_PATHS") != nullptr;
+
 RayResult trace_ray(const Scene& s, const Config& cfg, Walker& walker, FpLcg& rng, const V3& start_point,
                     const NodePos& start_node, const V3& dir_in, int start_substance, PixelCounters& pc,
                     Totals& tot) {
@@ -684,6 +689,9 @@ RayResult trace_ray(const Scene& s, const Config& cfg, Walker& walker, FpLcg& rn
 			if (ci.hit) break;
 		}
 		if (!ci.hit) continue;
+		if (g_debug_paths)
+			fprintf(stderr, "[oracle] hit %d: entity %d from (%.17g %.17g %.17g) dir (%.17g %.17g %.17g) at (%.17g %.17g %.17g)\n", refcount,
+			        entity, refpoint[0], refpoint[1], refpoint[2], dir[0], dir[1], dir[2], ci.point[0], ci.point[1], ci.point[2]);
 		if (res.first_entity < 0) res.first_entity = entity;
 		if (dot(dir, ci.normal) >= 0) {  // :200-203
 			tot.acute_warnings++;

@@ -80,6 +80,7 @@ EXPORTS = {
     "rt_render_device": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32, C.c_void_p,
                                    C.c_void_p]),
     "rt_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
+    "rt_camera_directions": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.c_void_p]),
     "rt_present_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Tone), C.c_void_p]),
     "rt_present_stats": (C.c_int, [C.c_void_p, C.POINTER(ExposureStats)]),
     "rt_present": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Tone), C.c_void_p,

@@ -25,6 +25,25 @@ __global__ void rt_prepare_primary_kernel(const __grid_constant__ RtDevScene S, 
 	out[s] = r;
 }
 
+// Ray generation: Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250) for the whole frame.  The generator
+// ITERATES a rotation along every row, outwards from the middle column; in floating point that recurrence has no
+// closed form with the same bits, and after three mirror bounces off millimetre spheres a last-bit difference of a
+// camera direction is a different path.  So the recurrence itself runs here: one thread per half row (2 x height
+// threads, width / 2 dependent steps each - about 10 us at 1080p), every direction stored once, 32 B per pixel.
+__global__ void __launch_bounds__(32)
+    rt_raygen_kernel(const __grid_constant__ RtFrame F, RtD4* __restrict__ dirs, int tiles_x) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= 2 * F.height) return;
+	const int y = t >> 1, half = t & 1;
+	RtD4* out = dirs + (size_t)y * F.width;
+	if (F.tile_world > 1) {
+		const int row_tile = (y / RT_TILE_H) * tiles_x;
+		raygen_half_row(F, y, half, out, [&](int x) { return (row_tile + x / RT_TILE_W) % F.tile_world == F.tile_rank; });
+	} else {
+		raygen_half_row(F, y, half, out, [](int) { return true; });
+	}
+}
+
 // Persistent warps: the grid is sized to the resident capacity of the GPU (SMs x CTAs/SM) and every
 // warp pulls 8x4-pixel patches from an atomic counter until the frame (or this rank's share of its
 // 16x16 tiles, t % tile_world == tile_rank) is done.  One thread per pixel; the 32 rays of a patch
@@ -70,24 +89,31 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 	if (err) atomicOr(F.error_flags, err);
 }
 
-// ---- the two-stage pipeline (default): primary stage = packet walk, bounce stage = per-ray paths
-// Primary stage.  Same persistent-warp patch dispenser as above; every warp walks the octree ONCE for the
-// 32 camera rays of its patch (rt_trace.cuh: packet_primary_hits), finishes the pixels whose path ends at
-// the first hit and appends the others to the continuation queue with one warp-aggregated atomic.
+// ---- the pipeline (default): primary stage = packet walk + shading of the paths that end at their first hit,
+// bounce stage = the continued paths, ray by ray
+// Primary stage.  Same persistent-warp dispenser as above, handing out packets of PPL 8x4 sub-patches of a 16x16
+// tile; every warp walks the octree ONCE for the 32 x PPL camera rays of its packet (rt_trace.cuh:
+// packet_primary_hits), shades and stores the pixels whose path ends at the first hit and appends the others to
+// the continuation queue (primary_patch).  Per warp in shared memory: the node-record stack of the walk, the
+// packet's ray table (32 x PPL x 16 B: rays are touched only when a list entry survives the packet's cone test,
+// and keeping them out of the registers is what lets 5-6 CTAs be resident per SM), and the staging of a
+// sub-patch's pixels for 16-byte stores.
 #define RT_A_WARPS 4
 #ifndef RT_PPL
 #define RT_PPL 4  // rays per lane in the primary stage: a packet is RT_PPL 8x4 sub-patches of a 16x16 tile
 #endif
 #ifndef RT_A_MINB
-#define RT_A_MINB 4
+#define RT_A_MINB 5
 #endif
-template <int PPL>
-__global__ void __launch_bounds__(RT_A_WARPS * 32, RT_A_MINB)
+template <int PPL, int MINB>
+__global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
     rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_packets) {
 	__shared__ RtPNode stacks[RT_A_WARPS][RT_PACKET_STACK];
+	__shared__ __align__(16) RtPRay rays[RT_A_WARPS][PPL * 32];
+	__shared__ __align__(16) float stages[RT_A_WARPS][96];
 	constexpr int PER_TILE = 8 / PPL;
-	const int lane = threadIdx.x & 31;
-	RtPNode* stack = stacks[threadIdx.x >> 5];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t err = 0;
 	while (true) {
 		unsigned p = 0;
 		if (lane == 0) p = atomicAdd(F.work_counter, 1u);
@@ -101,79 +127,7 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, RT_A_MINB)
 		pt.y0 = (tile / tiles_x) * RT_TILE_H;
 		pt.sub0 = (int)(p % PER_TILE) * PPL;
 		pt.out_base = (size_t)k * RT_BLOCK;
-		primary_patch<PPL>(S, F, pt, stack);
-	}
-}
-
-// Shade stage: one thread per pixel of this rank (output order, coalesced).  Turns the first-hit slot into
-// the pixel's colour when the path ends there (miss -> sky, diffuse, light, ...: primary_terminal), else
-// appends the pixel to the continuation queue with one warp-aggregated atomic.
-// The colours leave through shared memory: 16 consecutive pixels are 192 contiguous bytes of the frame, which
-// 12 lanes store as whole 16-byte words - full sectors instead of three strided 4-byte stores per lane, which
-// is what matters when the frame lives in another GPU's memory (rt_render_shard_device: every store is an
-// NVLink write).
-__global__ void __launch_bounds__(256, 6)
-    rt_shade_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, size_t n_out) {
-	__shared__ __align__(16) float stage[256 * 3];
-	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	size_t i = F.out_first + t;
-	const int lane = threadIdx.x & 31;
-	uint32_t err = 0;
-	bool enqueue = false, done = false;
-	int x = 0, y = 0, slot = -1, first_entity = -1;
-	float px[3] = {0.f, 0.f, 0.f};
-	if (t < n_out) {
-		bool valid = true;
-		if (F.tile_compact || F.tile_world > 1) {
-			// sharded: thread t = pixel (t % 256) of this rank's k-th tile; the output index is tile-major
-			// (compact) or the pixel's place in the frame (a shard of ONE frame, possibly in peer memory)
-			const int k = (int)(t / RT_BLOCK), in = (int)(t % RT_BLOCK);
-			const int tile = F.tile_begin + F.tile_rank + k * F.tile_world;
-			valid = tile < F.tile_end;
-			x = (tile % tiles_x) * RT_TILE_W + (in & (RT_TILE_W - 1));
-			y = (tile / tiles_x) * RT_TILE_H + (in / RT_TILE_W);
-			valid = valid && x < F.width && y < F.height;
-			i = F.tile_compact ? t : (size_t)y * F.width + x;
-		} else if (i <= 0xffffffffull) {  // (32-bit division: the 64-bit one is a long instruction sequence)
-			y = (int)((unsigned)i / (unsigned)F.width);
-			x = (int)((unsigned)i - (unsigned)y * (unsigned)F.width);
-		} else {
-			y = (int)(i / F.width);
-			x = (int)(i % F.width);
-		}
-		if (valid) {
-			slot = F.hit_slots[i];
-			done = slot != RT_SLOT_UNKNOWN && primary_finish_px(S, F, x, y, slot, i, err, px, first_entity);
-			enqueue = !done;
-		}
-	}
-	// ---- colours: 16 pixels at a time
-	{
-		const int l16 = lane & 15;
-		const unsigned half = 0xffffu << (lane & 16);
-		const unsigned long long base = __shfl_sync(0xffffffffu, (unsigned long long)i, lane & 16);
-		const bool in_run = done && i == base + (unsigned)l16;
-		const bool wide = (__ballot_sync(0xffffffffu, in_run) & half) == half && (base & 3ull) == 0 &&
-		                  (reinterpret_cast<uintptr_t>(F.rgb) & 15u) == 0;
-		if (wide) {
-			stage[threadIdx.x * 3] = px[0]; stage[threadIdx.x * 3 + 1] = px[1]; stage[threadIdx.x * 3 + 2] = px[2];
-		}
-		__syncwarp();
-		if (wide) {
-			if (l16 < 12)
-				reinterpret_cast<float4*>(F.rgb + base * 3)[l16] = reinterpret_cast<const float4*>(stage + (threadIdx.x & ~15) * 3)[l16];
-		} else if (done) {
-			float* o = F.rgb + i * 3;
-			o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
-		}
-		if (done && F.first_ids) F.first_ids[i] = first_entity;
-	}
-	const unsigned m = __ballot_sync(0xffffffffu, enqueue);
-	if (m) {
-		unsigned base = 0;
-		if (lane == 0) base = atomicAdd(F.queue_count, (unsigned)__popc(m));
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (enqueue) F.queue[base + __popc(m & ((1u << lane) - 1u))] = RtQueueItem{((uint32_t)y << 16) | (uint32_t)x, slot};
+		primary_patch<PPL>(S, F, pt, stacks[warp], rays[warp], stages[warp], err);
 	}
 	if (err) atomicOr(F.error_flags, err);
 }
@@ -667,12 +621,11 @@ struct rt_ctx {
 	RtDevScene dev{};
 
 	// per-frame
-	DevBuf<RtD2> col_cs;
 	DevBuf<RtD4> row_fr;
+	DevBuf<RtD4> dirs;                           // [height][width] ray-generation table of the current camera
 	DevBuf<float> rgb;
 	DevBuf<int> ids;
 	DevBuf<unsigned long long> counters;
-	std::vector<RtD2> h_col_cs;
 	std::vector<RtD4> h_row_fr;
 	DevBuf<uint8_t> l2_scratch;
 	DevBuf<RtF4> prim_geom;
@@ -683,11 +636,11 @@ struct rt_ctx {
 	int present_blocks = 0;
 	uint32_t exposure_w = 0, exposure_h = 0;     // size of the resident ExposureBuffer in ctx->rgb (rt_render_present)
 	DevBuf<double> samples;
-	DevBuf<int> hit_slots;
 	DevBuf<uint32_t*> peer_flags;
 	std::vector<uint32_t*> peer_flags_host;
 	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
-	int ppl = RT_PPL;
+	int ppl = RT_PPL;                            // tuning knob RT_B200_PPL=4|8: sub-patches (rays per lane) of a packet
+	int primary_minb = RT_A_MINB;                // tuning knob RT_B200_PRIMARY_MINB=4|5|6: resident CTAs per SM the primary stage is compiled for
 	int bounce_min_walking = 12;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
 	int resample_min_frames = 8;                 // tuning knob RT_B200_RESAMPLE_MIN
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
@@ -726,7 +679,12 @@ rt_status check_args(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm) {
 	return st ? fail(ctx, st, err) : RT_OK;
 }
 
-// Builds the RtFrame (camera tables, start state) and launches the kernel on the ctx stream.
+const void* primary_kernel_of(int ppl, int minb) {
+	if (ppl == 8)
+		return minb == 4 ? (const void*)rt_primary_kernel<8, 4> : minb == 6 ? (const void*)rt_primary_kernel<8, 6> : (const void*)rt_primary_kernel<8, 5>;
+	return minb == 4 ? (const void*)rt_primary_kernel<4, 4> : minb == 6 ? (const void*)rt_primary_kernel<4, 6> : (const void*)rt_primary_kernel<4, 5>;
+}
+
 // Builds the RtFrame (camera tables, start state) and enqueues the kernels on the ctx stream.  The frame
 // can be cut into `n_bands` groups of whole tile rows, each rendered by its own launches; after_band(b,
 // row_begin, row_end) is called right after band b's kernels were enqueued (rt_render uses it to start the
@@ -769,27 +727,28 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	}
 
 	// ---- host preparation and every allocation (nothing below this block allocates: it may be captured)
-	const size_t n_col = cam->width, n_row = cam->height;
-	if (ctx->stage_cap < n_col * sizeof(RtD2) + n_row * sizeof(RtD4)) {
+	const size_t n_row = cam->height;
+	if (ctx->stage_cap < n_row * sizeof(RtD4)) {
 		if (ctx->stage) cudaFreeHost(ctx->stage);
 		ctx->stage = nullptr;
 		ctx->stage_cap = 0;
-		RT_CUDA(ctx, cudaMallocHost(&ctx->stage, n_col * sizeof(RtD2) + n_row * sizeof(RtD4)));
-		ctx->stage_cap = n_col * sizeof(RtD2) + n_row * sizeof(RtD4);
+		RT_CUDA(ctx, cudaMallocHost(&ctx->stage, n_row * sizeof(RtD4)));
+		ctx->stage_cap = n_row * sizeof(RtD4);
 	}
-	RT_CUDA(ctx, cudaEventSynchronize(ctx->stage_free));  // the previous frame's table copies have left the staging
-	rt_build_camera_tables(*cam, ctx->h_col_cs, ctx->h_row_fr);
+	RT_CUDA(ctx, cudaEventSynchronize(ctx->stage_free));  // the previous frame's table copy has left the staging
+	double scan_cos = 1.0, scan_sin = 0.0;
+	rt_build_camera_rows(*cam, ctx->h_row_fr, scan_cos, scan_sin);
 	RtD4* st_row = reinterpret_cast<RtD4*>(ctx->stage);
-	RtD2* st_col = reinterpret_cast<RtD2*>(st_row + n_row);
 	memcpy(st_row, ctx->h_row_fr.data(), n_row * sizeof(RtD4));
-	memcpy(st_col, ctx->h_col_cs.data(), n_col * sizeof(RtD2));
-	RT_CUDA(ctx, ctx->col_cs.alloc(n_col));
 	RT_CUDA(ctx, ctx->row_fr.alloc(n_row));
+	RT_CUDA(ctx, ctx->dirs.alloc((size_t)cam->width * cam->height));
 	RtFrame F{};
 	std::string err;
 	if (rt_status st = rt_fill_frame(ctx->host, cam, prm, F, err)) return fail(ctx, st, err);
-	F.col_cs = ctx->col_cs.p;
 	F.row_fr = ctx->row_fr.p;
+	F.dirs = ctx->dirs.p;
+	F.scan_cos = scan_cos;
+	F.scan_sin = scan_sin;
 	F.rgb = rgb_dev;
 	F.first_ids = ids_dev;
 	F.tile_rank = tile_rank;
@@ -833,7 +792,6 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 		                                : (size_t)F.width * F.height;
 		RT_CUDA(ctx, ctx->queue.alloc(cap));
 		if (resample) RT_CUDA(ctx, ctx->vqueue.alloc(cap));
-		RT_CUDA(ctx, ctx->hit_slots.alloc(cap));
 	}
 	auto grid_of = [&](int which, const void* kernel, int threads, int& out) -> rt_status {
 		int& grid = ctx->render_grid[which];
@@ -847,9 +805,8 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 		return RT_OK;
 	};
 	// rays per lane of the packet stage (tuning knob: RT_B200_PPL=1|2|4|8 in the environment)
-	const int ppl = ctx->ppl;
-	const void* primary_kernel = ppl == 1 ? (const void*)rt_primary_kernel<1> : ppl == 2 ? (const void*)rt_primary_kernel<2>
-	                           : ppl == 4 ? (const void*)rt_primary_kernel<4> : (const void*)rt_primary_kernel<8>;
+	const int ppl = ctx->ppl, pminb = ctx->primary_minb;
+	const void* primary_kernel = primary_kernel_of(ppl, pminb);
 	// resident CTAs per SM the bounce stage is compiled for (tuning knob: RT_B200_BOUNCE_MINB=4|5|6|8)
 	const int minb = ctx->bounce_minb;
 	const void* bounce_kernel = minb == 4 ? (const void*)rt_bounce_kernel<4> : minb == 5 ? (const void*)rt_bounce_kernel<5>
@@ -858,7 +815,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	                            : minb == 6 ? (const void*)rt_resample_kernel<6> : (const void*)rt_resample_kernel<8>;
 	int grid_primary = 0, grid_bounce = 0, grid_ray = 0, grid_resample = 0;
 	if (pipeline) {
-		if (rt_status st = grid_of(4 + (ppl == 1 ? 0 : ppl == 2 ? 1 : ppl == 4 ? 2 : 3), primary_kernel, RT_A_WARPS * 32, grid_primary)) return st;
+		if (rt_status st = grid_of(4, primary_kernel, RT_A_WARPS * 32, grid_primary)) return st;
 		if (rt_status st = grid_of(3, bounce_kernel, RT_WARPS_PER_CTA * 32, grid_bounce)) return st;
 		if (resample) {
 			if (rt_status st = grid_of(2, resample_kernel, RT_WARPS_PER_CTA * 32, grid_resample)) return st;
@@ -880,7 +837,6 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 		// origin-relative records that call left on the device are this frame's, so the graph holds neither.
 		if (!capture) {
 			RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, st_row, n_row * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
-			RT_CUDA(ctx, cudaMemcpyAsync(ctx->col_cs.p, st_col, n_col * sizeof(RtD2), cudaMemcpyHostToDevice, ctx->stream));
 			RT_CUDA(ctx, cudaEventRecord(ctx->stage_free, ctx->stream));
 		}
 		RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, n_cells * sizeof(unsigned long long), ctx->stream));
@@ -890,6 +846,12 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 			return prof ? cudaEventRecord(ctx->stage_ev[stage], ctx->stream) : cudaSuccess;
 		};
 		RT_CUDA(ctx, mark(0));
+		if (!capture) {  // ray generation: the generator's iterated rotations, every pixel's direction (2 x height threads)
+			rt_raygen_kernel<<<(2 * F.height + 31) / 32, 32, 0, ctx->stream>>>(F, ctx->dirs.p, tiles_x);
+			ctx->launches++;
+			ctx->stage_ran[0] = prof;
+			RT_CUDA(ctx, cudaGetLastError());
+		}
 		if (prim && !capture) {
 			rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
 			                                                                         cam->pos[2], ctx->prim_geom.p);
@@ -919,22 +881,21 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				// primary stage (packet walk) -> shade stage -> bounce stage over the continuation queue
 				F.queue = ctx->queue.p + F.out_first;
 				F.vqueue = resample ? ctx->vqueue.p + F.out_first : nullptr;
-				F.hit_slots = ctx->hit_slots.p;
 				const int n_packets = my_tiles * (8 / ppl);
 				const int blocks = std::min(grid_primary, (n_packets + RT_A_WARPS - 1) / RT_A_WARPS);
 				void* args[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x, (void*)&n_packets};
 				RT_CUDA(ctx, cudaLaunchKernel(primary_kernel, dim3(blocks), dim3(RT_A_WARPS * 32), args, 0, ctx->stream));
 				ctx->launches++;
 				RT_CUDA(ctx, mark(2));
-				rt_shade_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(ctx->dev, F, tiles_x, n_out);
-				ctx->launches++;
-				RT_CUDA(ctx, cudaGetLastError());
 				RT_CUDA(ctx, mark(3));
 				void* bargs[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x};
-				RT_CUDA(ctx, cudaLaunchKernel(bounce_kernel, dim3(std::min(grid_bounce, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA)),
+				// with refmax <= 1 no path continues after its first hit: the queue only ever holds rays the lock-step
+				// walk could not take, and one CTA per SM drains it
+				const int bounce_blocks = prm->refmax <= 1 ? std::max(1, grid_bounce / std::max(1, minb)) : grid_bounce;
+				RT_CUDA(ctx, cudaLaunchKernel(bounce_kernel, dim3(std::min(bounce_blocks, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA)),
 				                              dim3(RT_WARPS_PER_CTA * 32), bargs, 0, ctx->stream));
 				RT_CUDA(ctx, mark(4));
-				ctx->stage_ran[1] = ctx->stage_ran[2] = ctx->stage_ran[3] = prof;
+				ctx->stage_ran[1] = ctx->stage_ran[3] = prof;
 				if (resample) {
 					ctx->launches++;
 					RT_CUDA(ctx, cudaLaunchKernel(resample_kernel, dim3(std::min(grid_resample, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA)),
@@ -1059,7 +1020,11 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	}
 	if (const char* e = getenv("RT_B200_PPL")) {
 		const int v = atoi(e);
-		if (v == 1 || v == 2 || v == 4 || v == 8) ctx->ppl = v;
+		if (v == 4 || v == 8) ctx->ppl = v;
+	}
+	if (const char* e = getenv("RT_B200_PRIMARY_MINB")) {
+		const int v = atoi(e);
+		if (v == 4 || v == 5 || v == 6) ctx->primary_minb = v;
 	}
 	*out = ctx;
 	return RT_OK;
@@ -1072,8 +1037,8 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_walk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release(); ctx->bvh_geom.release();
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
-	ctx->col_cs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
-	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->hit_slots.release(); ctx->peer_flags.release();
+	ctx->dirs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
+	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->peer_flags.release();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	for (int b = 0; b < RT_MAX_BANDS; b++)
@@ -1209,6 +1174,41 @@ rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* p
 	if (!rgb_dev) return fail(ctx, RT_ERR_INVALID, "rt_render_device: rgb_dev is NULL");
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
 	return launch_render(ctx, cam, prm, flags, rgb_dev, ids_dev, 0, 1);
+}
+
+rt_status rt_camera_directions(rt_ctx* ctx, const rt_camera* cam, double* dirs) {
+	if (!ctx) return RT_ERR_INVALID;
+	if (!cam || !dirs) return fail(ctx, RT_ERR_INVALID, "rt_camera_directions: NULL argument");
+	if (cam->width == 0 || cam->height == 0 || cam->width > 65536 || cam->height > 65536)
+		return fail(ctx, RT_ERR_INVALID, rt_format("rt_camera_directions: bad frame size %ux%u", cam->width, cam->height));
+	if ((cam->flags & RT_CAM_REFERENCE_EXTENTS) && cam->width != cam->height) return fail(ctx, RT_ERR_BOUNDS, "x or y out of bounds");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	RtFrame F{};
+	for (int i = 0; i < 3; i++) F.lf[i] = cam->lf[i];
+	F.width = (int)cam->width;
+	F.height = (int)cam->height;
+	F.tile_world = 1;
+	std::vector<RtD4> rows;
+	rt_build_camera_rows(*cam, rows, F.scan_cos, F.scan_sin);
+	const size_t npx = (size_t)F.width * F.height;
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // (pageable source below: nothing may still read row_fr)
+	RT_CUDA(ctx, ctx->row_fr.alloc(rows.size()));
+	RT_CUDA(ctx, ctx->dirs.alloc(npx));
+	ctx->key_valid = false;  // the tables of a cached frame are gone
+	RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, rows.data(), rows.size() * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
+	F.row_fr = ctx->row_fr.p;
+	rt_raygen_kernel<<<(2 * F.height + 31) / 32, 32, 0, ctx->stream>>>(F, ctx->dirs.p, (F.width + RT_TILE_W - 1) / RT_TILE_W);
+	ctx->launches++;
+	RT_CUDA(ctx, cudaGetLastError());
+	std::vector<RtD4> host(npx);
+	RT_CUDA(ctx, cudaMemcpyAsync(host.data(), ctx->dirs.p, npx * sizeof(RtD4), cudaMemcpyDeviceToHost, ctx->stream));
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (size_t i = 0; i < npx; i++) {
+		dirs[3 * i] = host[i].x;
+		dirs[3 * i + 1] = host[i].y;
+		dirs[3 * i + 2] = host[i].z;
+	}
+	return RT_OK;
 }
 
 uint32_t rt_tiles_per_rank(uint32_t width, uint32_t height, uint32_t world) {

@@ -137,8 +137,13 @@ struct RtFrame {
 	// camera
 	double pos[3];
 	double lf[3];
-	const RtD2* col_cs;  // [width]  (cos,sin) of the accumulated horizontal scan rotation
-	const RtD4* row_fr;  // [height] fr rotated towards up by the accumulated vertical scan rotation
+	// Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250) iterates 2-D rotations: rows outwards from the middle
+	// row (fr towards up), then along every row outwards from the middle column (fr towards lf).  Floating-point
+	// rotations do not commute with any closed form, so the directions are produced by the very same iteration:
+	// row_fr on the host (height steps), the row scans by rt_raygen_kernel (one thread per half row), into `dirs`.
+	const RtD4* row_fr;  // [height] fr rotated towards up by the accumulated vertical scan rotation (host-built)
+	const RtD4* dirs;    // [height][width] the generator's direction of every pixel, bit for bit (xyz; w unused)
+	double scan_cos, scan_sin;  // rot_scan_h_v: cos / sin of fov_h / width
 	int width, height;
 	// start state shared by all primary rays (src/raytracer.ts:309-313)
 	int start_node, start_octant;  // start_node < 0: camera outside the root cube

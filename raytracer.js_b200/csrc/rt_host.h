@@ -408,15 +408,16 @@ inline int rt_host_entity_at_pos(const RtHostScene& c, const double* p) {
 	return -1;
 }
 
-// The accumulated scan rotations of Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250).
-// Rows: fr rotated towards up, iterated exactly like iter_v.  Columns: the 2x2 rotation the
-// generator applies to (fr_row, lf), iterated like iter_h on the coefficient pairs.
-inline void rt_build_camera_tables(const rt_camera& cam, std::vector<RtD2>& col, std::vector<RtD4>& row) {
+// The row part of Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250, iter_v): fr rotated towards up,
+// iterated exactly like the generator, outwards from the middle row.  The scans along the rows are iterated on
+// the device (rt_trace.cuh: raygen_half_row) from these and (scan_cos, scan_sin) = rot_scan_h_v.
+inline void rt_build_camera_rows(const rt_camera& cam, std::vector<RtD4>& row, double& scan_cos, double& scan_sin) {
 	const int W = (int)cam.width, H = (int)cam.height;
-	col.assign(W, RtD2{1, 0});
 	row.assign(H, RtD4{0, 0, 0, 0});
 	const double rad_h = cam.fov_h / W, rad_v = cam.fov_v / H;
-	const double ch = std::cos(rad_h), sh = std::sin(rad_h), cv = std::cos(rad_v), sv = std::sin(rad_v);
+	scan_cos = std::cos(rad_h);
+	scan_sin = std::sin(rad_h);
+	const double cv = std::cos(rad_v), sv = std::sin(rad_v);
 	auto rot3 = [](double* bx, double* by, double c, double s) {  // rotate_vectors vector.ts:318-323
 		for (int k = 0; k < 3; k++) {
 			const double x = bx[k] * c + by[k] * s;
@@ -425,41 +426,17 @@ inline void rt_build_camera_tables(const rt_camera& cam, std::vector<RtD2>& col,
 			by[k] = y;
 		}
 	};
-	{
-		const int y0 = H >> 1;
-		double fr[3] = {cam.fr[0], cam.fr[1], cam.fr[2]}, up[3] = {cam.up[0], cam.up[1], cam.up[2]};
-		for (int y = y0; y < H; y++) {
-			row[y] = RtD4{fr[0], fr[1], fr[2], 0};
-			rot3(fr, up, cv, sv);
-		}
-		double fr2[3] = {cam.fr[0], cam.fr[1], cam.fr[2]}, up2[3] = {cam.up[0], cam.up[1], cam.up[2]};
-		rot3(fr2, up2, cv, -sv);
-		for (int y = y0 - 1; y >= 0; y--) {
-			row[y] = RtD4{fr2[0], fr2[1], fr2[2], 0};
-			rot3(fr2, up2, cv, -sv);
-		}
+	const int y0 = H >> 1;
+	double fr[3] = {cam.fr[0], cam.fr[1], cam.fr[2]}, up[3] = {cam.up[0], cam.up[1], cam.up[2]};
+	for (int y = y0; y < H; y++) {
+		row[y] = RtD4{fr[0], fr[1], fr[2], 0};
+		rot3(fr, up, cv, sv);
 	}
-	{
-		const int x0 = W >> 1;
-		auto step = [](double* a, double c, double s) {  // (alpha,beta | gamma,delta)
-			const double al = a[0] * c + a[2] * s, be = a[1] * c + a[3] * s;
-			const double ga = a[0] * -s + a[2] * c, de = a[1] * -s + a[3] * c;
-			a[0] = al;
-			a[1] = be;
-			a[2] = ga;
-			a[3] = de;
-		};
-		double a[4] = {1, 0, 0, 1};
-		for (int x = x0; x < W; x++) {
-			col[x] = RtD2{a[0], a[1]};
-			step(a, ch, sh);
-		}
-		double b[4] = {1, 0, 0, 1};
-		step(b, ch, -sh);
-		for (int x = x0 - 1; x >= 0; x--) {
-			col[x] = RtD2{b[0], b[1]};
-			step(b, ch, -sh);
-		}
+	double fr2[3] = {cam.fr[0], cam.fr[1], cam.fr[2]}, up2[3] = {cam.up[0], cam.up[1], cam.up[2]};
+	rot3(fr2, up2, cv, -sv);
+	for (int y = y0 - 1; y >= 0; y--) {
+		row[y] = RtD4{fr2[0], fr2[1], fr2[2], 0};
+		rot3(fr2, up2, cv, -sv);
 	}
 }
 

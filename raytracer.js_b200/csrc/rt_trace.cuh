@@ -309,16 +309,18 @@ struct RtSearch {
 
 // The per-frame origin-relative record of one slot, for rays that start at the camera:
 //   xyz = centre - camera, taken in float64 (no cancellation) and rounded once;
-//   w   = +(radius+err)^2          sphere, camera outside it: the quick test of candidate_rel applies
-//         -(bounding radius+err)^2 box, camera outside its bounding sphere: packet cull on the bounding
-//                                  sphere, per-ray test = the generic slab test on slot_geom
-//         +inf                     camera inside the (bounding) sphere: always a candidate
+//   w   = +(radius+err)          sphere, camera outside it: the quick test of candidate_rel applies
+//         -(bounding radius+err) box, camera outside its bounding sphere: packet cull on the bounding
+//                                sphere, per-ray test = the generic slab test on slot_geom
+//         +inf                   camera inside the (bounding) sphere: always a candidate
+// (the radius itself, not its square: the packet's cone test - once per slot and packet - needs the radius,
+// the per-ray test squares it once per survivor)
 RT_HD RtF4 make_prim_record(const RtD4& g, bool is_sphere, double ox, double oy, double oz, float err_l) {
 	const double cx = g.x - ox, cy = g.y - oy, cz = g.z - oz;
 	const float rr = (is_sphere ? (float)(g.w * 0.5) : (float)(g.w * 0.8660254037844387) * 1.000001f) + err_l;
 	const float rr2 = rr * rr;
 	const bool inside = cx * cx + cy * cy + cz * cz <= (double)rr2 * 1.000001;
-	return RtF4{(float)cx, (float)cy, (float)cz, inside ? INFINITY : (is_sphere ? rr2 : -rr2)};
+	return RtF4{(float)cx, (float)cy, (float)cz, inside ? INFINITY : (is_sphere ? rr : -rr)};
 }
 
 // candidate test against the origin-relative sphere record (w finite, > 0): ~12 flops, no
@@ -328,7 +330,7 @@ RT_HD bool candidate_rel(const RtF4& g, const RtRayF& r) {
 	const float s = tca * r.inv_a;
 	const float lx = g.x - s * r.dx, ly = g.y - s * r.dy, lz = g.z - s * r.dz;
 	const float l2 = lx * lx + ly * ly + lz * lz;
-	return l2 <= g.w && tca >= 0.0f;  // camera outside the sphere: a forward root needs the centre ahead
+	return l2 <= g.w * g.w && tca >= 0.0f;  // camera outside the sphere: a forward root needs the centre ahead
 }
 
 RT_HD bool slot_candidate(const RtDevScene& S, const RtSearch& q, int s) {
@@ -705,7 +707,7 @@ RT_HD bool packet_meets_record(const RtPacket& P, const RtF4& g) {
 	const float t = g.x * P.ax + g.y * P.ay + g.z * P.az;
 	const float px = g.x - t * P.ax, py = g.y - t * P.ay, pz = g.z - t * P.az;
 	const float perp2 = px * px + py * py + pz * pz;
-	const float rhs = sqrtf(fabsf(g.w)) + t * P.sin_h;
+	const float rhs = fabsf(g.w) + t * P.sin_h;
 	return rhs >= 0.0f && perp2 * P.cos2_h <= rhs * rhs * 1.00001f;
 }
 
@@ -761,66 +763,88 @@ struct RtPatch {
 RT_HD int patch_x(const RtPatch& pt, int lane, int j) { return pt.x0 + (((pt.sub0 + j) & 1) << 3) + (lane & 7); }
 RT_HD int patch_y(const RtPatch& pt, int lane, int j) { return pt.y0 + (((pt.sub0 + j) >> 1) << 2) + (lane >> 3); }
 
-// Camera direction of pixel (x,y): get_dir_for_each_pixel (src/view/camera.ts:207-250) through the
-// host-built tables of the accumulated scan rotations.
+// Camera direction of pixel (x,y): get_dir_for_each_pixel (src/view/camera.ts:207-250), from the per-frame table
+// the ray-generation pass (raygen_half_row) filled with the generator's own iterated rotations.
 RT_HD void pixel_dir(const RtFrame& F, int x, int y, double* dir) {
-	const RtD4 fr = ld(F.row_fr + y);
-	const RtD2 cs = ld(F.col_cs + x);
-	dir[0] = xadd(xmul(fr.x, cs.x), xmul(F.lf[0], cs.y));
-	dir[1] = xadd(xmul(fr.y, cs.x), xmul(F.lf[1], cs.y));
-	dir[2] = xadd(xmul(fr.z, cs.x), xmul(F.lf[2], cs.y));
+	const RtD4 v = ld(F.dirs + ((size_t)y * F.width + x));
+	dir[0] = v.x; dir[1] = v.y; dir[2] = v.z;
+}
+
+// rotate_vectors (src/math/vector.ts:318-323): (a, b) <- (a*c + b*s, a*-s + b*c), every product and sum rounded
+RT_HD void rotate_pair(double* a, double* b, double c, double s) {
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const double x = xadd(xmul(a[k], c), xmul(b[k], s));
+		const double y = xadd(xmul(a[k], -s), xmul(b[k], c));
+		a[k] = x;
+		b[k] = y;
+	}
+}
+
+// Ray generation for one half of row y, exactly as iter_h of get_dir_for_each_pixel scans it
+// (src/view/camera.ts:214-226,240-249): starting from the row's fr (row_fr[y]) and norm_lf, the right half
+// (half == 0) yields x = width>>1, ... , width-1 rotating AFTER every yield by rot_scan_h_v, the left half
+// (half == 1) rotates by the counter-clockwise rotation FIRST and yields x = (width>>1)-1, ..., 0.
+// own(x): whether this rank stores pixel x of the row (tile sharding); `out` is the row of the table.
+template <class Own>
+RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own) {
+	const RtD4 r = ld(F.row_fr + y);
+	double fr[3] = {r.x, r.y, r.z}, lf[3] = {F.lf[0], F.lf[1], F.lf[2]};
+	const int x0 = F.width >> 1;
+	if (half == 0) {
+		for (int x = x0; x < F.width; x++) {
+			if (own(x)) out[x] = RtD4{fr[0], fr[1], fr[2], 0.0};
+			rotate_pair(fr, lf, F.scan_cos, F.scan_sin);
+		}
+	} else {
+		for (int x = x0 - 1; x >= 0; x--) {
+			rotate_pair(fr, lf, F.scan_cos, -F.scan_sin);
+			if (own(x)) out[x] = RtD4{fr[0], fr[1], fr[2], 0.0};
+		}
+	}
 }
 // pixels outside the frame ride along with the direction of the nearest pixel inside it
 RT_HD void pixel_dir_clamped(const RtFrame& F, int x, int y, double* dir) {
 	pixel_dir(F, x < F.width ? x : F.width - 1, y < F.height ? y : F.height - 1, dir);
 }
 
-// float64 confirmation of a float32 candidate for the camera ray of pixel (x,y): collision_info != null
-RT_COLD bool packet_confirm(const RtDevScene& S, const RtFrame& F, int x, int y, int slot) {
+// float64 confirmation of a float32 candidate for the camera ray of pixel (x,y): 0 = collision_info is null,
+// 1 = hit, 2 = hit whose normal does not face the ray (the guard of src/raytracer.ts:200-203 will end the path)
+RT_COLD int packet_confirm(const RtDevScene& S, const RtFrame& F, int x, int y, int slot) {
 	double dir[3];
 	pixel_dir_clamped(F, x, y, dir);
 	RtCollision col;
 	const RtD4 g64 = ld(S.slot_geom64 + slot);
-	return ld(S.slot_geom + slot).w > 0.0f ? exact_sphere(g64, F.pos, dir, col) : exact_box(g64, F.pos, dir, col);
+	const bool hit = ld(S.slot_geom + slot).w > 0.0f ? exact_sphere(g64, F.pos, dir, col) : exact_box(g64, F.pos, dir, col);
+	if (!hit) return 0;
+	return dot3(dir, col.normal) >= 0 ? 2 : 1;
 }
 
-// One lock-step walk for the rays of one direction-sign class (those with !done on entry).
+// Result of the primary search for one camera ray: the first-hit slot (bits 0..29) and RT_HIT_ACUTE, or
+// RT_HIT_NONE (miss: sky), or RT_SLOT_UNKNOWN (the ray could not take part in a lock-step walk).
+#define RT_HIT_NONE (-1)
+#define RT_HIT_ACUTE 0x40000000
+#define RT_HIT_SLOT_MASK 0x3fffffff
+// stack entries: bit 8 of child_mask = the mask has been narrowed to the children the packet may pierce
+#define RT_PNODE_TESTED 0x100
+
+// One lock-step walk for the rays of one direction-sign class: bit j of open[l] = ray j of lane l is still
+// searching.  `rays` is the packet's ray table, [PPL][32] (shared memory on the device).
 template <int PPL>
-RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const RtPRay (&r)[RT_NL][PPL],
-                             const RtPacket& P, bool (&done)[RT_NL][PPL], RtPNode* stack, int (&hit_slot)[RT_NL][PPL],
+RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const RtPRay* rays,
+                             const RtPacket& P, unsigned (&open)[RT_NL], RtPNode* stack, int (&hit)[RT_NL][PPL],
                              bool& overflow) {
 	int sp = 0;
-	auto all_done = [&]() -> bool {
-		bool open[RT_NL];
-		RT_LANES(l, lane) {
-			(void)lane;
-			open[l] = false;
-#pragma unroll
-			for (int j = 0; j < PPL; j++) open[l] = open[l] || !done[l][j];
-		}
-		return warp_ballot(open) == 0u;
-	};
-	// pushes the children of node nd the packet may pierce, last-visited first; after_oct >= 0: only the
-	// octants a ray can still reach from octant after_oct (the origin's cell / the chain child)
-	auto push_children = [&](const RtPNode& nd, int after_oct) {
-		if (!nd.child_mask) return;
-		bool ok[RT_NL];
-		const float h = nd.size * 0.5f;
-		const int want = after_oct >= 0 ? (after_oct ^ P.neg) : 0;
-		RT_LANES(l, lane) {
-			const int o = lane & 7;
-			const int key = o ^ P.neg;
-			ok[l] = lane < 8 && ((nd.child_mask >> o) & 1) && (key & want) == want && o != after_oct &&
-			        packet_pierces_cube(P, nd.x + ((o & 1) ? h : 0.0f), nd.y + ((o & 2) ? h : 0.0f),
-			                            nd.z + ((o & 4) ? h : 0.0f), h);
-		}
-		const unsigned m = warp_ballot(ok) & 0xffu;
+	// stores the children of `nd` whose octant is in the 8-bit mask m (already narrowed to what the packet may
+	// pierce) on the stack, last-visited first
+	auto push_mask = [&](const RtPNode& nd, unsigned m) {
 		if (!m) return;
 		if (sp + 8 > RT_PACKET_STACK) { overflow = true; return; }
 		const unsigned mk = xor_permute8(m, P.neg);  // bit = visit key
 		RT_LANES(l, lane) {
-			if (ok[l]) {
-				const int o = lane & 7;
+			(void)l;
+			const int o = lane & 7;
+			if (lane < 8 && ((m >> o) & 1u)) {
 				const int key = o ^ P.neg;
 				// The stack holds the children's RECORDS, not their indices: the (up to 8) records are
 				// consecutive in memory (breadth-first numbering), so this is one coalesced fetch whose
@@ -832,6 +856,53 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 			}
 		}
 		sp += popc32(m);
+		warp_sync();
+	};
+	// children of an origin-chain node: only the octants a ray can still reach from octant after_oct (the
+	// origin's cell / the chain child below), pierce test on lanes 0..7
+	auto push_chain_children = [&](const RtPNode& nd, int after_oct) {
+		if (!nd.child_mask) return;
+		bool ok[RT_NL];
+		const float h = nd.size * 0.5f;
+		const int want = after_oct ^ P.neg;
+		RT_LANES(l, lane) {
+			const int o = lane & 7;
+			const int key = o ^ P.neg;
+			ok[l] = lane < 8 && ((nd.child_mask >> o) & 1) && (key & want) == want && o != after_oct &&
+			        packet_pierces_cube(P, nd.x + ((o & 1) ? h : 0.0f), nd.y + ((o & 2) ? h : 0.0f),
+			                            nd.z + ((o & 4) ? h : 0.0f), h);
+		}
+		push_mask(nd, warp_ballot(ok) & 0xffu);
+	};
+	// The pierce test of the (up to) 4 topmost stack entries at once: lane group g = lane >> 3 takes entry
+	// sp-1-g, lane & 7 is the octant - 32 cube tests for the price of one, and the siblings below the top are
+	// popped next anyway.  The entry's child_mask is narrowed in place and marked RT_PNODE_TESTED.
+	auto test_top = [&]() {
+		bool ok[RT_NL];
+		RT_LANES(l, lane) {
+			const int e = sp - 1 - (lane >> 3);
+			ok[l] = false;
+			if (e >= 0) {
+				const RtPNode& nd = stack[e];
+				const int o = lane & 7;
+				if (!(nd.child_mask & RT_PNODE_TESTED) && ((nd.child_mask >> o) & 1)) {
+					const float h = nd.size * 0.5f;
+					ok[l] = packet_pierces_cube(P, nd.x + ((o & 1) ? h : 0.0f), nd.y + ((o & 2) ? h : 0.0f),
+					                            nd.z + ((o & 4) ? h : 0.0f), h);
+				}
+			}
+		}
+		const unsigned m = warp_ballot(ok);
+		warp_sync();
+		RT_LANES(l, lane) {
+			(void)l;
+			const int e = sp - 1 - (lane >> 3);
+			if ((lane & 7) == 0 && e >= 0 && !(stack[e].child_mask & RT_PNODE_TESTED)) {
+				// (the full child_mask stays in bits 16..23: push_mask needs it to locate the records)
+				const int full = stack[e].child_mask & 0xff;
+				stack[e].child_mask = (int)((m >> (lane & 24)) & 0xffu) | RT_PNODE_TESTED | (full << 16);
+			}
+		}
 		warp_sync();
 	};
 	// scans slots [beg,end) in list order; returns true when every ray has its hit
@@ -849,17 +920,18 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 				m &= m - 1;
 				const RtF4 g = ld(F.prim_geom + slot);
 				const bool quick = g.w > 0.0f && g.w != INFINITY;
+				const float rr2 = g.w * g.w;
 				RT_LANES(l, lane) {
 #pragma unroll
 					for (int j = 0; j < PPL; j++) {
-						if (done[l][j]) continue;
-						const RtPRay& q = r[l][j];
+						if (!((open[l] >> j) & 1u)) continue;
+						const RtPRay q = rays[j * 32 + lane];
 						bool cand;
 						if (quick) {  // candidate_rel
 							const float tca = g.x * q.dx + g.y * q.dy + g.z * q.dz;
 							const float sc = tca * q.inv_a;
 							const float lx = g.x - sc * q.dx, ly = g.y - sc * q.dy, lz = g.z - sc * q.dz;
-							cand = lx * lx + ly * ly + lz * lz <= g.w && tca >= 0.0f;
+							cand = lx * lx + ly * ly + lz * lz <= rr2 && tca >= 0.0f;
 						} else {
 							RtRayF rf;
 							rf.ox = P.ox; rf.oy = P.oy; rf.oz = P.oz;
@@ -868,99 +940,100 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 							rf.inv_a = q.inv_a;
 							cand = candidate(ld(S.slot_geom + slot), rf, S.err_l);
 						}
-						if (cand && packet_confirm(S, F, patch_x(pt, lane, j), patch_y(pt, lane, j), slot)) {
-							hit_slot[l][j] = slot;
-							done[l][j] = true;
+						if (cand) {
+							const int c = packet_confirm(S, F, patch_x(pt, lane, j), patch_y(pt, lane, j), slot);
+							if (c) {
+								hit[l][j] = slot | (c == 2 ? RT_HIT_ACUTE : 0);
+								open[l] &= ~(1u << j);
+							}
 						}
 					}
 				}
 			}
-			if (all_done()) return true;
+			bool any[RT_NL];
+			RT_LANES(l, lane) { (void)lane; any[l] = open[l] != 0u; }
+			if (warp_ballot(any) == 0u) return true;
 		}
 		return false;
 	};
 
 	for (int k = 0; k < F.chain_levels; k++) {
-		push_children(ld(S.node_pk + F.chain_node[k]), F.chain_oct[k]);
+		push_chain_children(ld(S.node_pk + F.chain_node[k]), F.chain_oct[k]);
 		while (sp > 0 && !overflow) {
-			const RtPNode nd = stack[--sp];
+			if (!(stack[sp - 1].child_mask & RT_PNODE_TESTED)) test_top();
+			RtPNode nd = stack[--sp];
 			warp_sync();
+			const unsigned pierced = (unsigned)nd.child_mask & 0xffu;
+			nd.child_mask = (nd.child_mask >> 16) & 0xff;
 			if (nd.list_cnt > 0 && scan(nd.list_off, nd.list_off + nd.list_cnt)) return;
-			push_children(nd, -1);
+			push_mask(nd, pierced);
 		}
 		if (overflow) return;
 		if (F.chain_end[k] > F.chain_beg[k] && scan(F.chain_beg[k], F.chain_end[k])) return;
 	}
 }
 
-// First-hit slot of every camera ray of the packet in the reference's visit order, or -1.  Rays with
-// skip[l][j] set (pixels outside the frame) take no part.  `stack` is RT_PACKET_STACK ints private to
-// the warp.  A packet whose rays differ in the sign of a direction component (it straddles one of the
-// three great circles through the axes) is walked once per sign class (a zero component counts as
-// positive: such a ray never crosses a plane of that axis, so either order is its own).  unresolved[l][j]
-// is set for rays that cannot take part in a lock-step walk (non-finite direction; node stack overflow):
-// the caller searches those ray by ray.
+// First-hit code of every camera ray of the packet in the reference's visit order (RT_HIT_* above).  Rays with
+// bit j of skip[l] set (pixels outside the frame) take no part.  `stack` is RT_PACKET_STACK records and `rays`
+// PPL * 32 ray records private to the warp.  A packet whose rays differ in the sign of a direction component
+// (it straddles one of the three great circles through the axes) is walked once per sign class (a zero
+// component counts as positive: such a ray never crosses a plane of that axis, so either order is its own).
+// Rays that cannot take part in a lock-step walk (non-finite direction; node stack overflow; a packet that is
+// not narrow) come back as RT_SLOT_UNKNOWN: the bounce stage searches those ray by ray.
 template <int PPL>
-RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const bool (&skip)[RT_NL][PPL],
-                               RtPNode* stack, int (&hit_slot)[RT_NL][PPL], bool (&unresolved)[RT_NL][PPL]) {
-	RtPRay r[RT_NL][PPL];
-	int neg[RT_NL][PPL];
-	bool todo[RT_NL][PPL];
+RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const unsigned (&skip)[RT_NL],
+                               RtPNode* stack, RtPRay* rays, int (&hit)[RT_NL][PPL]) {
+	unsigned todo[RT_NL], negs[RT_NL];  // bit j: ray j still to do; 3 bits per ray: its direction-sign class
 	RT_LANES(l, lane) {
+		todo[l] = 0u;
+		negs[l] = 0u;
 #pragma unroll
 		for (int j = 0; j < PPL; j++) {
 			double dir[3];
 			pixel_dir_clamped(F, patch_x(pt, lane, j), patch_y(pt, lane, j), dir);
-			RtPRay& q = r[l][j];
+			RtPRay q;
 			q.dx = (float)dir[0]; q.dy = (float)dir[1]; q.dz = (float)dir[2];
 			q.inv_a = 1.0f / (q.dx * q.dx + q.dy * q.dy + q.dz * q.dz);
-			neg[l][j] = (q.dx < 0.0f ? 1 : 0) | (q.dy < 0.0f ? 2 : 0) | (q.dz < 0.0f ? 4 : 0);
-			hit_slot[l][j] = -1;
-			unresolved[l][j] = !skip[l][j] && !(q.inv_a > 0.0f && q.inv_a < INFINITY);
-			todo[l][j] = !skip[l][j] && !unresolved[l][j];
+			rays[j * 32 + lane] = q;
+			negs[l] |= (unsigned)((q.dx < 0.0f ? 1 : 0) | (q.dy < 0.0f ? 2 : 0) | (q.dz < 0.0f ? 4 : 0)) << (3 * j);
+			const bool skipped = (skip[l] >> j) & 1u;
+			const bool finite = q.inv_a > 0.0f && q.inv_a < INFINITY;
+			hit[l][j] = !skipped && !finite ? RT_SLOT_UNKNOWN : RT_HIT_NONE;
+			if (!skipped && finite) todo[l] |= 1u << j;
 		}
 	}
+	warp_sync();
 	while (true) {
 		// ---- next sign class: that of the first ray still to do (lowest lane, then lowest j)
-		int first_j[RT_NL];
 		bool any[RT_NL];
-		RT_LANES(l, lane) {
-			(void)lane;
-			first_j[l] = -1;
-#pragma unroll
-			for (int j = PPL - 1; j >= 0; j--)
-				if (todo[l][j]) first_j[l] = j;
-			any[l] = first_j[l] >= 0;
-		}
+		RT_LANES(l, lane) { (void)lane; any[l] = todo[l] != 0u; }
 		const unsigned todo_mask = warp_ballot(any);
 		if (!todo_mask) break;
 		const int first_lane = ffs32(todo_mask);
 		RtPacket P;
 		{
 			int cls[RT_NL];
-			RT_LANES(l, lane) { (void)lane; cls[l] = first_j[l] >= 0 ? neg[l][first_j[l]] : 0; }
+			RT_LANES(l, lane) { (void)lane; cls[l] = todo[l] ? (int)((negs[l] >> (3 * ffs32(todo[l]))) & 7u) : 0; }
 			P.neg = warp_get(cls, first_lane);
 		}
-		bool done[RT_NL][PPL];
+		unsigned open[RT_NL];
 		float lo[3][RT_NL], hi[3][RT_NL], sx[RT_NL], sy[RT_NL], sz[RT_NL];
 		RT_LANES(l, lane) {
-			(void)lane;
+			open[l] = 0u;
 			lo[0][l] = lo[1][l] = lo[2][l] = INFINITY;
 			hi[0][l] = hi[1][l] = hi[2][l] = 0.0f;
 			sx[l] = sy[l] = sz[l] = 0.0f;
 #pragma unroll
 			for (int j = 0; j < PPL; j++) {
-				const bool in_class = todo[l][j] && neg[l][j] == P.neg;
-				done[l][j] = !in_class;
-				if (in_class) {
-					const RtPRay& q = r[l][j];
-					const float ix = fabsf(1.0f / q.dx), iy = fabsf(1.0f / q.dy), iz = fabsf(1.0f / q.dz);
-					lo[0][l] = fminf(lo[0][l], ix); hi[0][l] = fmaxf(hi[0][l], ix);
-					lo[1][l] = fminf(lo[1][l], iy); hi[1][l] = fmaxf(hi[1][l], iy);
-					lo[2][l] = fminf(lo[2][l], iz); hi[2][l] = fmaxf(hi[2][l], iz);
-					const float k = sqrtf(q.inv_a);  // sum of the unit directions: the cone axis
-					sx[l] += q.dx * k; sy[l] += q.dy * k; sz[l] += q.dz * k;
-				}
+				if (!((todo[l] >> j) & 1u) || (int)((negs[l] >> (3 * j)) & 7u) != P.neg) continue;
+				open[l] |= 1u << j;
+				const RtPRay q = rays[j * 32 + lane];
+				const float ix = fabsf(1.0f / q.dx), iy = fabsf(1.0f / q.dy), iz = fabsf(1.0f / q.dz);
+				lo[0][l] = fminf(lo[0][l], ix); hi[0][l] = fmaxf(hi[0][l], ix);
+				lo[1][l] = fminf(lo[1][l], iy); hi[1][l] = fmaxf(hi[1][l], iy);
+				lo[2][l] = fminf(lo[2][l], iz); hi[2][l] = fmaxf(hi[2][l], iz);
+				const float k = sqrtf(q.inv_a);  // sum of the unit directions: the cone axis
+				sx[l] += q.dx * k; sy[l] += q.dy * k; sz[l] += q.dz * k;
 			}
 		}
 #pragma unroll
@@ -974,34 +1047,34 @@ RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const RtPa
 			P.ax = ax * k; P.ay = ay * k; P.az = az * k;
 			float sn[RT_NL];
 			RT_LANES(l, lane) {
-				(void)lane;
 				sn[l] = 0.0f;
 #pragma unroll
 				for (int j = 0; j < PPL; j++) {
-					if (done[l][j]) continue;
-					const RtPRay& q = r[l][j];
+					if (!((open[l] >> j) & 1u)) continue;
+					const RtPRay q = rays[j * 32 + lane];
 					const float kk = sqrtf(q.inv_a);
 					const float nx = q.dx * kk, ny = q.dy * kk, nz = q.dz * kk;
 					const float t = nx * P.ax + ny * P.ay + nz * P.az;
 					const float px = nx - t * P.ax, py = ny - t * P.ay, pz = nz - t * P.az;
-					sn[l] = fmaxf(sn[l], sqrtf(px * px + py * py + pz * pz));
+					sn[l] = fmaxf(sn[l], px * px + py * py + pz * pz);
 				}
 			}
-			P.sin_h = warp_max_pos(sn) * 1.0001f + 1e-6f;
+			P.sin_h = sqrtf(warp_max_pos(sn)) * 1.0001f + 1e-6f;
 			P.cos2_h = 1.0f - P.sin_h * P.sin_h;
 			P.ox = (float)F.pos[0]; P.oy = (float)F.pos[1]; P.oz = (float)F.pos[2];
 			P.err_l = S.err_l;
 		}
+		unsigned cls_rays[RT_NL];
+		RT_LANES(l, lane) { (void)lane; cls_rays[l] = open[l]; }
 		bool overflow = !(P.sin_h < 0.5f);  // not a narrow packet (tiny frames, huge fov): ray by ray
-		if (!overflow) packet_walk_class<PPL>(S, F, pt, r, P, done, stack, hit_slot, overflow);
+		if (!overflow) packet_walk_class<PPL>(S, F, pt, rays, P, open, stack, hit, overflow);
 		RT_LANES(l, lane) {
 			(void)lane;
+			todo[l] &= ~cls_rays[l];
+			if (overflow) {
 #pragma unroll
-			for (int j = 0; j < PPL; j++) {
-				if (todo[l][j] && neg[l][j] == P.neg) {
-					todo[l][j] = false;
-					if (overflow) { unresolved[l][j] = true; hit_slot[l][j] = -1; }
-				}
+				for (int j = 0; j < PPL; j++)
+					if ((cls_rays[l] >> j) & 1u) hit[l][j] = RT_SLOT_UNKNOWN;
 			}
 		}
 	}
@@ -1577,12 +1650,9 @@ RT_HD bool trace_path(const RtDevScene& S, const RtFrame& F, const double* dir_i
 template <bool COUNT>
 RT_HD void render_pixel(const RtDevScene& S, const RtFrame& F, int x, int y, size_t out_index, RtCounts& cnt,
                         uint32_t& err, int primary_slot = RT_SLOT_UNKNOWN) {
-	// camera direction: get_dir_for_each_pixel (src/view/camera.ts:207-250) through the host-built
-	// tables of the accumulated scan rotations
-	const RtD4 fr = ld(F.row_fr + y);
-	const RtD2 cs = ld(F.col_cs + x);
-	const double dir[3] = {xadd(xmul(fr.x, cs.x), xmul(F.lf[0], cs.y)), xadd(xmul(fr.y, cs.x), xmul(F.lf[1], cs.y)),
-	                       xadd(xmul(fr.z, cs.x), xmul(F.lf[2], cs.y))};
+	// camera direction: get_dir_for_each_pixel (src/view/camera.ts:207-250), from the ray-generation table
+	double dir[3];
+	pixel_dir(F, x, y, dir);
 	const size_t pix = (size_t)y * F.width + x;
 	float* o = F.rgb + out_index * 3;  // frame order, or tile-major when tile-sharded (seed stays per frame pixel)
 	float px[3] = {0.f, 0.f, 0.f};
@@ -1681,52 +1751,165 @@ RT_HD void blend_constant_sample(const RtFrame& F, size_t out_index, const doubl
 	}
 }
 
-// The pixel (x,y) whose camera ray has the first hit `slot`, if its path ends there: blended colour in px and
-// the first-hit entity, nothing stored; false: the bounce stage continues it.
-RT_HD bool primary_finish_px(const RtDevScene& S, const RtFrame& F, int x, int y, int slot, size_t out_index, uint32_t& err,
-                             float* px, int& first_entity) {
-	double dir[3], c[3];
-	pixel_dir(F, x, y, dir);
-	if (!primary_terminal(S, F, dir, slot, c, first_entity, err)) return false;
-	blend_constant_sample(F, out_index, c, px);
-	return true;
+// Appends `n` items to the continuation queue; returns the index of the first one.
+RT_HD unsigned queue_reserve(unsigned* counter, unsigned n) {
+#if defined(__CUDACC__)
+	return atomicAdd(counter, n);
+#else
+	return __atomic_fetch_add(counter, n, __ATOMIC_RELAXED);
+#endif
 }
 
-// ... and stored.
-RT_HD bool primary_finish(const RtDevScene& S, const RtFrame& F, int x, int y, int slot, size_t out_index, uint32_t& err) {
-	float px[3];
-	int first_entity;
-	if (!primary_finish_px(S, F, x, y, slot, out_index, err, px, first_entity)) return false;
-	float* o = F.rgb + out_index * 3;
-	o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
-	if (F.first_ids) F.first_ids[out_index] = first_entity;
-	return true;
-}
-
-// The primary stage for one packet of RT_PPL sub-patches: writes the first-hit slot of every pixel of the
-// packet (or -1: miss; RT_SLOT_UNKNOWN: the ray could not take part in a lock-step walk) to F.hit_slots.
-// The shade stage (primary_finish per pixel) turns the slots into colours or queue entries.
+// The primary stage for one packet of PPL 8x4 sub-patches (rt_primary_kernel; tests/hostsim runs the same code
+// with the lanes as loop iterations): the packet walk finds the first-hit code of every camera ray, then every
+// pixel whose path ENDS at that first hit is shaded right here - the first iteration of Ray.trace
+// (src/raytracer.ts:179-263) -, blended into the ExposureBuffer and stored; the others (mirror bounce,
+// transmission, rays the lock-step walk could not take) go to the continuation queue with one warp-aggregated
+// atomic per sub-patch.  The common endings need no float64 geometry at all: a miss is the sky texture's colour, a
+// hit on a non-light surface with a SolidTexture is that texture's colour (the confirmation already told whether
+// the acute-normal guard of :200-203 fires); lights, image textures and an image sky take primary_terminal().
+// `stage`: 96 floats per warp (device: shared memory) through which the 32 pixels of a sub-patch leave as whole
+// 16-byte words - full sectors, which is what matters when the frame lives in another GPU's or the host's memory.
 template <int PPL>
-RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, RtPNode* stack) {
-	bool skip[RT_NL][PPL], unresolved[RT_NL][PPL];
-	int hit_slot[RT_NL][PPL];
+RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, RtPNode* stack, RtPRay* rays, float* stage,
+                         uint32_t& err_out) {
+	unsigned skip[RT_NL];
+	int hit[RT_NL][PPL];
 	RT_LANES(l, lane) {
+		skip[l] = 0u;
 #pragma unroll
 		for (int j = 0; j < PPL; j++) {
 			const bool valid = patch_x(pt, lane, j) < F.width && patch_y(pt, lane, j) < F.height;
-			skip[l][j] = !valid;
-			unresolved[l][j] = valid;
-			hit_slot[l][j] = -1;
+			if (!valid) skip[l] |= 1u << j;
+			hit[l][j] = valid ? RT_SLOT_UNKNOWN : RT_HIT_NONE;
 		}
 	}
-	if (F.packet_ok) packet_primary_hits<PPL>(S, F, pt, skip, stack, hit_slot, unresolved);
+	if (F.packet_ok) packet_primary_hits<PPL>(S, F, pt, skip, stack, rays, hit);
+	// the hit codes move from registers into the ray table (the rays are not needed any more), so that the loop
+	// over the sub-patches below need not be unrolled
+	int* const codes = reinterpret_cast<int*>(rays);
+	warp_sync();
 	RT_LANES(l, lane) {
 #pragma unroll
-		for (int j = 0; j < PPL; j++) {
-			if (skip[l][j]) continue;
+		for (int j = 0; j < PPL; j++) codes[j * 32 + lane] = hit[l][j];
+	}
+	warp_sync();
+	// ---- the paths that end at their first hit
+	const RtTexture* sky = S.textures + F.sky_texture;
+	const bool sky_simple = !sky->image;
+#pragma unroll 1
+	for (int j = 0; j < PPL; j++) {
+		bool done[RT_NL], enqueue[RT_NL];
+		float px[RT_NL][3];
+		int first_entity[RT_NL];
+		size_t out_index[RT_NL];
+		RT_LANES(l, lane) {
 			const int x = patch_x(pt, lane, j), y = patch_y(pt, lane, j);
-			const size_t out_index = F.tile_compact ? pt.out_base + (size_t)((y & 15) * 16 + (x & 15)) : (size_t)y * F.width + x;
-			F.hit_slots[out_index] = unresolved[l][j] ? RT_SLOT_UNKNOWN : hit_slot[l][j];
+			const bool valid = !((skip[l] >> j) & 1u);
+			out_index[l] = F.tile_compact ? pt.out_base + (size_t)((y & 15) * 16 + (x & 15)) : (size_t)y * F.width + x;
+			done[l] = enqueue[l] = false;
+			first_entity[l] = -1;
+			px[l][0] = px[l][1] = px[l][2] = 0.f;
+			if (!valid) continue;
+			const int code = codes[j * 32 + lane];
+			double c[3];
+			uint32_t err = 0;
+			bool simple = false, full = false;
+			if (code == RT_SLOT_UNKNOWN) {
+				enqueue[l] = true;
+			} else if (code < 0) {  // miss: SkySphere.get_color (src/sky/sky_sphere.ts:22-27) times the colour (1,1,1)
+				if (sky_simple) {
+					c[0] = xmul(1.0, sky->r); c[1] = xmul(1.0, sky->g); c[2] = xmul(1.0, sky->b);
+					simple = true;
+				} else {
+					full = true;
+				}
+			} else {
+				const int slot = code & RT_HIT_SLOT_MASK;
+				const RtI4 attr = ld(S.slot_attr + slot);
+				const RtMaterial m = S.materials[attr.y & RT_ATTR_MAT_MASK];
+				const RtTexture* T = S.textures + attr.z;
+				const uint32_t response = m.flags & RT_MAT_RESPONSE_MASK;
+				const bool bounces = !(m.flags & RT_MAT_LIGHT) && ((response == 0u && (m.flags & RT_MAT_MIRROR)) || response == 1u);
+				if (bounces && F.refmax > 1) {
+					enqueue[l] = true;
+				} else if (code & RT_HIT_ACUTE) {  // :200-203: the path keeps its colour (1,1,1)
+					err |= RT_ERRFLAG_ACUTE;
+					c[0] = c[1] = c[2] = 1.0;
+					first_entity[l] = attr.x;
+					simple = true;
+				} else if ((m.flags & RT_MAT_LIGHT) || T->image) {
+					full = true;
+				} else {  // alter_ray: colour (1,1,1) times the SolidTexture's colour; refmax reached -> black (:256-263)
+					c[0] = xmul(1.0, T->r); c[1] = xmul(1.0, T->g); c[2] = xmul(1.0, T->b);
+					if (bounces) c[0] = c[1] = c[2] = 0.0;
+					first_entity[l] = attr.x;
+					simple = true;
+				}
+			}
+			if (full) {
+				double dir[3];
+				pixel_dir(F, x, y, dir);
+				if (primary_terminal(S, F, dir, code < 0 ? -1 : (code & RT_HIT_SLOT_MASK), c, first_entity[l], err)) simple = true;
+				else enqueue[l] = true;  // (cannot happen; the bounce stage decides)
+			}
+			if (simple) {
+				blend_constant_sample(F, out_index[l], c, px[l]);
+				done[l] = true;
+			}
+			err_out |= err;
 		}
+		// ---- colours: the 32 pixels of the sub-patch are 4 rows of 8 pixels = 4 x 96 contiguous bytes
+#if defined(__CUDACC__)
+		{
+			const int lane = (int)(threadIdx.x & 31u);
+			const int x0 = patch_x(pt, 0, j), y0 = patch_y(pt, 0, j);
+			const bool rows_aligned = F.tile_compact || (F.width & 3) == 0;
+			const bool wide = __ballot_sync(0xffffffffu, done[0]) == 0xffffffffu && rows_aligned &&
+			                  (reinterpret_cast<uintptr_t>(F.rgb) & 15u) == 0;
+			if (wide) {
+				stage[lane * 3] = px[0][0]; stage[lane * 3 + 1] = px[0][1]; stage[lane * 3 + 2] = px[0][2];
+				__syncwarp();
+				if (lane < 24) {
+					const int row = lane / 6, chunk = lane - row * 6;
+					const size_t first = F.tile_compact ? pt.out_base + (size_t)(((y0 + row) & 15) * 16 + (x0 & 15))
+					                                    : (size_t)(y0 + row) * F.width + x0;
+					reinterpret_cast<float4*>(F.rgb + first * 3)[chunk] = reinterpret_cast<const float4*>(stage + row * 24)[chunk];
+				}
+				__syncwarp();
+			} else if (done[0]) {
+				float* o = F.rgb + out_index[0] * 3;
+				o[0] = px[0][0]; o[1] = px[0][1]; o[2] = px[0][2];
+			}
+			if (done[0] && F.first_ids) F.first_ids[out_index[0]] = first_entity[0];
+			const unsigned m = __ballot_sync(0xffffffffu, enqueue[0]);
+			if (m) {
+				unsigned base = 0;
+				if (lane == 0) base = queue_reserve(F.queue_count, (unsigned)__popc(m));
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (enqueue[0]) {
+					const int code = codes[j * 32 + lane];
+					F.queue[base + __popc(m & ((1u << lane) - 1u))] =
+					    RtQueueItem{((uint32_t)patch_y(pt, lane, j) << 16) | (uint32_t)patch_x(pt, lane, j),
+					                code == RT_SLOT_UNKNOWN ? RT_SLOT_UNKNOWN : (code & RT_HIT_SLOT_MASK)};
+				}
+			}
+		}
+#else
+		(void)stage;
+		RT_LANES(l, lane) {
+			if (done[l]) {
+				float* o = F.rgb + out_index[l] * 3;
+				o[0] = px[l][0]; o[1] = px[l][1]; o[2] = px[l][2];
+				if (F.first_ids) F.first_ids[out_index[l]] = first_entity[l];
+			}
+			if (enqueue[l]) {
+				const int code = codes[j * 32 + lane];
+				F.queue[queue_reserve(F.queue_count, 1u)] =
+				    RtQueueItem{((uint32_t)patch_y(pt, lane, j) << 16) | (uint32_t)patch_x(pt, lane, j),
+				                code == RT_SLOT_UNKNOWN ? RT_SLOT_UNKNOWN : (code & RT_HIT_SLOT_MASK)};
+			}
+		}
+#endif
 	}
 }

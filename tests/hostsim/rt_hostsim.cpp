@@ -13,10 +13,36 @@
 #include "../../raytracer.js_b200/csrc/rt_host.h"
 #include "../../raytracer.js_b200/csrc/rt_trace.cuh"
 
+// Camera.get_dir_for_each_pixel through the kernel body's ray generation (raygen_half_row): dirs[h][w][3].
+extern "C" void hostsim_raygen(const rt_camera* cam, double* dirs) {
+	RtFrame F{};
+	std::vector<RtD4> row;
+	rt_build_camera_rows(*cam, row, F.scan_cos, F.scan_sin);
+	for (int i = 0; i < 3; i++) F.lf[i] = cam->lf[i];
+	F.width = (int)cam->width;
+	F.height = (int)cam->height;
+	F.row_fr = row.data();
+	std::vector<RtD4> line(F.width);
+	for (int y = 0; y < F.height; y++) {
+		for (int half = 0; half < 2; half++) raygen_half_row(F, y, half, line.data(), [](int) { return true; });
+		for (int x = 0; x < F.width; x++) {
+			double* o = dirs + ((size_t)y * F.width + x) * 3;
+			o[0] = line[x].x; o[1] = line[x].y; o[2] = line[x].z;
+		}
+	}
+}
+
+// Debugging aid: restrict the ray-by-ray mode (pipeline == 0) to a crop of the frame (w == 0: whole frame).
+static int g_crop[4] = {0, 0, 0, 0};
+extern "C" void hostsim_set_crop(int x, int y, int w, int h) {
+	g_crop[0] = x; g_crop[1] = y; g_crop[2] = w; g_crop[3] = h;
+}
+
 // tile_world <= 1: full frame into rgb[height][width][3].  tile_world > 1: only the tiles of tile_rank,
 // tile-major into rgb[k][16*16][3] (the layout of rt_render_tiles_device).
-// pipeline != 0: the two-stage pipeline of rt_b200.cu (primary_patch per 8x4 patch with the 32 lanes as loop
-// iterations, then the bounce stage over the continuation queue); no work counters in that mode.
+// pipeline != 0: the pipeline of rt_b200.cu (primary_patch per packet with the 32 lanes as loop iterations: packet
+// walk + shading of the paths that end at their first hit; then the bounce stage over the continuation queue); no
+// work counters in that mode.
 // pipeline == 0: every path ray by ray with the counting variant (what rt_render_kernel<true> runs).
 extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, const rt_params* prm, int n_threads,
                               int tile_rank, int tile_world, int pipeline, float* rgb, int32_t* ids,
@@ -31,9 +57,8 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 		snprintf(errbuf, errlen, "%s", err.c_str());
 		return (int)st;
 	}
-	std::vector<RtD2> col;
 	std::vector<RtD4> row;
-	rt_build_camera_tables(*cam, col, row);
+	rt_build_camera_rows(*cam, row, F.scan_cos, F.scan_sin);
 	RtDevScene S{};
 	S.node_geom = hs.node_geom.data(); S.node_link = hs.node_link.data(); S.node_child = hs.node_child.data(); S.node_pk = hs.node_pk.data(); S.node_walk = hs.node_walk.data(); S.node_bvh = hs.node_bvh.data(); S.bvh_nodes = hs.bvh_nodes.data(); S.bvh_slots = hs.bvh_slots.data(); S.bvh_geom = hs.bvh_geom.data();
 	S.slot_geom = hs.slot_geom.data(); S.slot_geom64 = hs.slot_geom64.data(); S.slot_attr = hs.slot_attr.data();
@@ -45,8 +70,12 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 	S.n_slots = (int)hs.slot_geom.size();
 	S.err_l = hs.err_l;
 	S.ordered_ok = rt_ordered_walk_fits(hs);
-	F.col_cs = col.data();
 	F.row_fr = row.data();
+	// ray generation (rt_raygen_kernel's body): the generator's iterated rotations along every row
+	std::vector<RtD4> dirs((size_t)F.width * F.height);
+	for (int y = 0; y < F.height; y++)
+		for (int half = 0; half < 2; half++) raygen_half_row(F, y, half, dirs.data() + (size_t)y * F.width, [](int) { return true; });
+	F.dirs = dirs.data();
 	F.rgb = rgb;
 	F.first_ids = ids;
 	// bit 1 of `pipeline`: a shard (tile_world > 1) writes into a FRAME-layout buffer (rt_render_shard_device)
@@ -67,14 +96,21 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 		// ---- primary stage, patch by patch in the kernel's own patch geometry
 		const int tiles_x = (F.width + 15) / 16, tiles_y = (F.height + 15) / 16, n_tiles = tiles_x * tiles_y;
 		const int my_tiles = (n_tiles - F.tile_rank + F.tile_world - 1) / F.tile_world;
-		std::vector<std::vector<RtQueueItem>> queues(n_threads);
 		std::vector<uint32_t> errs(n_threads, 0);
 		auto out_index_of = [&](int x, int y, int k) {
 			return F.tile_compact ? (size_t)k * 256 + ((y & 15) * 16 + (x & 15)) : (size_t)y * F.width + x;
 		};
 		constexpr int PPL = HOSTSIM_PPL, PER_TILE = 8 / PPL;
+		// the continuation queue of the primary stage (rt_trace.cuh: primary_patch appends with an atomic)
+		std::vector<RtQueueItem> queue(tiled ? (size_t)my_tiles * 256 : (size_t)F.width * F.height);
+		unsigned queue_count = 0;
+		F.queue = queue.data();
+		F.queue_count = &queue_count;
+		// ---- primary stage: packet walk + shading of the paths that end at their first hit
 		auto stage_a = [&](int t) {
 			std::vector<RtPNode> stack(RT_PACKET_STACK);
+			std::vector<RtPRay> rays(PPL * 32);
+			float stage[96];
 			for (int p = t; p < my_tiles * PER_TILE; p += n_threads) {
 				const int k = p / PER_TILE;
 				const int tile = F.tile_rank + k * F.tile_world;
@@ -84,47 +120,25 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 				pt.y0 = (tile / tiles_x) * 16;
 				pt.sub0 = (p % PER_TILE) * PPL;
 				pt.out_base = (size_t)k * 256;
-				primary_patch<PPL>(S, F, pt, stack.data());
+				primary_patch<PPL>(S, F, pt, stack.data(), rays.data(), stage, errs[t]);
 			}
 		};
-		// shade stage: per pixel of this rank, primary_finish or queue
-		auto stage_shade = [&](int t) {
-			for (int k = t; k < my_tiles; k += n_threads) {
-				const int tile = F.tile_rank + k * F.tile_world;
-				if (tile >= n_tiles) continue;
-				for (int in = 0; in < 256; in++) {
-					const int x = (tile % tiles_x) * 16 + (in & 15), y = (tile / tiles_x) * 16 + (in >> 4);
-					if (x >= F.width || y >= F.height) continue;
-					const size_t oi = out_index_of(x, y, k);
-					const int slot = F.hit_slots[oi];
-					if (slot == RT_SLOT_UNKNOWN || !primary_finish(S, F, x, y, slot, oi, errs[t]))
-						queues[t].push_back(RtQueueItem{((uint32_t)y << 16) | (uint32_t)x, slot});
-				}
-			}
-		};
-		std::vector<int> hit_slots(tiled ? (size_t)my_tiles * 256 : (size_t)F.width * F.height, -1);
-		F.hit_slots = hit_slots.data();
 		std::vector<std::thread> th;
 		for (int t = 0; t < n_threads; t++) th.emplace_back(stage_a, t);
 		for (auto& t : th) t.join();
 		th.clear();
-		for (int t = 0; t < n_threads; t++) th.emplace_back(stage_shade, t);
-		for (auto& t : th) t.join();
-		th.clear();
 		// ---- bounce stage over the continuation queue
-		uint64_t queued = 0;
+		const uint64_t queued = queue_count;
 		auto stage_b = [&](int t) {
-			for (const RtQueueItem& it : queues[t]) {
+			for (size_t i = t; i < queued; i += n_threads) {
+				const RtQueueItem& it = queue[i];
 				const int x = (int)(it.xy & 0xffffu), y = (int)(it.xy >> 16);
 				const int tile = (y / 16) * tiles_x + (x / 16);
 				RtCounts c = {0, 0, 0, 0, 0};
 				render_pixel<false>(S, F, x, y, out_index_of(x, y, tile / F.tile_world), c, errs[t], it.slot);
 			}
 		};
-		for (int t = 0; t < n_threads; t++) {
-			queued += queues[t].size();
-			th.emplace_back(stage_b, t);
-		}
+		for (int t = 0; t < n_threads; t++) th.emplace_back(stage_b, t);
 		for (auto& t : th) t.join();
 		if (counters) {
 			memset(counters, 0, sizeof *counters);
@@ -145,6 +159,7 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 			for (int x = 0; x < F.width; x++) {
 				RtCounts c = {0, 0, 0, 0, 0};
 				size_t out_index = (size_t)y * F.width + x;
+				if (g_crop[2] > 0 && (x < g_crop[0] || x >= g_crop[0] + g_crop[2] || y < g_crop[1] || y >= g_crop[1] + g_crop[3])) continue;
 				if (F.tile_world > 1) {  // same mapping as rt_render_kernel
 					const int tiles_x = (F.width + 15) / 16;
 					const int tile = (y / 16) * tiles_x + (x / 16);

@@ -59,6 +59,34 @@ def oracle_for(tracer, bundle, width, height, n_frames=1, pos=scenes.BENCH_CAMER
                          want_counters=want_counters)
 
 
+@pytest.mark.parametrize("W,H,pos,yaw,pitch", [
+    (96, 96, scenes.BENCH_CAMERA_POS, 30.0, 0.0),
+    (257, 131, (0.2, 0.7, 0.4), -75.0, 0.4),
+    (1080, 1080, scenes.BENCH_CAMERA_POS, 30.0, 0.0),
+    (1920, 1080, scenes.BENCH_CAMERA_POS, 30.0, 0.0),
+    (7680, 64, scenes.DEMO_CAMERA_POS, 30.0, 0.0),  # rows of an 8K frame: 3840 iterated rotations per half row
+])
+def test_ray_generation_bit_for_bit(oracle, W, H, pos, yaw, pitch):
+    """Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250) on the device (rt_raygen_kernel through
+    rt_camera_directions): every direction equals the oracle's generator's, bit for bit."""
+    cam = scenes.bench_camera(W, H, pos, yaw, pitch)
+    ocam = ocam_for(W, H, pos, yaw, pitch)
+    fixed = W != H
+    xy, d, n = ocam.dirs(fixed_extents=fixed)
+    assert n == W * H
+    want = np.zeros((H, W, 3))
+    want[xy[:, 1], xy[:, 0]] = d
+    lib = N.load()
+    ctx = C.c_void_p()
+    N.check(None, lib.rt_create(-1, C.byref(ctx)))
+    got = np.zeros((H, W, 3))
+    cd = rt.camera_desc(cam, reference_extents=not fixed)
+    N.check(ctx, lib.rt_camera_directions(ctx, C.byref(cd), got.ctypes.data))
+    assert lib.rt_launch_count(ctx) == 1
+    lib.rt_destroy(ctx)
+    np.testing.assert_array_equal(got, want)
+
+
 def test_config1_diffuse_spheres_square(oracle):
     """BASELINE config 1 scene (10 k spheres, diffuse + sky, refmax 1) on a 1080 x 1080 frame."""
     b = scenes.random_spheres(10000, 0.002, 0.006, seed=42.0, mix="diffuse")

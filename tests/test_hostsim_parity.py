@@ -39,16 +39,36 @@ def run_both(bundle, width, height, n_frames=1, frame_first=0, pos=scenes.BENCH_
     return compare(rgb, ids, orgb, oids), cnt, tot, (rgb, ids, orgb, oids)
 
 
-def test_camera_tables_match_generator():
-    """The closed scan tables (rt_host.h: rt_build_camera_tables) against the iterated generator."""
-    W = H = 64
-    cam, ocam = cameras(W, H)
-    xy, d, n = ocam.dirs(fixed_extents=False)
+@pytest.mark.parametrize("W,H,pos,yaw,pitch", [
+    (64, 64, scenes.BENCH_CAMERA_POS, 30.0, 0.0),
+    (257, 131, (0.2, 0.7, 0.4), -75.0, 0.4),       # non-square, odd sizes (intent mapping)
+    (1080, 1080, scenes.BENCH_CAMERA_POS, 30.0, 0.0),
+    (3840, 16, scenes.DEMO_CAMERA_POS, 30.0, 0.0),  # rows as long as a 4K frame's: 1920 iterated rotations per half row
+])
+def test_ray_generation_is_the_generator_bit_for_bit(oracle, W, H, pos, yaw, pitch):
+    """Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250): the kernel body's ray generation (row table on
+    the host, iterated scan along the rows: rt_host.h rt_build_camera_rows + rt_trace.cuh raygen_half_row) must
+    give the oracle's generator's direction for every pixel, every bit: floating-point rotations iterated along a
+    row have no closed form with the same bits, and a last-bit difference in a camera direction is a different
+    path after three bounces off millimetre spheres (tests/test_gpu_full_size.py, configs[4])."""
+    import ctypes as C
+    from util import hostsim
+    cam, ocam = cameras(W, H, pos, yaw, pitch)
+    fixed = W != H
+    xy, d, n = ocam.dirs(fixed_extents=fixed)
     assert n == W * H
-    # host generator of the product's Camera yields the same sequence as the oracle's
-    mine = list(cam.get_dir_for_each_pixel())
-    assert [(x, y) for x, y, _ in mine] == [tuple(p) for p in xy.tolist()]
-    np.testing.assert_array_equal(np.array([v.v for _, _, v in mine]), d)
+    want = np.zeros((H, W, 3))
+    want[xy[:, 1], xy[:, 0]] = d
+    cd = rt.camera_desc(cam, reference_extents=not fixed)
+    got = np.zeros((H, W, 3))
+    L = hostsim()
+    L.hostsim_raygen.restype = None
+    L.hostsim_raygen(C.byref(cd), got.ctypes.data_as(C.c_void_p))
+    np.testing.assert_array_equal(got, want)
+    if W == 64:  # the host mirror's generator yields the same sequence too
+        mine = list(cam.get_dir_for_each_pixel())
+        assert [(x, y) for x, y, _ in mine] == [tuple(p) for p in xy.tolist()]
+        np.testing.assert_array_equal(np.array([v.v for _, _, v in mine]), d)
 
 
 def test_diffuse_spheres_primary(oracle):

@@ -51,10 +51,15 @@ for name in ("primary", "c2_primary", "c2_bounce", "c2_resample"):
     reg = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), rep], capture_output=True, text=True).stdout
     open(os.path.join(P, f"{tag}_regions_{name}.txt"), "w").write(f"# {d['kernel']}\n# ncu --set full --import-source on, aggregated per function by tools/ncu_regions.py\n" + reg)
 # bench.py quotes these numbers only while the kernel sources are the ones they were captured from
-sys.path.insert(0, ROOT)
-import bench
-summary["fingerprint"] = bench.source_fingerprint()
-summary["fingerprint_of"] = "sha256[:16] over raytracer.js_b200/csrc/* + include/rt_b200.h (bench.source_fingerprint)"
+# (the fingerprint the profiled run itself printed: the working tree may have moved on since the GPU call)
+fp = None
+try:
+    lines = [l for l in open(os.path.join(G, f"{tag}_bench.log")).read().splitlines() if l.startswith("{")]
+    fp = json.loads(lines[-1])["roofline"]["source_fingerprint"]
+except Exception:
+    pass
+summary["fingerprint"] = fp
+summary["fingerprint_of"] = "sha256[:16] over raytracer.js_b200/csrc/* + include/rt_b200.h (bench.source_fingerprint), as printed by the profiled run"
 json.dump(summary, open(os.path.join(P, f"{tag}_summary.json"), "w"), indent=1)
 
 for f in (f"{tag}_launches.csv", f"{tag}_c2_launches.csv"):
