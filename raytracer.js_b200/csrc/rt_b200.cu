@@ -583,6 +583,8 @@ struct rt_ctx {
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	cudaStream_t copy_stream = nullptr;          // device->host band copies of rt_render
+	cudaStream_t aux_stream = nullptr;           // the origin-relative records are prepared beside the ray generation
+	cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 	cudaEvent_t band_done[16] = {};              // band b rendered (RT_MAX_BANDS)
 	cudaEvent_t stage_free = nullptr;            // camera-table staging may be rewritten
 	void* stage = nullptr;                       // pinned staging of the camera scan tables
@@ -846,18 +848,23 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 			return prof ? cudaEventRecord(ctx->stage_ev[stage], ctx->stream) : cudaSuccess;
 		};
 		RT_CUDA(ctx, mark(0));
-		if (!capture) {  // ray generation: the generator's iterated rotations, every pixel's direction (2 x height threads)
+		if (!capture) {
+			// ray generation (the generator's iterated rotations: 2 x height threads, latency bound) on the ctx stream,
+			// and beside it, on the auxiliary stream, the origin-relative records of this camera position
+			if (prim) {
+				RT_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+				RT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
+				rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->aux_stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
+				                                                                             cam->pos[2], ctx->prim_geom.p);
+				ctx->launches++;
+				RT_CUDA(ctx, cudaGetLastError());
+				RT_CUDA(ctx, cudaEventRecord(ctx->join_ev, ctx->aux_stream));
+			}
 			rt_raygen_kernel<<<(2 * F.height + 31) / 32, 32, 0, ctx->stream>>>(F, ctx->dirs.p, tiles_x);
 			ctx->launches++;
 			ctx->stage_ran[0] = prof;
 			RT_CUDA(ctx, cudaGetLastError());
-		}
-		if (prim && !capture) {
-			rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
-			                                                                         cam->pos[2], ctx->prim_geom.p);
-			ctx->launches++;
-			ctx->stage_ran[0] = prof;
-			RT_CUDA(ctx, cudaGetLastError());
+			if (prim) RT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
 		}
 		RT_CUDA(ctx, mark(1));
 		for (int band = 0; band < n_bands; band++) {
@@ -988,6 +995,9 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	ctx->device = device;
 	e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->stage_free, cudaEventDisableTiming);
@@ -1041,6 +1051,9 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->peer_flags.release();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+	if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+	if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+	if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
 	for (int b = 0; b < RT_MAX_BANDS; b++)
 		if (ctx->band_done[b]) cudaEventDestroy(ctx->band_done[b]);
 	for (int k = 0; k <= RT_N_STAGES; k++)

@@ -791,18 +791,17 @@ RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own
 	const RtD4 r = ld(F.row_fr + y);
 	double fr[3] = {r.x, r.y, r.z}, lf[3] = {F.lf[0], F.lf[1], F.lf[2]};
 	const int x0 = F.width >> 1;
-	if (half == 0) {
-		for (int x = x0; x < F.width; x++) {
-			if (own(x)) out[x] = RtD4{fr[0], fr[1], fr[2], 0.0};
-			rotate_pair(fr, lf, F.scan_cos, F.scan_sin);
-		}
-	} else {
-		for (int x = x0 - 1; x >= 0; x--) {
-			rotate_pair(fr, lf, F.scan_cos, -F.scan_sin);
-			if (own(x)) out[x] = RtD4{fr[0], fr[1], fr[2], 0.0};
-		}
+	// one loop shape for both halves (the two lanes of a row run it in lock-step): the left half has rotated once
+	// before its first yield, both rotate after every yield (the rotation after the last one is unused)
+	const double s = half ? -F.scan_sin : F.scan_sin;
+	const int n = half ? x0 : F.width - x0, first = half ? x0 - 1 : x0, step = half ? -1 : 1;
+	if (half) rotate_pair(fr, lf, F.scan_cos, s);
+	for (int i = 0, x = first; i < n; i++, x += step) {
+		if (own(x)) out[x] = RtD4{fr[0], fr[1], fr[2], 0.0};
+		rotate_pair(fr, lf, F.scan_cos, s);
 	}
 }
+
 // pixels outside the frame ride along with the direction of the nearest pixel inside it
 RT_HD void pixel_dir_clamped(const RtFrame& F, int x, int y, double* dir) {
 	pixel_dir(F, x < F.width ? x : F.width - 1, y < F.height ? y : F.height - 1, dir);
