@@ -136,14 +136,19 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
 // exposure frames) and is in one of four states:
 //   IDLE   no job: refilled from the continuation queue (one atomic per refill, ranks by popc of the vote);
 //   BEGIN  a ray segment starts: walker re-seed (segment_begin);
-//   WALK   the ordered walk, run by the whole warp in lock-step (walk_iter: every lane does one node step
-//          and/or one list-BVH step per iteration, phases re-converged);
+//   WALK   the ordered walk, run by the whole warp in lock-step (walk_step: per iteration the warp takes ONE kind
+//          of step - octree node, BVH pair or BVH leaf -, the one most lanes wait for);
 //   END    the search is over: collision + the material's response (segment_end), which starts the next
 //          segment (BEGIN), the next exposure frame, or ends the job (IDLE).
 // The warp leaves the walk loop as soon as a quarter of the lanes that entered it have finished (or fewer
 // than F.bounce_min_walking are left), so that a path that bounces four times or crosses a long list does
 // not hold finished lanes hostage: those shade, start their next segment or fetch a new pixel, and re-join.
 // Frames whose path never drew from the RNG reuse the first frame's sample.
+// Entries of a lane's walk stack in shared memory (interleaved: entry i of thread t at [i * 128 + t]), sized so that
+// MINB CTAs of 128 threads fit one SM's 227 KB.  Octree entries: at most 3 pending siblings per level are usual (a
+// line pierces at most 4 octants of a cube), plus the list BVH's depth; a ray that needs more is searched by the
+// reference-order walker instead (RtWalk.overflow).
+#define RT_WALK_SCAP(minb) ((minb) >= 8 ? 48 : (minb) >= 6 ? 64 : (minb) >= 5 ? 80 : 96)
 #define RT_ST_IDLE 0
 #define RT_ST_BEGIN 1
 #define RT_ST_WALK 2
@@ -151,6 +156,8 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
 template <int MINB>
 __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
     rt_bounce_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
+	__shared__ unsigned stacks[RT_WALK_SCAP(MINB) * RT_WARPS_PER_CTA * 32];
+	const RtWalkStack K = {stacks + threadIdx.x, RT_WARPS_PER_CTA * 32, RT_WALK_SCAP(MINB)};
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const unsigned n = *F.queue_count;
@@ -233,13 +240,14 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			double c[3];
 			int hit = -1;
 			RtCollision ci;
-			const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
+			const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, &K, hit, ci);
 			if (r == RT_SEG_DONE) {
 				sample_done(c);
 			} else if (r == RT_SEG_WALK) {
 				st = RT_ST_WALK;
 			} else {
 				W.hit = hit;  // known from the primary stage (or searched by the fallback walker)
+				W.overflow = 0;
 				st = RT_ST_END;
 			}
 		}
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			if (nw > 0) {
 				const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
 				do {
-					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
+					walking = walk_step<true>(S, W, K, P.refpoint, P.dir, walking);
 					nw = __popc(__ballot_sync(0xffffffffu, walking));
 				} while (nw >= limit);
 				if (st == RT_ST_WALK && !walking) st = RT_ST_END;
@@ -263,9 +271,9 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			const double seed = xadd(xadd(F.rng_seed, (double)((size_t)y * F.width + x)),
 			                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
 			double c[3];
-			int hit = W.hit;
+			int hit;
 			RtCollision ci;
-			if (hit >= 0 && !confirm_slot(S, hit, P.refpoint, P.dir, ci)) hit = -1;  // (same formula as in the search: cannot fail)
+			segment_found(S, P, W, hit, ci);
 			if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
 			else st = RT_ST_BEGIN;
 		}
@@ -287,6 +295,8 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 template <int MINB>
 __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
     rt_resample_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
+	__shared__ unsigned stacks[RT_WALK_SCAP(MINB) * RT_WARPS_PER_CTA * 32];
+	const RtWalkStack K = {stacks + threadIdx.x, RT_WARPS_PER_CTA * 32, RT_WALK_SCAP(MINB)};
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const unsigned n = *F.vqueue_count;
@@ -350,13 +360,14 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 				double c[3];
 				int hit = -1;
 				RtCollision ci;
-				const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
+				const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, &K, hit, ci);
 				if (r == RT_SEG_DONE) {
 					sample_done(c);
 				} else if (r == RT_SEG_WALK) {
 					st = RT_ST_WALK;
 				} else {
 					W.hit = hit;
+					W.overflow = 0;
 					st = RT_ST_END;
 				}
 			}
@@ -368,7 +379,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 				if (nw > 0) {
 					const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
 					do {
-						walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
+						walking = walk_step<true>(S, W, K, P.refpoint, P.dir, walking);
 						nw = __popc(__ballot_sync(0xffffffffu, walking));
 					} while (nw >= limit);
 					if (st == RT_ST_WALK && !walking) st = RT_ST_END;
@@ -380,9 +391,9 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 				const double seed = xadd(xadd(F.rng_seed, (double)((size_t)y * F.width + x)),
 				                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
 				double c[3];
-				int hit = W.hit;
+				int hit;
 				RtCollision ci;
-				if (hit >= 0 && !confirm_slot(S, hit, P.refpoint, P.dir, ci)) hit = -1;  // (same formula as in the search: cannot fail)
+				segment_found(S, P, W, hit, ci);
 				if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
 				else st = RT_ST_BEGIN;
 			}

@@ -380,3 +380,33 @@ def test_published_entity_counts_small_frames(oracle):
     res = compare(rgb, ids, orgb, oids)
     assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0, res
     assert tot["segments"] > 1.2 * tot["paths"]
+
+
+def test_walk_stack_overflow_falls_back_to_the_reference_order_walker(oracle, tmp_path):
+    """A ray whose ordered walk needs more stack than it has (RtWalk.overflow) is searched again by the
+    reference-order walker: same pixels.  The kernel body is built here with a 6-entry stack, so that most
+    secondary rays of a mirror scene overflow."""
+    import ctypes as C
+    import subprocess
+    import util
+    from raytracer_js_b200 import _native as N
+    lib = tmp_path / "librt_hostsim_cap6.so"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-pthread", "-shared", "-DRT_TEST_WALK_CAP=6",
+                           "-Wno-unknown-pragmas", "-Wno-comment", "-o", str(lib), util.os.path.join(util.HOSTSIM_DIR, "rt_hostsim.cpp")])
+    L = C.CDLL(str(lib))
+    L.hostsim_render.restype = C.c_int
+    b = scenes.random_spheres(3000, 0.01, 0.05, seed=8.0, mix="mirrors", box_fraction=0.1)
+    flat = flat_of(b)
+    cam, ocam = cameras(96, 96)
+    prm = make_params(flat, b, n_frames=2)
+    rgb = np.zeros((96, 96, 3), np.float32)
+    ids = np.full((96, 96), -1, np.int32)
+    cnt = N.Counters()
+    err = C.create_string_buffer(512)
+    d, cd = flat.desc(), rt.camera_desc(cam)
+    assert L.hostsim_render(C.byref(d), C.byref(cd), C.byref(prm), 8, 0, 1, 1, C.c_void_p(rgb.ctypes.data), C.c_void_p(ids.ctypes.data),
+                            C.byref(cnt), err, 512) == 0, err.value
+    orgb, oids, _, tot = oracle_render(oracle_scene(flat, b), ocam, flat, b, prm, fixed_extents=True)
+    res = compare(rgb, insertion_ids(flat, b, ids), orgb, oids)
+    assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0, res
+    assert tot["segments"] > 1.3 * tot["paths"]
