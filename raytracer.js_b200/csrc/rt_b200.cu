@@ -105,6 +105,29 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 #ifndef RT_A_MINB
 #define RT_A_MINB 5
 #endif
+// Ray generation rides along in the same launch: the first F.raygen_jobs tickets of the dispenser are groups of 32
+// half rows (rt_trace.cuh: raygen_half_row, the generator's iterated rotations - FP64-issue bound, ~30 us at 1080p
+// for 68 warps of the ~3000 resident ones), which publish their progress every 16 columns with release stores; the
+// packets are handed out column by column from the MIDDLE tile column outwards, the order in which the rows grow, so
+// a packet's directions are in the table long before its ticket comes up (the wait below is a formality except for
+// the first few packets).  All CTAs of the persistent grid are resident, and the ray-generation tickets are taken
+// before any packet ticket: no packet can wait for a job that is not already running.
+RT_D void wait_for_rows(const RtFrame& F, int x_lo, int x_hi, int y_lo, int n_rows) {
+	const int lane = threadIdx.x & 31;
+	const int r = lane & 15, half = lane >> 4, y = y_lo + r, xc = F.width >> 1;
+	x_hi = min(x_hi, F.width - 1);
+	int need = 0;
+	if (r < n_rows && y < F.height) need = half ? (x_lo < xc ? xc - x_lo : 0) : (x_hi >= xc ? x_hi - xc + 1 : 0);
+	if (need > 0) {
+		const unsigned* flag = F.raygen_progress + 2 * y + half;
+		unsigned v;
+		do {
+			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+		} while (v < (unsigned)need);
+	}
+	__syncwarp();
+}
+
 template <int PPL, int MINB>
 __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
     rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_packets) {
@@ -113,37 +136,48 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
 	__shared__ __align__(16) float stages[RT_A_WARPS][96];
 	constexpr int PER_TILE = 8 / PPL;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int band_row0 = F.tile_begin / tiles_x, band_rows = (F.tile_end - F.tile_begin) / tiles_x;
+	const unsigned n_jobs = (unsigned)F.raygen_jobs;
 	uint32_t err = 0;
 	while (true) {
 		unsigned p = 0;
 		if (lane == 0) p = atomicAdd(F.work_counter, 1u);
 		p = __shfl_sync(0xffffffffu, p, 0);
-		if (p >= (unsigned)n_packets) break;
-		const int k = (int)(p / PER_TILE);
-		const int tile = F.tile_begin + F.tile_rank + k * F.tile_world;
-		if (tile >= F.tile_end) continue;
+		if (p >= n_jobs + (unsigned)n_packets) break;
+		if (p < n_jobs) {  // ---- ray generation for the half rows 32 p ... 32 p + 31
+			const int t = (int)p * 32 + lane;
+			if (t < 2 * F.height) {
+				const int y = t >> 1, half = t & 1;
+				unsigned* flag = F.raygen_progress + t;
+				RtD4* out = const_cast<RtD4*>(F.dirs) + (size_t)y * F.width;
+				const int row_tile = (y / RT_TILE_H) * tiles_x;
+				auto publish = [&](int n) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"((unsigned)n) : "memory"); };
+				if (F.tile_world > 1)
+					raygen_half_row(F, y, half, out, [&](int x) { return (row_tile + x / RT_TILE_W) % F.tile_world == F.tile_rank; }, publish);
+				else
+					raygen_half_row(F, y, half, out, [](int) { return true; }, publish);
+			}
+			__syncwarp();
+			continue;
+		}
+		// ---- a packet: tiles of the band column by column, from the middle column outwards
+		p -= n_jobs;
+		const int ka = (int)(p / PER_TILE);
+		const int c = ka / band_rows, ty = band_row0 + (ka - c * band_rows);
+		const int tx = (c & 1) ? (tiles_x >> 1) - ((c + 1) >> 1) : (tiles_x >> 1) + (c >> 1);
+		const int tile = ty * tiles_x + tx;
+		if (tile % F.tile_world != F.tile_rank) continue;
 		RtPatch pt;
-		pt.x0 = (tile % tiles_x) * RT_TILE_W;
-		pt.y0 = (tile / tiles_x) * RT_TILE_H;
+		pt.x0 = tx * RT_TILE_W;
+		pt.y0 = ty * RT_TILE_H;
 		pt.sub0 = (int)(p % PER_TILE) * PPL;
-		pt.out_base = (size_t)k * RT_BLOCK;
+		pt.out_base = (size_t)(tile / F.tile_world) * RT_BLOCK;
+		if (F.raygen_progress) wait_for_rows(F, pt.x0, pt.x0 + RT_TILE_W - 1, pt.y0 + (pt.sub0 >> 1) * 4, PPL * 2);
 		primary_patch<PPL>(S, F, pt, stacks[warp], rays[warp], stages[warp], err);
 	}
 	if (err) atomicOr(F.error_flags, err);
 }
 
-// Bounce stage: persistent wavefront with a per-warp ray queue.  Every lane owns one pixel job (all its
-// exposure frames) and is in one of four states:
-//   IDLE   no job: refilled from the continuation queue (one atomic per refill, ranks by popc of the vote);
-//   BEGIN  a ray segment starts: walker re-seed (segment_begin);
-//   WALK   the ordered walk, run by the whole warp in lock-step (walk_step: per iteration the warp takes ONE kind
-//          of step - octree node, BVH pair or BVH leaf -, the one most lanes wait for);
-//   END    the search is over: collision + the material's response (segment_end), which starts the next
-//          segment (BEGIN), the next exposure frame, or ends the job (IDLE).
-// The warp leaves the walk loop as soon as a quarter of the lanes that entered it have finished (or fewer
-// than F.bounce_min_walking are left), so that a path that bounces four times or crosses a long list does
-// not hold finished lanes hostage: those shade, start their next segment or fetch a new pixel, and re-join.
-// Frames whose path never drew from the RNG reuse the first frame's sample.
 // Entries of a lane's walk stack in shared memory (interleaved: entry i of thread t at [i * 128 + t]), sized so that
 // MINB CTAs of 128 threads fit one SM's 227 KB.  Octree entries: at most 3 pending siblings per level are usual (a
 // line pierces at most 4 octants of a cube), plus the list BVH's depth; a ray that needs more is searched by the
@@ -594,8 +628,6 @@ struct rt_ctx {
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	cudaStream_t copy_stream = nullptr;          // device->host band copies of rt_render
-	cudaStream_t aux_stream = nullptr;           // the origin-relative records are prepared beside the ray generation
-	cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 	cudaEvent_t band_done[16] = {};              // band b rendered (RT_MAX_BANDS)
 	cudaEvent_t stage_free = nullptr;            // camera-table staging may be rewritten
 	void* stage = nullptr;                       // pinned staging of the camera scan tables
@@ -656,6 +688,7 @@ struct rt_ctx {
 	int primary_minb = RT_A_MINB;                // tuning knob RT_B200_PRIMARY_MINB=4|5|6: resident CTAs per SM the primary stage is compiled for
 	int bounce_min_walking = 12;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
 	int resample_min_frames = 8;                 // tuning knob RT_B200_RESAMPLE_MIN
+	bool fuse_raygen = true;                     // tuning knob RT_B200_FUSE_RAYGEN=0: ray generation as a kernel of its own
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
 	int bounce_minb = 8;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
 	int bounce_node_batch = 4;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
@@ -772,7 +805,9 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	// u64 cells: [0..7] work counters, [8] error flags, then per band {patch dispenser, queue count, queue cursor,
 	// resample queue count, resample queue cursor}
 	n_bands = std::max(1, std::min(n_bands, RT_MAX_BANDS));
-	const size_t n_cells = 9 + 5 * RT_MAX_BANDS;
+	// ... then the ray-generation progress flags, 2 x height x u32
+	const size_t n_ctl_cells = 9 + 5 * RT_MAX_BANDS;
+	const size_t n_cells = n_ctl_cells + (size_t)cam->height;
 	RT_CUDA(ctx, ctx->counters.alloc(n_cells));
 	F.counters = ctx->counters.p;
 	F.error_flags = reinterpret_cast<uint32_t*>(ctx->counters.p + 8);
@@ -859,23 +894,26 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 			return prof ? cudaEventRecord(ctx->stage_ev[stage], ctx->stream) : cudaSuccess;
 		};
 		RT_CUDA(ctx, mark(0));
+		// Per camera pose (a captured frame repeats the call before it and inherits both): the origin-relative records,
+		// a small kernel of its own, and the ray generation - inside the primary stage's launch when there is one
+		// (rt_primary_kernel: the first tickets of its dispenser), else as a kernel of its own.
+		bool raygen_fused = false;
 		if (!capture) {
-			// ray generation (the generator's iterated rotations: 2 x height threads, latency bound) on the ctx stream,
-			// and beside it, on the auxiliary stream, the origin-relative records of this camera position
 			if (prim) {
-				RT_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-				RT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
-				rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->aux_stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
-				                                                                             cam->pos[2], ctx->prim_geom.p);
+				rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
+				                                                                         cam->pos[2], ctx->prim_geom.p);
 				ctx->launches++;
+				ctx->stage_ran[0] = prof;
 				RT_CUDA(ctx, cudaGetLastError());
-				RT_CUDA(ctx, cudaEventRecord(ctx->join_ev, ctx->aux_stream));
 			}
-			rt_raygen_kernel<<<(2 * F.height + 31) / 32, 32, 0, ctx->stream>>>(F, ctx->dirs.p, tiles_x);
-			ctx->launches++;
-			ctx->stage_ran[0] = prof;
-			RT_CUDA(ctx, cudaGetLastError());
-			if (prim) RT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
+			if (pipeline && ctx->fuse_raygen) {
+				raygen_fused = true;
+			} else {
+				rt_raygen_kernel<<<(2 * F.height + 31) / 32, 32, 0, ctx->stream>>>(F, ctx->dirs.p, tiles_x);
+				ctx->launches++;
+				ctx->stage_ran[0] = prof;
+				RT_CUDA(ctx, cudaGetLastError());
+			}
 		}
 		RT_CUDA(ctx, mark(1));
 		for (int band = 0; band < n_bands; band++) {
@@ -899,8 +937,11 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				// primary stage (packet walk) -> shade stage -> bounce stage over the continuation queue
 				F.queue = ctx->queue.p + F.out_first;
 				F.vqueue = resample ? ctx->vqueue.p + F.out_first : nullptr;
-				const int n_packets = my_tiles * (8 / ppl);
-				const int blocks = std::min(grid_primary, (n_packets + RT_A_WARPS - 1) / RT_A_WARPS);
+				// the dispenser walks ALL tiles of the band (middle column outwards); a rank skips the tiles of the others
+				const int n_packets = band_tiles * (8 / ppl);
+				F.raygen_jobs = raygen_fused && band == 0 ? (2 * F.height + 31) / 32 : 0;
+				F.raygen_progress = raygen_fused && band == 0 ? reinterpret_cast<unsigned*>(ctx->counters.p + n_ctl_cells) : nullptr;
+				const int blocks = std::min(grid_primary, (my_tiles * (8 / ppl) + F.raygen_jobs + RT_A_WARPS - 1) / RT_A_WARPS);
 				void* args[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x, (void*)&n_packets};
 				RT_CUDA(ctx, cudaLaunchKernel(primary_kernel, dim3(blocks), dim3(RT_A_WARPS * 32), args, 0, ctx->stream));
 				ctx->launches++;
@@ -1006,9 +1047,6 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	ctx->device = device;
 	e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->stage_free, cudaEventDisableTiming);
@@ -1030,6 +1068,7 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 		if (v >= 1 && v <= 32) ctx->bounce_min_walking = v;
 	}
 	if (const char* e = getenv("RT_B200_RESAMPLE")) ctx->resample = atoi(e) != 0;
+	if (const char* e = getenv("RT_B200_FUSE_RAYGEN")) ctx->fuse_raygen = atoi(e) != 0;
 	if (const char* e = getenv("RT_B200_RESAMPLE_MIN")) ctx->resample_min_frames = std::max(2, atoi(e));
 	if (const char* e = getenv("RT_B200_BOUNCE_MINB")) {
 		const int v = atoi(e);
@@ -1062,9 +1101,6 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->peer_flags.release();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
-	if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
-	if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
-	if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
 	for (int b = 0; b < RT_MAX_BANDS; b++)
 		if (ctx->band_done[b]) cudaEventDestroy(ctx->band_done[b]);
 	for (int k = 0; k <= RT_N_STAGES; k++)

@@ -765,9 +765,17 @@ RT_HD int patch_y(const RtPatch& pt, int lane, int j) { return pt.y0 + (((pt.sub
 
 // Camera direction of pixel (x,y): get_dir_for_each_pixel (src/view/camera.ts:207-250), from the per-frame table
 // the ray-generation pass (raygen_half_row) filled with the generator's own iterated rotations.
+// (read through L2 only: the primary stage reads rows that warps of the SAME launch are still producing, and the
+// table is read once or twice per pixel anyway)
 RT_HD void pixel_dir(const RtFrame& F, int x, int y, double* dir) {
-	const RtD4 v = ld(F.dirs + ((size_t)y * F.width + x));
-	dir[0] = v.x; dir[1] = v.y; dir[2] = v.z;
+	const RtD4* p = F.dirs + ((size_t)y * F.width + x);
+#if defined(__CUDACC__)
+	const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+	const double b = __ldcg(reinterpret_cast<const double*>(p) + 2);
+	dir[0] = a.x; dir[1] = a.y; dir[2] = b;
+#else
+	dir[0] = p->x; dir[1] = p->y; dir[2] = p->z;
+#endif
 }
 
 // rotate_vectors (src/math/vector.ts:318-323): (a, b) <- (a*c + b*s, a*-s + b*c), every product and sum rounded
@@ -786,8 +794,9 @@ RT_HD void rotate_pair(double* a, double* b, double c, double s) {
 // (half == 0) yields x = width>>1, ... , width-1 rotating AFTER every yield by rot_scan_h_v, the left half
 // (half == 1) rotates by the counter-clockwise rotation FIRST and yields x = (width>>1)-1, ..., 0.
 // own(x): whether this rank stores pixel x of the row (tile sharding); `out` is the row of the table.
-template <class Own>
-RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own) {
+// publish(n): the first n columns of this half row are in the table (called every 16 columns and at the end).
+template <class Own, class Publish>
+RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own, Publish publish) {
 	const RtD4 r = ld(F.row_fr + y);
 	double fr[3] = {r.x, r.y, r.z}, lf[3] = {F.lf[0], F.lf[1], F.lf[2]};
 	const int x0 = F.width >> 1;
@@ -798,8 +807,13 @@ RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own
 	if (half) rotate_pair(fr, lf, F.scan_cos, s);
 	for (int i = 0, x = first; i < n; i++, x += step) {
 		if (own(x)) out[x] = RtD4{fr[0], fr[1], fr[2], 0.0};
+		if (((i + 1) & 15) == 0 || i + 1 == n) publish(i + 1);
 		rotate_pair(fr, lf, F.scan_cos, s);
 	}
+}
+template <class Own>
+RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own) {
+	raygen_half_row(F, y, half, out, own, [](int) {});
 }
 
 // pixels outside the frame ride along with the direction of the nearest pixel inside it
