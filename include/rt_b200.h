@@ -169,6 +169,23 @@ typedef struct rt_counters {
 /* ---- lifetime ------------------------------------------------------------------------------ */
 /* device < 0: current CUDA device. */
 rt_status rt_create(int32_t device, rt_ctx** out);
+/* ONE process, n_gpus GPUs: the ctx handed back drives all of them behind the same entry points,
+ * so that the reference's call site stays one `trace_frame()` (src/main.ts:408-414).  devices: n_gpus CUDA device
+ * numbers, or NULL for 0 .. n_gpus-1 (a device may be named more than once: several members on one GPU, which is
+ * how the sharding is tested on a one-GPU box).  Peer access is enabled between all of them.
+ *   rt_scene_upload   validates and packs the scene ONCE on the host, uploads it to the first GPU and replicates it
+ *                     from there device to device (cudaMemcpyPeerAsync over NVLink / NVSwitch);
+ *   rt_render         every member renders its interleaved 16x16 tiles (tile t -> member t % n_gpus) and stores them
+ *                     straight into the caller's host frame, page-locked and mapped into every GPU's address space,
+ *                     over that GPU's own PCIe link; the launch sequences of the members are enqueued by one worker
+ *                     thread per GPU; counters are summed;
+ *   rt_render_device / rt_render_present
+ *                     the frame lives on the first GPU, the others store their tiles into it over NVLink (peer
+ *                     memory), the first GPU's stream waits for their events (no host round trip);
+ *   rt_get_counters, rt_synchronize cover all members; everything else acts on the first GPU.
+ * n_gpus == 1 is rt_create(devices ? devices[0] : 0). */
+rt_status rt_create_multi(int32_t n_gpus, const int32_t* devices, rt_ctx** out);
+uint32_t rt_group_size(const rt_ctx* ctx); /* GPUs (members) behind this ctx: 1 for rt_create */
 void rt_destroy(rt_ctx* ctx);
 const char* rt_last_error(const rt_ctx* ctx);
 uint32_t rt_abi_version(void);

@@ -71,6 +71,8 @@ class ExposureStats(C.Structure):
 EXPORTS = {
     "rt_abi_version": (C.c_uint32, []),
     "rt_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
+    "rt_create_multi": (C.c_int, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]),
+    "rt_group_size": (C.c_uint32, [C.c_void_p]),
     "rt_destroy": (None, [C.c_void_p]),
     "rt_last_error": (C.c_char_p, [C.c_void_p]),
     "rt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -2,8 +2,13 @@
 // No PyTorch, no CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 
 #include "rt_build.h"
 #include "rt_build_gpu.cuh"
@@ -28,20 +33,23 @@ __global__ void rt_prepare_primary_kernel(const __grid_constant__ RtDevScene S, 
 // Ray generation: Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250) for the whole frame.  The generator
 // ITERATES a rotation along every row, outwards from the middle column; in floating point that recurrence has no
 // closed form with the same bits, and after three mirror bounces off millimetre spheres a last-bit difference of a
-// camera direction is a different path.  So the recurrence itself runs here: one thread per half row (2 x height
-// threads, width / 2 dependent steps each - about 10 us at 1080p), every direction stored once, 32 B per pixel.
-__global__ void __launch_bounds__(32)
+// camera direction is a different path.  So the recurrence itself runs here.  rotate_vectors works component by
+// component - (fr[k], lf[k]) <- (fr[k] c + lf[k] s, -fr[k] s + lf[k] c) -, so a half row is THREE independent
+// recurrences: one lane per (row, half, component), 6 x height lanes, width / 2 dependent steps of 4 multiplications
+// and 2 additions each (the kernel is bound by FP64 issue and latency: a third of the instructions per lane is three
+// times faster), every direction stored once, 32 B per pixel.
+#define RT_RAYGEN_THREADS 96
+__global__ void __launch_bounds__(RT_RAYGEN_THREADS)
     rt_raygen_kernel(const __grid_constant__ RtFrame F, RtD4* __restrict__ dirs, int tiles_x) {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= 2 * F.height) return;
-	const int y = t >> 1, half = t & 1;
-	RtD4* out = dirs + (size_t)y * F.width;
-	if (F.tile_world > 1) {
-		const int row_tile = (y / RT_TILE_H) * tiles_x;
-		raygen_half_row(F, y, half, out, [&](int x) { return (row_tile + x / RT_TILE_W) % F.tile_world == F.tile_rank; });
-	} else {
-		raygen_half_row(F, y, half, out, [](int) { return true; });
-	}
+	if (t >= 6 * F.height) return;
+	const int comp = t % 3, half = (t / 3) & 1, y = t / 6;
+	double* out = reinterpret_cast<double*>(dirs + (size_t)y * F.width) + comp;
+	const int row_tile = (y / RT_TILE_H) * tiles_x;
+	if (F.tile_world > 1)
+		raygen_half_row_component(F, y, half, comp, out, [&](int x) { return (row_tile + x / RT_TILE_W) % F.tile_world == F.tile_rank; });
+	else
+		raygen_half_row_component(F, y, half, comp, out, [](int) { return true; });
 }
 
 // Persistent warps: the grid is sized to the resident capacity of the GPU (SMs x CTAs/SM) and every
@@ -105,29 +113,6 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 #ifndef RT_A_MINB
 #define RT_A_MINB 5
 #endif
-// Ray generation rides along in the same launch: the first F.raygen_jobs tickets of the dispenser are groups of 32
-// half rows (rt_trace.cuh: raygen_half_row, the generator's iterated rotations - FP64-issue bound, ~30 us at 1080p
-// for 68 warps of the ~3000 resident ones), which publish their progress every 16 columns with release stores; the
-// packets are handed out column by column from the MIDDLE tile column outwards, the order in which the rows grow, so
-// a packet's directions are in the table long before its ticket comes up (the wait below is a formality except for
-// the first few packets).  All CTAs of the persistent grid are resident, and the ray-generation tickets are taken
-// before any packet ticket: no packet can wait for a job that is not already running.
-RT_D void wait_for_rows(const RtFrame& F, int x_lo, int x_hi, int y_lo, int n_rows) {
-	const int lane = threadIdx.x & 31;
-	const int r = lane & 15, half = lane >> 4, y = y_lo + r, xc = F.width >> 1;
-	x_hi = min(x_hi, F.width - 1);
-	int need = 0;
-	if (r < n_rows && y < F.height) need = half ? (x_lo < xc ? xc - x_lo : 0) : (x_hi >= xc ? x_hi - xc + 1 : 0);
-	if (need > 0) {
-		const unsigned* flag = F.raygen_progress + 2 * y + half;
-		unsigned v;
-		do {
-			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-		} while (v < (unsigned)need);
-	}
-	__syncwarp();
-}
-
 template <int PPL, int MINB>
 __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
     rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_packets) {
@@ -136,53 +121,37 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
 	__shared__ __align__(16) float stages[RT_A_WARPS][96];
 	constexpr int PER_TILE = 8 / PPL;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int band_row0 = F.tile_begin / tiles_x, band_rows = (F.tile_end - F.tile_begin) / tiles_x;
-	const unsigned n_jobs = (unsigned)F.raygen_jobs;
 	uint32_t err = 0;
 	while (true) {
 		unsigned p = 0;
 		if (lane == 0) p = atomicAdd(F.work_counter, 1u);
 		p = __shfl_sync(0xffffffffu, p, 0);
-		if (p >= n_jobs + (unsigned)n_packets) break;
-		if (p < n_jobs) {  // ---- ray generation for the half rows 32 p ... 32 p + 31
-			const int t = (int)p * 32 + lane;
-			if (t < 2 * F.height) {
-				const int y = t >> 1, half = t & 1;
-				unsigned* flag = F.raygen_progress + t;
-				RtD4* out = const_cast<RtD4*>(F.dirs) + (size_t)y * F.width;
-				const int row_tile = (y / RT_TILE_H) * tiles_x;
-				auto publish = [&](int n) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"((unsigned)n) : "memory"); };
-				if (F.tile_world > 1)
-					raygen_half_row(F, y, half, out, [&](int x) { return (row_tile + x / RT_TILE_W) % F.tile_world == F.tile_rank; }, publish);
-				else
-					raygen_half_row(F, y, half, out, [](int) { return true; }, publish);
-			}
-			__syncwarp();
-			continue;
-		}
-		// ---- a packet: tiles of the band column by column, from the middle column outwards
-		p -= n_jobs;
-		const int ka = (int)(p / PER_TILE);
-		const int c = ka / band_rows, ty = band_row0 + (ka - c * band_rows);
-		const int tx = (c & 1) ? (tiles_x >> 1) - ((c + 1) >> 1) : (tiles_x >> 1) + (c >> 1);
-		const int tile = ty * tiles_x + tx;
-		if (tile % F.tile_world != F.tile_rank) continue;
+		if (p >= (unsigned)n_packets) break;
+		const int k = (int)(p / PER_TILE);
+		const int tile = F.tile_begin + F.tile_rank + k * F.tile_world;
+		if (tile >= F.tile_end) continue;
 		RtPatch pt;
-		pt.x0 = tx * RT_TILE_W;
-		pt.y0 = ty * RT_TILE_H;
+		pt.x0 = (tile % tiles_x) * RT_TILE_W;
+		pt.y0 = (tile / tiles_x) * RT_TILE_H;
 		pt.sub0 = (int)(p % PER_TILE) * PPL;
-		pt.out_base = (size_t)(tile / F.tile_world) * RT_BLOCK;
-		if (F.raygen_progress) wait_for_rows(F, pt.x0, pt.x0 + RT_TILE_W - 1, pt.y0 + (pt.sub0 >> 1) * 4, PPL * 2);
+		pt.out_base = (size_t)k * RT_BLOCK;
 		primary_patch<PPL>(S, F, pt, stacks[warp], rays[warp], stages[warp], err);
 	}
 	if (err) atomicOr(F.error_flags, err);
 }
 
-// Entries of a lane's walk stack in shared memory (interleaved: entry i of thread t at [i * 128 + t]), sized so that
-// MINB CTAs of 128 threads fit one SM's 227 KB.  Octree entries: at most 3 pending siblings per level are usual (a
-// line pierces at most 4 octants of a cube), plus the list BVH's depth; a ray that needs more is searched by the
-// reference-order walker instead (RtWalk.overflow).
-#define RT_WALK_SCAP(minb) ((minb) >= 8 ? 48 : (minb) >= 6 ? 64 : (minb) >= 5 ? 80 : 96)
+// Bounce stage: persistent wavefront with a per-warp ray queue.  Every lane owns one pixel job (all its
+// exposure frames) and is in one of four states:
+//   IDLE   no job: refilled from the continuation queue (one atomic per refill, ranks by popc of the vote);
+//   BEGIN  a ray segment starts: walker re-seed (segment_begin);
+//   WALK   the ordered walk, run by the whole warp in lock-step (walk_iter: every lane does one node step
+//          and/or one list-BVH step per iteration, phases re-converged);
+//   END    the search is over: collision + the material's response (segment_end), which starts the next
+//          segment (BEGIN), the next exposure frame, or ends the job (IDLE).
+// The warp leaves the walk loop as soon as a quarter of the lanes that entered it have finished (or fewer
+// than F.bounce_min_walking are left), so that a path that bounces four times or crosses a long list does
+// not hold finished lanes hostage: those shade, start their next segment or fetch a new pixel, and re-join.
+// Frames whose path never drew from the RNG reuse the first frame's sample.
 #define RT_ST_IDLE 0
 #define RT_ST_BEGIN 1
 #define RT_ST_WALK 2
@@ -190,8 +159,6 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
 template <int MINB>
 __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
     rt_bounce_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
-	__shared__ unsigned stacks[RT_WALK_SCAP(MINB) * RT_WARPS_PER_CTA * 32];
-	const RtWalkStack K = {stacks + threadIdx.x, RT_WARPS_PER_CTA * 32, RT_WALK_SCAP(MINB)};
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const unsigned n = *F.queue_count;
@@ -274,7 +241,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			double c[3];
 			int hit = -1;
 			RtCollision ci;
-			const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, &K, hit, ci);
+			const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
 			if (r == RT_SEG_DONE) {
 				sample_done(c);
 			} else if (r == RT_SEG_WALK) {
@@ -293,7 +260,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			if (nw > 0) {
 				const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
 				do {
-					walking = walk_step<true>(S, W, K, P.refpoint, P.dir, walking);
+					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
 					nw = __popc(__ballot_sync(0xffffffffu, walking));
 				} while (nw >= limit);
 				if (st == RT_ST_WALK && !walking) st = RT_ST_END;
@@ -329,8 +296,6 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 template <int MINB>
 __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
     rt_resample_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
-	__shared__ unsigned stacks[RT_WALK_SCAP(MINB) * RT_WARPS_PER_CTA * 32];
-	const RtWalkStack K = {stacks + threadIdx.x, RT_WARPS_PER_CTA * 32, RT_WALK_SCAP(MINB)};
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const unsigned n = *F.vqueue_count;
@@ -394,7 +359,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 				double c[3];
 				int hit = -1;
 				RtCollision ci;
-				const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, &K, hit, ci);
+				const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
 				if (r == RT_SEG_DONE) {
 					sample_done(c);
 				} else if (r == RT_SEG_WALK) {
@@ -413,7 +378,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 				if (nw > 0) {
 					const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
 					do {
-						walking = walk_step<true>(S, W, K, P.refpoint, P.dir, walking);
+						walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
 						nw = __popc(__ballot_sync(0xffffffffu, walking));
 					} while (nw >= limit);
 					if (st == RT_ST_WALK && !walking) st = RT_ST_END;
@@ -623,8 +588,18 @@ struct RenderKey {
 	void* stream;
 };
 
+// Identity of a ray-generation table: the camera's basis and frame, not its position.
+struct RaygenKey {
+	double basis[9], fov_h, fov_v;
+	uint32_t width, height, flags;
+	int rank, world;
+	void* dirs;
+};
+
 struct rt_ctx {
 	int device = 0;
+	RaygenKey raygen_key;
+	bool raygen_key_valid = false;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	cudaStream_t copy_stream = nullptr;          // device->host band copies of rt_render
@@ -646,7 +621,25 @@ struct rt_ctx {
 	cudaEvent_t stage_ev[RT_N_STAGES + 1] = {};
 	bool stage_ran[RT_N_STAGES] = {};
 
-	RtHostScene host;  // packed host copy (also serves the once-per-frame start state)
+	// packed host copy (also serves the once-per-frame start state); the members of a multi-GPU group share one
+	std::shared_ptr<RtHostScene> host_p = std::make_shared<RtHostScene>();
+	RtHostScene& host_ref() { return *host_p; }
+	// ---- multi-GPU group (rt_create_multi): ONE process drives every GPU.  The ctx handed to the caller is the
+	// leader (group[0] == this); members[1..] own a device, a stream and a worker thread that enqueues their share
+	// of a frame (the per-call CPU cost of a launch sequence times 8 GPUs from one thread would be the frame time).
+	std::vector<rt_ctx*> group;
+	rt_ctx* leader = nullptr;
+	int rank = 0;
+	cudaEvent_t fork_ev = nullptr, done_ev = nullptr;
+	std::thread worker;
+	std::mutex wm;
+	std::condition_variable wcv;
+	std::atomic<uint64_t> w_posted{0}, w_finished{0};
+	std::function<rt_status()> w_job;
+	rt_status w_status = RT_OK;
+	bool w_quit = false;
+	struct HostMap { void* host; size_t bytes; bool registered; std::vector<void*> dev; };
+	std::vector<HostMap> hostmaps;  // caller-owned host frames mapped into every member's address space
 	DevBuf<RtF4> node_geom;
 	DevBuf<RtI4> node_link;
 	DevBuf<int> node_child;
@@ -688,7 +681,6 @@ struct rt_ctx {
 	int primary_minb = RT_A_MINB;                // tuning knob RT_B200_PRIMARY_MINB=4|5|6: resident CTAs per SM the primary stage is compiled for
 	int bounce_min_walking = 12;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
 	int resample_min_frames = 8;                 // tuning knob RT_B200_RESAMPLE_MIN
-	bool fuse_raygen = true;                     // tuning knob RT_B200_FUSE_RAYGEN=0: ray generation as a kernel of its own
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
 	int bounce_minb = 8;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
 	int bounce_node_batch = 4;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
@@ -720,8 +712,8 @@ rt_status upload(rt_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& host) {
 rt_status check_args(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm) {
 	if (!ctx) return RT_ERR_INVALID;
 	std::string err;
-	const rt_status st = rt_check_render_args(ctx->has_scene, (uint32_t)ctx->host.textures.size(),
-	                                          (uint32_t)ctx->host.substances.size(), cam, prm, err);
+	const rt_status st = rt_check_render_args(ctx->has_scene, (uint32_t)ctx->host_ref().textures.size(),
+	                                          (uint32_t)ctx->host_ref().substances.size(), cam, prm, err);
 	return st ? fail(ctx, st, err) : RT_OK;
 }
 
@@ -790,7 +782,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	RT_CUDA(ctx, ctx->dirs.alloc((size_t)cam->width * cam->height));
 	RtFrame F{};
 	std::string err;
-	if (rt_status st = rt_fill_frame(ctx->host, cam, prm, F, err)) return fail(ctx, st, err);
+	if (rt_status st = rt_fill_frame(ctx->host_ref(), cam, prm, F, err)) return fail(ctx, st, err);
 	F.row_fr = ctx->row_fr.p;
 	F.dirs = ctx->dirs.p;
 	F.scan_cos = scan_cos;
@@ -805,9 +797,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	// u64 cells: [0..7] work counters, [8] error flags, then per band {patch dispenser, queue count, queue cursor,
 	// resample queue count, resample queue cursor}
 	n_bands = std::max(1, std::min(n_bands, RT_MAX_BANDS));
-	// ... then the ray-generation progress flags, 2 x height x u32
-	const size_t n_ctl_cells = 9 + 5 * RT_MAX_BANDS;
-	const size_t n_cells = n_ctl_cells + (size_t)cam->height;
+	const size_t n_cells = 9 + 5 * RT_MAX_BANDS;
 	RT_CUDA(ctx, ctx->counters.alloc(n_cells));
 	F.counters = ctx->counters.p;
 	F.error_flags = reinterpret_cast<uint32_t*>(ctx->counters.p + 8);
@@ -818,7 +808,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	if (tile_compact || tile_world > 1) n_bands = 1;
 	n_bands = std::min(n_bands, tiles_y);
 	// primary-ray preparation: origin-relative slot records + the origin chain (start node ... root)
-	const RtHostScene& H = ctx->host;
+	const RtHostScene& H = ctx->host_ref();
 	const int n_slots = (int)H.slot_geom.size();
 	const bool prim = n_slots > 0 && !(prm->flags & RT_PARAM_NO_PRIMARY_RECORDS);
 	F.prim_geom = nullptr;
@@ -894,10 +884,9 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 			return prof ? cudaEventRecord(ctx->stage_ev[stage], ctx->stream) : cudaSuccess;
 		};
 		RT_CUDA(ctx, mark(0));
-		// Per camera pose (a captured frame repeats the call before it and inherits both): the origin-relative records,
-		// a small kernel of its own, and the ray generation - inside the primary stage's launch when there is one
-		// (rt_primary_kernel: the first tickets of its dispenser), else as a kernel of its own.
-		bool raygen_fused = false;
+		// Per camera pose (a captured frame repeats the call before it and inherits both): the origin-relative records
+		// and the ray generation (the generator's iterated rotations, 3 lanes per half row).  The directions depend on
+		// the camera's basis only: a camera that merely moved (the reference's WASD keys, src/main.ts:296-330) keeps them.
 		if (!capture) {
 			if (prim) {
 				rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
@@ -906,13 +895,19 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				ctx->stage_ran[0] = prof;
 				RT_CUDA(ctx, cudaGetLastError());
 			}
-			if (pipeline && ctx->fuse_raygen) {
-				raygen_fused = true;
-			} else {
-				rt_raygen_kernel<<<(2 * F.height + 31) / 32, 32, 0, ctx->stream>>>(F, ctx->dirs.p, tiles_x);
+			RaygenKey rk;
+			memset(&rk, 0, sizeof rk);
+			memcpy(rk.basis, cam->fr, sizeof cam->fr); memcpy(rk.basis + 3, cam->lf, sizeof cam->lf); memcpy(rk.basis + 6, cam->up, sizeof cam->up);
+			rk.fov_h = cam->fov_h; rk.fov_v = cam->fov_v; rk.width = cam->width; rk.height = cam->height; rk.flags = cam->flags;
+			rk.rank = tile_rank; rk.world = tile_world; rk.dirs = ctx->dirs.p;
+			if (!ctx->raygen_key_valid || memcmp(&rk, &ctx->raygen_key, sizeof rk) != 0) {
+				const int lanes = 6 * F.height;  // (row, half, component)
+				rt_raygen_kernel<<<(lanes + RT_RAYGEN_THREADS - 1) / RT_RAYGEN_THREADS, RT_RAYGEN_THREADS, 0, ctx->stream>>>(F, ctx->dirs.p, tiles_x);
 				ctx->launches++;
 				ctx->stage_ran[0] = prof;
 				RT_CUDA(ctx, cudaGetLastError());
+				ctx->raygen_key = rk;
+				ctx->raygen_key_valid = true;
 			}
 		}
 		RT_CUDA(ctx, mark(1));
@@ -937,11 +932,8 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				// primary stage (packet walk) -> shade stage -> bounce stage over the continuation queue
 				F.queue = ctx->queue.p + F.out_first;
 				F.vqueue = resample ? ctx->vqueue.p + F.out_first : nullptr;
-				// the dispenser walks ALL tiles of the band (middle column outwards); a rank skips the tiles of the others
-				const int n_packets = band_tiles * (8 / ppl);
-				F.raygen_jobs = raygen_fused && band == 0 ? (2 * F.height + 31) / 32 : 0;
-				F.raygen_progress = raygen_fused && band == 0 ? reinterpret_cast<unsigned*>(ctx->counters.p + n_ctl_cells) : nullptr;
-				const int blocks = std::min(grid_primary, (my_tiles * (8 / ppl) + F.raygen_jobs + RT_A_WARPS - 1) / RT_A_WARPS);
+				const int n_packets = my_tiles * (8 / ppl);
+				const int blocks = std::min(grid_primary, (n_packets + RT_A_WARPS - 1) / RT_A_WARPS);
 				void* args[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x, (void*)&n_packets};
 				RT_CUDA(ctx, cudaLaunchKernel(primary_kernel, dim3(blocks), dim3(RT_A_WARPS * 32), args, 0, ctx->stream));
 				ctx->launches++;
@@ -1021,6 +1013,190 @@ rt_status read_counters(rt_ctx* ctx, rt_counters* out) {
 
 }  // namespace
 
+// ================================================================== multi-GPU group (one process, every GPU)
+namespace {
+
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+	__builtin_ia32_pause();
+#else
+	std::this_thread::yield();
+#endif
+}
+
+// A member's worker: sleeps on its condition variable, spins for a moment before that (a frame is a fraction of a
+// millisecond: the next job usually arrives before a sleeping thread could be woken).
+void worker_loop(rt_ctx* m) {
+	cudaSetDevice(m->device);
+	uint64_t seen = 0;
+	for (;;) {
+		for (int i = 0; i < 40000 && m->w_posted.load(std::memory_order_acquire) == seen; i++) cpu_relax();
+		if (m->w_posted.load(std::memory_order_acquire) == seen) {
+			std::unique_lock<std::mutex> lk(m->wm);
+			m->wcv.wait(lk, [&] { return m->w_posted.load(std::memory_order_acquire) != seen; });
+		}
+		std::function<rt_status()> job;
+		{
+			std::lock_guard<std::mutex> lk(m->wm);
+			seen = m->w_posted.load(std::memory_order_acquire);
+			if (m->w_quit) return;
+			job = m->w_job;
+		}
+		m->w_status = job ? job() : RT_OK;
+		m->w_finished.store(seen, std::memory_order_release);
+	}
+}
+
+void worker_post(rt_ctx* m, std::function<rt_status()> job) {
+	{
+		std::lock_guard<std::mutex> lk(m->wm);
+		m->w_job = std::move(job);
+		m->w_posted.fetch_add(1, std::memory_order_release);
+	}
+	m->wcv.notify_one();
+}
+
+rt_status worker_wait(rt_ctx* m) {
+	const uint64_t want = m->w_posted.load(std::memory_order_acquire);
+	for (int i = 0; m->w_finished.load(std::memory_order_acquire) != want; i++)
+		if (i < 100000) cpu_relax();
+		else std::this_thread::yield();
+	return m->w_status;
+}
+
+// fn(rank, member) for every member of the leader's group: members 1.. on their workers, member 0 on the calling
+// thread.  Returns the first failure, with the member's message copied to the leader.
+rt_status group_run(rt_ctx* L, const std::function<rt_status(int, rt_ctx*)>& fn) {
+	const int n = (int)L->group.size();
+	for (int r = 1; r < n; r++) {
+		rt_ctx* m = L->group[r];
+		worker_post(m, [&fn, r, m]() { return fn(r, m); });
+	}
+	rt_status st = fn(0, L);
+	for (int r = 1; r < n; r++) {
+		const rt_status sr = worker_wait(L->group[r]);
+		if (sr != RT_OK && st == RT_OK) {
+			st = sr;
+			L->err = rt_format("GPU %d of the group: %s", L->group[r]->device, L->group[r]->err.c_str());
+		}
+	}
+	cudaSetDevice(L->device);
+	return st;
+}
+
+// A caller-owned host buffer, page-locked and mapped into every member's address space (zero copy): each GPU's
+// kernels store its tiles straight into it over that GPU's own PCIe link.
+rt_status group_map_host(rt_ctx* L, void* ptr, size_t bytes, rt_ctx::HostMap** out) {
+	for (auto& hm : L->hostmaps)
+		if (hm.host == ptr && hm.bytes == bytes) { *out = &hm; return RT_OK; }
+	for (size_t i = 0; i < L->hostmaps.size();)  // the same address with another size: the old buffer is gone
+		if (L->hostmaps[i].host == ptr) {
+			if (L->hostmaps[i].registered) cudaHostUnregister(ptr);
+			L->hostmaps.erase(L->hostmaps.begin() + (long)i);
+		} else i++;
+	if (L->hostmaps.size() >= 8) {
+		if (L->hostmaps[0].registered) cudaHostUnregister(L->hostmaps[0].host);
+		L->hostmaps.erase(L->hostmaps.begin());
+	}
+	rt_ctx::HostMap hm{ptr, bytes, true, {}};
+	RT_CUDA(L, cudaSetDevice(L->device));
+	cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+	if (e == cudaErrorHostMemoryAlreadyRegistered) {  // pinned by the caller (rt_host_register): with UVA it is mapped already
+		cudaGetLastError();
+		hm.registered = false;
+	} else if (e != cudaSuccess) {
+		return fail(L, RT_ERR_CUDA, rt_format("cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e)));
+	}
+	for (rt_ctx* m : L->group) {
+		void* d = nullptr;
+		cudaSetDevice(m->device);
+		e = cudaHostGetDevicePointer(&d, ptr, 0);
+		if (e != cudaSuccess) {
+			if (hm.registered) cudaHostUnregister(ptr);
+			cudaSetDevice(L->device);
+			return fail(L, RT_ERR_CUDA, rt_format("cudaHostGetDevicePointer on GPU %d: %s", m->device, cudaGetErrorString(e)));
+		}
+		hm.dev.push_back(d);
+	}
+	cudaSetDevice(L->device);
+	L->hostmaps.push_back(hm);
+	*out = &L->hostmaps.back();
+	return RT_OK;
+}
+
+// trace_frame() of a group into HOST buffers: every member renders its interleaved 16x16 tiles (tile t -> member
+// t % n) from its replica of the scene and stores them into the mapped host frame.  Synchronous.
+rt_status group_render_host(rt_ctx* L, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb, int32_t* ids,
+                            rt_counters* counters) {
+	const int n = (int)L->group.size();
+	const size_t npx = (size_t)cam->width * cam->height;
+	rt_ctx::HostMap *mr = nullptr, *mi = nullptr;
+	if (rt_status st = group_map_host(L, rgb, npx * 3 * sizeof(float), &mr)) return st;
+	const std::vector<void*> rgb_dev = mr->dev;  // (copied: a second mapping may move the table)
+	std::vector<void*> ids_dev(n, nullptr);
+	if (ids) {
+		if (rt_status st = group_map_host(L, ids, npx * sizeof(int32_t), &mi)) return st;
+		ids_dev = mi->dev;
+	}
+	if (counters) flags |= RT_RENDER_COUNTERS;
+	std::vector<rt_counters> part(n);
+	const rt_status st = group_run(L, [&](int r, rt_ctx* m) -> rt_status {
+		RT_CUDA(m, cudaSetDevice(m->device));
+		if (rt_status s = launch_render(m, cam, prm, flags, (float*)rgb_dev[r], (int*)ids_dev[r], r, n, false)) return s;
+		return read_counters(m, &part[r]);  // synchronises the member's stream and fetches its error flags
+	});
+	if (st != RT_OK) return st;
+	rt_counters tot;
+	memset(&tot, 0, sizeof tot);
+	for (const rt_counters& c : part) {
+		tot.paths += c.paths; tot.segments += c.segments; tot.nodes += c.nodes; tot.tests += c.tests; tot.shades += c.shades;
+		tot.confirms += c.confirms; tot.texture_errors |= c.texture_errors; tot.acute_warnings |= c.acute_warnings;
+	}
+	if (counters) *counters = tot;
+	if (tot.texture_errors) return fail(L, RT_ERR_TEXTURE, "Texture coordinates out of bounds");
+	return RT_OK;
+}
+
+// ... into a DEVICE frame that lives on the leader's GPU: the other members store their tiles into it over NVLink
+// (peer access inside one process: plain pointers), the leader's stream waits for their events.  Asynchronous.
+rt_status group_render_device(rt_ctx* L, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb_dev, int32_t* ids_dev) {
+	const int n = (int)L->group.size();
+	RT_CUDA(L, cudaSetDevice(L->device));
+	RT_CUDA(L, cudaEventRecord(L->fork_ev, L->stream));  // whatever the leader's stream did to the frame so far comes first
+	const rt_status st = group_run(L, [&](int r, rt_ctx* m) -> rt_status {
+		RT_CUDA(m, cudaSetDevice(m->device));
+		if (r > 0) RT_CUDA(m, cudaStreamWaitEvent(m->stream, L->fork_ev, 0));
+		if (rt_status s = launch_render(m, cam, prm, flags, rgb_dev, ids_dev, r, n, false)) return s;
+		if (r > 0) RT_CUDA(m, cudaEventRecord(m->done_ev, m->stream));
+		return RT_OK;
+	});
+	if (st != RT_OK) return st;
+	for (int r = 1; r < n; r++) RT_CUDA(L, cudaStreamWaitEvent(L->stream, L->group[r]->done_ev, 0));
+	return RT_OK;
+}
+
+// one render into a device frame, single GPU or group
+rt_status render_device_any(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb_dev, int32_t* ids_dev) {
+	if (ctx->group.size() > 1) return group_render_device(ctx, cam, prm, flags, rgb_dev, ids_dev);
+	return launch_render(ctx, cam, prm, flags, rgb_dev, ids_dev, 0, 1);
+}
+
+rt_status read_counters_any(rt_ctx* ctx, rt_counters* out) {
+	if (ctx->group.size() <= 1) return read_counters(ctx, out);
+	memset(out, 0, sizeof *out);
+	for (rt_ctx* m : ctx->group) {
+		rt_counters c;
+		RT_CUDA(ctx, cudaSetDevice(m->device));
+		if (rt_status st = read_counters(m, &c)) return st;
+		out->paths += c.paths; out->segments += c.segments; out->nodes += c.nodes; out->tests += c.tests; out->shades += c.shades;
+		out->confirms += c.confirms; out->texture_errors |= c.texture_errors; out->acute_warnings |= c.acute_warnings;
+	}
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	return RT_OK;
+}
+
+}  // namespace
+
 // ================================================================== C ABI
 extern "C" {
 
@@ -1068,7 +1244,6 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 		if (v >= 1 && v <= 32) ctx->bounce_min_walking = v;
 	}
 	if (const char* e = getenv("RT_B200_RESAMPLE")) ctx->resample = atoi(e) != 0;
-	if (const char* e = getenv("RT_B200_FUSE_RAYGEN")) ctx->fuse_raygen = atoi(e) != 0;
 	if (const char* e = getenv("RT_B200_RESAMPLE_MIN")) ctx->resample_min_frames = std::max(2, atoi(e));
 	if (const char* e = getenv("RT_B200_BOUNCE_MINB")) {
 		const int v = atoi(e);
@@ -1090,9 +1265,102 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	return RT_OK;
 }
 
+rt_status rt_create_multi(int32_t n_gpus, const int32_t* devices, rt_ctx** out) {
+	if (!out) return fail(nullptr, RT_ERR_INVALID, "rt_create_multi: out is NULL");
+	*out = nullptr;
+	if (n_gpus < 1 || n_gpus > 64) return fail(nullptr, RT_ERR_INVALID, rt_format("rt_create_multi: n_gpus %d", n_gpus));
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(nullptr, RT_ERR_CUDA, rt_format("rt_create_multi: no CUDA device (%s); this library has no CPU path",
+		                                            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
+	if (!devices && n_gpus > count)
+		return fail(nullptr, RT_ERR_INVALID, rt_format("rt_create_multi: %d GPUs asked for, %d present", n_gpus, count));
+	std::vector<rt_ctx*> members;
+	auto undo = [&]() {
+		for (rt_ctx* m : members) rt_destroy(m);
+	};
+	for (int i = 0; i < n_gpus; i++) {
+		rt_ctx* m = nullptr;
+		const rt_status st = rt_create(devices ? devices[i] : i, &m);
+		if (st != RT_OK) {
+			undo();
+			return st;
+		}
+		members.push_back(m);
+	}
+	rt_ctx* L = members[0];
+	if (n_gpus == 1) {
+		*out = L;
+		return RT_OK;
+	}
+	// every GPU reaches every other GPU's memory (NVLink / NVSwitch): scene replication and the device-resident frame
+	for (rt_ctx* a : members)
+		for (rt_ctx* b : members) {
+			if (a->device == b->device) continue;
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, a->device, b->device);
+			cudaSetDevice(a->device);
+			e = can ? cudaDeviceEnablePeerAccess(b->device, 0) : cudaErrorPeerAccessUnsupported;
+			if (e == cudaErrorPeerAccessAlreadyEnabled) {
+				cudaGetLastError();
+			} else if (e != cudaSuccess) {
+				const rt_status st = fail(nullptr, RT_ERR_CUDA, rt_format("rt_create_multi: GPU %d cannot map GPU %d's memory: %s", a->device,
+				                                                          b->device, cudaGetErrorString(e)));
+				cudaGetLastError();
+				undo();
+				return st;
+			}
+		}
+	for (int r = 0; r < n_gpus; r++) {
+		rt_ctx* m = members[r];
+		m->rank = r;
+		m->leader = r ? L : nullptr;
+		cudaSetDevice(m->device);
+		e = cudaEventCreateWithFlags(&m->fork_ev, cudaEventDisableTiming);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->done_ev, cudaEventDisableTiming);
+		if (e != cudaSuccess) {
+			const rt_status st = fail(nullptr, RT_ERR_CUDA, rt_format("rt_create_multi: %s", cudaGetErrorString(e)));
+			undo();
+			return st;
+		}
+	}
+	L->group = members;
+	for (int r = 1; r < n_gpus; r++) members[r]->worker = std::thread(worker_loop, members[r]);
+	cudaSetDevice(L->device);
+	*out = L;
+	return RT_OK;
+}
+
+uint32_t rt_group_size(const rt_ctx* ctx) { return ctx ? (uint32_t)std::max<size_t>(1, ctx->group.size()) : 0; }
+
 void rt_destroy(rt_ctx* ctx) {
 	if (!ctx) return;
+	if (ctx->group.size() > 1) {  // a leader: stop and free the other members first
+		std::vector<rt_ctx*> members = ctx->group;
+		ctx->group.clear();
+		for (size_t r = 1; r < members.size(); r++) {
+			rt_ctx* m = members[r];
+			if (m->worker.joinable()) {
+				{
+					std::lock_guard<std::mutex> lk(m->wm);
+					m->w_quit = true;
+					m->w_posted.fetch_add(1, std::memory_order_release);
+				}
+				m->wcv.notify_one();
+				m->worker.join();
+			}
+			m->leader = nullptr;
+			rt_destroy(m);
+		}
+		cudaSetDevice(ctx->device);
+		for (auto& hm : ctx->hostmaps)
+			if (hm.registered) cudaHostUnregister(hm.host);
+		ctx->hostmaps.clear();
+	}
 	cudaSetDevice(ctx->device);
+	if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+	if (ctx->done_ev) cudaEventDestroy(ctx->done_ev);
 	cudaStreamSynchronize(ctx->stream);
 	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_walk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release(); ctx->bvh_geom.release();
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
@@ -1122,6 +1390,10 @@ rt_status rt_set_stream(rt_ctx* ctx, void* cuda_stream) {
 
 rt_status rt_synchronize(rt_ctx* ctx) {
 	if (!ctx) return RT_ERR_INVALID;
+	for (size_t r = 1; r < ctx->group.size(); r++) {
+		RT_CUDA(ctx, cudaSetDevice(ctx->group[r]->device));
+		RT_CUDA(ctx, cudaStreamSynchronize(ctx->group[r]->stream));
+	}
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return RT_OK;
@@ -1193,38 +1465,63 @@ rt_status rt_host_unregister(rt_ctx* ctx, void* ptr) {
 	return RT_OK;
 }
 
-rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
-	if (!ctx) return RT_ERR_INVALID;
-	RT_CUDA(ctx, cudaSetDevice(ctx->device));
-	std::string err;
-	RtHostScene hs;
-	if (rt_status st = rt_pack_scene(sc, hs, err)) return fail(ctx, st, err);
-	ctx->has_scene = false;
-	ctx->scene_version++;
-	ctx->key_valid = false;
-	ctx->host = std::move(hs);
-	const RtHostScene& H = ctx->host;
-	rt_status st;
-	if ((st = upload(ctx, ctx->node_geom, H.node_geom)) || (st = upload(ctx, ctx->node_link, H.node_link)) ||
-	    (st = upload(ctx, ctx->node_child, H.node_child)) || (st = upload(ctx, ctx->node_pk, H.node_pk)) || (st = upload(ctx, ctx->node_walk, H.node_walk)) || (st = upload(ctx, ctx->node_bvh, H.node_bvh)) ||
-	    (st = upload(ctx, ctx->bvh_nodes, H.bvh_nodes)) || (st = upload(ctx, ctx->bvh_slots, H.bvh_slots)) || (st = upload(ctx, ctx->bvh_geom, H.bvh_geom)) || (st = upload(ctx, ctx->slot_geom, H.slot_geom)) ||
-	    (st = upload(ctx, ctx->slot_geom64, H.slot_geom64)) || (st = upload(ctx, ctx->slot_attr, H.slot_attr)) ||
-	    (st = upload(ctx, ctx->materials, H.materials)) || (st = upload(ctx, ctx->textures, H.textures)) ||
-	    (st = upload(ctx, ctx->substances, H.substances)) || (st = upload(ctx, ctx->texels, H.texels)))
-		return st;
-	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+// every device array of a scene, with its host vector of the same name in RtHostScene
+#define RT_SCENE_ARRAYS(X) \
+	X(node_geom) X(node_link) X(node_child) X(node_pk) X(node_walk) X(node_bvh) X(bvh_nodes) X(bvh_slots) X(bvh_geom) \
+	X(slot_geom) X(slot_geom64) X(slot_attr) X(materials) X(textures) X(substances) X(texels)
+
+static void set_dev_scene(rt_ctx* ctx) {
+	const RtHostScene& H = ctx->host_ref();
 	RtDevScene& D = ctx->dev;
-	D.node_geom = ctx->node_geom.p; D.node_link = ctx->node_link.p; D.node_child = ctx->node_child.p; D.node_pk = ctx->node_pk.p; D.node_walk = ctx->node_walk.p; D.node_bvh = ctx->node_bvh.p; D.bvh_nodes = ctx->bvh_nodes.p; D.bvh_slots = ctx->bvh_slots.p; D.bvh_geom = ctx->bvh_geom.p;
-	D.slot_geom = ctx->slot_geom.p; D.slot_geom64 = ctx->slot_geom64.p; D.slot_attr = ctx->slot_attr.p;
-	D.materials = ctx->materials.p; D.textures = ctx->textures.p; D.substances = ctx->substances.p;
-	D.texels = ctx->texels.p;
+#define X(name) D.name = ctx->name.p;
+	RT_SCENE_ARRAYS(X)
+#undef X
 	for (int k = 0; k < 3; k++) D.root_pos[k] = H.root_pos[k];
 	D.root_size = H.root_size;
 	D.n_nodes = (int)H.node_geom.size();
 	D.n_slots = (int)H.slot_geom.size();
 	D.err_l = H.err_l;
 	D.ordered_ok = rt_ordered_walk_fits(H);
+}
+
+rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
+	if (!ctx) return RT_ERR_INVALID;
+	if (ctx->leader) return fail(ctx, RT_ERR_INVALID, "rt_scene_upload: this ctx is a member of a multi-GPU group; upload through its leader");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	std::string err;
+	auto hs = std::make_shared<RtHostScene>();
+	if (rt_status st = rt_pack_scene(sc, *hs, err)) return fail(ctx, st, err);  // validated and packed ONCE, on the host
+	std::vector<rt_ctx*> all = ctx->group.empty() ? std::vector<rt_ctx*>{ctx} : ctx->group;
+	for (rt_ctx* m : all) {
+		m->has_scene = false;
+		m->scene_version++;
+		m->key_valid = false;
+		m->host_p = hs;
+	}
+	const RtHostScene& H = *hs;
+	rt_status st = RT_OK;
+#define X(name) if (!st) st = upload(ctx, ctx->name, H.name);
+	RT_SCENE_ARRAYS(X)
+#undef X
+	if (st) return st;
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	set_dev_scene(ctx);
 	ctx->has_scene = true;
+	// the other GPUs of a group get their replica device to device (NVLink / NVSwitch), not from the host again
+	for (size_t r = 1; r < all.size(); r++) {
+		rt_ctx* m = all[r];
+		RT_CUDA(ctx, cudaSetDevice(m->device));
+#define X(name)                                                                                                         \
+		RT_CUDA(ctx, m->name.alloc(H.name.size()));                                                                         \
+		if (!H.name.empty())                                                                                                \
+			RT_CUDA(ctx, cudaMemcpyPeerAsync(m->name.p, m->device, ctx->name.p, ctx->device, H.name.size() * sizeof(H.name[0]), m->stream));
+		RT_SCENE_ARRAYS(X)
+#undef X
+		RT_CUDA(ctx, cudaStreamSynchronize(m->stream));
+		set_dev_scene(m);
+		m->has_scene = true;
+	}
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
 	return RT_OK;
 }
 
@@ -1233,7 +1530,7 @@ rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* p
 	if (rt_status st = check_args(ctx, cam, prm)) return st;
 	if (!rgb_dev) return fail(ctx, RT_ERR_INVALID, "rt_render_device: rgb_dev is NULL");
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
-	return launch_render(ctx, cam, prm, flags, rgb_dev, ids_dev, 0, 1);
+	return render_device_any(ctx, cam, prm, flags, rgb_dev, ids_dev);
 }
 
 rt_status rt_camera_directions(rt_ctx* ctx, const rt_camera* cam, double* dirs) {
@@ -1257,7 +1554,8 @@ rt_status rt_camera_directions(rt_ctx* ctx, const rt_camera* cam, double* dirs) 
 	ctx->key_valid = false;  // the tables of a cached frame are gone
 	RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, rows.data(), rows.size() * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
 	F.row_fr = ctx->row_fr.p;
-	rt_raygen_kernel<<<(2 * F.height + 31) / 32, 32, 0, ctx->stream>>>(F, ctx->dirs.p, (F.width + RT_TILE_W - 1) / RT_TILE_W);
+	ctx->raygen_key_valid = false;
+	rt_raygen_kernel<<<(6 * F.height + RT_RAYGEN_THREADS - 1) / RT_RAYGEN_THREADS, RT_RAYGEN_THREADS, 0, ctx->stream>>>(F, ctx->dirs.p, (F.width + RT_TILE_W - 1) / RT_TILE_W);
 	ctx->launches++;
 	RT_CUDA(ctx, cudaGetLastError());
 	std::vector<RtD4> host(npx);
@@ -1438,7 +1736,7 @@ rt_status rt_untile_device(rt_ctx* ctx, uint32_t width, uint32_t height, uint32_
 
 rt_status rt_get_counters(rt_ctx* ctx, rt_counters* out) {
 	if (!ctx || !out) return RT_ERR_INVALID;
-	return read_counters(ctx, out);
+	return read_counters_any(ctx, out);
 }
 
 rt_status rt_present_device(rt_ctx* ctx, const float* rgb_dev, uint32_t width, uint32_t height, const rt_tone* tone,
@@ -1504,13 +1802,13 @@ rt_status rt_render_present(rt_ctx* ctx, const rt_camera* cam, const rt_params* 
 	ctx->exposure_w = cam->width;
 	ctx->exposure_h = cam->height;
 	if (counters) flags |= RT_RENDER_COUNTERS;
-	if (rt_status st = launch_render(ctx, cam, prm, flags, ctx->rgb.p, nullptr, 0, 1)) return st;
+	if (rt_status st = render_device_any(ctx, cam, prm, flags, ctx->rgb.p, nullptr)) return st;
 	if (rt_status st = rt_present_device(ctx, ctx->rgb.p, cam->width, cam->height, tone, ctx->rgba.p)) return st;
 	RT_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->rgba.p, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	if (stats)
 		if (rt_status st = rt_present_stats(ctx, stats)) return st;
 	rt_counters tmp;
-	if (rt_status st = read_counters(ctx, &tmp)) return st;  // also synchronises and fetches the error flags
+	if (rt_status st = read_counters_any(ctx, &tmp)) return st;  // also synchronises and fetches the error flags
 	if (counters) *counters = tmp;
 	if (tmp.texture_errors) return fail(ctx, RT_ERR_TEXTURE, "Texture coordinates out of bounds");
 	return RT_OK;
@@ -1531,6 +1829,7 @@ rt_status rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uin
 	if (rt_status st = check_args(ctx, cam, prm)) return st;
 	if (!rgb) return fail(ctx, RT_ERR_INVALID, "rt_render: rgb is NULL");
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (ctx->group.size() > 1) return group_render_host(ctx, cam, prm, flags, rgb, first_ids, counters);
 	const size_t npx = (size_t)cam->width * cam->height;
 	RT_CUDA(ctx, ctx->rgb.alloc(npx * 3));
 	ctx->exposure_w = ctx->exposure_h = 0;  // ctx->rgb is this call's staging, not a resident exposure

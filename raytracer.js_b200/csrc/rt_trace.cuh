@@ -794,26 +794,42 @@ RT_HD void rotate_pair(double* a, double* b, double c, double s) {
 // (half == 0) yields x = width>>1, ... , width-1 rotating AFTER every yield by rot_scan_h_v, the left half
 // (half == 1) rotates by the counter-clockwise rotation FIRST and yields x = (width>>1)-1, ..., 0.
 // own(x): whether this rank stores pixel x of the row (tile sharding); `out` is the row of the table.
-// publish(n): the first n columns of this half row are in the table (called every 16 columns and at the end).
-template <class Own, class Publish>
-RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own, Publish publish) {
+template <class Own>
+RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own) {
 	const RtD4 r = ld(F.row_fr + y);
 	double fr[3] = {r.x, r.y, r.z}, lf[3] = {F.lf[0], F.lf[1], F.lf[2]};
 	const int x0 = F.width >> 1;
-	// one loop shape for both halves (the two lanes of a row run it in lock-step): the left half has rotated once
-	// before its first yield, both rotate after every yield (the rotation after the last one is unused)
+	// one loop shape for both halves: the left half has rotated once before its first yield, both rotate after
+	// every yield (the rotation after the last one is unused)
 	const double s = half ? -F.scan_sin : F.scan_sin;
 	const int n = half ? x0 : F.width - x0, first = half ? x0 - 1 : x0, step = half ? -1 : 1;
 	if (half) rotate_pair(fr, lf, F.scan_cos, s);
 	for (int i = 0, x = first; i < n; i++, x += step) {
 		if (own(x)) out[x] = RtD4{fr[0], fr[1], fr[2], 0.0};
-		if (((i + 1) & 15) == 0 || i + 1 == n) publish(i + 1);
 		rotate_pair(fr, lf, F.scan_cos, s);
 	}
 }
+
+// The same for ONE component of the direction (rotate_vectors never mixes components): what one lane of
+// rt_raygen_kernel runs.  `out` points at that component of the row's first record (stride 4 doubles).
 template <class Own>
-RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own) {
-	raygen_half_row(F, y, half, out, own, [](int) {});
+RT_HD void raygen_half_row_component(const RtFrame& F, int y, int half, int comp, double* out, Own own) {
+	const RtD4 r = ld(F.row_fr + y);
+	double a = comp == 0 ? r.x : comp == 1 ? r.y : r.z, b = F.lf[comp];
+	const int x0 = F.width >> 1;
+	const double c = F.scan_cos, s = half ? -F.scan_sin : F.scan_sin;
+	const int n = half ? x0 : F.width - x0, first = half ? x0 - 1 : x0, step = half ? -1 : 1;
+	if (half) {
+		const double x = xadd(xmul(a, c), xmul(b, s)), yy = xadd(xmul(a, -s), xmul(b, c));
+		a = x;
+		b = yy;
+	}
+	for (int i = 0, x = first; i < n; i++, x += step) {
+		if (own(x)) out[(size_t)x * 4] = a;
+		const double na = xadd(xmul(a, c), xmul(b, s)), nb = xadd(xmul(a, -s), xmul(b, c));
+		a = na;
+		b = nb;
+	}
 }
 
 // pixels outside the frame ride along with the direction of the nearest pixel inside it
@@ -1158,30 +1174,23 @@ RT_HD double rng_next(RtRng& g) {
 // visits the children a ray pierces in ascending (octant ^ neg), subtrees in pre-order, and the nodes that
 // contain the ray origin in post-order.  Unlike the state machine of walk_and_scan (which follows the
 // reference's walker step by step and is kept for the counting kernel), this formulation is a stack machine
-// with three kinds of step, so that the 32 independent rays of a warp in the bounce stage run it in lock-step
-// (walk_step) instead of serialising on the branches of 32 different walker states.  The kind of a lane's next
-// step is the kind of its top stack entry:
-//   node step  (stack empty, or an octree node on top) pop the next octree node - or go one level up the origin
-//              chain -, push the children the ray pierces, last-visited first, and on top of them the root of the
-//              node's list BVH (tested right here: its box is part of the 64-byte node record);
-//   pair step  (a BVH pair on top) fetch the two sibling BVH nodes together (64 bytes), slab tests, push the inner
-//              ones that are hit and the leaves that are hit;
-//   leaf step  (a leaf on top) test the up to RT_BVH_LEAF entities of the leaf, keeping the LOWEST hit slot = the
-//              first entity in list order the ray hits (src/raytracer.ts:186-195).
+// with two kinds of step only, so that the 32 independent rays of a warp in the bounce stage run it in
+// lock-step (walk_iter) instead of serialising on the branches of 32 different walker states:
+//   node step  pop the next octree node (or, with the stack empty, go one level up the origin chain), push
+//              the children the ray pierces - last-visited first - and then the root of the node's list BVH;
+//   list step  pop one node of the current list's BVH and fetch its two children together (64 bytes): slab
+//              tests, then push the inner ones that are hit and test the up to RT_BVH_LEAF entities of the
+//              leaves that are hit, keeping the LOWEST hit slot = the first entity in list order the ray hits
+//              (src/raytracer.ts:186-195).
 // The list BVH sits on top of the octree entries, so a list is finished before the next node is popped, and
 // the walk ends at the first list that holds a hit.  A conservative (slack) pierce test can only add nodes,
 // which cannot change a first hit (entities lie inside their node's cube).
-// In lock-step the warp votes on the kinds and executes ONE kind per iteration, the one most lanes wait for: every
-// instruction of a step then runs for all the lanes that need that kind of step, instead of each kind running
-// every iteration for the few lanes that happen to need it.
-#define RT_WALK_LEAF 0x80000000u  // stack entry: bits 0..29 = first entry of a BVH leaf
-#define RT_WALK_PAIR 0x40000000u  // stack entry: bits 0..29 = first node of a BVH sibling pair (else: an octree node)
 struct RtWalk {
 	RtRayF r;
 	int neg;          // bit k: d_k < 0
 	int sp;
 	int floor;        // stack height below the current list's BVH entries
-	int in_list;      // 1: the entries above `floor` are BVH entries of the current list
+	int in_list;      // 1: the entries above `floor` are BVH nodes of the current list
 	int chain_node;   // origin-chain node whose list is returned once the stack is empty
 	int chain_oct;    // octant of chain_node the ray leaves (its children before it cannot be reached); < 0: root only
 	int chain_listed; // 1: chain_node's list has been scanned, next is its parent
@@ -1190,27 +1199,24 @@ struct RtWalk {
 	int hit;          // result: first-hit slot, -1 none
 	int overflow;     // 1: the stack was too small for this ray - the caller searches it with walk_and_scan instead
 	float slack;
+	int stack[RT_WALK_STACK];
 };
-// The stack of a walk: `cap` entries, entry i at base[i * stride] (the bounce stage keeps the stacks of a CTA
-// interleaved in shared memory, stride = threads per CTA: whatever the lanes' stack heights, every lane hits its
-// own bank).
-struct RtWalkStack {
-	unsigned* base;
-	int stride, cap;
-};
-RT_HD void walk_push(RtWalk& W, const RtWalkStack& K, unsigned v) {
-	if (W.sp < K.cap) K.base[(size_t)W.sp++ * K.stride] = v;
-	else W.overflow = 1;
+#ifdef RT_TEST_WALK_CAP  // tests/hostsim only: a tiny stack, so that the overflow path (segment_found) is exercised
+#define RT_WALK_CAP RT_TEST_WALK_CAP
+#else
+#define RT_WALK_CAP RT_WALK_STACK
+#endif
+RT_HD void walk_push(RtWalk& W, int v) {
+	if (W.sp < RT_WALK_CAP) W.stack[W.sp++] = v;
+	else W.overflow = 1;  // never a silent drop: the ray is searched again by the reference-order walker
 }
-RT_HD unsigned walk_pop(RtWalk& W, const RtWalkStack& K) { return K.base[(size_t)(--W.sp) * K.stride]; }
-RT_HD unsigned walk_top(const RtWalk& W, const RtWalkStack& K) { return K.base[(size_t)(W.sp - 1) * K.stride]; }
 
 // pushes the children of `nd` the ray may pierce, last-visited first.  In the ray's own frame (axis k
 // mirrored when d_k < 0) the half of the cube entered first is "half 0": key bit k of a child says which
 // half it is in, so the parameter interval of a child is a static selection among the intervals of the two
 // halves per axis.  The eight interval tests are predicates only (no branches); the loop runs once per child
 // actually pushed.
-RT_HD void walk_push_children(RtWalk& W, const RtWalkStack& K, const RtWNode& nd, int after_oct) {
+RT_HD void walk_push_children(RtWalk& W, const RtWNode& nd, int after_oct) {
 	const RtRayF& r = W.r;
 	const float h = nd.size * 0.5f;
 	float n0[3], f0[3], n1[3], f1[3];  // [near, far] of half 0 and of half 1, per axis
@@ -1250,12 +1256,12 @@ RT_HD void walk_push_children(RtWalk& W, const RtWalkStack& K, const RtWNode& nd
 		const int key = 31 - clz32(m);
 		m ^= 1u << key;
 		const int o = key ^ W.neg;
-		walk_push(W, K, (unsigned)(nd.child_base + popc32((unsigned)nd.child_mask & ((1u << o) - 1u))));
+		walk_push(W, nd.child_base + popc32((unsigned)nd.child_mask & ((1u << o) - 1u)));
 	}
 }
 
 // (node, octant): node_at_pos of the ray origin, or octant < 0 for "origin outside the root: root only"
-RT_HD void walk_begin(const RtDevScene& S, RtWalk& W, const RtWalkStack& K, int node, int octant) {
+RT_HD void walk_begin(const RtDevScene& S, RtWalk& W, int node, int octant) {
 	const RtRayF& r = W.r;
 	W.neg = (r.dx < 0.0f ? 1 : 0) | (r.dy < 0.0f ? 2 : 0) | (r.dz < 0.0f ? 4 : 0);
 	W.sp = 0;
@@ -1269,7 +1275,7 @@ RT_HD void walk_begin(const RtDevScene& S, RtWalk& W, const RtWalkStack& K, int 
 	W.chain_oct = octant;
 	W.chain_listed = 0;
 	W.chain_up = -1;
-	if (octant >= 0) walk_push_children(W, K, ld(S.node_walk + node), octant);
+	if (octant >= 0) walk_push_children(W, ld(S.node_walk + node), octant);
 }
 
 // float64 confirmation without the collision record (the caller recomputes it for the one slot it keeps)
@@ -1336,32 +1342,25 @@ RT_HD void walk_leaf(const RtDevScene& S, RtWalk& W, int leaf_a, const double* o
 	}
 }
 
-// One step of the walk for every lane of the warp (`walking`: this lane takes part).  Returns false when this
-// lane's walk is over (W.hit = slot or -1, or W.overflow).  LOCKSTEP: all 32 lanes of the warp call this together
-// (bounce stage), vote on the kind of step and take the one most lanes wait for; without it the caller may be one
-// lane of a diverged warp (ray-by-ray kernels, host build) and simply takes its own next step.
-#define RT_KIND_NODE 0
-#define RT_KIND_PAIR 1
-#define RT_KIND_LEAF 2
+// One iteration of the walk for every lane of the warp (`walking`: this lane takes part).  Returns false
+// when this lane's walk is over (W.hit = slot or -1).  LOCKSTEP: all 32 lanes of the warp call this together
+// (bounce stage) and the phases re-converge the warp between them; without it the caller may be one lane of a
+// diverged warp (ray-by-ray kernels) and no warp-wide barrier is used.
 template <bool LOCKSTEP>
-RT_HD bool walk_step(const RtDevScene& S, RtWalk& W, const RtWalkStack& K, const double* o, const double* d, bool walking) {
-	int kind = RT_KIND_NODE;
-	if (walking && W.in_list) kind = (walk_top(W, K) & RT_WALK_LEAF) ? RT_KIND_LEAF : RT_KIND_PAIR;  // (in_list => sp > floor)
-	bool mine = walking;
+RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const double* d, bool walking, int node_batch = 1) {
+	// ---- node step.  It is several times the cost of a list step, so in lock-step the lanes that need one
+	// wait until `node_batch` of them do (or no lane is inside a list), and then take it together.
+	bool node_step = walking && !W.in_list;
 	if (LOCKSTEP) {
-		const int n_node = popc32(lane_vote(walking && kind == RT_KIND_NODE));
-		const int n_pair = popc32(lane_vote(walking && kind == RT_KIND_PAIR));
-		const int n_leaf = popc32(lane_vote(walking && kind == RT_KIND_LEAF));
-		// the kind most lanes wait for (ties: leaf, then pair - they finish lists, which frees node steps)
-		const int chosen = n_leaf >= n_pair && n_leaf >= n_node ? RT_KIND_LEAF : (n_pair >= n_node ? RT_KIND_PAIR : RT_KIND_NODE);
-		mine = walking && kind == chosen;
+		const unsigned need = lane_vote(node_step), busy = lane_vote(walking && W.in_list);
+		if (busy != 0u && popc32(need) < node_batch) node_step = false;
 	}
-	if (mine && kind == RT_KIND_NODE) {
-		// (a) which node: the next one on the stack, or - stack empty - the next move along the origin chain
-		int rec_node = -1, after = -1;
-		bool push = false, list = false;
+	// (a) which node: the next one on the stack, or - stack empty - the next move along the origin chain
+	int rec_node = -1, after = -1;
+	bool push = false, list = false;
+	if (node_step) {
 		if (W.sp > 0) {
-			rec_node = (int)walk_pop(W, K);
+			rec_node = W.stack[--W.sp];
 			push = list = true;
 		} else if (!W.chain_listed) {
 			// the ray leaves the current origin-chain node, which is returned now (post-order)
@@ -1376,22 +1375,27 @@ RT_HD bool walk_step(const RtDevScene& S, RtWalk& W, const RtWalkStack& K, const
 			W.chain_listed = 0;
 			push = true;
 		}
-		// (b) its 64-byte record: children, then the root of the list's BVH (box test right here)
-		if (rec_node >= 0) {
-			const RtWNode nd = ld(S.node_walk + rec_node);
-			if (push) walk_push_children(W, K, nd, after);
-			else W.chain_up = nd.up;
-			if (list && nd.b != 0 && walk_hits_box(W, nd.lo[0], nd.lo[1], nd.lo[2], nd.hi[0], nd.hi[1], nd.hi[2])) {
-				W.floor = W.sp;
-				W.in_list = 1;
-				W.best = RT_NO_SLOT;
-				walk_push(W, K, (unsigned)nd.a | (nd.b < 0 ? RT_WALK_PAIR : RT_WALK_LEAF));
-			}
+	}
+	if (LOCKSTEP) warp_sync();
+	// (b) its 64-byte record: children, then the root of the list's BVH (box test right here)
+	int leaf0 = -1, leaf1 = -1;  // leaves whose entities are to be tested in this iteration
+	if (rec_node >= 0) {
+		const RtWNode nd = ld(S.node_walk + rec_node);
+		if (push) walk_push_children(W, nd, after);
+		else W.chain_up = nd.up;
+		if (list && nd.b != 0 && walk_hits_box(W, nd.lo[0], nd.lo[1], nd.lo[2], nd.hi[0], nd.hi[1], nd.hi[2])) {
+			W.floor = W.sp;
+			W.in_list = 1;
+			W.best = RT_NO_SLOT;
+			if (nd.b < 0) walk_push(W, nd.a);
+			else leaf0 = nd.a;
 		}
-	} else if (mine && kind == RT_KIND_PAIR) {
-		// the two children of a BVH node are neighbours in memory and are fetched and tested together (half as
-		// many dependent fetches as one node per step)
-		const RtBvhNode* np = S.bvh_nodes + (walk_pop(W, K) & 0x3fffffffu);
+	}
+	if (LOCKSTEP) warp_sync();
+	// ---- list step: the two children of a BVH node are neighbours in memory and are fetched and tested
+	// together (half as many dependent fetches as one node per step)
+	if (walking && W.in_list && W.sp > W.floor) {
+		const RtBvhNode* np = S.bvh_nodes + W.stack[--W.sp];
 		const RtF4 a0 = ld(reinterpret_cast<const RtF4*>(np));
 		const RtI4 a1 = ld(reinterpret_cast<const RtI4*>(np) + 1);
 		const RtF4 b0 = ld(reinterpret_cast<const RtF4*>(np) + 2);
@@ -1399,13 +1403,28 @@ RT_HD bool walk_step(const RtDevScene& S, RtWalk& W, const RtWalkStack& K, const
 		// x0 = lo.xyz, hi.x ; x1 = hi.y, hi.z (as bits), a, b
 		const bool hit_a = walk_hits_box(W, a0.x, a0.y, a0.z, a0.w, int_as_float(a1.x), int_as_float(a1.y));
 		const bool hit_b = walk_hits_box(W, b0.x, b0.y, b0.z, b0.w, int_as_float(b1.x), int_as_float(b1.y));
-		// the right sibling first, so that the left one - which holds the lowest slot - is popped first; an inner
-		// node is skipped when nothing below it can beat the hit we have
-		if (hit_b && (b1.w > 0 || -(b1.w + 1) < W.best)) walk_push(W, K, (unsigned)b1.z | (b1.w < 0 ? RT_WALK_PAIR : RT_WALK_LEAF));
-		if (hit_a && (a1.w > 0 || -(a1.w + 1) < W.best)) walk_push(W, K, (unsigned)a1.z | (a1.w < 0 ? RT_WALK_PAIR : RT_WALK_LEAF));
-	} else if (mine && kind == RT_KIND_LEAF) {
-		walk_leaf(S, W, (int)(walk_pop(W, K) & 0x3fffffffu), o, d);
+		// the right sibling first, so that the left one - which holds the lowest slot - is popped first
+		if (hit_b) {
+			if (b1.w < 0) {
+				if (-(b1.w + 1) < W.best) walk_push(W, b1.z);  // else: nothing below can beat the hit we have
+			} else {
+				leaf1 = b1.z;
+			}
+		}
+		if (hit_a) {
+			if (a1.w < 0) {
+				if (-(a1.w + 1) < W.best) walk_push(W, a1.z);
+			} else {
+				leaf0 = a1.z;
+			}
+		}
 	}
+	if (LOCKSTEP) warp_sync();
+	// ---- leaf entities
+	if (leaf0 >= 0) walk_leaf(S, W, leaf0, o, d);
+	if (LOCKSTEP) warp_sync();
+	if (leaf1 >= 0) walk_leaf(S, W, leaf1, o, d);
+	if (LOCKSTEP) warp_sync();
 	if (walking && W.overflow) walking = false;
 	if (walking && W.in_list && W.sp == W.floor) {  // the list is finished
 		W.in_list = 0;
@@ -1414,7 +1433,6 @@ RT_HD bool walk_step(const RtDevScene& S, RtWalk& W, const RtWalkStack& K, const
 			walking = false;
 		}
 	}
-	if (LOCKSTEP) warp_sync();
 	return walking;
 }
 
@@ -1481,7 +1499,7 @@ RT_HD bool path_finish(const RtDevScene& S, const RtFrame& F, RtPath& P, double*
 #define RT_SEG_WALK 2
 template <bool COUNT>
 RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int primary_slot, double* out, RtCounts& cnt,
-                        uint32_t& err, RtWalk* W, const RtWalkStack* K, int& slot, RtCollision& ci) {
+                        uint32_t& err, RtWalk* W, int& slot, RtCollision& ci) {
 	// walker.set_pos_and_dir -> set_position -> setup_cur_node (src/octree_space.ts:188-205,251-278)
 	if (COUNT) cnt.segments++;
 	slot = -1;
@@ -1511,7 +1529,7 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 	if (P.primary && F.prim_geom) q.rel = F.prim_geom;  // camera rays: origin-relative records
 	if (W) {
 		W->r = q.r;
-		walk_begin(S, *W, *K, P.node, P.octant);
+		walk_begin(S, *W, P.node, P.octant);
 		return RT_SEG_WALK;
 	}
 	if (q.rel && P.have_node) {  // lock-step pre-test of the shared origin chain
@@ -1522,18 +1540,23 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 	return RT_SEG_SLOT;
 }
 
-// after the ordered walk: the collision of the slot it found.  A ray whose stack overflowed (W.overflow: trees much
-// deeper than the stack was sized for) is searched again from scratch by the reference-order walker, which needs no
-// stack - slower, never wrong.
+// A ray whose stack overflowed (W.overflow: trees much deeper than the stack was sized for) is searched again from
+// scratch by the reference-order walker, which needs no stack - slower, never wrong.  Out of line: rare.
+RT_COLD int search_without_stack(const RtDevScene& S, const RtRayF& r, int node, int octant, const double* o, const double* d,
+                                 RtCollision& ci) {
+	RtSearch q;
+	q.r = r;
+	q.rel = nullptr;
+	q.chain_mask = 0xffffffffu;
+	q.chain_levels = 0;
+	RtCounts cnt = {0, 0, 0, 0, 0};
+	return walk_and_scan<false>(S, q, node, octant, o, d, ci, cnt);
+}
+
+// after the ordered walk: the collision of the slot it found
 RT_HD void segment_found(const RtDevScene& S, const RtPath& P, const RtWalk& W, int& slot, RtCollision& ci) {
 	if (W.overflow) {
-		RtSearch q;
-		q.r = W.r;
-		q.rel = nullptr;
-		q.chain_mask = 0xffffffffu;
-		q.chain_levels = 0;
-		RtCounts cnt = {0, 0, 0, 0, 0};
-		slot = walk_and_scan<false>(S, q, P.node, P.octant, P.refpoint, P.dir, ci, cnt);
+		slot = search_without_stack(S, W.r, P.node, P.octant, P.refpoint, P.dir, ci);
 		return;
 	}
 	slot = W.hit;
@@ -1653,21 +1676,15 @@ RT_HD bool path_segment(const RtDevScene& S, const RtFrame& F, RtPath& P, double
 	RtCollision ci;
 	if (!COUNT && S.ordered_ok) {
 		RtWalk W;
-		unsigned stack[RT_WALK_STACK];
-#ifdef RT_TEST_WALK_CAP  // tests/hostsim only: a tiny stack, so that the overflow path (segment_found) is exercised
-		const RtWalkStack K = {stack, 1, RT_TEST_WALK_CAP};
-#else
-		const RtWalkStack K = {stack, 1, RT_WALK_STACK};
-#endif
-		const int r = segment_begin<COUNT>(S, F, P, primary_slot, out, cnt, err, &W, &K, slot, ci);
+		const int r = segment_begin<COUNT>(S, F, P, primary_slot, out, cnt, err, &W, slot, ci);
 		if (r == RT_SEG_DONE) return true;
 		if (r == RT_SEG_WALK) {
-			while (walk_step<false>(S, W, K, P.refpoint, P.dir, true)) {
+			while (walk_iter<false>(S, W, P.refpoint, P.dir, true)) {
 			}
 			segment_found(S, P, W, slot, ci);
 		}
 	} else {
-		if (segment_begin<COUNT>(S, F, P, primary_slot, out, cnt, err, nullptr, nullptr, slot, ci) == RT_SEG_DONE) return true;
+		if (segment_begin<COUNT>(S, F, P, primary_slot, out, cnt, err, nullptr, slot, ci) == RT_SEG_DONE) return true;
 	}
 	return segment_end<COUNT>(S, F, P, pixel_seed, slot, ci, out, cnt, err);
 }

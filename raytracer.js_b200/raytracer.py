@@ -46,10 +46,18 @@ def camera_desc(camera: Camera, reference_extents: bool = False) -> N.CameraDesc
 
 class GpuRaytracer:
     def __init__(self, config: RaytracerConfig, otree: Octree, camera: Camera, ebuffer: ExposureBuffer, rng: RNG,
-                 device: int = -1, reference_extents: bool = False):
+                 device: int = -1, reference_extents: bool = False, n_gpus: int = 1, devices=None):
+        """n_gpus > 1 (or an explicit `devices` list): one process drives all of them behind the same calls
+        (rt_create_multi): the scene is packed once and replicated device to device, trace_frame() shards the
+        frame into interleaved tiles and every GPU stores its tiles straight into the ExposureBuffer."""
         self._lib = N.load()
         self._ctx = C.c_void_p()
-        N.check(None, self._lib.rt_create(int(device), C.byref(self._ctx)))
+        if devices is not None or n_gpus > 1:
+            devs = list(devices) if devices is not None else list(range(n_gpus))
+            arr = (C.c_int32 * len(devs))(*devs)
+            N.check(None, self._lib.rt_create_multi(len(devs), arr, C.byref(self._ctx)))
+        else:
+            N.check(None, self._lib.rt_create(int(device), C.byref(self._ctx)))
         self.config = config.copy()
         self._otree = otree
         self._camera = camera
@@ -82,6 +90,8 @@ class GpuRaytracer:
         eb, cam = self._ebuffer, self._camera
         if (eb.width, eb.height) != (cam.conf.screen_w, cam.conf.screen_h):
             raise IndexError("x or y out of bounds")  # ExposureBuffer.check_bounds
+        if eb.max_exposure_frames >= 0:  # never blend more frames than the ExposureBuffer will count (next_frame)
+            n_frames = max(1, min(n_frames, eb.max_exposure_frames - eb.current_frame))
         p = self.params(n_frames=n_frames, frame_first=eb.current_frame)
         cd = camera_desc(cam, self.reference_extents)
         ids = np.empty(eb.width * eb.height, np.int32) if want_ids else None
