@@ -99,8 +99,11 @@ export function flatten(root: EntityOtree, extra_textures: any[], extra_substanc
 			}
 		} else throw Error(`unsupported Texture subclass ${t.constructor.name}`);
 	});
+	// ImageTexture.image_data holds the decoded channels as doubles in [0,1] (`image_data[index] / 255.0`,
+	// src/texture/texture_image.ts:117-119): the texel pool wants the 8-bit values back (the device divides by 255.0
+	// again on use, the reference's own expression).  Math.round(v * 255) is exact: the values are k / 255.
 	const tx = new Uint8Array(texels * 3); let o = 0;
-	for (const d of pool) { tx.set(d, o); o += d.length; }
+	for (const d of pool) for (const v of d) tx[o++] = Math.round(v * 255);
 	f.texels = tx;
 	f.sub_refractive_index = new Float64Array(sub.size);
 	sub.forEach((i, s: Substance) => { (f.sub_refractive_index as Float64Array)[i] = s.refractive_index; });
@@ -116,18 +119,23 @@ export class GpuRaytracer {
 	private tex!: Map<any, number>;
 	private sub!: Map<any, number>;
 	private pinned?: Float32Array;
+	private n_gpus = 1;
 	/** seed handed to the per-pixel reseed policy (rt_b200.h: rt_params.rng_seed) */
 	rng_seed = 1.0;
 
 	config: RaytracerConfig;
 
-	constructor(config: RaytracerConfig, otree: EntityOtree, camera: Camera, ebuffer: GpuExposureBuffer, rng: RNG, device = -1) {
+	/** n_gpus > 1: ONE process drives that many GPUs behind the same calls (rt_create_multi): the scene is packed once
+	 *  and replicated device to device, trace_frame() shards the frame into interleaved 16x16 tiles and every GPU
+	 *  stores its tiles straight into the ExposureBuffer's Float32Array (page-locked and mapped by the library). */
+	constructor(config: RaytracerConfig, otree: EntityOtree, camera: Camera, ebuffer: GpuExposureBuffer, rng: RNG, device = -1, n_gpus = 1) {
 		this.camera = camera;
 		this.ebuffer = ebuffer;
 		this.otree = otree;
 		this._rng = rng;
 		this.config = Object.assign({}, config);
-		this.ctx = native.create(device);          // throws without a CUDA device: no CPU fallback
+		this.n_gpus = n_gpus;
+		this.ctx = n_gpus > 1 ? native.createMulti(n_gpus) : native.create(device);  // throws without a CUDA device: no CPU fallback
 		this.refresh_scene();
 	}
 
@@ -147,7 +155,8 @@ export class GpuRaytracer {
 	trace_frame(n_frames = 1) {
 		const cam: any = this.camera, conf = cam.conf;    // norm_fr/lf/up, pos, conf are TS-private, plain at run time
 		const eb = this.ebuffer;
-		if (this.pinned !== eb.store) { if (this.pinned) native.unpin(this.ctx, this.pinned); native.pin(this.ctx, eb.store); this.pinned = eb.store; }
+		// one GPU: page-lock the pixel store once so that the copy runs at PCIe rate; a group maps it itself
+		if (this.n_gpus === 1 && this.pinned !== eb.store) { if (this.pinned) native.unpin(this.ctx, this.pinned); native.pin(this.ctx, eb.store); this.pinned = eb.store; }
 		native.render(this.ctx,
 			{ pos: Float64Array.from(cam.pos.v), fr: Float64Array.from(cam.norm_fr.v), lf: Float64Array.from(cam.norm_lf.v),
 			  up: Float64Array.from(cam.norm_up.v), fov_h: conf.fov_h, fov_v: conf.fov_v, width: conf.screen_w, height: conf.screen_h,

@@ -10,6 +10,7 @@
  * Build check here (no Node): gcc -fsyntax-only -Wall -I../../include rt_napi.c   (uses node_api_min.h)
  *
  * Exports:  create(device) -> ctx      (freed by the finalizer of the external)
+ *           createMulti(nGpus) -> ctx  one process, nGpus GPUs behind the same calls (rt_create_multi)
  *           uploadScene(ctx, flat)     flat = the object gpu_raytracer.ts: flatten() builds (typed arrays)
  *           render(ctx, camera, params, pixels: Float32Array, ids?: Int32Array) -> counters | undefined
  *           pin(ctx, Float32Array)     unpin(ctx, Float32Array)
@@ -23,6 +24,7 @@
 #else
 #include "node_api_min.h"
 #endif
+#include <stdio.h>
 #include <string.h>
 
 #include "rt_b200.h"
@@ -48,17 +50,38 @@ static rt_ctx* ctx_of(napi_env env, napi_value v) {
 	return (rt_ctx*)p;
 }
 
-/* typed array property `name` of `obj` -> data pointer (+ element count) */
-static void* ta(napi_env env, napi_value obj, const char* name, size_t* len) {
+/* typed array property `name` of `obj` -> data pointer (+ element count, + element type) */
+static void* ta_typed(napi_env env, napi_value obj, const char* name, size_t* len, napi_typedarray_type* type) {
 	napi_value v;
 	bool is = false;
 	void* data = NULL;
 	size_t n = 0;
 	napi_typedarray_type t;
+	if (len) *len = 0;
 	if (napi_get_named_property(env, obj, name, &v) != napi_ok || napi_is_typedarray(env, v, &is) != napi_ok || !is) return NULL;
 	if (napi_get_typedarray_info(env, v, &t, &n, &data, NULL, NULL) != napi_ok) return NULL;
 	if (len) *len = n;
+	if (type) *type = t;
 	return data;
+}
+static void* ta(napi_env env, napi_value obj, const char* name, size_t* len) { return ta_typed(env, obj, name, len, NULL); }
+/* The flat scene's arrays are indexed by rt_pack_scene with the counts taken from a few of them: every array
+ * must have the element type and EXACTLY the length those counts imply, or the library would read past its end. */
+static void* ta_checked(napi_env env, napi_value obj, const char* name, napi_typedarray_type want, size_t want_len, int* bad) {
+	size_t n = 0;
+	napi_typedarray_type t = want;
+	void* p = ta_typed(env, obj, name, &n, &t);
+	if ((!p && want_len) || t != want || n != want_len) {
+		if (!*bad) {
+			char msg[160];
+			snprintf(msg, sizeof msg, "rt_b200: flat.%s must be a typed array of kind %d with %zu elements (got kind %d, %zu)", name, (int)want,
+			         want_len, (int)t, n);
+			napi_throw_error(env, "ERR_OUT_OF_RANGE", msg);
+		}
+		*bad = 1;
+		return NULL;
+	}
+	return p;
 }
 static double num(napi_env env, napi_value obj, const char* name) {
 	napi_value v;
@@ -90,6 +113,20 @@ static napi_value Create(napi_env env, napi_callback_info info) {
 	return out;
 }
 
+/* createMulti(nGpus) -> ctx driving GPUs 0 .. nGpus-1 from this one process (rt_create_multi) */
+static napi_value CreateMulti(napi_env env, napi_callback_info info) {
+	size_t argc = 1;
+	napi_value argv[1], out;
+	int32_t n_gpus = 1;
+	rt_ctx* ctx = NULL;
+	RT_NAPI_TRY(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc >= 1) napi_get_value_int32(env, argv[0], &n_gpus);
+	rt_status st = rt_create_multi(n_gpus, NULL, &ctx);
+	if (st != RT_OK) return throw_rt(env, NULL, st);
+	RT_NAPI_TRY(env, napi_create_external(env, ctx, finalize_ctx, NULL, &out));
+	return out;
+}
+
 static napi_value UploadScene(napi_env env, napi_callback_info info) {
 	size_t argc = 2, n = 0;
 	napi_value argv[2], flat;
@@ -97,33 +134,52 @@ static napi_value UploadScene(napi_env env, napi_callback_info info) {
 	rt_ctx* ctx = ctx_of(env, argv[0]);
 	flat = argv[1];
 	rt_scene_desc d;
+	int bad = 0;
+	size_t N = 0, L = 0, E = 0, M = 0, T = 0, S = 0, X = 0;
 	memset(&d, 0, sizeof d);
 	d.struct_size = (uint32_t)sizeof d;
-	d.node_pos = (const double*)ta(env, flat, "node_pos", NULL);
-	d.node_size = (const double*)ta(env, flat, "node_size", &n);             d.n_nodes = (uint32_t)n;
-	d.node_child = (const int32_t*)ta(env, flat, "node_child", NULL);
-	d.node_parent = (const int32_t*)ta(env, flat, "node_parent", NULL);
-	d.node_octant = (const int32_t*)ta(env, flat, "node_octant", NULL);
-	d.node_list_off = (const uint32_t*)ta(env, flat, "node_list_off", NULL);
-	d.list_entity = (const uint32_t*)ta(env, flat, "list_entity", &n);       d.n_list = (uint32_t)n;
-	d.ent_type = (const uint8_t*)ta(env, flat, "ent_type", &n);              d.n_entities = (uint32_t)n;
-	d.ent_pos = (const double*)ta(env, flat, "ent_pos", NULL);
-	d.ent_extent = (const double*)ta(env, flat, "ent_extent", NULL);
-	d.ent_material = (const int32_t*)ta(env, flat, "ent_material", NULL);
-	d.ent_texture = (const int32_t*)ta(env, flat, "ent_texture", NULL);
-	d.ent_substance = (const int32_t*)ta(env, flat, "ent_substance", NULL);
-	d.mat_response = (const uint8_t*)ta(env, flat, "mat_response", &n);      d.n_materials = (uint32_t)n;
-	d.mat_light = (const uint8_t*)ta(env, flat, "mat_light", NULL);
-	d.mat_mirror = (const uint8_t*)ta(env, flat, "mat_mirror", NULL);
-	d.mat_roughness = (const double*)ta(env, flat, "mat_roughness", NULL);
-	d.tex_kind = (const uint8_t*)ta(env, flat, "tex_kind", &n);              d.n_textures = (uint32_t)n;
-	d.tex_color = (const double*)ta(env, flat, "tex_color", NULL);
-	d.tex_width = (const int32_t*)ta(env, flat, "tex_width", NULL);
-	d.tex_height = (const int32_t*)ta(env, flat, "tex_height", NULL);
-	d.tex_loaded = (const uint8_t*)ta(env, flat, "tex_loaded", NULL);
-	d.tex_texel_off = (const uint64_t*)ta(env, flat, "tex_texel_off", NULL); /* BigUint64Array */
-	d.texels = (const uint8_t*)ta(env, flat, "texels", &n);                  d.n_texels = n / 3;
-	d.sub_refractive_index = (const double*)ta(env, flat, "sub_refractive_index", &n); d.n_substances = (uint32_t)n;
+	/* the counts come from one array per table; every other array is checked against them */
+	ta(env, flat, "node_size", &N);
+	ta(env, flat, "list_entity", &L);
+	ta(env, flat, "ent_type", &E);
+	ta(env, flat, "mat_response", &M);
+	ta(env, flat, "tex_kind", &T);
+	ta(env, flat, "sub_refractive_index", &S);
+	ta(env, flat, "texels", &X);
+	(void)n;
+	d.n_nodes = (uint32_t)N; d.n_list = (uint32_t)L; d.n_entities = (uint32_t)E; d.n_materials = (uint32_t)M;
+	d.n_textures = (uint32_t)T; d.n_substances = (uint32_t)S; d.n_texels = X / 3;
+#define RT_TA(field, ctype, kind, len) d.field = (const ctype*)ta_checked(env, flat, #field, kind, (len), &bad)
+	RT_TA(node_pos, double, napi_float64_array, 3 * N);
+	RT_TA(node_size, double, napi_float64_array, N);
+	RT_TA(node_child, int32_t, napi_int32_array, 8 * N);
+	RT_TA(node_parent, int32_t, napi_int32_array, N);
+	RT_TA(node_octant, int32_t, napi_int32_array, N);
+	RT_TA(node_list_off, uint32_t, napi_uint32_array, N + 1);
+	RT_TA(list_entity, uint32_t, napi_uint32_array, L);
+	RT_TA(ent_type, uint8_t, napi_uint8_array, E);
+	RT_TA(ent_pos, double, napi_float64_array, 3 * E);
+	RT_TA(ent_extent, double, napi_float64_array, E);
+	RT_TA(ent_material, int32_t, napi_int32_array, E);
+	RT_TA(ent_texture, int32_t, napi_int32_array, E);
+	RT_TA(ent_substance, int32_t, napi_int32_array, E);
+	RT_TA(mat_response, uint8_t, napi_uint8_array, M);
+	RT_TA(mat_light, uint8_t, napi_uint8_array, M);
+	RT_TA(mat_mirror, uint8_t, napi_uint8_array, M);
+	RT_TA(mat_roughness, double, napi_float64_array, M);
+	RT_TA(tex_kind, uint8_t, napi_uint8_array, T);
+	RT_TA(tex_color, double, napi_float64_array, 4 * T);
+	RT_TA(tex_width, int32_t, napi_int32_array, T);
+	RT_TA(tex_height, int32_t, napi_int32_array, T);
+	RT_TA(tex_loaded, uint8_t, napi_uint8_array, T);
+	RT_TA(tex_texel_off, uint64_t, napi_biguint64_array, T);
+	RT_TA(texels, uint8_t, napi_uint8_array, X);
+	RT_TA(sub_refractive_index, double, napi_float64_array, S);
+#undef RT_TA
+	if (bad || X % 3 != 0) {
+		if (!bad) napi_throw_error(env, "ERR_OUT_OF_RANGE", "rt_b200: flat.texels must hold RGB triples");
+		return NULL;
+	}
 	rt_status st = rt_scene_upload(ctx, &d);
 	if (st != RT_OK) return throw_rt(env, ctx, st);
 	return NULL;
@@ -162,8 +218,14 @@ static napi_value Render(napi_env env, napi_callback_info info) {
 	}
 	if (argc >= 5) {
 		bool is = false;
-		if (napi_is_typedarray(env, argv[4], &is) == napi_ok && is)
+		if (napi_is_typedarray(env, argv[4], &is) == napi_ok && is) {
 			RT_NAPI_TRY(env, napi_get_typedarray_info(env, argv[4], &t, &nid, &ids, NULL, NULL));
+			/* rt_render writes width*height int32 into it: anything else would be a write past the array's end */
+			if (t != napi_int32_array || nid != npx / 3) {
+				napi_throw_error(env, "ERR_OUT_OF_RANGE", "rt_b200: ids must be an Int32Array of width * height elements");
+				return NULL;
+			}
+		}
 	}
 	rt_counters cnt;
 	rt_status st = rt_render(ctx, &cam, &prm, 0, (float*)rgb, (int32_t*)ids, want_counters ? &cnt : NULL);
@@ -229,6 +291,7 @@ static napi_value Unpin(napi_env env, napi_callback_info info) { return PinOrUnp
 napi_value napi_register_module_v1(napi_env env, napi_value exports) {
 	const napi_property_descriptor props[] = {
 	    {"create", NULL, Create, NULL, NULL, NULL, napi_default, NULL},
+	    {"createMulti", NULL, CreateMulti, NULL, NULL, NULL, napi_default, NULL},
 	    {"uploadScene", NULL, UploadScene, NULL, NULL, NULL, napi_default, NULL},
 	    {"render", NULL, Render, NULL, NULL, NULL, napi_default, NULL},
 	    {"present", NULL, Present, NULL, NULL, NULL, napi_default, NULL},

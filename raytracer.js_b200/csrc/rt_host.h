@@ -305,6 +305,38 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 	}
 	hs.err_l = (float)(16.0 * 1.1920929e-7 * scale);
 	{
+		// The two geometric invariants every walker here relies on to be exact (the reference's own walker only needs
+		// the links): a child's cell IS the parent's octant, and every entity's cubic AABB lies inside its node's cube
+		// (what add_entity_to_octree guarantees, src/octree_entity.ts:60-79,174-188).  A tree from another flattener,
+		// or one whose entities were moved without being re-inserted, would render differently here without an error:
+		// it is refused instead.  float64, O(nodes + entities), tolerance = a few ulps of the coordinate scale.
+		const double tol = 1e-12 * (scale > 0 ? scale : 1.0);
+		for (uint32_t i = 1; i < N; i++) {
+			const int par = sc->node_parent[i], oc = sc->node_octant[i];
+			const double ps = sc->node_size[par], half = ps / 2;
+			if (std::fabs(sc->node_size[i] - half) > tol) RT_FAIL(RT_ERR_INVALID, "node %u: size %.17g is not half of its parent's %.17g", i, sc->node_size[i], ps);
+			for (int k = 0; k < 3; k++) {
+				const double want = sc->node_pos[3 * (size_t)par + k] + (((oc >> k) & 1) ? half : 0.0);
+				if (std::fabs(sc->node_pos[3 * (size_t)i + k] - want) > tol)
+					RT_FAIL(RT_ERR_INVALID, "node %u: its cell is not octant %d of its parent's cube (axis %d: %.17g, expected %.17g)", i, oc, k,
+					        sc->node_pos[3 * (size_t)i + k], want);
+			}
+		}
+		for (uint32_t i = 0; i < N; i++) {
+			const double* np = sc->node_pos + 3 * (size_t)i;
+			const double ns = sc->node_size[i];
+			for (uint32_t li = sc->node_list_off[i]; li < sc->node_list_off[i + 1]; li++) {
+				const uint32_t e = sc->list_entity[li];
+				const double* p = sc->ent_pos + 3 * (size_t)e;
+				const double h = sc->ent_extent[e] / 2;
+				for (int k = 0; k < 3; k++)
+					if (p[k] - h < np[k] - tol || p[k] + h > np[k] + ns + tol)
+						RT_FAIL(RT_ERR_INVALID, "entity %u sticks out of the cube of node %u that lists it (axis %d): re-insert moved entities "
+						                        "(add_entity_to_octree) before uploading", e, i, k);
+			}
+		}
+	}
+	{
 		// The search runs in float32 (RT_PRECISION_F32): a cell's corners and centre must be distinct float32
 		// numbers at the scene's coordinate scale, or the walkers cannot tell neighbouring cells apart.  With a
 		// unit root that is 23 levels; the reference (float64 throughout) has no such limit.
