@@ -113,32 +113,6 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 #ifndef RT_A_MINB
 #define RT_A_MINB 5
 #endif
-// Ray generation rides along in the same launch: the first F.raygen_jobs tickets of the dispenser are groups of 32
-// half rows (rt_trace.cuh: raygen_half_row, the generator's iterated rotations - FP64-issue bound, ~30 us at 1080p
-// for 68 warps of the ~3000 resident ones), which publish their progress every 16 columns with release stores; the
-// packets are handed out column by column from the MIDDLE tile column outwards, the order in which the rows grow, so
-// a packet's directions are in the table long before its ticket comes up (the wait below is a formality except for
-// the first few packets).  All CTAs of the persistent grid are resident, and the ray-generation tickets are taken
-// before any packet ticket: no packet can wait for a job that is not already running.
-RT_D void wait_for_rows(const RtFrame& F, int x_lo, int x_hi, int y_lo, int n_rows) {
-	const int lane = threadIdx.x & 31;
-	const int r = lane & 15, half = lane >> 4, y = y_lo + r, xc = F.width >> 1;
-	x_hi = min(x_hi, F.width - 1);
-	int need = 0;
-	if (r < n_rows && y < F.height) need = half ? (x_lo < xc ? xc - x_lo : 0) : (x_hi >= xc ? x_hi - xc + 1 : 0);
-	if (need > 0) {
-		const unsigned* flag = F.raygen_progress + 2 * y + half;
-		unsigned v;
-		// (with a pause between polls: thousands of warps polling the L2 without one starve the very stores they wait for)
-		for (;;) {
-			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-			if (v >= (unsigned)need) break;
-			__nanosleep(400);
-		}
-	}
-	__syncwarp();
-}
-
 template <int PPL, int MINB>
 __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
     rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_packets) {
@@ -147,43 +121,20 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
 	__shared__ __align__(16) float stages[RT_A_WARPS][96];
 	constexpr int PER_TILE = 8 / PPL;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int band_row0 = F.tile_begin / tiles_x, band_rows = (F.tile_end - F.tile_begin) / tiles_x;
-	const unsigned n_jobs = (unsigned)F.raygen_jobs;
 	uint32_t err = 0;
 	while (true) {
 		unsigned p = 0;
 		if (lane == 0) p = atomicAdd(F.work_counter, 1u);
 		p = __shfl_sync(0xffffffffu, p, 0);
-		if (p >= n_jobs + (unsigned)n_packets) break;
-		if (p < n_jobs) {  // ---- ray generation for the half rows 32 p ... 32 p + 31
-			const int t = (int)p * 32 + lane;
-			if (t < 2 * F.height) {
-				const int y = t >> 1, half = t & 1;
-				unsigned* flag = F.raygen_progress + t;
-				RtD4* out = const_cast<RtD4*>(F.dirs) + (size_t)y * F.width;
-				const int row_tile = (y / RT_TILE_H) * tiles_x;
-				auto publish = [&](int n) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"((unsigned)n) : "memory"); };
-				if (F.tile_world > 1)
-					raygen_half_row(F, y, half, out, [&](int x) { return (row_tile + x / RT_TILE_W) % F.tile_world == F.tile_rank; }, publish);
-				else
-					raygen_half_row(F, y, half, out, [](int) { return true; }, publish);
-			}
-			__syncwarp();
-			continue;
-		}
-		// ---- a packet: tiles of the band column by column, from the middle column outwards
-		p -= n_jobs;
-		const int ka = (int)(p / PER_TILE);
-		const int c = ka / band_rows, ty = band_row0 + (ka - c * band_rows);
-		const int tx = (c & 1) ? (tiles_x >> 1) - ((c + 1) >> 1) : (tiles_x >> 1) + (c >> 1);
-		const int tile = ty * tiles_x + tx;
-		if (tile % F.tile_world != F.tile_rank) continue;
+		if (p >= (unsigned)n_packets) break;
+		const int k = (int)(p / PER_TILE);
+		const int tile = F.tile_begin + F.tile_rank + k * F.tile_world;
+		if (tile >= F.tile_end) continue;
 		RtPatch pt;
-		pt.x0 = tx * RT_TILE_W;
-		pt.y0 = ty * RT_TILE_H;
+		pt.x0 = (tile % tiles_x) * RT_TILE_W;
+		pt.y0 = (tile / tiles_x) * RT_TILE_H;
 		pt.sub0 = (int)(p % PER_TILE) * PPL;
-		pt.out_base = (size_t)(tile / F.tile_world) * RT_BLOCK;
-		if (F.raygen_progress) wait_for_rows(F, pt.x0, pt.x0 + RT_TILE_W - 1, pt.y0 + (pt.sub0 >> 1) * 4, PPL * 2);
+		pt.out_base = (size_t)k * RT_BLOCK;
 		primary_patch<PPL>(S, F, pt, stacks[warp], rays[warp], stages[warp], err);
 	}
 	if (err) atomicOr(F.error_flags, err);
@@ -730,7 +681,6 @@ struct rt_ctx {
 	int primary_minb = RT_A_MINB;                // tuning knob RT_B200_PRIMARY_MINB=4|5|6: resident CTAs per SM the primary stage is compiled for
 	int bounce_min_walking = 12;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
 	int resample_min_frames = 8;                 // tuning knob RT_B200_RESAMPLE_MIN
-	bool fuse_raygen = true;                     // tuning knob RT_B200_FUSE_RAYGEN=0: ray generation as a kernel of its own
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
 	int bounce_minb = 8;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
 	int bounce_node_batch = 4;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
@@ -847,9 +797,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	// u64 cells: [0..7] work counters, [8] error flags, then per band {patch dispenser, queue count, queue cursor,
 	// resample queue count, resample queue cursor}
 	n_bands = std::max(1, std::min(n_bands, RT_MAX_BANDS));
-	// ... then the ray-generation progress flags, 2 x height x u32
-	const size_t n_ctl_cells = 9 + 5 * RT_MAX_BANDS;
-	const size_t n_cells = n_ctl_cells + (size_t)cam->height;
+	const size_t n_cells = 9 + 5 * RT_MAX_BANDS;
 	RT_CUDA(ctx, ctx->counters.alloc(n_cells));
 	F.counters = ctx->counters.p;
 	F.error_flags = reinterpret_cast<uint32_t*>(ctx->counters.p + 8);
@@ -939,7 +887,6 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 		// Per camera pose (a captured frame repeats the call before it and inherits both): the origin-relative records
 		// and the ray generation (the generator's iterated rotations, 3 lanes per half row).  The directions depend on
 		// the camera's basis only: a camera that merely moved (the reference's WASD keys, src/main.ts:296-330) keeps them.
-		bool raygen_fused = false;
 		if (!capture) {
 			if (prim) {
 				rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
@@ -954,15 +901,11 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 			rk.fov_h = cam->fov_h; rk.fov_v = cam->fov_v; rk.width = cam->width; rk.height = cam->height; rk.flags = cam->flags;
 			rk.rank = tile_rank; rk.world = tile_world; rk.dirs = ctx->dirs.p;
 			if (!ctx->raygen_key_valid || memcmp(&rk, &ctx->raygen_key, sizeof rk) != 0) {
-				if (pipeline && ctx->fuse_raygen) {
-					raygen_fused = true;  // inside the primary stage's launch (rt_primary_kernel: the first tickets of its dispenser)
-				} else {
-					const int lanes = 6 * F.height;  // (row, half, component)
-					rt_raygen_kernel<<<(lanes + RT_RAYGEN_THREADS - 1) / RT_RAYGEN_THREADS, RT_RAYGEN_THREADS, 0, ctx->stream>>>(F, ctx->dirs.p, tiles_x);
-					ctx->launches++;
-					ctx->stage_ran[0] = prof;
-					RT_CUDA(ctx, cudaGetLastError());
-				}
+				const int lanes = 6 * F.height;  // (row, half, component)
+				rt_raygen_kernel<<<(lanes + RT_RAYGEN_THREADS - 1) / RT_RAYGEN_THREADS, RT_RAYGEN_THREADS, 0, ctx->stream>>>(F, ctx->dirs.p, tiles_x);
+				ctx->launches++;
+				ctx->stage_ran[0] = prof;
+				RT_CUDA(ctx, cudaGetLastError());
 				ctx->raygen_key = rk;
 				ctx->raygen_key_valid = true;
 			}
@@ -989,11 +932,8 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				// primary stage (packet walk) -> shade stage -> bounce stage over the continuation queue
 				F.queue = ctx->queue.p + F.out_first;
 				F.vqueue = resample ? ctx->vqueue.p + F.out_first : nullptr;
-				// the dispenser walks ALL tiles of the band (middle column outwards); a rank skips the tiles of the others
-				const int n_packets = band_tiles * (8 / ppl);
-				F.raygen_jobs = raygen_fused && band == 0 ? (2 * F.height + 31) / 32 : 0;
-				F.raygen_progress = raygen_fused && band == 0 ? reinterpret_cast<unsigned*>(ctx->counters.p + n_ctl_cells) : nullptr;
-				const int blocks = std::min(grid_primary, (my_tiles * (8 / ppl) + F.raygen_jobs + RT_A_WARPS - 1) / RT_A_WARPS);
+				const int n_packets = my_tiles * (8 / ppl);
+				const int blocks = std::min(grid_primary, (n_packets + RT_A_WARPS - 1) / RT_A_WARPS);
 				void* args[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x, (void*)&n_packets};
 				RT_CUDA(ctx, cudaLaunchKernel(primary_kernel, dim3(blocks), dim3(RT_A_WARPS * 32), args, 0, ctx->stream));
 				ctx->launches++;
@@ -1304,7 +1244,6 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 		if (v >= 1 && v <= 32) ctx->bounce_min_walking = v;
 	}
 	if (const char* e = getenv("RT_B200_RESAMPLE")) ctx->resample = atoi(e) != 0;
-	if (const char* e = getenv("RT_B200_FUSE_RAYGEN")) ctx->fuse_raygen = atoi(e) != 0;
 	if (const char* e = getenv("RT_B200_RESAMPLE_MIN")) ctx->resample_min_frames = std::max(2, atoi(e));
 	if (const char* e = getenv("RT_B200_BOUNCE_MINB")) {
 		const int v = atoi(e);

@@ -144,11 +144,6 @@ struct RtFrame {
 	const RtD4* row_fr;  // [height] fr rotated towards up by the accumulated vertical scan rotation (host-built)
 	const RtD4* dirs;    // [height][width] the generator's direction of every pixel, bit for bit (xyz; w unused)
 	double scan_cos, scan_sin;  // rot_scan_h_v: cos / sin of fov_h / width
-	// Ray generation inside the primary stage: the first raygen_jobs tickets of the work dispenser are groups of 32
-	// half rows; raygen_progress[2*y + half] = columns of that half row produced so far (release stores), which the
-	// packets wait for before they read their pixels' directions.  0 / null: the table is already complete.
-	int raygen_jobs;
-	unsigned* raygen_progress;
 	int width, height;
 	// start state shared by all primary rays (src/raytracer.ts:309-313)
 	int start_node, start_octant;  // start_node < 0: camera outside the root cube

@@ -794,9 +794,8 @@ RT_HD void rotate_pair(double* a, double* b, double c, double s) {
 // (half == 0) yields x = width>>1, ... , width-1 rotating AFTER every yield by rot_scan_h_v, the left half
 // (half == 1) rotates by the counter-clockwise rotation FIRST and yields x = (width>>1)-1, ..., 0.
 // own(x): whether this rank stores pixel x of the row (tile sharding); `out` is the row of the table.
-// publish(n): the first n columns of this half row are in the table (called every 16 columns and at the end).
-template <class Own, class Publish>
-RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own, Publish publish) {
+template <class Own>
+RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own) {
 	const RtD4 r = ld(F.row_fr + y);
 	double fr[3] = {r.x, r.y, r.z}, lf[3] = {F.lf[0], F.lf[1], F.lf[2]};
 	const int x0 = F.width >> 1;
@@ -807,13 +806,8 @@ RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own
 	if (half) rotate_pair(fr, lf, F.scan_cos, s);
 	for (int i = 0, x = first; i < n; i++, x += step) {
 		if (own(x)) out[x] = RtD4{fr[0], fr[1], fr[2], 0.0};
-		if (((i + 1) & 15) == 0 || i + 1 == n) publish(i + 1);
 		rotate_pair(fr, lf, F.scan_cos, s);
 	}
-}
-template <class Own>
-RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own) {
-	raygen_half_row(F, y, half, out, own, [](int) {});
 }
 
 // The same for ONE component of the direction (rotate_vectors never mixes components): what one lane of
