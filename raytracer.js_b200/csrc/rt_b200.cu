@@ -20,28 +20,15 @@
 #define RT_TILE_H 16
 #define RT_BLOCK (RT_TILE_W * RT_TILE_H)
 
-// Per-frame preparation for camera rays: the origin-relative copy of the slot geometry.  The
-// subtraction centre - camera is done in float64 (no cancellation), then rounded once.
-__global__ void rt_prepare_primary_kernel(const __grid_constant__ RtDevScene S, double ox, double oy, double oz,
-                                          RtF4* __restrict__ out) {
-	const int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= S.n_slots) return;
-	const RtF4 r = make_prim_record(ld(S.slot_geom64 + s), ld(S.slot_geom + s).w > 0.0f, ox, oy, oz, S.err_l);
-	out[s] = r;
-}
-
 // Ray generation: Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250) for the whole frame.  The generator
 // ITERATES a rotation along every row, outwards from the middle column; in floating point that recurrence has no
 // closed form with the same bits, and after three mirror bounces off millimetre spheres a last-bit difference of a
 // camera direction is a different path.  So the recurrence itself runs here.  rotate_vectors works component by
 // component - (fr[k], lf[k]) <- (fr[k] c + lf[k] s, -fr[k] s + lf[k] c) -, so a half row is THREE independent
 // recurrences: one lane per (row, half, component), 6 x height lanes, width / 2 dependent steps of 4 multiplications
-// and 2 additions each (the kernel is bound by FP64 issue and latency: a third of the instructions per lane is three
-// times faster), every direction stored once, 32 B per pixel.
-#define RT_RAYGEN_THREADS 96
-__global__ void __launch_bounds__(RT_RAYGEN_THREADS)
-    rt_raygen_kernel(const __grid_constant__ RtFrame F, RtD4* __restrict__ dirs, int tiles_x) {
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// and 2 additions each (latency bound: ~29 cycles per step), every direction stored once, 32 B per pixel.
+#define RT_SETUP_THREADS 96
+RT_D void raygen_lane(const RtFrame& F, RtD4* __restrict__ dirs, int tiles_x, int t) {
 	if (t >= 6 * F.height) return;
 	const int comp = t % 3, half = (t / 3) & 1, y = t / 6;
 	double* out = reinterpret_cast<double*>(dirs + (size_t)y * F.width) + comp;
@@ -50,6 +37,33 @@ __global__ void __launch_bounds__(RT_RAYGEN_THREADS)
 		raygen_half_row_component(F, y, half, comp, out, [&](int x) { return (row_tile + x / RT_TILE_W) % F.tile_world == F.tile_rank; });
 	else
 		raygen_half_row_component(F, y, half, comp, out, [](int) { return true; });
+}
+__global__ void __launch_bounds__(RT_SETUP_THREADS)
+    rt_raygen_kernel(const __grid_constant__ RtFrame F, RtD4* __restrict__ dirs, int tiles_x) {
+	raygen_lane(F, dirs, tiles_x, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// Everything a frame needs before its first ray, in ONE launch (three launches and their gaps would be a tenth of
+// the headline frame): block 0 zeroes the control cells (work counters, error flags, dispensers, queue cursors); the
+// next raygen_blocks blocks are the ray generation (skipped when the camera's basis has not changed: 0 blocks); the
+// rest compute the per-frame origin-relative copy of the slot geometry for camera rays (centre - camera in float64,
+// no cancellation, rounded once; skipped without primary records: 0 blocks).
+__global__ void __launch_bounds__(RT_SETUP_THREADS)
+    rt_frame_setup_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, unsigned long long* __restrict__ cells,
+                          int n_cells, int raygen_blocks, RtD4* __restrict__ dirs, int tiles_x, RtF4* __restrict__ prim_out) {
+	int b = (int)blockIdx.x;
+	if (b == 0) {
+		for (int i = threadIdx.x; i < n_cells; i += RT_SETUP_THREADS) cells[i] = 0ull;
+		return;
+	}
+	b -= 1;
+	if (b < raygen_blocks) {
+		raygen_lane(F, dirs, tiles_x, b * RT_SETUP_THREADS + (int)threadIdx.x);
+		return;
+	}
+	const int s = (b - raygen_blocks) * RT_SETUP_THREADS + (int)threadIdx.x;
+	if (s >= S.n_slots) return;
+	prim_out[s] = make_prim_record(ld(S.slot_geom64 + s), ld(S.slot_geom + s).w > 0.0f, F.pos[0], F.pos[1], F.pos[2], S.err_l);
 }
 
 // Persistent warps: the grid is sized to the resident capacity of the GPU (SMs x CTAs/SM) and every
@@ -765,21 +779,32 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	}
 
 	// ---- host preparation and every allocation (nothing below this block allocates: it may be captured)
+	// Ray generation is per camera BASIS (and frame, and shard): the directions do not depend on where the camera
+	// stands, so a camera that merely moved (the reference's WASD keys, src/main.ts:296-330) keeps its table.
 	const size_t n_row = cam->height;
-	if (ctx->stage_cap < n_row * sizeof(RtD4)) {
-		if (ctx->stage) cudaFreeHost(ctx->stage);
-		ctx->stage = nullptr;
-		ctx->stage_cap = 0;
-		RT_CUDA(ctx, cudaMallocHost(&ctx->stage, n_row * sizeof(RtD4)));
-		ctx->stage_cap = n_row * sizeof(RtD4);
-	}
-	RT_CUDA(ctx, cudaEventSynchronize(ctx->stage_free));  // the previous frame's table copy has left the staging
-	double scan_cos = 1.0, scan_sin = 0.0;
-	rt_build_camera_rows(*cam, ctx->h_row_fr, scan_cos, scan_sin);
-	RtD4* st_row = reinterpret_cast<RtD4*>(ctx->stage);
-	memcpy(st_row, ctx->h_row_fr.data(), n_row * sizeof(RtD4));
 	RT_CUDA(ctx, ctx->row_fr.alloc(n_row));
 	RT_CUDA(ctx, ctx->dirs.alloc((size_t)cam->width * cam->height));
+	RaygenKey rk;
+	memset(&rk, 0, sizeof rk);
+	memcpy(rk.basis, cam->fr, sizeof cam->fr); memcpy(rk.basis + 3, cam->lf, sizeof cam->lf); memcpy(rk.basis + 6, cam->up, sizeof cam->up);
+	rk.fov_h = cam->fov_h; rk.fov_v = cam->fov_v; rk.width = cam->width; rk.height = cam->height; rk.flags = cam->flags;
+	rk.rank = tile_rank; rk.world = tile_world; rk.dirs = ctx->dirs.p;
+	const bool need_raygen = !capture && (!ctx->raygen_key_valid || memcmp(&rk, &ctx->raygen_key, sizeof rk) != 0);
+	double scan_cos = 1.0, scan_sin = 0.0;
+	RtD4* st_row = nullptr;
+	if (need_raygen) {
+		if (ctx->stage_cap < n_row * sizeof(RtD4)) {
+			if (ctx->stage) cudaFreeHost(ctx->stage);
+			ctx->stage = nullptr;
+			ctx->stage_cap = 0;
+			RT_CUDA(ctx, cudaMallocHost(&ctx->stage, n_row * sizeof(RtD4)));
+			ctx->stage_cap = n_row * sizeof(RtD4);
+		}
+		RT_CUDA(ctx, cudaEventSynchronize(ctx->stage_free));  // the previous table copy has left the staging
+		rt_build_camera_rows(*cam, ctx->h_row_fr, scan_cos, scan_sin);
+		st_row = reinterpret_cast<RtD4*>(ctx->stage);
+		memcpy(st_row, ctx->h_row_fr.data(), n_row * sizeof(RtD4));
+	}
 	RtFrame F{};
 	std::string err;
 	if (rt_status st = rt_fill_frame(ctx->host_ref(), cam, prm, F, err)) return fail(ctx, st, err);
@@ -873,42 +898,33 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	auto enqueue = [&]() -> rt_status {
 		// A captured frame repeats the call before it (same camera, same scene): the scan tables and the
 		// origin-relative records that call left on the device are this frame's, so the graph holds neither.
-		if (!capture) {
+		if (need_raygen) {
 			RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, st_row, n_row * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
 			RT_CUDA(ctx, cudaEventRecord(ctx->stage_free, ctx->stream));
 		}
-		RT_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, n_cells * sizeof(unsigned long long), ctx->stream));
 		const bool prof = ctx->profile && !capture && n_bands == 1;
 		for (int k = 0; k < RT_N_STAGES; k++) ctx->stage_ran[k] = false;
 		auto mark = [&](int stage) -> cudaError_t {  // event before stage `stage` (= after the one before it)
 			return prof ? cudaEventRecord(ctx->stage_ev[stage], ctx->stream) : cudaSuccess;
 		};
 		RT_CUDA(ctx, mark(0));
-		// Per camera pose (a captured frame repeats the call before it and inherits both): the origin-relative records
-		// and the ray generation (the generator's iterated rotations, 3 lanes per half row).  The directions depend on
-		// the camera's basis only: a camera that merely moved (the reference's WASD keys, src/main.ts:296-330) keeps them.
-		if (!capture) {
-			if (prim) {
-				rt_prepare_primary_kernel<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(ctx->dev, cam->pos[0], cam->pos[1],
-				                                                                         cam->pos[2], ctx->prim_geom.p);
-				ctx->launches++;
-				ctx->stage_ran[0] = prof;
-				RT_CUDA(ctx, cudaGetLastError());
-			}
-			RaygenKey rk;
-			memset(&rk, 0, sizeof rk);
-			memcpy(rk.basis, cam->fr, sizeof cam->fr); memcpy(rk.basis + 3, cam->lf, sizeof cam->lf); memcpy(rk.basis + 6, cam->up, sizeof cam->up);
-			rk.fov_h = cam->fov_h; rk.fov_v = cam->fov_v; rk.width = cam->width; rk.height = cam->height; rk.flags = cam->flags;
-			rk.rank = tile_rank; rk.world = tile_world; rk.dirs = ctx->dirs.p;
-			if (!ctx->raygen_key_valid || memcmp(&rk, &ctx->raygen_key, sizeof rk) != 0) {
-				const int lanes = 6 * F.height;  // (row, half, component)
-				rt_raygen_kernel<<<(lanes + RT_RAYGEN_THREADS - 1) / RT_RAYGEN_THREADS, RT_RAYGEN_THREADS, 0, ctx->stream>>>(F, ctx->dirs.p, tiles_x);
-				ctx->launches++;
-				ctx->stage_ran[0] = prof;
-				RT_CUDA(ctx, cudaGetLastError());
+		// Frame setup, one launch: the control cells are zeroed; per camera POSE (a captured frame repeats the call
+		// before it and inherits it) the origin-relative records; per camera BASIS the ray generation - the directions
+		// do not depend on where the camera stands, so a camera that merely moved (the reference's WASD keys,
+		// src/main.ts:296-330) keeps its table.
+		{
+			int raygen_blocks = 0, prep_blocks = 0;
+			if (!capture && prim) prep_blocks = (n_slots + RT_SETUP_THREADS - 1) / RT_SETUP_THREADS;
+			if (need_raygen) {
+				raygen_blocks = (6 * F.height + RT_SETUP_THREADS - 1) / RT_SETUP_THREADS;
 				ctx->raygen_key = rk;
 				ctx->raygen_key_valid = true;
 			}
+			rt_frame_setup_kernel<<<1 + raygen_blocks + prep_blocks, RT_SETUP_THREADS, 0, ctx->stream>>>(
+			    ctx->dev, F, ctx->counters.p, (int)n_cells, raygen_blocks, ctx->dirs.p, tiles_x, ctx->prim_geom.p);
+			ctx->launches++;
+			ctx->stage_ran[0] = prof;
+			RT_CUDA(ctx, cudaGetLastError());
 		}
 		RT_CUDA(ctx, mark(1));
 		for (int band = 0; band < n_bands; band++) {
@@ -1555,7 +1571,7 @@ rt_status rt_camera_directions(rt_ctx* ctx, const rt_camera* cam, double* dirs) 
 	RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, rows.data(), rows.size() * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
 	F.row_fr = ctx->row_fr.p;
 	ctx->raygen_key_valid = false;
-	rt_raygen_kernel<<<(6 * F.height + RT_RAYGEN_THREADS - 1) / RT_RAYGEN_THREADS, RT_RAYGEN_THREADS, 0, ctx->stream>>>(F, ctx->dirs.p, (F.width + RT_TILE_W - 1) / RT_TILE_W);
+	rt_raygen_kernel<<<(6 * F.height + RT_SETUP_THREADS - 1) / RT_SETUP_THREADS, RT_SETUP_THREADS, 0, ctx->stream>>>(F, ctx->dirs.p, (F.width + RT_TILE_W - 1) / RT_TILE_W);
 	ctx->launches++;
 	RT_CUDA(ctx, cudaGetLastError());
 	std::vector<RtD4> host(npx);

@@ -810,8 +810,10 @@ RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own
 	}
 }
 
-// The same for ONE component of the direction (rotate_vectors never mixes components): what one lane of
-// rt_raygen_kernel runs.  `out` points at that component of the row's first record (stride 4 doubles).
+// The same for ONE component of the direction (rotate_vectors never mixes components): what one lane of the
+// ray-generation kernel runs.  `out` points at that component of the row's first record (stride 4 doubles); the
+// lane of component 2 stores the unused fourth double with it, so that the three lanes of a pixel together write a
+// whole 32-byte sector (a 24-byte write would make the L2 fetch the sector first).
 template <class Own>
 RT_HD void raygen_half_row_component(const RtFrame& F, int y, int half, int comp, double* out, Own own) {
 	const RtD4 r = ld(F.row_fr + y);
@@ -825,7 +827,14 @@ RT_HD void raygen_half_row_component(const RtFrame& F, int y, int half, int comp
 		b = yy;
 	}
 	for (int i = 0, x = first; i < n; i++, x += step) {
-		if (own(x)) out[(size_t)x * 4] = a;
+		if (own(x)) {
+#if defined(__CUDACC__)
+			if (comp == 2) *reinterpret_cast<double2*>(out + (size_t)x * 4) = make_double2(a, 0.0);
+			else out[(size_t)x * 4] = a;
+#else
+			out[(size_t)x * 4] = a;
+#endif
+		}
 		const double na = xadd(xmul(a, c), xmul(b, s)), nb = xadd(xmul(a, -s), xmul(b, c));
 		a = na;
 		b = nb;
