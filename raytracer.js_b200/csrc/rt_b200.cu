@@ -26,21 +26,22 @@
 // camera direction is a different path.  So the recurrence itself runs here.  rotate_vectors works component by
 // component - (fr[k], lf[k]) <- (fr[k] c + lf[k] s, -fr[k] s + lf[k] c) -, so a half row is THREE independent
 // recurrences: one lane per (row, half, component), 6 x height lanes, width / 2 dependent steps of 4 multiplications
-// and 2 additions each (latency bound: ~29 cycles per step), every direction stored once, 32 B per pixel.
+// and 2 additions each (latency bound: ~25 cycles per step); every 8th state is kept (rt_common.h: RtFrame.ray_ck).
 #define RT_SETUP_THREADS 96
-RT_D void raygen_lane(const RtFrame& F, RtD4* __restrict__ dirs, int tiles_x, int t) {
+RT_D void raygen_lane(const RtFrame& F, double* __restrict__ ck, int t) {
 	if (t >= 6 * F.height) return;
-	const int comp = t % 3, half = (t / 3) & 1, y = t / 6;
-	double* out = reinterpret_cast<double*>(dirs + (size_t)y * F.width) + comp;
-	const int row_tile = (y / RT_TILE_H) * tiles_x;
-	if (F.tile_world > 1)
-		raygen_half_row_component(F, y, half, comp, out, [&](int x) { return (row_tile + x / RT_TILE_W) % F.tile_world == F.tile_rank; });
-	else
-		raygen_half_row_component(F, y, half, comp, out, [](int) { return true; });
+	raygen_half_row_component(F, t / 6, (t / 3) & 1, t % 3, ck);
 }
-__global__ void __launch_bounds__(RT_SETUP_THREADS)
-    rt_raygen_kernel(const __grid_constant__ RtFrame F, RtD4* __restrict__ dirs, int tiles_x) {
-	raygen_lane(F, dirs, tiles_x, blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void __launch_bounds__(RT_SETUP_THREADS) rt_raygen_kernel(const __grid_constant__ RtFrame F, double* __restrict__ ck) {
+	raygen_lane(F, ck, blockIdx.x * blockDim.x + threadIdx.x);
+}
+// the direction of every pixel, expanded from the checkpoints (rt_camera_directions)
+__global__ void rt_expand_dirs_kernel(const __grid_constant__ RtFrame F, double* __restrict__ out) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (size_t)F.width * F.height) return;
+	double d[3];
+	pixel_dir(F, (int)(i % F.width), (int)(i / F.width), d);
+	out[3 * i] = d[0]; out[3 * i + 1] = d[1]; out[3 * i + 2] = d[2];
 }
 
 // Everything a frame needs before its first ray, in ONE launch (three launches and their gaps would be a tenth of
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(RT_SETUP_THREADS)
 // no cancellation, rounded once; skipped without primary records: 0 blocks).
 __global__ void __launch_bounds__(RT_SETUP_THREADS)
     rt_frame_setup_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, unsigned long long* __restrict__ cells,
-                          int n_cells, int raygen_blocks, RtD4* __restrict__ dirs, int tiles_x, RtF4* __restrict__ prim_out) {
+                          int n_cells, int raygen_blocks, double* __restrict__ ray_ck, RtF4* __restrict__ prim_out) {
 	int b = (int)blockIdx.x;
 	if (b == 0) {
 		for (int i = threadIdx.x; i < n_cells; i += RT_SETUP_THREADS) cells[i] = 0ull;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(RT_SETUP_THREADS)
 	}
 	b -= 1;
 	if (b < raygen_blocks) {
-		raygen_lane(F, dirs, tiles_x, b * RT_SETUP_THREADS + (int)threadIdx.x);
+		raygen_lane(F, ray_ck, b * RT_SETUP_THREADS + (int)threadIdx.x);
 		return;
 	}
 	const int s = (b - raygen_blocks) * RT_SETUP_THREADS + (int)threadIdx.x;
@@ -606,7 +607,6 @@ struct RenderKey {
 struct RaygenKey {
 	double basis[9], fov_h, fov_v;
 	uint32_t width, height, flags;
-	int rank, world;
 	void* dirs;
 };
 
@@ -674,7 +674,7 @@ struct rt_ctx {
 
 	// per-frame
 	DevBuf<RtD4> row_fr;
-	DevBuf<RtD4> dirs;                           // [height][width] ray-generation table of the current camera
+	DevBuf<double> ray_ck;                       // ray-generation checkpoints of the current camera basis (RtFrame.ray_ck)
 	DevBuf<float> rgb;
 	DevBuf<int> ids;
 	DevBuf<unsigned long long> counters;
@@ -783,14 +783,15 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	// stands, so a camera that merely moved (the reference's WASD keys, src/main.ts:296-330) keeps its table.
 	const size_t n_row = cam->height;
 	RT_CUDA(ctx, ctx->row_fr.alloc(n_row));
-	RT_CUDA(ctx, ctx->dirs.alloc((size_t)cam->width * cam->height));
+	const int ray_ckh = raygen_checkpoints_per_half((int)cam->width);
+	RT_CUDA(ctx, ctx->ray_ck.alloc((size_t)cam->height * 2 * ray_ckh * 6));
 	RaygenKey rk;
 	memset(&rk, 0, sizeof rk);
 	memcpy(rk.basis, cam->fr, sizeof cam->fr); memcpy(rk.basis + 3, cam->lf, sizeof cam->lf); memcpy(rk.basis + 6, cam->up, sizeof cam->up);
 	rk.fov_h = cam->fov_h; rk.fov_v = cam->fov_v; rk.width = cam->width; rk.height = cam->height; rk.flags = cam->flags;
-	rk.rank = tile_rank; rk.world = tile_world; rk.dirs = ctx->dirs.p;
+	rk.dirs = ctx->ray_ck.p;
 	const bool need_raygen = !capture && (!ctx->raygen_key_valid || memcmp(&rk, &ctx->raygen_key, sizeof rk) != 0);
-	double scan_cos = 1.0, scan_sin = 0.0;
+	double scan_cos = std::cos(cam->fov_h / cam->width), scan_sin = std::sin(cam->fov_h / cam->width);  // (as rt_build_camera_rows)
 	RtD4* st_row = nullptr;
 	if (need_raygen) {
 		if (ctx->stage_cap < n_row * sizeof(RtD4)) {
@@ -809,7 +810,8 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	std::string err;
 	if (rt_status st = rt_fill_frame(ctx->host_ref(), cam, prm, F, err)) return fail(ctx, st, err);
 	F.row_fr = ctx->row_fr.p;
-	F.dirs = ctx->dirs.p;
+	F.ray_ck = ctx->ray_ck.p;
+	F.ray_ckh = ray_ckh;
 	F.scan_cos = scan_cos;
 	F.scan_sin = scan_sin;
 	F.rgb = rgb_dev;
@@ -921,7 +923,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				ctx->raygen_key_valid = true;
 			}
 			rt_frame_setup_kernel<<<1 + raygen_blocks + prep_blocks, RT_SETUP_THREADS, 0, ctx->stream>>>(
-			    ctx->dev, F, ctx->counters.p, (int)n_cells, raygen_blocks, ctx->dirs.p, tiles_x, ctx->prim_geom.p);
+			    ctx->dev, F, ctx->counters.p, (int)n_cells, raygen_blocks, ctx->ray_ck.p, ctx->prim_geom.p);
 			ctx->launches++;
 			ctx->stage_ran[0] = prof;
 			RT_CUDA(ctx, cudaGetLastError());
@@ -1381,7 +1383,7 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_walk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release(); ctx->bvh_geom.release();
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
-	ctx->dirs.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
+	ctx->ray_ck.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
 	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->peer_flags.release();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -1564,24 +1566,25 @@ rt_status rt_camera_directions(rt_ctx* ctx, const rt_camera* cam, double* dirs) 
 	std::vector<RtD4> rows;
 	rt_build_camera_rows(*cam, rows, F.scan_cos, F.scan_sin);
 	const size_t npx = (size_t)F.width * F.height;
+	F.ray_ckh = raygen_checkpoints_per_half(F.width);
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // (pageable source below: nothing may still read row_fr)
 	RT_CUDA(ctx, ctx->row_fr.alloc(rows.size()));
-	RT_CUDA(ctx, ctx->dirs.alloc(npx));
+	RT_CUDA(ctx, ctx->ray_ck.alloc((size_t)F.height * 2 * F.ray_ckh * 6));
+	DevBuf<double> out;
+	RT_CUDA(ctx, out.alloc(npx * 3));
 	ctx->key_valid = false;  // the tables of a cached frame are gone
+	ctx->raygen_key_valid = false;
 	RT_CUDA(ctx, cudaMemcpyAsync(ctx->row_fr.p, rows.data(), rows.size() * sizeof(RtD4), cudaMemcpyHostToDevice, ctx->stream));
 	F.row_fr = ctx->row_fr.p;
-	ctx->raygen_key_valid = false;
-	rt_raygen_kernel<<<(6 * F.height + RT_SETUP_THREADS - 1) / RT_SETUP_THREADS, RT_SETUP_THREADS, 0, ctx->stream>>>(F, ctx->dirs.p, (F.width + RT_TILE_W - 1) / RT_TILE_W);
-	ctx->launches++;
-	RT_CUDA(ctx, cudaGetLastError());
-	std::vector<RtD4> host(npx);
-	RT_CUDA(ctx, cudaMemcpyAsync(host.data(), ctx->dirs.p, npx * sizeof(RtD4), cudaMemcpyDeviceToHost, ctx->stream));
-	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	for (size_t i = 0; i < npx; i++) {
-		dirs[3 * i] = host[i].x;
-		dirs[3 * i + 1] = host[i].y;
-		dirs[3 * i + 2] = host[i].z;
-	}
+	F.ray_ck = ctx->ray_ck.p;
+	rt_raygen_kernel<<<(6 * F.height + RT_SETUP_THREADS - 1) / RT_SETUP_THREADS, RT_SETUP_THREADS, 0, ctx->stream>>>(F, ctx->ray_ck.p);
+	rt_expand_dirs_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(F, out.p);
+	ctx->launches += 2;
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaMemcpyAsync(dirs, out.p, npx * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	out.release();
+	if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, rt_format("rt_camera_directions: %s", cudaGetErrorString(e)));
 	return RT_OK;
 }
 

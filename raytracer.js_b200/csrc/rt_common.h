@@ -121,6 +121,9 @@ struct RtDevScene {
 	float _pad;
 };
 
+#define RT_RAYGEN_STRIDE 8  // yields between two checkpoints of the ray generation (a power of two)
+// checkpoints per half row (the right half is the longer one when the width is odd)
+inline int raygen_checkpoints_per_half(int width) { return ((width - (width >> 1)) + RT_RAYGEN_STRIDE - 1) / RT_RAYGEN_STRIDE; }
 #define RT_MAX_CHAIN 32
 
 // One pixel handed from the primary stage to the bounce stage: its path continues after the first hit
@@ -140,9 +143,15 @@ struct RtFrame {
 	// Camera.get_dir_for_each_pixel (src/view/camera.ts:207-250) iterates 2-D rotations: rows outwards from the middle
 	// row (fr towards up), then along every row outwards from the middle column (fr towards lf).  Floating-point
 	// rotations do not commute with any closed form, so the directions are produced by the very same iteration:
-	// row_fr on the host (height steps), the row scans by rt_raygen_kernel (one thread per half row), into `dirs`.
-	const RtD4* row_fr;  // [height] fr rotated towards up by the accumulated vertical scan rotation (host-built)
-	const RtD4* dirs;    // [height][width] the generator's direction of every pixel, bit for bit (xyz; w unused)
+	// row_fr on the host (height steps); the scans along the rows by the ray-generation lanes of the frame-setup kernel,
+	// which keep the generator's state (fr, lf) of every RT_RAYGEN_STRIDE-th yield of each half row in `ray_ck`; a
+	// pixel's direction is its checkpoint iterated the remaining 0..7 steps (rt_trace.cuh: pixel_dir) - the same
+	// operations in the same order as the generator's, hence the same bits.  (A full table of directions would be
+	// 32 B per pixel written and read per camera pose: the scan is then bound by the L2's request rate, not by its
+	// own dependent chain.)
+	const RtD4* row_fr;    // [height] fr rotated towards up by the accumulated vertical scan rotation (host-built)
+	const double* ray_ck;  // [height][2 halves][ray_ckh] records of 6 doubles: fr.x, lf.x, fr.y, lf.y, fr.z, lf.z
+	int ray_ckh;           // checkpoints per half row
 	double scan_cos, scan_sin;  // rot_scan_h_v: cos / sin of fov_h / width
 	int width, height;
 	// start state shared by all primary rays (src/raytracer.ts:309-313)

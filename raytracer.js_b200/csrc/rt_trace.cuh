@@ -763,21 +763,6 @@ struct RtPatch {
 RT_HD int patch_x(const RtPatch& pt, int lane, int j) { return pt.x0 + (((pt.sub0 + j) & 1) << 3) + (lane & 7); }
 RT_HD int patch_y(const RtPatch& pt, int lane, int j) { return pt.y0 + (((pt.sub0 + j) >> 1) << 2) + (lane >> 3); }
 
-// Camera direction of pixel (x,y): get_dir_for_each_pixel (src/view/camera.ts:207-250), from the per-frame table
-// the ray-generation pass (raygen_half_row) filled with the generator's own iterated rotations.
-// (read through L2 only: the primary stage reads rows that warps of the SAME launch are still producing, and the
-// table is read once or twice per pixel anyway)
-RT_HD void pixel_dir(const RtFrame& F, int x, int y, double* dir) {
-	const RtD4* p = F.dirs + ((size_t)y * F.width + x);
-#if defined(__CUDACC__)
-	const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
-	const double b = __ldcg(reinterpret_cast<const double*>(p) + 2);
-	dir[0] = a.x; dir[1] = a.y; dir[2] = b;
-#else
-	dir[0] = p->x; dir[1] = p->y; dir[2] = p->z;
-#endif
-}
-
 // rotate_vectors (src/math/vector.ts:318-323): (a, b) <- (a*c + b*s, a*-s + b*c), every product and sum rounded
 RT_HD void rotate_pair(double* a, double* b, double c, double s) {
 #pragma unroll
@@ -789,56 +774,48 @@ RT_HD void rotate_pair(double* a, double* b, double c, double s) {
 	}
 }
 
-// Ray generation for one half of row y, exactly as iter_h of get_dir_for_each_pixel scans it
+// Ray generation for ONE component of one half of row y, exactly as iter_h of get_dir_for_each_pixel scans it
 // (src/view/camera.ts:214-226,240-249): starting from the row's fr (row_fr[y]) and norm_lf, the right half
-// (half == 0) yields x = width>>1, ... , width-1 rotating AFTER every yield by rot_scan_h_v, the left half
-// (half == 1) rotates by the counter-clockwise rotation FIRST and yields x = (width>>1)-1, ..., 0.
-// own(x): whether this rank stores pixel x of the row (tile sharding); `out` is the row of the table.
-template <class Own>
-RT_HD void raygen_half_row(const RtFrame& F, int y, int half, RtD4* out, Own own) {
-	const RtD4 r = ld(F.row_fr + y);
-	double fr[3] = {r.x, r.y, r.z}, lf[3] = {F.lf[0], F.lf[1], F.lf[2]};
-	const int x0 = F.width >> 1;
-	// one loop shape for both halves: the left half has rotated once before its first yield, both rotate after
-	// every yield (the rotation after the last one is unused)
-	const double s = half ? -F.scan_sin : F.scan_sin;
-	const int n = half ? x0 : F.width - x0, first = half ? x0 - 1 : x0, step = half ? -1 : 1;
-	if (half) rotate_pair(fr, lf, F.scan_cos, s);
-	for (int i = 0, x = first; i < n; i++, x += step) {
-		if (own(x)) out[x] = RtD4{fr[0], fr[1], fr[2], 0.0};
-		rotate_pair(fr, lf, F.scan_cos, s);
-	}
-}
-
-// The same for ONE component of the direction (rotate_vectors never mixes components): what one lane of the
-// ray-generation kernel runs.  `out` points at that component of the row's first record (stride 4 doubles); the
-// lane of component 2 stores the unused fourth double with it, so that the three lanes of a pixel together write a
-// whole 32-byte sector (a 24-byte write would make the L2 fetch the sector first).
-template <class Own>
-RT_HD void raygen_half_row_component(const RtFrame& F, int y, int half, int comp, double* out, Own own) {
+// (half == 0) yields x = width>>1, ..., width-1 rotating AFTER every yield by rot_scan_h_v, the left half
+// (half == 1) rotates by the counter-clockwise rotation FIRST and yields x = (width>>1)-1, ..., 0.  rotate_vectors
+// never mixes components, so (fr[k], lf[k]) is a recurrence of its own: one lane of the frame-setup kernel.  The
+// state at every RT_RAYGEN_STRIDE-th yield goes to the checkpoint table (F.ray_ck).
+RT_HD void raygen_half_row_component(const RtFrame& F, int y, int half, int comp, double* ck) {
 	const RtD4 r = ld(F.row_fr + y);
 	double a = comp == 0 ? r.x : comp == 1 ? r.y : r.z, b = F.lf[comp];
 	const int x0 = F.width >> 1;
 	const double c = F.scan_cos, s = half ? -F.scan_sin : F.scan_sin;
-	const int n = half ? x0 : F.width - x0, first = half ? x0 - 1 : x0, step = half ? -1 : 1;
+	const int n = half ? x0 : F.width - x0;
 	if (half) {
 		const double x = xadd(xmul(a, c), xmul(b, s)), yy = xadd(xmul(a, -s), xmul(b, c));
 		a = x;
 		b = yy;
 	}
-	for (int i = 0, x = first; i < n; i++, x += step) {
-		if (own(x)) {
-#if defined(__CUDACC__)
-			if (comp == 2) *reinterpret_cast<double2*>(out + (size_t)x * 4) = make_double2(a, 0.0);
-			else out[(size_t)x * 4] = a;
-#else
-			out[(size_t)x * 4] = a;
-#endif
+	double* out = ck + ((size_t)(y * 2 + half) * F.ray_ckh) * 6 + comp * 2;
+	for (int i = 0; i < n; i++) {
+		if ((i & (RT_RAYGEN_STRIDE - 1)) == 0) {
+			out[0] = a;
+			out[1] = b;
+			out += 6;
 		}
 		const double na = xadd(xmul(a, c), xmul(b, s)), nb = xadd(xmul(a, -s), xmul(b, c));
 		a = na;
 		b = nb;
 	}
+}
+
+// Camera direction of pixel (x,y): get_dir_for_each_pixel (src/view/camera.ts:207-250): the generator's state at
+// the checkpoint before the pixel, iterated the remaining steps with the generator's own operations.
+RT_HD void pixel_dir(const RtFrame& F, int x, int y, double* dir) {
+	const int x0 = F.width >> 1;
+	const int half = x < x0 ? 1 : 0;
+	const int i = half ? x0 - 1 - x : x - x0;
+	const RtD2* p = reinterpret_cast<const RtD2*>(F.ray_ck + ((size_t)(y * 2 + half) * F.ray_ckh + (i / RT_RAYGEN_STRIDE)) * 6);
+	const RtD2 cx = ld(p), cy = ld(p + 1), cz = ld(p + 2);
+	double fr[3] = {cx.x, cy.x, cz.x}, lf[3] = {cx.y, cy.y, cz.y};
+	const double s = half ? -F.scan_sin : F.scan_sin;
+	for (int k = i & (RT_RAYGEN_STRIDE - 1); k > 0; k--) rotate_pair(fr, lf, F.scan_cos, s);
+	dir[0] = fr[0]; dir[1] = fr[1]; dir[2] = fr[2];
 }
 
 // pixels outside the frame ride along with the direction of the nearest pixel inside it

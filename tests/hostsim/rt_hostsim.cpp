@@ -22,14 +22,12 @@ extern "C" void hostsim_raygen(const rt_camera* cam, double* dirs) {
 	F.width = (int)cam->width;
 	F.height = (int)cam->height;
 	F.row_fr = row.data();
-	std::vector<RtD4> line(F.width);
-	for (int y = 0; y < F.height; y++) {
-		for (int half = 0; half < 2; half++) raygen_half_row(F, y, half, line.data(), [](int) { return true; });
-		for (int x = 0; x < F.width; x++) {
-			double* o = dirs + ((size_t)y * F.width + x) * 3;
-			o[0] = line[x].x; o[1] = line[x].y; o[2] = line[x].z;
-		}
-	}
+	F.ray_ckh = raygen_checkpoints_per_half(F.width);
+	std::vector<double> ck((size_t)F.height * 2 * F.ray_ckh * 6);
+	for (int t = 0; t < 6 * F.height; t++) raygen_half_row_component(F, t / 6, (t / 3) & 1, t % 3, ck.data());
+	F.ray_ck = ck.data();
+	for (int y = 0; y < F.height; y++)
+		for (int x = 0; x < F.width; x++) pixel_dir(F, x, y, dirs + ((size_t)y * F.width + x) * 3);
 }
 
 // Debugging aid: restrict the ray-by-ray mode (pipeline == 0) to a crop of the frame (w == 0: whole frame).
@@ -71,11 +69,12 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 	S.err_l = hs.err_l;
 	S.ordered_ok = rt_ordered_walk_fits(hs);
 	F.row_fr = row.data();
-	// ray generation (rt_raygen_kernel's body): the generator's iterated rotations along every row
-	std::vector<RtD4> dirs((size_t)F.width * F.height);
-	for (int y = 0; y < F.height; y++)
-		for (int half = 0; half < 2; half++) raygen_half_row(F, y, half, dirs.data() + (size_t)y * F.width, [](int) { return true; });
-	F.dirs = dirs.data();
+	// ray generation (the body of the frame-setup kernel's ray-generation lanes): checkpoints of the generator's
+	// iterated rotations along every row
+	F.ray_ckh = raygen_checkpoints_per_half(F.width);
+	std::vector<double> ray_ck((size_t)F.height * 2 * F.ray_ckh * 6);
+	for (int t = 0; t < 6 * F.height; t++) raygen_half_row_component(F, t / 6, (t / 3) & 1, t % 3, ray_ck.data());
+	F.ray_ck = ray_ck.data();
 	F.rgb = rgb;
 	F.first_ids = ids;
 	// bit 1 of `pipeline`: a shard (tile_world > 1) writes into a FRAME-layout buffer (rt_render_shard_device)
