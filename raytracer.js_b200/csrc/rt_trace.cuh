@@ -73,6 +73,13 @@ RT_HD RtD4 ld(const RtD4* p) {
 	return *p;
 #endif
 }
+RT_HD double ld(const double* p) {
+#if defined(__CUDACC__)
+	return __ldg(p);
+#else
+	return *p;
+#endif
+}
 RT_HD int ld(const int* p) {
 #if defined(__CUDACC__)
 	return __ldg(p);
@@ -988,6 +995,48 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 	}
 }
 
+// The directions of all the packet's pixels, produced cooperatively into `scratch` ([PPL][32][3] doubles: pixel
+// `lane` of sub-patch j at scratch[(j * 32 + lane) * 3]).  A lane iterating its own pixel from the checkpoint
+// (pixel_dir) repeats what its left neighbour did plus one step, and the FP64 pipe is narrow; here one lane takes
+// one COMPONENT of one 8-pixel ROW of a sub-patch - 12 lanes per sub-patch, two sub-patches per round - and walks
+// it once, in generator order (outwards from the middle column), leaving every intermediate state behind: a sixth
+// of the FP64 instructions.  Same operations in the same order as the generator, hence the same bits.
+template <int PPL>
+RT_HD void packet_directions(const RtFrame& F, const RtPatch& pt, double* scratch) {
+	const int x0 = F.width >> 1;
+	for (int round = 0; round < (PPL + 1) / 2; round++) {
+		RT_LANES(l, lane) {
+			(void)l;
+			const int jj = round * 2 + lane / 12, r = (lane % 12) / 3, c = lane % 3;
+			if (lane >= 24 || jj >= PPL) continue;
+			const int y = patch_y(pt, r * 8, jj) < F.height ? patch_y(pt, r * 8, jj) : F.height - 1;
+			const int xa = patch_x(pt, 0, jj), xb = xa + 7 < F.width - 1 ? xa + 7 : F.width - 1;  // columns xa..xb are in the frame
+			double* out = scratch + ((size_t)(jj * 32 + r * 8) * 3 + c);
+			for (int half = 0; half < 2; half++) {
+				// the pixels of this half in generator order: ascending x from the middle on the right, descending on the left
+				const int lo = half ? xa : (xa > x0 ? xa : x0), hi = half ? (xb < x0 - 1 ? xb : x0 - 1) : xb;
+				if (lo > hi) continue;
+				const int i_lo = half ? x0 - 1 - hi : lo - x0, step = half ? -1 : 1;
+				const double* ck = F.ray_ck + ((size_t)(y * 2 + half) * F.ray_ckh + i_lo / RT_RAYGEN_STRIDE) * 6 + c * 2;
+				double a = ld(ck), b = ld(ck + 1);
+				const double cs = F.scan_cos, sn = half ? -F.scan_sin : F.scan_sin;
+				for (int k = i_lo & (RT_RAYGEN_STRIDE - 1); k > 0; k--) {
+					const double na = xadd(xmul(a, cs), xmul(b, sn)), nb = xadd(xmul(a, -sn), xmul(b, cs));
+					a = na;
+					b = nb;
+				}
+				for (int x = half ? hi : lo, n = hi - lo + 1; n > 0; n--, x += step) {
+					out[(x - xa) * 3] = a;
+					const double na = xadd(xmul(a, cs), xmul(b, sn)), nb = xadd(xmul(a, -sn), xmul(b, cs));
+					a = na;
+					b = nb;
+				}
+			}
+		}
+	}
+	warp_sync();
+}
+
 // First-hit code of every camera ray of the packet in the reference's visit order (RT_HIT_* above).  Rays with
 // bit j of skip[l] set (pixels outside the frame) take no part.  `stack` is RT_PACKET_STACK records and `rays`
 // PPL * 32 ray records private to the warp.  A packet whose rays differ in the sign of a direction component
@@ -999,13 +1048,23 @@ template <int PPL>
 RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const unsigned (&skip)[RT_NL],
                                RtPNode* stack, RtPRay* rays, int (&hit)[RT_NL][PPL]) {
 	unsigned todo[RT_NL], negs[RT_NL];  // bit j: ray j still to do; 3 bits per ray: its direction-sign class
+	// the node stack is not in use yet: its memory holds the packet's float64 directions for a moment
+	double* const dirs = reinterpret_cast<double*>(stack);
+	static_assert(sizeof(RtPNode) * RT_PACKET_STACK >= sizeof(double) * 3 * 32 * PPL, "scratch for the packet's directions");
+	packet_directions<PPL>(F, pt, dirs);
 	RT_LANES(l, lane) {
 		todo[l] = 0u;
 		negs[l] = 0u;
 #pragma unroll
 		for (int j = 0; j < PPL; j++) {
 			double dir[3];
-			pixel_dir_clamped(F, patch_x(pt, lane, j), patch_y(pt, lane, j), dir);
+			const int px = patch_x(pt, lane, j);
+			if (px < F.width) {  // (rows below the frame were produced with the last row's checkpoints)
+				const double* d = dirs + (size_t)(j * 32 + lane) * 3;
+				dir[0] = d[0]; dir[1] = d[1]; dir[2] = d[2];
+			} else {
+				pixel_dir_clamped(F, px, patch_y(pt, lane, j), dir);
+			}
 			RtPRay q;
 			q.dx = (float)dir[0]; q.dy = (float)dir[1]; q.dz = (float)dir[2];
 			q.inv_a = 1.0f / (q.dx * q.dx + q.dy * q.dy + q.dz * q.dz);
