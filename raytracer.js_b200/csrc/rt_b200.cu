@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 template <int PPL, int MINB>
 __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
     rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_packets) {
-	__shared__ RtPNode stacks[RT_A_WARPS][RT_PACKET_STACK];
+	__shared__ RtPNode stacks[RT_A_WARPS][RT_PACKET_STACK(PPL)];
 	__shared__ __align__(16) RtPRay rays[RT_A_WARPS][PPL * 32];
 	__shared__ __align__(16) float stages[RT_A_WARPS][96];
 	constexpr int PER_TILE = 8 / PPL;

@@ -550,6 +550,6 @@ inline void rt_fill_chain(const RtHostScene& hs, RtFrame& F) {
 		F.chain_oct[k] = oct;
 		oct = hs.node_link[n].y;
 	}
-	// the packet stage needs the whole chain (up to the root) and a node stack that cannot overflow
-	F.packet_ok = (F.start_node >= 0 && n < 0 && 7 * hs.max_depth + 8 <= RT_PACKET_STACK) ? 1 : 0;
+	// the packet stage needs the whole chain (up to the root); its node stack is checked as it grows
+	F.packet_ok = (F.start_node >= 0 && n < 0) ? 1 : 0;
 }

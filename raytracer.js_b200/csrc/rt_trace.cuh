@@ -73,9 +73,18 @@ RT_HD RtD4 ld(const RtD4* p) {
 	return *p;
 #endif
 }
-RT_HD double ld(const double* p) {
+// ray-generation checkpoints: read once per packet - through the L2 only, the L1 is for the scene
+RT_HD double ld_stream(const double* p) {
 #if defined(__CUDACC__)
-	return __ldg(p);
+	return __ldcg(p);
+#else
+	return *p;
+#endif
+}
+RT_HD RtD2 ld_stream(const RtD2* p) {
+#if defined(__CUDACC__)
+	const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+	return RtD2{v.x, v.y};
 #else
 	return *p;
 #endif
@@ -818,7 +827,7 @@ RT_HD void pixel_dir(const RtFrame& F, int x, int y, double* dir) {
 	const int half = x < x0 ? 1 : 0;
 	const int i = half ? x0 - 1 - x : x - x0;
 	const RtD2* p = reinterpret_cast<const RtD2*>(F.ray_ck + ((size_t)(y * 2 + half) * F.ray_ckh + (i / RT_RAYGEN_STRIDE)) * 6);
-	const RtD2 cx = ld(p), cy = ld(p + 1), cz = ld(p + 2);
+	const RtD2 cx = ld_stream(p), cy = ld_stream(p + 1), cz = ld_stream(p + 2);
 	double fr[3] = {cx.x, cy.x, cz.x}, lf[3] = {cx.y, cy.y, cz.y};
 	const double s = half ? -F.scan_sin : F.scan_sin;
 	for (int k = i & (RT_RAYGEN_STRIDE - 1); k > 0; k--) rotate_pair(fr, lf, F.scan_cos, s);
@@ -861,7 +870,7 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 	// pierce) on the stack, last-visited first
 	auto push_mask = [&](const RtPNode& nd, unsigned m) {
 		if (!m) return;
-		if (sp + 8 > RT_PACKET_STACK) { overflow = true; return; }
+		if (sp + 8 > RT_PACKET_STACK(PPL)) { overflow = true; return; }
 		const unsigned mk = xor_permute8(m, P.neg);  // bit = visit key
 		RT_LANES(l, lane) {
 			(void)l;
@@ -1018,7 +1027,8 @@ RT_HD void packet_directions(const RtFrame& F, const RtPatch& pt, double* scratc
 				if (lo > hi) continue;
 				const int i_lo = half ? x0 - 1 - hi : lo - x0, step = half ? -1 : 1;
 				const double* ck = F.ray_ck + ((size_t)(y * 2 + half) * F.ray_ckh + i_lo / RT_RAYGEN_STRIDE) * 6 + c * 2;
-				double a = ld(ck), b = ld(ck + 1);
+				const RtD2 ab = ld_stream(reinterpret_cast<const RtD2*>(ck));
+				double a = ab.x, b = ab.y;
 				const double cs = F.scan_cos, sn = half ? -F.scan_sin : F.scan_sin;
 				for (int k = i_lo & (RT_RAYGEN_STRIDE - 1); k > 0; k--) {
 					const double na = xadd(xmul(a, cs), xmul(b, sn)), nb = xadd(xmul(a, -sn), xmul(b, cs));
@@ -1038,7 +1048,7 @@ RT_HD void packet_directions(const RtFrame& F, const RtPatch& pt, double* scratc
 }
 
 // First-hit code of every camera ray of the packet in the reference's visit order (RT_HIT_* above).  Rays with
-// bit j of skip[l] set (pixels outside the frame) take no part.  `stack` is RT_PACKET_STACK records and `rays`
+// bit j of skip[l] set (pixels outside the frame) take no part.  `stack` is RT_PACKET_STACK(PPL) records and `rays`
 // PPL * 32 ray records private to the warp.  A packet whose rays differ in the sign of a direction component
 // (it straddles one of the three great circles through the axes) is walked once per sign class (a zero
 // component counts as positive: such a ray never crosses a plane of that axis, so either order is its own).
@@ -1050,7 +1060,7 @@ RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const RtPa
 	unsigned todo[RT_NL], negs[RT_NL];  // bit j: ray j still to do; 3 bits per ray: its direction-sign class
 	// the node stack is not in use yet: its memory holds the packet's float64 directions for a moment
 	double* const dirs = reinterpret_cast<double*>(stack);
-	static_assert(sizeof(RtPNode) * RT_PACKET_STACK >= sizeof(double) * 3 * 32 * PPL, "scratch for the packet's directions");
+	static_assert(sizeof(RtPNode) * RT_PACKET_STACK(PPL) >= sizeof(double) * 3 * 32 * PPL, "scratch for the packet's directions");
 	packet_directions<PPL>(F, pt, dirs);
 	RT_LANES(l, lane) {
 		todo[l] = 0u;

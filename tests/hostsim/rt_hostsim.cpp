@@ -107,7 +107,7 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 		F.queue_count = &queue_count;
 		// ---- primary stage: packet walk + shading of the paths that end at their first hit
 		auto stage_a = [&](int t) {
-			std::vector<RtPNode> stack(RT_PACKET_STACK);
+			std::vector<RtPNode> stack(RT_PACKET_STACK(HOSTSIM_PPL));
 			std::vector<RtPRay> rays(PPL * 32);
 			float stage[96];
 			for (int p = t; p < my_tiles * PER_TILE; p += n_threads) {
