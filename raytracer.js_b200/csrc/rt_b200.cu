@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
     rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_packets) {
 	__shared__ RtPNode stacks[RT_A_WARPS][RT_PACKET_STACK(PPL)];
 	__shared__ __align__(16) RtPRay rays[RT_A_WARPS][PPL * 32];
+	__shared__ __align__(16) double dirs[RT_A_WARPS][PPL * 32 * 3];
 	__shared__ __align__(16) float stages[RT_A_WARPS][96];
 	constexpr int PER_TILE = 8 / PPL;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
 		pt.y0 = (tile / tiles_x) * RT_TILE_H;
 		pt.sub0 = (int)(p % PER_TILE) * PPL;
 		pt.out_base = (size_t)k * RT_BLOCK;
-		primary_patch<PPL>(S, F, pt, stacks[warp], rays[warp], stages[warp], err);
+		primary_patch<PPL>(S, F, pt, stacks[warp], rays[warp], dirs[warp], stages[warp], err);
 	}
 	if (err) atomicOr(F.error_flags, err);
 }
@@ -691,7 +692,7 @@ struct rt_ctx {
 	DevBuf<uint32_t*> peer_flags;
 	std::vector<uint32_t*> peer_flags_host;
 	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
-	int ppl = RT_PPL;                            // tuning knob RT_B200_PPL=4|8: sub-patches (rays per lane) of a packet
+	int ppl = RT_PPL;                            // sub-patches (rays per lane) of a packet: 4
 	int primary_minb = RT_A_MINB;                // tuning knob RT_B200_PRIMARY_MINB=4|5|6: resident CTAs per SM the primary stage is compiled for
 	int bounce_min_walking = 12;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
 	int resample_min_frames = 8;                 // tuning knob RT_B200_RESAMPLE_MIN
@@ -732,8 +733,7 @@ rt_status check_args(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm) {
 }
 
 const void* primary_kernel_of(int ppl, int minb) {
-	if (ppl == 8)
-		return minb == 4 ? (const void*)rt_primary_kernel<8, 4> : minb == 6 ? (const void*)rt_primary_kernel<8, 6> : (const void*)rt_primary_kernel<8, 5>;
+	(void)ppl;  // (8 rays per lane was measured no faster than 4 in round 2 and no longer fits the shared memory of a CTA)
 	return minb == 4 ? (const void*)rt_primary_kernel<4, 4> : minb == 6 ? (const void*)rt_primary_kernel<4, 6> : (const void*)rt_primary_kernel<4, 5>;
 }
 
@@ -1273,7 +1273,7 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	}
 	if (const char* e = getenv("RT_B200_PPL")) {
 		const int v = atoi(e);
-		if (v == 4 || v == 8) ctx->ppl = v;
+		if (v == 4) ctx->ppl = v;
 	}
 	if (const char* e = getenv("RT_B200_PRIMARY_MINB")) {
 		const int v = atoi(e);

@@ -136,8 +136,7 @@ struct alignas(8) RtQueueItem {
 // Node stack of the packet walk, in records per warp (shared memory): a packet usually keeps at most 3-4 pending
 // siblings per level (the packet is narrow), so 96 records cover trees far deeper than float32 can resolve; a walk
 // that would overflow hands its rays to the bounce stage instead (RT_SLOT_UNKNOWN), never drops a node silently.
-// (8 rays per lane: 192, because the same memory first holds the packet's float64 directions.)
-#define RT_PACKET_STACK(ppl) ((ppl) > 4 ? 192 : 96)
+#define RT_PACKET_STACK(ppl) 96
 #define RT_WALK_STACK 160    // stack of the per-ray ordered walk (bounce stage): octree nodes (same bound) + one list BVH on top
 
 struct RtFrame {

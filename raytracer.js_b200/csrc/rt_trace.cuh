@@ -841,9 +841,7 @@ RT_HD void pixel_dir_clamped(const RtFrame& F, int x, int y, double* dir) {
 
 // float64 confirmation of a float32 candidate for the camera ray of pixel (x,y): 0 = collision_info is null,
 // 1 = hit, 2 = hit whose normal does not face the ray (the guard of src/raytracer.ts:200-203 will end the path)
-RT_COLD int packet_confirm(const RtDevScene& S, const RtFrame& F, int x, int y, int slot) {
-	double dir[3];
-	pixel_dir_clamped(F, x, y, dir);
+RT_COLD int packet_confirm(const RtDevScene& S, const RtFrame& F, const double* dir, int slot) {
 	RtCollision col;
 	const RtD4 g64 = ld(S.slot_geom64 + slot);
 	const bool hit = ld(S.slot_geom + slot).w > 0.0f ? exact_sphere(g64, F.pos, dir, col) : exact_box(g64, F.pos, dir, col);
@@ -862,7 +860,7 @@ RT_COLD int packet_confirm(const RtDevScene& S, const RtFrame& F, int x, int y, 
 // One lock-step walk for the rays of one direction-sign class: bit j of open[l] = ray j of lane l is still
 // searching.  `rays` is the packet's ray table, [PPL][32] (shared memory on the device).
 template <int PPL>
-RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const RtPRay* rays,
+RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const RtPRay* rays, const double* dirs,
                              const RtPacket& P, unsigned (&open)[RT_NL], RtPNode* stack, int (&hit)[RT_NL][PPL],
                              bool& overflow) {
 	int sp = 0;
@@ -972,7 +970,7 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 							cand = candidate(ld(S.slot_geom + slot), rf, S.err_l);
 						}
 						if (cand) {
-							const int c = packet_confirm(S, F, patch_x(pt, lane, j), patch_y(pt, lane, j), slot);
+							const int c = packet_confirm(S, F, dirs + (size_t)(j * 32 + lane) * 3, slot);
 							if (c) {
 								hit[l][j] = slot | (c == 2 ? RT_HIT_ACUTE : 0);
 								open[l] &= ~(1u << j);
@@ -1048,7 +1046,7 @@ RT_HD void packet_directions(const RtFrame& F, const RtPatch& pt, double* scratc
 }
 
 // First-hit code of every camera ray of the packet in the reference's visit order (RT_HIT_* above).  Rays with
-// bit j of skip[l] set (pixels outside the frame) take no part.  `stack` is RT_PACKET_STACK(PPL) records and `rays`
+// bit j of skip[l] set (pixels outside the frame) take no part.  `stack` is RT_PACKET_STACK(PPL) records, `dirs` PPL * 32 * 3 doubles and `rays`
 // PPL * 32 ray records private to the warp.  A packet whose rays differ in the sign of a direction component
 // (it straddles one of the three great circles through the axes) is walked once per sign class (a zero
 // component counts as positive: such a ray never crosses a plane of that axis, so either order is its own).
@@ -1056,12 +1054,9 @@ RT_HD void packet_directions(const RtFrame& F, const RtPatch& pt, double* scratc
 // not narrow) come back as RT_SLOT_UNKNOWN: the bounce stage searches those ray by ray.
 template <int PPL>
 RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, const unsigned (&skip)[RT_NL],
-                               RtPNode* stack, RtPRay* rays, int (&hit)[RT_NL][PPL]) {
+                               RtPNode* stack, RtPRay* rays, double* dirs, int (&hit)[RT_NL][PPL]) {
 	unsigned todo[RT_NL], negs[RT_NL];  // bit j: ray j still to do; 3 bits per ray: its direction-sign class
-	// the node stack is not in use yet: its memory holds the packet's float64 directions for a moment
-	double* const dirs = reinterpret_cast<double*>(stack);
-	static_assert(sizeof(RtPNode) * RT_PACKET_STACK(PPL) >= sizeof(double) * 3 * 32 * PPL, "scratch for the packet's directions");
-	packet_directions<PPL>(F, pt, dirs);
+	packet_directions<PPL>(F, pt, dirs);  // float64, kept for the confirmations; the float32 copies go to `rays`
 	RT_LANES(l, lane) {
 		todo[l] = 0u;
 		negs[l] = 0u;
@@ -1069,11 +1064,12 @@ RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const RtPa
 		for (int j = 0; j < PPL; j++) {
 			double dir[3];
 			const int px = patch_x(pt, lane, j);
+			double* d = dirs + (size_t)(j * 32 + lane) * 3;
 			if (px < F.width) {  // (rows below the frame were produced with the last row's checkpoints)
-				const double* d = dirs + (size_t)(j * 32 + lane) * 3;
 				dir[0] = d[0]; dir[1] = d[1]; dir[2] = d[2];
 			} else {
 				pixel_dir_clamped(F, px, patch_y(pt, lane, j), dir);
+				d[0] = dir[0]; d[1] = dir[1]; d[2] = dir[2];
 			}
 			RtPRay q;
 			q.dx = (float)dir[0]; q.dy = (float)dir[1]; q.dz = (float)dir[2];
@@ -1151,7 +1147,7 @@ RT_HD void packet_primary_hits(const RtDevScene& S, const RtFrame& F, const RtPa
 		unsigned cls_rays[RT_NL];
 		RT_LANES(l, lane) { (void)lane; cls_rays[l] = open[l]; }
 		bool overflow = !(P.sin_h < 0.5f);  // not a narrow packet (tiny frames, huge fov): ray by ray
-		if (!overflow) packet_walk_class<PPL>(S, F, pt, rays, P, open, stack, hit, overflow);
+		if (!overflow) packet_walk_class<PPL>(S, F, pt, rays, dirs, P, open, stack, hit, overflow);
 		RT_LANES(l, lane) {
 			(void)lane;
 			todo[l] &= ~cls_rays[l];
@@ -1884,8 +1880,8 @@ RT_HD unsigned queue_reserve(unsigned* counter, unsigned n) {
 // `stage`: 96 floats per warp (device: shared memory) through which the 32 pixels of a sub-patch leave as whole
 // 16-byte words - full sectors, which is what matters when the frame lives in another GPU's or the host's memory.
 template <int PPL>
-RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, RtPNode* stack, RtPRay* rays, float* stage,
-                         uint32_t& err_out) {
+RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const RtPatch& pt, RtPNode* stack, RtPRay* rays, double* dirs,
+                         float* stage, uint32_t& err_out) {
 	unsigned skip[RT_NL];
 	int hit[RT_NL][PPL];
 	RT_LANES(l, lane) {
@@ -1897,7 +1893,7 @@ RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const RtPatch& p
 			hit[l][j] = valid ? RT_SLOT_UNKNOWN : RT_HIT_NONE;
 		}
 	}
-	if (F.packet_ok) packet_primary_hits<PPL>(S, F, pt, skip, stack, rays, hit);
+	if (F.packet_ok) packet_primary_hits<PPL>(S, F, pt, skip, stack, rays, dirs, hit);
 	// the hit codes move from registers into the ray table (the rays are not needed any more), so that the loop
 	// over the sub-patches below need not be unrolled
 	int* const codes = reinterpret_cast<int*>(rays);

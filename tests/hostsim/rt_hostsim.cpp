@@ -109,6 +109,7 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 		auto stage_a = [&](int t) {
 			std::vector<RtPNode> stack(RT_PACKET_STACK(HOSTSIM_PPL));
 			std::vector<RtPRay> rays(PPL * 32);
+			std::vector<double> dirs(PPL * 32 * 3);
 			float stage[96];
 			for (int p = t; p < my_tiles * PER_TILE; p += n_threads) {
 				const int k = p / PER_TILE;
@@ -119,7 +120,7 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 				pt.y0 = (tile / tiles_x) * 16;
 				pt.sub0 = (p % PER_TILE) * PPL;
 				pt.out_base = (size_t)k * 256;
-				primary_patch<PPL>(S, F, pt, stack.data(), rays.data(), stage, errs[t]);
+				primary_patch<PPL>(S, F, pt, stack.data(), rays.data(), dirs.data(), stage, errs[t]);
 			}
 		};
 		std::vector<std::thread> th;
