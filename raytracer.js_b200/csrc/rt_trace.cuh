@@ -1592,25 +1592,26 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 }
 
 // A ray whose stack overflowed (W.overflow: trees much deeper than the stack was sized for) is searched again from
-// scratch by the reference-order walker, which needs no stack - slower, never wrong.  Out of line: rare.
-RT_COLD int search_without_stack(const RtDevScene& S, const RtRayF& r, int node, int octant, const double* o, const double* d,
-                                 RtCollision& ci) {
+// scratch by the reference-order walker, which needs no stack - slower, never wrong.  Out of line and by VALUE: the
+// hot loop's path state must not have its address taken for the sake of a branch that is almost never run.
+RT_COLD int search_without_stack(const RtDevScene& S, RtRayF r, int node, int octant, double ox, double oy, double oz, double dx,
+                                 double dy, double dz) {
 	RtSearch q;
 	q.r = r;
 	q.rel = nullptr;
 	q.chain_mask = 0xffffffffu;
 	q.chain_levels = 0;
 	RtCounts cnt = {0, 0, 0, 0, 0};
+	RtCollision ci;
+	const double o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
 	return walk_and_scan<false>(S, q, node, octant, o, d, ci, cnt);
 }
 
 // after the ordered walk: the collision of the slot it found
 RT_HD void segment_found(const RtDevScene& S, const RtPath& P, const RtWalk& W, int& slot, RtCollision& ci) {
-	if (W.overflow) {
-		slot = search_without_stack(S, W.r, P.node, P.octant, P.refpoint, P.dir, ci);
-		return;
-	}
 	slot = W.hit;
+	if (W.overflow)
+		slot = search_without_stack(S, W.r, P.node, P.octant, P.refpoint[0], P.refpoint[1], P.refpoint[2], P.dir[0], P.dir[1], P.dir[2]);
 	if (slot >= 0 && !confirm_slot(S, slot, P.refpoint, P.dir, ci)) slot = -1;  // (same formula as in the walk: cannot fail)
 }
 
