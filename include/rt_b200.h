@@ -342,7 +342,7 @@ uint64_t rt_launch_count(const rt_ctx* ctx);
  * did not run.  The events add a little launch gap: keep it off in the timed region of a benchmark. */
 #define RT_STAGE_PREPARE 0  /* per-camera origin-relative records */
 #define RT_STAGE_PRIMARY 1  /* camera rays: packet walk + shading of the paths that end at their first hit */
-#define RT_STAGE_SHADE 2    /* (unused since ABI 2: the primary stage shades) */
+#define RT_STAGE_SHADE 2    /* refmax > 1: the continuation queue is put in output order (the primary stage itself shades) */
 #define RT_STAGE_BOUNCE 3   /* continued paths */
 #define RT_STAGE_RESAMPLE 4 /* (pixel, frame) samples of rough pixels, n_frames >= 8 */
 #define RT_N_STAGES 5

@@ -156,6 +156,42 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
 	if (err) atomicOr(F.error_flags, err);
 }
 
+// The continuation queue in OUTPUT ORDER (refmax > 1): the primary stage left one code per pixel; one thread per pixel,
+// one warp-aggregated atomic per 32 pixels.  Blocks start in index order, so the queue comes out (nearly) sorted by
+// pixel: a bounce-stage warp's 32 rays, and the warps beside it, start from neighbouring pixels - which is what keeps
+// their node and list fetches in the L1 (measured: appending in packet-completion order cost the bounce stage 17 %).
+__global__ void __launch_bounds__(256)
+    rt_queue_compact_kernel(const __grid_constant__ RtFrame F, int tiles_x, size_t n_out) {
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	int code = RT_NOT_QUEUED, x = 0, y = 0;
+	if (t < n_out) {
+		size_t i = F.out_first + t;
+		bool valid = true;
+		if (F.tile_compact || F.tile_world > 1) {
+			const int k = (int)(t / RT_BLOCK), in = (int)(t % RT_BLOCK);
+			const int tile = F.tile_begin + F.tile_rank + k * F.tile_world;
+			valid = tile < F.tile_end;
+			x = (tile % tiles_x) * RT_TILE_W + (in & (RT_TILE_W - 1));
+			y = (tile / tiles_x) * RT_TILE_H + (in / RT_TILE_W);
+			valid = valid && x < F.width && y < F.height;
+			i = F.tile_compact ? t : (size_t)y * F.width + x;
+		} else {
+			y = (int)(i / (size_t)F.width);
+			x = (int)(i - (size_t)y * F.width);
+		}
+		if (valid) code = F.queue_dense[i];
+	}
+	const bool enqueue = code != RT_NOT_QUEUED;
+	const unsigned m = __ballot_sync(0xffffffffu, enqueue);
+	if (m) {
+		unsigned base = 0;
+		if (lane == 0) base = atomicAdd(F.queue_count, (unsigned)__popc(m));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (enqueue) F.queue[base + __popc(m & ((1u << lane) - 1u))] = RtQueueItem{((uint32_t)y << 16) | (uint32_t)x, code};
+	}
+}
+
 // Bounce stage: persistent wavefront with a per-warp ray queue.  Every lane owns one pixel job (all its
 // exposure frames) and is in one of four states:
 //   IDLE   no job: refilled from the continuation queue (one atomic per refill, ranks by popc of the vote);
@@ -684,6 +720,7 @@ struct rt_ctx {
 	DevBuf<RtF4> prim_geom;
 	DevBuf<RtQueueItem> queue;
 	DevBuf<RtQueueItem> vqueue;
+	DevBuf<int> queue_dense;
 	DevBuf<double> present_partial;              // 3 x blocks partial sums + 8 stats (rt_present_device)
 	DevBuf<uint8_t> rgba;                        // RGBA8 image of rt_present / rt_render_present
 	int present_blocks = 0;
@@ -696,6 +733,7 @@ struct rt_ctx {
 	int primary_minb = RT_A_MINB;                // tuning knob RT_B200_PRIMARY_MINB=4|5|6: resident CTAs per SM the primary stage is compiled for
 	int bounce_min_walking = 12;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
 	int resample_min_frames = 8;                 // tuning knob RT_B200_RESAMPLE_MIN
+	bool ordered_queue = true;                   // tuning knob RT_B200_ORDERED_QUEUE=0: packets append to the continuation queue as they finish
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
 	int bounce_minb = 8;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
 	int bounce_node_batch = 4;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
@@ -857,6 +895,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 		                                : (size_t)F.width * F.height;
 		RT_CUDA(ctx, ctx->queue.alloc(cap));
 		if (resample) RT_CUDA(ctx, ctx->vqueue.alloc(cap));
+		if (prm->refmax > 1 && ctx->ordered_queue) RT_CUDA(ctx, ctx->queue_dense.alloc(cap));
 	}
 	auto grid_of = [&](int which, const void* kernel, int threads, int& out) -> rt_status {
 		int& grid = ctx->render_grid[which];
@@ -949,6 +988,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 			if (pipeline) {
 				// primary stage (packet walk) -> shade stage -> bounce stage over the continuation queue
 				F.queue = ctx->queue.p + F.out_first;
+				F.queue_dense = prm->refmax > 1 && ctx->ordered_queue ? ctx->queue_dense.p : nullptr;
 				F.vqueue = resample ? ctx->vqueue.p + F.out_first : nullptr;
 				const int n_packets = my_tiles * (8 / ppl);
 				const int blocks = std::min(grid_primary, (n_packets + RT_A_WARPS - 1) / RT_A_WARPS);
@@ -956,6 +996,12 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				RT_CUDA(ctx, cudaLaunchKernel(primary_kernel, dim3(blocks), dim3(RT_A_WARPS * 32), args, 0, ctx->stream));
 				ctx->launches++;
 				RT_CUDA(ctx, mark(2));
+				if (F.queue_dense) {
+					rt_queue_compact_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(F, tiles_x, n_out);
+					ctx->launches++;
+					ctx->stage_ran[2] = prof;
+					RT_CUDA(ctx, cudaGetLastError());
+				}
 				RT_CUDA(ctx, mark(3));
 				void* bargs[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x};
 				// with refmax <= 1 no path continues after its first hit: the queue only ever holds rays the lock-step
@@ -1262,6 +1308,7 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 		if (v >= 1 && v <= 32) ctx->bounce_min_walking = v;
 	}
 	if (const char* e = getenv("RT_B200_RESAMPLE")) ctx->resample = atoi(e) != 0;
+	if (const char* e = getenv("RT_B200_ORDERED_QUEUE")) ctx->ordered_queue = atoi(e) != 0;
 	if (const char* e = getenv("RT_B200_RESAMPLE_MIN")) ctx->resample_min_frames = std::max(2, atoi(e));
 	if (const char* e = getenv("RT_B200_BOUNCE_MINB")) {
 		const int v = atoi(e);
@@ -1384,7 +1431,7 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->ray_ck.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
-	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->peer_flags.release();
+	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->queue_dense.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->peer_flags.release();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	for (int b = 0; b < RT_MAX_BANDS; b++)

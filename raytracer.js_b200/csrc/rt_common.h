@@ -133,6 +133,7 @@ struct alignas(8) RtQueueItem {
 	int32_t slot; // first-hit slot of the camera ray, or RT_SLOT_UNKNOWN
 };
 #define RT_SLOT_UNKNOWN (-2)
+#define RT_NOT_QUEUED (-3)
 // Node stack of the packet walk, in records per warp (shared memory): a packet usually keeps at most 3-4 pending
 // siblings per level (the packet is narrow), so 96 records cover trees far deeper than float32 can resolve; a walk
 // that would overflow hands its rays to the bounce stage instead (RT_SLOT_UNKNOWN), never drops a node silently.
@@ -190,6 +191,7 @@ struct RtFrame {
 	int* hit_slots;          // [pixels of this rank, output order] first-hit slots: primary stage -> shade stage
 	// continuation queue between the shade stage and the bounce stage
 	RtQueueItem* queue;      // [capacity]
+	int* queue_dense;        // [pixels, output order] or null: per-pixel code (first-hit slot, RT_SLOT_UNKNOWN, RT_NOT_QUEUED) the primary stage leaves for rt_queue_compact_kernel
 	unsigned* queue_count;   // items appended by the primary stage
 	unsigned* queue_taken;   // consumer cursor of the bounce stage
 	// resample queue between the bounce stage and the resample stage (n_frames > 1): the pixels whose path

@@ -1992,6 +1992,16 @@ RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const RtPatch& p
 				o[0] = px[0][0]; o[1] = px[0][1]; o[2] = px[0][2];
 			}
 			if (done[0] && F.first_ids) F.first_ids[out_index[0]] = first_entity[0];
+			if (F.queue_dense) {
+				// ordered continuation queue (refmax > 1): every pixel leaves its code in place, and a compaction pass
+				// builds the queue in output order, so that the 32 pixels a bounce-stage warp takes - and the warps
+				// that run beside it - are neighbours in the frame, whatever order the packets finished in
+				if (!((skip[0] >> j) & 1u)) {
+					const int code = codes[j * 32 + lane];
+					F.queue_dense[out_index[0]] = !enqueue[0] ? RT_NOT_QUEUED : (code == RT_SLOT_UNKNOWN ? RT_SLOT_UNKNOWN : (code & RT_HIT_SLOT_MASK));
+				}
+				continue;
+			}
 			const unsigned m = __ballot_sync(0xffffffffu, enqueue[0]);
 			if (m) {
 				unsigned base = 0;

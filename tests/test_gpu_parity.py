@@ -341,9 +341,10 @@ def test_repeated_device_renders_replay_a_graph():
         else:
             frames[name] = out.clone()
     assert not torch.equal(frames["a"], frames["b"])
-    # every call is three launches: frame setup (control cells; per camera pose the origin-relative records, per
-    # camera basis the ray generation - a replayed graph carries neither), primary stage, bounce stage
-    assert launches == [3] * len(launches), launches
+    # every call is four launches: frame setup (control cells; per camera pose the origin-relative records, per
+    # camera basis the ray generation - a replayed graph carries neither), primary stage, queue compaction (refmax > 1),
+    # bounce stage
+    assert launches == [4] * len(launches), launches
 
 
 @pytest.mark.parametrize("max_in_depth", [20, 23])
