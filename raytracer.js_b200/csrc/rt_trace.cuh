@@ -1257,10 +1257,12 @@ struct RtWalk {
 #else
 #define RT_WALK_CAP RT_WALK_STACK
 #endif
-RT_HD void walk_push(RtWalk& W, int v) {
-	if (W.sp < RT_WALK_CAP) W.stack[W.sp++] = v;
-	else W.overflow = 1;  // never a silent drop: the ray is searched again by the reference-order walker
-}
+// One iteration of the walk pushes at most 8 children, a list root and two BVH nodes: the room for that is checked
+// ONCE per iteration (walk_iter), not per push - a ray that runs out of stack is never dropped silently, it is
+// searched again by the reference-order walker (W.overflow, segment_found).
+#define RT_WALK_PUSHES_PER_ITER 11
+static_assert(RT_WALK_CAP > RT_WALK_PUSHES_PER_ITER, "walk stack smaller than one iteration's pushes");
+RT_HD void walk_push(RtWalk& W, int v) { W.stack[W.sp++] = v; }
 
 // pushes the children of `nd` the ray may pierce, last-visited first.  In the ray's own frame (axis k
 // mirrored when d_k < 0) the half of the cube entered first is "half 0": key bit k of a child says which
@@ -1399,6 +1401,10 @@ RT_HD void walk_leaf(const RtDevScene& S, RtWalk& W, int leaf_a, const double* o
 // diverged warp (ray-by-ray kernels) and no warp-wide barrier is used.
 template <bool LOCKSTEP>
 RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const double* d, bool walking, int node_batch = 1) {
+	if (walking && W.sp > RT_WALK_CAP - RT_WALK_PUSHES_PER_ITER) {  // no room for this iteration's pushes
+		W.overflow = 1;
+		walking = false;
+	}
 	// ---- node step.  It is several times the cost of a list step, so in lock-step the lanes that need one
 	// wait until `node_batch` of them do (or no lane is inside a list), and then take it together.
 	bool node_step = walking && !W.in_list;
@@ -1476,7 +1482,6 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 	if (LOCKSTEP) warp_sync();
 	if (leaf1 >= 0) walk_leaf(S, W, leaf1, o, d);
 	if (LOCKSTEP) warp_sync();
-	if (walking && W.overflow) walking = false;
 	if (walking && W.in_list && W.sp == W.floor) {  // the list is finished
 		W.in_list = 0;
 		if (W.best != RT_NO_SLOT) {

@@ -384,14 +384,14 @@ def test_published_entity_counts_small_frames(oracle):
 
 def test_walk_stack_overflow_falls_back_to_the_reference_order_walker(oracle, tmp_path):
     """A ray whose ordered walk needs more stack than it has (RtWalk.overflow) is searched again by the
-    reference-order walker: same pixels.  The kernel body is built here with a 6-entry stack, so that most
+    reference-order walker: same pixels.  The kernel body is built here with a 16-entry stack (5 free entries at the start of an iteration are the limit), so that most
     secondary rays of a mirror scene overflow."""
     import ctypes as C
     import subprocess
     import util
     from raytracer_js_b200 import _native as N
-    lib = tmp_path / "librt_hostsim_cap6.so"
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-pthread", "-shared", "-DRT_TEST_WALK_CAP=6",
+    lib = tmp_path / "librt_hostsim_cap16.so"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-pthread", "-shared", "-DRT_TEST_WALK_CAP=16",
                            "-Wno-unknown-pragmas", "-Wno-comment", "-o", str(lib), util.os.path.join(util.HOSTSIM_DIR, "rt_hostsim.cpp")])
     L = C.CDLL(str(lib))
     L.hostsim_render.restype = C.c_int
