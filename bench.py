@@ -172,6 +172,91 @@ def committed_profile(stage: str):
     return {"file": f"profiles/{f}", "stale": d.get("fingerprint") != source_fingerprint(), "data": d[stage]}
 
 
+def group_records(args, lib, n_gpus, flat, sky_tex, def_sub, cds, warm):
+    """rt_create_multi(n_gpus) in THIS process: the headline frame and a configs[4]-class frame on n_gpus GPUs."""
+    import numpy as np
+    import raytracer_js_b200 as rt
+    from raytracer_js_b200 import _native as N
+    from raytracer_js_b200 import scenes
+    out = {"n_gpus": n_gpus, "how": "one process, rt_create_multi: scene packed once and replicated device to device, one worker "
+                                    "thread per GPU, interleaved 16x16 tiles; device frame on GPU 0 (peer stores) / host frame mapped into every GPU"}
+    g = C.c_void_p()
+    N.check(None, lib.rt_create_multi(n_gpus, None, C.byref(g)))
+    try:
+        t0 = time.perf_counter()
+        d = flat.desc()
+        N.check(g, lib.rt_scene_upload(g, C.byref(d)))
+        out["scene_upload_s"] = time.perf_counter() - t0
+        prm = N.Params()
+        prm.refmax, prm.sky_texture, prm.default_substance = 1, sky_tex, def_sub
+        prm.distance_attenuation_factor, prm.n_frames, prm.frame_first, prm.rng_seed = 1.0, 1, 0, 1.0
+        npx = WIDTH * HEIGHT
+        import torch
+        frame = torch.zeros(npx * 3, dtype=torch.float32, device="cuda:0")
+        el = C.c_float()
+
+        def timed(cam):
+            N.check(g, lib.rt_flush_l2(g))
+            N.check(g, lib.rt_timer_start(g))
+            N.check(g, lib.rt_render_device(g, C.byref(cam), C.byref(prm), 0, C.c_void_p(frame.data_ptr()), None))
+            N.check(g, lib.rt_timer_stop(g, C.byref(el)))
+            return el.value
+
+        for i in range(warm):
+            timed(cds[i])
+        ms = sum(timed(cds[warm + i]) for i in range(args.steps)) / args.steps
+        out["headline"] = {"ms_per_step": ms, "value": npx / (ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                           "timing": "CUDA events on GPU 0's stream around the whole group frame (it waits for the other GPUs' events)"}
+        host = np.zeros(npx * 3, np.float32)
+        for i in range(3):
+            N.check(g, lib.rt_render(g, C.byref(cds[i]), C.byref(prm), 0, host.ctypes.data, None, None))
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            N.check(g, lib.rt_render(g, C.byref(cds[warm + i]), C.byref(prm), 0, host.ctypes.data, None, None))
+        dt = time.perf_counter() - t0
+        out["headline"]["e2e"] = {"value": npx * args.steps / dt / 1e6, "unit": "Mrays/s", "frame_ms": dt / args.steps * 1e3,
+                                  "d2h_bytes_per_step": npx * 12, "delivery": "every GPU stores its tiles into the mapped host frame over its own PCIe link"}
+        del frame
+        # ---- configs[4] class
+        cfg = dict(scenes.BASELINE_CONFIGS["c4"])
+        cfg["spp"] = 8
+        t0 = time.perf_counter()
+        fb = scenes.build_config(cfg)
+        t_build = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        d4 = fb.flat.desc()
+        N.check(g, lib.rt_scene_upload(g, C.byref(d4)))
+        t_up = time.perf_counter() - t0
+        W4, H4 = cfg["w"], cfg["h"]
+        cd4 = rt.camera_desc(scenes.bench_camera(W4, H4))
+        p4 = N.Params()
+        p4.refmax, p4.sky_texture, p4.default_substance = fb.refmax, fb.sky_texture, fb.default_substance
+        p4.distance_attenuation_factor, p4.n_frames, p4.frame_first, p4.rng_seed = 1.0, 1, 0, 1.0
+        frame4 = torch.zeros(W4 * H4 * 3, dtype=torch.float32, device="cuda:0")
+        N.check(g, lib.rt_render_device(g, C.byref(cd4), C.byref(p4), N.RT_RENDER_COUNTERS, C.c_void_p(frame4.data_ptr()), None))
+        cnt = N.Counters()
+        N.check(g, lib.rt_get_counters(g, C.byref(cnt)))
+        seg_per_path = cnt.segments / max(cnt.paths, 1)
+        p4.n_frames = cfg["spp"]
+        times = []
+        for i in range(3):
+            N.check(g, lib.rt_flush_l2(g))
+            N.check(g, lib.rt_timer_start(g))
+            N.check(g, lib.rt_render_device(g, C.byref(cd4), C.byref(p4), 0, C.c_void_p(frame4.data_ptr()), None))
+            N.check(g, lib.rt_timer_stop(g, C.byref(el)))
+            if i:
+                times.append(el.value)
+        ms4 = sum(times) / len(times)
+        paths = W4 * H4 * cfg["spp"]
+        out["c4_class"] = {"workload": f"{W4}x{H4}, {cfg['spp']} spp (of configs[4]'s 64), 1 M spheres d in [0.0005,0.002], mirror mix, refmax 4",
+                           "frame_ms": ms4, "Mrays_per_s": paths * seg_per_path / ms4 / 1e3, "Mpaths_per_s": paths / ms4 / 1e3,
+                           "segments_per_path": seg_per_path, "scene_build_s": t_build, "scene_upload_s": t_up,
+                           "finite": bool(torch.isfinite(frame4).all())}
+    finally:
+        lib.rt_destroy(g)
+    return out
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import numpy as np
     import torch
@@ -471,6 +556,32 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     if peer is not None:
         peer.close()
+    # ---- the in-library group (rt_create_multi): ONE process - rank 0 - drives all N GPUs behind the plain entry
+    # points, the other ranks wait at the barrier with their GPUs idle.  (a) the headline frame: device-resident on
+    # GPU 0 and end to end into a host buffer; (b) a configs[4]-class frame (8K, 1 M spheres, mirror mix, 8 spp) on
+    # the same N GPUs, for the scaling of a frame that is long enough to scale.
+    group = None
+    store = None
+    if world > 1:
+        barrier()
+        try:  # the other ranks wait on the HOST (a key in the rendezvous store): an NCCL barrier would spin on their GPUs
+            store = dist.distributed_c10d._get_default_store()
+        except Exception:
+            store = None
+    if rank == 0 and not args.no_group:
+        try:
+            group = group_records(args, lib, world, flat, sky_tex, def_sub, cds, warm)
+        except Exception as e:  # reported, never fatal for the contract line
+            group = {"error": repr(e)[:300]}
+    if world > 1:
+        if store is not None:
+            if rank == 0:
+                store.set("rt_group_done", "1")
+            else:
+                import datetime
+                store.wait(["rt_group_done"], datetime.timedelta(seconds=600))
+        else:
+            barrier()
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -527,6 +638,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "precision": "float32 search + float64 confirmation/shading of the found hit",
                    "path": args.path},
         "clocks": clocks, "e2e": e2e, "present": present, "gpu_launches": launches, "roofline": roof,
+        "single_process_group": group,
     }
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -558,6 +670,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-group", action="store_true", help="skip the rt_create_multi records (single_process_group)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = kernels store into rank 0's frame over NVLink (CUDA IPC); nccl = all-gather + untile")
     ap.add_argument("--path", default="pipeline", choices=["pipeline", "per-ray"],

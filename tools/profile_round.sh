@@ -7,9 +7,9 @@ O=gpurun_out
 set -x
 timeout 200 python bench.py --steps 20 --warmup 3 > $O/${TAG}_bench.log 2>$O/${TAG}_bench.err || exit 1
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_launch.log 2>&1
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-group > $O/${TAG}_ncu_launch.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rt_primary_kernel -s 4 -c 1 -f -o $O/prof_${TAG}_primary \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_primary.log 2>&1
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-group > $O/${TAG}_ncu_primary.log 2>&1
 timeout 100 python tools/config_bench.py c2 --spp 1 > $O/${TAG}_c2_1spp.log 2>&1 || exit 1
 timeout 100 python tools/config_bench.py c2 > $O/${TAG}_c2_16spp.log 2>&1
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/${TAG}_c2_launches.csv \

@@ -6,7 +6,7 @@ O=gpurun_out
 : > $O/${TAG}_sweep.jsonl
 for ppl in 4 8; do
   for minb in 4 5 6; do
-    RT_B200_PPL=$ppl RT_B200_PRIMARY_MINB=$minb timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>>$O/${TAG}_sweep.err \
+    RT_B200_PPL=$ppl RT_B200_PRIMARY_MINB=$minb timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-group 2>>$O/${TAG}_sweep.err \
       | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
