@@ -196,6 +196,17 @@ rt_status rt_set_stream(rt_ctx* ctx, void* cuda_stream);
 /* Validates and copies the scene to the device (replaces any previous scene of the ctx). */
 rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* scene);
 
+/* Dynamic scenes: move entities the way the reference does - BasicEntity._set_pos
+ * (src/entities/entity_basic.ts:38-42) followed by add_entity_to_octree again (src/octree_entity.ts:174-188), whose
+ * Entity.set_octree (src/entity.ts:50-56) takes the entity out of its node's Set and adds it to the END of the Set of the
+ * node that now covers it; nodes are created on the way (max_in_depth as in AddEntityToOctreeFlags, max_out_depth = 0)
+ * and never removed.  The library applies the moves, in the order given, to the copy of the description it kept at
+ * rt_scene_upload - the caller passes only the moved entities, no re-flattening of its own tree - and refreshes the
+ * device scene (of every GPU of a group).  entity_ids index the entity arrays of the uploaded description.  Where the
+ * reference throws TreeOutsideGrowError the call fails with RT_ERR_UNSUPPORTED and the scene is unchanged. */
+rt_status rt_scene_update(rt_ctx* ctx, uint32_t n_moved, const uint32_t* entity_ids, const double* new_pos /* [n_moved*3] */,
+                          uint32_t max_in_depth);
+
 /* ---- render: the trace_frame() drop-in ------------------------------------------------------- */
 /* Host buffers.  rgb: float32 [height][width][3], the ExposureBuffer pixel store, read when
  * frame_first > 0 and always written.  first_ids (optional): int32 [height][width], the entity of

@@ -78,6 +78,7 @@ def lib():
         "orc_add_texture_image": (i32, [vp, i32, i32, C.c_void_p, dp]),
         "orc_add_entity": (i32, [vp, i32, dp, f64, i32, i32, i32, i32, i32]),
         "orc_add_entities": (i32, [vp, i32, C.c_void_p, dp, dp, ip, ip, ip, i32, i32]),
+        "orc_move_entity": (i32, [vp, i32, dp, i32, i32]),
         "orc_new_subtree": (i32, [vp, ip, i32, i32]),
         "orc_flat_counts": (None, [vp, up, up]),
         "orc_flat_export": (None, [vp, dp, dp, ip, ip, ip, up, up, ip]),
@@ -184,6 +185,14 @@ class Scene:
         if r < 0:
             raise RuntimeError(f"entity {-1 - r}: " + self._L.orc_scene_error(self._h).decode())
         return r
+
+    def move_entity(self, eid, pos, max_in_depth=16, max_out_depth=0):
+        """_set_pos + add_entity_to_octree again: out of its node's Set, to the END of the new node's."""
+        r = self._L.orc_move_entity(self._h, int(eid), _dp(_v3(pos)), int(max_in_depth), int(max_out_depth))
+        if r == -1:
+            raise RuntimeError(self._L.orc_scene_error(self._h).decode())
+        if r != 0:
+            raise IndexError(f"entity {eid}")
 
     def new_subtree(self, path, n):
         p = np.ascontiguousarray(path, dtype=np.int32)

@@ -939,6 +939,34 @@ int32_t orc_add_entity(void* h, int32_t type, const double* pos, double extent, 
 	e.substance = substance;
 	return add_entity(*s, e, max_in_depth, max_out_depth);
 }
+// Moving an entity as the reference does it: BasicEntity._set_pos (src/entities/entity_basic.ts:38-42), then
+// add_entity_to_octree again (src/octree_entity.ts:174-188), whose Entity.set_octree (src/entity.ts:50-56) deletes the
+// entity from the Set of the node it was in and adds it to the END of the new node's Set.  0 / -1 (TreeOutsideGrowError).
+int32_t orc_move_entity(void* h, int32_t id, const double* pos, int32_t max_in_depth, int32_t max_out_depth) {
+	Scene& s = *(Scene*)h;
+	if (id < 0 || id >= (int)s.entities.size()) return -2;
+	Entity& e = s.entities[id];
+	e.pos = {pos[0], pos[1], pos[2]};
+	V3 apos;
+	double asize;
+	entity_aabb(e, apos, asize);
+	Node* fitting = get_covering_node(s, apos, asize);
+	if (fitting == nullptr) {
+		fitting = extend_outside(s, s.root, s.abs_root(), apos, asize, max_out_depth);
+		if (fitting == nullptr) {
+			s.error = "TreeOutsideGrowError: The tree outside-depth limit exceeded";
+			return -1;
+		}
+	}
+	fitting = extend_inside(s, s.root, fitting, apos, asize, max_in_depth);
+	if (e.node) {  // set_octree: this._octree.value.set.delete(this)
+		std::vector<int>& old = e.node->set;
+		old.erase(std::find(old.begin(), old.end(), id));
+	}
+	e.node = fitting;
+	fitting->set.push_back(id);  // tree.value.set.add(this): insertion order, i.e. last
+	return 0;
+}
 // bulk variant of orc_add_entity (same order, same semantics); stops at the first error.
 int32_t orc_add_entities(void* h, int32_t n, const uint8_t* type, const double* pos, const double* extent,
                          const int32_t* material, const int32_t* texture, const int32_t* substance,

@@ -77,6 +77,7 @@ EXPORTS = {
     "rt_last_error": (C.c_char_p, [C.c_void_p]),
     "rt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_scene_upload": (C.c_int, [C.c_void_p, C.POINTER(SceneDesc)]),
+    "rt_scene_update": (C.c_int, [C.c_void_p, C.c_uint32, _up, _dp, C.c_uint32]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32, C.c_void_p,
                             C.c_void_p, C.POINTER(Counters)]),
     "rt_render_device": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32, C.c_void_p,

@@ -674,6 +674,7 @@ struct rt_ctx {
 
 	// packed host copy (also serves the once-per-frame start state); the members of a multi-GPU group share one
 	std::shared_ptr<RtHostScene> host_p = std::make_shared<RtHostScene>();
+	RtSceneCopy scene_copy;  // the uploaded description, kept for rt_scene_update
 	RtHostScene& host_ref() { return *host_p; }
 	// ---- multi-GPU group (rt_create_multi): ONE process drives every GPU.  The ctx handed to the caller is the
 	// leader (group[0] == this); members[1..] own a device, a stream and a worker thread that enqueues their share
@@ -1556,6 +1557,7 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	std::string err;
 	auto hs = std::make_shared<RtHostScene>();
 	if (rt_status st = rt_pack_scene(sc, *hs, err)) return fail(ctx, st, err);  // validated and packed ONCE, on the host
+	if (sc->node_size != ctx->scene_copy.node_size.data()) ctx->scene_copy.assign(*sc);  // (not when rt_scene_update hands its own copy back)
 	std::vector<rt_ctx*> all = ctx->group.empty() ? std::vector<rt_ctx*>{ctx} : ctx->group;
 	for (rt_ctx* m : all) {
 		m->has_scene = false;
@@ -1588,6 +1590,19 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	}
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
 	return RT_OK;
+}
+
+rt_status rt_scene_update(rt_ctx* ctx, uint32_t n_moved, const uint32_t* entity_ids, const double* new_pos, uint32_t max_in_depth) {
+	if (!ctx) return RT_ERR_INVALID;
+	if (ctx->leader) return fail(ctx, RT_ERR_INVALID, "rt_scene_update: this ctx is a member of a multi-GPU group; update through its leader");
+	if (!ctx->has_scene || !ctx->scene_copy.valid) return fail(ctx, RT_ERR_NO_SCENE, "rt_scene_update: no scene uploaded");
+	if (n_moved && (!entity_ids || !new_pos)) return fail(ctx, RT_ERR_INVALID, "rt_scene_update: NULL argument");
+	if (n_moved == 0) return RT_OK;
+	std::string err;
+	if (!rt_scene_move_entities(ctx->scene_copy, n_moved, entity_ids, new_pos, max_in_depth, err))
+		return fail(ctx, err.find("outside-depth") != std::string::npos ? RT_ERR_UNSUPPORTED : RT_ERR_INVALID, err);
+	const rt_scene_desc d = ctx->scene_copy.desc();
+	return rt_scene_upload(ctx, &d);
 }
 
 rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb_dev,

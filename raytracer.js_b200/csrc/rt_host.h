@@ -38,6 +38,138 @@ struct RtHostScene {
 	int max_depth = 0;  // deepest node level (root = 0)
 };
 
+inline std::string rt_format(const char* fmt, ...);
+
+// A deep, mutable copy of an rt_scene_desc: what rt_scene_update edits (the caller's arrays were only borrowed
+// for the duration of rt_scene_upload).
+struct RtSceneCopy {
+	std::vector<double> node_pos, node_size, ent_pos, ent_extent, mat_roughness, tex_color, sub_refractive_index;
+	std::vector<int32_t> node_child, node_parent, node_octant, ent_material, ent_texture, ent_substance, tex_width, tex_height;
+	std::vector<uint32_t> node_list_off, list_entity;
+	std::vector<uint8_t> ent_type, mat_response, mat_light, mat_mirror, tex_kind, tex_loaded, texels;
+	std::vector<uint64_t> tex_texel_off;
+	bool valid = false;
+
+	void assign(const rt_scene_desc& d) {
+		const size_t N = d.n_nodes, L = d.n_list, E = d.n_entities, M = d.n_materials, T = d.n_textures, S = d.n_substances;
+		auto cp = [](auto& v, const auto* p, size_t n) { if (p && n) v.assign(p, p + n); else v.clear(); };
+		cp(node_pos, d.node_pos, 3 * N); cp(node_size, d.node_size, N); cp(node_child, d.node_child, 8 * N);
+		cp(node_parent, d.node_parent, N); cp(node_octant, d.node_octant, N); cp(node_list_off, d.node_list_off, N + 1);
+		cp(list_entity, d.list_entity, L);
+		cp(ent_type, d.ent_type, E); cp(ent_pos, d.ent_pos, 3 * E); cp(ent_extent, d.ent_extent, E);
+		cp(ent_material, d.ent_material, E); cp(ent_texture, d.ent_texture, E); cp(ent_substance, d.ent_substance, E);
+		cp(mat_response, d.mat_response, M); cp(mat_light, d.mat_light, M); cp(mat_mirror, d.mat_mirror, M); cp(mat_roughness, d.mat_roughness, M);
+		cp(tex_kind, d.tex_kind, T); cp(tex_color, d.tex_color, 4 * T); cp(tex_width, d.tex_width, T); cp(tex_height, d.tex_height, T);
+		cp(tex_loaded, d.tex_loaded, T); cp(tex_texel_off, d.tex_texel_off, T); cp(texels, d.texels, (size_t)d.n_texels * 3);
+		cp(sub_refractive_index, d.sub_refractive_index, S);
+		valid = true;
+	}
+	rt_scene_desc desc() const {
+		rt_scene_desc d;
+		memset(&d, 0, sizeof d);
+		d.struct_size = (uint32_t)sizeof d;
+		auto ptr = [](const auto& v) { return v.empty() ? nullptr : v.data(); };
+		d.n_nodes = (uint32_t)node_size.size();
+		d.node_pos = ptr(node_pos); d.node_size = ptr(node_size); d.node_child = ptr(node_child); d.node_parent = ptr(node_parent);
+		d.node_octant = ptr(node_octant); d.node_list_off = ptr(node_list_off);
+		d.n_list = (uint32_t)list_entity.size(); d.list_entity = ptr(list_entity);
+		d.n_entities = (uint32_t)ent_extent.size();
+		d.ent_type = ptr(ent_type); d.ent_pos = ptr(ent_pos); d.ent_extent = ptr(ent_extent); d.ent_material = ptr(ent_material);
+		d.ent_texture = ptr(ent_texture); d.ent_substance = ptr(ent_substance);
+		d.n_materials = (uint32_t)mat_roughness.size();
+		d.mat_response = ptr(mat_response); d.mat_light = ptr(mat_light); d.mat_mirror = ptr(mat_mirror); d.mat_roughness = ptr(mat_roughness);
+		d.n_textures = (uint32_t)tex_kind.size();
+		d.tex_kind = ptr(tex_kind); d.tex_color = ptr(tex_color); d.tex_width = ptr(tex_width); d.tex_height = ptr(tex_height);
+		d.tex_loaded = ptr(tex_loaded); d.tex_texel_off = ptr(tex_texel_off);
+		d.n_texels = texels.size() / 3; d.texels = ptr(texels);
+		d.n_substances = (uint32_t)sub_refractive_index.size(); d.sub_refractive_index = ptr(sub_refractive_index);
+		return d;
+	}
+};
+
+// Moving entities the reference's way, on the flat tree: BasicEntity._set_pos (src/entities/entity_basic.ts:38-42)
+// followed by add_entity_to_octree (src/octree_entity.ts:174-188), whose Entity.set_octree (src/entity.ts:50-56)
+// deletes the entity from the Set of its node and adds it at the END of the Set of the node that now covers it
+// (the deepest cube, up to max_in_depth levels below the root, that contains the entity's cubic AABB: the placement
+// walk of rt_build.h, same float64 expressions; nodes are created on the way, never removed).  Moves are applied in
+// the order given.  false + message where the reference throws TreeOutsideGrowError (max_out_depth = 0); the copy is
+// then unchanged.
+inline bool rt_scene_move_entities(RtSceneCopy& sc, uint32_t n, const uint32_t* ids, const double* new_pos, uint32_t max_in_depth,
+                                   std::string& err) {
+	const size_t N0 = sc.node_size.size(), E = sc.ent_extent.size();
+	std::vector<double> node_pos = sc.node_pos, node_size = sc.node_size, ent_pos = sc.ent_pos;
+	std::vector<int32_t> child = sc.node_child, parent = sc.node_parent, octant = sc.node_octant;
+	std::vector<uint32_t> ent_node(E, 0), seq(E, 0);  // seq[e] = 0: still where the old lists have it
+	for (size_t i = 0; i < N0; i++)
+		for (uint32_t li = sc.node_list_off[i]; li < sc.node_list_off[i + 1]; li++) ent_node[sc.list_entity[li]] = (uint32_t)i;
+	struct Placed { uint32_t node, entity, seq; };
+	std::vector<Placed> placed;
+	for (uint32_t m = 0; m < n; m++) {
+		const uint32_t e = ids[m];
+		if (e >= E) { err = rt_format("rt_scene_update: entity %u out of range (%zu entities)", e, E); return false; }
+		const double ext = sc.ent_extent[e];
+		double mn[3];
+		for (int k = 0; k < 3; k++) {
+			ent_pos[3 * (size_t)e + k] = new_pos[3 * (size_t)m + k];
+			mn[k] = sc.ent_type[e] == 0 ? new_pos[3 * (size_t)m + k] - ext * 0.5 : new_pos[3 * (size_t)m + k] - ext / 2;
+		}
+		auto fits = [&](const double* p, double s) {
+			for (int k = 0; k < 3; k++)
+				if (!(mn[k] >= p[k] && mn[k] + ext <= p[k] + s)) return false;
+			return true;
+		};
+		bool inside = true;
+		for (int k = 0; k < 3; k++) inside = inside && mn[k] >= node_pos[k] && mn[k] < node_pos[k] + node_size[0];
+		if (!inside || !fits(node_pos.data(), node_size[0])) {
+			err = rt_format("The tree outside-depth limit exceeded (entity %u does not fit the root cube at its new position; max_out_depth is 0)", e);
+			return false;
+		}
+		uint32_t node = 0;
+		for (uint32_t depth = 0; depth < max_in_depth; depth++) {
+			const double* np = &node_pos[3 * (size_t)node];
+			const double ns = node_size[node], k2 = 2.0 / ns, hs = ns / 2;
+			int o[3];
+			double cp[3];
+			for (int k = 0; k < 3; k++) {
+				o[k] = (int)((mn[k] - np[k]) * k2);
+				cp[k] = np[k] + o[k] * hs;
+			}
+			if (!fits(cp, hs)) break;
+			const int idx = (o[2] << 2) | (o[1] << 1) | o[0];
+			int32_t ch = child[(size_t)node * 8 + idx];
+			if (ch < 0) {
+				ch = (int32_t)node_size.size();
+				child[(size_t)node * 8 + idx] = ch;
+				node_pos.insert(node_pos.end(), cp, cp + 3);
+				node_size.push_back(hs);
+				child.insert(child.end(), 8, -1);
+				parent.push_back((int32_t)node);
+				octant.push_back(idx);
+			}
+			node = (uint32_t)ch;
+		}
+		ent_node[e] = node;
+		seq[e] = m + 1;
+		placed.push_back(Placed{node, e, m + 1});
+	}
+	// the new lists: what is left of the old ones, in their order, then the arrivals in the order they came
+	const size_t N = node_size.size();
+	std::vector<uint32_t> off(N + 1, 0);
+	for (size_t e = 0; e < E; e++) off[ent_node[e] + 1]++;
+	for (size_t i = 0; i < N; i++) off[i + 1] += off[i];
+	std::vector<uint32_t> cur(off.begin(), off.end() - 1), list(sc.list_entity.size());
+	for (size_t i = 0; i < N0; i++)
+		for (uint32_t li = sc.node_list_off[i]; li < sc.node_list_off[i + 1]; li++) {
+			const uint32_t e = sc.list_entity[li];
+			if (seq[e] == 0) list[cur[i]++] = e;
+		}
+	for (const Placed& p : placed)
+		if (seq[p.entity] == p.seq) list[cur[p.node]++] = p.entity;
+	sc.node_pos.swap(node_pos); sc.node_size.swap(node_size); sc.node_child.swap(child); sc.node_parent.swap(parent);
+	sc.node_octant.swap(octant); sc.ent_pos.swap(ent_pos); sc.node_list_off.swap(off); sc.list_entity.swap(list);
+	return true;
+}
+
 inline std::string rt_format(const char* fmt, ...) {
 	char buf[512];
 	va_list ap;

@@ -116,6 +116,22 @@ class GpuRaytracer:
         d = self.flat.desc()
         N.check(self._ctx, self._lib.rt_scene_upload(self._ctx, C.byref(d)))
 
+    def move_entities(self, entities, positions, max_in_depth: int = 16) -> None:
+        """Dynamic scenes: move entities the reference's way - `_set_pos(p)` then
+        `add_entity_to_octree(tree, e, ...)` again, i.e. out of the node's Set and to the END of the Set of the node
+        that now covers it - both in the host octree and, through rt_scene_update, in the library's copy of the flat
+        scene: only the moved entities cross the boundary, the tree is not flattened again."""
+        from .octree_entity import add_entity_to_octree
+        index = {id(e): i for i, e in enumerate(self.flat.entities)}
+        ids = np.array([index[id(e)] for e in entities], np.uint32)
+        pos = np.ascontiguousarray([list(p.v) if hasattr(p, "v") else list(p) for p in positions], np.float64).reshape(-1, 3)
+        st = self._lib.rt_scene_update(self._ctx, len(ids), ids.ctypes.data_as(N._up), pos.ctypes.data_as(N._dp), int(max_in_depth))
+        N.check(self._ctx, st)
+        from .geometry import point
+        for e, p in zip(entities, pos):  # the host mirror follows (after the library accepted the moves)
+            e._set_pos(point(*p))
+            add_entity_to_octree(self._otree, e, {"max_in_depth": max_in_depth, "max_out_depth": 0})
+
     def params(self, n_frames: int = 1, frame_first: int = 0) -> N.Params:
         p = N.Params()
         p.refmax = self.config.refmax

@@ -30,6 +30,17 @@ extern "C" void hostsim_raygen(const rt_camera* cam, double* dirs) {
 		for (int x = 0; x < F.width; x++) pixel_dir(F, x, y, dirs + ((size_t)y * F.width + x) * 3);
 }
 
+// Entity moves (rt_host.h: rt_scene_move_entities, what rt_scene_update runs) applied to the description before the
+// next hostsim_render packs it; n == 0 clears them.
+static std::vector<uint32_t> g_move_ids;
+static std::vector<double> g_move_pos;
+static uint32_t g_move_depth = 16;
+extern "C" void hostsim_set_moves(uint32_t n, const uint32_t* ids, const double* pos, uint32_t max_in_depth) {
+	g_move_ids.assign(ids, ids + n);
+	g_move_pos.assign(pos, pos + 3 * (size_t)n);
+	g_move_depth = max_in_depth;
+}
+
 // Debugging aid: restrict the ray-by-ray mode (pipeline == 0) to a crop of the frame (w == 0: whole frame).
 static int g_crop[4] = {0, 0, 0, 0};
 extern "C" void hostsim_set_crop(int x, int y, int w, int h) {
@@ -47,6 +58,17 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
                               rt_counters* counters, char* errbuf, int errlen) {
 	std::string err;
 	RtHostScene hs;
+	RtSceneCopy moved;
+	rt_scene_desc moved_desc;
+	if (!g_move_ids.empty()) {
+		moved.assign(*sc);
+		if (!rt_scene_move_entities(moved, (uint32_t)g_move_ids.size(), g_move_ids.data(), g_move_pos.data(), g_move_depth, err)) {
+			snprintf(errbuf, errlen, "%s", err.c_str());
+			return (int)RT_ERR_UNSUPPORTED;
+		}
+		moved_desc = moved.desc();
+		sc = &moved_desc;
+	}
 	rt_status st = rt_pack_scene(sc, hs, err);
 	if (!st) st = rt_check_render_args(true, (uint32_t)hs.textures.size(), (uint32_t)hs.substances.size(), cam, prm, err);
 	RtFrame F{};

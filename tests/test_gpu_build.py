@@ -64,6 +64,26 @@ def test_gpu_tree_equals_host_tree(ctx, n, dmin, dmax, boxes, depth):
         assert (np.diff(ex) > 0).all()
 
 
+@pytest.mark.parametrize("n,dmin,dmax,boxes", [(50000, 0.002, 0.006, 0.1), (4000, 0.004, 0.08, 0.3)])
+def test_gpu_tree_equals_the_oracles_tree(ctx, oracle, n, dmin, dmax, boxes):
+    """The device-built tree against the ORACLE's own restatement of add_entity_to_octree (src/octree_entity.ts:60-188),
+    not against this repo's host builder: both number the nodes in depth-first pre-order with children 0..7, so the
+    arrays must be equal element by element - float64 positions and sizes bit for bit, child tables, parents,
+    index_within_parent, list offsets, and every node's entities in insertion order."""
+    from util import oracle_scene_flat
+    fb = scenes.random_spheres_flat(n, dmin, dmax, seed=11.0, mix="mirrors", box_fraction=boxes)
+    G = rebuild_on_gpu(ctx, fb).arrays
+    f = oracle_scene_flat(fb).flat()
+    assert f.root_index == 0 and len(f.node_size) == len(G["node_size"])
+    np.testing.assert_array_equal(G["node_pos"], f.node_pos)
+    np.testing.assert_array_equal(G["node_size"], f.node_size)
+    np.testing.assert_array_equal(G["node_child"], f.node_child)
+    np.testing.assert_array_equal(G["node_parent"], f.node_parent)
+    np.testing.assert_array_equal(G["node_octant"], f.node_octant)
+    np.testing.assert_array_equal(G["node_list_off"], f.node_list_off)
+    np.testing.assert_array_equal(G["list_entity"], f.list_entity)  # entity ids are insertion indices on both sides
+
+
 def test_gpu_tree_reference_placement_and_errors(ctx):
     mat = rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0)
     tex = rt.SolidTexture(rt.Color(1, 1, 1, 1))
