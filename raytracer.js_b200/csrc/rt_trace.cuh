@@ -1858,6 +1858,13 @@ RT_HD void blend_constant_sample(const RtFrame& F, size_t out_index, const doubl
 		const float* o = F.rgb + out_index * 3;
 		px[0] = o[0]; px[1] = o[1]; px[2] = o[2];
 	}
+	if (F.frame_first == 0 && F.n_frames == 1) {
+		// the first frame of an exposure: weight 1 on the sample, 0 on the (zero) pixel - c*1 is c and 0*0 is +0 exactly,
+		// so the blend is one addition
+#pragma unroll
+		for (int k = 0; k < 3; k++) px[k] = (float)xadd(c[k], 0.0);
+		return;
+	}
 	for (uint32_t f = 0; f < F.n_frames; f++) {
 		const double w = f == 0 ? F.w_first : xdiv(1.0, (double)(1u + F.frame_first + f));
 		const double w1 = f == 0 ? F.w1_first : xsub(1.0, w);
@@ -1914,6 +1921,33 @@ RT_HD void primary_patch(const RtDevScene& S, const RtFrame& F, const RtPatch& p
 	const bool sky_simple = !sky->image;
 #pragma unroll 1
 	for (int j = 0; j < PPL; j++) {
+#if defined(__CUDACC__)
+		// A sub-patch of sky only (most of them, on the headline scene), first frame of an exposure, constant sky: every
+		// pixel is the same colour - no per-pixel work at all, 24 lanes store the 384 bytes as repeating 16-byte words.
+		if (sky_simple && F.frame_first == 0 && !F.queue_dense) {
+			const int lane = (int)(threadIdx.x & 31u);
+			const bool is_sky = !((skip[0] >> j) & 1u) && codes[j * 32 + lane] == RT_HIT_NONE;
+			if (__ballot_sync(0xffffffffu, is_sky) == 0xffffffffu && (F.tile_compact || (F.width & 3) == 0) &&
+			    (reinterpret_cast<uintptr_t>(F.rgb) & 15u) == 0) {
+				const double c[3] = {xmul(1.0, sky->r), xmul(1.0, sky->g), xmul(1.0, sky->b)};
+				float p[3];
+				blend_constant_sample(F, 0, c, p);  // (frame_first == 0: the old pixel is not read)
+				const int x0 = patch_x(pt, 0, j), y0 = patch_y(pt, 0, j);
+				if (lane < 24) {
+					const int row = lane / 6, chunk = lane - row * 6, o = (chunk * 4) % 3;
+					const size_t first = F.tile_compact ? pt.out_base + (size_t)(((y0 + row) & 15) * 16 + (x0 & 15))
+					                                    : (size_t)(y0 + row) * F.width + x0;
+					const float a = p[o], b = p[(o + 1) % 3], cc = p[(o + 2) % 3];
+					reinterpret_cast<float4*>(F.rgb + first * 3)[chunk] = make_float4(a, b, cc, a);
+				}
+				if (F.first_ids) {
+					const int x = patch_x(pt, lane, j), y = patch_y(pt, lane, j);
+					F.first_ids[F.tile_compact ? pt.out_base + (size_t)((y & 15) * 16 + (x & 15)) : (size_t)y * F.width + x] = -1;
+				}
+				continue;
+			}
+		}
+#endif
 		bool done[RT_NL], enqueue[RT_NL];
 		float px[RT_NL][3];
 		int first_entity[RT_NL];
