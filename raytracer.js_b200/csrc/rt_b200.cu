@@ -300,7 +300,6 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 				st = RT_ST_WALK;
 			} else {
 				W.hit = hit;  // known from the primary stage (or searched by the fallback walker)
-				W.overflow = 0;
 				st = RT_ST_END;
 			}
 		}
@@ -326,7 +325,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			double c[3];
 			int hit;
 			RtCollision ci;
-			segment_found(S, P, W, hit, ci);
+			segment_found(S, P, W, hit, ci, err);
 			if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
 			else st = RT_ST_BEGIN;
 		}
@@ -418,7 +417,6 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 					st = RT_ST_WALK;
 				} else {
 					W.hit = hit;
-					W.overflow = 0;
 					st = RT_ST_END;
 				}
 			}
@@ -444,7 +442,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 				double c[3];
 				int hit;
 				RtCollision ci;
-				segment_found(S, P, W, hit, ci);
+				segment_found(S, P, W, hit, ci, err);
 				if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
 				else st = RT_ST_BEGIN;
 			}
@@ -1073,6 +1071,8 @@ rt_status read_counters(rt_ctx* ctx, rt_counters* out) {
 	out->confirms = h[5];
 	out->texture_errors = (ef & RT_ERRFLAG_TEXTURE) ? 1 : 0;
 	out->acute_warnings = (ef & RT_ERRFLAG_ACUTE) ? 1 : 0;
+	if (ef & RT_ERRFLAG_STACK)  // never a silently wrong pixel: the frame is refused
+		return fail(ctx, RT_ERR_UNSUPPORTED, "a traversal stack was too small for this scene (internal limit): the frame was not rendered correctly");
 	return RT_OK;
 }
 

@@ -207,3 +207,4 @@ struct RtFrame {
 
 #define RT_ERRFLAG_TEXTURE 1u
 #define RT_ERRFLAG_ACUTE 2u
+#define RT_ERRFLAG_STACK 4u  // a traversal stack was too small for a ray: the frame is refused (RT_ERR_UNSUPPORTED), never silently wrong

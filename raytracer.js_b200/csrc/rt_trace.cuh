@@ -125,6 +125,7 @@ struct RtCollision {
 
 struct RtCounts {
 	unsigned int segments, nodes, tests, shades, confirms;
+	unsigned int errors;  // RT_ERRFLAG_* raised below the functions that carry an error word
 };
 
 // ------------------------------------------------------------------ float64 confirmations
@@ -366,7 +367,7 @@ RT_HD bool confirm_slot(const RtDevScene& S, int s, const double* o, const doubl
 // Long lists: every entity of the list the ray hits is found through the list's BVH and the lowest slot
 // (= first in insertion order) wins, which is what the reference's linear scan with `break` returns.
 RT_HD int scan_list_bvh(const RtDevScene& S, const RtSearch& q, int root, const double* o, const double* d,
-                        RtCollision& col) {
+                        RtCollision& col, RtCounts& cnt) {
 	const RtRayF& r = q.r;
 	int stack[RT_BVH_STACK];
 	int sp = 0, best = 0x7fffffff;
@@ -390,6 +391,8 @@ RT_HD int scan_list_bvh(const RtDevScene& S, const RtSearch& q, int root, const 
 			if (sp + 2 <= RT_BVH_STACK) {
 				stack[sp++] = n1.z + 1;
 				stack[sp++] = n1.z;  // the child with the lowest slot first
+			} else {
+				cnt.errors |= RT_ERRFLAG_STACK;  // (balanced median-split BVHs: 40 levels are never reached; never silent)
 			}
 			continue;
 		}
@@ -415,7 +418,7 @@ template <bool COUNT>
 RT_HD int scan_list(const RtDevScene& S, const RtSearch& q, int node, int beg, int end, const double* o, const double* d,
                     RtCollision& col, RtCounts& cnt) {
 	if (end - beg >= RT_BVH_MIN_LIST) {
-		const int s = scan_list_bvh(S, q, ld(S.node_bvh + node), o, d, col);
+		const int s = scan_list_bvh(S, q, ld(S.node_bvh + node), o, d, col, cnt);
 		// the counters count the reference's linear scan: up to and including the hit, or the whole list
 		if (COUNT) {
 			cnt.tests += (unsigned)(s >= 0 ? s - beg + 1 : end - beg);
@@ -1247,8 +1250,8 @@ struct RtWalk {
 	int chain_listed; // 1: chain_node's list has been scanned, next is its parent
 	int chain_up;     // RtWNode.up of chain_node (known once its list has been started)
 	int best;         // lowest hit slot of the current list, RT_NO_SLOT while none
-	int hit;          // result: first-hit slot, -1 none
-	int overflow;     // 1: the stack was too small for this ray - the caller searches it with walk_and_scan instead
+	int hit;          // result: first-hit slot, -1 none, RT_WALK_OVERFLOW: the stack was too small for this ray - the
+	                  // caller searches it with the reference-order walker instead (segment_found)
 	float slack;
 	int stack[RT_WALK_STACK];
 };
@@ -1259,8 +1262,9 @@ struct RtWalk {
 #endif
 // One iteration of the walk pushes at most 8 children, a list root and two BVH nodes: the room for that is checked
 // ONCE per iteration (walk_iter), not per push - a ray that runs out of stack is never dropped silently, it is
-// searched again by the reference-order walker (W.overflow, segment_found).
+// reported (W.hit == RT_WALK_OVERFLOW -> RT_ERRFLAG_STACK, segment_found) and the render call fails.
 #define RT_WALK_PUSHES_PER_ITER 11
+#define RT_WALK_OVERFLOW (-3)
 static_assert(RT_WALK_CAP > RT_WALK_PUSHES_PER_ITER, "walk stack smaller than one iteration's pushes");
 RT_HD void walk_push(RtWalk& W, int v) { W.stack[W.sp++] = v; }
 
@@ -1322,7 +1326,6 @@ RT_HD void walk_begin(const RtDevScene& S, RtWalk& W, int node, int octant) {
 	W.in_list = 0;
 	W.best = RT_NO_SLOT;
 	W.hit = -1;
-	W.overflow = 0;
 	W.slack = S.err_l * fminf(fmaxf(fabsf(r.ix), fmaxf(fabsf(r.iy), fabsf(r.iz))), 1e7f);
 	W.chain_node = node;
 	W.chain_oct = octant;
@@ -1402,7 +1405,7 @@ RT_HD void walk_leaf(const RtDevScene& S, RtWalk& W, int leaf_a, const double* o
 template <bool LOCKSTEP>
 RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const double* d, bool walking, int node_batch = 1) {
 	if (walking && W.sp > RT_WALK_CAP - RT_WALK_PUSHES_PER_ITER) {  // no room for this iteration's pushes
-		W.overflow = 1;
+		W.hit = RT_WALK_OVERFLOW;
 		walking = false;
 	}
 	// ---- node step.  It is several times the cost of a list step, so in lock-step the lanes that need one
@@ -1593,30 +1596,19 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 		q.chain_mask = pretest_chain(F, S, q);
 	}
 	slot = walk_and_scan<COUNT>(S, q, P.node, P.octant, P.refpoint, P.dir, ci, cnt);
+	err |= cnt.errors;
 	return RT_SEG_SLOT;
 }
 
-// A ray whose stack overflowed (W.overflow: trees much deeper than the stack was sized for) is searched again from
-// scratch by the reference-order walker, which needs no stack - slower, never wrong.  Out of line and by VALUE: the
-// hot loop's path state must not have its address taken for the sake of a branch that is almost never run.
-RT_COLD int search_without_stack(const RtDevScene& S, RtRayF r, int node, int octant, double ox, double oy, double oz, double dx,
-                                 double dy, double dz) {
-	RtSearch q;
-	q.r = r;
-	q.rel = nullptr;
-	q.chain_mask = 0xffffffffu;
-	q.chain_levels = 0;
-	RtCounts cnt = {0, 0, 0, 0, 0};
-	RtCollision ci;
-	const double o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
-	return walk_and_scan<false>(S, q, node, octant, o, d, ci, cnt);
-}
-
-// after the ordered walk: the collision of the slot it found
-RT_HD void segment_found(const RtDevScene& S, const RtPath& P, const RtWalk& W, int& slot, RtCollision& ci) {
+// after the ordered walk: the collision of the slot it found.  A walk that ran out of stack (W.hit ==
+// RT_WALK_OVERFLOW; rt_ordered_walk_fits sizes the stack for the tree's depth at upload, so this is a defect, not an
+// input) is not answered with a guess: the frame's error flag is raised and the render call fails.
+RT_HD void segment_found(const RtDevScene& S, const RtPath& P, const RtWalk& W, int& slot, RtCollision& ci, uint32_t& err) {
 	slot = W.hit;
-	if (W.overflow)
-		slot = search_without_stack(S, W.r, P.node, P.octant, P.refpoint[0], P.refpoint[1], P.refpoint[2], P.dir[0], P.dir[1], P.dir[2]);
+	if (slot == RT_WALK_OVERFLOW) {
+		err |= RT_ERRFLAG_STACK;
+		slot = -1;
+	}
 	if (slot >= 0 && !confirm_slot(S, slot, P.refpoint, P.dir, ci)) slot = -1;  // (same formula as in the walk: cannot fail)
 }
 
@@ -1738,7 +1730,7 @@ RT_HD bool path_segment(const RtDevScene& S, const RtFrame& F, RtPath& P, double
 		if (r == RT_SEG_WALK) {
 			while (walk_iter<false>(S, W, P.refpoint, P.dir, true)) {
 			}
-			segment_found(S, P, W, slot, ci);
+			segment_found(S, P, W, slot, ci, err);
 		}
 	} else {
 		if (segment_begin<COUNT>(S, F, P, primary_slot, out, cnt, err, nullptr, slot, ci) == RT_SEG_DONE) return true;

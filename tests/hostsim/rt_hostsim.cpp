@@ -171,6 +171,16 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 				if (errs[t] & RT_ERRFLAG_ACUTE) counters->acute_warnings = 1;
 			}
 		}
+		for (int t = 0; t < n_threads; t++)
+			if (errs[t] & RT_ERRFLAG_STACK) {
+				snprintf(errbuf, errlen, "a traversal stack was too small for this scene");
+				return (int)RT_ERR_UNSUPPORTED;
+			}
+		for (int t = 0; t < n_threads; t++)
+			if (errs[t] & RT_ERRFLAG_STACK) {
+				snprintf(errbuf, errlen, "a traversal stack was too small for this scene");
+				return (int)RT_ERR_UNSUPPORTED;
+			}
 		return 0;
 	}
 	F.packet_ok = 0;
@@ -206,5 +216,10 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 			if (errs[t] & RT_ERRFLAG_ACUTE) counters->acute_warnings = 1;
 		}
 	}
+	for (int t = 0; t < n_threads; t++)
+		if ((errs[t] | part[t].errors) & RT_ERRFLAG_STACK) {
+			snprintf(errbuf, errlen, "a traversal stack was too small for this scene");
+			return (int)RT_ERR_UNSUPPORTED;
+		}
 	return 0;
 }
