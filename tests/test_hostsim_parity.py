@@ -407,3 +407,18 @@ def test_walk_stack_overflow_is_reported_not_dropped(oracle, tmp_path):
     st = L.hostsim_render(C.byref(d), C.byref(cd), C.byref(prm), 8, 0, 1, 1, C.c_void_p(rgb.ctypes.data), C.c_void_p(ids.ctypes.data),
                           C.byref(cnt), err, 512)
     assert st == N.RT_ERR_UNSUPPORTED and b"stack" in err.value, (st, err.value)
+
+
+@pytest.mark.parametrize("W,H", [(100, 100), (77, 45), (60, 52), (1, 1), (9, 40)])
+def test_frames_whose_middle_column_is_not_tile_aligned(oracle, W, H):
+    """The packet stage produces its pixels' directions cooperatively from the ray-generation checkpoints
+    (packet_directions): frames whose middle column falls inside an 8-pixel sub-patch (both scan directions in one
+    row of a sub-patch), ragged right and bottom edges, and frames narrower than a sub-patch."""
+    b = scenes.random_spheres(600, 0.03, 0.12, seed=4.0, mix="mirrors", box_fraction=0.2)
+    flat = flat_of(b)
+    cam, ocam = cameras(W, H)
+    prm = make_params(flat, b, n_frames=2)
+    rgb, ids, _ = hostsim_render(flat, cam, prm, pipeline=True)
+    orgb, oids, _, tot = oracle_render(oracle_scene(flat, b), ocam, flat, b, prm, fixed_extents=True)
+    res = compare(rgb, insertion_ids(flat, b, ids), orgb, oids)
+    assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0 and res["rgb_max_abs"] == 0.0, res
