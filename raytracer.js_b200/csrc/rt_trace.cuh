@@ -869,39 +869,26 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 	int sp = 0;
 	// stores the children of `nd` whose octant is in the 8-bit mask m (already narrowed to what the packet may
 	// pierce) on the stack, last-visited first
-	// The stack holds the children's RECORDS, not their indices: the (up to 8) records are consecutive in memory
-	// (breadth-first numbering), so this is one coalesced fetch whose latency is paid once per push instead of once per
-	// pop; and since the slots follow the same order, the children's lists are neighbours too and can be prefetched
-	// right here.  The fetch (fetch_children, lanes 0..7) is issued BEFORE the node's own list is scanned and used
-	// after it (push_fetched): the two dependent chains of a node step - list entries, child records - overlap.
-	auto fetch_children = [&](const RtPNode& nd, unsigned m, RtPNode (&rec)[RT_NL]) {
-		RT_LANES(l, lane) {
-			const int o = lane & 7;
-			if (lane < 8 && ((m >> o) & 1u)) {
-				rec[l] = ld(S.node_pk + nd.child_base + popc32(nd.child_mask & ((1u << o) - 1u)));
-				if (rec[l].list_cnt > 0) prefetch_l1(F.prim_geom + rec[l].list_off);
-			}
-		}
-	};
-	auto push_fetched = [&](unsigned m, const RtPNode (&rec)[RT_NL]) {
+	auto push_mask = [&](const RtPNode& nd, unsigned m) {
 		if (!m) return;
 		if (sp + 8 > RT_PACKET_STACK(PPL)) { overflow = true; return; }
 		const unsigned mk = xor_permute8(m, P.neg);  // bit = visit key
 		RT_LANES(l, lane) {
+			(void)l;
 			const int o = lane & 7;
 			if (lane < 8 && ((m >> o) & 1u)) {
 				const int key = o ^ P.neg;
-				stack[sp + popc32(mk >> (key + 1))] = rec[l];  // smaller key = popped earlier = higher on the stack
+				// The stack holds the children's RECORDS, not their indices: the (up to 8) records are
+				// consecutive in memory (breadth-first numbering), so this is one coalesced fetch whose
+				// latency is paid once per push instead of once per pop; and since the slots follow the same
+				// order, the children's lists are neighbours too and can be prefetched right here.
+				const RtPNode rec = ld(S.node_pk + nd.child_base + popc32(nd.child_mask & ((1u << o) - 1u)));
+				if (rec.list_cnt > 0) prefetch_l1(F.prim_geom + rec.list_off);
+				stack[sp + popc32(mk >> (key + 1))] = rec;  // smaller key = popped earlier = higher on the stack
 			}
 		}
 		sp += popc32(m);
 		warp_sync();
-	};
-	auto push_mask = [&](const RtPNode& nd, unsigned m) {
-		if (!m) return;
-		RtPNode rec[RT_NL];
-		fetch_children(nd, m, rec);
-		push_fetched(m, rec);
 	};
 	// children of an origin-chain node: only the octants a ray can still reach from octant after_oct (the
 	// origin's cell / the chain child below), pierce test on lanes 0..7
@@ -1010,10 +997,8 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 			warp_sync();
 			const unsigned pierced = (unsigned)nd.child_mask & 0xffu;
 			nd.child_mask = (nd.child_mask >> 16) & 0xff;
-			RtPNode rec[RT_NL];
-			fetch_children(nd, pierced, rec);
 			if (nd.list_cnt > 0 && scan(nd.list_off, nd.list_off + nd.list_cnt)) return;
-			push_fetched(pierced, rec);
+			push_mask(nd, pierced);
 		}
 		if (overflow) return;
 		if (F.chain_end[k] > F.chain_beg[k] && scan(F.chain_beg[k], F.chain_end[k])) return;
