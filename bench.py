@@ -375,6 +375,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     t_wall0 = time.perf_counter()
     for i, (a, b) in enumerate(evs):
         N.check(ctx, lib.rt_flush_l2(ctx))
+        if peer is not None:
+            # every rank has finished its (untimed) flush before any rank's timed step begins: without this a rank's
+            # step time would include the flush of the slowest other rank, which it meets at the frame's own barrier
+            peer.barrier()
+        elif world > 1:
+            dist.barrier()
         a.record(stream)
         step(cam=cds[warm + i])
         b.record(stream)
