@@ -446,7 +446,29 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         assert np.array_equal(host_rgb, frame.cpu().numpy()), "host path and device path disagree"
         N.check(ctx, lib.rt_host_unregister(ctx, host_rgb.ctypes.data))
         e2e = {"value": segments * args.steps / dt / 1e6, "unit": "Mrays/s", "frame_ms": dt / args.steps * 1e3,
-               "h2d_bytes_per_step": WIDTH * 16 + HEIGHT * 32 + 80, "d2h_bytes_per_step": npx * 12 + 68}
+               "h2d_bytes_per_step": HEIGHT * 32, "d2h_bytes_per_step": npx * 12 + 72}
+        # ---- the same frames PIPELINED (rt_render_begin / rt_render_end, two ExposureBuffers): the host copy of frame k
+        # overlaps the rendering of frame k + 1; every frame still arrives complete in host memory
+        host2 = [np.zeros(npx * 3, np.float32), np.zeros(npx * 3, np.float32)]
+        for hb in host2:
+            N.check(ctx, lib.rt_host_register(ctx, hb.ctypes.data, hb.nbytes))
+        for rep in range(2):  # the first pass warms the second device frame up
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                N.check(ctx, lib.rt_render_begin(ctx, C.byref(cds[warm + i]), C.byref(prm), 0, host2[i & 1].ctypes.data, None))
+                if i:
+                    N.check(ctx, lib.rt_render_end(ctx, None))
+            N.check(ctx, lib.rt_render_end(ctx, None))
+            dtp2 = time.perf_counter() - t0
+        check = np.zeros(npx * 3, np.float32)
+        N.check(ctx, lib.rt_render(ctx, C.byref(cds[warm + args.steps - 1]), C.byref(prm), 0, check.ctypes.data, None, None))
+        assert np.array_equal(host2[(args.steps - 1) & 1], check), "pipelined frame differs from the synchronous one"
+        del check
+        for hb in host2:
+            N.check(ctx, lib.rt_host_unregister(ctx, hb.ctypes.data))
+        e2e["pipelined"] = {"value": segments * args.steps / dtp2 / 1e6, "unit": "Mrays/s", "frame_ms": dtp2 / args.steps * 1e3,
+                            "note": "rt_render_begin / rt_render_end, two frames in flight, two host buffers: throughput of a frame loop; "
+                                    "`value` above is the synchronous call's (latency of one frame)"}
         # ---- the step after the path: View.draw_ebuffer() on the device.  (a) the three
         # present kernels alone on the resident frame, (b) trace_frame + draw_ebuffer end to end with the
         # ExposureBuffer resident in HBM: only the RGBA8 screen travels to the host.

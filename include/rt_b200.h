@@ -214,6 +214,16 @@ rt_status rt_scene_update(rt_ctx* ctx, uint32_t n_moved, const uint32_t* entity_
 rt_status rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* params, uint32_t render_flags,
                     float* rgb, int32_t* first_ids, rt_counters* counters);
 
+/* Pipelined frames, for a host loop that renders frame after frame (the tick handler of src/main.ts:210,410-414 with
+ * two ExposureBuffers): rt_render_begin enqueues a frame and returns at once; rt_render_end waits for the OLDEST frame
+ * begun and not yet ended - its pixels (and ids) are then in the host buffers given to ITS rt_render_begin, which must
+ * stay valid and untouched until then.  At most two frames in flight: the device-to-host copy of frame k (the larger
+ * part of a 1080p frame's end-to-end time) overlaps the rendering of frame k + 1.  Counters need RT_RENDER_COUNTERS in
+ * `flags`.  One GPU only (a group's members already deliver their tiles concurrently, over one PCIe link each). */
+rt_status rt_render_begin(rt_ctx* ctx, const rt_camera* cam, const rt_params* params, uint32_t render_flags, float* rgb,
+                          int32_t* first_ids);
+rt_status rt_render_end(rt_ctx* ctx, rt_counters* counters);
+
 /* Device buffers (same layouts), enqueued on the ctx stream, asynchronous.  For callers that keep
  * the ExposureBuffer resident on the GPU (tone mapping on device, multi-GPU tile exchange). */
 rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* params, uint32_t render_flags,

@@ -80,6 +80,8 @@ EXPORTS = {
     "rt_scene_update": (C.c_int, [C.c_void_p, C.c_uint32, _up, _dp, C.c_uint32]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32, C.c_void_p,
                             C.c_void_p, C.POINTER(Counters)]),
+    "rt_render_begin": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32, C.c_void_p, C.c_void_p]),
+    "rt_render_end": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
     "rt_render_device": (C.c_int, [C.c_void_p, C.POINTER(CameraDesc), C.POINTER(Params), C.c_uint32, C.c_void_p,
                                    C.c_void_p]),
     "rt_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),

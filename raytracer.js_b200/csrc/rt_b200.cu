@@ -688,6 +688,12 @@ struct rt_ctx {
 	std::function<rt_status()> w_job;
 	rt_status w_status = RT_OK;
 	bool w_quit = false;
+	// pipelined frames (rt_render_begin / rt_render_end): two device frames, two pinned counter snapshots
+	DevBuf<float> pipe_rgb[2];
+	DevBuf<int> pipe_ids[2];
+	unsigned long long* pipe_counters = nullptr;  // pinned, [2][9]
+	cudaEvent_t pipe_kernels[2] = {}, pipe_done[2] = {};
+	uint64_t pipe_begun = 0, pipe_ended = 0;
 	struct HostMap { void* host; size_t bytes; bool registered; std::vector<void*> dev; };
 	std::vector<HostMap> hostmaps;  // caller-owned host frames mapped into every member's address space
 	DevBuf<RtF4> node_geom;
@@ -1425,6 +1431,15 @@ void rt_destroy(rt_ctx* ctx) {
 		ctx->hostmaps.clear();
 	}
 	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+	for (int k = 0; k < 2; k++) {
+		ctx->pipe_rgb[k].release();
+		ctx->pipe_ids[k].release();
+		if (ctx->pipe_kernels[k]) cudaEventDestroy(ctx->pipe_kernels[k]);
+		if (ctx->pipe_done[k]) cudaEventDestroy(ctx->pipe_done[k]);
+	}
+	if (ctx->pipe_counters) cudaFreeHost(ctx->pipe_counters);
 	if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
 	if (ctx->done_ev) cudaEventDestroy(ctx->done_ev);
 	cudaStreamSynchronize(ctx->stream);
@@ -1938,6 +1953,69 @@ rt_status rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uin
 	if (rt_status st = read_counters(ctx, &tmp)) return st;  // also synchronises and fetches the error flags
 	if (counters) *counters = tmp;
 	if (tmp.texture_errors) return fail(ctx, RT_ERR_TEXTURE, "Texture coordinates out of bounds");
+	return RT_OK;
+}
+
+// ---- pipelined frames: the copy of frame k to the host overlaps the rendering of frame k + 1 -----------------------
+rt_status rt_render_begin(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb, int32_t* first_ids) {
+	if (rt_status st = check_args(ctx, cam, prm)) return st;
+	if (!rgb) return fail(ctx, RT_ERR_INVALID, "rt_render_begin: rgb is NULL");
+	if (ctx->group.size() > 1) return fail(ctx, RT_ERR_UNSUPPORTED, "rt_render_begin: not on a multi-GPU group (its members already deliver their tiles concurrently)");
+	if (ctx->pipe_begun - ctx->pipe_ended >= 2) return fail(ctx, RT_ERR_INVALID, "rt_render_begin: two frames are already in flight; call rt_render_end first");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	const int k = (int)(ctx->pipe_begun & 1);
+	if (!ctx->pipe_counters) {
+		RT_CUDA(ctx, cudaMallocHost((void**)&ctx->pipe_counters, 2 * 9 * sizeof(unsigned long long)));
+		for (int i = 0; i < 2; i++) {
+			RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_kernels[i], cudaEventDisableTiming));
+			RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming));
+		}
+	}
+	const size_t npx = (size_t)cam->width * cam->height;
+	RT_CUDA(ctx, ctx->pipe_rgb[k].alloc(npx * 3));
+	if (first_ids) RT_CUDA(ctx, ctx->pipe_ids[k].alloc(npx));
+	float* rgb_dev = ctx->pipe_rgb[k].p;
+	int* ids_dev = first_ids ? ctx->pipe_ids[k].p : nullptr;
+	if (prm->frame_first > 0)
+		RT_CUDA(ctx, cudaMemcpyAsync(rgb_dev, rgb, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	const size_t W = cam->width;
+	const BandHook copy_band = [&](int band, int y_begin, int y_end) -> rt_status {
+		RT_CUDA(ctx, cudaEventRecord(ctx->band_done[band], ctx->stream));
+		RT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->band_done[band], 0));
+		const size_t off = (size_t)y_begin * W, n = (size_t)(y_end - y_begin) * W;
+		RT_CUDA(ctx, cudaMemcpyAsync(rgb + off * 3, rgb_dev + off * 3, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+		if (first_ids)
+			RT_CUDA(ctx, cudaMemcpyAsync(first_ids + off, ids_dev + off, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
+		return RT_OK;
+	};
+	if (rt_status st = launch_render(ctx, cam, prm, flags, rgb_dev, ids_dev, 0, 1, false, ctx->n_bands, copy_band)) return st;
+	// this frame's counters and error flags, before the next frame's setup kernel zeroes the cells
+	RT_CUDA(ctx, cudaMemcpyAsync(ctx->pipe_counters + 9 * k, ctx->counters.p, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	RT_CUDA(ctx, cudaEventRecord(ctx->pipe_kernels[k], ctx->stream));
+	RT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_kernels[k], 0));
+	RT_CUDA(ctx, cudaEventRecord(ctx->pipe_done[k], ctx->copy_stream));
+	ctx->pipe_begun++;
+	return RT_OK;
+}
+
+rt_status rt_render_end(rt_ctx* ctx, rt_counters* counters) {
+	if (!ctx) return RT_ERR_INVALID;
+	if (ctx->pipe_begun == ctx->pipe_ended) return fail(ctx, RT_ERR_INVALID, "rt_render_end: no frame in flight");
+	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	const int k = (int)(ctx->pipe_ended & 1);
+	RT_CUDA(ctx, cudaEventSynchronize(ctx->pipe_done[k]));
+	ctx->pipe_ended++;
+	const unsigned long long* h = ctx->pipe_counters + 9 * k;
+	const uint32_t ef = (uint32_t)h[8];
+	if (counters) {
+		counters->paths = h[0]; counters->segments = h[1]; counters->nodes = h[2]; counters->tests = h[3]; counters->shades = h[4];
+		counters->confirms = h[5];
+		counters->texture_errors = (ef & RT_ERRFLAG_TEXTURE) ? 1 : 0;
+		counters->acute_warnings = (ef & RT_ERRFLAG_ACUTE) ? 1 : 0;
+	}
+	if (ef & RT_ERRFLAG_STACK)
+		return fail(ctx, RT_ERR_UNSUPPORTED, "a traversal stack was too small for this scene (internal limit): the frame was not rendered correctly");
+	if (ef & RT_ERRFLAG_TEXTURE) return fail(ctx, RT_ERR_TEXTURE, "Texture coordinates out of bounds");
 	return RT_OK;
 }
 

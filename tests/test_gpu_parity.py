@@ -429,3 +429,40 @@ def test_zero_copy_host_frame(oracle):
         np.testing.assert_array_equal(host, eb.pixels)
     finally:
         N.check(ctx, lib.rt_host_unregister(ctx, host.ctypes.data))
+
+
+def test_pipelined_frames_equal_synchronous_frames():
+    """rt_render_begin / rt_render_end (two frames in flight: the host copy of frame k overlaps the rendering of k + 1)
+    deliver exactly the frames of rt_render, ids and counters included; a third begin without an end is refused."""
+    b = scenes.random_spheres(3000, 0.01, 0.05, seed=8.0, mix="mirrors", box_fraction=0.1)
+    W, H = 320, 200
+    cams = [scenes.bench_camera(W, H, yaw_deg=30.0 + 7.0 * i) for i in range(5)]
+    tracer = rt.GpuRaytracer(rt.RaytracerConfig(b.refmax, b.sky, b.default_substance, 1.0), b.tree, cams[0],
+                             rt.ExposureBuffer(W, H), rt.FpLcg(1.0))
+    lib, ctx = tracer.lib, tracer.ctx
+    prm = tracer.params(n_frames=2)
+    want = []
+    for cam in cams:
+        rgb, ids, cnt = np.zeros(W * H * 3, np.float32), np.zeros(W * H, np.int32), N.Counters()
+        cd = rt.camera_desc(cam)
+        N.check(ctx, lib.rt_render(ctx, C.byref(cd), C.byref(prm), 0, rgb.ctypes.data, ids.ctypes.data, C.byref(cnt)))
+        want.append((rgb, ids, cnt.as_dict()))
+    bufs = [(np.full(W * H * 3, -1.0, np.float32), np.full(W * H, -7, np.int32)) for _ in cams]
+    got_cnt = []
+    for i, cam in enumerate(cams):
+        cd = rt.camera_desc(cam)
+        N.check(ctx, lib.rt_render_begin(ctx, C.byref(cd), C.byref(prm), N.RT_RENDER_COUNTERS, bufs[i][0].ctypes.data, bufs[i][1].ctypes.data))
+        if i == 1:  # two in flight: a third is refused, nothing is lost
+            assert lib.rt_render_begin(ctx, C.byref(cd), C.byref(prm), 0, bufs[i][0].ctypes.data, None) == N.RT_ERR_INVALID
+        if i >= 1:
+            cnt = N.Counters()
+            N.check(ctx, lib.rt_render_end(ctx, C.byref(cnt)))
+            got_cnt.append(cnt.as_dict())
+    cnt = N.Counters()
+    N.check(ctx, lib.rt_render_end(ctx, C.byref(cnt)))
+    got_cnt.append(cnt.as_dict())
+    assert lib.rt_render_end(ctx, None) == N.RT_ERR_INVALID  # nothing in flight
+    for i in range(len(cams)):
+        np.testing.assert_array_equal(bufs[i][0], want[i][0])
+        np.testing.assert_array_equal(bufs[i][1], want[i][1])
+        assert got_cnt[i] == want[i][2]
