@@ -3,11 +3,17 @@
 // layout of rt_common.h, the camera scan tables, and the once-per-frame start state.
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rt_b200.h"
@@ -39,6 +45,56 @@ struct RtHostScene {
 };
 
 inline std::string rt_format(const char* fmt, ...);
+
+// Packing a scene is O(nodes + entities) of independent work per node: it runs on the host's cores.
+// RT_B200_PACK_THREADS overrides the thread count (default: the hardware's, at most 16); the packed arrays do not
+// depend on it.  fn(begin, end) is called for blocks of `grain` indices of [0, n), handed out dynamically.
+inline unsigned rt_pack_threads(size_t work) {
+	const char* e = getenv("RT_B200_PACK_THREADS");
+	int v = e ? atoi(e) : 0;
+	if (v <= 0) v = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+	return work < 65536 ? 1u : (unsigned)v;
+}
+
+template <class F>
+inline void rt_parallel_blocks(size_t n, size_t grain, size_t work, F&& fn) {
+	const unsigned T = rt_pack_threads(work);
+	if (T <= 1 || n <= grain) {
+		if (n) fn((size_t)0, n);
+		return;
+	}
+	std::atomic<size_t> next{0};
+	auto run = [&] {
+		for (;;) {
+			const size_t b = next.fetch_add(grain);
+			if (b >= n) return;
+			fn(b, std::min(n, b + grain));
+		}
+	};
+	std::vector<std::thread> pool;
+	for (unsigned t = 1; t < T; t++) pool.emplace_back(run);
+	run();
+	for (std::thread& t : pool) t.join();
+}
+
+// The error a single thread walking the indices in order would have met first: blocks report (key, status,
+// message), the lowest key wins.
+struct RtFirstError {
+	std::mutex mu;
+	std::atomic<bool> any{false};
+	uint64_t key = ~0ull;
+	rt_status st = RT_OK;
+	std::string msg;
+	void report(uint64_t k, rt_status s, std::string m) {
+		std::lock_guard<std::mutex> g(mu);
+		if (k < key) {
+			key = k;
+			st = s;
+			msg = std::move(m);
+		}
+		any = true;
+	}
+};
 
 // A deep, mutable copy of an rt_scene_desc: what rt_scene_update edits (the caller's arrays were only borrowed
 // for the duration of rt_scene_upload).
@@ -187,9 +243,6 @@ inline std::string rt_format(const char* fmt, ...) {
 inline void rt_build_list_bvhs(RtHostScene& hs) {
 	const size_t N = hs.node_link.size();
 	hs.node_bvh.assign(N, -1);
-	hs.bvh_nodes.clear();
-	hs.bvh_slots.clear();
-	hs.bvh_geom.clear();
 	hs.max_bvh_depth = 0;
 	struct Box { float lo[3], hi[3]; };
 	const double infl = (double)hs.err_l;
@@ -204,94 +257,125 @@ inline void rt_build_list_bvhs(RtHostScene& hs) {
 		}
 		return b;
 	};
-	std::vector<int> idx;
-	struct Job { int node, beg, end, depth; };
-	std::vector<Job> jobs;
+	// The shape of a list's BVH depends on its length alone (median splits down to RT_BVH_LEAF entries), so every
+	// list knows where its records go before any is built, and the lists are built in parallel straight into place:
+	// the arrays are the ones a single thread produces, whatever the thread count.
+	struct Shape { int nodes, leaves; };
+	std::vector<Shape> memo(4096, Shape{0, 0});
+	std::function<Shape(int)> shape = [&](int cnt) -> Shape {
+		if (cnt <= RT_BVH_LEAF) return Shape{1, 1};
+		if ((size_t)cnt < memo.size() && memo[cnt].nodes) return memo[cnt];
+		const Shape l = shape(cnt / 2), r = shape(cnt - cnt / 2);
+		const Shape t{1 + l.nodes + r.nodes, l.leaves + r.leaves};
+		if ((size_t)cnt < memo.size()) memo[cnt] = t;
+		return t;
+	};
+	std::vector<int> leaf_base(N, 0);
+	size_t n_bvh = 0, n_leaves = 0;
 	for (size_t n = 0; n < N; n++) {
-		const int off = hs.node_link[n].z, cnt = hs.node_link[n].w;
+		const int cnt = hs.node_link[n].w;
 		if (cnt <= 0) continue;
-		idx.resize(cnt);
-		for (int i = 0; i < cnt; i++) idx[i] = off + i;
-		hs.node_bvh[n] = (int)hs.bvh_nodes.size();
-		hs.bvh_nodes.push_back(RtBvhNode{});
-		jobs.clear();
-		jobs.push_back(Job{hs.node_bvh[n], 0, cnt, 0});
-		while (!jobs.empty()) {
-			const Job j = jobs.back();
-			jobs.pop_back();
-			hs.max_bvh_depth = std::max(hs.max_bvh_depth, j.depth);
-			Box bb;
-			double cmin[3] = {1e300, 1e300, 1e300}, cmax[3] = {-1e300, -1e300, -1e300};
-			int min_slot = 0x7fffffff;
-			for (int k = 0; k < 3; k++) { bb.lo[k] = INFINITY; bb.hi[k] = -INFINITY; }
-			for (int i = j.beg; i < j.end; i++) {
-				const Box b = box_of(idx[i]);
-				const RtD4& g = hs.slot_geom64[idx[i]];
-				const double c[3] = {g.x, g.y, g.z};
-				min_slot = std::min(min_slot, idx[i]);
-				for (int k = 0; k < 3; k++) {
-					bb.lo[k] = std::min(bb.lo[k], b.lo[k]);
-					bb.hi[k] = std::max(bb.hi[k], b.hi[k]);
-					cmin[k] = std::min(cmin[k], c[k]);
-					cmax[k] = std::max(cmax[k], c[k]);
-				}
-			}
-			RtBvhNode nd;
-			for (int k = 0; k < 3; k++) { nd.lo[k] = bb.lo[k]; nd.hi[k] = bb.hi[k]; }
-			const int count = j.end - j.beg;
-			int axis = 0;
-			for (int k = 1; k < 3; k++)
-				if (cmax[k] - cmin[k] > cmax[axis] - cmin[axis]) axis = k;
-			if (count <= RT_BVH_LEAF) {  // (leaves never hold more: the leaf test is unrolled over RT_BVH_LEAF entries)
-				std::sort(idx.begin() + j.beg, idx.begin() + j.end);  // ascending slots: list order within the leaf
-				nd.a = (int)hs.bvh_slots.size();
-				nd.b = count;
-				for (int i = 0; i < RT_BVH_LEAF; i++) {  // padded to RT_BVH_LEAF entries (finite geometry, slot = none)
-					const bool real = j.beg + i < j.end;
-					hs.bvh_slots.push_back(real ? idx[j.beg + i] : RT_NO_SLOT);
-					hs.bvh_geom.push_back(hs.slot_geom[idx[real ? j.beg + i : j.beg]]);
-				}
-			} else {
-				const int mid = j.beg + count / 2;
-				// (coincident centres: the comparator falls back to the slot numbers, any split is as good)
-				std::nth_element(idx.begin() + j.beg, idx.begin() + mid, idx.begin() + j.end, [&](int p, int q) {
-					const double a = axis == 0 ? hs.slot_geom64[p].x : axis == 1 ? hs.slot_geom64[p].y : hs.slot_geom64[p].z;
-					const double b = axis == 0 ? hs.slot_geom64[q].x : axis == 1 ? hs.slot_geom64[q].y : hs.slot_geom64[q].z;
-					return a < b || (a == b && p < q);
-				});
-				const bool min_left = std::find(idx.begin() + j.beg, idx.begin() + mid, min_slot) != idx.begin() + mid;
-				nd.a = (int)hs.bvh_nodes.size();
-				nd.b = -(min_slot + 1);
-				hs.bvh_nodes.push_back(RtBvhNode{});
-				hs.bvh_nodes.push_back(RtBvhNode{});
-				jobs.push_back(Job{nd.a + (min_left ? 0 : 1), j.beg, mid, j.depth + 1});
-				jobs.push_back(Job{nd.a + (min_left ? 1 : 0), mid, j.end, j.depth + 1});
-			}
-			hs.bvh_nodes[j.node] = nd;
-		}
+		const Shape t = shape(cnt);
+		hs.node_bvh[n] = (int)n_bvh;
+		leaf_base[n] = (int)n_leaves;
+		n_bvh += (size_t)t.nodes;
+		n_leaves += (size_t)t.leaves;
 	}
-	if (hs.bvh_nodes.empty()) hs.bvh_nodes.push_back(RtBvhNode{});
-	if (hs.bvh_slots.empty()) hs.bvh_slots.assign(RT_BVH_LEAF, RT_NO_SLOT);
-	if (hs.bvh_geom.empty()) hs.bvh_geom.assign(RT_BVH_LEAF, RtF4{0, 0, 0, 0});
+	hs.bvh_nodes.assign(std::max<size_t>(n_bvh, 1), RtBvhNode{});
+	hs.bvh_slots.assign(std::max<size_t>(n_leaves, 1) * RT_BVH_LEAF, RT_NO_SLOT);
+	hs.bvh_geom.assign(std::max<size_t>(n_leaves, 1) * RT_BVH_LEAF, RtF4{0, 0, 0, 0});
+	std::mutex mu;
+	rt_parallel_blocks(N, 256, hs.slot_geom.size(), [&](size_t n0, size_t n1) {
+		std::vector<int> idx;
+		struct Job { int node, beg, end, depth; };
+		std::vector<Job> jobs;
+		int deepest = 0;
+		for (size_t n = n0; n < n1; n++) {
+			const int off = hs.node_link[n].z, cnt = hs.node_link[n].w;
+			if (cnt <= 0) continue;
+			idx.resize(cnt);
+			for (int i = 0; i < cnt; i++) idx[i] = off + i;
+			int next_node = hs.node_bvh[n] + 1, next_leaf = leaf_base[n];  // where this list's next records go
+			jobs.clear();
+			jobs.push_back(Job{hs.node_bvh[n], 0, cnt, 0});
+			while (!jobs.empty()) {
+				const Job j = jobs.back();
+				jobs.pop_back();
+				deepest = std::max(deepest, j.depth);
+				Box bb;
+				double cmin[3] = {1e300, 1e300, 1e300}, cmax[3] = {-1e300, -1e300, -1e300};
+				int min_slot = 0x7fffffff;
+				for (int k = 0; k < 3; k++) { bb.lo[k] = INFINITY; bb.hi[k] = -INFINITY; }
+				for (int i = j.beg; i < j.end; i++) {
+					const Box b = box_of(idx[i]);
+					const RtD4& g = hs.slot_geom64[idx[i]];
+					const double c[3] = {g.x, g.y, g.z};
+					min_slot = std::min(min_slot, idx[i]);
+					for (int k = 0; k < 3; k++) {
+						bb.lo[k] = std::min(bb.lo[k], b.lo[k]);
+						bb.hi[k] = std::max(bb.hi[k], b.hi[k]);
+						cmin[k] = std::min(cmin[k], c[k]);
+						cmax[k] = std::max(cmax[k], c[k]);
+					}
+				}
+				RtBvhNode nd;
+				for (int k = 0; k < 3; k++) { nd.lo[k] = bb.lo[k]; nd.hi[k] = bb.hi[k]; }
+				const int count = j.end - j.beg;
+				int axis = 0;
+				for (int k = 1; k < 3; k++)
+					if (cmax[k] - cmin[k] > cmax[axis] - cmin[axis]) axis = k;
+				if (count <= RT_BVH_LEAF) {  // (leaves never hold more: the leaf test is unrolled over RT_BVH_LEAF entries)
+					std::sort(idx.begin() + j.beg, idx.begin() + j.end);  // ascending slots: list order within the leaf
+					nd.a = next_leaf * RT_BVH_LEAF;
+					nd.b = count;
+					for (int i = 0; i < RT_BVH_LEAF; i++) {  // padded to RT_BVH_LEAF entries (finite geometry, slot = none)
+						const bool real = j.beg + i < j.end;
+						hs.bvh_slots[(size_t)nd.a + i] = real ? idx[j.beg + i] : RT_NO_SLOT;
+						hs.bvh_geom[(size_t)nd.a + i] = hs.slot_geom[idx[real ? j.beg + i : j.beg]];
+					}
+					next_leaf++;
+				} else {
+					const int mid = j.beg + count / 2;
+					// (coincident centres: the comparator falls back to the slot numbers, any split is as good)
+					std::nth_element(idx.begin() + j.beg, idx.begin() + mid, idx.begin() + j.end, [&](int p, int q) {
+						const double a = axis == 0 ? hs.slot_geom64[p].x : axis == 1 ? hs.slot_geom64[p].y : hs.slot_geom64[p].z;
+						const double b = axis == 0 ? hs.slot_geom64[q].x : axis == 1 ? hs.slot_geom64[q].y : hs.slot_geom64[q].z;
+						return a < b || (a == b && p < q);
+					});
+					const bool min_left = std::find(idx.begin() + j.beg, idx.begin() + mid, min_slot) != idx.begin() + mid;
+					nd.a = next_node;
+					nd.b = -(min_slot + 1);
+					next_node += 2;
+					jobs.push_back(Job{nd.a + (min_left ? 0 : 1), j.beg, mid, j.depth + 1});
+					jobs.push_back(Job{nd.a + (min_left ? 1 : 0), mid, j.end, j.depth + 1});
+				}
+				hs.bvh_nodes[j.node] = nd;
+			}
+		}
+		std::lock_guard<std::mutex> g(mu);
+		hs.max_bvh_depth = std::max(hs.max_bvh_depth, deepest);
+	});
 	// the walk records (rt_common.h: RtWNode)
 	hs.node_walk.resize(N);
-	for (size_t n = 0; n < N; n++) {
-		const RtPNode& pk = hs.node_pk[n];
-		const RtI4& link = hs.node_link[n];
-		RtWNode w{};
-		w.x = pk.x; w.y = pk.y; w.z = pk.z; w.size = pk.size;
-		w.child_base = pk.child_base; w.child_mask = pk.child_mask;
-		w.up = link.x < 0 ? -1 : (int)((unsigned)link.x | ((unsigned)link.y << 28));
-		w.a = -1;
-		w.b = 0;
-		if (hs.node_bvh[n] >= 0) {
-			const RtBvhNode& r = hs.bvh_nodes[hs.node_bvh[n]];
-			for (int k = 0; k < 3; k++) { w.lo[k] = r.lo[k]; w.hi[k] = r.hi[k]; }
-			w.a = r.a;
-			w.b = r.b;
+	rt_parallel_blocks(N, 4096, N, [&](size_t n0, size_t n1) {
+		for (size_t n = n0; n < n1; n++) {
+			const RtPNode& pk = hs.node_pk[n];
+			const RtI4& link = hs.node_link[n];
+			RtWNode w{};
+			w.x = pk.x; w.y = pk.y; w.z = pk.z; w.size = pk.size;
+			w.child_base = pk.child_base; w.child_mask = pk.child_mask;
+			w.up = link.x < 0 ? -1 : (int)((unsigned)link.x | ((unsigned)link.y << 28));
+			w.a = -1;
+			w.b = 0;
+			if (hs.node_bvh[n] >= 0) {
+				const RtBvhNode& r = hs.bvh_nodes[hs.node_bvh[n]];
+				for (int k = 0; k < 3; k++) { w.lo[k] = r.lo[k]; w.hi[k] = r.hi[k]; }
+				w.a = r.a;
+				w.b = r.b;
+			}
+			hs.node_walk[n] = w;
 		}
-		hs.node_walk[n] = w;
-	}
+	});
 }
 
 // 1 when the stack of the bounce stage's ordered walk (RT_WALK_STACK entries) holds the deepest case: up to 7
@@ -300,6 +384,18 @@ inline int rt_ordered_walk_fits(const RtHostScene& hs) {
 	if (hs.node_link.size() > (size_t)RT_WNODE_PARENT_MASK) return 0;  // RtWNode.up packs the parent in 28 bits
 	return 7 * hs.max_depth + 8 + hs.max_bvh_depth + 2 <= RT_WALK_STACK ? 1 : 0;
 }
+
+// RT_B200_PACK_TIMING=1: the stages of rt_pack_scene on stderr
+struct RtPackClock {
+	bool on = getenv("RT_B200_PACK_TIMING") != nullptr;
+	std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+	void mark(const char* what) {
+		if (!on) return;
+		const auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[rt_pack_scene] %-16s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+		t = now;
+	}
+};
 
 // Validates `sc` and fills `hs`.  On failure returns the status and a message in `err`.
 inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::string& err) {
@@ -329,30 +425,49 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 	if (sc->node_list_off[0] != 0 || sc->node_list_off[N] != L)
 		RT_FAIL(RT_ERR_INVALID, "node_list_off must start at 0 and end at n_list");
 
+	RtPackClock clk;
+	RtFirstError fe;
+#define RT_FAIL_AT(key, st, ...)                                   \
+	do {                                                           \
+		fe.report((uint64_t)(key), st, rt_format(__VA_ARGS__)); \
+		return;                                                    \
+	} while (0)
+#define RT_STAGE_END()         \
+	do {                       \
+		if (fe.any) {          \
+			err = fe.msg;      \
+			return fe.st;      \
+		}                      \
+	} while (0)
+	const size_t work = (size_t)N + L;
 	// ---- validate the links, then renumber breadth-first (children of a node become consecutive)
-	for (uint32_t i = 0; i < N; i++) {
-		const double s = sc->node_size[i];
-		if (!(s > 0) || !std::isfinite(s)) RT_FAIL(RT_ERR_INVALID, "node %u: bad size", i);
-		if (sc->node_list_off[i + 1] < sc->node_list_off[i]) RT_FAIL(RT_ERR_INVALID, "node %u: list offsets not monotone", i);
-		const int par = sc->node_parent[i];
-		if (i > 0 && (par < 0 || (uint32_t)par >= N)) RT_FAIL(RT_ERR_INVALID, "node %u: bad parent %d", i, par);
-		const int oc = sc->node_octant[i];
-		if (i > 0 && (oc < 0 || oc > 7)) RT_FAIL(RT_ERR_INVALID, "node %u: bad octant %d", i, oc);
-		// node_octant is the reference's index_within_parent() (src/octree_space.ts:110-125), which derives the
-		// index from the cell positions ("FIXME: ... not merely by checking geometry"): for a root whose cell
-		// corners are not exactly representable it can disagree with the slot the node really sits in, and the
-		// reference's own walker then steps back into the wrong octant.  Such a tree is refused, not guessed at.
+	// node_octant is the reference's index_within_parent() (src/octree_space.ts:110-125), which derives the
+	// index from the cell positions ("FIXME: ... not merely by checking geometry"): for a root whose cell
+	// corners are not exactly representable it can disagree with the slot the node really sits in, and the
+	// reference's own walker then steps back into the wrong octant.  Such a tree is refused, not guessed at.
 #define RT_OCTANT_HINT "index_within_parent() disagrees with the child slot (src/octree_space.ts:110-125 computes it from positions): " \
 	"use a root cube whose size is a power of two, placed at a multiple of it"
-		if (i > 0 && sc->node_child[(size_t)par * 8 + oc] != (int)i)
-			RT_FAIL(RT_ERR_INVALID, "node %u: parent %d does not list it as child %d; " RT_OCTANT_HINT, i, par, oc);
-		for (int c = 0; c < 8; c++) {
-			const int ch = sc->node_child[(size_t)i * 8 + c];
-			if (ch < -1 || ch >= (int)N || ch == 0) RT_FAIL(RT_ERR_INVALID, "node %u: bad child %d", i, ch);
-			if (ch > 0 && (sc->node_parent[ch] != (int)i || sc->node_octant[ch] != c))
-				RT_FAIL(RT_ERR_INVALID, "node %u: child %d does not point back; " RT_OCTANT_HINT, i, ch);
+	rt_parallel_blocks(N, 4096, work, [&](size_t i0, size_t i1) {
+		for (size_t i = i0; i < i1; i++) {
+			const double s = sc->node_size[i];
+			if (!(s > 0) || !std::isfinite(s)) RT_FAIL_AT(i, RT_ERR_INVALID, "node %zu: bad size", i);
+			if (sc->node_list_off[i + 1] < sc->node_list_off[i]) RT_FAIL_AT(i, RT_ERR_INVALID, "node %zu: list offsets not monotone", i);
+			const int par = sc->node_parent[i];
+			if (i > 0 && (par < 0 || (uint32_t)par >= N)) RT_FAIL_AT(i, RT_ERR_INVALID, "node %zu: bad parent %d", i, par);
+			const int oc = sc->node_octant[i];
+			if (i > 0 && (oc < 0 || oc > 7)) RT_FAIL_AT(i, RT_ERR_INVALID, "node %zu: bad octant %d", i, oc);
+			if (i > 0 && sc->node_child[(size_t)par * 8 + oc] != (int)i)
+				RT_FAIL_AT(i, RT_ERR_INVALID, "node %zu: parent %d does not list it as child %d; " RT_OCTANT_HINT, i, par, oc);
+			for (int c = 0; c < 8; c++) {
+				const int ch = sc->node_child[i * 8 + c];
+				if (ch < -1 || ch >= (int)N || ch == 0) RT_FAIL_AT(i, RT_ERR_INVALID, "node %zu: bad child %d", i, ch);
+				if (ch > 0 && (sc->node_parent[ch] != (int)i || sc->node_octant[ch] != c))
+					RT_FAIL_AT(i, RT_ERR_INVALID, "node %zu: child %d does not point back; " RT_OCTANT_HINT, i, ch);
+			}
 		}
-	}
+	});
+	RT_STAGE_END();
+	clk.mark("links");
 	std::vector<int> perm(N, -1), order;  // perm[old] = new, order[new] = old
 	order.reserve(N);
 	order.push_back(0);
@@ -373,27 +488,40 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 	hs.node_link.resize(N);
 	hs.node_child.resize((size_t)N * 8);
 	hs.node_pk.resize(N);
+	// Slots follow the breadth-first node numbering (each node's run keeps its insertion order), so the lists
+	// of sibling nodes are neighbours in memory, like their records.
+	std::vector<uint32_t> slot_base(N + 1, 0);
+	for (uint32_t ni = 0; ni < N; ni++) slot_base[ni + 1] = slot_base[ni] + (sc->node_list_off[order[ni] + 1] - sc->node_list_off[order[ni]]);
 	double scale = 0;
-	for (uint32_t ni = 0; ni < N; ni++) {
-		const int i = order[ni];
-		const double* p = sc->node_pos + 3 * (size_t)i;
-		const double s = sc->node_size[i];
-		hs.node_geom[ni] = RtF4{(float)p[0], (float)p[1], (float)p[2], (float)s};
-		const int par = sc->node_parent[i];
-		const int off = (int)sc->node_list_off[i], cnt = (int)(sc->node_list_off[i + 1] - sc->node_list_off[i]);
-		hs.node_link[ni] = RtI4{i > 0 ? perm[par] : -1, i > 0 ? sc->node_octant[i] : -1, off, cnt};
-		int base = -1, mask = 0;
-		for (int c = 0; c < 8; c++) {
-			const int ch = sc->node_child[(size_t)i * 8 + c];
-			hs.node_child[(size_t)ni * 8 + c] = ch > 0 ? perm[ch] : -1;
-			if (ch > 0) {
-				if (base < 0) base = perm[ch];
-				mask |= 1 << c;
+	std::mutex scale_mu;
+	auto merge_scale = [&](double v) {
+		std::lock_guard<std::mutex> g(scale_mu);
+		scale = std::max(scale, v);
+	};
+	rt_parallel_blocks(N, 4096, work, [&](size_t n0, size_t n1) {
+		double sc_max = 0;
+		for (size_t ni = n0; ni < n1; ni++) {
+			const int i = order[ni];
+			const double* p = sc->node_pos + 3 * (size_t)i;
+			const double s = sc->node_size[i];
+			hs.node_geom[ni] = RtF4{(float)p[0], (float)p[1], (float)p[2], (float)s};
+			const int par = sc->node_parent[i];
+			const int off = (int)slot_base[ni], cnt = (int)(slot_base[ni + 1] - slot_base[ni]);
+			hs.node_link[ni] = RtI4{i > 0 ? perm[par] : -1, i > 0 ? sc->node_octant[i] : -1, off, cnt};
+			int base = -1, mask = 0;
+			for (int c = 0; c < 8; c++) {
+				const int ch = sc->node_child[(size_t)i * 8 + c];
+				hs.node_child[ni * 8 + c] = ch > 0 ? perm[ch] : -1;
+				if (ch > 0) {
+					if (base < 0) base = perm[ch];
+					mask |= 1 << c;
+				}
 			}
+			hs.node_pk[ni] = RtPNode{(float)p[0], (float)p[1], (float)p[2], (float)s, off, cnt, base, mask};
+			for (int k = 0; k < 3; k++) sc_max = std::max(sc_max, std::fabs(p[k]) + s);
 		}
-		hs.node_pk[ni] = RtPNode{(float)p[0], (float)p[1], (float)p[2], (float)s, off, cnt, base, mask};
-		for (int k = 0; k < 3; k++) scale = std::max(scale, std::fabs(p[k]) + s);
-	}
+		merge_scale(sc_max);
+	});
 	{
 		std::vector<int> depth(N, 0);  // breadth-first numbering: a parent always precedes its children
 		hs.max_depth = 0;
@@ -402,40 +530,57 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 			hs.max_depth = std::max(hs.max_depth, depth[i]);
 		}
 	}
-	// Slots follow the breadth-first node numbering (each node's run keeps its insertion order), so the lists
-	// of sibling nodes are neighbours in memory, like their records.
+	clk.mark("renumber");
 	hs.slot_geom.resize(L);
 	hs.slot_geom64.resize(L);
 	hs.slot_attr.resize(L);
-	std::vector<uint8_t> seen(E, 0);
-	uint32_t s = 0;
-	for (uint32_t ni = 0; ni < N; ni++) {
-		const int i = order[ni];
-		const uint32_t beg = sc->node_list_off[i], end = sc->node_list_off[i + 1];
-		hs.node_link[ni].z = (int)s;
-		hs.node_pk[ni].list_off = (int)s;
-		for (uint32_t li = beg; li < end; li++, s++) {
-			const uint32_t e = sc->list_entity[li];
-			if (e >= E) RT_FAIL(RT_ERR_INVALID, "list slot %u: entity %u out of range", li, e);
-			if (seen[e]) RT_FAIL(RT_ERR_INVALID, "entity %u is listed in more than one node", e);
-			seen[e] = 1;
-			const double* p = sc->ent_pos + 3 * (size_t)e;
-			const double ext = sc->ent_extent[e];
-			const uint32_t type = sc->ent_type[e];
-			if (type > RT_ENTITY_BOX) RT_FAIL(RT_ERR_UNSUPPORTED, "unsupported Entity subclass (type %u) for entity %u", type, e);
-			if (!(ext > 0) || !std::isfinite(ext)) RT_FAIL(RT_ERR_INVALID, "entity %u: bad extent", e);
-			const int m = sc->ent_material[e], t = sc->ent_texture[e], sb = sc->ent_substance[e];
-			if (m < 0 || (uint32_t)m >= sc->n_materials) RT_FAIL(RT_ERR_INVALID, "entity %u: material %d", e, m);
-			if (t < 0 || (uint32_t)t >= sc->n_textures) RT_FAIL(RT_ERR_INVALID, "entity %u: texture %d", e, t);
-			if (sb < -1 || sb >= (int)sc->n_substances) RT_FAIL(RT_ERR_INVALID, "entity %u: substance %d", e, sb);
-			const float w = type == RT_ENTITY_SPHERE ? (float)(ext / 2) : -(float)(ext / 2);
-			hs.slot_geom[s] = RtF4{(float)p[0], (float)p[1], (float)p[2], w};
-			hs.slot_geom64[s] = RtD4{p[0], p[1], p[2], ext};
-			hs.slot_attr[s] = RtI4{(int)e, m | (int)(type << RT_ATTR_TYPE_SHIFT), t, sb};
-			for (int k = 0; k < 3; k++) scale = std::max(scale, std::fabs(p[k]) + ext);
+	// (error keys: 4 * slot + the place of the check in a single thread's order)
+	rt_parallel_blocks(N, 1024, work, [&](size_t n0, size_t n1) {
+		double sc_max = 0;
+		for (size_t ni = n0; ni < n1; ni++) {
+			const int i = order[ni];
+			const uint32_t beg = sc->node_list_off[i], end = sc->node_list_off[i + 1];
+			uint32_t s = slot_base[ni];
+			for (uint32_t li = beg; li < end; li++, s++) {
+				const uint32_t e = sc->list_entity[li];
+				if (e >= E) RT_FAIL_AT(4ull * s, RT_ERR_INVALID, "list slot %u: entity %u out of range", li, e);
+				const double* p = sc->ent_pos + 3 * (size_t)e;
+				const double ext = sc->ent_extent[e];
+				const uint32_t type = sc->ent_type[e];
+				if (type > RT_ENTITY_BOX) RT_FAIL_AT(4ull * s + 2, RT_ERR_UNSUPPORTED, "unsupported Entity subclass (type %u) for entity %u", type, e);
+				if (!(ext > 0) || !std::isfinite(ext)) RT_FAIL_AT(4ull * s + 2, RT_ERR_INVALID, "entity %u: bad extent", e);
+				const int m = sc->ent_material[e], t = sc->ent_texture[e], sb = sc->ent_substance[e];
+				if (m < 0 || (uint32_t)m >= sc->n_materials) RT_FAIL_AT(4ull * s + 2, RT_ERR_INVALID, "entity %u: material %d", e, m);
+				if (t < 0 || (uint32_t)t >= sc->n_textures) RT_FAIL_AT(4ull * s + 2, RT_ERR_INVALID, "entity %u: texture %d", e, t);
+				if (sb < -1 || sb >= (int)sc->n_substances) RT_FAIL_AT(4ull * s + 2, RT_ERR_INVALID, "entity %u: substance %d", e, sb);
+				const float w = type == RT_ENTITY_SPHERE ? (float)(ext / 2) : -(float)(ext / 2);
+				hs.slot_geom[s] = RtF4{(float)p[0], (float)p[1], (float)p[2], w};
+				hs.slot_geom64[s] = RtD4{p[0], p[1], p[2], ext};
+				hs.slot_attr[s] = RtI4{(int)e, m | (int)(type << RT_ATTR_TYPE_SHIFT), t, sb};
+				for (int k = 0; k < 3; k++) sc_max = std::max(sc_max, std::fabs(p[k]) + ext);
+			}
+		}
+		merge_scale(sc_max);
+	});
+	{
+		std::vector<uint8_t> seen(E, 0);  // an entity sits in ONE node's Set (src/entity.ts:50-56)
+		uint32_t s = 0;
+		for (uint32_t ni = 0; ni < N && !(fe.any && 4ull * s > fe.key); ni++) {
+			const int i = order[ni];
+			for (uint32_t li = sc->node_list_off[i]; li < sc->node_list_off[i + 1]; li++, s++) {
+				const uint32_t e = sc->list_entity[li];
+				if (e >= E) continue;
+				if (seen[e]) {
+					fe.report(4ull * s + 1, RT_ERR_INVALID, rt_format("entity %u is listed in more than one node", e));
+					break;
+				}
+				seen[e] = 1;
+			}
 		}
 	}
+	RT_STAGE_END();
 	hs.err_l = (float)(16.0 * 1.1920929e-7 * scale);
+	clk.mark("slots");
 	{
 		// The two geometric invariants every walker here relies on to be exact (the reference's own walker only needs
 		// the links): a child's cell IS the parent's octant, and every entity's cubic AABB lies inside its node's cube
@@ -443,30 +588,37 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 		// or one whose entities were moved without being re-inserted, would render differently here without an error:
 		// it is refused instead.  float64, O(nodes + entities), tolerance = a few ulps of the coordinate scale.
 		const double tol = 1e-12 * (scale > 0 ? scale : 1.0);
-		for (uint32_t i = 1; i < N; i++) {
-			const int par = sc->node_parent[i], oc = sc->node_octant[i];
-			const double ps = sc->node_size[par], half = ps / 2;
-			if (std::fabs(sc->node_size[i] - half) > tol) RT_FAIL(RT_ERR_INVALID, "node %u: size %.17g is not half of its parent's %.17g", i, sc->node_size[i], ps);
-			for (int k = 0; k < 3; k++) {
-				const double want = sc->node_pos[3 * (size_t)par + k] + (((oc >> k) & 1) ? half : 0.0);
-				if (std::fabs(sc->node_pos[3 * (size_t)i + k] - want) > tol)
-					RT_FAIL(RT_ERR_INVALID, "node %u: its cell is not octant %d of its parent's cube (axis %d: %.17g, expected %.17g)", i, oc, k,
-					        sc->node_pos[3 * (size_t)i + k], want);
+		rt_parallel_blocks(N, 4096, work, [&](size_t i0, size_t i1) {
+			for (size_t i = std::max<size_t>(i0, 1); i < i1; i++) {
+				const int par = sc->node_parent[i], oc = sc->node_octant[i];
+				const double ps = sc->node_size[par], half = ps / 2;
+				if (std::fabs(sc->node_size[i] - half) > tol)
+					RT_FAIL_AT(i, RT_ERR_INVALID, "node %zu: size %.17g is not half of its parent's %.17g", i, sc->node_size[i], ps);
+				for (int k = 0; k < 3; k++) {
+					const double want = sc->node_pos[3 * (size_t)par + k] + (((oc >> k) & 1) ? half : 0.0);
+					if (std::fabs(sc->node_pos[3 * i + k] - want) > tol)
+						RT_FAIL_AT(i, RT_ERR_INVALID, "node %zu: its cell is not octant %d of its parent's cube (axis %d: %.17g, expected %.17g)", i, oc, k,
+						           sc->node_pos[3 * i + k], want);
+				}
 			}
-		}
-		for (uint32_t i = 0; i < N; i++) {
-			const double* np = sc->node_pos + 3 * (size_t)i;
-			const double ns = sc->node_size[i];
-			for (uint32_t li = sc->node_list_off[i]; li < sc->node_list_off[i + 1]; li++) {
-				const uint32_t e = sc->list_entity[li];
-				const double* p = sc->ent_pos + 3 * (size_t)e;
-				const double h = sc->ent_extent[e] / 2;
-				for (int k = 0; k < 3; k++)
-					if (p[k] - h < np[k] - tol || p[k] + h > np[k] + ns + tol)
-						RT_FAIL(RT_ERR_INVALID, "entity %u sticks out of the cube of node %u that lists it (axis %d): re-insert moved entities "
-						                        "(add_entity_to_octree) before uploading", e, i, k);
+		});
+		RT_STAGE_END();
+		rt_parallel_blocks(N, 1024, work, [&](size_t i0, size_t i1) {
+			for (size_t i = i0; i < i1; i++) {
+				const double* np = sc->node_pos + 3 * i;
+				const double ns = sc->node_size[i];
+				for (uint32_t li = sc->node_list_off[i]; li < sc->node_list_off[i + 1]; li++) {
+					const uint32_t e = sc->list_entity[li];
+					const double* p = sc->ent_pos + 3 * (size_t)e;
+					const double h = sc->ent_extent[e] / 2;
+					for (int k = 0; k < 3; k++)
+						if (p[k] - h < np[k] - tol || p[k] + h > np[k] + ns + tol)
+							RT_FAIL_AT(li, RT_ERR_INVALID, "entity %u sticks out of the cube of node %zu that lists it (axis %d): re-insert moved entities "
+							                               "(add_entity_to_octree) before uploading", e, i, k);
+				}
 			}
-		}
+		});
+		RT_STAGE_END();
 	}
 	{
 		// The search runs in float32 (RT_PRECISION_F32): a cell's corners and centre must be distinct float32
@@ -479,7 +631,9 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 			RT_FAIL(RT_ERR_UNSUPPORTED, "octree cells of size %.3g are below the float32 resolution of the search at coordinate scale %.3g "
 			                            "(a unit root allows 23 levels): lower max_in_depth", min_size, scale);
 	}
+	clk.mark("geometry checks");
 	rt_build_list_bvhs(hs);
+	clk.mark("list BVHs");
 	hs.materials.resize(sc->n_materials);
 	hs.any_transmission = false;
 	for (uint32_t i = 0; i < sc->n_materials; i++) {
@@ -491,33 +645,39 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 		hs.any_transmission |= sc->mat_response[i] == RT_RESPONSE_TRANSMISSION;
 	}
 	hs.textures.resize(sc->n_textures);
-	for (uint32_t i = 0; i < sc->n_textures; i++) {
-		RtTexture& T = hs.textures[i];
-		memset(&T, 0, sizeof T);
-		T.r = sc->tex_color[4 * (size_t)i];
-		T.g = sc->tex_color[4 * (size_t)i + 1];
-		T.b = sc->tex_color[4 * (size_t)i + 2];
-		if (sc->tex_kind[i] > RT_TEXTURE_IMAGE) RT_FAIL(RT_ERR_UNSUPPORTED, "unsupported Texture subclass (kind %u)", sc->tex_kind[i]);
-		if (sc->tex_kind[i] == RT_TEXTURE_IMAGE && sc->tex_loaded && sc->tex_loaded[i]) {
-			if (!sc->tex_width || !sc->tex_height || !sc->tex_texel_off || !sc->texels)
-				RT_FAIL(RT_ERR_INVALID, "image texture arrays must not be NULL");
-			const int64_t w = sc->tex_width[i], h = sc->tex_height[i];
-			if (w <= 0 || h <= 0 || sc->tex_texel_off[i] + (uint64_t)(w * h) > sc->n_texels)
-				RT_FAIL(RT_ERR_INVALID, "texture %u: %lldx%lld texels out of the pool", i, (long long)w, (long long)h);
-			T.image = 1;
-			T.width = (int)w;
-			T.height = (int)h;
-			T.texel_off = sc->tex_texel_off[i];
+	rt_parallel_blocks(sc->n_textures, 8192, sc->n_textures, [&](size_t i0, size_t i1) {  // (one SolidTexture per entity is common)
+		for (size_t i = i0; i < i1; i++) {
+			RtTexture& T = hs.textures[i];
+			memset(&T, 0, sizeof T);
+			T.r = sc->tex_color[4 * i];
+			T.g = sc->tex_color[4 * i + 1];
+			T.b = sc->tex_color[4 * i + 2];
+			if (sc->tex_kind[i] > RT_TEXTURE_IMAGE) RT_FAIL_AT(2 * i, RT_ERR_UNSUPPORTED, "unsupported Texture subclass (kind %u)", sc->tex_kind[i]);
+			if (sc->tex_kind[i] == RT_TEXTURE_IMAGE && sc->tex_loaded && sc->tex_loaded[i]) {
+				if (!sc->tex_width || !sc->tex_height || !sc->tex_texel_off || !sc->texels)
+					RT_FAIL_AT(2 * i + 1, RT_ERR_INVALID, "image texture arrays must not be NULL");
+				const int64_t w = sc->tex_width[i], h = sc->tex_height[i];
+				if (w <= 0 || h <= 0 || sc->tex_texel_off[i] + (uint64_t)(w * h) > sc->n_texels)
+					RT_FAIL_AT(2 * i + 1, RT_ERR_INVALID, "texture %zu: %lldx%lld texels out of the pool", i, (long long)w, (long long)h);
+				T.image = 1;
+				T.width = (int)w;
+				T.height = (int)h;
+				T.texel_off = sc->tex_texel_off[i];
+			}
 		}
-	}
+	});
+	RT_STAGE_END();
 	hs.substances.assign(sc->sub_refractive_index, sc->sub_refractive_index + sc->n_substances);
 	hs.texels.assign(sc->texels, sc->texels + (sc->texels ? sc->n_texels * 3 : 0));
+	clk.mark("materials+texels");
 	for (int k = 0; k < 3; k++) hs.root_pos[k] = sc->node_pos[k];
 	hs.root_size = sc->node_size[0];
 	// bound on the float32 error of a centre-to-line distance for coordinates up to `scale`
 	hs.err_l = (float)(16.0 * 1.1920929e-7 * scale);
 	return RT_OK;
 #undef RT_FAIL
+#undef RT_FAIL_AT
+#undef RT_STAGE_END
 }
 
 // ---- host float64 restatements used once per frame (src/raytracer.ts:309-313) -----------------

@@ -43,6 +43,30 @@ extern "C" void hostsim_set_moves(uint32_t n, const uint32_t* ids, const double*
 
 // Debugging aid: restrict the ray-by-ray mode (pipeline == 0) to a crop of the frame (w == 0: whole frame).
 static int g_crop[4] = {0, 0, 0, 0};
+// A digest (FNV-1a, 64 bit) of everything rt_pack_scene produces, for the test that the packed scene does not depend
+// on the number of packing threads.  Returns the status; the message goes to errbuf.
+extern "C" int hostsim_pack_digest(const rt_scene_desc* sc, uint64_t* digest, char* errbuf, int errlen) {
+	RtHostScene hs;
+	std::string err;
+	const rt_status st = rt_pack_scene(sc, hs, err);
+	if (errbuf && errlen > 0) snprintf(errbuf, errlen, "%s", err.c_str());
+	if (st) return st;
+	uint64_t h = 1469598103934665603ull;
+	auto eat = [&](const void* p, size_t n) {
+		const unsigned char* b = (const unsigned char*)p;
+		for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+	};
+#define EAT(v) eat(hs.v.data(), hs.v.size() * sizeof(hs.v[0]));
+	EAT(node_geom) EAT(node_link) EAT(node_child) EAT(node_pk) EAT(node_walk) EAT(node_bvh) EAT(bvh_nodes) EAT(bvh_slots) EAT(bvh_geom)
+	EAT(slot_geom) EAT(slot_geom64) EAT(slot_attr) EAT(materials) EAT(textures) EAT(substances) EAT(texels)
+#undef EAT
+	eat(&hs.max_bvh_depth, sizeof hs.max_bvh_depth);
+	eat(&hs.max_depth, sizeof hs.max_depth);
+	eat(&hs.err_l, sizeof hs.err_l);
+	*digest = h;
+	return RT_OK;
+}
+
 extern "C" void hostsim_set_crop(int x, int y, int w, int h) {
 	g_crop[0] = x; g_crop[1] = y; g_crop[2] = w; g_crop[3] = h;
 }
