@@ -288,6 +288,10 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			}
 		}
 		if (__ballot_sync(0xffffffffu, st != RT_ST_IDLE) == 0u) break;
+		RT_PROF_COUNT(9);                        // outer passes
+		RT_PROF_LANES(10, st == RT_ST_BEGIN);
+		RT_PROF_LANES(11, st == RT_ST_IDLE);
+		RT_PROF_LANES(12, st == RT_ST_END);
 		// ---- BEGIN: walker re-seed
 		if (st == RT_ST_BEGIN) {
 			double c[3];
@@ -311,12 +315,19 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			if (nw > 0) {
 				const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
 				do {
+#ifdef RT_WALK_PROFILE
+					if (!exhausted) {
+						RT_PROF_COUNT(14);
+						RT_PROF_LANES(15, walking);
+					}
+#endif
 					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
 					nw = __popc(__ballot_sync(0xffffffffu, walking));
 				} while (nw >= limit);
 				if (st == RT_ST_WALK && !walking) st = RT_ST_END;
 			}
 		}
+		RT_PROF_LANES(13, st == RT_ST_END);
 		// ---- END: collision, material response
 		if (st == RT_ST_END) {
 			const uint32_t frame_count = F.frame_first + frame;
@@ -337,143 +348,135 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 // Resample stage (n_frames > 1).  A pixel whose path scatters off a rough surface is a different path in
 // every exposure frame, and ExposureBuffer.set_color_i (src/view/exposure_buffer.ts:77-91) blends the frames
 // one after the other into a float32 pixel.  One lane tracing all frames of such a pixel in a row is the
-// longest job of the whole render (n_frames x bounces walks of ~0.5 ms each) and would be its tail on any
-// number of GPUs.  Here the job is one (pixel, frame) sample: a warp takes a group of G pixels from the
-// resample queue (G x n_frames >= 256 samples when it can), its lanes run the bounce stage's state machine
-// over that pool - IDLE lanes take the next sample, BEGIN / lock-step WALK / END as in rt_bounce_kernel - and
-// park every path colour as float64 in the warp's sample buffer; when the pool is done, lane g blends the
-// samples of pixel g in frame order, so the pixel is the sequential one, bit for bit.
-#define RT_RESAMPLE_POOL 256
+// longest job of the whole render (n_frames x bounces walks) and would be its tail on any number of GPUs.
+// Here the job is one (pixel, frame) SAMPLE: the samples of all queued pixels are one stream of jobs
+// (job j = frame j % n_frames of pixel j / n_frames, so neighbouring lanes start on the same ray), the lanes of
+// the persistent warps run the bounce stage's state machine over it - IDLE lanes take the next samples, BEGIN /
+// lock-step WALK / END as in rt_bounce_kernel - and park every path colour as float64 in the frame's sample table;
+// rt_resample_blend_kernel then blends the samples of each pixel in frame order, so the pixel is the sequential
+// one, bit for bit.  (Round 1 gave every warp its own pool of 256 samples and blended when the pool was done: each
+// pool ended with its own tail of a few long paths in a nearly empty warp.)  The table holds `chunk` pixels; a queue
+// longer than that takes several rounds of the two kernels (`first` = the round's first queued pixel).
+RT_HD size_t frame_out_index(const RtFrame& F, int x, int y, int tiles_x) {
+	if (!F.tile_compact) return (size_t)y * F.width + x;
+	const int tile = (y / RT_TILE_H) * tiles_x + (x / RT_TILE_W);
+	return (size_t)(tile / F.tile_world) * RT_BLOCK + ((y & (RT_TILE_H - 1)) * RT_TILE_W + (x & (RT_TILE_W - 1)));
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
-    rt_resample_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
+    rt_resample_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, unsigned first, unsigned chunk) {
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
-	const unsigned n = *F.vqueue_count;
+	const unsigned queued = *F.vqueue_count;
+	if (queued <= first) return;
 	const unsigned nf = F.n_frames;
-	const unsigned G_max = min(32u, max(1u, RT_RESAMPLE_POOL / nf));  // pixels per group
-	const unsigned n_warps = gridDim.x * RT_WARPS_PER_CTA;
-	const size_t warp_id = (size_t)blockIdx.x * RT_WARPS_PER_CTA + (threadIdx.x >> 5);
-	double* const samples = F.samples + warp_id * F.samples_per_warp;  // [G][nf][3] behind a header of 32 ints
-	int* const group_entity = reinterpret_cast<int*>(samples);
-	double* const colour = samples + 16;
+	const unsigned n = min(queued - first, chunk) * nf;  // samples of this round (chunk * nf < 2^32, launch_render)
 	RtCounts cnt = {0, 0, 0, 0, 0};
 	uint32_t err = 0;
+	int st = RT_ST_IDLE;
+	unsigned job = 0;
+	int x = 0, y = 0, slot = RT_SLOT_UNKNOWN;
+	RtPath P = {};
+	RtWalk W;
+	bool exhausted = false;
+	auto sample_done = [&](const double* c) {
+		double* o = F.samples + (size_t)job * 3;
+		o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
+		if (job % nf == 0 && F.first_ids) F.first_ids[frame_out_index(F, x, y, tiles_x)] = P.first_entity;
+		st = RT_ST_IDLE;
+	};
 	while (true) {
-		// ---- the next group of pixels
-		// guided self-scheduling: full groups while the queue is long, smaller ones towards its end, so that
-		// the last pools - the tail of the frame - are short
-		unsigned g0 = 0, G = G_max;
-		if (lane == 0) {
-			const unsigned taken = *reinterpret_cast<volatile unsigned*>(F.vqueue_taken);
-			const unsigned left = taken < n ? n - taken : 0u;
-			G = max(1u, min(G_max, left / (2u * n_warps)));
-			g0 = atomicAdd(F.vqueue_taken, G);
+		// ---- idle lanes take the next samples
+		const unsigned idle = __ballot_sync(0xffffffffu, st == RT_ST_IDLE);
+		if (idle && !exhausted) {
+			const unsigned want = (unsigned)__popc(idle);
+			unsigned base = 0;
+			if (lane == 0) base = atomicAdd(F.vqueue_taken, want);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			exhausted = base + want >= n;
+			const unsigned j = base + (unsigned)__popc(idle & lt_mask);
+			if (st == RT_ST_IDLE && j < n) {
+				job = j;
+				const RtQueueItem it = F.vqueue[first + j / nf];
+				x = (int)(it.xy & 0xffffu);
+				y = (int)(it.xy >> 16);
+				slot = it.slot;
+				double dir[3];
+				pixel_dir(F, x, y, dir);
+				path_begin(F, dir, P);
+				st = RT_ST_BEGIN;
+			}
 		}
-		g0 = __shfl_sync(0xffffffffu, g0, 0);
-		G = __shfl_sync(0xffffffffu, G, 0);
-		if (g0 >= n) break;
-		const unsigned g_cnt = min(G, n - g0), pool = g_cnt * nf;
-		unsigned next = 0;  // warp-uniform cursor into the pool
-		int st = RT_ST_IDLE;
-		unsigned job = 0;
-		int x = 0, y = 0, slot = RT_SLOT_UNKNOWN;
-		RtPath P = {};
-		RtWalk W;
-		auto sample_done = [&](const double* c) {
-			double* o = colour + (size_t)job * 3;
-			o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
-			if (job % nf == 0) group_entity[job / nf] = P.first_entity;
-			st = RT_ST_IDLE;
-		};
-		while (true) {
-			// ---- idle lanes take the next samples of the pool
-			const unsigned idle = __ballot_sync(0xffffffffu, st == RT_ST_IDLE);
-			if (idle && next < pool) {
-				const unsigned j = next + (unsigned)__popc(idle & lt_mask);
-				next += (unsigned)__popc(idle);
-				if (st == RT_ST_IDLE && j < pool) {
-					job = j;
-					const RtQueueItem it = F.vqueue[g0 + j / nf];
-					x = (int)(it.xy & 0xffffu);
-					y = (int)(it.xy >> 16);
-					slot = it.slot;
-					double dir[3];
-					pixel_dir(F, x, y, dir);
-					path_begin(F, dir, P);
-					st = RT_ST_BEGIN;
-				}
+		if (__ballot_sync(0xffffffffu, st != RT_ST_IDLE) == 0u) break;
+		// ---- BEGIN: walker re-seed
+		if (st == RT_ST_BEGIN) {
+			double c[3];
+			int hit = -1;
+			RtCollision ci;
+			const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
+			if (r == RT_SEG_DONE) {
+				sample_done(c);
+			} else if (r == RT_SEG_WALK) {
+				st = RT_ST_WALK;
+			} else {
+				W.hit = hit;
+				st = RT_ST_END;
 			}
-			if (__ballot_sync(0xffffffffu, st != RT_ST_IDLE) == 0u) break;
-			// ---- BEGIN: walker re-seed
-			if (st == RT_ST_BEGIN) {
-				double c[3];
-				int hit = -1;
-				RtCollision ci;
-				const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
-				if (r == RT_SEG_DONE) {
-					sample_done(c);
-				} else if (r == RT_SEG_WALK) {
-					st = RT_ST_WALK;
-				} else {
-					W.hit = hit;
-					st = RT_ST_END;
-				}
-			}
-			__syncwarp();
-			// ---- WALK in lock-step
-			{
-				bool walking = st == RT_ST_WALK;
-				int nw = __popc(__ballot_sync(0xffffffffu, walking));
-				if (nw > 0) {
-					const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
-					do {
-						walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
-						nw = __popc(__ballot_sync(0xffffffffu, walking));
-					} while (nw >= limit);
-					if (st == RT_ST_WALK && !walking) st = RT_ST_END;
-				}
-			}
-			// ---- END: collision, material response
-			if (st == RT_ST_END) {
-				const uint32_t frame_count = F.frame_first + job % nf;
-				const double seed = xadd(xadd(F.rng_seed, (double)((size_t)y * F.width + x)),
-				                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
-				double c[3];
-				int hit;
-				RtCollision ci;
-				segment_found(S, P, W, hit, ci, err);
-				if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
-				else st = RT_ST_BEGIN;
-			}
-			__syncwarp();
 		}
-		// ---- ExposureBuffer.set_color_i, frame after frame: lane g owns pixel g of the group
 		__syncwarp();
-		if ((unsigned)lane < g_cnt) {
-			const RtQueueItem it = F.vqueue[g0 + lane];
-			const int px_x = (int)(it.xy & 0xffffu), px_y = (int)(it.xy >> 16);
-			size_t out_index = (size_t)px_y * F.width + px_x;
-			if (F.tile_compact) {
-				const int tile = (px_y / RT_TILE_H) * tiles_x + (px_x / RT_TILE_W);
-				out_index = (size_t)(tile / F.tile_world) * RT_BLOCK + ((px_y & (RT_TILE_H - 1)) * RT_TILE_W + (px_x & (RT_TILE_W - 1)));
+		// ---- WALK in lock-step
+		{
+			bool walking = st == RT_ST_WALK;
+			int nw = __popc(__ballot_sync(0xffffffffu, walking));
+			if (nw > 0) {
+				const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
+				do {
+					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
+					nw = __popc(__ballot_sync(0xffffffffu, walking));
+				} while (nw >= limit);
+				if (st == RT_ST_WALK && !walking) st = RT_ST_END;
 			}
-			float* o = F.rgb + out_index * 3;
-			float px[3] = {0.f, 0.f, 0.f};
-			if (F.frame_first > 0) { px[0] = o[0]; px[1] = o[1]; px[2] = o[2]; }
-			const double* c = colour + (size_t)lane * nf * 3;
-			for (unsigned f = 0; f < nf; f++, c += 3) {
-				const double w = xdiv(1.0, (double)(1u + F.frame_first + f));
-				const double w1 = xsub(1.0, w);
-#pragma unroll
-				for (int q = 0; q < 3; q++) px[q] = (float)xadd(xmul(c[q], w), xmul((double)px[q], w1));
-			}
-			o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
-			if (F.first_ids) F.first_ids[out_index] = group_entity[lane];
+		}
+		// ---- END: collision, material response
+		if (st == RT_ST_END) {
+			const uint32_t frame_count = F.frame_first + job % nf;
+			const double seed = xadd(xadd(F.rng_seed, (double)((size_t)y * F.width + x)),
+			                         xmul(xmul((double)frame_count, (double)F.width), (double)F.height));
+			double c[3];
+			int hit;
+			RtCollision ci;
+			segment_found(S, P, W, hit, ci, err);
+			if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
+			else st = RT_ST_BEGIN;
 		}
 		__syncwarp();
 	}
 	if (err) atomicOr(F.error_flags, err);
+}
+
+// ExposureBuffer.set_color_i (src/view/exposure_buffer.ts:77-91), frame after frame, for the pixels of one round of
+// the resample stage: one thread per queued pixel.  Re-arms the sample counter for the next round.
+__global__ void rt_resample_blend_kernel(const __grid_constant__ RtFrame F, int tiles_x, unsigned first, unsigned chunk) {
+	const unsigned queued = *F.vqueue_count;
+	const unsigned nf = F.n_frames;
+	const unsigned n = queued <= first ? 0u : min(queued - first, chunk);
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const RtQueueItem it = F.vqueue[first + i];
+		const size_t out_index = frame_out_index(F, (int)(it.xy & 0xffffu), (int)(it.xy >> 16), tiles_x);
+		float* o = F.rgb + out_index * 3;
+		float px[3] = {0.f, 0.f, 0.f};
+		if (F.frame_first > 0) { px[0] = o[0]; px[1] = o[1]; px[2] = o[2]; }
+		const double* c = F.samples + (size_t)i * nf * 3;
+		for (unsigned f = 0; f < nf; f++, c += 3) {
+			const double w = xdiv(1.0, (double)(1u + F.frame_first + f));
+			const double w1 = xsub(1.0, w);
+#pragma unroll
+			for (int q = 0; q < 3; q++) px[q] = (float)xadd(xmul(c[q], w), xmul((double)px[q], w1));
+		}
+		o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) *F.vqueue_taken = 0u;
 }
 
 // Tile-major buffers of all ranks, concatenated [world][tiles_per_rank][16*16][3]  ->  frame [H][W][3].
@@ -737,6 +740,7 @@ struct rt_ctx {
 	int ppl = RT_PPL;                            // sub-patches (rays per lane) of a packet: 4
 	int primary_minb = RT_A_MINB;                // tuning knob RT_B200_PRIMARY_MINB=4|5|6: resident CTAs per SM the primary stage is compiled for
 	int bounce_min_walking = 12;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
+	size_t sample_bytes = (size_t)2048 << 20;    // bound on the resample stage's sample table (RT_B200_SAMPLE_MIB)
 	int resample_min_frames = 8;                 // tuning knob RT_B200_RESAMPLE_MIN
 	bool ordered_queue = true;                   // tuning knob RT_B200_ORDERED_QUEUE=0: packets append to the continuation queue as they finish
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
@@ -923,14 +927,19 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	const void* resample_kernel = minb == 4 ? (const void*)rt_resample_kernel<4> : minb == 5 ? (const void*)rt_resample_kernel<5>
 	                            : minb == 6 ? (const void*)rt_resample_kernel<6> : (const void*)rt_resample_kernel<8>;
 	int grid_primary = 0, grid_bounce = 0, grid_ray = 0, grid_resample = 0;
+	unsigned resample_chunk = 1;
 	if (pipeline) {
 		if (rt_status st = grid_of(4, primary_kernel, RT_A_WARPS * 32, grid_primary)) return st;
 		if (rt_status st = grid_of(3, bounce_kernel, RT_WARPS_PER_CTA * 32, grid_bounce)) return st;
 		if (resample) {
 			if (rt_status st = grid_of(2, resample_kernel, RT_WARPS_PER_CTA * 32, grid_resample)) return st;
-			// per warp: a header of 32 ints + [pool][3] float64 path colours (rt_resample_kernel)
-			F.samples_per_warp = 16 + 3 * (unsigned long long)std::max<uint32_t>(RT_RESAMPLE_POOL, prm->n_frames);
-			RT_CUDA(ctx, ctx->samples.alloc((size_t)grid_resample * RT_WARPS_PER_CTA * F.samples_per_warp));
+			// the sample table: [pixels of a round][n_frames][3] float64 path colours; a queue longer than the table
+			// takes several rounds (RT_B200_SAMPLE_MIB bounds the table, default 2 GiB)
+			const size_t cap = tile_compact ? (size_t)((n_tiles - tile_rank + tile_world - 1) / tile_world) * RT_BLOCK
+			                                : (size_t)F.width * F.height;
+			const size_t per_pixel = (size_t)prm->n_frames * 3 * sizeof(double);
+			resample_chunk = (unsigned)std::max<size_t>(1, std::min<size_t>(cap, ctx->sample_bytes / per_pixel));
+			RT_CUDA(ctx, ctx->samples.alloc((size_t)resample_chunk * prm->n_frames * 3));
 			F.samples = ctx->samples.p;
 		}
 	} else if (count) {
@@ -1017,9 +1026,16 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 				RT_CUDA(ctx, mark(4));
 				ctx->stage_ran[1] = ctx->stage_ran[3] = prof;
 				if (resample) {
-					ctx->launches++;
-					RT_CUDA(ctx, cudaLaunchKernel(resample_kernel, dim3(std::min(grid_resample, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA)),
-					                              dim3(RT_WARPS_PER_CTA * 32), bargs, 0, ctx->stream));
+					const int blocks = std::min(grid_resample, (n_patches + RT_WARPS_PER_CTA - 1) / RT_WARPS_PER_CTA);
+					for (size_t first = 0; first < n_out; first += resample_chunk) {
+						unsigned first_u = (unsigned)first, chunk_u = resample_chunk;
+						void* rargs[] = {(void*)&ctx->dev, (void*)&F, (void*)&tiles_x, (void*)&first_u, (void*)&chunk_u};
+						RT_CUDA(ctx, cudaLaunchKernel(resample_kernel, dim3(blocks), dim3(RT_WARPS_PER_CTA * 32), rargs, 0, ctx->stream));
+						rt_resample_blend_kernel<<<std::min(blocks, (int)((std::min<size_t>(n_out - first, resample_chunk) + 255) / 256)), 256, 0, ctx->stream>>>(
+						    F, tiles_x, first_u, chunk_u);
+						ctx->launches += 2;
+						RT_CUDA(ctx, cudaGetLastError());
+					}
 					ctx->stage_ran[4] = prof;
 				}
 				RT_CUDA(ctx, mark(5));
@@ -1317,6 +1333,7 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	if (const char* e = getenv("RT_B200_RESAMPLE")) ctx->resample = atoi(e) != 0;
 	if (const char* e = getenv("RT_B200_ORDERED_QUEUE")) ctx->ordered_queue = atoi(e) != 0;
 	if (const char* e = getenv("RT_B200_RESAMPLE_MIN")) ctx->resample_min_frames = std::max(2, atoi(e));
+	if (const char* e = getenv("RT_B200_SAMPLE_MIB")) ctx->sample_bytes = (size_t)std::max(1, atoi(e)) << 20;
 	if (const char* e = getenv("RT_B200_BOUNCE_MINB")) {
 		const int v = atoi(e);
 		if (v == 4 || v == 5 || v == 6 || v == 8) ctx->bounce_minb = v;
@@ -1407,6 +1424,18 @@ rt_status rt_create_multi(int32_t n_gpus, const int32_t* devices, rt_ctx** out) 
 uint32_t rt_group_size(const rt_ctx* ctx) { return ctx ? (uint32_t)std::max<size_t>(1, ctx->group.size()) : 0; }
 
 void rt_destroy(rt_ctx* ctx) {
+#ifdef RT_WALK_PROFILE
+	if (ctx) {
+		unsigned long long h[16];
+		cudaSetDevice(ctx->device);
+		cudaDeviceSynchronize();
+		if (cudaMemcpyFromSymbol(h, g_walk_prof, sizeof h) == cudaSuccess) {
+			fprintf(stderr, "[walk profile]");
+			for (int k = 0; k < 16; k++) fprintf(stderr, " %llu", h[k]);
+			fprintf(stderr, "\n");
+		}
+	}
+#endif
 	if (!ctx) return;
 	if (ctx->group.size() > 1) {  // a leader: stop and free the other members first
 		std::vector<rt_ctx*> members = ctx->group;

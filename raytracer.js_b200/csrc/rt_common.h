@@ -199,8 +199,7 @@ struct RtFrame {
 	RtQueueItem* vqueue;     // [capacity], or null: the bounce stage traces all frames of such a pixel itself
 	unsigned* vqueue_count;
 	unsigned* vqueue_taken;
-	double* samples;         // resample stage: per-warp sample buffers
-	unsigned long long samples_per_warp;  // doubles per warp
+	double* samples;         // resample stage: [pixels of a round][n_frames][3] path colours
 	int bounce_min_walking;  // bounce stage: leave the lock-step walk when fewer lanes than this are still walking
 	int bounce_node_batch;   // bounce stage: lanes that need a node step wait until this many do
 };

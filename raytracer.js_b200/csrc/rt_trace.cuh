@@ -1239,6 +1239,29 @@ RT_HD double rng_next(RtRng& g) {
 // The list BVH sits on top of the octree entries, so a list is finished before the next node is popped, and
 // the walk ends at the first list that holds a hit.  A conservative (slack) pierce test can only add nodes,
 // which cannot change a first hit (entities lie inside their node's cube).
+#if defined(RT_WALK_STATS) && !defined(__CUDA_ARCH__)  // tests/hostsim: step counts of the ordered walk (tools, not product)
+extern unsigned long long g_walk_stats[8];  // iterations, node steps, pair steps, leaf tests, confirmations, lists entered
+#define RT_STAT(k) (__atomic_fetch_add(&g_walk_stats[k], 1ull, __ATOMIC_RELAXED))
+#else
+#define RT_STAT(k) ((void)0)
+#endif
+#if defined(RT_WALK_PROFILE) && defined(__CUDACC__)  // tools/ only: lane occupancy of the lock-step walk's phases
+__device__ unsigned long long g_walk_prof[16];
+#endif
+#if defined(RT_WALK_PROFILE) && defined(__CUDA_ARCH__)
+#define RT_PROF_LANES(k, cond)                                                                    \
+	do {                                                                                          \
+		const unsigned m_ = __ballot_sync(0xffffffffu, (cond));                                    \
+		if ((threadIdx.x & 31) == 0 && m_) atomicAdd(&g_walk_prof[k], (unsigned long long)__popc(m_)); \
+	} while (0)
+#define RT_PROF_COUNT(k)                                                  \
+	do {                                                                  \
+		if ((threadIdx.x & 31) == 0) atomicAdd(&g_walk_prof[k], 1ull);     \
+	} while (0)
+#else
+#define RT_PROF_LANES(k, cond) ((void)0)
+#define RT_PROF_COUNT(k) ((void)0)
+#endif
 struct RtWalk {
 	RtRayF r;
 	int neg;          // bit k: d_k < 0
@@ -1398,6 +1421,7 @@ RT_HD void walk_leaf(const RtDevScene& S, RtWalk& W, int leaf_a, const double* o
 #pragma unroll
 		for (int q = 1; q < RT_BVH_LEAF; q++) s = k == q ? slots[q] : s;
 		if (s >= W.best) break;
+		RT_STAT(4);
 		if (confirm_hit(S, s, (spheres >> k) & 1u, o, d)) {
 			W.best = s;  // ascending slots: the later candidates of this leaf cannot beat it
 			break;
@@ -1411,6 +1435,7 @@ RT_HD void walk_leaf(const RtDevScene& S, RtWalk& W, int leaf_a, const double* o
 // diverged warp (ray-by-ray kernels) and no warp-wide barrier is used.
 template <bool LOCKSTEP>
 RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const double* d, bool walking, int node_batch = 1) {
+	if (walking) RT_STAT(0);
 	if (walking && W.sp > RT_WALK_CAP - RT_WALK_PUSHES_PER_ITER) {  // no room for this iteration's pushes
 		W.hit = RT_WALK_OVERFLOW;
 		walking = false;
@@ -1443,12 +1468,19 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 			push = true;
 		}
 	}
-	if (LOCKSTEP) warp_sync();
+	if (LOCKSTEP) {
+		warp_sync();
+		RT_PROF_COUNT(0);                      // warp iterations
+		RT_PROF_LANES(1, walking);             // lanes walking
+		RT_PROF_LANES(2, rec_node >= 0);       // lanes taking a node step
+		RT_PROF_LANES(3, walking && !W.in_list && rec_node < 0);  // lanes waiting for a node batch
+	}
 	// (b) its 64-byte record: children, then the root of the list's BVH (box test right here)
 	int leaf0 = -1, leaf1 = -1;  // leaves whose entities are to be tested in this iteration
 	int nd_leaf = -1;
 	(void)leaf1; (void)nd_leaf;
 	if (rec_node >= 0) {
+		RT_STAT(1);
 		const RtWNode nd = ld(S.node_walk + rec_node);
 		if (push) walk_push_children(W, nd, after);
 		else W.chain_up = nd.up;
@@ -1469,6 +1501,7 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 	if (nd_leaf >= 0) walk_push(W, nd_leaf | RT_WALK_LEAF_TAG);
 	if (walking && W.in_list && W.sp > W.floor && !(W.stack[W.sp - 1] & RT_WALK_LEAF_TAG)) {
 		pair_step = true;
+		RT_STAT(2);
 		const RtBvhNode* np = S.bvh_nodes + W.stack[--W.sp];
 		const RtF4 a0 = ld(reinterpret_cast<const RtF4*>(np));
 		const RtI4 a1 = ld(reinterpret_cast<const RtI4*>(np) + 1);
@@ -1480,7 +1513,10 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 		if (hit_b && (b1.w > 0 || -(b1.w + 1) < W.best)) walk_push(W, b1.w < 0 ? b1.z : (b1.z | RT_WALK_LEAF_TAG));
 		if (hit_a && (a1.w > 0 || -(a1.w + 1) < W.best)) walk_push(W, a1.w < 0 ? a1.z : (a1.z | RT_WALK_LEAF_TAG));
 	}
-	if (LOCKSTEP) warp_sync();
+	if (LOCKSTEP) {
+		warp_sync();
+		RT_PROF_LANES(4, pair_step);
+	}
 	// ---- leaf entities
 	{
 		bool leaf_step = walking && W.in_list && W.sp > W.floor && (W.stack[W.sp - 1] & RT_WALK_LEAF_TAG);
@@ -1488,7 +1524,14 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 			const int n_leaf = popc32(lane_vote(leaf_step));
 			const unsigned moved = lane_vote(pair_step || rec_node >= 0);
 			if (n_leaf < RT_LEAF_DEFER && moved != 0u) leaf_step = false;
+			RT_PROF_LANES(5, leaf_step);
+#ifdef RT_WALK_PROFILE
+			if (lane_vote(leaf_step)) RT_PROF_COUNT(6);  // iterations with a leaf phase
+			if (lane_vote(rec_node >= 0)) RT_PROF_COUNT(7);  // iterations with a node phase
+			if (lane_vote(pair_step)) RT_PROF_COUNT(8);
+#endif
 		}
+		if (leaf_step) RT_STAT(3);
 		if (leaf_step) walk_leaf(S, W, W.stack[--W.sp] & ~RT_WALK_LEAF_TAG, o, d);
 	}
 	if (LOCKSTEP) warp_sync();
@@ -1528,6 +1571,7 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 	if (LOCKSTEP) warp_sync();
 #endif
 	if (walking && W.in_list && W.sp == W.floor) {  // the list is finished
+		RT_STAT(5);
 		W.in_list = 0;
 		if (W.best != RT_NO_SLOT) {
 			W.hit = W.best;

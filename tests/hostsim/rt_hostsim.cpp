@@ -67,6 +67,16 @@ extern "C" int hostsim_pack_digest(const rt_scene_desc* sc, uint64_t* digest, ch
 	return RT_OK;
 }
 
+#ifdef RT_WALK_STATS
+unsigned long long g_walk_stats[8];
+extern "C" void hostsim_walk_stats(unsigned long long* out, int reset) {
+	for (int k = 0; k < 8; k++) {
+		out[k] = g_walk_stats[k];
+		if (reset) g_walk_stats[k] = 0;
+	}
+}
+#endif
+
 extern "C" void hostsim_set_crop(int x, int y, int w, int h) {
 	g_crop[0] = x; g_crop[1] = y; g_crop[2] = w; g_crop[3] = h;
 }
