@@ -204,6 +204,15 @@ __global__ void __launch_bounds__(256)
 // than F.bounce_min_walking are left), so that a path that bounces four times or crosses a long list does
 // not hold finished lanes hostage: those shade, start their next segment or fetch a new pixel, and re-join.
 // Frames whose path never drew from the RNG reuse the first frame's sample.
+#ifdef RT_WALK_TIMELINE  // tools/ only: when do the warps of the bounce stage run out of queue, and when do they finish
+#define RT_PROF_WARPS 8192
+__device__ unsigned long long g_prof_start[RT_PROF_WARPS], g_prof_exhaust[RT_PROF_WARPS], g_prof_exit[RT_PROF_WARPS];
+__device__ __forceinline__ unsigned long long prof_now() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+#endif
 #define RT_ST_IDLE 0
 #define RT_ST_BEGIN 1
 #define RT_ST_WALK 2
@@ -225,6 +234,11 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 	RtPath P = {};  // (set by path_begin before any use; value-initialised to keep the compiler quiet)
 	RtWalk W;
 	bool exhausted = n == 0;
+#ifdef RT_WALK_TIMELINE
+	const unsigned prof_warp = min((unsigned)RT_PROF_WARPS - 1u, blockIdx.x * RT_WARPS_PER_CTA + (threadIdx.x >> 5));
+	if (lane == 0) g_prof_start[prof_warp] = prof_now();
+	bool prof_seen_exhausted = false;
+#endif
 	// a sample (path colour c) of exposure frame `frame` is complete: ExposureBuffer.set_color_i
 	// (src/view/exposure_buffer.ts:77-91) for this frame, and for all remaining ones when the path cannot
 	// change (it never drew from the RNG); then the next frame's path, or the end of the job
@@ -288,6 +302,12 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			}
 		}
 		if (__ballot_sync(0xffffffffu, st != RT_ST_IDLE) == 0u) break;
+#ifdef RT_WALK_TIMELINE
+		if (exhausted && !prof_seen_exhausted) {
+			prof_seen_exhausted = true;
+			if (lane == 0) g_prof_exhaust[prof_warp] = prof_now();
+		}
+#endif
 		RT_PROF_COUNT(9);                        // outer passes
 		RT_PROF_LANES(10, st == RT_ST_BEGIN);
 		RT_PROF_LANES(11, st == RT_ST_IDLE);
@@ -342,6 +362,9 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 		}
 		__syncwarp();
 	}
+#ifdef RT_WALK_TIMELINE
+	if (lane == 0) g_prof_exit[prof_warp] = prof_now();
+#endif
 	if (err) atomicOr(F.error_flags, err);
 }
 
@@ -665,6 +688,7 @@ struct rt_ctx {
 	cudaGraphExec_t graph_exec = nullptr;
 	uint64_t graph_kernels = 0, scene_version = 0;
 	int n_bands = 4;                             // rt_render: bands of tile rows (tuning knob RT_B200_BANDS)
+	bool n_bands_forced = false;
 	std::string err;
 	uint64_t launches = 0;
 	bool has_scene = false;
@@ -1083,6 +1107,12 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	return RT_OK;
 }
 
+// Bands overlap the host copy of a finished part of the frame with the rendering of the next - worth it while a frame
+// renders about as fast as it travels (refmax <= 1: 0.2 ms against 0.45 ms of copy).  With bouncing paths every band
+// would run its own bounce / resample stage over a quarter of the queue, and those stages end in a tail of long paths
+// whose length does not shrink with the queue: measured on configs[2], 4 bands cost 4.99 ms against 3.37 ms for one.
+int host_bands(const rt_ctx* ctx, const rt_params* prm) { return ctx->n_bands_forced || prm->refmax <= 1 ? ctx->n_bands : 1; }
+
 rt_status read_counters(rt_ctx* ctx, rt_counters* out) {
 	unsigned long long h[9] = {0};
 	if (ctx->counters.p)
@@ -1324,7 +1354,10 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	if (const char* e = getenv("RT_B200_GRAPHS")) ctx->use_graphs = atoi(e) != 0;
 	if (const char* e = getenv("RT_B200_BANDS")) {
 		const int v = atoi(e);
-		if (v >= 1 && v <= RT_MAX_BANDS) ctx->n_bands = v;
+		if (v >= 1 && v <= RT_MAX_BANDS) {
+			ctx->n_bands = v;
+			ctx->n_bands_forced = true;
+		}
 	}
 	if (const char* e = getenv("RT_B200_BOUNCE_MIN")) {
 		const int v = atoi(e);
@@ -1433,6 +1466,29 @@ void rt_destroy(rt_ctx* ctx) {
 			fprintf(stderr, "[walk profile]");
 			for (int k = 0; k < 16; k++) fprintf(stderr, " %llu", h[k]);
 			fprintf(stderr, "\n");
+		}
+	}
+#endif
+#ifdef RT_WALK_TIMELINE
+	if (ctx) {
+		cudaSetDevice(ctx->device);
+		cudaDeviceSynchronize();
+		static unsigned long long t_start[RT_PROF_WARPS], t_exh[RT_PROF_WARPS], t_exit[RT_PROF_WARPS];
+		if (cudaMemcpyFromSymbol(t_start, g_prof_start, sizeof t_start) == cudaSuccess && cudaMemcpyFromSymbol(t_exh, g_prof_exhaust, sizeof t_exh) == cudaSuccess &&
+		    cudaMemcpyFromSymbol(t_exit, g_prof_exit, sizeof t_exit) == cudaSuccess) {
+			unsigned long long t0 = ~0ull;
+			for (int k = 0; k < RT_PROF_WARPS; k++)
+				if (t_start[k]) t0 = std::min(t0, t_start[k]);
+			unsigned hist[3][256] = {{0}};
+			for (int k = 0; k < RT_PROF_WARPS; k++) {
+				if (!t_start[k]) continue;
+				hist[0][std::min<unsigned long long>(255, (t_start[k] - t0) / 50000)]++;
+				if (t_exh[k]) hist[1][std::min<unsigned long long>(255, (t_exh[k] - t0) / 50000)]++;
+				if (t_exit[k]) hist[2][std::min<unsigned long long>(255, (t_exit[k] - t0) / 50000)]++;
+			}
+			fprintf(stderr, "[bounce warps (last launch), 50 us buckets: started / queue exhausted / finished]\n");
+			for (int k = 0; k < 256; k++)
+				if (hist[0][k] || hist[1][k] || hist[2][k]) fprintf(stderr, "  %5d us  %6u %6u %6u\n", k * 50, hist[0][k], hist[1][k], hist[2][k]);
 		}
 	}
 #endif
@@ -1975,7 +2031,7 @@ rt_status rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uin
 		return RT_OK;
 	};
 	if (rt_status st = launch_render(ctx, cam, prm, flags, ctx->rgb.p, first_ids ? ctx->ids.p : nullptr, 0, 1, false,
-	                                 ctx->n_bands, copy_band))
+	                                 host_bands(ctx, prm), copy_band))
 		return st;
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
 	rt_counters tmp;
@@ -2017,7 +2073,7 @@ rt_status rt_render_begin(rt_ctx* ctx, const rt_camera* cam, const rt_params* pr
 			RT_CUDA(ctx, cudaMemcpyAsync(first_ids + off, ids_dev + off, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
 		return RT_OK;
 	};
-	if (rt_status st = launch_render(ctx, cam, prm, flags, rgb_dev, ids_dev, 0, 1, false, ctx->n_bands, copy_band)) return st;
+	if (rt_status st = launch_render(ctx, cam, prm, flags, rgb_dev, ids_dev, 0, 1, false, host_bands(ctx, prm), copy_band)) return st;
 	// this frame's counters and error flags, before the next frame's setup kernel zeroes the cells
 	RT_CUDA(ctx, cudaMemcpyAsync(ctx->pipe_counters + 9 * k, ctx->counters.p, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	RT_CUDA(ctx, cudaEventRecord(ctx->pipe_kernels[k], ctx->stream));

@@ -40,6 +40,15 @@ RT_HD double xsqrt(double a) { return sqrt(a); }
 #endif
 
 // ------------------------------------------------------------------ loads (read-only path, 16 B)
+// a record that will be fetched an iteration or more from now: start the fetch (no register, no dependency)
+RT_HD void prefetch_record(const void* p) {
+#ifdef __CUDA_ARCH__
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+	(void)p;
+#endif
+}
+
 RT_HD RtF4 ld(const RtF4* p) {
 #if defined(__CUDACC__)
 	const float4 v = __ldg(reinterpret_cast<const float4*>(p));
@@ -1295,6 +1304,12 @@ struct RtWalk {
 #ifndef RT_LEAF_DEFER
 #define RT_LEAF_DEFER 4
 #endif
+// Every stack entry is a dependent fetch when it is popped; the record is requested when the entry is PUSHED.
+// (Measured on configs[2] / [3], round 2: 2-3 % SLOWER with it - the 32 resident warps already cover the fetch, the
+// extra instructions do not pay.  Off.)
+#ifndef RT_WALK_PREFETCH
+#define RT_WALK_PREFETCH 0
+#endif
 static_assert(RT_WALK_CAP > RT_WALK_PUSHES_PER_ITER, "walk stack smaller than one iteration's pushes");
 RT_HD void walk_push(RtWalk& W, int v) { W.stack[W.sp++] = v; }
 
@@ -1303,7 +1318,7 @@ RT_HD void walk_push(RtWalk& W, int v) { W.stack[W.sp++] = v; }
 // half it is in, so the parameter interval of a child is a static selection among the intervals of the two
 // halves per axis.  The eight interval tests are predicates only (no branches); the loop runs once per child
 // actually pushed.
-RT_HD void walk_push_children(RtWalk& W, const RtWNode& nd, int after_oct) {
+RT_HD void walk_push_children(RtWalk& W, const RtWNode& nd, int after_oct, const RtWNode* node_walk) {
 	const RtRayF& r = W.r;
 	const float h = nd.size * 0.5f;
 	float n0[3], f0[3], n1[3], f1[3];  // [near, far] of half 0 and of half 1, per axis
@@ -1343,7 +1358,9 @@ RT_HD void walk_push_children(RtWalk& W, const RtWNode& nd, int after_oct) {
 		const int key = 31 - clz32(m);
 		m ^= 1u << key;
 		const int o = key ^ W.neg;
-		walk_push(W, nd.child_base + popc32((unsigned)nd.child_mask & ((1u << o) - 1u)));
+		const int child = nd.child_base + popc32((unsigned)nd.child_mask & ((1u << o) - 1u));
+		walk_push(W, child);
+		if (RT_WALK_PREFETCH) prefetch_record(node_walk + child);
 	}
 }
 
@@ -1361,7 +1378,7 @@ RT_HD void walk_begin(const RtDevScene& S, RtWalk& W, int node, int octant) {
 	W.chain_oct = octant;
 	W.chain_listed = 0;
 	W.chain_up = -1;
-	if (octant >= 0) walk_push_children(W, ld(S.node_walk + node), octant);
+	if (octant >= 0) walk_push_children(W, ld(S.node_walk + node), octant, S.node_walk);
 }
 
 // float64 confirmation without the collision record (the caller recomputes it for the one slot it keeps)
@@ -1482,7 +1499,7 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 	if (rec_node >= 0) {
 		RT_STAT(1);
 		const RtWNode nd = ld(S.node_walk + rec_node);
-		if (push) walk_push_children(W, nd, after);
+		if (push) walk_push_children(W, nd, after, S.node_walk);
 		else W.chain_up = nd.up;
 		if (list && nd.b != 0 && walk_hits_box(W, nd.lo[0], nd.lo[1], nd.lo[2], nd.hi[0], nd.hi[1], nd.hi[2])) {
 			W.floor = W.sp;
@@ -1490,6 +1507,7 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 			W.best = RT_NO_SLOT;
 			if (nd.b < 0) walk_push(W, nd.a);
 			else leaf0 = nd_leaf = nd.a;
+			if (RT_WALK_PREFETCH) prefetch_record(nd.b < 0 ? (const void*)(S.bvh_nodes + nd.a) : (const void*)(S.bvh_geom + nd.a));
 		}
 	}
 	if (LOCKSTEP) warp_sync();
@@ -1510,8 +1528,14 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 		const bool hit_a = walk_hits_box(W, a0.x, a0.y, a0.z, a0.w, int_as_float(a1.x), int_as_float(a1.y));
 		const bool hit_b = walk_hits_box(W, b0.x, b0.y, b0.z, b0.w, int_as_float(b1.x), int_as_float(b1.y));
 		// the right sibling first, so that the left one - which holds the lowest slot - is popped first
-		if (hit_b && (b1.w > 0 || -(b1.w + 1) < W.best)) walk_push(W, b1.w < 0 ? b1.z : (b1.z | RT_WALK_LEAF_TAG));
-		if (hit_a && (a1.w > 0 || -(a1.w + 1) < W.best)) walk_push(W, a1.w < 0 ? a1.z : (a1.z | RT_WALK_LEAF_TAG));
+		if (hit_b && (b1.w > 0 || -(b1.w + 1) < W.best)) {
+			walk_push(W, b1.w < 0 ? b1.z : (b1.z | RT_WALK_LEAF_TAG));
+			if (RT_WALK_PREFETCH) prefetch_record(b1.w < 0 ? (const void*)(S.bvh_nodes + b1.z) : (const void*)(S.bvh_geom + b1.z));
+		}
+		if (hit_a && (a1.w > 0 || -(a1.w + 1) < W.best)) {
+			walk_push(W, a1.w < 0 ? a1.z : (a1.z | RT_WALK_LEAF_TAG));
+			if (RT_WALK_PREFETCH) prefetch_record(a1.w < 0 ? (const void*)(S.bvh_nodes + a1.z) : (const void*)(S.bvh_geom + a1.z));
+		}
 	}
 	if (LOCKSTEP) {
 		warp_sync();

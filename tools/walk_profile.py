@@ -11,7 +11,26 @@ from util import gpu_render_flat  # noqa: E402
 cfg = scenes.BASELINE_CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
 fb = scenes.build_config(cfg)
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-rgb, ids, launches = gpu_render_flat(fb, cfg["w"], cfg["h"], spp)
-print("launches", launches, "hit fraction", float((ids >= 0).mean()))
+import ctypes as C  # noqa: E402
+
+import torch  # noqa: E402
+
+import raytracer_js_b200 as rt  # noqa: E402
+from raytracer_js_b200 import _native as N  # noqa: E402
+from util import flat_params  # noqa: E402
+
+lib = N.load()
+ctx = C.c_void_p()
+N.check(None, lib.rt_create(0, C.byref(ctx)))
+d = fb.flat.desc()
+N.check(ctx, lib.rt_scene_upload(ctx, C.byref(d)))
+W, H = cfg["w"], cfg["h"]
+cd = rt.camera_desc(scenes.bench_camera(W, H))
+prm = flat_params(fb, spp)
+frame = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda")
+N.check(ctx, lib.rt_render_device(ctx, C.byref(cd), C.byref(prm), 0, C.c_void_p(frame.data_ptr()), None))  # one band, one launch per stage
+N.check(ctx, lib.rt_synchronize(ctx))
+print("launches", int(lib.rt_launch_count(ctx)))
+lib.rt_destroy(ctx)
 print("fields: iterations walking node_steps node_waiting pair_steps leaf_steps iters_with_leaf iters_with_node iters_with_pair "
       "passes begin idle end_top end")
