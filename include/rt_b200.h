@@ -126,6 +126,11 @@ typedef struct rt_camera {
 } rt_camera;
 
 #define RT_PRECISION_F32 0u /* float search + float64 confirmation/shading of the found hit (default) */
+/* float64 search: every ray is walked by the reference's own walker (OctreeWalker.next, src/octree_space.ts:316-361)
+ * restated in float64 - cell by cell, same expressions - one ray per lane.  No packet stage and no lock-step walk:
+ * several times slower, but without the float32 search's limit on the depth of the octree (cells smaller than a
+ * float32 ulp of the coordinates, about 23 levels below a unit root, are refused with RT_PRECISION_F32). */
+#define RT_PRECISION_F64 1u
 
 /* rt_params.flags (validation / A-B measurement switches; results are identical either way) */
 #define RT_PARAM_NO_PRIMARY_RECORDS 1u /* no per-frame origin-relative records: every ray takes the generic path */

@@ -724,6 +724,7 @@ struct rt_ctx {
 	struct HostMap { void* host; size_t bytes; bool registered; std::vector<void*> dev; };
 	std::vector<HostMap> hostmaps;  // caller-owned host frames mapped into every member's address space
 	DevBuf<RtF4> node_geom;
+	DevBuf<RtD4> node_geom64;
 	DevBuf<RtI4> node_link;
 	DevBuf<int> node_child;
 	DevBuf<RtPNode> node_pk;
@@ -917,7 +918,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 		F.prim_geom = ctx->prim_geom.p;
 		rt_fill_chain(H, F);
 	}
-	const bool pipeline = F.packet_ok && !count && !(prm->flags & RT_PARAM_PER_RAY);
+	const bool pipeline = F.packet_ok && !count && !(prm->flags & RT_PARAM_PER_RAY) && !F.search64;
 	if (!pipeline) F.packet_ok = 0;
 	// rough pixels: from RT_RESAMPLE_MIN_FRAMES exposure frames on, their frames are traced as independent samples
 	// by the resample stage (below that the bounce stage's lane traces them in a row: re-tracing the first frame
@@ -1528,7 +1529,7 @@ void rt_destroy(rt_ctx* ctx) {
 	if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
 	if (ctx->done_ev) cudaEventDestroy(ctx->done_ev);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->node_geom.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_walk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release(); ctx->bvh_geom.release();
+	ctx->node_geom.release(); ctx->node_geom64.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_walk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release(); ctx->bvh_geom.release();
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->ray_ck.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
@@ -1633,7 +1634,7 @@ rt_status rt_host_unregister(rt_ctx* ctx, void* ptr) {
 
 // every device array of a scene, with its host vector of the same name in RtHostScene
 #define RT_SCENE_ARRAYS(X) \
-	X(node_geom) X(node_link) X(node_child) X(node_pk) X(node_walk) X(node_bvh) X(bvh_nodes) X(bvh_slots) X(bvh_geom) \
+	X(node_geom) X(node_geom64) X(node_link) X(node_child) X(node_pk) X(node_walk) X(node_bvh) X(bvh_nodes) X(bvh_slots) X(bvh_geom) \
 	X(slot_geom) X(slot_geom64) X(slot_attr) X(materials) X(textures) X(substances) X(texels)
 
 static void set_dev_scene(rt_ctx* ctx) {

@@ -96,6 +96,7 @@ struct alignas(16) RtTexture {
 struct RtDevScene {
 	// octree, 64 B per node across three arrays
 	const RtF4* node_geom;   // pos.xyz, size  (float copy of OctreeDim)
+	const RtD4* node_geom64; // pos.xyz, size as the reference holds them (RT_PRECISION_F64: the float64 walker)
 	const RtI4* node_link;   // parent, index_within_parent, list_off, list_cnt
 	const int* node_child;   // [n*8], -1 none
 	const RtPNode* node_pk;  // the same nodes as one 32-byte record each, for the packet walk
@@ -200,6 +201,7 @@ struct RtFrame {
 	unsigned* vqueue_count;
 	unsigned* vqueue_taken;
 	double* samples;         // resample stage: [pixels of a round][n_frames][3] path colours
+	int search64;            // RT_PRECISION_F64: the cell-by-cell walker in float64 (walk_and_scan64), one ray per lane
 	int bounce_min_walking;  // bounce stage: leave the lock-step walk when fewer lanes than this are still walking
 	int bounce_node_batch;   // bounce stage: lanes that need a node step wait until this many do
 };

@@ -21,6 +21,7 @@
 
 struct RtHostScene {
 	std::vector<RtF4> node_geom;
+	std::vector<RtD4> node_geom64;
 	std::vector<RtI4> node_link;
 	std::vector<int> node_child;
 	std::vector<RtPNode> node_pk;
@@ -42,6 +43,7 @@ struct RtHostScene {
 	float err_l = 0;
 	bool any_transmission = false;
 	int max_depth = 0;  // deepest node level (root = 0)
+	std::string f32_refusal;  // non-empty: why this tree cannot be searched in float32 (RT_PRECISION_F64 can)
 };
 
 inline std::string rt_format(const char* fmt, ...);
@@ -485,6 +487,7 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 	}
 	if (order.size() != N) RT_FAIL(RT_ERR_INVALID, "%zu of %u nodes are not reachable from the root", (size_t)N - order.size(), N);
 	hs.node_geom.resize(N);
+	hs.node_geom64.resize(N);
 	hs.node_link.resize(N);
 	hs.node_child.resize((size_t)N * 8);
 	hs.node_pk.resize(N);
@@ -505,6 +508,7 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 			const double* p = sc->node_pos + 3 * (size_t)i;
 			const double s = sc->node_size[i];
 			hs.node_geom[ni] = RtF4{(float)p[0], (float)p[1], (float)p[2], (float)s};
+			hs.node_geom64[ni] = RtD4{p[0], p[1], p[2], s};
 			const int par = sc->node_parent[i];
 			const int off = (int)slot_base[ni], cnt = (int)(slot_base[ni + 1] - slot_base[ni]);
 			hs.node_link[ni] = RtI4{i > 0 ? perm[par] : -1, i > 0 ? sc->node_octant[i] : -1, off, cnt};
@@ -627,9 +631,10 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 		double min_size = sc->node_size[0];
 		for (uint32_t i = 0; i < N; i++) min_size = std::min(min_size, sc->node_size[i]);
 		const double ulp = std::ldexp(1.0, std::ilogb(scale > 0 ? scale : 1.0) - 23);
-		if (min_size * 0.5 < ulp)
-			RT_FAIL(RT_ERR_UNSUPPORTED, "octree cells of size %.3g are below the float32 resolution of the search at coordinate scale %.3g "
-			                            "(a unit root allows 23 levels): lower max_in_depth", min_size, scale);
+		hs.f32_refusal.clear();
+		if (min_size * 0.5 < ulp)  // (not an upload error: RT_PRECISION_F64 renders such a tree; a float32 render call is refused)
+			hs.f32_refusal = rt_format("octree cells of size %.3g are below the float32 resolution of the search at coordinate scale %.3g "
+			                           "(a unit root allows 23 levels): lower max_in_depth, or render with RT_PRECISION_F64", min_size, scale);
 	}
 	clk.mark("geometry checks");
 	rt_build_list_bvhs(hs);
@@ -777,7 +782,7 @@ inline rt_status rt_check_render_args(bool has_scene, uint32_t n_textures, uint3
 		err = "x or y out of bounds";
 		return RT_ERR_BOUNDS;
 	}
-	if (prm->precision != RT_PRECISION_F32) { err = rt_format("unsupported precision %u", prm->precision); return RT_ERR_UNSUPPORTED; }
+	if (prm->precision != RT_PRECISION_F32 && prm->precision != RT_PRECISION_F64) { err = rt_format("unsupported precision %u", prm->precision); return RT_ERR_UNSUPPORTED; }
 	if (prm->n_frames == 0) { err = "rt_render: n_frames must be >= 1"; return RT_ERR_INVALID; }
 	if (prm->sky_texture < 0 || (uint32_t)prm->sky_texture >= n_textures) {
 		err = rt_format("rt_render: sky_texture %d out of range", prm->sky_texture);
@@ -793,6 +798,11 @@ inline rt_status rt_check_render_args(bool has_scene, uint32_t n_textures, uint3
 // Fills the camera / start-state / config part of an RtFrame (pointers are left to the caller).
 inline rt_status rt_fill_frame(const RtHostScene& hs, const rt_camera* cam, const rt_params* prm, RtFrame& F,
                                std::string& err) {
+	if (prm->precision == RT_PRECISION_F32 && !hs.f32_refusal.empty()) {
+		err = hs.f32_refusal;
+		return RT_ERR_UNSUPPORTED;
+	}
+	F.search64 = prm->precision == RT_PRECISION_F64;
 	for (int i = 0; i < 3; i++) {
 		F.pos[i] = cam->pos[i];
 		F.lf[i] = cam->lf[i];

@@ -561,6 +561,83 @@ RT_HD int walk_and_scan(const RtDevScene& S, const RtSearch& q, int node, int oc
 	return -1;
 }
 
+// RT_PRECISION_F64: the same walker with the reference's own float64 expressions - the cells are taken from
+// node_geom64 (the OctreeDim values the reference holds), the exit point of a cell is Box.line_intersection's u2 and
+// its face (update_next_pos, src/octree_space.ts:369-384 via dim_relative_to_parent :127-136), a step into a child
+// is octant_adj_pos (:41-50) of that point.  No float32 value takes part in a decision of the walk, so the tree may
+// be as deep as the reference allows; the list scan keeps its float32 FILTER (conservative by err_l at any depth)
+// in front of the float64 confirmations.
+template <bool COUNT>
+RT_HD int walk_and_scan64(const RtDevScene& S, const RtSearch& q, int node, int octant, const double* o,
+                          const double* d, RtCollision& col, RtCounts& cnt) {
+	bool cur_returned = false, stepped_in = false, ahead = false;
+	int depth = 0;
+	double np[3] = {o[0], o[1], o[2]};  // next_pos[0]
+	int face = -1;                       // next_pos[1] as a face index (axis*2 + positive), -1: the zero vector
+	RtD4 g = ld(S.node_geom64 + node);
+	while (true) {
+		const int child = octant >= 0 ? ld(S.node_child + node * 8 + octant) : node;
+		if (!cur_returned && child >= 0) {
+			cur_returned = true;
+			if (COUNT) cnt.nodes++;
+			const RtI4 link = ld(S.node_link + child);
+			if (link.w > 0) {
+				const int s = scan_list<COUNT>(S, q, child, link.z, link.z + link.w, o, d, col, cnt);
+				if (s >= 0) return s;
+			}
+		}
+		if (octant >= 0) {
+			if (!ahead) {
+				if (!stepped_in && child >= 0) {  // step_in :310-314 with octant_adj_pos(child, next_pos[0])
+					g = ld(S.node_geom64 + child);
+					const double h = g.w / 2;
+					octant = (np[0] >= xadd(g.x, h) ? 1 : 0) | (np[1] >= xadd(g.y, h) ? 2 : 0) | (np[2] >= xadd(g.z, h) ? 4 : 0);
+					node = child;
+					depth++;
+					cur_returned = false;
+					continue;
+				}
+				// update_next_pos: the cell (node, octant) as a box, Box.line_intersection, the far parameter and its face
+				const double ph = g.w / 2;
+				const double gp[3] = {g.x, g.y, g.z};
+				double c[3];
+#pragma unroll
+				for (int k = 0; k < 3; k++) c[k] = xadd(xadd(gp[k], xmul((double)((octant >> k) & 1), ph)), xmul(0.5, ph));
+				double u1, u2;
+				int i1, i2;
+				exact_box_params(c, ph, o, d, u1, u2, i1, i2);
+				if (i2 < 0) return -1;  // no parameter at all (a zero direction): the reference throws a TypeError here
+#pragma unroll
+				for (int k = 0; k < 3; k++) np[k] = xadd(o[k], xmul(d[k], u2));
+				face = i2;
+			}
+			const int axis = face >> 1;
+			const int bit = (octant >> axis) & 1;
+			if (bit != (face & 1)) {  // octant + normal stays inside the parent cube :344-352
+				octant ^= 1 << axis;
+				cur_returned = false;
+				stepped_in = false;
+				ahead = false;
+				continue;
+			}
+			ahead = true;
+		}
+		// step_back :280-308
+		stepped_in = true;
+		if (octant < 0) return -1;
+		if (depth > 0) { depth--; cur_returned = true; }
+		else cur_returned = false;
+		const RtI4 link = ld(S.node_link + node);
+		if (link.x >= 0) {
+			octant = link.y;
+			node = link.x;
+			g = ld(S.node_geom64 + node);
+		} else {
+			octant = -1;
+		}
+	}
+}
+
 // Lock-step pre-test of the origin-chain lists for a primary ray: every lane of the warp runs over the
 // same slots (uniform 16 B loads).  Bit k of the result is set if the list of chain level k holds a
 // (conservative) candidate.
@@ -1701,6 +1778,11 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 		walk_begin(S, *W, P.node, P.octant);
 		return RT_SEG_WALK;
 	}
+	if (F.search64) {
+		slot = walk_and_scan64<COUNT>(S, q, P.node, P.octant, P.refpoint, P.dir, ci, cnt);
+		err |= cnt.errors;
+		return RT_SEG_SLOT;
+	}
 	if (q.rel && P.have_node) {  // lock-step pre-test of the shared origin chain
 		q.chain_levels = F.chain_levels;
 		q.chain_mask = pretest_chain(F, S, q);
@@ -1833,7 +1915,7 @@ RT_HD bool path_segment(const RtDevScene& S, const RtFrame& F, RtPath& P, double
                         RtCounts& cnt, uint32_t& err) {
 	int slot;
 	RtCollision ci;
-	if (!COUNT && S.ordered_ok) {
+	if (!COUNT && S.ordered_ok && !F.search64) {
 		RtWalk W;
 		const int r = segment_begin<COUNT>(S, F, P, primary_slot, out, cnt, err, &W, slot, ci);
 		if (r == RT_SEG_DONE) return true;

@@ -46,8 +46,11 @@ def camera_desc(camera: Camera, reference_extents: bool = False) -> N.CameraDesc
 
 class GpuRaytracer:
     def __init__(self, config: RaytracerConfig, otree: Octree, camera: Camera, ebuffer: ExposureBuffer, rng: RNG,
-                 device: int = -1, reference_extents: bool = False, n_gpus: int = 1, devices=None):
-        """n_gpus > 1 (or an explicit `devices` list): one process drives all of them behind the same calls
+                 device: int = -1, reference_extents: bool = False, n_gpus: int = 1, devices=None,
+                 precision: int = N.RT_PRECISION_F32):
+        """precision: RT_PRECISION_F32 (float search + float64 confirmation, the default) or RT_PRECISION_F64 (the
+        reference's walker in float64, ray by ray: slower, but for octrees of any depth).
+        n_gpus > 1 (or an explicit `devices` list): one process drives all of them behind the same calls
         (rt_create_multi): the scene is packed once and replicated device to device, trace_frame() shards the
         frame into interleaved tiles and every GPU stores its tiles straight into the ExposureBuffer."""
         self._lib = N.load()
@@ -64,6 +67,7 @@ class GpuRaytracer:
         self._ebuffer = ebuffer
         self._rng = rng
         self.reference_extents = bool(reference_extents)
+        self.precision = int(precision)
         self.last_counters: Optional[dict] = None
         self.last_first_ids: Optional[np.ndarray] = None
         self.flat: Optional[FlatScene] = None
@@ -141,7 +145,7 @@ class GpuRaytracer:
         p.n_frames, p.frame_first = int(n_frames), int(frame_first)
         # the harness RNG policy (rt_b200.h): per-pixel reseed through the public PRNG.seed()
         p.rng_seed = float(getattr(self._rng, "seed_value", 1.0)) if isinstance(self._rng, PRNG) else 1.0
-        p.precision = N.RT_PRECISION_F32
+        p.precision = self.precision
         return p
 
     @property

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 
 def gpu_render(bundle, width, height, n_frames=1, pos=scenes.BENCH_CAMERA_POS, yaw=30.0, pitch=0.0, refmax=None,
-               reference_extents=False, frames_as_calls=False):
+               reference_extents=False, frames_as_calls=False, precision=N.RT_PRECISION_F32):
     """Renders the frame twice through rt_render: (1) the default path, the two-stage pipeline (packet
     primary stage + bounce stage); (2) the counting variant, which walks every ray one by one and returns
     the reference-pattern work counters.  Both must give the same pixels; the pipeline's are returned."""
@@ -29,7 +29,7 @@ def gpu_render(bundle, width, height, n_frames=1, pos=scenes.BENCH_CAMERA_POS, y
     out = []
     for want_counters in (False, True):
         eb = rt.ExposureBuffer(width, height)
-        tracer = rt.GpuRaytracer(cfg, bundle.tree, cam, eb, rt.FpLcg(1.0), reference_extents=reference_extents)
+        tracer = rt.GpuRaytracer(cfg, bundle.tree, cam, eb, rt.FpLcg(1.0), reference_extents=reference_extents, precision=precision)
         assert tracer.lib.rt_launch_count(tracer.ctx) == 0
         if frames_as_calls:
             for f in range(n_frames):  # the reference's own loop: tick(); next_frame(); tick(); ...
@@ -350,8 +350,7 @@ def test_repeated_device_renders_replay_a_graph():
 @pytest.mark.parametrize("max_in_depth", [20, 23])
 def test_deep_trees_take_the_fallback_walker(oracle, max_in_depth):
     """An octree deeper than the bounce stage's walk stack (RT_WALK_STACK): secondary rays are searched by the
-    reference-order walker instead of the lock-step one; same pixels as the oracle.  Deeper than float32 can
-    resolve: refused (RT_ERR_UNSUPPORTED)."""
+    reference-order walker instead of the lock-step one; same pixels as the oracle."""
     from test_hostsim_parity import deep_scene
     b = deep_scene(max_in_depth)
     rgb, ids, cnt, tracer = gpu_render(b, 64, 64, n_frames=2)
@@ -361,11 +360,39 @@ def test_deep_trees_take_the_fallback_walker(oracle, max_in_depth):
     orgb, oids, _, tot = oracle_render(oracle_scene(flat, b, max_in_depth=max_in_depth), ocam, flat, b, prm, fixed_extents=True)
     res = compare(rgb, ids, orgb, oids)
     assert res["id_match"] >= 0.9999 and res["rgb_bad"] == 0, res
-    if max_in_depth == 23:
-        deep = deep_scene(30)
-        with pytest.raises(N.RtError, match="float32 resolution"):
-            rt.GpuRaytracer(rt.RaytracerConfig(deep.refmax, deep.sky, deep.default_substance, 1.0), deep.tree,
-                            scenes.bench_camera(64, 64), rt.ExposureBuffer(64, 64), rt.FpLcg(1.0))
+
+
+@pytest.mark.parametrize("max_in_depth", [30, 34])
+def test_float64_search_renders_trees_of_any_depth(oracle, max_in_depth):
+    """A tree deeper than float32 can resolve: the float32 search refuses the render call (RT_ERR_UNSUPPORTED, the
+    upload is fine); RT_PRECISION_F64 - the reference's walker in float64, ray by ray - gives the oracle's frame, and
+    its counting variant the oracle's counters, exactly."""
+    from test_hostsim_parity import deep_scene
+    deep = deep_scene(max_in_depth)
+    cfg = rt.RaytracerConfig(deep.refmax, deep.sky, deep.default_substance, 1.0)
+    refused = rt.GpuRaytracer(cfg, deep.tree, scenes.bench_camera(64, 64), rt.ExposureBuffer(64, 64), rt.FpLcg(1.0))
+    with pytest.raises(N.RtError, match="float32 resolution") as e:
+        refused.trace_frame()
+    assert e.value.status == N.RT_ERR_UNSUPPORTED
+    refused.close()
+    rgb, ids, cnt, tracer = gpu_render(deep, 64, 64, n_frames=2, precision=N.RT_PRECISION_F64)
+    flat = tracer.flat
+    ocam = ocam_for(64, 64)
+    prm = make_params(flat, deep, n_frames=2)
+    orgb, oids, _, tot = oracle_render(oracle_scene(flat, deep, max_in_depth=max_in_depth), ocam, flat, deep, prm, fixed_extents=True,
+                                       want_counters=True)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0 and res["rgb_max_abs"] == 0.0, res
+    for key in ("paths", "segments", "nodes", "tests", "shades"):
+        assert cnt[key] == tot[key], (key, cnt, tot)
+
+
+def test_float64_search_equals_float32_search(oracle):
+    b = scenes.random_spheres(3000, 0.01, 0.05, seed=8.0, mix="mirrors", box_fraction=0.1)
+    rgb32, ids32, _, _ = gpu_render(b, 200, 120, n_frames=2)
+    rgb64, ids64, _, _ = gpu_render(b, 200, 120, n_frames=2, precision=N.RT_PRECISION_F64)
+    np.testing.assert_array_equal(ids64, ids32)
+    np.testing.assert_array_equal(rgb64, rgb32)
 
 
 def test_resample_stage_equals_frames_in_a_row(oracle, monkeypatch):

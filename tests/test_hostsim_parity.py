@@ -8,6 +8,7 @@ import pytest
 
 import oracle as orc
 import raytracer_js_b200 as rt
+from raytracer_js_b200 import _native as N
 from raytracer_js_b200 import scenes
 
 from util import assert_parity, compare, flat_of, hostsim_render, insertion_ids, make_params, oracle_render, oracle_scene
@@ -299,6 +300,42 @@ def test_trees_below_float32_resolution_are_refused():
     cam, _ = cameras(64, 64)
     with pytest.raises(RuntimeError, match="float32 resolution"):
         hostsim_render(flat, cam, make_params(flat, b))
+
+
+@pytest.mark.parametrize("max_in_depth", [30, 34])
+def test_float64_search_renders_trees_of_any_depth(oracle, max_in_depth):
+    """RT_PRECISION_F64: the walker in the reference's own float64 expressions (walk_and_scan64).  A tree 30 or 34 levels
+    deep - refused by the float32 search - gives the oracle's frame, and the walk visits exactly the oracle's nodes
+    (the counters are the reference's access pattern: equal, not close)."""
+    b = deep_scene(max_in_depth)
+    flat = flat_of(b)
+    cam, ocam = cameras(64, 64)
+    prm = make_params(flat, b, n_frames=2)
+    prm.precision = N.RT_PRECISION_F64
+    rgb, ids, cnt = hostsim_render(flat, cam, prm)
+    orgb, oids, _, tot = oracle_render(oracle_scene(flat, b, max_in_depth=max_in_depth), ocam, flat, b, prm, fixed_extents=True,
+                                       want_counters=True)
+    ids = insertion_ids(flat, b, ids)
+    res = compare(rgb, ids, orgb, oids)
+    assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0 and res["rgb_max_abs"] == 0.0, res
+    assert len(set(ids.ravel().tolist()) & set(range(len(b.entities) - 4, len(b.entities)))) >= 2  # the tiny spheres are seen
+    for key in ("paths", "segments", "nodes", "tests", "shades"):
+        assert cnt[key] == tot[key], (key, cnt, tot)
+
+
+def test_float64_search_equals_float32_search_on_an_ordinary_scene(oracle):
+    b = scenes.random_spheres(3000, 0.01, 0.05, seed=8.0, mix="mirrors", box_fraction=0.1)
+    flat = flat_of(b)
+    cam, ocam = cameras(96, 96)
+    prm = make_params(flat, b, n_frames=2)
+    rgb32, ids32, cnt32 = hostsim_render(flat, cam, prm)
+    prm.precision = N.RT_PRECISION_F64
+    rgb64, ids64, cnt64 = hostsim_render(flat, cam, prm)
+    np.testing.assert_array_equal(ids64, ids32)
+    np.testing.assert_array_equal(rgb64, rgb32)
+    _, _, _, tot = oracle_render(oracle_scene(flat, b), ocam, flat, b, prm, fixed_extents=True, want_counters=True)
+    for key in ("paths", "segments", "nodes", "tests", "shades"):
+        assert cnt64[key] == tot[key], (key, cnt64, tot)
 
 
 @pytest.mark.parametrize("max_in_depth", [20, 23])
