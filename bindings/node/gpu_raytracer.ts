@@ -122,6 +122,9 @@ export class GpuRaytracer {
 	private n_gpus = 1;
 	/** seed handed to the per-pixel reseed policy (rt_b200.h: rt_params.rng_seed) */
 	rng_seed = 1.0;
+	/** 0: float32 search + float64 confirmation (default); 1: RT_PRECISION_F64, the walker in float64, ray by ray -
+	 *  for octrees deeper than float32 resolves (max_in_depth beyond ~23 below a unit root) */
+	precision = 0;
 
 	config: RaytracerConfig;
 
@@ -164,7 +167,7 @@ export class GpuRaytracer {
 			{ refmax: this.config.refmax, sky_texture: this.tex.get((this.config.sky as any).texture),
 			  default_substance: this.sub.get(this.config.default_substance),
 			  distance_attenuation_factor: this.config.distance_attenuation_factor,
-			  n_frames, frame_first: eb.current_frame, rng_seed: this.rng_seed, want_counters: 0 },
+			  n_frames, frame_first: eb.current_frame, rng_seed: this.rng_seed, want_counters: 0, precision: this.precision },
 			eb.store);
 		for (let i = 1; i < n_frames; ++i) eb.next_frame();
 	}

@@ -209,7 +209,7 @@ static napi_value Render(napi_env env, napi_callback_info info) {
 	prm.n_frames = (uint32_t)num(env, argv[2], "n_frames");
 	prm.frame_first = (uint32_t)num(env, argv[2], "frame_first");
 	prm.rng_seed = num(env, argv[2], "rng_seed");
-	prm.precision = RT_PRECISION_F32;
+	prm.precision = num(env, argv[2], "precision") == 1 ? RT_PRECISION_F64 : RT_PRECISION_F32; /* absent: float32 search */
 	want_counters = num(env, argv[2], "want_counters") != 0;
 	RT_NAPI_TRY(env, napi_get_typedarray_info(env, argv[3], &t, &npx, &rgb, NULL, NULL));
 	if (t != napi_float32_array || npx != (size_t)cam.width * cam.height * 3) {

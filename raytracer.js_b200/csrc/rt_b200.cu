@@ -128,6 +128,20 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, 4)
 #ifndef RT_A_MINB
 #define RT_A_MINB 5
 #endif
+#ifdef RT_WALK_TIMELINE  // tools/ only: when do the warps of the bounce stage run out of queue, and when do they finish
+#define RT_PROF_WARPS 8192
+__device__ unsigned long long g_prof_start[RT_PROF_WARPS], g_prof_exhaust[RT_PROF_WARPS], g_prof_exit[RT_PROF_WARPS];
+__device__ __forceinline__ unsigned long long prof_now() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+#endif
+#ifdef RT_WALK_TIMELINE  // tools/ only: start and duration of every packet of the primary stage
+#define RT_PROF_PACKETS 65536
+__device__ unsigned long long g_pk_start[RT_PROF_PACKETS];
+__device__ unsigned int g_pk_dur[RT_PROF_PACKETS];
+#endif
 template <int PPL, int MINB>
 __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
     rt_primary_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, int n_packets) {
@@ -151,7 +165,16 @@ __global__ void __launch_bounds__(RT_A_WARPS * 32, MINB)
 		pt.y0 = (tile / tiles_x) * RT_TILE_H;
 		pt.sub0 = (int)(p % PER_TILE) * PPL;
 		pt.out_base = (size_t)k * RT_BLOCK;
+#ifdef RT_WALK_TIMELINE
+		const unsigned long long pk_t0 = prof_now();
+#endif
 		primary_patch<PPL>(S, F, pt, stacks[warp], rays[warp], dirs[warp], stages[warp], err);
+#ifdef RT_WALK_TIMELINE
+		if (lane == 0 && p < RT_PROF_PACKETS) {
+			g_pk_start[p] = pk_t0;
+			g_pk_dur[p] = (unsigned)(prof_now() - pk_t0);
+		}
+#endif
 	}
 	if (err) atomicOr(F.error_flags, err);
 }
@@ -204,15 +227,6 @@ __global__ void __launch_bounds__(256)
 // than F.bounce_min_walking are left), so that a path that bounces four times or crosses a long list does
 // not hold finished lanes hostage: those shade, start their next segment or fetch a new pixel, and re-join.
 // Frames whose path never drew from the RNG reuse the first frame's sample.
-#ifdef RT_WALK_TIMELINE  // tools/ only: when do the warps of the bounce stage run out of queue, and when do they finish
-#define RT_PROF_WARPS 8192
-__device__ unsigned long long g_prof_start[RT_PROF_WARPS], g_prof_exhaust[RT_PROF_WARPS], g_prof_exit[RT_PROF_WARPS];
-__device__ __forceinline__ unsigned long long prof_now() {
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	return t;
-}
-#endif
 #define RT_ST_IDLE 0
 #define RT_ST_BEGIN 1
 #define RT_ST_WALK 2
@@ -1486,6 +1500,37 @@ void rt_destroy(rt_ctx* ctx) {
 				hist[0][std::min<unsigned long long>(255, (t_start[k] - t0) / 50000)]++;
 				if (t_exh[k]) hist[1][std::min<unsigned long long>(255, (t_exh[k] - t0) / 50000)]++;
 				if (t_exit[k]) hist[2][std::min<unsigned long long>(255, (t_exit[k] - t0) / 50000)]++;
+			}
+			{
+				static unsigned long long pk_start[RT_PROF_PACKETS];
+				static unsigned int pk_dur[RT_PROF_PACKETS];
+				if (cudaMemcpyFromSymbol(pk_start, g_pk_start, sizeof pk_start) == cudaSuccess && cudaMemcpyFromSymbol(pk_dur, g_pk_dur, sizeof pk_dur) == cudaSuccess) {
+					unsigned long long p0 = ~0ull, p1 = 0;
+					int n = 0;
+					for (int k = 0; k < RT_PROF_PACKETS; k++)
+						if (pk_start[k]) { p0 = std::min(p0, pk_start[k]); p1 = std::max(p1, pk_start[k] + pk_dur[k]); n = k + 1; }
+					if (n) {
+						fprintf(stderr, "[primary stage (last launch): %d packets, span %.1f us]\n", n, (p1 - p0) / 1e3);
+						unsigned started[64] = {0}, ended[64] = {0};
+						double dur_sum[64] = {0};
+						for (int k = 0; k < n; k++) {
+							if (!pk_start[k]) continue;
+							const int b0 = (int)std::min<unsigned long long>(63, (pk_start[k] - p0) / 10000), b1 = (int)std::min<unsigned long long>(63, (pk_start[k] + pk_dur[k] - p0) / 10000);
+							started[b0]++; ended[b1]++; dur_sum[b0] += pk_dur[k] / 1e3;
+						}
+						fprintf(stderr, "  10 us buckets: packets started / finished / mean duration (us) of those started\n");
+						for (int b = 0; b < 64; b++)
+							if (started[b] || ended[b]) fprintf(stderr, "  %4d us %6u %6u %8.1f\n", b * 10, started[b], ended[b], started[b] ? dur_sum[b] / started[b] : 0.0);
+						// by position in the dispenser's order (= tile order, row-major): mean duration of each 1/16 of the packets
+						fprintf(stderr, "  mean packet duration (us) by sixteenth of the frame:");
+						for (int q = 0; q < 16; q++) {
+							double sum = 0; int c = 0;
+							for (int k = n * q / 16; k < n * (q + 1) / 16; k++) if (pk_start[k]) { sum += pk_dur[k] / 1e3; c++; }
+							fprintf(stderr, " %.1f", c ? sum / c : 0.0);
+						}
+						fprintf(stderr, "\n");
+					}
+				}
 			}
 			fprintf(stderr, "[bounce warps (last launch), 50 us buckets: started / queue exhausted / finished]\n");
 			for (int k = 0; k < 256; k++)

@@ -8,8 +8,13 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from raytracer_js_b200 import scenes  # noqa: E402
 from util import gpu_render_flat  # noqa: E402
 
-cfg = scenes.BASELINE_CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
-fb = scenes.build_config(cfg)
+name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+if name == "c1":  # the headline scene of bench.py (configs[1]): 10 k diffuse spheres, refmax 1
+    cfg = dict(w=1920, h=1080)
+    fb = scenes.random_spheres_flat(10000, 0.002, 0.006, seed=42.0, mix="diffuse")
+else:
+    cfg = scenes.BASELINE_CONFIGS[name]
+    fb = scenes.build_config(cfg)
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 import ctypes as C  # noqa: E402
 
