@@ -208,6 +208,8 @@ def group_records(args, lib, n_gpus, flat, sky_tex, def_sub, cds, warm):
         out["headline"] = {"ms_per_step": ms, "value": npx / (ms * 1e-3) / 1e6, "unit": "Mrays/s",
                            "timing": "CUDA events on GPU 0's stream around the whole group frame (it waits for the other GPUs' events)"}
         host = np.zeros(npx * 3, np.float32)
+        if n_gpus == 1:  # a group of one is a plain ctx: page-lock the frame as the e2e leg does (a group maps it itself)
+            N.check(g, lib.rt_host_register(g, host.ctypes.data, host.nbytes))
         for i in range(3):
             N.check(g, lib.rt_render(g, C.byref(cds[i]), C.byref(prm), 0, host.ctypes.data, None, None))
         t0 = time.perf_counter()
@@ -215,7 +217,11 @@ def group_records(args, lib, n_gpus, flat, sky_tex, def_sub, cds, warm):
             N.check(g, lib.rt_render(g, C.byref(cds[warm + i]), C.byref(prm), 0, host.ctypes.data, None, None))
         dt = time.perf_counter() - t0
         out["headline"]["e2e"] = {"value": npx * args.steps / dt / 1e6, "unit": "Mrays/s", "frame_ms": dt / args.steps * 1e3,
-                                  "d2h_bytes_per_step": npx * 12, "delivery": "every GPU stores its tiles into the mapped host frame over its own PCIe link"}
+                                  "d2h_bytes_per_step": npx * 12,
+                                  "delivery": "every GPU stores its tiles into the mapped host frame over its own PCIe link" if n_gpus > 1
+                                  else "one GPU: banded copies into the page-locked host frame"}
+        if n_gpus == 1:
+            lib.rt_host_unregister(g, host.ctypes.data)
         del frame
         # ---- configs[4] class
         cfg = dict(scenes.BASELINE_CONFIGS["c4"])

@@ -355,7 +355,9 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 						RT_PROF_LANES(15, walking);
 					}
 #endif
-					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
+					// (a warp that is running empty - the stage's tail - batches nothing: its few paths are the critical path)
+					const bool sparse = nw < F.bounce_sparse;
+					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, sparse ? 1 : F.bounce_node_batch, sparse ? 1 : RT_LEAF_DEFER);
 					nw = __popc(__ballot_sync(0xffffffffu, walking));
 				} while (nw >= limit);
 				if (st == RT_ST_WALK && !walking) st = RT_ST_END;
@@ -469,7 +471,9 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			if (nw > 0) {
 				const int limit = max(1, min(F.bounce_min_walking, nw - (nw >> 2)));
 				do {
-					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, F.bounce_node_batch);
+					// (a warp that is running empty - the stage's tail - batches nothing: its few paths are the critical path)
+					const bool sparse = nw < F.bounce_sparse;
+					walking = walk_iter<true>(S, W, P.refpoint, P.dir, walking, sparse ? 1 : F.bounce_node_batch, sparse ? 1 : RT_LEAF_DEFER);
 					nw = __popc(__ballot_sync(0xffffffffu, walking));
 				} while (nw >= limit);
 				if (st == RT_ST_WALK && !walking) st = RT_ST_END;
@@ -785,6 +789,7 @@ struct rt_ctx {
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
 	int bounce_minb = 8;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
 	int bounce_node_batch = 4;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
+	int bounce_sparse = 8;                       // tuning knob RT_B200_SPARSE: below this many walking lanes a warp stops batching node / leaf steps
 };
 
 namespace {
@@ -907,6 +912,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	F.tile_compact = tile_compact ? 1 : 0;
 	F.bounce_min_walking = ctx->bounce_min_walking;
 	F.bounce_node_batch = ctx->bounce_node_batch;
+	F.bounce_sparse = ctx->bounce_sparse;
 	// u64 cells: [0..7] work counters, [8] error flags, then per band {patch dispenser, queue count, queue cursor,
 	// resample queue count, resample queue cursor}
 	n_bands = std::max(1, std::min(n_bands, RT_MAX_BANDS));
@@ -1389,6 +1395,10 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	if (const char* e = getenv("RT_B200_NODE_BATCH")) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= 32) ctx->bounce_node_batch = v;
+	}
+	if (const char* e = getenv("RT_B200_SPARSE")) {
+		const int v = atoi(e);
+		if (v >= 0 && v <= 33) ctx->bounce_sparse = v;
 	}
 	if (const char* e = getenv("RT_B200_PPL")) {
 		const int v = atoi(e);

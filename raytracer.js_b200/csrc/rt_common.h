@@ -204,6 +204,7 @@ struct RtFrame {
 	int search64;            // RT_PRECISION_F64: the cell-by-cell walker in float64 (walk_and_scan64), one ray per lane
 	int bounce_min_walking;  // bounce stage: leave the lock-step walk when fewer lanes than this are still walking
 	int bounce_node_batch;   // bounce stage: lanes that need a node step wait until this many do
+	int bounce_sparse;       // ... unless fewer lanes than this are walking at all (the stage's tail)
 };
 
 #define RT_ERRFLAG_TEXTURE 1u

@@ -1383,7 +1383,8 @@ struct RtWalk {
 #endif
 // Every stack entry is a dependent fetch when it is popped; the record is requested when the entry is PUSHED.
 // (Measured on configs[2] / [3], round 2: 2-3 % SLOWER with it - the 32 resident warps already cover the fetch, the
-// extra instructions do not pay.  Off.)
+// extra instructions do not pay; switched on at run time for the sparse warps of the stage's tail only, the test of
+// the switch cost the full warps more than the tail gained.  Off.)
 #ifndef RT_WALK_PREFETCH
 #define RT_WALK_PREFETCH 0
 #endif
@@ -1528,7 +1529,8 @@ RT_HD void walk_leaf(const RtDevScene& S, RtWalk& W, int leaf_a, const double* o
 // (bounce stage) and the phases re-converge the warp between them; without it the caller may be one lane of a
 // diverged warp (ray-by-ray kernels) and no warp-wide barrier is used.
 template <bool LOCKSTEP>
-RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const double* d, bool walking, int node_batch = 1) {
+RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const double* d, bool walking, int node_batch = 1,
+                     int leaf_batch = RT_LEAF_DEFER) {
 	if (walking) RT_STAT(0);
 	if (walking && W.sp > RT_WALK_CAP - RT_WALK_PUSHES_PER_ITER) {  // no room for this iteration's pushes
 		W.hit = RT_WALK_OVERFLOW;
@@ -1624,7 +1626,7 @@ RT_HD bool walk_iter(const RtDevScene& S, RtWalk& W, const double* o, const doub
 		if (LOCKSTEP) {
 			const int n_leaf = popc32(lane_vote(leaf_step));
 			const unsigned moved = lane_vote(pair_step || rec_node >= 0);
-			if (n_leaf < RT_LEAF_DEFER && moved != 0u) leaf_step = false;
+			if (n_leaf < leaf_batch && moved != 0u) leaf_step = false;
 			RT_PROF_LANES(5, leaf_step);
 #ifdef RT_WALK_PROFILE
 			if (lane_vote(leaf_step)) RT_PROF_COUNT(6);  // iterations with a leaf phase
