@@ -259,8 +259,16 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 	auto sample_done = [&](const double* c) {
 		const bool varies = P.rng.seeded;
 		if (varies && F.vqueue && F.n_frames > 1) {
-			// every frame of this pixel is a different path: the resample stage traces them 32 at a time
-			F.vqueue[atomicAdd(F.vqueue_count, 1u)] = RtQueueItem{((uint32_t)y << 16) | (uint32_t)x, slot};
+			// every frame of this pixel is a different path: the resample stage traces them as independent samples.
+			// This one - the first frame's - goes into the sample table right away (when the pixel falls into the
+			// table's first round), so that it is not traced a second time.
+			const unsigned qi = atomicAdd(F.vqueue_count, 1u);
+			F.vqueue[qi] = RtQueueItem{((uint32_t)y << 16) | (uint32_t)x, slot};
+			if (qi < F.sample_chunk) {
+				double* o = F.samples + (size_t)qi * F.n_frames * 3;
+				o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
+				if (F.first_ids) F.first_ids[out_index] = P.first_entity;
+			}
 			st = RT_ST_IDLE;
 			return;
 		}
@@ -410,7 +418,9 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 	const unsigned queued = *F.vqueue_count;
 	if (queued <= first) return;
 	const unsigned nf = F.n_frames;
-	const unsigned n = min(queued - first, chunk) * nf;  // samples of this round (chunk * nf < 2^32, launch_render)
+	// the first round's pixels come with their first frame's sample (the bounce stage traced it): nf - 1 jobs per pixel
+	const unsigned per_pixel = first == 0 ? nf - 1 : nf;
+	const unsigned n = min(queued - first, chunk) * per_pixel;  // samples of this round (chunk * nf < 2^32, launch_render)
 	RtCounts cnt = {0, 0, 0, 0, 0};
 	uint32_t err = 0;
 	int st = RT_ST_IDLE;
@@ -436,8 +446,9 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			exhausted = base + want >= n;
 			const unsigned j = base + (unsigned)__popc(idle & lt_mask);
 			if (st == RT_ST_IDLE && j < n) {
-				job = j;
-				const RtQueueItem it = F.vqueue[first + j / nf];
+				const unsigned pixel = j / per_pixel;
+				job = pixel * nf + (nf - per_pixel) + j % per_pixel;  // place in the sample table: [pixel][frame]
+				const RtQueueItem it = F.vqueue[first + pixel];
 				x = (int)(it.xy & 0xffffu);
 				y = (int)(it.xy >> 16);
 				slot = it.slot;
@@ -782,13 +793,13 @@ struct rt_ctx {
 	int render_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // persistent grid sizes: rt_render_kernel<false/true>, -, bounce, primary<1,2,4,8>
 	int ppl = RT_PPL;                            // sub-patches (rays per lane) of a packet: 4
 	int primary_minb = RT_A_MINB;                // tuning knob RT_B200_PRIMARY_MINB=4|5|6: resident CTAs per SM the primary stage is compiled for
-	int bounce_min_walking = 12;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
+	int bounce_min_walking = 16;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
 	size_t sample_bytes = (size_t)2048 << 20;    // bound on the resample stage's sample table (RT_B200_SAMPLE_MIB)
 	int resample_min_frames = 8;                 // tuning knob RT_B200_RESAMPLE_MIN
 	bool ordered_queue = true;                   // tuning knob RT_B200_ORDERED_QUEUE=0: packets append to the continuation queue as they finish
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
 	int bounce_minb = 8;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
-	int bounce_node_batch = 4;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
+	int bounce_node_batch = 8;                   // tuning knob RT_B200_NODE_BATCH (walk_iter)
 	int bounce_sparse = 8;                       // tuning knob RT_B200_SPARSE: below this many walking lanes a warp stops batching node / leaf steps
 };
 
@@ -973,6 +984,8 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	                            : minb == 6 ? (const void*)rt_resample_kernel<6> : (const void*)rt_resample_kernel<8>;
 	int grid_primary = 0, grid_bounce = 0, grid_ray = 0, grid_resample = 0;
 	unsigned resample_chunk = 1;
+	F.samples = nullptr;
+	F.sample_chunk = 0;
 	if (pipeline) {
 		if (rt_status st = grid_of(4, primary_kernel, RT_A_WARPS * 32, grid_primary)) return st;
 		if (rt_status st = grid_of(3, bounce_kernel, RT_WARPS_PER_CTA * 32, grid_bounce)) return st;
@@ -986,6 +999,7 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 			resample_chunk = (unsigned)std::max<size_t>(1, std::min<size_t>(cap, ctx->sample_bytes / per_pixel));
 			RT_CUDA(ctx, ctx->samples.alloc((size_t)resample_chunk * prm->n_frames * 3));
 			F.samples = ctx->samples.p;
+			F.sample_chunk = resample_chunk;
 		}
 	} else if (count) {
 		if (rt_status st = grid_of(1, (const void*)rt_render_kernel<true>, RT_WARPS_PER_CTA * 32, grid_ray)) return st;
@@ -1388,6 +1402,7 @@ rt_status rt_create(int32_t device, rt_ctx** out) {
 	if (const char* e = getenv("RT_B200_ORDERED_QUEUE")) ctx->ordered_queue = atoi(e) != 0;
 	if (const char* e = getenv("RT_B200_RESAMPLE_MIN")) ctx->resample_min_frames = std::max(2, atoi(e));
 	if (const char* e = getenv("RT_B200_SAMPLE_MIB")) ctx->sample_bytes = (size_t)std::max(1, atoi(e)) << 20;
+	if (const char* e = getenv("RT_B200_SAMPLE_KIB")) ctx->sample_bytes = (size_t)std::max(1, atoi(e)) << 10;  // (tests: several rounds on a small frame)
 	if (const char* e = getenv("RT_B200_BOUNCE_MINB")) {
 		const int v = atoi(e);
 		if (v == 4 || v == 5 || v == 6 || v == 8) ctx->bounce_minb = v;

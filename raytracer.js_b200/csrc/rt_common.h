@@ -201,6 +201,7 @@ struct RtFrame {
 	unsigned* vqueue_count;
 	unsigned* vqueue_taken;
 	double* samples;         // resample stage: [pixels of a round][n_frames][3] path colours
+	unsigned sample_chunk;   // pixels the table holds (a longer resample queue takes several rounds)
 	int search64;            // RT_PRECISION_F64: the cell-by-cell walker in float64 (walk_and_scan64), one ray per lane
 	int bounce_min_walking;  // bounce stage: leave the lock-step walk when fewer lanes than this are still walking
 	int bounce_node_batch;   // bounce stage: lanes that need a node step wait until this many do

@@ -414,6 +414,14 @@ def test_resample_stage_equals_frames_in_a_row(oracle, monkeypatch):
     np.testing.assert_array_equal(ids0, ids)
     rgbc, idsc, _, _ = gpu_render(b, W, H, n_frames=11, frames_as_calls=True)
     np.testing.assert_array_equal(rgbc, rgb)
+    # a sample table that holds 248 pixels only: the resample queue takes several rounds (the first one reuses the
+    # bounce stage's first-frame samples, the later ones trace all 11 frames)
+    monkeypatch.setenv("RT_B200_SAMPLE_KIB", "64")
+    rgbk, idsk, _, trk = gpu_render(b, W, H, n_frames=11)
+    monkeypatch.delenv("RT_B200_SAMPLE_KIB")
+    np.testing.assert_array_equal(rgbk, rgb)
+    np.testing.assert_array_equal(idsk, ids)
+    assert trk.lib.rt_launch_count(trk.ctx) > launches  # more rounds, more launches
     # a continued exposure: 3 frames, then 9 more through the resample stage == 12 frames in a row
     cam = scenes.bench_camera(W, H)
     cfg = rt.RaytracerConfig(b.refmax, b.sky, b.default_substance, 1.0)
