@@ -157,6 +157,30 @@ def test_image_textures_and_sky(oracle):
     assert_parity(rgb, ids, orgb, oids, scenes.BENCH_CAMERA_POS, ocam_for(300, 300), image_textures=True)
 
 
+def test_textures_decoded_from_files(oracle, tmp_path):
+    """the texel pool filled from image FILES (ImageTexture.from_file, the host stand-in for the
+    reference's browser-only load_image, src/texture/texture_image.ts:76-136) - a PNG with alpha, a
+    BMP flipped both ways, and a file that does not decode (the reference then shades with fallback_color, :45-47) - rendered through
+    the C ABI against the oracle."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (64, 128, 4), dtype=np.uint8)
+    Image.fromarray(a, "RGBA").save(tmp_path / "a.png")
+    bimg = rng.integers(0, 256, (96, 48, 3), dtype=np.uint8)
+    Image.fromarray(bimg, "RGB").save(tmp_path / "b.bmp")
+    (tmp_path / "broken.png").write_bytes(b"not an image")
+    texs = [rt.ImageTexture.from_file(str(tmp_path / "a.png"), rt.Color(1, 0, 1, 1)),
+            rt.ImageTexture.from_file(str(tmp_path / "b.bmp"), rt.Color(0, 1, 1, 1), horizontal_flip=True, vertical_flip=True),
+            rt.ImageTexture.from_file(str(tmp_path / "broken.png"), rt.Color(0.25, 0.5, 0.75, 1))]
+    assert texs[0].get_size() == (128, 64) and texs[1].get_size() == (48, 96) and texs[2].get_size() is None
+    b = scenes.random_spheres(2500, 0.02, 0.08, seed=11.0, mix="mirrors", textures=texs)
+    b.sky = rt.SkySphere(texs[0])
+    rgb, ids, cnt, tr = gpu_render(b, 256, 256, n_frames=2)
+    orgb, oids, _, tot = oracle_for(tr, b, 256, 256, n_frames=2)
+    assert_parity(rgb, ids, orgb, oids, scenes.BENCH_CAMERA_POS, ocam_for(256, 256), image_textures=True)
+    assert (oids >= 0).mean() > 0.2
+
+
 @pytest.mark.parametrize("pos,yaw,pitch", [
     (scenes.BENCH_CAMERA_POS, 0.0, 0.0),      # axis-aligned: a pixel row and a column with exactly-zero components
     ((0.5, 0.5, 0.5), 45.0, 0.3),             # on the root's centre planes (the demo pose, src/main.ts:364)
