@@ -664,6 +664,7 @@ template <class T>
 struct DevBuf {
 	T* p = nullptr;
 	size_t n = 0;
+	bool owned = true;  // false: a slice of a pool (adopt), freed with the pool
 	cudaError_t alloc(size_t count) {
 		if (count <= n && p) return cudaSuccess;
 		release();
@@ -672,10 +673,17 @@ struct DevBuf {
 		else p = nullptr;
 		return e;
 	}
+	void adopt(void* slice, size_t count) {
+		release();
+		p = static_cast<T*>(slice);
+		n = count;
+		owned = false;
+	}
 	void release() {
-		if (p) cudaFree(p);
+		if (p && owned) cudaFree(p);
 		p = nullptr;
 		n = 0;
+		owned = true;
 	}
 };
 
@@ -729,6 +737,7 @@ struct rt_ctx {
 	// packed host copy (also serves the once-per-frame start state); the members of a multi-GPU group share one
 	std::shared_ptr<RtHostScene> host_p = std::make_shared<RtHostScene>();
 	RtSceneCopy scene_copy;  // the uploaded description, kept for rt_scene_update
+	DevBuf<unsigned char> scene_pool;            // ONE allocation behind all the scene arrays (17 cudaMallocs of a 1 M-entity scene: 77 ms)
 	RtHostScene& host_ref() { return *host_p; }
 	// ---- multi-GPU group (rt_create_multi): ONE process drives every GPU.  The ctx handed to the caller is the
 	// leader (group[0] == this); members[1..] own a device, a stream and a worker thread that enqueues their share
@@ -1603,7 +1612,7 @@ void rt_destroy(rt_ctx* ctx) {
 	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->ray_ck.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
-	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->queue_dense.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->peer_flags.release();
+	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->queue_dense.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->scene_pool.release(); ctx->peer_flags.release();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	for (int b = 0; b < RT_MAX_BANDS; b++)
@@ -1707,6 +1716,28 @@ rt_status rt_host_unregister(rt_ctx* ctx, void* ptr) {
 	X(node_geom) X(node_geom64) X(node_link) X(node_child) X(node_pk) X(node_walk) X(node_bvh) X(bvh_nodes) X(bvh_slots) X(bvh_geom) \
 	X(slot_geom) X(slot_geom64) X(slot_attr) X(materials) X(textures) X(substances) X(texels)
 
+// All scene arrays of a ctx as slices of one pool allocation (grow-only: a re-upload of a scene that fits allocates
+// nothing), each aligned to 256 bytes.
+static cudaError_t alloc_scene_arrays(rt_ctx* m, const RtHostScene& H) {
+	size_t total = 0;
+#define X(name) total += (std::max<size_t>(H.name.size(), 1) * sizeof(H.name[0]) + 255) & ~(size_t)255;
+	RT_SCENE_ARRAYS(X)
+#undef X
+	if (total > m->scene_pool.n || !m->scene_pool.p) {
+#define X(name) m->name.release();
+		RT_SCENE_ARRAYS(X)
+#undef X
+		if (cudaError_t e = m->scene_pool.alloc(total + total / 8)) return e;  // (headroom: a dynamic scene grows by a few nodes per update)
+	}
+	size_t off = 0;
+#define X(name)                                                                        \
+	m->name.adopt(m->scene_pool.p + off, H.name.size());                               \
+	off += (std::max<size_t>(H.name.size(), 1) * sizeof(H.name[0]) + 255) & ~(size_t)255;
+	RT_SCENE_ARRAYS(X)
+#undef X
+	return cudaSuccess;
+}
+
 static void set_dev_scene(rt_ctx* ctx) {
 	const RtHostScene& H = ctx->host_ref();
 	RtDevScene& D = ctx->dev;
@@ -1726,9 +1757,21 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	if (ctx->leader) return fail(ctx, RT_ERR_INVALID, "rt_scene_upload: this ctx is a member of a multi-GPU group; upload through its leader");
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
 	std::string err;
+	RtPackClock clk;  // (RT_B200_PACK_TIMING=1: the stages of the upload on stderr)
 	auto hs = std::make_shared<RtHostScene>();
-	if (rt_status st = rt_pack_scene(sc, *hs, err)) return fail(ctx, st, err);  // validated and packed ONCE, on the host
-	if (sc->node_size != ctx->scene_copy.node_size.data()) ctx->scene_copy.assign(*sc);  // (not when rt_scene_update hands its own copy back)
+	// the library's own copy of the description (what rt_scene_update edits) is taken beside the packing, on a thread
+	// of its own - the caller's arrays are only borrowed for the duration of this call - and kept only if the scene
+	// is accepted (not when rt_scene_update hands its own copy back)
+	const bool take_copy = sc && sc->struct_size == sizeof(rt_scene_desc) && sc->n_nodes > 0 && sc->node_size &&
+	                       sc->node_size != ctx->scene_copy.node_size.data();
+	RtSceneCopy fresh;
+	std::thread copier;
+	if (take_copy) copier = std::thread([&] { fresh.assign(*sc); });
+	const rt_status pack_st = rt_pack_scene(sc, *hs, err);  // validated and packed ONCE, on the host
+	if (copier.joinable()) copier.join();
+	if (pack_st) return fail(ctx, pack_st, err);
+	if (take_copy) ctx->scene_copy = std::move(fresh);
+	clk.mark("= pack + description copy");
 	std::vector<rt_ctx*> all = ctx->group.empty() ? std::vector<rt_ctx*>{ctx} : ctx->group;
 	for (rt_ctx* m : all) {
 		m->has_scene = false;
@@ -1738,19 +1781,22 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	}
 	const RtHostScene& H = *hs;
 	rt_status st = RT_OK;
+	RT_CUDA(ctx, alloc_scene_arrays(ctx, H));
+	clk.mark("device alloc");
 #define X(name) if (!st) st = upload(ctx, ctx->name, H.name);
 	RT_SCENE_ARRAYS(X)
 #undef X
 	if (st) return st;
 	RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	clk.mark("H2D");
 	set_dev_scene(ctx);
 	ctx->has_scene = true;
 	// the other GPUs of a group get their replica device to device (NVLink / NVSwitch), not from the host again
 	for (size_t r = 1; r < all.size(); r++) {
 		rt_ctx* m = all[r];
 		RT_CUDA(ctx, cudaSetDevice(m->device));
+		RT_CUDA(ctx, alloc_scene_arrays(m, H));
 #define X(name)                                                                                                         \
-		RT_CUDA(ctx, m->name.alloc(H.name.size()));                                                                         \
 		if (!H.name.empty())                                                                                                \
 			RT_CUDA(ctx, cudaMemcpyPeerAsync(m->name.p, m->device, ctx->name.p, ctx->device, H.name.size() * sizeof(H.name[0]), m->stream));
 		RT_SCENE_ARRAYS(X)
@@ -1760,6 +1806,7 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 		m->has_scene = true;
 	}
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (all.size() > 1) clk.mark("replication");
 	return RT_OK;
 }
 
