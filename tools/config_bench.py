@@ -73,11 +73,19 @@ def main():
                 ms.append(el.value)
         ms.sort()
         med = ms[len(ms) // 2]
+        # live duration of every stage of one more frame (CUDA events between the kernels)
+        N.check(ctx, lib.rt_set_profiling(ctx, 1))
+        cd_moved = rt.camera_desc(scenes.bench_camera(W, H, yaw_deg=30.01))  # (a repeated identical call would replay a graph: no stage events)
+        N.check(ctx, lib.rt_render_device(ctx, C.byref(cd_moved), C.byref(prm), 0, C.c_void_p(frame.data_ptr()), None))
+        st = (C.c_float * 5)()
+        N.check(ctx, lib.rt_stage_times(ctx, st))
+        N.check(ctx, lib.rt_set_profiling(ctx, 0))
+        stages = dict(zip(("setup", "primary", "queue", "bounce", "resample"), [round(float(v), 4) for v in st]))
         seg_per_path = c1["segments"] / c1["paths"]
         paths = W * H * cfg["spp"]
         algo = 64 * c1["nodes"] + 16 * c1["tests"] + 16 * c1["shades"] + 12 * c1["paths"]
         print(json.dumps({"config": name, "frame": f"{W}x{H}x{cfg['spp']}spp", "entities": cfg["n"], "nodes": int(d.n_nodes),
-                          "frame_ms": med, "Mpaths_per_s": paths / med / 1e3, "Mrays_per_s": paths * seg_per_path / med / 1e3,
+                          "frame_ms": med, "stage_ms": stages, "Mpaths_per_s": paths / med / 1e3, "Mrays_per_s": paths * seg_per_path / med / 1e3,
                           "segments_per_path": seg_per_path, "nodes_per_segment": c1["nodes"] / c1["segments"],
                           "tests_per_segment": c1["tests"] / c1["segments"], "algorithmic_bytes_per_segment": algo / c1["segments"],
                           "algorithmic_GBps": algo / c1["paths"] * paths / med / 1e6, "path": "per-ray" if args.per_ray else "pipeline",
