@@ -153,8 +153,8 @@ def source_fingerprint() -> str:
 
 
 def committed_profile(stage: str):
-    """The newest profiles/*_summary.json that holds `stage` ("primary", "c2_bounce", ...), with a flag telling
-    whether it was captured from the sources this run was built from."""
+    """The profiles/*_summary.json that holds `stage` ("primary", "c2_bounce", ...) and was captured from the sources
+    this run was built from; failing that the last one by name, flagged stale."""
     pdir = os.path.join(ROOT, "profiles")
     best = None
     for f in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
@@ -164,12 +164,96 @@ def committed_profile(stage: str):
             d = json.load(open(os.path.join(pdir, f)))
         except Exception:
             continue
-        if stage in d:
-            best = (f, d)
+        if stage in d and (best is None or best[1].get("fingerprint") != source_fingerprint()):
+            best = (f, d)  # the capture of THESE sources when there is one, else the last by name
     if not best:
         return None
     f, d = best
     return {"file": f"profiles/{f}", "stale": d.get("fingerprint") != source_fingerprint(), "data": d[stage]}
+
+
+def configs2_record(lib, with_parity: bool):
+    """configs[2] (1920x1080, 100 k spheres, 70 % mirrors / 15 % diffuse / 10 % rough / 5 % lights, refmax 4) on one
+    GPU: what the bounce and resample stages do.  Frame and per-stage times at 1 and 16 spp, the committed ncu figures
+    of the bounce kernel when they were captured from these sources, and (with the cpu baseline leg) the parity of a
+    256 x 128 crop of the 16-spp frame against the oracle."""
+    import numpy as np
+    import torch
+    import raytracer_js_b200 as rt
+    from raytracer_js_b200 import _native as N
+    from raytracer_js_b200 import scenes
+    cfg = scenes.BASELINE_CONFIGS["c2"]
+    fb = scenes.build_config(cfg)
+    W, H = cfg["w"], cfg["h"]
+    ctx = C.c_void_p()
+    N.check(None, lib.rt_create(0, C.byref(ctx)))
+    out = {"workload": "configs[2]: 1920x1080, 100 k spheres d in [0.002,0.006], mirrors / diffuse / rough / lights 70/15/10/5 %, refmax 4"}
+    try:
+        d = fb.flat.desc()
+        N.check(ctx, lib.rt_scene_upload(ctx, C.byref(d)))
+        prm = N.Params()
+        prm.refmax, prm.sky_texture, prm.default_substance = fb.refmax, fb.sky_texture, fb.default_substance
+        prm.distance_attenuation_factor, prm.n_frames, prm.frame_first, prm.rng_seed = 1.0, 1, 0, 1.0
+        frame = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda:0")
+        cams = [rt.camera_desc(scenes.bench_camera(W, H, yaw_deg=30.0 + 0.001 * i)) for i in range(6)]
+        N.check(ctx, lib.rt_render_device(ctx, C.byref(cams[0]), C.byref(prm), N.RT_RENDER_COUNTERS, C.c_void_p(frame.data_ptr()), None))
+        cnt = N.Counters()
+        N.check(ctx, lib.rt_get_counters(ctx, C.byref(cnt)))
+        seg_per_path = cnt.segments / max(cnt.paths, 1)
+        el = C.c_float()
+        N.check(ctx, lib.rt_set_profiling(ctx, 1))
+        for spp in (1, cfg["spp"]):
+            prm.n_frames = spp
+            ms, stages = [], None
+            for i in range(6):  # the camera moves every frame: no graph replay
+                N.check(ctx, lib.rt_flush_l2(ctx))
+                N.check(ctx, lib.rt_timer_start(ctx))
+                N.check(ctx, lib.rt_render_device(ctx, C.byref(cams[i]), C.byref(prm), 0, C.c_void_p(frame.data_ptr()), None))
+                N.check(ctx, lib.rt_timer_stop(ctx, C.byref(el)))
+                if i:
+                    ms.append(el.value)
+            st = (C.c_float * 5)()
+            N.check(ctx, lib.rt_stage_times(ctx, st))
+            stages = dict(zip(("setup", "primary", "queue", "bounce", "resample"), [round(float(v), 4) for v in st]))
+            ms.sort()
+            med = ms[len(ms) // 2]
+            out[f"spp{spp}"] = {"frame_ms": med, "Mrays_per_s": W * H * spp * seg_per_path / med / 1e3,
+                                "Mpaths_per_s": W * H * spp / med / 1e3, "stage_ms_live": stages}
+        out["segments_per_path"] = seg_per_path
+        N.check(ctx, lib.rt_set_profiling(ctx, 0))
+        prof = committed_profile("c2_bounce")
+        if prof and not prof["stale"]:
+            pk = prof["data"]
+            out["bounce_kernel_ncu"] = {"file": prof["file"], "kernel_ms_under_ncu": pk["gpu__time_duration.sum"],
+                                        "issue_slot_utilisation_pct": pk["smsp__issue_active.avg.pct_of_peak_sustained_active"],
+                                        "active_lanes_per_instruction": pk["smsp__thread_inst_executed_per_inst_executed.ratio"],
+                                        "issue_x_lanes": pk["smsp__issue_active.avg.pct_of_peak_sustained_active"] / 100
+                                                         * pk["smsp__thread_inst_executed_per_inst_executed.ratio"] / 32,
+                                        "registers_per_thread": pk["launch__registers_per_thread"],
+                                        "dram_bytes": pk["dram__bytes_read.sum"] + pk["dram__bytes_write.sum"]}
+        else:
+            out["bounce_kernel_ncu"] = {"stale_profile": (prof or {}).get("file", "no committed capture")}
+        if with_parity:  # the oracle on a crop of the 16-spp frame (same camera, same per-pixel seeds)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from util import classify_outliers, compare, oracle_crop, oracle_scene_flat
+            prm.n_frames = cfg["spp"]
+            host = np.zeros((H, W, 3), np.float32)
+            ids = np.zeros((H, W), np.int32)
+            cam0 = rt.camera_desc(scenes.bench_camera(W, H))
+            N.check(ctx, lib.rt_render(ctx, C.byref(cam0), C.byref(prm), 0, host.ctypes.data, ids.ctypes.data, None))
+            crop = (1000, 500, 256, 128)
+            x, y, w, h = crop
+            orgb, oids, _ = oracle_crop(oracle_scene_flat(fb), fb, W, H, crop, cfg["spp"])
+            par = compare(host[y:y + h, x:x + w], ids[y:y + h, x:x + w], orgb, oids)
+            kinds = classify_outliers(host[y:y + h, x:x + w], ids[y:y + h, x:x + w], orgb, oids, cam_pos=scenes.BENCH_CAMERA_POS,
+                                      ocam=None, image_textures=False, offset=(x, y))
+            par.update({"crop": list(crop), "spp": cfg["spp"], "hit_fraction": float((oids >= 0).mean()),
+                        "unexplained_outliers": len(kinds["unexplained"]),
+                        "pass": bool(par["id_match"] >= 0.9999 and par["rgb_bad"] == 0 and not kinds["unexplained"])})
+            out["parity"] = par
+    finally:
+        lib.rt_destroy(ctx)
+    return out
 
 
 def group_records(args, lib, n_gpus, flat, sky_tex, def_sub, cds, warm):
@@ -602,11 +686,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             store = dist.distributed_c10d._get_default_store()
         except Exception:
             store = None
+    configs2 = None
     if rank == 0 and not args.no_group:
         try:
             group = group_records(args, lib, world, flat, sky_tex, def_sub, cds, warm)
         except Exception as e:  # reported, never fatal for the contract line
             group = {"error": repr(e)[:300]}
+        if world == 1:
+            try:
+                configs2 = configs2_record(lib, with_parity=not args.no_cpu_baseline)
+            except Exception as e:
+                configs2 = {"error": repr(e)[:300]}
     if world > 1:
         if store is not None:
             if rank == 0:
@@ -672,7 +762,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "precision": "float32 search + float64 confirmation/shading of the found hit",
                    "path": args.path},
         "clocks": clocks, "e2e": e2e, "present": present, "gpu_launches": launches, "roofline": roof,
-        "single_process_group": group,
+        "single_process_group": group, "configs2": configs2,
     }
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -704,7 +794,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-group", action="store_true", help="skip the rt_create_multi records (single_process_group)")
+    ap.add_argument("--no-group", action="store_true", help="skip the extra records (single_process_group, configs2)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = kernels store into rank 0's frame over NVLink (CUDA IPC); nccl = all-gather + untile")
     ap.add_argument("--path", default="pipeline", choices=["pipeline", "per-ray"],
