@@ -1359,6 +1359,21 @@ rt_status read_counters_any(rt_ctx* ctx, rt_counters* out) {
 }  // namespace
 
 // ================================================================== C ABI
+// No C++ exception crosses the C ABI: the entry points that build large host structures (a 1 M-entity scene is a few
+// hundred MB of vectors, on several threads) turn an allocation failure into a status and a message.
+template <class F>
+static rt_status abi_guard(rt_ctx* ctx, const char* what, F&& body) {
+	try {
+		return body();
+	} catch (const std::bad_alloc&) {
+		return fail(ctx, RT_ERR_INVALID, rt_format("%s: out of host memory", what));
+	} catch (const std::exception& e) {
+		return fail(ctx, RT_ERR_INVALID, rt_format("%s: %s", what, e.what()));
+	} catch (...) {
+		return fail(ctx, RT_ERR_INVALID, rt_format("%s: unknown failure", what));
+	}
+}
+
 extern "C" {
 
 uint32_t rt_abi_version(void) { return RT_B200_ABI_VERSION; }
@@ -1752,8 +1767,14 @@ static void set_dev_scene(rt_ctx* ctx) {
 	D.ordered_ok = rt_ordered_walk_fits(H);
 }
 
+static rt_status scene_upload_impl(rt_ctx* ctx, const rt_scene_desc* sc);
+
 rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	if (!ctx) return RT_ERR_INVALID;
+	return abi_guard(ctx, "rt_scene_upload", [&] { return scene_upload_impl(ctx, sc); });
+}
+
+static rt_status scene_upload_impl(rt_ctx* ctx, const rt_scene_desc* sc) {
 	if (ctx->leader) return fail(ctx, RT_ERR_INVALID, "rt_scene_upload: this ctx is a member of a multi-GPU group; upload through its leader");
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
 	std::string err;
@@ -1766,9 +1787,24 @@ rt_status rt_scene_upload(rt_ctx* ctx, const rt_scene_desc* sc) {
 	                       sc->node_size != ctx->scene_copy.node_size.data();
 	RtSceneCopy fresh;
 	std::thread copier;
-	if (take_copy) copier = std::thread([&] { fresh.assign(*sc); });
-	const rt_status pack_st = rt_pack_scene(sc, *hs, err);  // validated and packed ONCE, on the host
+	std::exception_ptr copy_thrown, pack_thrown;
+	if (take_copy)
+		copier = std::thread([&] {
+			try {
+				fresh.assign(*sc);
+			} catch (...) {
+				copy_thrown = std::current_exception();
+			}
+		});
+	rt_status pack_st = RT_OK;
+	try {
+		pack_st = rt_pack_scene(sc, *hs, err);  // validated and packed ONCE, on the host
+	} catch (...) {
+		pack_thrown = std::current_exception();
+	}
 	if (copier.joinable()) copier.join();
+	if (pack_thrown) std::rethrow_exception(pack_thrown);  // (caught at the ABI: abi_guard)
+	if (copy_thrown) std::rethrow_exception(copy_thrown);
 	if (pack_st) return fail(ctx, pack_st, err);
 	if (take_copy) ctx->scene_copy = std::move(fresh);
 	clk.mark("= pack + description copy");
@@ -1816,11 +1852,13 @@ rt_status rt_scene_update(rt_ctx* ctx, uint32_t n_moved, const uint32_t* entity_
 	if (!ctx->has_scene || !ctx->scene_copy.valid) return fail(ctx, RT_ERR_NO_SCENE, "rt_scene_update: no scene uploaded");
 	if (n_moved && (!entity_ids || !new_pos)) return fail(ctx, RT_ERR_INVALID, "rt_scene_update: NULL argument");
 	if (n_moved == 0) return RT_OK;
-	std::string err;
-	if (!rt_scene_move_entities(ctx->scene_copy, n_moved, entity_ids, new_pos, max_in_depth, err))
-		return fail(ctx, err.find("outside-depth") != std::string::npos ? RT_ERR_UNSUPPORTED : RT_ERR_INVALID, err);
-	const rt_scene_desc d = ctx->scene_copy.desc();
-	return rt_scene_upload(ctx, &d);
+	return abi_guard(ctx, "rt_scene_update", [&]() -> rt_status {
+		std::string err;
+		if (!rt_scene_move_entities(ctx->scene_copy, n_moved, entity_ids, new_pos, max_in_depth, err))
+			return fail(ctx, err.find("outside-depth") != std::string::npos ? RT_ERR_UNSUPPORTED : RT_ERR_INVALID, err);
+		const rt_scene_desc d = ctx->scene_copy.desc();
+		return scene_upload_impl(ctx, &d);
+	});
 }
 
 rt_status rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, uint32_t flags, float* rgb_dev,
@@ -1956,14 +1994,13 @@ rt_status rt_tree_build(const double root_pos[3], double root_size, uint32_t n, 
 	*out = nullptr;
 	if (!root_pos || !(root_size > 0) || (n && (!type || !pos || !extent)))
 		return fail(nullptr, RT_ERR_INVALID, "rt_tree_build: bad arguments");
-	rt_tree* t = new rt_tree();
-	std::string err;
-	if (!rt_tree_build_impl(*t, root_pos, root_size, n, type, pos, extent, max_in_depth, err)) {
-		delete t;
-		return fail(nullptr, RT_ERR_UNSUPPORTED, err);
-	}
-	*out = t;
-	return RT_OK;
+	return abi_guard(nullptr, "rt_tree_build", [&]() -> rt_status {
+		std::unique_ptr<rt_tree> t(new rt_tree());
+		std::string err;
+		if (!rt_tree_build_impl(*t, root_pos, root_size, n, type, pos, extent, max_in_depth, err)) return fail(nullptr, RT_ERR_UNSUPPORTED, err);
+		*out = t.release();
+		return RT_OK;
+	});
 }
 
 rt_status rt_tree_build_gpu(rt_ctx* ctx, const double root_pos[3], double root_size, uint32_t n, const uint8_t* type,
@@ -1978,15 +2015,14 @@ rt_status rt_tree_build_gpu(rt_ctx* ctx, const double root_pos[3], double root_s
 	if ((uint64_t)n * (max_in_depth + 1) + 1 > 0x7fffffffull)
 		return fail(ctx, RT_ERR_UNSUPPORTED, "rt_tree_build_gpu: too many entities for one sort");
 	RT_CUDA(ctx, cudaSetDevice(ctx->device));
-	rt_tree* t = new rt_tree();
-	std::string err;
-	const int rc = rt_gpu_build::build(*t, ctx->stream, root_pos, root_size, n, type, pos, extent, max_in_depth, err, &ctx->launches);
-	if (rc != 0) {
-		delete t;
-		return fail(ctx, rc == 1 ? RT_ERR_UNSUPPORTED : RT_ERR_CUDA, err);
-	}
-	*out = t;
-	return RT_OK;
+	return abi_guard(ctx, "rt_tree_build_gpu", [&]() -> rt_status {
+		std::unique_ptr<rt_tree> t(new rt_tree());
+		std::string err;
+		const int rc = rt_gpu_build::build(*t, ctx->stream, root_pos, root_size, n, type, pos, extent, max_in_depth, err, &ctx->launches);
+		if (rc != 0) return fail(ctx, rc == 1 ? RT_ERR_UNSUPPORTED : RT_ERR_CUDA, err);
+		*out = t.release();
+		return RT_OK;
+	});
 }
 
 uint32_t rt_tree_node_count(const rt_tree* t) { return t ? (uint32_t)t->size.size() : 0; }

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <exception>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -66,17 +67,26 @@ inline void rt_parallel_blocks(size_t n, size_t grain, size_t work, F&& fn) {
 		return;
 	}
 	std::atomic<size_t> next{0};
+	std::exception_ptr thrown;  // (an allocation failure inside a block: re-thrown on the calling thread, after the join)
+	std::mutex thrown_mu;
 	auto run = [&] {
-		for (;;) {
-			const size_t b = next.fetch_add(grain);
-			if (b >= n) return;
-			fn(b, std::min(n, b + grain));
+		try {
+			for (;;) {
+				const size_t b = next.fetch_add(grain);
+				if (b >= n) return;
+				fn(b, std::min(n, b + grain));
+			}
+		} catch (...) {
+			next.store(n);  // the other threads stop at their next block
+			std::lock_guard<std::mutex> g(thrown_mu);
+			if (!thrown) thrown = std::current_exception();
 		}
 	};
 	std::vector<std::thread> pool;
 	for (unsigned t = 1; t < T; t++) pool.emplace_back(run);
 	run();
 	for (std::thread& t : pool) t.join();
+	if (thrown) std::rethrow_exception(thrown);
 }
 
 // The error a single thread walking the indices in order would have met first: blocks report (key, status,
