@@ -110,6 +110,30 @@ export function flatten(root: EntityOtree, extra_textures: any[], extra_substanc
 	return { flat: f, tex, sub };
 }
 
+/** `new ImageTexture(url, fallback, hflip, vflip)` for a host without a DOM (SURVEY.md 8f N3).  The reference's
+ *  constructor decodes through `new Image()` + a canvas (src/texture/texture_image.ts:76-136) and cannot run under
+ *  Node; this builds the same object - same prototype, same fields, so `get_color` and the flattener above see no
+ *  difference - from the library's decoder (native.decodeImage: PNG, BMP, binary PPM; RGB kept, alpha dropped), with
+ *  the flips done by the reference's own index walk.  A file that does not decode leaves `image_data` undefined: the
+ *  texture answers its fallback colour, as while the reference's loading promise is pending or rejected. */
+export function image_texture_from_file(path: string, fallback_color: any, hflip = false, vflip = false): ImageTexture {
+	const t: any = Object.create(ImageTexture.prototype);
+	t.image_url = path; t.image_data = undefined; t.fallback_color = fallback_color; t.loading_promise = Promise.resolve();
+	try {
+		const { width, height, rgb } = native.decodeImage(new Uint8Array(require('fs').readFileSync(path)));
+		const data: number[] = Array(width * height * 3);
+		let j = 0;
+		for (let y = vflip ? height - 1 : 0; y !== (vflip ? -1 : height); y += vflip ? -1 : 1)
+			for (let x = hflip ? width - 1 : 0; x !== (hflip ? -1 : width); x += hflip ? -1 : 1) {
+				const k = (y * width + x) * 3;
+				data[j] = rgb[k] / 255.0; data[j + 1] = rgb[k + 1] / 255.0; data[j + 2] = rgb[k + 2] / 255.0;
+				j += 3;
+			}
+		t.image_data = data; t.width = width; t.height = height;
+	} catch (e) { /* not decodable: fallback colour */ }
+	return t as ImageTexture;
+}
+
 export class GpuRaytracer {
 	private otree: EntityOtree;
 	private camera: Camera;

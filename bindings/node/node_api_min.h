@@ -35,6 +35,9 @@ napi_status napi_is_typedarray(napi_env, napi_value, bool* result);
 napi_status napi_create_external(napi_env, void* data, napi_finalize finalize_cb, void* hint, napi_value* result);
 napi_status napi_get_value_external(napi_env, napi_value, void** result);
 napi_status napi_create_object(napi_env, napi_value* result);
+napi_status napi_create_arraybuffer(napi_env, size_t byte_length, void** data, napi_value* result);
+napi_status napi_create_typedarray(napi_env, napi_typedarray_type type, size_t length, napi_value arraybuffer, size_t byte_offset,
+                                   napi_value* result);
 napi_status napi_create_double(napi_env, double, napi_value* result);
 napi_status napi_set_named_property(napi_env, napi_value object, const char* name, napi_value value);
 napi_status napi_get_undefined(napi_env, napi_value* result);

@@ -288,6 +288,39 @@ static napi_value PinOrUnpin(napi_env env, napi_callback_info info, int pin) {
 static napi_value Pin(napi_env env, napi_callback_info info) { return PinOrUnpin(env, info, 1); }
 static napi_value Unpin(napi_env env, napi_callback_info info) { return PinOrUnpin(env, info, 0); }
 
+/* decodeImage(bytes: Uint8Array) -> { width, height, rgb: Uint8Array }: ImageTexture's decode step for a host without
+ * a DOM (src/texture/texture_image.ts:76-136 draws the file into a canvas): rt_image_decode, PNG / BMP / binary PPM ->
+ * RGB8 rows top to bottom, alpha dropped.  Throws for anything else; the adapter then keeps the fallback colour. */
+static napi_value DecodeImage(napi_env env, napi_callback_info info) {
+	size_t argc = 1, n = 0;
+	napi_value argv[1], out = NULL, ab = NULL, arr = NULL, v;
+	napi_typedarray_type t;
+	void *bytes = NULL, *dst = NULL;
+	uint32_t w = 0, h = 0;
+	uint8_t* rgb = NULL;
+	RT_NAPI_TRY(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	RT_NAPI_TRY(env, napi_get_typedarray_info(env, argv[0], &t, &n, &bytes, NULL, NULL));
+	if (t != napi_uint8_array) {
+		napi_throw_error(env, "ERR_INVALID_ARG_TYPE", "rt_b200: decodeImage takes a Uint8Array");
+		return NULL;
+	}
+	rt_status st = rt_image_decode((const uint8_t*)bytes, (uint64_t)n, &w, &h, &rgb);
+	if (st != RT_OK) return throw_rt(env, NULL, st);
+	if (napi_create_arraybuffer(env, (size_t)w * h * 3, &dst, &ab) != napi_ok ||
+	    napi_create_typedarray(env, napi_uint8_array, (size_t)w * h * 3, ab, 0, &arr) != napi_ok) {
+		rt_image_free(rgb);
+		napi_throw_error(env, NULL, "rt_b200: decodeImage: cannot allocate the texel array");
+		return NULL;
+	}
+	memcpy(dst, rgb, (size_t)w * h * 3);
+	rt_image_free(rgb);
+	RT_NAPI_TRY(env, napi_create_object(env, &out));
+	napi_create_double(env, (double)w, &v); napi_set_named_property(env, out, "width", v);
+	napi_create_double(env, (double)h, &v); napi_set_named_property(env, out, "height", v);
+	napi_set_named_property(env, out, "rgb", arr);
+	return out;
+}
+
 napi_value napi_register_module_v1(napi_env env, napi_value exports) {
 	const napi_property_descriptor props[] = {
 	    {"create", NULL, Create, NULL, NULL, NULL, napi_default, NULL},
@@ -297,6 +330,7 @@ napi_value napi_register_module_v1(napi_env env, napi_value exports) {
 	    {"present", NULL, Present, NULL, NULL, NULL, napi_default, NULL},
 	    {"pin", NULL, Pin, NULL, NULL, NULL, napi_default, NULL},
 	    {"unpin", NULL, Unpin, NULL, NULL, NULL, napi_default, NULL},
+	    {"decodeImage", NULL, DecodeImage, NULL, NULL, NULL, napi_default, NULL},
 	};
 	napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
 	return exports;

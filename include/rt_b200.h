@@ -315,6 +315,16 @@ rt_status rt_peer_close(rt_ctx* ctx, void* dev_ptr);
  * visible to whatever is enqueued after it on every rank. */
 rt_status rt_peer_barrier(rt_ctx* ctx, uint32_t rank, uint32_t world, uint32_t* const* flags, uint32_t epoch);
 
+/* ---- host-side helpers (no GPU work): texture ingest ---------------------------------------------- */
+/* ImageTexture's decode step (src/texture/texture_image.ts:76-136) for hosts without a DOM: the reference draws the
+ * file into a canvas and keeps the RGB bytes of getImageData (alpha dropped); here the bytes of a PNG (8 bits per
+ * channel, non-interlaced: grey, grey + alpha, RGB, RGBA, palette), an uncompressed 24 / 32-bit BMP or a binary PPM
+ * (P6) are decoded into RGB8, rows top to bottom - the layout of rt_scene_desc.texels.  *rgb is malloc'ed, release it
+ * with rt_image_free.  RT_ERR_UNSUPPORTED for anything else (the caller then uses the texture's fallback colour, as
+ * the reference does while an image is not loaded, :45-47); the message is rt_last_error(NULL). */
+rt_status rt_image_decode(const uint8_t* bytes, uint64_t n_bytes, uint32_t* width, uint32_t* height, uint8_t** rgb);
+void rt_image_free(uint8_t* rgb);
+
 /* ---- host-side helpers (no GPU work): bulk scene construction ------------------------------------ */
 /* Bulk restatement of add_entity_to_octree (src/octree_entity.ts:174-188) with max_out_depth = 0: inserts
  * the entities in index order into an empty octree rooted at (root_pos, root_size) and keeps the result in

@@ -115,6 +115,8 @@ EXPORTS = {
     "rt_tree_build_gpu": (C.c_int, [C.c_void_p, _dp, C.c_double, C.c_uint32, _bp, _dp, _dp, C.c_uint32, C.POINTER(C.c_void_p)]),
     "rt_tree_node_count": (C.c_uint32, [C.c_void_p]),
     "rt_tree_export": (None, [C.c_void_p, _dp, _dp, _ip, _ip, _ip, _up, _up]),
+    "rt_image_decode": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.POINTER(C.c_uint8))]),
+    "rt_image_free": (None, [C.POINTER(C.c_uint8)]),
     "rt_tree_free": (None, [C.c_void_p]),
     "rt_fplcg_fill": (None, [C.c_double, C.c_uint64, _dp]),
     "rt_flush_l2": (C.c_int, [C.c_void_p]),

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librt_b200.so")
 SOURCES = ["rt_b200.cu"]
-HEADERS = ["rt_common.h", "rt_host.h", "rt_build.h", "rt_build_gpu.cuh", "rt_trace.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
+HEADERS = ["rt_common.h", "rt_host.h", "rt_image.h", "rt_build.h", "rt_build_gpu.cuh", "rt_trace.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -41,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc_path(), *NVCC_FLAGS]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]  # zlib: the PNG inflate of rt_image.h
     subprocess.check_call(cmd)
     return LIB
 

@@ -13,6 +13,7 @@
 #include "rt_build.h"
 #include "rt_build_gpu.cuh"
 #include "rt_host.h"
+#include "rt_image.h"
 #include "rt_trace.cuh"
 
 // ================================================================== kernels
@@ -1987,6 +1988,27 @@ rt_status rt_peer_barrier(rt_ctx* ctx, uint32_t rank, uint32_t world, uint32_t* 
 	RT_CUDA(ctx, cudaGetLastError());
 	return RT_OK;
 }
+
+rt_status rt_image_decode(const uint8_t* bytes, uint64_t n_bytes, uint32_t* width, uint32_t* height, uint8_t** rgb) {
+	if (!bytes || !width || !height || !rgb) return fail(nullptr, RT_ERR_INVALID, "rt_image_decode: NULL argument");
+	*rgb = nullptr;
+	*width = *height = 0;
+	return abi_guard(nullptr, "rt_image_decode", [&]() -> rt_status {
+		std::vector<uint8_t> px;
+		std::string err;
+		uint32_t w = 0, h = 0;
+		if (!rt_image::decode(bytes, (size_t)n_bytes, w, h, px, err)) return fail(nullptr, RT_ERR_UNSUPPORTED, err);
+		uint8_t* out = static_cast<uint8_t*>(malloc(px.size()));
+		if (!out) return fail(nullptr, RT_ERR_INVALID, "rt_image_decode: out of host memory");
+		memcpy(out, px.data(), px.size());
+		*rgb = out;
+		*width = w;
+		*height = h;
+		return RT_OK;
+	});
+}
+
+void rt_image_free(uint8_t* rgb) { free(rgb); }
 
 rt_status rt_tree_build(const double root_pos[3], double root_size, uint32_t n, const uint8_t* type, const double* pos,
                         const double* extent, uint32_t max_in_depth, rt_tree** out) {

@@ -60,10 +60,32 @@ class ImageTexture(Texture):
         channel is dropped like `image_data[index+3]` is never read), then flipped as load_image does
         (:103-113).  A file that cannot be decoded leaves the texture unloaded: lookups answer the fallback
         colour, as while the reference's loading promise is pending or rejected."""
-        try:
-            from PIL import Image
-            with Image.open(image_url) as im:
-                px = np.asarray(im.convert("RGB"), dtype=np.uint8)
-        except Exception:
-            return cls(None, fallback_color)
+        px = cls._decode_native(image_url)
+        if px is None:  # a format the library's decoder does not read (JPEG ...): Pillow, where it is installed
+            try:
+                from PIL import Image
+                with Image.open(image_url) as im:
+                    px = np.asarray(im.convert("RGB"), dtype=np.uint8)
+            except Exception:
+                return cls(None, fallback_color)
         return cls(px, fallback_color, horizontal_flip, vertical_flip)
+
+    @staticmethod
+    def _decode_native(image_url: str):
+        """rt_image_decode (include/rt_b200.h): the library's own host decoder - PNG, BMP, binary PPM - the one the
+        N-API shim hands to the TypeScript adapter; None when the file is not one of those (or cannot be read)."""
+        import ctypes as C
+        try:
+            from . import _native as N
+            lib = N.load()
+            with open(image_url, "rb") as fh:
+                data = fh.read()
+        except Exception:
+            return None
+        w, h, rgb = C.c_uint32(), C.c_uint32(), C.POINTER(C.c_uint8)()
+        if lib.rt_image_decode(data, len(data), C.byref(w), C.byref(h), C.byref(rgb)) != N.RT_OK:
+            return None
+        try:
+            return np.ctypeslib.as_array(rgb, shape=(h.value, w.value, 3)).copy()
+        finally:
+            lib.rt_image_free(rgb)
