@@ -461,6 +461,21 @@ def test_resample_stage_equals_frames_in_a_row(oracle, monkeypatch):
     np.testing.assert_array_equal(eb.pixels, eb2.pixels)
 
 
+def test_banded_host_path_with_bouncing_paths(monkeypatch):
+    """rt_render cuts the frame into bands only while no path bounces (refmax <= 1); RT_B200_BANDS forces it: every band
+    then runs its own continuation queue, resample queue and rounds over the shared sample table - same frame."""
+    b = scenes.random_spheres(1500, 0.02, 0.07, seed=19.0, mix="mirrors", box_fraction=0.1)
+    W, H = 200, 150  # 10 tile rows: bands of 3 / 3 / 4
+    rgb, ids, _, tr = gpu_render(b, W, H, n_frames=9)
+    base = tr.lib.rt_launch_count(tr.ctx)
+    monkeypatch.setenv("RT_B200_BANDS", "3")
+    monkeypatch.setenv("RT_B200_SAMPLE_KIB", "32")
+    rgb3, ids3, _, tr3 = gpu_render(b, W, H, n_frames=9)
+    np.testing.assert_array_equal(rgb3, rgb)
+    np.testing.assert_array_equal(ids3, ids)
+    assert tr3.lib.rt_launch_count(tr3.ctx) > base
+
+
 def test_zero_copy_host_frame(oracle):
     """rt_host_map: the kernels store the pixels straight into a mapped host buffer (the delivery every rank of a
     multi-GPU render uses for its own tiles); same frame as rt_render's copy path, also through the shard entry
