@@ -828,8 +828,8 @@ rt_status fail(rt_ctx* ctx, rt_status st, const std::string& msg) {
 			return fail(ctx, RT_ERR_CUDA, rt_format("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
 	} while (0)
 
-template <class T>
-rt_status upload(rt_ctx* ctx, DevBuf<T>& buf, const std::vector<T>& host) {
+template <class T, class A>
+rt_status upload(rt_ctx* ctx, DevBuf<T>& buf, const std::vector<T, A>& host) {
 	RT_CUDA(ctx, buf.alloc(host.size()));
 	if (!host.empty())
 		RT_CUDA(ctx, cudaMemcpyAsync(buf.p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));

@@ -15,28 +15,49 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/rt_b200.h"
 #include "rt_common.h"
 
+// The packed arrays are written once, in full, by the parallel loops of rt_pack_scene: a std::vector that zero-fills
+// them first touches every page of a few hundred MB on ONE thread (half of the packing time at 1 M entities).  RtVec
+// is std::vector with default-initialisation: resize() reserves, the loops' own stores touch the pages, in parallel.
+template <class T>
+struct RtNoInit {
+	using value_type = T;
+	RtNoInit() = default;
+	template <class U> RtNoInit(const RtNoInit<U>&) {}
+	T* allocate(size_t n) { return std::allocator<T>().allocate(n); }
+	void deallocate(T* p, size_t n) { std::allocator<T>().deallocate(p, n); }
+	template <class U, class... Args>
+	void construct(U* p, Args&&... args) {
+		if constexpr (sizeof...(Args) == 0) ::new ((void*)p) U;  // default-init: nothing written for trivial types
+		else ::new ((void*)p) U(std::forward<Args>(args)...);
+	}
+	template <class U> bool operator==(const RtNoInit<U>&) const { return true; }
+	template <class U> bool operator!=(const RtNoInit<U>&) const { return false; }
+};
+template <class T> using RtVec = std::vector<T, RtNoInit<T>>;
+
 struct RtHostScene {
-	std::vector<RtF4> node_geom;
-	std::vector<RtD4> node_geom64;
-	std::vector<RtI4> node_link;
-	std::vector<int> node_child;
-	std::vector<RtPNode> node_pk;
-	std::vector<RtWNode> node_walk;
-	std::vector<int> node_bvh;
-	std::vector<RtBvhNode> bvh_nodes;
-	std::vector<int> bvh_slots;
-	std::vector<RtF4> bvh_geom;
+	RtVec<RtF4> node_geom;
+	RtVec<RtD4> node_geom64;
+	RtVec<RtI4> node_link;
+	RtVec<int> node_child;
+	RtVec<RtPNode> node_pk;
+	RtVec<RtWNode> node_walk;
+	RtVec<int> node_bvh;
+	RtVec<RtBvhNode> bvh_nodes;
+	RtVec<int> bvh_slots;
+	RtVec<RtF4> bvh_geom;
 	int max_bvh_depth = 0;  // deepest list-BVH level (root = 0)
-	std::vector<RtF4> slot_geom;
-	std::vector<RtD4> slot_geom64;
-	std::vector<RtI4> slot_attr;
+	RtVec<RtF4> slot_geom;
+	RtVec<RtD4> slot_geom64;
+	RtVec<RtI4> slot_attr;
 	std::vector<RtMaterial> materials;
-	std::vector<RtTexture> textures;
+	RtVec<RtTexture> textures;
 	std::vector<double> substances;
 	std::vector<uint8_t> texels;
 	double root_pos[3] = {0, 0, 0};
@@ -293,9 +314,17 @@ inline void rt_build_list_bvhs(RtHostScene& hs) {
 		n_bvh += (size_t)t.nodes;
 		n_leaves += (size_t)t.leaves;
 	}
-	hs.bvh_nodes.assign(std::max<size_t>(n_bvh, 1), RtBvhNode{});
-	hs.bvh_slots.assign(std::max<size_t>(n_leaves, 1) * RT_BVH_LEAF, RT_NO_SLOT);
-	hs.bvh_geom.assign(std::max<size_t>(n_leaves, 1) * RT_BVH_LEAF, RtF4{0, 0, 0, 0});
+	// (every record is written by the build below; only the place-holders of a scene without entities are filled here)
+	hs.bvh_nodes.clear(); hs.bvh_slots.clear(); hs.bvh_geom.clear();
+	if (n_bvh == 0) hs.bvh_nodes.assign(1, RtBvhNode{});
+	else hs.bvh_nodes.resize(n_bvh);
+	if (n_leaves == 0) {
+		hs.bvh_slots.assign(RT_BVH_LEAF, RT_NO_SLOT);
+		hs.bvh_geom.assign(RT_BVH_LEAF, RtF4{0, 0, 0, 0});
+	} else {
+		hs.bvh_slots.resize(n_leaves * RT_BVH_LEAF);
+		hs.bvh_geom.resize(n_leaves * RT_BVH_LEAF);
+	}
 	std::mutex mu;
 	rt_parallel_blocks(N, 256, hs.slot_geom.size(), [&](size_t n0, size_t n1) {
 		std::vector<int> idx;
