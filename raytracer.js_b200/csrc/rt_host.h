@@ -82,7 +82,7 @@ inline unsigned rt_pack_threads(size_t work) {
 
 template <class F>
 inline void rt_parallel_blocks(size_t n, size_t grain, size_t work, F&& fn) {
-	const unsigned T = rt_pack_threads(work);
+	const unsigned T = (unsigned)std::min<size_t>(rt_pack_threads(work), (n + grain - 1) / std::max<size_t>(grain, 1));
 	if (T <= 1 || n <= grain) {
 		if (n) fn((size_t)0, n);
 		return;
@@ -139,18 +139,25 @@ struct RtSceneCopy {
 	std::vector<uint64_t> tex_texel_off;
 	bool valid = false;
 
+	// (a 1 M-entity description is ~110 MB in two dozen arrays: copied by a few threads, each taking whole arrays)
 	void assign(const rt_scene_desc& d) {
 		const size_t N = d.n_nodes, L = d.n_list, E = d.n_entities, M = d.n_materials, T = d.n_textures, S = d.n_substances;
 		auto cp = [](auto& v, const auto* p, size_t n) { if (p && n) v.assign(p, p + n); else v.clear(); };
-		cp(node_pos, d.node_pos, 3 * N); cp(node_size, d.node_size, N); cp(node_child, d.node_child, 8 * N);
-		cp(node_parent, d.node_parent, N); cp(node_octant, d.node_octant, N); cp(node_list_off, d.node_list_off, N + 1);
-		cp(list_entity, d.list_entity, L);
-		cp(ent_type, d.ent_type, E); cp(ent_pos, d.ent_pos, 3 * E); cp(ent_extent, d.ent_extent, E);
-		cp(ent_material, d.ent_material, E); cp(ent_texture, d.ent_texture, E); cp(ent_substance, d.ent_substance, E);
-		cp(mat_response, d.mat_response, M); cp(mat_light, d.mat_light, M); cp(mat_mirror, d.mat_mirror, M); cp(mat_roughness, d.mat_roughness, M);
-		cp(tex_kind, d.tex_kind, T); cp(tex_color, d.tex_color, 4 * T); cp(tex_width, d.tex_width, T); cp(tex_height, d.tex_height, T);
-		cp(tex_loaded, d.tex_loaded, T); cp(tex_texel_off, d.tex_texel_off, T); cp(texels, d.texels, (size_t)d.n_texels * 3);
-		cp(sub_refractive_index, d.sub_refractive_index, S);
+		const std::function<void()> groups[] = {
+		    [&] { cp(node_pos, d.node_pos, 3 * N); cp(node_size, d.node_size, N); cp(node_child, d.node_child, 8 * N);
+		          cp(node_parent, d.node_parent, N); cp(node_octant, d.node_octant, N); cp(node_list_off, d.node_list_off, N + 1); },
+		    [&] { cp(ent_pos, d.ent_pos, 3 * E); cp(ent_type, d.ent_type, E); },
+		    [&] { cp(list_entity, d.list_entity, L); cp(ent_extent, d.ent_extent, E); cp(ent_material, d.ent_material, E);
+		          cp(ent_texture, d.ent_texture, E); cp(ent_substance, d.ent_substance, E); },
+		    [&] { cp(tex_color, d.tex_color, 4 * T); cp(tex_kind, d.tex_kind, T); cp(tex_width, d.tex_width, T); cp(tex_height, d.tex_height, T);
+		          cp(tex_loaded, d.tex_loaded, T); cp(tex_texel_off, d.tex_texel_off, T); cp(texels, d.texels, (size_t)d.n_texels * 3);
+		          cp(mat_response, d.mat_response, M); cp(mat_light, d.mat_light, M); cp(mat_mirror, d.mat_mirror, M);
+		          cp(mat_roughness, d.mat_roughness, M); cp(sub_refractive_index, d.sub_refractive_index, S); },
+		};
+		const size_t n_groups = sizeof groups / sizeof groups[0];
+		rt_parallel_blocks(n_groups, 1, N + L + E + T, [&](size_t g0, size_t g1) {
+			for (size_t g = g0; g < g1; g++) groups[g]();
+		});
 		valid = true;
 	}
 	rt_scene_desc desc() const {
