@@ -380,7 +380,7 @@ uint64_t rt_launch_count(const rt_ctx* ctx);
 #define RT_STAGE_PRIMARY 1  /* camera rays: packet walk + shading of the paths that end at their first hit */
 #define RT_STAGE_SHADE 2    /* refmax > 1: the continuation queue is put in output order (the primary stage itself shades) */
 #define RT_STAGE_BOUNCE 3   /* continued paths */
-#define RT_STAGE_RESAMPLE 4 /* (pixel, frame) samples of rough pixels, n_frames >= 8 */
+#define RT_STAGE_RESAMPLE 4 /* (pixel, frame) samples of rough pixels, n_frames >= 4 */
 #define RT_N_STAGES 5
 rt_status rt_set_profiling(rt_ctx* ctx, int32_t on);
 rt_status rt_stage_times(rt_ctx* ctx, float ms[RT_N_STAGES]);

@@ -805,7 +805,7 @@ struct rt_ctx {
 	int primary_minb = RT_A_MINB;                // tuning knob RT_B200_PRIMARY_MINB=4|5|6: resident CTAs per SM the primary stage is compiled for
 	int bounce_min_walking = 16;                 // tuning knob RT_B200_BOUNCE_MIN (rt_bounce_kernel)
 	size_t sample_bytes = (size_t)2048 << 20;    // bound on the resample stage's sample table (RT_B200_SAMPLE_MIB)
-	int resample_min_frames = 8;                 // tuning knob RT_B200_RESAMPLE_MIN
+	int resample_min_frames = 4;                 // tuning knob RT_B200_RESAMPLE_MIN
 	bool ordered_queue = true;                   // tuning knob RT_B200_ORDERED_QUEUE=0: packets append to the continuation queue as they finish
 	bool resample = true;                        // tuning knob RT_B200_RESAMPLE=0: the bounce stage traces all frames of a rough pixel
 	int bounce_minb = 8;                         // tuning knob RT_B200_BOUNCE_MINB (rt_bounce_kernel<MINB>)
@@ -961,9 +961,9 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	}
 	const bool pipeline = F.packet_ok && !count && !(prm->flags & RT_PARAM_PER_RAY) && !F.search64;
 	if (!pipeline) F.packet_ok = 0;
-	// rough pixels: from RT_RESAMPLE_MIN_FRAMES exposure frames on, their frames are traced as independent samples
-	// by the resample stage (below that the bounce stage's lane traces them in a row: re-tracing the first frame
-	// and pooling cost more than the short tail they remove)
+	// rough pixels: from resample_min_frames exposure frames on (4), their frames are traced as independent samples by
+	// the resample stage (below that the bounce stage's lane traces them in a row: the stage's launches and its own
+	// tail cost more than the short in-lane tail they remove)
 	const bool resample = pipeline && prm->n_frames >= (uint32_t)ctx->resample_min_frames && ctx->resample;
 	if (pipeline) {
 		const size_t cap = tile_compact ? (size_t)((n_tiles - tile_rank + tile_world - 1) / tile_world) * RT_BLOCK

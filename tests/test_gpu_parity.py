@@ -420,7 +420,7 @@ def test_float64_search_equals_float32_search(oracle):
 
 
 def test_resample_stage_equals_frames_in_a_row(oracle, monkeypatch):
-    """From 8 exposure frames on, the frames of a rough pixel are traced as independent (pixel, frame) samples by
+    """From 4 exposure frames on, the frames of a rough pixel are traced as independent (pixel, frame) samples by
     the resample stage and blended in frame order: the same pixels, bit for bit, as one lane tracing them in a row
     (RT_B200_RESAMPLE=0), as the reference's call-per-frame loop, and - within the gate - as the oracle.  Also on a
     continued exposure (frame_first > 0) and for a frame count that is not a multiple of the pool geometry."""
