@@ -1,0 +1,65 @@
+"""Random small scenes and poses for the differential fuzz tests (kernel body on the host / CUDA path vs the oracle):
+every material response (reflection: mirror, rough mirror, diffuse, light; transmission: smooth and rough; BOTH), spheres
+and boxes, all three substances, cameras inside and outside the cube, on dyadic planes, inside entities, axis-aligned
+and arbitrary directions, square and ragged frames, 1-5 exposure frames, refmax 1-9.  tools/fuzz_parity.py runs it for
+as long as one likes (3 000 cases without a mismatch at the time of writing)."""
+import math
+import random
+
+import oracle as orc
+import raytracer_js_b200 as rt
+from raytracer_js_b200 import scenes
+
+MATERIAL_SETS = [["mirror", "diffuse", "light"], ["mirror", "rough", "light", "diffuse"], ["glass", "mirror", "both", "light"],
+                 ["roughglass", "glass", "rough", "mirror"], ["diffuse"]]
+
+
+def build_scene(seed, n, dmin, dmax, kinds):
+    rng = rt.FpLcg(float(seed))
+    tree = rt.new_entity_octree(rt.OctreeDim(rt.point(0, 0, 0), 1.0), None)
+    mats = {"glass": rt.SolidMaterial(rt.ResponseType.TRANSMISSION, False, False, 0),
+            "mirror": rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0),
+            "rough": rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0.5),
+            "diffuse": rt.SolidMaterial(rt.ResponseType.REFLECTION, False, False, 0),
+            "light": rt.SolidMaterial(rt.ResponseType.REFLECTION, True, False, 0),
+            "both": rt.SolidMaterial(rt.ResponseType.BOTH, False, False, 0),
+            "roughglass": rt.SolidMaterial(rt.ResponseType.TRANSMISSION, False, False, 0.3)}
+    subs = [rt.SUBSTANCE_AIR, rt.SUBSTANCE_WATER, rt.SUBSTANCE_GLASS]
+    ents = []
+    for _ in range(n):
+        d = dmin + rng.next() * (dmax - dmin)
+        c = [d / 2 + rng.next() * (1 - d) for _ in range(3)]
+        m = mats[kinds[int(rng.next() * len(kinds))]]
+        tex = rt.SolidTexture(rt.Color(0.2 + rng.next(), 0.2 + rng.next(), 0.2 + rng.next(), 1))
+        cls = rt.BoxEntity if rng.next() < 0.25 else rt.SphereEntity
+        e = cls(None, m, tex, subs[int(rng.next() * 3)], rt.point(*c), d)
+        rt.add_entity_to_octree(tree, e, {"max_in_depth": 16, "max_out_depth": 0})
+        ents.append(e)
+    return scenes.SceneBundle(tree, ents, rt.SkySphere(rt.SolidTexture(rt.Color(0.2, 0.3, 0.7, 1))), rt.SUBSTANCE_AIR, 5)
+
+
+def cases(seed, count, max_entities=4000):
+    """Yields dicts: bundle, pos, yaw, pitch, w, h, n_frames, refmax (+ the generator's choices, for the report)."""
+    R = random.Random(seed)
+    for k in range(count):
+        c = dict(case=k, seed=R.randint(1, 10 ** 6), n=min(max_entities, R.choice([40, 300, 1500, 4000])),
+                 d=R.choice([(0.01, 0.05), (0.03, 0.2), (0.005, 0.02), (0.1, 0.45), (0.02, 0.08)]), kinds=R.choice(MATERIAL_SETS))
+        c["pos"] = R.choice([(0.5, 0.5, 0.5), (R.random(), R.random(), R.random()), (R.random(), R.random(), R.random()),
+                             (0.25, 0.75, 0.5), (0.013, 0.487, 0.021), (0.5, 0.5, 0.0009765625), (-0.2, 0.5, 0.4)])
+        c["yaw"] = R.choice([0.0, 30.0, 45.0, 90.0, 180.0, R.uniform(-180, 180)])
+        c["pitch"] = R.choice([0.0, 0.3, -0.7, R.uniform(-1.2, 1.2)])
+        c["w"], c["h"] = R.choice([(40, 40), (64, 48), (33, 57), (96, 16), (72, 72)])
+        c["n_frames"] = R.choice([1, 2, 5])
+        c["refmax"] = R.choice([1, 4, 6, 9])
+        c["bundle"] = build_scene(c["seed"], c["n"], c["d"][0], c["d"][1], c["kinds"])
+        yield c
+
+
+def cameras(c):
+    cam = scenes.bench_camera(c["w"], c["h"], c["pos"], c["yaw"], c["pitch"])
+    ocam = orc.Camera(math.pi / 2, math.pi / 2, c["w"], c["h"], c["pos"], c["pitch"], math.pi / 180 * c["yaw"], vertical_locked=True)
+    return cam, ocam
+
+
+def describe(c):
+    return {k: v for k, v in c.items() if k != "bundle"}

@@ -1,0 +1,50 @@
+"""Differential fuzz (tests/fuzz_scenes.py): random scenes, poses, frame shapes, exposure counts and refmax - the kernel
+body compiled for the host (pipeline and ray by ray) and, with a device, the CUDA path through the C ABI, against the
+oracle.  No pixel may differ in colour; every id mismatch must be a classified dyadic tie."""
+import numpy as np
+import pytest
+
+import raytracer_js_b200 as rt
+from raytracer_js_b200 import scenes  # noqa: F401
+
+import fuzz_scenes
+from util import classify_outliers, compare, flat_of, hostsim_render, insertion_ids, make_params, oracle_render, oracle_scene
+
+
+def check(c, rgb, ids, flat, prm):
+    _, ocam = fuzz_scenes.cameras(c)
+    orgb, oids, _, tot = oracle_render(oracle_scene(flat, c["bundle"]), ocam, flat, c["bundle"], prm, fixed_extents=True)
+    ids = insertion_ids(flat, c["bundle"], ids)
+    res = compare(rgb, ids, orgb, oids)
+    kinds = classify_outliers(rgb, ids, orgb, oids, cam_pos=c["pos"], ocam=ocam)
+    assert res["rgb_bad"] == 0 and not kinds["unexplained"], (fuzz_scenes.describe(c), res, {k: len(v) for k, v in kinds.items()})
+    return float((oids >= 0).mean())
+
+
+def test_host_build_of_the_kernel_body_against_the_oracle(oracle):
+    hits = []
+    for c in fuzz_scenes.cases(seed=20261019, count=60, max_entities=1500):
+        flat = flat_of(c["bundle"])
+        cam, _ = fuzz_scenes.cameras(c)
+        prm = make_params(flat, c["bundle"], n_frames=c["n_frames"], refmax=c["refmax"])
+        rgb_p, ids_p, _ = hostsim_render(flat, cam, prm, pipeline=True)
+        rgb, ids, _ = hostsim_render(flat, cam, prm)
+        np.testing.assert_array_equal(ids_p, ids, err_msg=str(fuzz_scenes.describe(c)))
+        np.testing.assert_array_equal(rgb_p, rgb, err_msg=str(fuzz_scenes.describe(c)))
+        hits.append(check(c, rgb, ids, flat, prm))
+    assert sum(h > 0.05 for h in hits) >= 25  # the cases do look at geometry
+
+
+@pytest.mark.gpu
+def test_cuda_path_against_the_oracle(oracle):
+    hits = []
+    for c in fuzz_scenes.cases(seed=977, count=50):
+        b = c["bundle"]
+        cam, _ = fuzz_scenes.cameras(c)
+        eb = rt.ExposureBuffer(c["w"], c["h"])
+        tracer = rt.GpuRaytracer(rt.RaytracerConfig(c["refmax"], b.sky, b.default_substance, 1.0), b.tree, cam, eb, rt.FpLcg(1.0))
+        tracer.trace_frame(n_frames=c["n_frames"], want_ids=True)
+        prm = make_params(tracer.flat, b, n_frames=c["n_frames"], refmax=c["refmax"])
+        hits.append(check(c, eb.image().copy(), tracer.last_first_ids.copy(), tracer.flat, prm))
+        tracer.close()
+    assert sum(h > 0.05 for h in hits) >= 20
