@@ -1,7 +1,7 @@
 """Random small scenes and poses for the differential fuzz tests (kernel body on the host / CUDA path vs the oracle):
 every material response (reflection: mirror, rough mirror, diffuse, light; transmission: smooth and rough; BOTH), spheres
 and boxes, all three substances, cameras inside and outside the cube, on dyadic planes, inside entities, axis-aligned
-and arbitrary directions, square and ragged frames, 1-5 exposure frames, refmax 1-9.  tools/fuzz_parity.py runs it for
+and arbitrary directions, solid and image textures, square and ragged frames, 1-5 exposure frames, refmax 1-9.  tools/fuzz_parity.py runs it for
 as long as one likes (3 000 cases without a mismatch at the time of writing)."""
 import math
 import random
@@ -14,8 +14,9 @@ MATERIAL_SETS = [["mirror", "diffuse", "light"], ["mirror", "rough", "light", "d
                  ["roughglass", "glass", "rough", "mirror"], ["diffuse"]]
 
 
-def build_scene(seed, n, dmin, dmax, kinds):
+def build_scene(seed, n, dmin, dmax, kinds, images=False):
     rng = rt.FpLcg(float(seed))
+    texs = [scenes.checker_texture(64, 32, seed=s) for s in (1, 2)] if images else None
     tree = rt.new_entity_octree(rt.OctreeDim(rt.point(0, 0, 0), 1.0), None)
     mats = {"glass": rt.SolidMaterial(rt.ResponseType.TRANSMISSION, False, False, 0),
             "mirror": rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0),
@@ -31,11 +32,14 @@ def build_scene(seed, n, dmin, dmax, kinds):
         c = [d / 2 + rng.next() * (1 - d) for _ in range(3)]
         m = mats[kinds[int(rng.next() * len(kinds))]]
         tex = rt.SolidTexture(rt.Color(0.2 + rng.next(), 0.2 + rng.next(), 0.2 + rng.next(), 1))
+        if texs and rng.next() < 0.6:
+            tex = texs[int(rng.next() * 2)]
         cls = rt.BoxEntity if rng.next() < 0.25 else rt.SphereEntity
         e = cls(None, m, tex, subs[int(rng.next() * 3)], rt.point(*c), d)
         rt.add_entity_to_octree(tree, e, {"max_in_depth": 16, "max_out_depth": 0})
         ents.append(e)
-    return scenes.SceneBundle(tree, ents, rt.SkySphere(rt.SolidTexture(rt.Color(0.2, 0.3, 0.7, 1))), rt.SUBSTANCE_AIR, 5)
+    sky = rt.SkySphere(scenes.checker_texture(128, 64, seed=4) if images else rt.SolidTexture(rt.Color(0.2, 0.3, 0.7, 1)))
+    return scenes.SceneBundle(tree, ents, sky, rt.SUBSTANCE_AIR, 5)
 
 
 def cases(seed, count, max_entities=4000):
@@ -51,7 +55,8 @@ def cases(seed, count, max_entities=4000):
         c["w"], c["h"] = R.choice([(40, 40), (64, 48), (33, 57), (96, 16), (72, 72)])
         c["n_frames"] = R.choice([1, 2, 5])
         c["refmax"] = R.choice([1, 4, 6, 9])
-        c["bundle"] = build_scene(c["seed"], c["n"], c["d"][0], c["d"][1], c["kinds"])
+        c["images"] = R.random() < 0.25  # image textures (nearest texel, src/texture/texture_image.ts:40-63) and an image sky
+        c["bundle"] = build_scene(c["seed"], c["n"], c["d"][0], c["d"][1], c["kinds"], c["images"])
         yield c
 
 

@@ -16,8 +16,8 @@ def check(c, rgb, ids, flat, prm):
     orgb, oids, _, tot = oracle_render(oracle_scene(flat, c["bundle"]), ocam, flat, c["bundle"], prm, fixed_extents=True)
     ids = insertion_ids(flat, c["bundle"], ids)
     res = compare(rgb, ids, orgb, oids)
-    kinds = classify_outliers(rgb, ids, orgb, oids, cam_pos=c["pos"], ocam=ocam)
-    assert res["rgb_bad"] == 0 and not kinds["unexplained"], (fuzz_scenes.describe(c), res, {k: len(v) for k, v in kinds.items()})
+    kinds = classify_outliers(rgb, ids, orgb, oids, cam_pos=c["pos"], ocam=ocam, image_textures=c["images"])
+    assert res["rgb_bad"] == len(kinds["texel_edge"]) and not kinds["unexplained"], (fuzz_scenes.describe(c), res, {k: len(v) for k, v in kinds.items()})
     return float((oids >= 0).mean())
 
 
