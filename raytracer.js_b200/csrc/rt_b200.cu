@@ -775,6 +775,7 @@ struct rt_ctx {
 	DevBuf<RtF4> slot_geom;
 	DevBuf<RtD4> slot_geom64;
 	DevBuf<RtI4> slot_attr;
+	DevBuf<int> slot_node;
 	DevBuf<RtMaterial> materials;
 	DevBuf<RtTexture> textures;
 	DevBuf<double> substances;
@@ -1625,7 +1626,7 @@ void rt_destroy(rt_ctx* ctx) {
 	if (ctx->done_ev) cudaEventDestroy(ctx->done_ev);
 	cudaStreamSynchronize(ctx->stream);
 	ctx->node_geom.release(); ctx->node_geom64.release(); ctx->node_link.release(); ctx->node_child.release(); ctx->node_pk.release(); ctx->node_walk.release(); ctx->node_bvh.release(); ctx->bvh_nodes.release(); ctx->bvh_slots.release(); ctx->bvh_geom.release();
-	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release();
+	ctx->slot_geom.release(); ctx->slot_geom64.release(); ctx->slot_attr.release(); ctx->slot_node.release();
 	ctx->materials.release(); ctx->textures.release(); ctx->substances.release(); ctx->texels.release();
 	ctx->ray_ck.release(); ctx->row_fr.release(); ctx->rgb.release(); ctx->ids.release();
 	ctx->counters.release(); ctx->l2_scratch.release(); ctx->prim_geom.release(); ctx->queue.release(); ctx->vqueue.release(); ctx->queue_dense.release(); ctx->present_partial.release(); ctx->rgba.release(); ctx->samples.release(); ctx->scene_pool.release(); ctx->peer_flags.release();
@@ -1730,7 +1731,7 @@ rt_status rt_host_unregister(rt_ctx* ctx, void* ptr) {
 // every device array of a scene, with its host vector of the same name in RtHostScene
 #define RT_SCENE_ARRAYS(X) \
 	X(node_geom) X(node_geom64) X(node_link) X(node_child) X(node_pk) X(node_walk) X(node_bvh) X(bvh_nodes) X(bvh_slots) X(bvh_geom) \
-	X(slot_geom) X(slot_geom64) X(slot_attr) X(materials) X(textures) X(substances) X(texels)
+	X(slot_geom) X(slot_geom64) X(slot_attr) X(slot_node) X(materials) X(textures) X(substances) X(texels)
 
 // All scene arrays of a ctx as slices of one pool allocation (grow-only: a re-upload of a scene that fits allocates
 // nothing), each aligned to 256 bytes.

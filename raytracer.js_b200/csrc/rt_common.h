@@ -109,6 +109,7 @@ struct RtDevScene {
 	const RtF4* slot_geom;   // centre.xyz, w = radius (>0, sphere) | -half_size (<0, box)
 	const RtD4* slot_geom64; // centre.xyz, w = diameter | size  (the reference's float64 values)
 	const RtI4* slot_attr;   // entity id, material|type<<24, texture, substance (-1 undefined)
+	const int* slot_node;    // the node whose list holds the slot (hit_only_touches_its_cell)
 	// tables
 	const RtMaterial* materials;
 	const RtTexture* textures;

@@ -56,6 +56,7 @@ struct RtHostScene {
 	RtVec<RtF4> slot_geom;
 	RtVec<RtD4> slot_geom64;
 	RtVec<RtI4> slot_attr;
+	RtVec<int> slot_node;
 	std::vector<RtMaterial> materials;
 	RtVec<RtTexture> textures;
 	std::vector<double> substances;
@@ -584,6 +585,7 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 	hs.slot_geom.resize(L);
 	hs.slot_geom64.resize(L);
 	hs.slot_attr.resize(L);
+	hs.slot_node.resize(L);
 	// (error keys: 4 * slot + the place of the check in a single thread's order)
 	rt_parallel_blocks(N, 1024, work, [&](size_t n0, size_t n1) {
 		double sc_max = 0;
@@ -607,6 +609,7 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 				hs.slot_geom[s] = RtF4{(float)p[0], (float)p[1], (float)p[2], w};
 				hs.slot_geom64[s] = RtD4{p[0], p[1], p[2], ext};
 				hs.slot_attr[s] = RtI4{(int)e, m | (int)(type << RT_ATTR_TYPE_SHIFT), t, sb};
+				hs.slot_node[s] = (int)ni;
 				for (int k = 0; k < 3; k++) sc_max = std::max(sc_max, std::fabs(p[k]) + ext);
 			}
 		}

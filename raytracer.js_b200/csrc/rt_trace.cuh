@@ -930,11 +930,42 @@ RT_HD void pixel_dir_clamped(const RtFrame& F, int x, int y, double* dir) {
 
 // float64 confirmation of a float32 candidate for the camera ray of pixel (x,y): 0 = collision_info is null,
 // 1 = hit, 2 = hit whose normal does not face the ray (the guard of src/raytracer.ts:200-203 will end the path)
+// A hit only counts if the reference's walker visits the entity's node for this ray.  The packet walk and the ordered
+// walk visit a SUPERSET of the walker's nodes (conservative pierce tests), which cannot change a first hit as long as a
+// ray that hits an entity really runs through its node's cube.  It does - except when it merely TOUCHES the cube: a
+// corner or an edge (the float64 parameter interval of the cube has zero length: a camera standing on a corner of a
+// box that fills its cell, a 45-degree ray through a lattice corner), or a ray that runs inside one of the cube's
+// face planes.  Whether the walker visits such a node is decided by its half-open cells and its tie order (x, then
+// y, then z), not by geometry, and the float64 hit test of an entity that touches the same corner says "hit, t = 0".
+// Such a hit is not trusted: the segment is searched again by the float64 restatement of the walker itself
+// (walk_and_scan64).  Generic scenes never get here (the coincidences have to be exact in float64); scenes built on a
+// dyadic lattice with the camera on a lattice point - the demo pose (0.5, 0.5, 0.5) is one - do.
+RT_HD bool hit_only_touches_its_cell(const RtDevScene& S, int slot, const double* o, const double* d) {
+	const RtD4 g = ld(S.node_geom64 + ld(S.slot_node + slot));
+	const double lo[3] = {g.x, g.y, g.z};
+	double c[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		c[k] = xadd(lo[k], xmul(g.w, 0.5));
+		if (d[k] == 0.0 && (o[k] == lo[k] || o[k] == xadd(lo[k], g.w))) return true;  // the ray runs inside a face plane
+	}
+	double u1, u2;
+	int i1, i2;
+	if (!exact_box_params(c, g.w, o, d, u1, u2, i1, i2)) return true;  // (the line misses the cube altogether: roundings only)
+	// (not only an exactly empty interval: the walker decides by ITS arithmetic - exit points, octant_adj_pos - and
+	// that can disagree with this slab test when the overlap is within rounding.  1e-9 of the parameter scale is far
+	// above rounding and far below any overlap that matters: a generic ray is re-searched about once in a million hits.)
+	const double lo_t = u1 > 0.0 ? u1 : 0.0;
+	return !(u2 > lo_t + 1e-9 * (1.0 + (u2 < 0.0 ? -u2 : u2)));
+}
+
+// 0: no hit; 1: hit; 2: hit under an acute angle (:200-203); 3: a hit that only touches its cell - not decided here
 RT_COLD int packet_confirm(const RtDevScene& S, const RtFrame& F, const double* dir, int slot) {
 	RtCollision col;
 	const RtD4 g64 = ld(S.slot_geom64 + slot);
 	const bool hit = ld(S.slot_geom + slot).w > 0.0f ? exact_sphere(g64, F.pos, dir, col) : exact_box(g64, F.pos, dir, col);
 	if (!hit) return 0;
+	if (hit_only_touches_its_cell(S, slot, F.pos, dir)) return 3;
 	return dot3(dir, col.normal) >= 0 ? 2 : 1;
 }
 
@@ -1060,8 +1091,8 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 						}
 						if (cand) {
 							const int c = packet_confirm(S, F, dirs + (size_t)(j * 32 + lane) * 3, slot);
-							if (c) {
-								hit[l][j] = slot | (c == 2 ? RT_HIT_ACUTE : 0);
+							if (c) {  // (3: the bounce stage searches this ray again, alone and exactly - segment_found)
+								hit[l][j] = c == 3 ? RT_SLOT_UNKNOWN : (slot | (c == 2 ? RT_HIT_ACUTE : 0));
 								open[l] &= ~(1u << j);
 							}
 						}
@@ -1412,6 +1443,14 @@ RT_HD void walk_push_children(RtWalk& W, const RtWNode& nd, int after_oct, const
 			// 0 * inf is dropped by fminf / fmaxf (the half then keeps the other bound: conservative)
 			n0[k] = fminf(te, tm); f0[k] = fmaxf(te, tm);
 			n1[k] = fminf(tm, tx); f1[k] = fmaxf(tm, tx);
+			if (fabsf(inv[k]) == INFINITY) {
+				// d_k == 0: the ray stays at o_k.  A plane it lies IN gives 0 * inf = NaN, and dropping the NaN would leave
+				// [inf, inf] - an empty interval for a half the ray runs along the face of (cells are half-open: the
+				// reference does visit the upper one).  Membership of o_k in the closed halves instead: conservative.
+				const bool in0 = o[k] >= lo[k] && o[k] <= lo[k] + h, in1 = o[k] >= lo[k] + h && o[k] <= lo[k] + nd.size;
+				n0[k] = in0 ? -INFINITY : INFINITY; f0[k] = in0 ? INFINITY : -INFINITY;
+				n1[k] = in1 ? -INFINITY : INFINITY; f1[k] = in1 ? INFINITY : -INFINITY;
+			}
 		}
 	}
 	// x/y combinations shared by the two z halves
@@ -1742,6 +1781,17 @@ RT_HD bool path_finish(const RtDevScene& S, const RtFrame& F, RtPath& P, double*
 //   segment_end    the material's response to the hit (or the sky / light ending); true when the path ended.
 // `primary_slot`: the first-hit slot of the camera segment when the primary stage already found it (>= 0), or
 // RT_SLOT_UNKNOWN to search.
+// the exact re-search of a segment whose hit only touches its cell (hit_only_touches_its_cell): the walker itself, in float64
+RT_COLD int exact_research(const RtDevScene& S, const double* o, const double* d, int node, int octant, RtCollision* ci) {
+	RtSearch q;
+	q.r = make_ray_f(o, d);
+	q.rel = nullptr;
+	q.chain_mask = 0xffffffffu;
+	q.chain_levels = 0;
+	RtCounts cnt = {0, 0, 0, 0, 0, 0};
+	return walk_and_scan64<false>(S, q, node, octant, o, d, *ci, cnt);
+}
+
 #define RT_SEG_DONE 0
 #define RT_SEG_SLOT 1
 #define RT_SEG_WALK 2
@@ -1780,7 +1830,9 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 		walk_begin(S, *W, P.node, P.octant);
 		return RT_SEG_WALK;
 	}
-	if (F.search64) {
+	// RT_PRECISION_F64 - and the counting variant always: its counters are the reference's access pattern, and at an
+	// exact tie (a ray inside a cell-boundary plane, through a lattice corner) only the float64 steps are the walker's
+	if (F.search64 || COUNT) {
 		slot = walk_and_scan64<COUNT>(S, q, P.node, P.octant, P.refpoint, P.dir, ci, cnt);
 		err |= cnt.errors;
 		return RT_SEG_SLOT;
@@ -1791,6 +1843,10 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 	}
 	slot = walk_and_scan<COUNT>(S, q, P.node, P.octant, P.refpoint, P.dir, ci, cnt);
 	err |= cnt.errors;
+	if (slot >= 0 && hit_only_touches_its_cell(S, slot, P.refpoint, P.dir)) {
+		const double o[3] = {P.refpoint[0], P.refpoint[1], P.refpoint[2]}, d[3] = {P.dir[0], P.dir[1], P.dir[2]};
+		slot = exact_research(S, o, d, P.node, P.octant, &ci);
+	}
 	return RT_SEG_SLOT;
 }
 
@@ -1804,6 +1860,10 @@ RT_HD void segment_found(const RtDevScene& S, const RtPath& P, const RtWalk& W, 
 		slot = -1;
 	}
 	if (slot >= 0 && !confirm_slot(S, slot, P.refpoint, P.dir, ci)) slot = -1;  // (same formula as in the walk: cannot fail)
+	if (slot >= 0 && hit_only_touches_its_cell(S, slot, P.refpoint, P.dir)) {
+		const double o[3] = {P.refpoint[0], P.refpoint[1], P.refpoint[2]}, d[3] = {P.dir[0], P.dir[1], P.dir[2]};
+		slot = exact_research(S, o, d, P.node, P.octant, &ci);
+	}
 }
 
 template <bool COUNT>

@@ -68,3 +68,58 @@ def cameras(c):
 
 def describe(c):
     return {k: v for k, v in c.items() if k != "bundle"}
+
+
+# ---- lattice scenes: everything on a dyadic grid - entities that fill their cells exactly, touch each other and the
+# cell planes, are centred on lattice planes; cameras on lattice points (the demo pose (0.5, 0.5, 0.5) is one) looking
+# along the axes and the diagonals.  Exact ties everywhere: rays inside cell-boundary planes, through lattice corners,
+# cameras standing on the corner of a box.  What the reference does there is decided by its half-open cells and the tie
+# order of its walker, not by geometry (rt_trace.cuh: hit_only_touches_its_cell).
+def lattice_scene(seed, cells, fill, kinds):
+    R = random.Random(seed)
+    tree = rt.new_entity_octree(rt.OctreeDim(rt.point(0, 0, 0), 1.0), None)
+    mats = {"mirror": rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0),
+            "diffuse": rt.SolidMaterial(rt.ResponseType.REFLECTION, False, False, 0),
+            "light": rt.SolidMaterial(rt.ResponseType.REFLECTION, True, False, 0),
+            "glass": rt.SolidMaterial(rt.ResponseType.TRANSMISSION, False, False, 0),
+            "rough": rt.SolidMaterial(rt.ResponseType.REFLECTION, False, True, 0.5)}
+    ents = []
+    step = 1.0 / cells
+    for i in range(cells):
+        for j in range(cells):
+            for k in range(cells):
+                if R.random() > fill:
+                    continue
+                d = step * R.choice([1.0, 1.0, 0.5, 2.0])  # fills its cell / half of it / overlaps the neighbours
+                c = [(i + 0.5) * step, (j + 0.5) * step, (k + 0.5) * step]
+                if R.random() < 0.3:
+                    c = [i * step, j * step, k * step]  # centred ON the lattice planes
+                if any(x - d / 2 < 0 or x + d / 2 > 1 for x in c):
+                    continue
+                m = mats[R.choice(kinds)]
+                tex = rt.SolidTexture(rt.Color(0.2 + R.random(), 0.2 + R.random(), 0.2 + R.random(), 1))
+                cls = rt.BoxEntity if R.random() < 0.4 else rt.SphereEntity
+                sub = rt.SUBSTANCE_GLASS if m.response == rt.ResponseType.TRANSMISSION else rt.SUBSTANCE_AIR
+                e = cls(None, m, tex, sub, rt.point(*c), d)
+                rt.add_entity_to_octree(tree, e, {"max_in_depth": 16, "max_out_depth": 0})
+                ents.append(e)
+    return scenes.SceneBundle(tree, ents, rt.SkySphere(rt.SolidTexture(rt.Color(0.2, 0.3, 0.7, 1))), rt.SUBSTANCE_AIR, 5)
+
+
+def lattice_cases(seed, count):
+    R = random.Random(seed)
+    k = 0
+    while k < count:
+        cells = R.choice([4, 8, 8, 16])
+        b = lattice_scene(R.randint(1, 10 ** 6), cells, R.choice([0.05, 0.2, 0.5]),
+                          R.choice([["mirror", "diffuse", "light"], ["mirror", "rough"], ["glass", "mirror", "light"], ["diffuse"]]))
+        g = 1.0 / R.choice([2, 4, 8, 16])
+        pos = R.choice([(0.5, 0.5, 0.5), (R.randint(1, 7) / 8, R.randint(1, 7) / 8, R.randint(1, 7) / 8), (g, 0.5, 0.5 + g / 2),
+                        (R.random(), R.random(), R.random()), (-0.25, 0.5, 0.5)])
+        c = dict(case=k, cells=cells, n=len(b.entities), pos=pos, yaw=R.choice([0.0, 90.0, 180.0, -90.0, 45.0, R.uniform(-180, 180)]),
+                 pitch=R.choice([0.0, 0.0, math.pi / 4, R.uniform(-1, 1)]), w=R.choice([33, 48, 64]), h=R.choice([33, 48]),
+                 n_frames=R.choice([1, 2]), refmax=R.choice([1, 4, 7]), bundle=b, images=False)
+        if not b.entities:
+            continue
+        k += 1
+        yield c

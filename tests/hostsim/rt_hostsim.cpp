@@ -58,7 +58,7 @@ extern "C" int hostsim_pack_digest(const rt_scene_desc* sc, uint64_t* digest, ch
 	};
 #define EAT(v) eat(hs.v.data(), hs.v.size() * sizeof(hs.v[0]));
 	EAT(node_geom) EAT(node_geom64) EAT(node_link) EAT(node_child) EAT(node_pk) EAT(node_walk) EAT(node_bvh) EAT(bvh_nodes) EAT(bvh_slots) EAT(bvh_geom)
-	EAT(slot_geom) EAT(slot_geom64) EAT(slot_attr) EAT(materials) EAT(textures) EAT(substances) EAT(texels)
+	EAT(slot_geom) EAT(slot_geom64) EAT(slot_attr) EAT(slot_node) EAT(materials) EAT(textures) EAT(substances) EAT(texels)
 #undef EAT
 	eat(&hs.max_bvh_depth, sizeof hs.max_bvh_depth);
 	eat(&hs.max_depth, sizeof hs.max_depth);
@@ -115,7 +115,7 @@ extern "C" int hostsim_render(const rt_scene_desc* sc, const rt_camera* cam, con
 	rt_build_camera_rows(*cam, row, F.scan_cos, F.scan_sin);
 	RtDevScene S{};
 	S.node_geom = hs.node_geom.data(); S.node_geom64 = hs.node_geom64.data(); S.node_link = hs.node_link.data(); S.node_child = hs.node_child.data(); S.node_pk = hs.node_pk.data(); S.node_walk = hs.node_walk.data(); S.node_bvh = hs.node_bvh.data(); S.bvh_nodes = hs.bvh_nodes.data(); S.bvh_slots = hs.bvh_slots.data(); S.bvh_geom = hs.bvh_geom.data();
-	S.slot_geom = hs.slot_geom.data(); S.slot_geom64 = hs.slot_geom64.data(); S.slot_attr = hs.slot_attr.data();
+	S.slot_geom = hs.slot_geom.data(); S.slot_geom64 = hs.slot_geom64.data(); S.slot_attr = hs.slot_attr.data(); S.slot_node = hs.slot_node.data();
 	S.materials = hs.materials.data(); S.textures = hs.textures.data(); S.substances = hs.substances.data();
 	S.texels = hs.texels.data();
 	for (int k = 0; k < 3; k++) S.root_pos[k] = hs.root_pos[k];

@@ -35,6 +35,45 @@ def test_host_build_of_the_kernel_body_against_the_oracle(oracle):
     assert sum(h > 0.05 for h in hits) >= 25  # the cases do look at geometry
 
 
+def test_lattice_scenes_on_the_host_build(oracle):
+    """Exact ties everywhere (fuzz_scenes.lattice_cases): a hit whose ray only touches the entity's cell is searched again
+    by the float64 walker, so the frame is the oracle's - no id mismatch at all, not even the dyadic ties the float32
+    walker used to leave - on the pipeline and ray by ray."""
+    for c in fuzz_scenes.lattice_cases(seed=4, count=80):
+        flat = flat_of(c["bundle"])
+        cam, ocam = fuzz_scenes.cameras(c)
+        prm = make_params(flat, c["bundle"], n_frames=c["n_frames"], refmax=c["refmax"])
+        rgb_p, ids_p, _ = hostsim_render(flat, cam, prm, pipeline=True)
+        rgb, ids, _ = hostsim_render(flat, cam, prm)
+        np.testing.assert_array_equal(ids_p, ids, err_msg=str(fuzz_scenes.describe(c)))
+        np.testing.assert_array_equal(rgb_p, rgb, err_msg=str(fuzz_scenes.describe(c)))
+        orgb, oids, _, tot = oracle_render(oracle_scene(flat, c["bundle"]), ocam, flat, c["bundle"], prm, fixed_extents=True)
+        res = compare(rgb, insertion_ids(flat, c["bundle"], ids), orgb, oids)
+        assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0, (fuzz_scenes.describe(c), res)
+
+
+@pytest.mark.gpu
+def test_lattice_scenes_on_the_cuda_path(oracle):
+    for c in fuzz_scenes.lattice_cases(seed=9, count=60):
+        b = c["bundle"]
+        cam, ocam = fuzz_scenes.cameras(c)
+        out = []
+        for want_counters in (False, True):  # the pipeline, and the counting variant (the float64 walker, ray by ray)
+            eb = rt.ExposureBuffer(c["w"], c["h"])
+            tracer = rt.GpuRaytracer(rt.RaytracerConfig(c["refmax"], b.sky, b.default_substance, 1.0), b.tree, cam, eb, rt.FpLcg(1.0))
+            tracer.trace_frame(n_frames=c["n_frames"], want_ids=True, want_counters=want_counters)
+            out.append((eb.image().copy(), tracer.last_first_ids.copy(), tracer.last_counters))
+            flat = tracer.flat
+            tracer.close()
+        prm = make_params(flat, b, n_frames=c["n_frames"], refmax=c["refmax"])
+        orgb, oids, _, tot = oracle_render(oracle_scene(flat, b), ocam, flat, b, prm, fixed_extents=True, want_counters=True)
+        for rgb, ids, cnt in out:
+            res = compare(rgb, insertion_ids(flat, b, ids), orgb, oids)
+            assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0, (fuzz_scenes.describe(c), res)
+        for key in ("paths", "segments", "nodes", "tests", "shades"):
+            assert out[1][2][key] == tot[key], (key, fuzz_scenes.describe(c), out[1][2], tot)
+
+
 @pytest.mark.gpu
 def test_cuda_path_against_the_oracle(oracle):
     hits = []
