@@ -135,6 +135,15 @@ typedef struct rt_camera {
 /* rt_params.flags (validation / A-B measurement switches; results are identical either way) */
 #define RT_PARAM_NO_PRIMARY_RECORDS 1u /* no per-frame origin-relative records: every ray takes the generic path */
 #define RT_PARAM_PER_RAY 2u            /* camera rays are walked one by one too (no packet stage) */
+/* Exact ties.  The packet walk and the ordered walk visit a superset of the nodes the reference's walker visits, which
+ * cannot change a first hit unless a ray merely TOUCHES the cell of an entity it "hits" (a corner, an edge, a face plane
+ * it runs inside): whether the walker visits such a cell is its half-open rule and its tie order, not geometry.  With
+ * this flag - and by itself whenever the camera stands on a cell plane of the octree (the demo pose (0.5, 0.5, 0.5) does),
+ * which is where camera rays can tie - every such hit is searched again by the float64 restatement of the walker, and
+ * rays with an exactly zero direction component are walked by it from the start.  Set it for scenes built on a dyadic
+ * lattice (entities that fill or touch their cells exactly) viewed from anywhere: bounced rays can tie there too.
+ * A few per cent slower; generic scenes and cameras never need it. */
+#define RT_PARAM_EXACT_TIES 4u
 
 /* RaytracerConfig (src/raytracer.ts:33-43) + exposure state + the harness RNG policy */
 typedef struct rt_params {

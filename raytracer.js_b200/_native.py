@@ -13,6 +13,7 @@ RT_ENTITY_SPHERE, RT_ENTITY_BOX = 0, 1
 RT_TEXTURE_SOLID, RT_TEXTURE_IMAGE = 0, 1
 RT_CAM_REFERENCE_EXTENTS = 1
 RT_PRECISION_F32 = 0
+RT_PARAM_EXACT_TIES = 4
 RT_PRECISION_F64 = 1
 RT_RENDER_COUNTERS = 1
 RT_B200_ABI_VERSION = 1

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256)
 #define RT_ST_BEGIN 1
 #define RT_ST_WALK 2
 #define RT_ST_END 3
-template <int MINB>
+template <int MINB, bool TIES>
 __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
     rt_bounce_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x) {
 	const int lane = threadIdx.x & 31;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			double c[3];
 			int hit = -1;
 			RtCollision ci;
-			const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
+			const int r = segment_begin<false, TIES>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
 			if (r == RT_SEG_DONE) {
 				sample_done(c);
 			} else if (r == RT_SEG_WALK) {
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			double c[3];
 			int hit;
 			RtCollision ci;
-			segment_found(S, P, W, hit, ci, err);
+			segment_found<TIES>(S, F, P, W, hit, ci, err);
 			if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
 			else st = RT_ST_BEGIN;
 		}
@@ -411,7 +411,7 @@ RT_HD size_t frame_out_index(const RtFrame& F, int x, int y, int tiles_x) {
 	return (size_t)(tile / F.tile_world) * RT_BLOCK + ((y & (RT_TILE_H - 1)) * RT_TILE_W + (x & (RT_TILE_W - 1)));
 }
 
-template <int MINB>
+template <int MINB, bool TIES>
 __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
     rt_resample_kernel(const __grid_constant__ RtDevScene S, const __grid_constant__ RtFrame F, int tiles_x, unsigned first, unsigned chunk) {
 	const int lane = threadIdx.x & 31;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			double c[3];
 			int hit = -1;
 			RtCollision ci;
-			const int r = segment_begin<false>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
+			const int r = segment_begin<false, TIES>(S, F, P, slot, c, cnt, err, S.ordered_ok ? &W : nullptr, hit, ci);
 			if (r == RT_SEG_DONE) {
 				sample_done(c);
 			} else if (r == RT_SEG_WALK) {
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(RT_WARPS_PER_CTA * 32, MINB)
 			double c[3];
 			int hit;
 			RtCollision ci;
-			segment_found(S, P, W, hit, ci, err);
+			segment_found<TIES>(S, F, P, W, hit, ci, err);
 			if (segment_end<false>(S, F, P, seed, hit, ci, c, cnt, err)) sample_done(c);
 			else st = RT_ST_BEGIN;
 		}
@@ -989,19 +989,23 @@ rt_status launch_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm,
 	const void* primary_kernel = primary_kernel_of(ppl, pminb);
 	// resident CTAs per SM the bounce stage is compiled for (tuning knob: RT_B200_BOUNCE_MINB=4|5|6|8)
 	const int minb = ctx->bounce_minb;
-	const void* bounce_kernel = minb == 4 ? (const void*)rt_bounce_kernel<4> : minb == 5 ? (const void*)rt_bounce_kernel<5>
-	                          : minb == 6 ? (const void*)rt_bounce_kernel<6> : (const void*)rt_bounce_kernel<8>;
-	const void* resample_kernel = minb == 4 ? (const void*)rt_resample_kernel<4> : minb == 5 ? (const void*)rt_resample_kernel<5>
-	                            : minb == 6 ? (const void*)rt_resample_kernel<6> : (const void*)rt_resample_kernel<8>;
+	// (frames with exact ties, F.tie_checks, take the builds that carry the tie branches: one, for 8 resident CTAs)
+	const bool ties = F.tie_checks != 0;
+	const void* bounce_kernel = ties ? (const void*)rt_bounce_kernel<8, true>
+	                          : minb == 4 ? (const void*)rt_bounce_kernel<4, false> : minb == 5 ? (const void*)rt_bounce_kernel<5, false>
+	                          : minb == 6 ? (const void*)rt_bounce_kernel<6, false> : (const void*)rt_bounce_kernel<8, false>;
+	const void* resample_kernel = ties ? (const void*)rt_resample_kernel<8, true>
+	                            : minb == 4 ? (const void*)rt_resample_kernel<4, false> : minb == 5 ? (const void*)rt_resample_kernel<5, false>
+	                            : minb == 6 ? (const void*)rt_resample_kernel<6, false> : (const void*)rt_resample_kernel<8, false>;
 	int grid_primary = 0, grid_bounce = 0, grid_ray = 0, grid_resample = 0;
 	unsigned resample_chunk = 1;
 	F.samples = nullptr;
 	F.sample_chunk = 0;
 	if (pipeline) {
 		if (rt_status st = grid_of(4, primary_kernel, RT_A_WARPS * 32, grid_primary)) return st;
-		if (rt_status st = grid_of(3, bounce_kernel, RT_WARPS_PER_CTA * 32, grid_bounce)) return st;
+		if (rt_status st = grid_of(ties ? 5 : 3, bounce_kernel, RT_WARPS_PER_CTA * 32, grid_bounce)) return st;
 		if (resample) {
-			if (rt_status st = grid_of(2, resample_kernel, RT_WARPS_PER_CTA * 32, grid_resample)) return st;
+			if (rt_status st = grid_of(ties ? 6 : 2, resample_kernel, RT_WARPS_PER_CTA * 32, grid_resample)) return st;
 			// the sample table: [pixels of a round][n_frames][3] float64 path colours; a queue longer than the table
 			// takes several rounds (RT_B200_SAMPLE_MIB bounds the table, default 2 GiB)
 			const size_t cap = tile_compact ? (size_t)((n_tiles - tile_rank + tile_world - 1) / tile_world) * RT_BLOCK

@@ -203,6 +203,7 @@ struct RtFrame {
 	unsigned* vqueue_taken;
 	double* samples;         // resample stage: [pixels of a round][n_frames][3] path colours
 	unsigned sample_chunk;   // pixels the table holds (a longer resample queue takes several rounds)
+	int tie_checks;          // 1: exact ties are possible (rt_fill_frame): hits that only touch their cell are searched again by the float64 walker
 	int search64;            // RT_PRECISION_F64: the cell-by-cell walker in float64 (walk_and_scan64), one ray per lane
 	int bounce_min_walking;  // bounce stage: leave the lock-step walk when fewer lanes than this are still walking
 	int bounce_node_batch;   // bounce stage: lanes that need a node step wait until this many do

@@ -852,6 +852,13 @@ inline rt_status rt_fill_frame(const RtHostScene& hs, const rt_camera* cam, cons
 		return RT_ERR_UNSUPPORTED;
 	}
 	F.search64 = prm->precision == RT_PRECISION_F64;
+	// exact ties (rt_b200.h: RT_PARAM_EXACT_TIES): asked for, or possible for camera rays - the camera stands on a cell
+	// plane of the octree (a coordinate that is a multiple of the smallest cell's size, counted from the root's corner)
+	F.tie_checks = (prm->flags & RT_PARAM_EXACT_TIES) ? 1 : 0;
+	for (int k = 0; k < 3 && !F.tie_checks; k++) {
+		const double cells = std::ldexp((cam->pos[k] - hs.root_pos[k]) / hs.root_size, std::min(hs.max_depth, 48));
+		if (cells == std::floor(cells)) F.tie_checks = 1;
+	}
 	for (int i = 0; i < 3; i++) {
 		F.pos[i] = cam->pos[i];
 		F.lf[i] = cam->lf[i];

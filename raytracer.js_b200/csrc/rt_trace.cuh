@@ -940,7 +940,7 @@ RT_HD void pixel_dir_clamped(const RtFrame& F, int x, int y, double* dir) {
 // Such a hit is not trusted: the segment is searched again by the float64 restatement of the walker itself
 // (walk_and_scan64).  Generic scenes never get here (the coincidences have to be exact in float64); scenes built on a
 // dyadic lattice with the camera on a lattice point - the demo pose (0.5, 0.5, 0.5) is one - do.
-RT_HD bool hit_only_touches_its_cell(const RtDevScene& S, int slot, const double* o, const double* d) {
+RT_COLD bool hit_only_touches_its_cell(const RtDevScene& S, int slot, const double* o, const double* d) {
 	const RtD4 g = ld(S.node_geom64 + ld(S.slot_node + slot));
 	const double lo[3] = {g.x, g.y, g.z};
 	double c[3];
@@ -959,14 +959,33 @@ RT_HD bool hit_only_touches_its_cell(const RtDevScene& S, int slot, const double
 	return !(u2 > lo_t + 1e-9 * (1.0 + (u2 < 0.0 ? -u2 : u2)));
 }
 
-// 0: no hit; 1: hit; 2: hit under an acute angle (:200-203); 3: a hit that only touches its cell - not decided here
+// The same question in float32, answered "certainly not" for nearly every hit: the ray's overlap with the cell is
+// longer than anything float32 rounding (`slack`: the walks' own bound on a parameter's error) or the float64
+// threshold above could take away.  Only the others pay for the float64 test.
+RT_HD bool hit_may_only_touch_its_cell(const RtDevScene& S, int slot, const RtRayF& r, float slack) {
+	const RtF4 g = ld(S.node_geom + ld(S.slot_node + slot));
+	float ta = (g.x - r.ox) * r.ix, tb = (g.x + g.w - r.ox) * r.ix;
+	float tmin = fminf(ta, tb), tmax = fmaxf(ta, tb);
+	ta = (g.y - r.oy) * r.iy; tb = (g.y + g.w - r.oy) * r.iy;
+	tmin = fmaxf(tmin, fminf(ta, tb)); tmax = fminf(tmax, fmaxf(ta, tb));
+	ta = (g.z - r.oz) * r.iz; tb = (g.z + g.w - r.oz) * r.iz;
+	tmin = fmaxf(tmin, fminf(ta, tb)); tmax = fminf(tmax, fmaxf(ta, tb));
+	return !(tmax - fmaxf(tmin, 0.0f) > 4.0f * slack + 1e-6f * (1.0f + fabsf(tmax)));  // (NaN from 0 * inf: "may")
+}
+
+// 0: no hit; 1: hit; 2: hit under an acute angle (:200-203)
 RT_COLD int packet_confirm(const RtDevScene& S, const RtFrame& F, const double* dir, int slot) {
 	RtCollision col;
 	const RtD4 g64 = ld(S.slot_geom64 + slot);
 	const bool hit = ld(S.slot_geom + slot).w > 0.0f ? exact_sphere(g64, F.pos, dir, col) : exact_box(g64, F.pos, dir, col);
 	if (!hit) return 0;
-	if (hit_only_touches_its_cell(S, slot, F.pos, dir)) return 3;
 	return dot3(dir, col.normal) >= 0 ? 2 : 1;
+}
+// (a function of its own, so that the confirmation above stays what the packet stage's hot loop was tuned around)
+RT_COLD bool packet_hit_only_touches(const RtDevScene& S, const RtFrame& F, const double* dir, int slot) {
+	const RtRayF r = make_ray_f(F.pos, dir);
+	const float slack = S.err_l * fminf(fmaxf(fabsf(r.ix), fmaxf(fabsf(r.iy), fabsf(r.iz))), 1e7f);
+	return hit_may_only_touch_its_cell(S, slot, r, slack) && hit_only_touches_its_cell(S, slot, F.pos, dir);
 }
 
 // Result of the primary search for one camera ray: the first-hit slot (bits 0..29) and RT_HIT_ACUTE, or
@@ -1091,9 +1110,12 @@ RT_HD void packet_walk_class(const RtDevScene& S, const RtFrame& F, const RtPatc
 						}
 						if (cand) {
 							const int c = packet_confirm(S, F, dirs + (size_t)(j * 32 + lane) * 3, slot);
-							if (c) {  // (3: the bounce stage searches this ray again, alone and exactly - segment_found)
-								hit[l][j] = c == 3 ? RT_SLOT_UNKNOWN : (slot | (c == 2 ? RT_HIT_ACUTE : 0));
+							if (c) {
+								hit[l][j] = slot | (c == 2 ? RT_HIT_ACUTE : 0);
 								open[l] &= ~(1u << j);
+								// camera on a cell plane of the octree (F.tie_checks): a hit whose ray only touches the entity's cell is
+								// not decided here - the bounce stage searches the ray again, alone and exactly (segment_found)
+								if (F.tie_checks && packet_hit_only_touches(S, F, dirs + (size_t)(j * 32 + lane) * 3, slot)) hit[l][j] = RT_SLOT_UNKNOWN;
 							}
 						}
 					}
@@ -1443,14 +1465,6 @@ RT_HD void walk_push_children(RtWalk& W, const RtWNode& nd, int after_oct, const
 			// 0 * inf is dropped by fminf / fmaxf (the half then keeps the other bound: conservative)
 			n0[k] = fminf(te, tm); f0[k] = fmaxf(te, tm);
 			n1[k] = fminf(tm, tx); f1[k] = fmaxf(tm, tx);
-			if (fabsf(inv[k]) == INFINITY) {
-				// d_k == 0: the ray stays at o_k.  A plane it lies IN gives 0 * inf = NaN, and dropping the NaN would leave
-				// [inf, inf] - an empty interval for a half the ray runs along the face of (cells are half-open: the
-				// reference does visit the upper one).  Membership of o_k in the closed halves instead: conservative.
-				const bool in0 = o[k] >= lo[k] && o[k] <= lo[k] + h, in1 = o[k] >= lo[k] + h && o[k] <= lo[k] + nd.size;
-				n0[k] = in0 ? -INFINITY : INFINITY; f0[k] = in0 ? INFINITY : -INFINITY;
-				n1[k] = in1 ? -INFINITY : INFINITY; f1[k] = in1 ? INFINITY : -INFINITY;
-			}
 		}
 	}
 	// x/y combinations shared by the two z halves
@@ -1781,21 +1795,36 @@ RT_HD bool path_finish(const RtDevScene& S, const RtFrame& F, RtPath& P, double*
 //   segment_end    the material's response to the hit (or the sky / light ending); true when the path ended.
 // `primary_slot`: the first-hit slot of the camera segment when the primary stage already found it (>= 0), or
 // RT_SLOT_UNKNOWN to search.
-// the exact re-search of a segment whose hit only touches its cell (hit_only_touches_its_cell): the walker itself, in float64
-RT_COLD int exact_research(const RtDevScene& S, const double* o, const double* d, int node, int octant, RtCollision* ci) {
+// The tie machinery of a segment, all of it in two cold functions that take their arguments by value - nothing of the
+// hot path's state has its address taken, and with F.tie_checks == 0 (every generic frame) nothing of this runs:
+//   exact_research  the walker itself, in float64 (walk_and_scan64): the first-hit slot, or -1;
+//   tie_recheck     `slot` is the hit a conservative walk found: if its ray only touches the entity's cell (float32
+//                   pre-check, then float64), the segment is searched again exactly; returns the slot that counts.
+RT_COLD int exact_research(const RtDevScene& S, double ox, double oy, double oz, double dx, double dy, double dz, int node, int octant) {
+	const double o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
 	RtSearch q;
 	q.r = make_ray_f(o, d);
 	q.rel = nullptr;
 	q.chain_mask = 0xffffffffu;
 	q.chain_levels = 0;
 	RtCounts cnt = {0, 0, 0, 0, 0, 0};
-	return walk_and_scan64<false>(S, q, node, octant, o, d, *ci, cnt);
+	RtCollision ci;
+	return walk_and_scan64<false>(S, q, node, octant, o, d, ci, cnt);
+}
+RT_COLD int tie_recheck(const RtDevScene& S, int slot, double ox, double oy, double oz, double dx, double dy, double dz, int node, int octant) {
+	const double o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+	const RtRayF r = make_ray_f(o, d);
+	const float slack = S.err_l * fminf(fmaxf(fabsf(r.ix), fmaxf(fabsf(r.iy), fabsf(r.iz))), 1e7f);
+	if (!hit_may_only_touch_its_cell(S, slot, r, slack) || !hit_only_touches_its_cell(S, slot, o, d)) return slot;
+	return exact_research(S, ox, oy, oz, dx, dy, dz, node, octant);
 }
 
 #define RT_SEG_DONE 0
 #define RT_SEG_SLOT 1
 #define RT_SEG_WALK 2
-template <bool COUNT>
+// (TIES = false: the bounce / resample kernels built for frames without exact ties (F.tie_checks == 0) - the mere presence
+// of the tie branches, never taken, cost those kernels 4 % (same-box A/B); the frames that need them get the TIES build)
+template <bool COUNT, bool TIES = true>
 RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int primary_slot, double* out, RtCounts& cnt,
                         uint32_t& err, RtWalk* W, int& slot, RtCollision& ci) {
 	// walker.set_pos_and_dir -> set_position -> setup_cur_node (src/octree_space.ts:188-205,251-278)
@@ -1817,6 +1846,7 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 	if (P.primary && primary_slot >= 0) {
 		// found by the packet stage: only the collision itself is recomputed (same float64 formula)
 		slot = confirm_slot(S, primary_slot, P.refpoint, P.dir, ci) ? primary_slot : -1;
+		if (W) W->slack = -1.0f;  // (segment_found: this hit was looked at by packet_confirm)
 		return RT_SEG_SLOT;
 	}
 	RtSearch q;
@@ -1827,6 +1857,15 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 	if (P.primary && F.prim_geom) q.rel = F.prim_geom;  // camera rays: origin-relative records
 	if (W) {
 		W->r = q.r;
+		if (TIES && F.tie_checks && (P.dir[0] == 0.0 || P.dir[1] == 0.0 || P.dir[2] == 0.0)) {
+			// a ray that stays inside an axis plane (the middle row or column of an axis-aligned camera; next to never a
+			// bounced ray): where that plane is a cell boundary, which cells it belongs to is the walker's half-open rule,
+			// and 0 * inf has no place in the conservative pierce tests - the float64 walker itself takes the segment
+			W->slack = -1.0f;  // (segment_found: nothing left to check)
+			slot = exact_research(S, P.refpoint[0], P.refpoint[1], P.refpoint[2], P.dir[0], P.dir[1], P.dir[2], P.node, P.octant);
+			if (slot >= 0 && !confirm_slot(S, slot, P.refpoint, P.dir, ci)) slot = -1;
+			return RT_SEG_SLOT;
+		}
 		walk_begin(S, *W, P.node, P.octant);
 		return RT_SEG_WALK;
 	}
@@ -1843,9 +1882,12 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 	}
 	slot = walk_and_scan<COUNT>(S, q, P.node, P.octant, P.refpoint, P.dir, ci, cnt);
 	err |= cnt.errors;
-	if (slot >= 0 && hit_only_touches_its_cell(S, slot, P.refpoint, P.dir)) {
-		const double o[3] = {P.refpoint[0], P.refpoint[1], P.refpoint[2]}, d[3] = {P.dir[0], P.dir[1], P.dir[2]};
-		slot = exact_research(S, o, d, P.node, P.octant, &ci);
+	if (TIES && F.tie_checks && slot >= 0) {
+		const int exact = tie_recheck(S, slot, P.refpoint[0], P.refpoint[1], P.refpoint[2], P.dir[0], P.dir[1], P.dir[2], P.node, P.octant);
+		if (exact != slot) {
+			slot = exact;
+			if (slot >= 0 && !confirm_slot(S, slot, P.refpoint, P.dir, ci)) slot = -1;
+		}
 	}
 	return RT_SEG_SLOT;
 }
@@ -1853,17 +1895,16 @@ RT_HD int segment_begin(const RtDevScene& S, const RtFrame& F, RtPath& P, int pr
 // after the ordered walk: the collision of the slot it found.  A walk that ran out of stack (W.hit ==
 // RT_WALK_OVERFLOW; rt_ordered_walk_fits sizes the stack for the tree's depth at upload, so this is a defect, not an
 // input) is not answered with a guess: the frame's error flag is raised and the render call fails.
-RT_HD void segment_found(const RtDevScene& S, const RtPath& P, const RtWalk& W, int& slot, RtCollision& ci, uint32_t& err) {
+template <bool TIES = true>
+RT_HD void segment_found(const RtDevScene& S, const RtFrame& F, const RtPath& P, const RtWalk& W, int& slot, RtCollision& ci, uint32_t& err) {
 	slot = W.hit;
 	if (slot == RT_WALK_OVERFLOW) {
 		err |= RT_ERRFLAG_STACK;
 		slot = -1;
 	}
+	if (TIES && F.tie_checks && slot >= 0 && W.slack >= 0.0f)  // (exact ties: rt_b200.h RT_PARAM_EXACT_TIES; W.slack < 0: already exact)
+		slot = tie_recheck(S, slot, P.refpoint[0], P.refpoint[1], P.refpoint[2], P.dir[0], P.dir[1], P.dir[2], P.node, P.octant);
 	if (slot >= 0 && !confirm_slot(S, slot, P.refpoint, P.dir, ci)) slot = -1;  // (same formula as in the walk: cannot fail)
-	if (slot >= 0 && hit_only_touches_its_cell(S, slot, P.refpoint, P.dir)) {
-		const double o[3] = {P.refpoint[0], P.refpoint[1], P.refpoint[2]}, d[3] = {P.dir[0], P.dir[1], P.dir[2]};
-		slot = exact_research(S, o, d, P.node, P.octant, &ci);
-	}
 }
 
 template <bool COUNT>
@@ -1984,7 +2025,7 @@ RT_HD bool path_segment(const RtDevScene& S, const RtFrame& F, RtPath& P, double
 		if (r == RT_SEG_WALK) {
 			while (walk_iter<false>(S, W, P.refpoint, P.dir, true)) {
 			}
-			segment_found(S, P, W, slot, ci, err);
+			segment_found(S, F, P, W, slot, ci, err);
 		}
 	} else {
 		if (segment_begin<COUNT>(S, F, P, primary_slot, out, cnt, err, nullptr, slot, ci) == RT_SEG_DONE) return true;

@@ -47,9 +47,12 @@ def camera_desc(camera: Camera, reference_extents: bool = False) -> N.CameraDesc
 class GpuRaytracer:
     def __init__(self, config: RaytracerConfig, otree: Octree, camera: Camera, ebuffer: ExposureBuffer, rng: RNG,
                  device: int = -1, reference_extents: bool = False, n_gpus: int = 1, devices=None,
-                 precision: int = N.RT_PRECISION_F32):
+                 precision: int = N.RT_PRECISION_F32, exact_ties: bool = False):
         """precision: RT_PRECISION_F32 (float search + float64 confirmation, the default) or RT_PRECISION_F64 (the
         reference's walker in float64, ray by ray: slower, but for octrees of any depth).
+        exact_ties: RT_PARAM_EXACT_TIES - for scenes built on a dyadic lattice (entities that fill or touch their cells
+        exactly): hits whose ray only touches the entity's cell are searched again by the float64 walker.  On by itself
+        whenever the camera stands on a cell plane of the octree.
         n_gpus > 1 (or an explicit `devices` list): one process drives all of them behind the same calls
         (rt_create_multi): the scene is packed once and replicated device to device, trace_frame() shards the
         frame into interleaved tiles and every GPU stores its tiles straight into the ExposureBuffer."""
@@ -68,6 +71,7 @@ class GpuRaytracer:
         self._rng = rng
         self.reference_extents = bool(reference_extents)
         self.precision = int(precision)
+        self.exact_ties = bool(exact_ties)
         self.last_counters: Optional[dict] = None
         self.last_first_ids: Optional[np.ndarray] = None
         self.flat: Optional[FlatScene] = None
@@ -146,6 +150,7 @@ class GpuRaytracer:
         # the harness RNG policy (rt_b200.h): per-pixel reseed through the public PRNG.seed()
         p.rng_seed = float(getattr(self._rng, "seed_value", 1.0)) if isinstance(self._rng, PRNG) else 1.0
         p.precision = self.precision
+        p.flags = N.RT_PARAM_EXACT_TIES if self.exact_ties else 0
         return p
 
     @property

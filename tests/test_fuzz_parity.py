@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import raytracer_js_b200 as rt
+from raytracer_js_b200 import _native as N
 from raytracer_js_b200 import scenes  # noqa: F401
 
 import fuzz_scenes
@@ -36,13 +37,14 @@ def test_host_build_of_the_kernel_body_against_the_oracle(oracle):
 
 
 def test_lattice_scenes_on_the_host_build(oracle):
-    """Exact ties everywhere (fuzz_scenes.lattice_cases): a hit whose ray only touches the entity's cell is searched again
-    by the float64 walker, so the frame is the oracle's - no id mismatch at all, not even the dyadic ties the float32
+    """Exact ties everywhere (fuzz_scenes.lattice_cases), RT_PARAM_EXACT_TIES: a hit whose ray only touches the entity's cell
+    is searched again by the float64 walker, so the frame is the oracle's - no id mismatch at all, not even the dyadic ties the float32
     walker used to leave - on the pipeline and ray by ray."""
     for c in fuzz_scenes.lattice_cases(seed=4, count=80):
         flat = flat_of(c["bundle"])
         cam, ocam = fuzz_scenes.cameras(c)
         prm = make_params(flat, c["bundle"], n_frames=c["n_frames"], refmax=c["refmax"])
+        prm.flags |= N.RT_PARAM_EXACT_TIES  # a lattice scene: bounced rays can tie too, whatever the camera
         rgb_p, ids_p, _ = hostsim_render(flat, cam, prm, pipeline=True)
         rgb, ids, _ = hostsim_render(flat, cam, prm)
         np.testing.assert_array_equal(ids_p, ids, err_msg=str(fuzz_scenes.describe(c)))
@@ -60,7 +62,8 @@ def test_lattice_scenes_on_the_cuda_path(oracle):
         out = []
         for want_counters in (False, True):  # the pipeline, and the counting variant (the float64 walker, ray by ray)
             eb = rt.ExposureBuffer(c["w"], c["h"])
-            tracer = rt.GpuRaytracer(rt.RaytracerConfig(c["refmax"], b.sky, b.default_substance, 1.0), b.tree, cam, eb, rt.FpLcg(1.0))
+            tracer = rt.GpuRaytracer(rt.RaytracerConfig(c["refmax"], b.sky, b.default_substance, 1.0), b.tree, cam, eb, rt.FpLcg(1.0),
+                                     exact_ties=True)
             tracer.trace_frame(n_frames=c["n_frames"], want_ids=True, want_counters=want_counters)
             out.append((eb.image().copy(), tracer.last_first_ids.copy(), tracer.last_counters))
             flat = tracer.flat
