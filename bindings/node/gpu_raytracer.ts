@@ -149,6 +149,9 @@ export class GpuRaytracer {
 	/** 0: float32 search + float64 confirmation (default); 1: RT_PRECISION_F64, the walker in float64, ray by ray -
 	 *  for octrees deeper than float32 resolves (max_in_depth beyond ~23 below a unit root) */
 	precision = 0;
+	/** RT_PARAM_EXACT_TIES: for scenes built on a dyadic lattice (entities that fill or touch their cells exactly); on by
+	 *  itself whenever the camera stands on a cell plane of the octree */
+	exact_ties = false;
 
 	config: RaytracerConfig;
 
@@ -191,7 +194,7 @@ export class GpuRaytracer {
 			{ refmax: this.config.refmax, sky_texture: this.tex.get((this.config.sky as any).texture),
 			  default_substance: this.sub.get(this.config.default_substance),
 			  distance_attenuation_factor: this.config.distance_attenuation_factor,
-			  n_frames, frame_first: eb.current_frame, rng_seed: this.rng_seed, want_counters: 0, precision: this.precision },
+			  n_frames, frame_first: eb.current_frame, rng_seed: this.rng_seed, want_counters: 0, precision: this.precision, exact_ties: +this.exact_ties },
 			eb.store);
 		for (let i = 1; i < n_frames; ++i) eb.next_frame();
 	}

@@ -210,6 +210,7 @@ static napi_value Render(napi_env env, napi_callback_info info) {
 	prm.frame_first = (uint32_t)num(env, argv[2], "frame_first");
 	prm.rng_seed = num(env, argv[2], "rng_seed");
 	prm.precision = num(env, argv[2], "precision") == 1 ? RT_PRECISION_F64 : RT_PRECISION_F32; /* absent: float32 search */
+	prm.flags = num(env, argv[2], "exact_ties") != 0 ? RT_PARAM_EXACT_TIES : 0u;                /* lattice scenes (rt_b200.h) */
 	want_counters = num(env, argv[2], "want_counters") != 0;
 	RT_NAPI_TRY(env, napi_get_typedarray_info(env, argv[3], &t, &npx, &rgb, NULL, NULL));
 	if (t != napi_float32_array || npx != (size_t)cam.width * cam.height * 3) {
