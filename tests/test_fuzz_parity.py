@@ -54,6 +54,50 @@ def test_lattice_scenes_on_the_host_build(oracle):
         assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0, (fuzz_scenes.describe(c), res)
 
 
+def test_moved_entities_on_the_host_build(oracle):
+    """rt_scene_update's path (rt_host.h: rt_scene_move_entities on the library's copy of the flat scene) under random
+    moves - far away, by a hair, not at all, onto lattice points, the same entity twice - against the oracle's
+    orc_move_entity on its own pointer tree: 1 to 200 moves per scene."""
+    import random
+    from util import hostsim
+    R = random.Random(5)
+    L = hostsim()
+    L.hostsim_set_moves.restype = None
+    for c in fuzz_scenes.cases(seed=31, count=30, max_entities=1500):
+        b = c["bundle"]
+        flat0 = flat_of(b)
+        order0 = {id(e): i for i, e in enumerate(flat0.entities)}
+        os_ = oracle_scene(flat0, b)
+        mv = []
+        for _ in range(R.choice([1, 5, 40, 200])):
+            i = R.randrange(len(b.entities)) if not mv or R.random() > 0.15 else mv[-1][0]
+            e = b.entities[i]
+            d = e.get_diameter() if isinstance(e, rt.SphereEntity) else e.get_size()
+            kind = R.random()
+            if kind < 0.15:
+                p = [x + R.choice([1e-9, -1e-9, 0.0]) for x in e.get_pos().v]
+            elif kind < 0.35:
+                g = 1.0 / R.choice([2, 4, 8, 16, 64])
+                p = [round(R.random() / g) * g for _ in range(3)]
+            else:
+                p = [d / 2 + R.random() * (1 - d) for _ in range(3)]
+            mv.append((i, [min(max(x, d / 2), 1 - d / 2) for x in p]))
+        cam, ocam = fuzz_scenes.cameras(c)
+        prm = make_params(flat0, b, n_frames=c["n_frames"], refmax=c["refmax"])
+        ids = np.array([order0[id(b.entities[i])] for i, _ in mv], np.uint32)
+        pos = np.array([p for _, p in mv], np.float64)
+        L.hostsim_set_moves(len(ids), ids.ctypes.data_as(N._up), pos.ctypes.data_as(N._dp), 16)
+        try:
+            rgb, idm, _ = hostsim_render(flat0, cam, prm, pipeline=True)
+        finally:
+            L.hostsim_set_moves(0, None, None, 16)
+        for i, p in mv:
+            os_.move_entity(i, p)
+        orgb, oids, _, tot = oracle_render(os_, ocam, flat0, b, prm, fixed_extents=True)
+        res = compare(rgb, insertion_ids(flat0, b, idm), orgb, oids)
+        assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0, (fuzz_scenes.describe(c), len(mv), res)
+
+
 @pytest.mark.gpu
 def test_lattice_scenes_on_the_cuda_path(oracle):
     for c in fuzz_scenes.lattice_cases(seed=9, count=60):
