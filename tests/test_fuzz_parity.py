@@ -134,3 +134,25 @@ def test_cuda_path_against_the_oracle(oracle):
         hits.append(check(c, eb.image().copy(), tracer.last_first_ids.copy(), tracer.flat, prm))
         tracer.close()
     assert sum(h > 0.05 for h in hits) >= 20
+
+
+@pytest.mark.gpu
+def test_group_frames_equal_single_gpu_frames():
+    """rt_create_multi (three members on one GPU, or every GPU of the box) on the fuzz cases: the sharded frame - ids,
+    pixels - is the single-GPU frame, bit for bit, random and lattice scenes alike."""
+    import itertools
+    import torch
+    devs = list(range(torch.cuda.device_count())) if torch.cuda.device_count() > 1 else [0, 0, 0]
+    for c in itertools.chain(fuzz_scenes.cases(seed=71, count=20, max_entities=1500), fuzz_scenes.lattice_cases(seed=72, count=20)):
+        b = c["bundle"]
+        cam, _ = fuzz_scenes.cameras(c)
+        out = []
+        for kw in ({}, {"devices": devs}):
+            eb = rt.ExposureBuffer(c["w"], c["h"])
+            t = rt.GpuRaytracer(rt.RaytracerConfig(c["refmax"], b.sky, b.default_substance, 1.0), b.tree, cam, eb, rt.FpLcg(1.0),
+                                exact_ties=True, **kw)
+            t.trace_frame(n_frames=c["n_frames"], want_ids=True)
+            out.append((eb.pixels.copy(), t.last_first_ids.copy()))
+            t.close()
+        np.testing.assert_array_equal(out[1][0], out[0][0], err_msg=str(fuzz_scenes.describe(c)))
+        np.testing.assert_array_equal(out[1][1], out[0][1], err_msg=str(fuzz_scenes.describe(c)))
