@@ -138,11 +138,10 @@ typedef struct rt_camera {
 /* Exact ties.  The packet walk and the ordered walk visit a superset of the nodes the reference's walker visits, which
  * cannot change a first hit unless a ray merely TOUCHES the cell of an entity it "hits" (a corner, an edge, a face plane
  * it runs inside): whether the walker visits such a cell is its half-open rule and its tie order, not geometry.  With
- * this flag - and by itself whenever the camera stands on a cell plane of the octree (the demo pose (0.5, 0.5, 0.5) does),
- * which is where camera rays can tie - every such hit is searched again by the float64 restatement of the walker, and
- * rays with an exactly zero direction component are walked by it from the start.  Set it for scenes built on a dyadic
- * lattice (entities that fill or touch their cells exactly) viewed from anywhere: bounced rays can tie there too.
- * A few per cent slower; generic scenes and cameras never need it. */
+ * this flag - and by itself whenever the camera stands on a cell plane of the octree (the demo pose (0.5, 0.5, 0.5) does)
+ * or the uploaded scene has an entity whose bounding cube has a face on a cell plane (scenes placed on a grid) - every
+ * such hit is searched again by the float64 restatement of the walker, and rays with an exactly zero direction
+ * component are walked by it from the start.  A few per cent slower; generic scenes and cameras never get it. */
 #define RT_PARAM_EXACT_TIES 4u
 
 /* RaytracerConfig (src/raytracer.ts:33-43) + exposure state + the harness RNG policy */

@@ -67,6 +67,7 @@ struct RtHostScene {
 	bool any_transmission = false;
 	int max_depth = 0;  // deepest node level (root = 0)
 	std::string f32_refusal;  // non-empty: why this tree cannot be searched in float32 (RT_PRECISION_F64 can)
+	bool entities_on_cell_planes = false;  // some entity's bounding cube has a face on a cell plane of the tree: exact ties are possible
 };
 
 inline std::string rt_format(const char* fmt, ...);
@@ -587,8 +588,16 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 	hs.slot_attr.resize(L);
 	hs.slot_node.resize(L);
 	// (error keys: 4 * slot + the place of the check in a single thread's order)
+	// An entity whose bounding cube has a face ON a cell plane of the tree (a coordinate that is a whole number of the
+	// smallest cells, counted from the root's corner) fills or touches cells exactly: rays can merely touch such cells,
+	// and what the reference does then is its tie rules (rt_trace.cuh: hit_only_touches_its_cell).  Random scenes have
+	// none; scenes placed on a grid - a floor on the root's face is enough - do, and get the tie checks by themselves.
+	std::atomic<bool> on_planes{false};
+	const double root_size = sc->node_size[0];
+	const int plane_depth = std::min(hs.max_depth, 48);
 	rt_parallel_blocks(N, 1024, work, [&](size_t n0, size_t n1) {
 		double sc_max = 0;
+		bool planes = false;
 		for (size_t ni = n0; ni < n1; ni++) {
 			const int i = order[ni];
 			const uint32_t beg = sc->node_list_off[i], end = sc->node_list_off[i + 1];
@@ -610,11 +619,19 @@ inline rt_status rt_pack_scene(const rt_scene_desc* sc, RtHostScene& hs, std::st
 				hs.slot_geom64[s] = RtD4{p[0], p[1], p[2], ext};
 				hs.slot_attr[s] = RtI4{(int)e, m | (int)(type << RT_ATTR_TYPE_SHIFT), t, sb};
 				hs.slot_node[s] = (int)ni;
-				for (int k = 0; k < 3; k++) sc_max = std::max(sc_max, std::fabs(p[k]) + ext);
+				for (int k = 0; k < 3; k++) {
+					sc_max = std::max(sc_max, std::fabs(p[k]) + ext);
+					const double c_lo = std::ldexp((p[k] - ext / 2 - sc->node_pos[k]) / root_size, plane_depth);
+					const double c_hi = std::ldexp((p[k] + ext / 2 - sc->node_pos[k]) / root_size, plane_depth);
+					planes |= c_lo == std::floor(c_lo) || c_hi == std::floor(c_hi);
+				}
 			}
 		}
 		merge_scale(sc_max);
+		if (planes) on_planes.store(true);
 	});
+	hs.entities_on_cell_planes = on_planes.load();
+	if (clk.on) fprintf(stderr, "[rt_pack_scene] entity faces on cell planes: %s\n", hs.entities_on_cell_planes ? "yes (exact-tie checks on)" : "no");
 	{
 		std::vector<uint8_t> seen(E, 0);  // an entity sits in ONE node's Set (src/entity.ts:50-56)
 		uint32_t s = 0;
@@ -852,9 +869,9 @@ inline rt_status rt_fill_frame(const RtHostScene& hs, const rt_camera* cam, cons
 		return RT_ERR_UNSUPPORTED;
 	}
 	F.search64 = prm->precision == RT_PRECISION_F64;
-	// exact ties (rt_b200.h: RT_PARAM_EXACT_TIES): asked for, or possible for camera rays - the camera stands on a cell
-	// plane of the octree (a coordinate that is a multiple of the smallest cell's size, counted from the root's corner)
-	F.tie_checks = (prm->flags & RT_PARAM_EXACT_TIES) ? 1 : 0;
+	// exact ties (rt_b200.h: RT_PARAM_EXACT_TIES): asked for, or the scene has entities whose faces lie on cell planes
+	// (rt_pack_scene), or possible for camera rays - the camera stands on a cell plane of the octree (a coordinate that is a multiple of the smallest cell's size, counted from the root's corner)
+	F.tie_checks = ((prm->flags & RT_PARAM_EXACT_TIES) || hs.entities_on_cell_planes) ? 1 : 0;
 	for (int k = 0; k < 3 && !F.tie_checks; k++) {
 		const double cells = std::ldexp((cam->pos[k] - hs.root_pos[k]) / hs.root_size, std::min(hs.max_depth, 48));
 		if (cells == std::floor(cells)) F.tie_checks = 1;

@@ -37,14 +37,14 @@ def test_host_build_of_the_kernel_body_against_the_oracle(oracle):
 
 
 def test_lattice_scenes_on_the_host_build(oracle):
-    """Exact ties everywhere (fuzz_scenes.lattice_cases), RT_PARAM_EXACT_TIES: a hit whose ray only touches the entity's cell
-    is searched again by the float64 walker, so the frame is the oracle's - no id mismatch at all, not even the dyadic ties the float32
+    """Exact ties everywhere (fuzz_scenes.lattice_cases): a hit whose ray only touches the entity's cell is searched again
+    by the float64 walker, so the frame is the oracle's - no id mismatch at all, not even the dyadic ties the float32
     walker used to leave - on the pipeline and ray by ray."""
     for c in fuzz_scenes.lattice_cases(seed=4, count=80):
         flat = flat_of(c["bundle"])
         cam, ocam = fuzz_scenes.cameras(c)
         prm = make_params(flat, c["bundle"], n_frames=c["n_frames"], refmax=c["refmax"])
-        prm.flags |= N.RT_PARAM_EXACT_TIES  # a lattice scene: bounced rays can tie too, whatever the camera
+        # (no RT_PARAM_EXACT_TIES: rt_pack_scene sees entity faces on cell planes and switches the tie checks on itself)
         rgb_p, ids_p, _ = hostsim_render(flat, cam, prm, pipeline=True)
         rgb, ids, _ = hostsim_render(flat, cam, prm)
         np.testing.assert_array_equal(ids_p, ids, err_msg=str(fuzz_scenes.describe(c)))
