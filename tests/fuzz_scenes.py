@@ -123,3 +123,28 @@ def lattice_cases(seed, count):
             continue
         k += 1
         yield c
+
+
+def edge_cases(seed, count):
+    """Cameras outside the cube on every side, on its faces and corners, a hair inside; entities from 1e-4 to 0.9 of the
+    root; refmax 0 - 5; square frames with the reference's own extents (`reference_extents`), ragged ones without."""
+    R = random.Random(seed)
+    k = 0
+    while k < count:
+        lattice = R.random() < 0.4
+        if lattice:
+            b = lattice_scene(R.randint(1, 10 ** 6), R.choice([2, 4, 8]), R.choice([0.1, 0.4, 0.9]),
+                              R.choice([["mirror", "diffuse", "light"], ["glass", "mirror", "light"], ["rough", "mirror"]]))
+            if not b.entities:
+                continue
+        else:
+            dm = R.choice([(1e-4, 1e-3), (0.3, 0.9), (0.0005, 0.3), (0.05, 0.06)])
+            b = build_scene(R.randint(1, 10 ** 6), R.choice([3, 30, 600]), dm[0], dm[1], R.choice(MATERIAL_SETS), R.random() < 0.2)
+        pos = R.choice([(-0.5, 0.5, 0.5), (1.5, 0.3, 0.7), (0.5, -2.0, 0.5), (0.5, 0.5, 3.0), (0.0, 0.5, 0.5), (1.0, 1.0, 1.0), (0.0, 0.0, 0.0),
+                        (1e-9, 0.5, 0.5), (0.999999999, 0.2, 0.9), (R.uniform(-1, 2), R.uniform(-1, 2), R.uniform(-1, 2)), (0.5, 0.5, 0.5)])
+        square = R.random() < 0.4
+        w, h = (R.choice([32, 50, 64]),) * 2 if square else R.choice([(40, 24), (24, 40), (72, 8)])
+        yield dict(case=k, lattice=lattice, n=len(b.entities), pos=pos, yaw=R.choice([0.0, 90.0, -90.0, 180.0, 45.0, 135.0, R.uniform(-180, 180)]),
+                   pitch=R.choice([0.0, 0.5, -0.5, 1.4, -1.4, R.uniform(-1.5, 1.5)]), w=w, h=h, n_frames=R.choice([1, 3]),
+                   refmax=R.choice([0, 1, 2, 5]), bundle=b, images=False, reference_extents=square and R.random() < 0.5)
+        k += 1

@@ -54,6 +54,22 @@ def test_lattice_scenes_on_the_host_build(oracle):
         assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0, (fuzz_scenes.describe(c), res)
 
 
+def test_edge_cameras_and_sizes_on_the_host_build(oracle):
+    """fuzz_scenes.edge_cases: no id and no colour may differ from the oracle's - not even a classified tie."""
+    for c in fuzz_scenes.edge_cases(seed=13, count=80):
+        flat = flat_of(c["bundle"])
+        cam, ocam = fuzz_scenes.cameras(c)
+        prm = make_params(flat, c["bundle"], n_frames=c["n_frames"], refmax=c["refmax"])
+        ref = c["reference_extents"]
+        rgb_p, ids_p, _ = hostsim_render(flat, cam, prm, pipeline=True, reference_extents=ref)
+        rgb, ids, _ = hostsim_render(flat, cam, prm, reference_extents=ref)
+        np.testing.assert_array_equal(ids_p, ids, err_msg=str(fuzz_scenes.describe(c)))
+        np.testing.assert_array_equal(rgb_p, rgb, err_msg=str(fuzz_scenes.describe(c)))
+        orgb, oids, _, tot = oracle_render(oracle_scene(flat, c["bundle"]), ocam, flat, c["bundle"], prm, fixed_extents=not ref)
+        res = compare(rgb, insertion_ids(flat, c["bundle"], ids), orgb, oids)
+        assert res["id_mismatch"] == 0 and res["rgb_bad"] == 0, (fuzz_scenes.describe(c), res)
+
+
 def test_moved_entities_on_the_host_build(oracle):
     """rt_scene_update's path (rt_host.h: rt_scene_move_entities on the library's copy of the flat scene) under random
     moves - far away, by a hair, not at all, onto lattice points, the same entity twice - against the oracle's
